@@ -1,0 +1,438 @@
+/*
+ * pb_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE ONLY; see pb_oracle.h).
+ *
+ * Plain-C restatement of the reference's read-to-reference path.  Parity is
+ * PINNED by tests/test_oracle.py against oracle/_ref (the unmodified reference
+ * compiled from /root/reference) and the reference's own test vectors.
+ */
+#include "pb_oracle.h"
+
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------- */
+/* L0                                                                        */
+/* ------------------------------------------------------------------------- */
+
+int pbo_c2i(int ch)
+{ /* dna_seq.h:21 */
+    return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3;
+}
+
+static const char k_codes[4] = {'A', 'C', 'G', 'T'}; /* dna_seq.h:30 */
+
+uint32_t pbo_encode(const char *text, size_t avail)
+{ /* dna_seq.h:86-96 + t2b :147-159.  Byte k of the word (k=0 is the LSB on the
+     little-endian reference platform) holds bases 4k..4k+3, first base in bits 7:6. */
+    uint32_t w = 0;
+    for (int k = 0; k < 16; ++k) {
+        int ch = (size_t)k < avail ? (unsigned char)text[k] : 0;
+        uint32_t code = (uint32_t)pbo_c2i(ch);
+        int byte = k >> 2, slot = k & 3;
+        w |= code << (8 * byte + 6 - 2 * slot);
+    }
+    return w;
+}
+
+void pbo_decode(uint32_t code, char *out16)
+{ /* dna_seq.h:101-107 + b2t :160-176 */
+    for (int k = 0; k < 16; ++k) {
+        int byte = k >> 2, slot = k & 3;
+        out16[k] = k_codes[(code >> (8 * byte + 6 - 2 * slot)) & 3];
+    }
+}
+
+size_t pbo_text2bin(const char *text, size_t tlen, uint8_t *out, size_t cap)
+{ /* dna_seq.h:113-127 */
+    size_t blen = 4 + (tlen + 3) / 4;
+    if (cap < blen) return 0;
+    uint32_t l32 = (uint32_t)tlen;
+    memcpy(out, &l32, 4); /* native little-endian u32 length */
+    uint8_t *pb = out + 4;
+    for (size_t i = 0; i < tlen; i += 4) {
+        uint8_t b = 0;
+        for (size_t k = 0; k < 4 && i + k < tlen; ++k)
+            b |= (uint8_t)(pbo_c2i((unsigned char)text[i + k]) << (6 - 2 * k));
+        *pb++ = b;
+    }
+    return blen;
+}
+
+size_t pbo_bin2text(const uint8_t *rec, char *out, size_t cap)
+{ /* dna_seq.h:133-145 */
+    uint32_t tlen;
+    memcpy(&tlen, rec, 4);
+    if (cap <= tlen) return 0;
+    const uint8_t *pb = rec + 4;
+    for (size_t i = 0; i < tlen; ++i)
+        out[i] = k_codes[(pb[i >> 2] >> (6 - 2 * (i & 3))) & 3];
+    out[tlen] = '\0';
+    return tlen;
+}
+
+static uint8_t rec_byte(const uint8_t *rec, size_t rec_bytes, size_t off)
+{
+    return off < rec_bytes ? rec[off] : 0;
+}
+
+uint32_t pbo_seed_at(const uint8_t *rec, size_t rec_bytes, int pos, int quirk)
+{ /* dna_seq.h:62-76 */
+    if (quirk && (pos & 3) == 0) {
+        /* Q-S1: *((unsigned*)(pbin + 4 + pos)) -- byte offset pos, not pos>>2 */
+        uint32_t w = 0;
+        for (int k = 0; k < 4; ++k)
+            w |= (uint32_t)rec_byte(rec, rec_bytes, 4 + (size_t)pos + k) << (8 * k);
+        return w;
+    }
+    size_t base = 4 + ((size_t)pos >> 2);
+    unsigned ls = ((unsigned)pos & 3u) << 1, rs = 8 - ls;
+    uint32_t w = 0;
+    for (int k = 0; k < 4; ++k) {
+        uint8_t hi = rec_byte(rec, rec_bytes, base + k);
+        uint8_t lo = rec_byte(rec, rec_bytes, base + k + 1);
+        uint8_t v = (uint8_t)((hi << ls) | (ls ? (lo >> rs) : 0));
+        w |= (uint32_t)v << (8 * k);
+    }
+    return w;
+}
+
+uint32_t pbo_parse_pattern(const char *pat)
+{ /* spaced_seed.cpp:166-180 */
+    char dnapat[17] = "AAAAAAAAAAAAAAAA";
+    size_t len = strlen(pat);
+    if (len > 16) len = 16;
+    for (size_t i = 0; i < len; ++i) dnapat[i] = pat[i] == '1' ? 'T' : 'A';
+    return pbo_encode(dnapat, 16);
+}
+
+/* ------------------------------------------------------------------------- */
+/* L1: seed index.  Observable behaviour of hash_map<unsigned, list<int>>:    */
+/* key equality + per-key insertion order (common.h:54).                      */
+/* ------------------------------------------------------------------------- */
+
+struct pbo_index {
+    size_t n;         /* entries */
+    size_t nkeys;     /* distinct keys */
+    uint32_t *keys;   /* [n] sorted (stable) */
+    int32_t *pos;     /* [n] */
+    uint32_t *ukeys;  /* [nkeys] */
+    size_t *ustart;   /* [nkeys+1] */
+};
+
+static void stable_radix(uint32_t *keys, int32_t *pos, size_t n)
+{
+    uint32_t *k2 = (uint32_t *)malloc(n * sizeof *k2);
+    int32_t *p2 = (int32_t *)malloc(n * sizeof *p2);
+    for (int pass = 0; pass < 4; ++pass) {
+        size_t cnt[257] = {0};
+        int sh = pass * 8;
+        for (size_t i = 0; i < n; ++i) cnt[((keys[i] >> sh) & 255) + 1]++;
+        for (int d = 0; d < 256; ++d) cnt[d + 1] += cnt[d];
+        for (size_t i = 0; i < n; ++i) {
+            size_t o = cnt[(keys[i] >> sh) & 255]++;
+            k2[o] = keys[i];
+            p2[o] = pos[i];
+        }
+        memcpy(keys, k2, n * sizeof *k2);
+        memcpy(pos, p2, n * sizeof *p2);
+    }
+    free(k2);
+    free(p2);
+}
+
+pbo_index *pbo_index_build(const char *ref, size_t len, uint32_t mask, int policy)
+{
+    size_t cap = policy == PBO_POLICY_LOCATOR ? len : 40000;
+    uint32_t *keys = (uint32_t *)malloc((cap + 1) * sizeof *keys);
+    int32_t *pos = (int32_t *)malloc((cap + 1) * sizeof *pos);
+    size_t n = 0;
+    if (policy == PBO_POLICY_LOCATOR) { /* locator.cpp:62-66 */
+        for (size_t i = 0; i < len; ++i) {
+            uint32_t k = pbo_encode(ref + i, len - i) & mask;
+            if (k) { keys[n] = k; pos[n] = (int32_t)i; ++n; }
+        }
+    } else { /* ref_seq.h:291-311 */
+        long L = (long)len, nmax = L - 16;
+        long nhead = nmax < 20000 ? nmax : 20000;
+        for (long i = 0; i < nhead; ++i) {
+            uint32_t k = pbo_encode(ref + i, len - (size_t)i) & mask;
+            if (k) { keys[n] = k; pos[n] = (int32_t)i; ++n; }
+        }
+        long ntail = L - 20000 - 16;
+        if (ntail > 20000) ntail = 20000;
+        for (long i = 0; i < ntail; ++i) {
+            long p = L - 16 - i;
+            uint32_t k = pbo_encode(ref + p, len - (size_t)p) & mask;
+            if (k) { keys[n] = k; pos[n] = (int32_t)(L - i - 16); ++n; }
+        }
+    }
+    stable_radix(keys, pos, n);
+    pbo_index *ix = (pbo_index *)calloc(1, sizeof *ix);
+    ix->n = n;
+    ix->keys = keys;
+    ix->pos = pos;
+    size_t nk = 0;
+    for (size_t i = 0; i < n; ++i)
+        if (i == 0 || keys[i] != keys[i - 1]) ++nk;
+    ix->nkeys = nk;
+    ix->ukeys = (uint32_t *)malloc((nk + 1) * sizeof *ix->ukeys);
+    ix->ustart = (size_t *)malloc((nk + 1) * sizeof *ix->ustart);
+    nk = 0;
+    for (size_t i = 0; i < n; ++i)
+        if (i == 0 || keys[i] != keys[i - 1]) { ix->ukeys[nk] = keys[i]; ix->ustart[nk] = i; ++nk; }
+    ix->ustart[nk] = n;
+    return ix;
+}
+
+void pbo_index_free(pbo_index *ix)
+{
+    if (!ix) return;
+    free(ix->keys); free(ix->pos); free(ix->ukeys); free(ix->ustart); free(ix);
+}
+
+size_t pbo_index_nkeys(const pbo_index *ix) { return ix->nkeys; }
+size_t pbo_index_nentries(const pbo_index *ix) { return ix->n; }
+
+size_t pbo_index_find(const pbo_index *ix, uint32_t key, const int32_t **pos)
+{
+    size_t lo = 0, hi = ix->nkeys;
+    while (lo < hi) {
+        size_t mid = (lo + hi) >> 1;
+        if (ix->ukeys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    if (lo == ix->nkeys || ix->ukeys[lo] != key) { if (pos) *pos = NULL; return 0; }
+    if (pos) *pos = ix->pos + ix->ustart[lo];
+    return ix->ustart[lo + 1] - ix->ustart[lo];
+}
+
+/* ------------------------------------------------------------------------- */
+/* L2: banded DP                                                             */
+/* ------------------------------------------------------------------------- */
+
+typedef struct {
+    int32_t *cost;
+    uint8_t *par;
+    size_t cap;
+} dp_ws;
+
+static int dp_ws_reserve(dp_ws *ws, size_t cells)
+{
+    if (cells <= ws->cap) return 0;
+    free(ws->cost); free(ws->par);
+    ws->cost = (int32_t *)malloc(cells * sizeof(int32_t));
+    ws->par = (uint8_t *)malloc(cells);
+    ws->cap = ws->cost && ws->par ? cells : 0;
+    return ws->cap ? 0 : -1;
+}
+
+static void dp_ws_free(dp_ws *ws) { free(ws->cost); free(ws->par); ws->cost = NULL; ws->par = NULL; ws->cap = 0; }
+
+static int align_ws(dp_ws *ws, const char *a, int a_len, int a_stride,
+                    const char *b, int b_len, int b_stride,
+                    double R, int maxn, int maxm,
+                    pbo_align_out *out, uint8_t *ops, char *vals, size_t cap)
+{
+    int len_a, len_b, max_dst;
+    memset(out, 0, sizeof *out);
+    out->ret = -1;
+    /* seq_aligner.h:94-102 */
+    if (b_len >= a_len) {
+        len_a = a_len;
+        max_dst = 1 + (int)(len_a * R);
+        len_b = b_len < len_a + max_dst ? b_len : len_a + max_dst;
+    } else {
+        len_b = b_len;
+        max_dst = 1 + (int)(len_b * R);
+        len_a = a_len < len_b + max_dst ? a_len : len_b + max_dst;
+    }
+    out->len_a = len_a; out->len_b = len_b; out->max_dst = max_dst;
+    /* seq_aligner.h:104-107, domain per SURVEY Q-D3 */
+    if (len_a >= maxn || max_dst >= maxm) return -1;
+
+    const size_t W = 2 * (size_t)max_dst + 1;
+    if (dp_ws_reserve(ws, ((size_t)len_a + 1) * W)) return -1;
+    int32_t *C = ws->cost;
+    uint8_t *P = ws->par;
+#define IDX(i, j) ((size_t)(i) * W + (size_t)((j) - (i) + max_dst))
+    /* init_cell, seq_aligner.h:139-150 */
+    for (int i = 1; i <= max_dst && i <= len_a; ++i) { C[IDX(i, 0)] = i; P[IDX(i, 0)] = PBO_DELETE; }
+    for (int j = 1; j <= max_dst; ++j) { C[IDX(0, j)] = j; P[IDX(0, j)] = PBO_INSERT; }
+    C[IDX(0, 0)] = 0; P[IDX(0, 0)] = 0;
+
+    /* search, seq_aligner.h:151-190 */
+    int64_t cells = 0;
+    for (int i = 1; i <= len_a; ++i) {
+        char c = a[(ptrdiff_t)(i - 1) * a_stride];
+        int beg = i - max_dst > 1 ? i - max_dst : 1;
+        int end = i + max_dst < len_b ? i + max_dst : len_b;
+        for (int j = beg; j <= end; ++j) {
+            char d = b[(ptrdiff_t)(j - 1) * b_stride];
+            int t, cost = C[IDX(i - 1, j - 1)] + (c != d);
+            int src = PBO_MATCH;
+            if (i - j < max_dst && (t = C[IDX(i, j - 1)] + 1) < cost) { cost = t; src = PBO_INSERT; }
+            if (j - i < max_dst && (t = C[IDX(i - 1, j)] + 1) < cost) { cost = t; src = PBO_DELETE; }
+            C[IDX(i, j)] = cost;
+            P[IDX(i, j)] = (uint8_t)src;
+        }
+        if (end >= beg) cells += end - beg + 1;
+        /* early failure :185 ; cell (i,i) unwritten for i>len_b reads 0 (fresh, Q-D2) */
+        if (i > 10 && i <= len_b && (double)C[IDX(i, i)] > i * R) {
+            out->fail_row = i;
+            out->cells = cells;
+            return -1;
+        }
+    }
+    out->cells = cells;
+
+    /* goal_cell, seq_aligner.h:191-213 */
+    int matlen_a, matlen_b;
+    if (len_a > len_b) {
+        matlen_a = len_b; matlen_b = len_b;
+        int best = C[IDX(len_b, len_b)];
+        for (int i = len_b + 1; i <= len_a; ++i)
+            if (C[IDX(i, len_b)] < best) { best = C[IDX(i, len_b)]; matlen_a = i; }
+    } else {
+        matlen_a = len_a; matlen_b = len_a;
+        int best = C[IDX(len_a, len_a)];
+        for (int j = len_a + 1; j <= len_b; ++j)
+            if (C[IDX(len_a, j)] < best) { best = C[IDX(len_a, j)]; matlen_b = j; }
+    }
+    out->matlen_a = matlen_a; out->matlen_b = matlen_b;
+    out->cost = C[IDX(matlen_a, matlen_b)];
+    out->diag_cost = (a_len <= len_a && a_len <= len_b) ? C[IDX(a_len, a_len)] : 0;
+    /* seq_aligner.h:114 */
+    if ((double)matlen_b < len_b * (1 - R)) return -1;
+
+    /* find_path, seq_aligner.h:214-233 (iterative, then reversed) */
+    size_t ne = 0;
+    {
+        int i = matlen_a, j = matlen_b;
+        for (;;) {
+            int p = P[IDX(i, j)];
+            if (p == 0) break;
+            ++ne;
+            if (p == PBO_MATCH) { --i; --j; }
+            else if (p == PBO_INSERT) { --j; }
+            else { --i; }
+        }
+        out->nedit = (int32_t)ne;
+        if (ops && ne <= cap) {
+            size_t k = ne;
+            i = matlen_a; j = matlen_b;
+            for (;;) {
+                int p = P[IDX(i, j)];
+                if (p == 0) break;
+                --k;
+                ops[k] = (uint8_t)p;
+                if (vals) vals[k] = p == PBO_DELETE ? 0 : b[(ptrdiff_t)(j - 1) * b_stride];
+                if (p == PBO_MATCH) { --i; --j; }
+                else if (p == PBO_INSERT) { --j; }
+                else { --i; }
+            }
+        }
+    }
+#undef IDX
+    out->ret = matlen_b;
+    return matlen_b;
+}
+
+int pbo_align(const char *a, int a_len, int a_stride,
+              const char *b, int b_len, int b_stride,
+              double R, int maxn, int maxm,
+              pbo_align_out *out, uint8_t *ops, char *vals, size_t cap)
+{
+    dp_ws ws = {0, 0, 0};
+    int r = align_ws(&ws, a, a_len, a_stride, b, b_len, b_stride, R, maxn, maxm, out, ops, vals, cap);
+    dp_ws_free(&ws);
+    return r;
+}
+
+/* ------------------------------------------------------------------------- */
+/* locate loop                                                               */
+/* ------------------------------------------------------------------------- */
+
+typedef struct {
+    const pbo_index *ix;
+    const char *ref; size_t ref_len;
+    const char *reads; const int64_t *offs; const int32_t *lens;
+    const int64_t *kept; int64_t k0, k1; /* kept-read range of this thread */
+    uint32_t mask; double R; int ntrial, maxn, maxm;
+    pbo_locate_rec *recs;
+    uint8_t *ops_out; const int64_t *ops_off;
+} locate_job;
+
+static void *locate_thread(void *arg)
+{
+    locate_job *jb = (locate_job *)arg;
+    dp_ws ws = {0, 0, 0};
+    uint8_t *ops = NULL; size_t ops_cap = 0;
+    for (int64_t k = jb->k0; k < jb->k1; ++k) {
+        int64_t r = jb->kept[k];
+        const char *seq = jb->reads + jb->offs[r];
+        int len = jb->lens[r];
+        pbo_locate_rec *rec = &jb->recs[k];
+        memset(rec, 0, sizeof *rec);
+        rec->nseq = (int32_t)k;
+        if (jb->ops_out) {
+            size_t need = (size_t)len * 2 + (size_t)jb->maxm + 16;
+            if (need > ops_cap) { free(ops); ops = (uint8_t *)malloc(need); ops_cap = need; }
+        }
+        int found = 0;
+        for (int j = 0; j < jb->ntrial && !found; ++j) { /* locator.cpp:74 */
+            uint32_t key = pbo_encode(seq + j, (size_t)(len - j) + 1 /* NUL terminator readable */) & jb->mask;
+            const int32_t *plist;
+            size_t cnt = pbo_index_find(jb->ix, key, &plist);
+            for (size_t c = 0; c < cnt; ++c) { /* locator.cpp:79 */
+                int pos = plist[c];
+                pbo_align_out ao;
+                rec->ncand++;
+                int ret = align_ws(&ws, seq + j, len - j, 1, jb->ref + pos, (int)(jb->ref_len - (size_t)pos), 1,
+                                   jb->R, jb->maxn, jb->maxm, &ao, jb->ops_out ? ops : NULL, NULL, ops_cap);
+                rec->cells += ao.cells;
+                if (ret > 0) { /* locator.cpp:82-88 */
+                    found = 1;
+                    rec->found = 1; rec->j = j; rec->pos = pos; rec->cost = ao.cost;
+                    rec->seg_len = len - j; rec->diag_cost = ao.diag_cost;
+                    rec->matlen_a = ao.matlen_a; rec->matlen_b = ao.matlen_b; rec->nedit = ao.nedit;
+                    if (jb->ops_out) memcpy(jb->ops_out + jb->ops_off[k], ops, (size_t)ao.nedit);
+                    break;
+                }
+            }
+        }
+    }
+    free(ops);
+    dp_ws_free(&ws);
+    return NULL;
+}
+
+int64_t pbo_locate(const pbo_index *ix, const char *ref, size_t ref_len,
+                   const char *reads, const int64_t *offs, const int32_t *lens,
+                   int64_t nreads, uint32_t mask, double R, int ntrial, int minlen,
+                   int maxn, int maxm, int nthreads, pbo_locate_rec *recs,
+                   uint8_t *ops_out, const int64_t *ops_off)
+{
+    int64_t *kept = (int64_t *)malloc((size_t)(nreads + 1) * sizeof *kept);
+    int64_t nk = 0;
+    for (int64_t r = 0; r < nreads; ++r)
+        if (lens[r] >= minlen) kept[nk++] = r; /* locator.cpp:72, Q-L1 */
+    if (nthreads < 1) nthreads = 1;
+    if ((int64_t)nthreads > nk) nthreads = nk > 0 ? (int)nk : 1;
+    locate_job *jobs = (locate_job *)calloc((size_t)nthreads, sizeof *jobs);
+    pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof *th);
+    /* interleaved-contiguous split balanced by count (reads are iid in the benchmarks) */
+    for (int t = 0; t < nthreads; ++t) {
+        locate_job *jb = &jobs[t];
+        jb->ix = ix; jb->ref = ref; jb->ref_len = ref_len;
+        jb->reads = reads; jb->offs = offs; jb->lens = lens; jb->kept = kept;
+        jb->k0 = nk * t / nthreads; jb->k1 = nk * (t + 1) / nthreads;
+        jb->mask = mask; jb->R = R; jb->ntrial = ntrial; jb->maxn = maxn; jb->maxm = maxm;
+        jb->recs = recs; jb->ops_out = ops_out; jb->ops_off = ops_off;
+        if (nthreads == 1) locate_thread(jb);
+        else pthread_create(&th[t], NULL, locate_thread, jb);
+    }
+    if (nthreads > 1)
+        for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+    free(jobs); free(th); free(kept);
+    return nk;
+}
