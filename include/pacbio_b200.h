@@ -1,0 +1,226 @@
+/*
+ * pacbio_b200.h -- C ABI of the B200-native read-to-reference hot path.
+ *
+ * Drop-in boundary for vmingchen/PacBioAssembly's spaced-seed lookup + banded-DP verify path.
+ * The reference has no FFI layer; its boundary is the header-level class API.  Each entry point
+ * below names the reference interface it replaces (file:line under the reference's src/).  The C++
+ * classes in pacbioassembly_b200/host/ (dna_seq, seq_accessor, seq_aligner<>, hash_table view, the
+ * locator driver) are thin wrappers over exactly these calls -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; no CUDA or torch types appear in any signature.
+ *   - every call returns PB_OK (0) or a negative pb_status; pb_last_error() gives the text.
+ *   - all work runs on the GPU (sm_100a).  There is NO CPU fallback: without a device every compute
+ *     call fails with PB_ERR_NO_DEVICE.
+ *   - calls are synchronous on return; internally they are ordered on the context's CUDA stream.
+ *   - one context per host thread per GPU (the reference is single-threaded with global state).
+ *   - host buffers are owned by the caller; handles are owned by the library until *_free.
+ */
+#ifndef PACBIO_B200_H
+#define PACBIO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PB_API __attribute__((visibility("default")))
+#else
+#define PB_API
+#endif
+
+typedef enum {
+    PB_OK = 0,
+    PB_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the product path never falls back to the CPU */
+    PB_ERR_CUDA = -2,        /* a CUDA call failed; see pb_last_error */
+    PB_ERR_ARG = -3,         /* invalid argument */
+    PB_ERR_NOMEM = -4,       /* device or host allocation failed */
+    PB_ERR_DOMAIN = -5,      /* outside the supported domain (e.g. band half-width >= PB_MAX_BAND) */
+    PB_ERR_ALPHABET = -6     /* a sequence holds bytes outside {A,C,G,T} and the requested path cannot take them */
+} pb_status;
+
+/* widest supported band half-width (max_dst); the reference's MAX_DIFF_LEN is 6000 (common.h:35) */
+#define PB_MAX_BAND 8191
+
+typedef struct pb_ctx pb_ctx;
+typedef struct pb_seqset pb_seqset; /* device-resident sequences: 2-bit packed (dna_seq.h:113-127 layout) + bit planes */
+typedef struct pb_index pb_index;   /* device-resident seed index: replaces hash_table (common.h:54) */
+
+/* edit operations, seq_aligner.h:32-36 */
+enum { PB_MATCH = 1, PB_INSERT = 2, PB_DELETE = 3 };
+
+/* seed-index build policy */
+enum {
+    PB_POLICY_LOCATOR = 0, /* locator.cpp:62-66 : every position 0..len-1, tail reads past the end as code 3 */
+    PB_POLICY_REFSEQ = 1   /* ref_seq.h:291-311 : head min(len-16,20000) ascending, then tail descending */
+};
+
+/* ---- context ------------------------------------------------------------------------------- */
+
+PB_API int pb_abi_version(void);
+PB_API int pb_device_count(void); /* 0 when no usable device; never an error */
+PB_API int pb_ctx_create(int device, pb_ctx **out);
+PB_API void pb_ctx_destroy(pb_ctx *ctx);
+/* text of the last error raised through ctx (or through pb_ctx_create when ctx is NULL) */
+PB_API const char *pb_last_error(const pb_ctx *ctx);
+/* the context's cudaStream_t as an opaque pointer, so callers can bracket calls with their own events */
+PB_API void *pb_ctx_stream(pb_ctx *ctx);
+/* number of kernels launched by this context since creation (bench.py reports the per-step difference) */
+PB_API int64_t pb_ctx_launch_count(const pb_ctx *ctx);
+/* upper bound on device scratch (bytes) the aligner may claim for parent matrices; 0 = default (40% of free) */
+PB_API int pb_ctx_set_scratch_limit(pb_ctx *ctx, size_t bytes);
+
+/* named device timings (milliseconds, CUDA events on the context stream) of the most recent call */
+enum {
+    PB_T_H2D = 0, PB_T_INGEST, PB_T_SEED, PB_T_INDEX, PB_T_PROBE, PB_T_PREFILTER, PB_T_ALIGN, PB_T_D2H, PB_T_TOTAL,
+    PB_T_COUNT
+};
+PB_API int pb_ctx_timings(const pb_ctx *ctx, float *ms /* [PB_T_COUNT] */);
+
+/* ---- L0: sequence representation (dna_seq.h) -------------------------------------------------- */
+
+/* dna_seq::encode (dna_seq.h:86-96) for n windows: out[i] = seed word of text[off[i] .. off[i]+16), where bytes
+ * at or beyond text_len read as NUL (-> code 3), which is what locator.cpp:63 sees at the contig tail. */
+PB_API int pb_encode_batch(pb_ctx *ctx, const char *text, size_t text_len, const int64_t *off, int64_t n, uint32_t *out);
+/* dna_seq::decode (dna_seq.h:101-107): out16[16*i .. 16*i+16) */
+PB_API int pb_decode_batch(pb_ctx *ctx, const uint32_t *codes, int64_t n, char *out16);
+/* dna_seq::text2bin (dna_seq.h:113-127): record = u32 length + ceil(tlen/4) bytes, 4 bases per byte, first base in
+ * bits 7:6.  Returns the record length through *written; PB_ERR_ARG if cap is too small (the reference asserts). */
+PB_API int pb_text2bin(pb_ctx *ctx, const char *text, size_t tlen, uint8_t *out, size_t cap, size_t *written);
+/* dna_seq::bin2text (dna_seq.h:133-145); writes tlen chars + NUL; needs cap > tlen */
+PB_API int pb_bin2text(pb_ctx *ctx, const uint8_t *rec, char *out, size_t cap, size_t *tlen);
+/* dna_seq::seed_at (dna_seq.h:62-76) for n positions of one packed record.  Canonical value = encode(text+pos);
+ * quirk != 0 reproduces the reference's pos%4==0 branch, which reads the word at byte offset pos (SURVEY Q-S1);
+ * bytes beyond rec_bytes read as 0. */
+PB_API int pb_seed_at_batch(pb_ctx *ctx, const uint8_t *rec, size_t rec_bytes, const int32_t *pos, int64_t n, int quirk,
+                     uint32_t *out);
+/* parse_pattern (spaced_seed.cpp:166-180; locator.cpp:51-54): '1' -> care.  Pure string -> mask, no device needed. */
+PB_API uint32_t pb_parse_pattern(const char *pattern);
+
+/* Upload n sequences.  Sequence i has len[i] elements; element k is text[off[i] + k*stride[i]] (stride +1 or -1:
+ * seq_accessor forward / backward views, dna_seq.h:185-233).  stride == NULL means all +1. */
+PB_API int pb_seqset_from_text(pb_ctx *ctx, const char *text, const int64_t *off, const int32_t *len, const int32_t *stride,
+                        int64_t n, pb_seqset **out);
+/* Same, but `d_text` is a DEVICE pointer to the text blob of text_bytes bytes (inputs already resident in HBM);
+ * off/len/stride are host arrays. */
+PB_API int pb_seqset_from_device_text(pb_ctx *ctx, const void *d_text, size_t text_bytes, const int64_t *off,
+                               const int32_t *len, const int32_t *stride, int64_t n, pb_seqset **out);
+/* Walk a .bin image (binary_test.cpp:55-63 writer, spaced_seed.cpp:330-342 reader): records back to back, keep those
+ * with min_excl < length < max_excl (the reference keeps 500 < len < 20000).  ids = rank among kept. */
+PB_API int pb_seqset_from_bin(pb_ctx *ctx, const uint8_t *bin, size_t nbytes, int min_excl, int max_excl, pb_seqset **out);
+PB_API void pb_seqset_free(pb_seqset *s);
+PB_API int64_t pb_seqset_count(const pb_seqset *s);
+PB_API int32_t pb_seqset_length(const pb_seqset *s, int64_t i);
+/* decode sequence i back to text (bin2text semantics: non-ACG bytes come back as 'T'); needs cap > length */
+PB_API int pb_seqset_text(pb_ctx *ctx, const pb_seqset *s, int64_t i, char *out, size_t cap);
+/* the packed body (4 bases/byte, MSB first) of sequence i, ceil(len/4) bytes */
+PB_API int pb_seqset_packed(pb_ctx *ctx, const pb_seqset *s, int64_t i, uint8_t *out, size_t cap);
+
+/* ---- L1: seeds and the seed index ------------------------------------------------------------ */
+
+/* K1 bulk: keys[p] = encode(text+p) & mask for every position p in [0,len) of sequence i (positions within 15 of the
+ * end see code 3 past the end, SURVEY Q-S3).  keys is a host buffer of len entries. */
+PB_API int pb_seed_extract(pb_ctx *ctx, const pb_seqset *s, int64_t i, uint32_t mask, uint32_t *keys);
+/* K1 bulk over the whole set, keys left on the device (bandwidth measurement).  Returns the number of keys produced
+ * through *nkeys and the kernel time in ms through *kernel_ms (either may be NULL). */
+PB_API int pb_seed_extract_all_device(pb_ctx *ctx, const pb_seqset *s, uint32_t mask, int64_t *nkeys, float *kernel_ms);
+
+/* key = encode(ref+i) & mask; if (key) map[key].push_back(i)   (locator.cpp:62-66 / ref_seq.h:291-311) */
+PB_API int pb_index_build(pb_ctx *ctx, const pb_seqset *ref, int64_t seq, uint32_t mask, int policy, pb_index **out);
+PB_API void pb_index_free(pb_index *ix);
+PB_API int64_t pb_index_nkeys(const pb_index *ix);    /* hash_table::size() */
+PB_API int64_t pb_index_nentries(const pb_index *ix); /* positions stored; get_seedmap's return value is nhead+ntail, see pb_index_nscanned */
+PB_API int64_t pb_index_nscanned(const pb_index *ix); /* positions visited (ref_seq.h:310 return value under PB_POLICY_REFSEQ) */
+PB_API uint32_t pb_index_mask(const pb_index *ix);
+/* hash_table::find (locator.cpp:76, spaced_seed.cpp:265) for n keys at once.  Positions of key i, in the
+ * reference's list order, are written to pos[pos_off[i] .. pos_off[i] + min(count[i], cap_each)); count[i]
+ * is the full list length (0 == end()).  pos/pos_off may be NULL to get counts only. */
+PB_API int pb_index_find_batch(pb_ctx *ctx, const pb_index *ix, const uint32_t *keys, int64_t n, int64_t *count, int32_t *pos,
+                        const int64_t *pos_off, int64_t cap_each);
+
+/* ---- L2: banded edit-distance aligner (seq_aligner.h) ---------------------------------------- */
+
+/* Result of one seq_aligner<MAXN,MAXM>::align call (seq_aligner.h:73-81,92-125), fresh-state semantics
+ * (cells the call never writes read as 0, SURVEY Q-D2). */
+typedef struct {
+    int32_t ret;               /* matlen_b, or -1 */
+    int32_t len_a, len_b, max_dst;
+    int32_t matlen_a, matlen_b;
+    int32_t cost;              /* final_cost() */
+    int32_t diag_cost;         /* get_cost(|a|,|a|) if that cell was computed, else 0 (locator.cpp:86) */
+    int32_t nedit;
+    int32_t fail_row;          /* row at which the early-failure test (seq_aligner.h:185) fired, else 0 */
+    int64_t cells;             /* DP cells of the reference's recurrence covered by this call */
+} pb_align_out;
+
+/* n independent align(seg_a, seg_b) calls with ratio R and template limits (maxn, maxm).
+ * Sequences are given as accessor views like pb_seqset_from_text.  ops (may be NULL) receives the forward-ordered
+ * edit operations of pair i at ops[ops_off[i] ..), nedit[i] bytes (PB_MATCH/INSERT/DELETE); the caller sizes each
+ * slot with at least a_len+b_len+1 bytes.  edit.val (seq_aligner.h:42) is seg_b's element under each MATCH/INSERT and is
+ * filled in by the C++ wrapper from the caller's own text. */
+PB_API int pb_align_batch(pb_ctx *ctx, const char *a_text, const int64_t *a_off, const int32_t *a_len, const int32_t *a_stride,
+                   const char *b_text, const int64_t *b_off, const int32_t *b_len, const int32_t *b_stride, int64_t n,
+                   double R, int maxn, int maxm, pb_align_out *out, uint8_t *ops, const int64_t *ops_off);
+
+/* ---- the locate loop (locator.cpp:70-92) ----------------------------------------------------- */
+
+typedef struct {
+    int32_t nseq;      /* rank among kept reads (len >= minlen), column 1 */
+    int32_t found;     /* 0/1 */
+    int32_t j;         /* read offset of the winning seed */
+    int32_t pos;       /* contig position, column 2 */
+    int32_t cost;      /* final_cost(), column 3 */
+    int32_t seg_len;   /* len - j, column 4 */
+    int32_t diag_cost; /* get_cost(len-j,len-j), column 5 */
+    int32_t matlen_a, matlen_b, nedit;
+    int32_t ncand;     /* align() calls the reference would have made for this read */
+    int32_t _pad;
+    int64_t cells;     /* DP cells the reference would have evaluated for this read */
+} pb_locate_rec;
+
+typedef struct {
+    double R;          /* 0.15 in locator.cpp:68 */
+    int32_t ntrial;    /* 50, locator.cpp:74 */
+    int32_t minlen;    /* 500, locator.cpp:72 */
+    int32_t maxn;      /* 40000, locator.cpp:23 */
+    int32_t maxm;      /* 6000, locator.cpp:24 */
+    int32_t want_ops;  /* also produce the winning transcripts */
+    int32_t reserved;
+} pb_locate_params;
+
+PB_API void pb_locate_default_params(pb_locate_params *p);
+
+/* For every read with len >= minlen: j = 0..ntrial-1 until found; key = encode(read+j) & mask; candidates in
+ * list order; first align(read[j:], ref[pos:]) > 0 wins.  recs has one entry per kept read, in input order;
+ * *nkept receives their number.  ops/ops_off as in pb_align_batch, indexed by kept rank, slots of at least
+ * 2*len + maxm + 16 bytes (ignored unless want_ops). */
+PB_API int pb_locate_batch(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const char *reads,
+                    const int64_t *off, const int32_t *len, int64_t nreads, const pb_locate_params *prm,
+                    pb_locate_rec *recs, int64_t *nkept, uint8_t *ops, const int64_t *ops_off);
+
+/* Device-resident variant used to time the path without host<->device copies: reads already uploaded as a seqset;
+ * results stay on the device until pb_locate_fetch.  ops_off (host array indexed by kept rank, may be NULL) fixes the
+ * transcript layout; with NULL the library packs slots of 2*len + maxm + 16 bytes (rounded up to 16) back to back and
+ * pb_locate_job_ops_layout reports them.  pb_locate_fetch copies the records and, if ops != NULL, the byte range
+ * [0, extent) of the transcript buffer straight into `ops` (one copy; bytes between slots are overwritten too). */
+typedef struct pb_locate_job pb_locate_job;
+PB_API int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const pb_seqset *reads,
+                  const pb_locate_params *prm, const int64_t *ops_off, pb_locate_job **job);
+PB_API int64_t pb_locate_job_nkept(const pb_locate_job *job);
+PB_API int64_t pb_locate_job_ncand(const pb_locate_job *job); /* seed hits (candidates) gathered for the batch */
+/* after pb_locate_fetch: out[0] = candidates gathered (K2), out[1] = alignments the banded aligner (K3) ran,
+ * out[2] = DP cells K3 computed (reference cell count of those alignments), out[3] = 0 */
+PB_API int pb_locate_job_stats(const pb_locate_job *job, int64_t *out /* [4] */);
+PB_API int pb_locate_job_ops_layout(const pb_locate_job *job, int64_t *ops_off /* [nkept] or NULL */, int64_t *extent);
+PB_API int pb_locate_fetch(pb_ctx *ctx, const pb_locate_job *job, pb_locate_rec *recs, uint8_t *ops);
+PB_API void pb_locate_job_free(pb_locate_job *job);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PACBIO_B200_H */

@@ -210,18 +210,39 @@ static void *locate_thread(void *arg)
     return NULL;
 }
 
-/* Same contract as pbo_locate (oracle/pb_oracle.h) with the locator's seq_aligner<40000,6000>. */
-int64_t pbref_locate(const char *ref, long ref_len, const char *reads, const int64_t *offs, const int32_t *lens,
-                     int64_t nreads, unsigned mask, double R, int ntrial, int minlen, int nthreads,
-                     locate_rec *recs, uint8_t *ops_out, const int64_t *ops_off)
+/* The locator's setup (locator.cpp:57-66): contig copy + seed map.  Built once, reused by pbref_locator_run, the way
+ * the reference program builds its map once and then streams reads. */
+struct locator_state { char *contig; long len; hash_table *map; unsigned mask; };
+
+void *pbref_locator_open(const char *ref, long ref_len, unsigned mask)
 {
-    char *contig = (char *)calloc((size_t)ref_len + 32, 1);
-    memcpy(contig, ref, (size_t)ref_len);
-    hash_table *map = new hash_table(1 << 23); /* locator.cpp:28 */
-    for (long i = 0; i < ref_len; ++i) {       /* locator.cpp:62-66 */
-        int sd = dna_seq::encode(contig + i);
-        if (sd & mask) (*map)[sd & mask].push_back((int)i);
+    locator_state *st = new locator_state();
+    st->contig = (char *)calloc((size_t)ref_len + 32, 1);
+    memcpy(st->contig, ref, (size_t)ref_len);
+    st->len = ref_len;
+    st->mask = mask;
+    st->map = new hash_table(1 << 23); /* locator.cpp:28 */
+    for (long i = 0; i < ref_len; ++i) { /* locator.cpp:62-66 */
+        int sd = dna_seq::encode(st->contig + i);
+        if (sd & mask) (*st->map)[sd & mask].push_back((int)i);
     }
+    return st;
+}
+
+void pbref_locator_close(void *h)
+{
+    locator_state *st = (locator_state *)h;
+    if (!st) return;
+    free(st->contig);
+    delete st->map;
+    delete st;
+}
+
+/* Same contract as pbo_locate (oracle/pb_oracle.h) with the locator's seq_aligner<40000,6000>. */
+int64_t pbref_locator_run(void *h, const char *reads, const int64_t *offs, const int32_t *lens, int64_t nreads, double R,
+                          int ntrial, int minlen, int nthreads, locate_rec *recs, uint8_t *ops_out, const int64_t *ops_off)
+{
+    locator_state *st = (locator_state *)h;
     int64_t *kept = (int64_t *)malloc((size_t)(nreads + 1) * sizeof *kept);
     int64_t nk = 0;
     for (int64_t r = 0; r < nreads; ++r)
@@ -232,18 +253,27 @@ int64_t pbref_locate(const char *ref, long ref_len, const char *reads, const int
     pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof *th);
     for (int t = 0; t < nthreads; ++t) {
         locate_job *jb = &jobs[t];
-        jb->map = map; jb->contig = contig; jb->contig_len = ref_len;
+        jb->map = st->map; jb->contig = st->contig; jb->contig_len = st->len;
         jb->reads = reads; jb->offs = offs; jb->lens = lens; jb->kept = kept;
         jb->k0 = nk * t / nthreads; jb->k1 = nk * (t + 1) / nthreads;
-        jb->mask = mask; jb->R = R; jb->ntrial = ntrial;
+        jb->mask = st->mask; jb->R = R; jb->ntrial = ntrial;
         jb->recs = recs; jb->ops_out = ops_out; jb->ops_off = ops_off;
         if (nthreads == 1) locate_thread(jb);
         else pthread_create(&th[t], NULL, locate_thread, jb);
     }
     if (nthreads > 1)
         for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
-    free(jobs); free(th); free(kept); free(contig);
-    delete map;
+    free(jobs); free(th); free(kept);
+    return nk;
+}
+
+int64_t pbref_locate(const char *ref, long ref_len, const char *reads, const int64_t *offs, const int32_t *lens,
+                     int64_t nreads, unsigned mask, double R, int ntrial, int minlen, int nthreads,
+                     locate_rec *recs, uint8_t *ops_out, const int64_t *ops_off)
+{
+    void *h = pbref_locator_open(ref, ref_len, mask);
+    int64_t nk = pbref_locator_run(h, reads, offs, lens, nreads, R, ntrial, minlen, nthreads, recs, ops_out, ops_off);
+    pbref_locator_close(h);
     return nk;
 }
 

@@ -1,0 +1,467 @@
+"""ctypes binding of the C ABI in include/pacbio_b200.h (Python host side of the drop-in boundary).
+
+Every method maps 1:1 onto an entry point of libpacbio_b200.so; there is no Python or CPU implementation
+behind any of them.  If the shared library is missing, or no sm_100a device is visible, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpacbio_b200.so")
+
+MATCH, INSERT, DELETE = 1, 2, 3
+POLICY_LOCATOR, POLICY_REFSEQ = 0, 1
+T_NAMES = ("h2d", "ingest", "seed", "index", "probe", "prefilter", "align", "d2h", "total")
+
+ALIGN_DTYPE = np.dtype([(n, np.int32) for n in ("ret", "len_a", "len_b", "max_dst", "matlen_a", "matlen_b", "cost",
+                                                 "diag_cost", "nedit", "fail_row")] + [("cells", np.int64)])
+LOCATE_DTYPE = np.dtype([(n, np.int32) for n in ("nseq", "found", "j", "pos", "cost", "seg_len", "diag_cost", "matlen_a",
+                                                  "matlen_b", "nedit", "ncand", "_pad")] + [("cells", np.int64)])
+assert ALIGN_DTYPE.itemsize == 48 and LOCATE_DTYPE.itemsize == 56
+
+
+class LocateParams(C.Structure):
+    _fields_ = [("R", C.c_double), ("ntrial", C.c_int32), ("minlen", C.c_int32), ("maxn", C.c_int32),
+                ("maxm", C.c_int32), ("want_ops", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"pacbio_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libpacbio_b200.so; raises if it has not been built (no fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -m pacbioassembly_b200.build` "
+                          "(the product path has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32, u32, sz = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_size_t
+    P = C.POINTER
+    sig = {
+        "pb_abi_version": (C.c_int, []),
+        "pb_device_count": (C.c_int, []),
+        "pb_ctx_create": (C.c_int, [C.c_int, P(vp)]),
+        "pb_ctx_destroy": (None, [vp]),
+        "pb_last_error": (C.c_char_p, [vp]),
+        "pb_ctx_stream": (vp, [vp]),
+        "pb_ctx_launch_count": (i64, [vp]),
+        "pb_ctx_set_scratch_limit": (C.c_int, [vp, sz]),
+        "pb_ctx_timings": (C.c_int, [vp, vp]),
+        "pb_encode_batch": (C.c_int, [vp, vp, sz, vp, i64, vp]),
+        "pb_decode_batch": (C.c_int, [vp, vp, i64, vp]),
+        "pb_text2bin": (C.c_int, [vp, vp, sz, vp, sz, P(sz)]),
+        "pb_bin2text": (C.c_int, [vp, vp, vp, sz, P(sz)]),
+        "pb_seed_at_batch": (C.c_int, [vp, vp, sz, vp, i64, C.c_int, vp]),
+        "pb_parse_pattern": (u32, [C.c_char_p]),
+        "pb_seqset_from_text": (C.c_int, [vp, vp, vp, vp, vp, i64, P(vp)]),
+        "pb_seqset_from_device_text": (C.c_int, [vp, vp, sz, vp, vp, vp, i64, P(vp)]),
+        "pb_seqset_from_bin": (C.c_int, [vp, vp, sz, C.c_int, C.c_int, P(vp)]),
+        "pb_seqset_free": (None, [vp]),
+        "pb_seqset_count": (i64, [vp]),
+        "pb_seqset_length": (i32, [vp, i64]),
+        "pb_seqset_text": (C.c_int, [vp, vp, i64, vp, sz]),
+        "pb_seqset_packed": (C.c_int, [vp, vp, i64, vp, sz]),
+        "pb_seed_extract": (C.c_int, [vp, vp, i64, u32, vp]),
+        "pb_seed_extract_all_device": (C.c_int, [vp, vp, u32, P(i64), P(C.c_float)]),
+        "pb_index_build": (C.c_int, [vp, vp, i64, u32, C.c_int, P(vp)]),
+        "pb_index_free": (None, [vp]),
+        "pb_index_nkeys": (i64, [vp]),
+        "pb_index_nentries": (i64, [vp]),
+        "pb_index_nscanned": (i64, [vp]),
+        "pb_index_mask": (u32, [vp]),
+        "pb_index_find_batch": (C.c_int, [vp, vp, vp, i64, vp, vp, vp, i64]),
+        "pb_align_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, C.c_double, C.c_int, C.c_int, vp, vp, vp]),
+        "pb_locate_default_params": (None, [P(LocateParams)]),
+        "pb_locate_batch": (C.c_int, [vp, vp, vp, i64, vp, vp, vp, i64, P(LocateParams), vp, P(i64), vp, vp]),
+        "pb_locate_run": (C.c_int, [vp, vp, vp, i64, vp, P(LocateParams), vp, P(vp)]),
+        "pb_locate_job_nkept": (i64, [vp]),
+        "pb_locate_job_ncand": (i64, [vp]),
+        "pb_locate_job_ops_layout": (C.c_int, [vp, vp, P(i64)]),
+        "pb_locate_job_stats": (C.c_int, [vp, vp]),
+        "pb_locate_fetch": (C.c_int, [vp, vp, vp, vp]),
+        "pb_locate_job_free": (None, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._declared = sorted(sig)
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _u8(x) -> np.ndarray:
+    if isinstance(x, (bytes, bytearray)):
+        return np.frombuffer(bytes(x), dtype=np.uint8)
+    return np.ascontiguousarray(x, dtype=np.uint8)
+
+
+def parse_pattern(pattern: str | bytes) -> int:
+    """parse_pattern, spaced_seed.cpp:166-180 (pure string -> mask)."""
+    if isinstance(pattern, str):
+        pattern = pattern.encode()
+    return int(lib().pb_parse_pattern(pattern))
+
+
+def default_locate_params(**kw) -> LocateParams:
+    p = LocateParams()
+    lib().pb_locate_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class Context:
+    """One per process per GPU (pb_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.pb_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise PbError(rc, (self._L.pb_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.pb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise PbError(rc, (self._L.pb_last_error(self.h) or b"").decode())
+
+    @property
+    def stream(self) -> int:
+        return int(self._L.pb_ctx_stream(self.h) or 0)
+
+    @property
+    def launches(self) -> int:
+        return int(self._L.pb_ctx_launch_count(self.h))
+
+    def set_scratch_limit(self, nbytes: int):
+        self.check(self._L.pb_ctx_set_scratch_limit(self.h, nbytes))
+
+    def timings(self) -> dict:
+        ms = (C.c_float * len(T_NAMES))()
+        self.check(self._L.pb_ctx_timings(self.h, ms))
+        return {n: float(ms[i]) for i, n in enumerate(T_NAMES)}
+
+    # ---- dna_seq statics -------------------------------------------------------------------
+    def encode(self, text, offsets=None) -> np.ndarray:
+        t = _u8(text)
+        off = np.ascontiguousarray([0] if offsets is None else offsets, dtype=np.int64)
+        out = np.zeros(len(off), dtype=np.uint32)
+        self.check(self._L.pb_encode_batch(self.h, _ptr(t), len(t), _ptr(off), len(off), _ptr(out)))
+        return out
+
+    def decode(self, codes) -> list[bytes]:
+        c = np.ascontiguousarray(codes, dtype=np.uint32).reshape(-1)
+        out = np.zeros(16 * len(c), dtype=np.uint8)
+        self.check(self._L.pb_decode_batch(self.h, _ptr(c), len(c), _ptr(out)))
+        return [out[16 * i:16 * i + 16].tobytes() for i in range(len(c))]
+
+    def text2bin(self, text: bytes, cap: int | None = None) -> bytes:
+        t = _u8(text)
+        need = 4 + (len(t) + 3) // 4
+        cap = need if cap is None else cap
+        out = np.zeros(max(cap, 1), dtype=np.uint8)
+        w = C.c_size_t(0)
+        self.check(self._L.pb_text2bin(self.h, _ptr(t) if len(t) else None, len(t), _ptr(out), cap, C.byref(w)))
+        return out[: w.value].tobytes()
+
+    def bin2text(self, rec: bytes, cap: int | None = None) -> bytes:
+        r = _u8(rec)
+        n = int.from_bytes(bytes(r[:4]), "little")
+        cap = n + 1 if cap is None else cap
+        out = np.zeros(max(cap, 1), dtype=np.uint8)
+        tl = C.c_size_t(0)
+        self.check(self._L.pb_bin2text(self.h, _ptr(r), _ptr(out), cap, C.byref(tl)))
+        return out[: tl.value].tobytes()
+
+    def seed_at(self, rec: bytes, positions, quirk: bool = False) -> np.ndarray:
+        r = _u8(rec)
+        pos = np.ascontiguousarray(positions, dtype=np.int32).reshape(-1)
+        out = np.zeros(len(pos), dtype=np.uint32)
+        self.check(self._L.pb_seed_at_batch(self.h, _ptr(r), len(r), _ptr(pos), len(pos), int(quirk), _ptr(out)))
+        return out
+
+    # ---- sequences ------------------------------------------------------------------------------
+    def seqset(self, text, offs, lens, strides=None) -> "SeqSet":
+        t = _u8(text)
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        st = None if strides is None else np.ascontiguousarray(strides, dtype=np.int32)
+        h = C.c_void_p()
+        self.check(self._L.pb_seqset_from_text(self.h, _ptr(t), _ptr(offs), _ptr(lens), _ptr(st), len(lens), C.byref(h)))
+        return SeqSet(self, h)
+
+    def seqset_one(self, text) -> "SeqSet":
+        t = _u8(text)
+        return self.seqset(t, [0], [len(t)])
+
+    def seqset_from_device(self, dptr: int, nbytes: int, offs, lens, strides=None) -> "SeqSet":
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        st = None if strides is None else np.ascontiguousarray(strides, dtype=np.int32)
+        h = C.c_void_p()
+        self.check(self._L.pb_seqset_from_device_text(self.h, dptr, nbytes, _ptr(offs), _ptr(lens), _ptr(st), len(lens),
+                                                      C.byref(h)))
+        return SeqSet(self, h)
+
+    def seqset_from_bin(self, image: bytes, min_excl: int = 500, max_excl: int = 20000) -> "SeqSet":
+        b = _u8(image)
+        h = C.c_void_p()
+        self.check(self._L.pb_seqset_from_bin(self.h, _ptr(b), len(b), min_excl, max_excl, C.byref(h)))
+        return SeqSet(self, h)
+
+    # ---- index ---------------------------------------------------------------------------------
+    def index(self, ref: "SeqSet", mask: int, policy: int = POLICY_LOCATOR, seq: int = 0) -> "Index":
+        h = C.c_void_p()
+        self.check(self._L.pb_index_build(self.h, ref.h, seq, mask, policy, C.byref(h)))
+        return Index(self, h, ref, seq)
+
+    # ---- aligner -------------------------------------------------------------------------------
+    def align_batch(self, a_text, a_off, a_len, b_text, b_off, b_len, R: float = 0.3, maxn: int = 26000, maxm: int = 6000,
+                    a_stride=None, b_stride=None, want_ops: bool = True):
+        """n seq_aligner::align calls; returns (records[ALIGN_DTYPE], list of op arrays or None)."""
+        at, bt = _u8(a_text), _u8(b_text)
+        a_off = np.ascontiguousarray(a_off, dtype=np.int64)
+        b_off = np.ascontiguousarray(b_off, dtype=np.int64)
+        a_len = np.ascontiguousarray(a_len, dtype=np.int32)
+        b_len = np.ascontiguousarray(b_len, dtype=np.int32)
+        ast = None if a_stride is None else np.ascontiguousarray(a_stride, dtype=np.int32)
+        bst = None if b_stride is None else np.ascontiguousarray(b_stride, dtype=np.int32)
+        n = len(a_len)
+        out = np.zeros(n, dtype=ALIGN_DTYPE)
+        ops = ops_off = None
+        if want_ops:
+            slots = (a_len.astype(np.int64) + b_len + 1 + 15) & ~15
+            ops_off = np.zeros(n, dtype=np.int64)
+            if n:
+                np.cumsum(slots[:-1], out=ops_off[1:])
+            ops = np.zeros(int(slots.sum()) + 16, dtype=np.uint8)
+        self.check(self._L.pb_align_batch(self.h, _ptr(at), _ptr(a_off), _ptr(a_len), _ptr(ast), _ptr(bt), _ptr(b_off),
+                                          _ptr(b_len), _ptr(bst), n, R, maxn, maxm, _ptr(out), _ptr(ops), _ptr(ops_off)))
+        if want_ops:
+            return out, [ops[ops_off[i]: ops_off[i] + max(int(out["nedit"][i]), 0)] if out["ret"][i] >= 0 else None
+                         for i in range(n)]
+        return out, None
+
+    def align(self, a: bytes, b: bytes, R: float = 0.3, a_fwd: bool = True, b_fwd: bool = True, maxn: int = 26000,
+              maxm: int = 6000):
+        """One seq_aligner::align(seg_a, seg_b) (batch of one).  a/b are the underlying texts; a backward accessor
+        starts at the last byte and walks down."""
+        a, b = _u8(a), _u8(b)
+        rec, ops = self.align_batch(a, [0 if a_fwd else max(len(a) - 1, 0)], [len(a)], b,
+                                    [0 if b_fwd else max(len(b) - 1, 0)], [len(b)], R, maxn, maxm,
+                                    [1 if a_fwd else -1], [1 if b_fwd else -1])
+        d = {k: int(rec[k][0]) for k in ALIGN_DTYPE.names}
+        if d["ret"] >= 0:
+            d["ops"] = ops[0].copy()
+            bb = b if b_fwd else b[::-1]
+            vals, j = np.zeros(len(d["ops"]), dtype=np.uint8), 0
+            for k, op in enumerate(d["ops"]):  # edit.val = seg_b->at(j-1) under MATCH/INSERT (seq_aligner.h:219,225)
+                if op != DELETE:
+                    vals[k] = bb[j]
+                    j += 1
+            d["vals"] = vals
+        return d
+
+    # ---- locate ----------------------------------------------------------------------------------
+    def locate(self, index: "Index", reads_text, offs, lens, want_ops: bool = False, **params):
+        """locator.cpp:70-92 for a batch of reads given as host text.  Returns records (and transcripts)."""
+        prm = default_locate_params(want_ops=int(want_ops), **params)
+        t = _u8(reads_text)
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        kept = lens >= prm.minlen
+        nk = int(kept.sum())
+        recs = np.zeros(nk, dtype=LOCATE_DTYPE)
+        ops = ops_off = None
+        if want_ops:
+            slots = (2 * lens[kept].astype(np.int64) + prm.maxm + 16 + 15) & ~15
+            ops_off = np.zeros(nk, dtype=np.int64)
+            if nk:
+                np.cumsum(slots[:-1], out=ops_off[1:])
+            ops = np.zeros(int(slots.sum()) + 16, dtype=np.uint8)
+        got = C.c_int64(0)
+        self.check(self._L.pb_locate_batch(self.h, index.h, index.ref.h, index.seq, _ptr(t), _ptr(offs), _ptr(lens),
+                                           len(lens), C.byref(prm), _ptr(recs), C.byref(got), _ptr(ops), _ptr(ops_off)))
+        assert got.value == nk
+        if want_ops:
+            return recs, [ops[ops_off[k]: ops_off[k] + int(recs["nedit"][k])] for k in range(nk)]
+        return recs
+
+    def locate_run(self, index: "Index", reads: "SeqSet", want_ops: bool = False, **params) -> "LocateJob":
+        prm = default_locate_params(want_ops=int(want_ops), **params)
+        h = C.c_void_p()
+        self.check(self._L.pb_locate_run(self.h, index.h, index.ref.h, index.seq, reads.h, C.byref(prm), None, C.byref(h)))
+        return LocateJob(self, h)
+
+
+class SeqSet:
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+
+    def free(self):
+        if self.h:
+            self.ctx._L.pb_seqset_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self.ctx._L.pb_seqset_count(self.h))
+
+    def length(self, i: int) -> int:
+        return int(self.ctx._L.pb_seqset_length(self.h, i))
+
+    def text(self, i: int) -> bytes:
+        n = self.length(i)
+        out = np.zeros(n + 1, dtype=np.uint8)
+        self.ctx.check(self.ctx._L.pb_seqset_text(self.ctx.h, self.h, i, _ptr(out), n + 1))
+        return out[:n].tobytes()
+
+    def packed(self, i: int) -> bytes:
+        n = (self.length(i) + 3) // 4
+        out = np.zeros(max(n, 1), dtype=np.uint8)
+        self.ctx.check(self.ctx._L.pb_seqset_packed(self.ctx.h, self.h, i, _ptr(out), n))
+        return out[:n].tobytes()
+
+    def seeds(self, i: int, mask: int) -> np.ndarray:
+        """K1 bulk: encode(text+p) & mask for every p of sequence i."""
+        out = np.zeros(self.length(i), dtype=np.uint32)
+        self.ctx.check(self.ctx._L.pb_seed_extract(self.ctx.h, self.h, i, mask, _ptr(out)))
+        return out
+
+    def seeds_device(self, mask: int) -> tuple[int, float]:
+        n, ms = C.c_int64(0), C.c_float(0)
+        self.ctx.check(self.ctx._L.pb_seed_extract_all_device(self.ctx.h, self.h, mask, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+
+class Index:
+    """Device seed index; find() is hash_table::find (common.h:54)."""
+
+    def __init__(self, ctx: Context, h, ref: SeqSet, seq: int):
+        self.ctx, self.h, self.ref, self.seq = ctx, h, ref, seq
+
+    def free(self):
+        if self.h:
+            self.ctx._L.pb_index_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    @property
+    def nkeys(self) -> int:
+        return int(self.ctx._L.pb_index_nkeys(self.h))
+
+    @property
+    def nentries(self) -> int:
+        return int(self.ctx._L.pb_index_nentries(self.h))
+
+    @property
+    def nscanned(self) -> int:
+        return int(self.ctx._L.pb_index_nscanned(self.h))
+
+    @property
+    def mask(self) -> int:
+        return int(self.ctx._L.pb_index_mask(self.h))
+
+    def find_batch(self, keys) -> list[list[int]]:
+        keys = np.ascontiguousarray(keys, dtype=np.uint32).reshape(-1)
+        n = len(keys)
+        cnt = np.zeros(n, dtype=np.int64)
+        self.ctx.check(self.ctx._L.pb_index_find_batch(self.ctx.h, self.h, _ptr(keys), n, _ptr(cnt), None, None, 0))
+        off = np.zeros(n, dtype=np.int64)
+        if n:
+            np.cumsum(cnt[:-1], out=off[1:])
+        pos = np.zeros(int(cnt.sum()) + 1, dtype=np.int32)
+        cap = int(cnt.max()) if n else 0
+        self.ctx.check(self.ctx._L.pb_index_find_batch(self.ctx.h, self.h, _ptr(keys), n, _ptr(cnt), _ptr(pos), _ptr(off), cap))
+        return [pos[off[i]: off[i] + cnt[i]].tolist() for i in range(n)]
+
+    def find(self, key: int) -> list[int]:
+        return self.find_batch([key])[0]
+
+
+class LocateJob:
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+
+    def free(self):
+        if self.h:
+            self.ctx._L.pb_locate_job_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    @property
+    def nkept(self) -> int:
+        return int(self.ctx._L.pb_locate_job_nkept(self.h))
+
+    @property
+    def ncand(self) -> int:
+        return int(self.ctx._L.pb_locate_job_ncand(self.h))
+
+    def stats(self) -> dict:
+        """valid after fetch(): candidates gathered, alignments run by K3, DP cells computed by K3"""
+        out = np.zeros(4, dtype=np.int64)
+        self.ctx.check(self.ctx._L.pb_locate_job_stats(self.h, _ptr(out)))
+        return {"ncand": int(out[0]), "dp_alignments": int(out[1]), "dp_cells": int(out[2])}
+
+    def ops_layout(self):
+        off = np.zeros(max(self.nkept, 1), dtype=np.int64)
+        ext = C.c_int64(0)
+        self.ctx.check(self.ctx._L.pb_locate_job_ops_layout(self.h, _ptr(off), C.byref(ext)))
+        return off[: self.nkept], ext.value
+
+    def fetch(self, want_ops: bool = False, recs: np.ndarray | None = None, ops: np.ndarray | None = None):
+        nk = self.nkept
+        if recs is None:
+            recs = np.zeros(nk, dtype=LOCATE_DTYPE)
+        if want_ops:
+            off, ext = self.ops_layout()
+            if ops is None:
+                ops = np.zeros(ext + 16, dtype=np.uint8)
+            self.ctx.check(self.ctx._L.pb_locate_fetch(self.ctx.h, self.h, _ptr(recs), _ptr(ops)))
+            return recs, [ops[off[k]: off[k] + int(recs["nedit"][k])] for k in range(nk)]
+        self.ctx.check(self.ctx._L.pb_locate_fetch(self.ctx.h, self.h, _ptr(recs), None))
+        return recs

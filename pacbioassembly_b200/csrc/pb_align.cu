@@ -1,0 +1,661 @@
+// pb_align.cu -- L2: banded edit-distance aligner on the GPU (replaces src/seq_aligner.h).
+//
+// The reference fills an 8-byte {cost,parent} cell at a time (seq_aligner.h:151-190).  Here one warp owns
+// one alignment and advances a whole band row per step with a bit-parallel recurrence (Myers 1999 /
+// Hyyro 2003, transposed: the state is the row's horizontal deltas, the band slides one bit per row).
+// 32 lanes x S 32-bit words hold the 2*max_dst+1 band bits; the only cross-lane traffic per row is two
+// 2-bit shuffles, two ballots (carry generate / propagate of the multi-word add) and one broadcast.
+// Costs AND parents come out identical to the reference, including its tie-breaking
+// (diag first, then left if strictly smaller, then up if strictly smaller; seq_aligner.h:164-173):
+//   D0 = cost(i,j)==cost(i-1,j-1);  parent = MATCH if Eq | ~D0, else INSERT if h(i,j)=+1, else DELETE.
+// tools/bitpar_model.c is the same arithmetic on the CPU, checked against the oracle cell by cell.
+//
+// Per cell the kernel touches 2 bits of HBM (the two parent planes, written once, coalesced 128 B per
+// store instruction) -- versus 8 bytes in the reference.  No tensor cores: this is integer/bit work.
+#include <algorithm>
+#include <map>
+
+#include "pb_internal.cuh"
+
+#define FULL 0xffffffffu
+#define ALIGN_WPB 4 // warps (alignments in flight) per CTA
+
+struct SeqView {
+    const uint32_t *hi, *lo;
+    const int64_t *base;
+    const int32_t *len;
+    int64_t nwords; // addressable words (line + guard)
+};
+
+static SeqView seq_view(const pb_seqset *s)
+{
+    SeqView v;
+    v.hi = s->d_hi.as<uint32_t>();
+    v.lo = s->d_lo.as<uint32_t>();
+    v.base = s->d_base.as<int64_t>();
+    v.len = s->d_len.as<int32_t>();
+    v.nwords = s->nwords() + 4;
+    return v;
+}
+
+// 32 bits of a plane starting at bit `bit`; bits outside the array read 0
+__device__ __forceinline__ uint32_t load_window(const uint32_t *__restrict__ arr, int64_t nwords, int64_t bit)
+{
+    const int64_t wi = bit >> 5;
+    const unsigned sh = (unsigned)(bit & 31);
+    const uint32_t w0 = (wi >= 0 && wi < nwords) ? __ldg(arr + wi) : 0u;
+    const uint32_t w1 = (wi + 1 >= 0 && wi + 1 < nwords) ? __ldg(arr + wi + 1) : 0u;
+    return __funnelshift_r(w0, w1, sh);
+}
+
+// seq_aligner.h:94-102
+__device__ __forceinline__ void derive_params(int a_len, int b_len, double R, int &len_a, int &len_b, int &D)
+{
+    if (b_len >= a_len) {
+        len_a = a_len;
+        D = 1 + (int)(len_a * R);
+        len_b = min(b_len, len_a + D);
+    } else {
+        len_b = b_len;
+        D = 1 + (int)(len_b * R);
+        len_a = min(a_len, len_b + D);
+    }
+}
+
+// DP cells the reference evaluates in rows 1..n: sum of min(len_b,i+D) - max(1,i-D) + 1 (seq_aligner.h:158-159)
+__device__ __forceinline__ long long cells_upto(int n, int D, int len_b)
+{
+    long long t = max(len_b - D, 0), m = min((long long)n, t);
+    long long f = m * (m + 1) / 2 + m * D + ((long long)n - m) * len_b;
+    long long m2 = min(n, D + 1);
+    long long g = m2;
+    if (n > D + 1) { long long x = n - D; g += x * (x + 1) / 2 - 1; }
+    return f - g + n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3a: prefix filter.  One thread replays rows 1..min(32,max_dst,len) of a candidate with a single
+// 32-bit word and applies the reference's early-failure test (seq_aligner.h:185) exactly.  A candidate
+// that fails here would have failed identically in the reference, so nothing is pruned that the
+// reference would have kept; everything that survives goes to the full aligner in list order.
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+prefilter_kernel(SeqView A, SeqView B, LocateView lv, int64_t ncand, double R, int maxn, int maxm,
+                 uint8_t *__restrict__ survive, int32_t *__restrict__ rej_cells)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncand) return;
+    const int q = lv.d_cand_q[c];
+    const int k = q / lv.ntrial, j = q - k * lv.ntrial;
+    const int r = lv.d_kept[k];
+    const int a_len = A.len[r] - j;
+    const int64_t a_bit = A.base[r] + j;
+    const int pos = lv.d_cand_pos[c];
+    const int b_len = lv.ref_len - pos;
+    const int64_t b_bit = lv.ref_base + pos;
+    int len_a, len_b, D;
+    derive_params(a_len, b_len, R, len_a, len_b, D);
+    if (len_a >= maxn || D >= maxm) { // seq_aligner.h:104-107 (domain per SURVEY Q-D3)
+        survive[c] = 0;
+        rej_cells[c] = 0;
+        return;
+    }
+    const int K = min(min(32, D), min(len_a, len_b));
+    const uint32_t ahi = load_window(A.hi, A.nwords, a_bit), alo = load_window(A.lo, A.nwords, a_bit);
+    const uint32_t bhi = load_window(B.hi, B.nwords, b_bit), blo = load_window(B.lo, B.nwords, b_bit);
+    const uint32_t peq0 = ~bhi & ~blo, peq1 = ~bhi & blo, peq2 = bhi & ~blo, peq3 = bhi & blo;
+    uint32_t Hp = 0xffffffffu, Hn = 0u;
+    int cii = 0, fail = 0;
+    for (int i = 1; i <= K; ++i) {
+        const uint32_t h = (ahi >> (i - 1)) & 1u, l = (alo >> (i - 1)) & 1u;
+        const uint32_t Eq = h ? (l ? peq3 : peq2) : (l ? peq1 : peq0);
+        const uint32_t Xv = (((Eq & Hp) + Hp) ^ Hp) | Eq;
+        const uint32_t Vp = Hn | ~(Xv | Hp), Vn = Hp & Xv;
+        const uint32_t D0 = Xv | Hn;
+        const uint32_t Xh = Eq | Hn;
+        const uint32_t vps = (Vp << 1) | 1u, vns = Vn << 1;
+        Hp = vns | ~(Xh | vps);
+        Hn = vps & Xh;
+        cii += 1 - (int)((D0 >> (i - 1)) & 1u);
+        if (i > 10 && (double)cii > i * R) { fail = i; break; }
+    }
+    survive[c] = fail ? 0 : 1;
+    rej_cells[c] = fail ? (int32_t)cells_upto(fail, D, len_b) : 0;
+}
+
+int pb_prefilter(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, const LocateView &lv, int64_t ncand, double R,
+                 int maxn, int maxm, uint8_t *d_survive, int32_t *d_rej_cells)
+{
+    if (ncand <= 0) return PB_OK;
+    prefilter_kernel<<<(unsigned)((ncand + 255) / 256), 256, 0, ctx->stream>>>(seq_view(A), seq_view(B), lv, ncand, R, maxn, maxm, d_survive, d_rej_cells);
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: the banded aligner.  One warp = one alignment; S = band words per lane (band <= 1024*S bits).
+// ---------------------------------------------------------------------------------------------
+
+struct AlnRes {
+    int ret, len_a, len_b, D, matlen_a, matlen_b, cost, diag_cost, nedit, fail_row;
+    long long cells;
+};
+
+template <int S>
+__device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_len, const SeqView &B, int64_t b_bit, int b_len,
+                                       double R, int maxn, int maxm, uint32_t *__restrict__ planes, int PW,
+                                       uint32_t *__restrict__ par, uint8_t *__restrict__ opsrev, uint8_t *__restrict__ ops_out,
+                                       AlnRes &res)
+{
+    constexpr int T = 32 * S;
+    const int lane = threadIdx.x & 31;
+    int len_a, len_b, D;
+    derive_params(a_len, b_len, R, len_a, len_b, D);
+    res.ret = -1; res.len_a = len_a; res.len_b = len_b; res.D = D;
+    res.matlen_a = res.matlen_b = res.cost = res.diag_cost = res.nedit = res.fail_row = 0;
+    res.cells = 0;
+    if (len_a >= maxn || D >= maxm) return; // seq_aligner.h:104-107
+
+    const int NW = (2 * D + 1 + 31) >> 5; // band words that carry real cells (NW <= T guaranteed by the host)
+
+    // ---- Eq planes of seg_b in shared memory: plane c, bit t <-> (b[t - D] == c), zero outside [0,len_b)
+    const int PWn = ((len_a + 31) >> 5) + T + 1;
+    for (int x = lane; x < PWn; x += 32) {
+        const int bidx0 = 32 * x - D; // b index of bit 0 of this word
+        uint32_t valid;
+        if (bidx0 >= len_b || bidx0 + 31 < 0) valid = 0u;
+        else {
+            valid = 0xffffffffu;
+            if (bidx0 < 0) valid &= 0xffffffffu << (-bidx0);
+            if (bidx0 + 31 >= len_b) valid &= 0xffffffffu >> (bidx0 + 32 - len_b);
+        }
+        uint32_t hi = 0u, lo = 0u;
+        if (valid) {
+            hi = load_window(B.hi, B.nwords, b_bit + bidx0);
+            lo = load_window(B.lo, B.nwords, b_bit + bidx0);
+        }
+        planes[0 * PW + x] = ~hi & ~lo & valid;
+        planes[1 * PW + x] = ~hi & lo & valid;
+        planes[2 * PW + x] = hi & ~lo & valid;
+        planes[3 * PW + x] = hi & lo & valid;
+    }
+    __syncwarp();
+
+    // ---- row 0: h = -1 for (fake) columns j <= 0, +1 for j >= 1; bits k >= 2D are pinned to +1 every row
+    uint32_t Hp[S], Hn[S], force[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int k0 = 32 * (lane * S + s);
+        uint32_t hn;
+        if (k0 + 31 <= D) hn = 0xffffffffu;
+        else if (k0 > D) hn = 0u;
+        else hn = 0xffffffffu >> (31 - (D - k0));
+        Hn[s] = hn;
+        Hp[s] = ~hn;
+        uint32_t f;
+        if (k0 >= 2 * D) f = 0xffffffffu;
+        else if (k0 + 31 < 2 * D) f = 0u;
+        else f = 0xffffffffu << (2 * D - k0);
+        force[s] = f;
+    }
+    const int wd = D >> 5, Ld = wd / S, sd = wd % S; // owner of the main-diagonal bit k = D
+
+    int cii = 0;                          // cost(i,i)
+    int colc = 0, colbest = 0, col_i = 0; // cost(i,len_b) tracking when len_a > len_b
+    int fail_row = 0;
+    uint32_t awin_hi = 0, awin_lo = 0;
+    int rows_done = 0;
+
+    for (int i = 1; i <= len_a; ++i) {
+        const int t = (i - 1) & 31;
+        if (t == 0) { // next 32 bases of seg_a (warp-uniform loads)
+            awin_hi = load_window(A.hi, A.nwords, a_bit + i - 1);
+            awin_lo = load_window(A.lo, A.nwords, a_bit + i - 1);
+        }
+        const int ca = (int)(((awin_hi >> t) & 1u) * 2u + ((awin_lo >> t) & 1u));
+        const uint32_t *pl = planes + ca * PW + ((i - 1) >> 5) + lane * S;
+        uint32_t *prow = par + (size_t)(i - 1) * (2 * T);
+
+        // phase A: slide the band (1-bit right shift across words and lanes), fetch Eq, block add with carry-in 0
+        uint32_t nx = __shfl_down_sync(FULL, (Hp[0] & 1u) | ((Hn[0] & 1u) << 1), 1);
+        if (lane == 31) nx = 1u;
+        uint32_t Eq[S], sum[S];
+        uint32_t carry = 0u, ones = 0xffffffffu;
+        uint32_t plw = pl[0];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const uint32_t hp_hi = (s + 1 < S) ? Hp[s + 1] : (nx & 1u);
+            const uint32_t hn_hi = (s + 1 < S) ? Hn[s + 1] : (nx >> 1);
+            Hp[s] = __funnelshift_r(Hp[s], hp_hi, 1) | force[s];
+            Hn[s] = __funnelshift_r(Hn[s], hn_hi, 1) & ~force[s];
+            const uint32_t nxt = pl[s + 1];
+            Eq[s] = __funnelshift_r(plw, nxt, t);
+            plw = nxt;
+            const uint32_t x = Eq[s] & Hp[s];
+            const uint32_t s1 = x + Hp[s];
+            const uint32_t s2 = s1 + carry;
+            carry = (uint32_t)(s1 < x) | (uint32_t)(s2 < s1);
+            sum[s] = s2;
+            ones &= s2;
+        }
+        const uint32_t G = __ballot_sync(FULL, carry);
+        const uint32_t P = __ballot_sync(FULL, ones == 0xffffffffu);
+        uint32_t cin = ((((G | P) + G) ^ P) >> lane) & 1u; // carry into this lane's block
+
+        // phase B: vertical deltas, D0, MATCH plane
+        uint32_t Vp[S], Vn[S];
+        uint32_t d0w = 0u;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const uint32_t v = sum[s] + cin;
+            cin &= (uint32_t)(v == 0u);
+            const uint32_t Xv = (v ^ Hp[s]) | Eq[s];
+            Vp[s] = Hn[s] | ~(Xv | Hp[s]);
+            Vn[s] = Hp[s] & Xv;
+            const uint32_t D0 = Xv | Hn[s];
+            if (lane * S + s < NW) prow[s * 32 + lane] = Eq[s] | ~D0;
+            if (s == sd) d0w = D0;
+        }
+        uint32_t pv = __shfl_up_sync(FULL, (Vp[S - 1] >> 31) | ((Vn[S - 1] >> 31) << 1), 1);
+        if (lane == 0) pv = 1u; // vin = +1 at the band's left edge (and at column 0)
+
+        // phase C: new horizontal deltas, INSERT plane
+        uint32_t pin = pv & 1u, nin = pv >> 1;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const uint32_t vps = (Vp[s] << 1) | pin, vns = (Vn[s] << 1) | nin;
+            pin = Vp[s] >> 31;
+            nin = Vn[s] >> 31;
+            const uint32_t Xh = Eq[s] | Hn[s];
+            Hp[s] = vns | ~(Xh | vps);
+            Hn[s] = vps & Xh;
+            if (lane * S + s < NW) prow[T + s * 32 + lane] = Hp[s];
+        }
+
+        const uint32_t d0bit = (__shfl_sync(FULL, d0w, Ld) >> (D & 31)) & 1u;
+        cii += 1 - (int)d0bit;
+        rows_done = i;
+        if (i > 10 && i <= len_b && (double)cii > i * R) { // seq_aligner.h:185; cell unwritten for i > len_b reads 0 (Q-D2)
+            fail_row = i;
+            break;
+        }
+        if (i == len_b) { colc = colbest = cii; col_i = i; }
+        if (i > len_b) { // vertical delta at column len_b (only when len_a > len_b)
+            const int k = len_b - i + D, wk = k >> 5, Lk = wk / S, sk = wk % S;
+            uint32_t vpw = 0u, vnw = 0u;
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                if (s == sk) { vpw = Vp[s]; vnw = Vn[s]; }
+            vpw = __shfl_sync(FULL, vpw, Lk);
+            vnw = __shfl_sync(FULL, vnw, Lk);
+            colc += (int)((vpw >> (k & 31)) & 1u) - (int)((vnw >> (k & 31)) & 1u);
+            if (colc < colbest) { colbest = colc; col_i = i; }
+        }
+    }
+    res.cells = cells_upto(rows_done, D, len_b);
+    if (fail_row) { res.fail_row = fail_row; return; }
+
+    // ---- goal_cell, seq_aligner.h:191-213
+    int matlen_a, matlen_b, cost;
+    if (len_a > len_b) {
+        matlen_a = col_i; matlen_b = len_b; cost = colbest;
+    } else {
+        // last row: cost(len_a, j) for j in (len_a, len_b] from the final horizontal deltas; earliest strict minimum
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            planes[lane * S + s] = Hp[s];
+            planes[T + lane * S + s] = Hn[s];
+        }
+        __syncwarp();
+        matlen_a = len_a; matlen_b = len_a; cost = cii;
+        if (lane == 0) {
+            int c = cii;
+            for (int j = len_a + 1; j <= len_b; ++j) {
+                const int k = j - len_a + D;
+                c += (int)((planes[k >> 5] >> (k & 31)) & 1u) - (int)((planes[T + (k >> 5)] >> (k & 31)) & 1u);
+                if (c < cost) { cost = c; matlen_b = j; }
+            }
+        }
+        cost = __shfl_sync(FULL, cost, 0);
+        matlen_b = __shfl_sync(FULL, matlen_b, 0);
+    }
+    res.matlen_a = matlen_a; res.matlen_b = matlen_b; res.cost = cost;
+    res.diag_cost = (a_len <= len_a && a_len <= len_b) ? cii : 0; // locator.cpp:86 (Q-L2)
+    if ((double)matlen_b < len_b * (1 - R)) return; // seq_aligner.h:114
+
+    // ---- find_path, seq_aligner.h:214-233: walk the parent planes back from the goal cell
+    __syncwarp();
+    int n = 0;
+    if (lane == 0) {
+        int i = matlen_a, j = matlen_b;
+        const int guard = len_a + len_b + 1; // a path can never be longer; keeps a corrupted plane from hanging the GPU
+        while ((i | j) && n < guard && i >= 0 && j >= 0) {
+            int op;
+            if (i == 0) op = PB_INSERT;      // init_cell row 0
+            else if (j == 0) op = PB_DELETE; // init_cell column 0
+            else {
+                const int k = j - i + D, w = k >> 5, L = w / S, s = w % S;
+                const uint32_t *prow = par + (size_t)(i - 1) * (2 * T) + s * 32 + L;
+                if ((__ldcg(prow) >> (k & 31)) & 1u) op = PB_MATCH;
+                else if ((__ldcg(prow + T) >> (k & 31)) & 1u) op = PB_INSERT;
+                else op = PB_DELETE;
+            }
+            opsrev[n++] = (uint8_t)op;
+            if (op == PB_MATCH) { --i; --j; } else if (op == PB_INSERT) --j; else --i;
+        }
+    }
+    n = __shfl_sync(FULL, n, 0);
+    __syncwarp();
+    if (ops_out)
+        for (int k = lane; k < n; k += 32) ops_out[k] = __ldcg(opsrev + (n - 1 - k));
+    res.nedit = n;
+    res.ret = matlen_b;
+}
+
+struct AlignLaunch {
+    SeqView A, B;
+    double R;
+    int maxn, maxm;
+    int PW;              // plane stride (words) for this launch
+    size_t slot_words;   // scratch words per warp slot
+    size_t par_words;    // of which parent planes
+    uint32_t *scratch;
+    int *queue;          // work counter
+    const int32_t *order; // item ids, longest first
+    int nitems;
+    uint8_t *ops;
+    const int64_t *ops_off;
+    unsigned long long *stats; // [0] DP cells computed by K3, [1] alignments run by K3 (may be NULL)
+};
+
+template <int S>
+__global__ void __launch_bounds__(ALIGN_WPB * 32)
+align_locate_kernel(AlignLaunch p, LocateView lv, const uint8_t *__restrict__ survive, const int32_t *__restrict__ rej_cells,
+                    pb_locate_rec *__restrict__ recs)
+{
+    extern __shared__ uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *planes = smem + (size_t)warp * 4 * p.PW;
+    const size_t slot = (size_t)blockIdx.x * ALIGN_WPB + warp;
+    uint32_t *par = p.scratch + slot * p.slot_words;
+    uint8_t *opsrev = reinterpret_cast<uint8_t *>(par + p.par_words);
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(p.queue, 1);
+        idx = __shfl_sync(FULL, idx, 0);
+        if (idx >= p.nitems) break;
+        const int k = p.order[idx];
+        const int r = lv.d_kept[k];
+        const int rlen = p.A.len[r];
+        const int64_t rbase = p.A.base[r];
+        const int64_t c0 = lv.d_qoff[(int64_t)k * lv.ntrial], c1 = lv.d_qoff[(int64_t)(k + 1) * lv.ntrial];
+        long long cells = 0;
+        int ncand = 0;
+        bool found = false;
+        AlnRes res;
+        int win_j = 0, win_pos = 0;
+        for (int64_t cb = c0; cb < c1 && !found; cb += 32) {
+            const int64_t c = cb + lane;
+            const int nvalid = (int)min((int64_t)32, c1 - cb);
+            int sv = 0, rc = 0;
+            if (lane < nvalid) { sv = survive[c]; rc = rej_cells[c]; }
+            uint32_t mask = __ballot_sync(FULL, sv);
+            int done = 0; // lanes [0,done) already accounted
+            while (mask) {
+                const int f = __ffs(mask) - 1;
+                cells += __reduce_add_sync(FULL, (lane >= done && lane < f) ? rc : 0);
+                ncand += f - done + 1;
+                const int q = lv.d_cand_q[cb + f];
+                const int j = q - k * lv.ntrial;
+                const int pos = lv.d_cand_pos[cb + f];
+                align_one<S>(p.A, rbase + j, rlen - j, p.B, lv.ref_base + pos, lv.ref_len - pos, p.R, p.maxn, p.maxm, planes,
+                             p.PW, par, opsrev, p.ops ? p.ops + p.ops_off[k] : nullptr, res);
+                cells += res.cells;
+                if (lane == 0 && p.stats) { atomicAdd(p.stats, (unsigned long long)res.cells); atomicAdd(p.stats + 1, 1ull); }
+                done = f + 1;
+                mask &= mask - 1;
+                if (res.ret > 0) { found = true; win_j = j; win_pos = pos; break; } // locator.cpp:82
+            }
+            if (!found) {
+                cells += __reduce_add_sync(FULL, (lane >= done && lane < nvalid) ? rc : 0);
+                ncand += nvalid - done;
+            }
+        }
+        if (lane == 0) {
+            pb_locate_rec rec;
+            rec.nseq = k; rec.found = found ? 1 : 0;
+            rec.j = found ? win_j : 0; rec.pos = found ? win_pos : 0;
+            rec.cost = found ? res.cost : 0; rec.seg_len = found ? rlen - win_j : 0;
+            rec.diag_cost = found ? res.diag_cost : 0;
+            rec.matlen_a = found ? res.matlen_a : 0; rec.matlen_b = found ? res.matlen_b : 0;
+            rec.nedit = found ? res.nedit : 0;
+            rec.ncand = ncand; rec._pad = 0; rec.cells = cells;
+            recs[k] = rec;
+        }
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(ALIGN_WPB * 32)
+align_pairs_kernel(AlignLaunch p, pb_align_out *__restrict__ out)
+{
+    extern __shared__ uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *planes = smem + (size_t)warp * 4 * p.PW;
+    const size_t slot = (size_t)blockIdx.x * ALIGN_WPB + warp;
+    uint32_t *par = p.scratch + slot * p.slot_words;
+    uint8_t *opsrev = reinterpret_cast<uint8_t *>(par + p.par_words);
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(p.queue, 1);
+        idx = __shfl_sync(FULL, idx, 0);
+        if (idx >= p.nitems) break;
+        const int k = p.order[idx];
+        AlnRes res;
+        align_one<S>(p.A, p.A.base[k], p.A.len[k], p.B, p.B.base[k], p.B.len[k], p.R, p.maxn, p.maxm, planes, p.PW, par, opsrev,
+                     p.ops ? p.ops + p.ops_off[k] : nullptr, res);
+        if (lane == 0 && p.stats) { atomicAdd(p.stats, (unsigned long long)res.cells); atomicAdd(p.stats + 1, 1ull); }
+        if (lane == 0) {
+            pb_align_out o;
+            o.ret = res.ret; o.len_a = res.len_a; o.len_b = res.len_b; o.max_dst = res.D;
+            o.matlen_a = res.matlen_a; o.matlen_b = res.matlen_b; o.cost = res.cost; o.diag_cost = res.diag_cost;
+            o.nedit = res.nedit; o.fail_row = res.fail_row; o.cells = res.cells;
+            out[k] = o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: size classes, scratch, launches
+// ---------------------------------------------------------------------------------------------
+
+static const int kClasses[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
+static const int kNumClasses = (int)(sizeof(kClasses) / sizeof(kClasses[0]));
+
+static int class_for_band(int D)
+{ // smallest S with 32*S words >= ceil((2D+1)/32)
+    const int NW = (2 * D + 1 + 31) >> 5;
+    for (int c = 0; c < kNumClasses; ++c)
+        if (32 * kClasses[c] >= NW) return c;
+    return -1;
+}
+
+struct ClassPlan {
+    std::vector<int32_t> items;
+    int max_rows = 0, max_D = 0;
+};
+
+template <int S> struct KernelSel {
+    static const void *locate() { return (const void *)align_locate_kernel<S>; }
+    static const void *pairs() { return (const void *)align_pairs_kernel<S>; }
+};
+
+static const void *kernel_ptr(int S, bool locate)
+{
+    switch (S) {
+#define CASE(s) case s: return locate ? KernelSel<s>::locate() : KernelSel<s>::pairs();
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(8) CASE(10) CASE(12) CASE(16)
+#undef CASE
+    }
+    return nullptr;
+}
+
+struct LaunchGeom {
+    int PW;
+    size_t smem_bytes, slot_words, par_words;
+    int blocks;
+};
+
+static int plan_launch(pb_ctx *ctx, int S, const ClassPlan &cp, bool locate, size_t scratch_budget, LaunchGeom *g)
+{
+    const int T = 32 * S;
+    g->PW = ((cp.max_rows + 31) >> 5) + T + 2;
+    g->smem_bytes = (size_t)ALIGN_WPB * 4 * g->PW * sizeof(uint32_t);
+    g->par_words = (size_t)std::max(cp.max_rows, 1) * 2 * T;
+    const size_t ops_bytes = ((size_t)2 * cp.max_rows + cp.max_D + 64 + 15) & ~(size_t)15;
+    g->slot_words = g->par_words + ops_bytes / 4;
+    const void *fn = kernel_ptr(S, locate);
+    if (g->smem_bytes > 200 * 1024) return pb_fail(ctx, PB_ERR_DOMAIN, "sequence of %d rows needs %zu bytes of shared memory per CTA", cp.max_rows, g->smem_bytes);
+    PB_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes));
+    int occ = 0;
+    PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, ALIGN_WPB * 32, g->smem_bytes));
+    if (occ < 1) occ = 1;
+    int64_t blocks = (int64_t)occ * ctx->sm_count;
+    blocks = std::min<int64_t>(blocks, ((int64_t)cp.items.size() + ALIGN_WPB - 1) / ALIGN_WPB);
+    const size_t slot_bytes = g->slot_words * 4;
+    const int64_t by_mem = (int64_t)(scratch_budget / (slot_bytes * ALIGN_WPB));
+    if (by_mem < 1) return pb_fail(ctx, PB_ERR_NOMEM, "scratch budget %zu too small for one CTA (%zu bytes per alignment)", scratch_budget, slot_bytes);
+    blocks = std::max<int64_t>(1, std::min(blocks, by_mem));
+    g->blocks = (int)blocks;
+    return PB_OK;
+}
+
+static size_t scratch_budget(pb_ctx *ctx)
+{
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); fr = (size_t)8 << 30; }
+    size_t b = (size_t)((double)fr * 0.4);
+    if (ctx->scratch_limit && ctx->scratch_limit < b) b = ctx->scratch_limit;
+    return b;
+}
+
+template <class LaunchFn>
+static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate, AlignLaunch base, LaunchFn &&launch)
+{
+    if (plans.empty()) return PB_OK;
+    const size_t budget = scratch_budget(ctx);
+    // geometry per class, one scratch buffer reused by the (stream-ordered) launches
+    std::map<int, LaunchGeom> geoms;
+    size_t need = 0;
+    for (auto &kv : plans) {
+        LaunchGeom g;
+        PB_TRY(plan_launch(ctx, kClasses[kv.first], kv.second, locate, budget, &g));
+        geoms[kv.first] = g;
+        need = std::max(need, (size_t)g.blocks * ALIGN_WPB * g.slot_words * 4);
+    }
+    DevBuf scratch, d_order, d_queue;
+    PB_TRY(scratch.alloc(ctx, need + 256));
+    size_t nitems = 0;
+    for (auto &kv : plans) nitems += kv.second.items.size();
+    PB_TRY(d_order.alloc(ctx, nitems * 4 + 16));
+    PB_TRY(d_queue.alloc_zero(ctx, (size_t)plans.size() * 4 + 16));
+    size_t off = 0;
+    int ci = 0;
+    // widest band first: those alignments are the longest running
+    for (auto it = plans.rbegin(); it != plans.rend(); ++it, ++ci) {
+        ClassPlan &cp = it->second;
+        const LaunchGeom &g = geoms[it->first];
+        PB_TRY(pb_h2d(ctx, d_order.as<int32_t>() + off, cp.items.data(), cp.items.size() * 4));
+        AlignLaunch p = base;
+        p.PW = g.PW;
+        p.slot_words = g.slot_words;
+        p.par_words = g.par_words;
+        p.scratch = scratch.as<uint32_t>();
+        p.queue = d_queue.as<int>() + ci;
+        p.order = d_order.as<int32_t>() + off;
+        p.nitems = (int)cp.items.size();
+        PB_TRY(launch(kClasses[it->first], p, g));
+        off += cp.items.size();
+    }
+    return PB_OK;
+}
+
+int pb_align_locate(pb_ctx *ctx, const pb_seqset *reads, const pb_seqset *ref, const LocateView &lv, int64_t nkept,
+                    const std::vector<int32_t> &kept_lens, double R, int maxn, int maxm, const uint8_t *d_survive,
+                    const int32_t *d_rej_cells, pb_locate_rec *d_recs, uint8_t *d_ops, const int64_t *d_ops_off,
+                    unsigned long long *d_stats)
+{
+    if (nkept == 0) return PB_OK;
+    std::map<int, ClassPlan> plans;
+    std::vector<int32_t> order((size_t)nkept);
+    for (int64_t k = 0; k < nkept; ++k) order[k] = (int32_t)k;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return kept_lens[x] > kept_lens[y]; });
+    for (int32_t k : order) {
+        const int L = kept_lens[k];
+        // widest band / longest seg_a any candidate of this read can reach the DP with: len_a <= L, and the domain
+        // check (seq_aligner.h:104) turns away len_a >= maxn or max_dst >= maxm before any row is computed
+        const int D = std::min(1 + (int)(L * R), maxm - 1);
+        const int cls = class_for_band(std::max(D, 1));
+        if (cls < 0) return pb_fail(ctx, PB_ERR_DOMAIN, "band half-width %d exceeds PB_MAX_BAND", D);
+        ClassPlan &cp = plans[cls];
+        cp.items.push_back(k);
+        cp.max_rows = std::max(cp.max_rows, std::min(L, std::max(maxn - 1, 1)));
+        cp.max_D = std::max(cp.max_D, D);
+    }
+    AlignLaunch base;
+    memset(&base, 0, sizeof base);
+    base.A = seq_view(reads);
+    base.B = seq_view(ref);
+    base.R = R; base.maxn = maxn; base.maxm = maxm;
+    base.ops = d_ops; base.ops_off = d_ops_off;
+    base.stats = d_stats;
+    return run_classes(ctx, plans, true, base, [&](int S, const AlignLaunch &p, const LaunchGeom &g) -> int {
+        void *args[] = {(void *)&p, (void *)&lv, (void *)&d_survive, (void *)&d_rej_cells, (void *)&d_recs};
+        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(S, true), dim3(g.blocks), dim3(ALIGN_WPB * 32), args, g.smem_bytes, ctx->stream));
+        ctx->launches++;
+        return PB_OK;
+    });
+}
+
+int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t n, double R, int maxn, int maxm,
+                   pb_align_out *d_out, uint8_t *d_ops, const int64_t *d_ops_off)
+{
+    if (n == 0) return PB_OK;
+    std::map<int, ClassPlan> plans;
+    std::vector<int32_t> order((size_t)n);
+    for (int64_t k = 0; k < n; ++k) order[k] = (int32_t)k;
+    std::vector<int> la((size_t)n), D((size_t)n);
+    for (int64_t k = 0; k < n; ++k) {
+        int lb;
+        pb_align_params(A->len[k], B->len[k], R, &la[k], &lb, &D[k]);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return (int64_t)la[x] * D[x] > (int64_t)la[y] * D[y]; });
+    for (int32_t k : order) {
+        const bool rejected = la[k] >= maxn || D[k] >= maxm;
+        int cls = 0;
+        if (!rejected) {
+            cls = class_for_band(D[k]);
+            if (cls < 0) return pb_fail(ctx, PB_ERR_DOMAIN, "band half-width %d exceeds PB_MAX_BAND", D[k]);
+        }
+        ClassPlan &cp = plans[cls];
+        cp.items.push_back(k);
+        if (!rejected) {
+            cp.max_rows = std::max(cp.max_rows, la[k]);
+            cp.max_D = std::max(cp.max_D, D[k]);
+        }
+    }
+    AlignLaunch base;
+    memset(&base, 0, sizeof base);
+    base.A = seq_view(A);
+    base.B = seq_view(B);
+    base.R = R; base.maxn = maxn; base.maxm = maxm;
+    base.ops = d_ops; base.ops_off = d_ops_off;
+    return run_classes(ctx, plans, false, base, [&](int S, const AlignLaunch &p, const LaunchGeom &g) -> int {
+        void *args[] = {(void *)&p, (void *)&d_out};
+        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(S, false), dim3(g.blocks), dim3(ALIGN_WPB * 32), args, g.smem_bytes, ctx->stream));
+        ctx->launches++;
+        return PB_OK;
+    });
+}

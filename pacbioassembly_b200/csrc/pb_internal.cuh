@@ -1,0 +1,192 @@
+// pb_internal.cuh -- shared declarations of the B200 read-to-reference library (not installed).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pacbio_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+
+struct pb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2 * PB_T_COUNT] = {};
+    float times[PB_T_COUNT] = {};
+    bool timed[PB_T_COUNT] = {};
+    int64_t launches = 0;
+    size_t scratch_limit = 0;
+    int sm_count = 148;
+    std::string err;
+    // pinned staging for small host<->device exchanges
+    void *h_pin = nullptr;
+    size_t h_pin_bytes = 0;
+};
+
+void pb_set_error(pb_ctx *ctx, const char *fmt, ...);
+int pb_fail(pb_ctx *ctx, int code, const char *fmt, ...);
+
+#define PB_CUDA(ctx, call)                                                                            \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return pb_fail((ctx), _e == cudaErrorMemoryAllocation ? PB_ERR_NOMEM : PB_ERR_CUDA,       \
+                           "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define PB_TRY(expr)                 \
+    do {                             \
+        int _r = (expr);             \
+        if (_r != PB_OK) return _r;  \
+    } while (0)
+
+#define PB_LAUNCH_CHECK(ctx)                        \
+    do {                                            \
+        (ctx)->launches++;                          \
+        PB_CUDA((ctx), cudaGetLastError());         \
+    } while (0)
+
+// stage timers: CUDA events on the context stream; times are read back by pb_timer_collect
+void pb_timer_reset(pb_ctx *ctx);
+void pb_timer_begin(pb_ctx *ctx, int which);
+void pb_timer_end(pb_ctx *ctx, int which);
+void pb_timer_collect(pb_ctx *ctx); // requires the stream to be idle
+
+// stream-ordered device buffer (cudaMallocAsync pool: reuse across calls is cheap)
+struct DevBuf {
+    pb_ctx *ctx = nullptr;
+    void *p = nullptr;
+    size_t bytes = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    int alloc(pb_ctx *c, size_t n);
+    int alloc_zero(pb_ctx *c, size_t n);
+    void release();
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+int pb_h2d(pb_ctx *ctx, void *dst, const void *src, size_t bytes);
+int pb_d2h(pb_ctx *ctx, void *dst, const void *src, size_t bytes);
+int pb_sync(pb_ctx *ctx);
+
+// ---------------------------------------------------------------------------------------------
+// device-resident sequences
+// ---------------------------------------------------------------------------------------------
+//
+// Padded layout: sequence i occupies base offsets [base[i], base[i]+len[i]) of one long coordinate line;
+// base[i] is a multiple of 32 and at least 16 padding bases (code 3, what a NUL/T/N maps to under C2I,
+// dna_seq.h:21) follow every sequence, so a 16-base seed window starting at any in-sequence position
+// never sees a neighbour (SURVEY Q-S3).  Three views of the same line are kept in HBM:
+//   packed : 4 bases per byte, first base in bits 7:6 (dna_seq.h:113-127)          -> seeds (K1)
+//   hi, lo : bit planes, bit (g & 31) of word (g >> 5) = code bit of base g          -> banded DP (K3)
+// flags[i] bit 0 = the text held a byte outside {A,C,G,T} (it maps to code 3 for seeding exactly like
+// the reference, but DP compares raw bytes, so such sequences take the byte-exact DP path).
+
+struct pb_seqset {
+    pb_ctx *ctx = nullptr;
+    int64_t n = 0;
+    int64_t total = 0; // padded bases, multiple of 128
+    std::vector<int64_t> base;
+    std::vector<int32_t> len;
+    std::vector<uint32_t> flags;
+    DevBuf d_base, d_len, d_flags, d_hi, d_lo, d_packed;
+    // optional raw text kept on the device for the byte-exact path: element k of sequence i is
+    // d_text[toff[i] + k*tstride[i]]
+    DevBuf d_text, d_toff, d_tstride;
+    int64_t nwords() const { return total / 32; }
+};
+
+#define PB_FLAG_IRREGULAR 1u
+
+// ---------------------------------------------------------------------------------------------
+// seed index
+// ---------------------------------------------------------------------------------------------
+
+#define PB_MAX_RUNS 16
+
+struct BucketFn {          // key -> bucket id
+    int exact;             // 1: bit-compress under the mask (injective); 0: multiplicative hash + key check
+    int nruns;
+    int bits;              // log2(number of buckets)
+    uint32_t run_mask[PB_MAX_RUNS];
+    uint8_t run_shift[PB_MAX_RUNS];
+};
+
+struct pb_index {
+    pb_ctx *ctx = nullptr;
+    uint32_t mask = 0;
+    int policy = 0;
+    int64_t nbuckets = 0;
+    int64_t nentries = 0, nkeys = 0, nscanned = 0;
+    int64_t ref_len = 0;
+    BucketFn fn;
+    DevBuf d_start; // [nbuckets+1] u32
+    DevBuf d_pos;   // [nentries] i32, per bucket in the reference's list order
+    DevBuf d_key;   // [nentries] u32 (only when !fn.exact)
+};
+
+// ---------------------------------------------------------------------------------------------
+// kernels / stages implemented across the .cu files
+// ---------------------------------------------------------------------------------------------
+
+// pb_seq.cu
+int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, const int32_t *h_len,
+                    const int32_t *h_stride, int64_t n, bool keep_text_ref, pb_seqset **out);
+
+// pb_seed.cu
+int pb_seed_bulk_device(pb_ctx *ctx, const pb_seqset *s, int64_t first_base, int64_t count, uint32_t mask,
+                        uint32_t *d_keys);
+int pb_scan_u32(pb_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, int64_t n, DevBuf &tmp);   // exclusive, out[n] = total
+int pb_scan_i64(pb_ctx *ctx, const uint32_t *d_in, int64_t *d_out, int64_t n, DevBuf &tmp);    // exclusive, out[n] = total
+
+struct ProbeOut {
+    DevBuf d_qoff;     // [nq+1] i64 exclusive offsets into the candidate arrays
+    DevBuf d_cand_pos; // [ncand] i32
+    DevBuf d_cand_q;   // [ncand] i32 query id
+    int64_t ncand = 0;
+};
+// keys of the first ntrial offsets of every kept read, then probe + gather
+int pb_locate_seed_probe(pb_ctx *ctx, const pb_index *ix, const pb_seqset *reads, const int32_t *d_kept, int64_t nkept,
+                         int ntrial, ProbeOut *po);
+
+// pb_align.cu
+struct LocateView { // everything the aligner needs to derive candidate (a,b) views in locate mode
+    const int32_t *d_kept;
+    const int64_t *d_qoff;
+    const int32_t *d_cand_pos;
+    const int32_t *d_cand_q;
+    int ntrial;
+    int64_t ref_base; // base offset of the reference sequence inside its seqset
+    int32_t ref_len;
+};
+int pb_prefilter(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, const LocateView &lv, int64_t ncand, double R,
+                 int maxn, int maxm, uint8_t *d_survive, int32_t *d_rej_cells);
+int pb_align_locate(pb_ctx *ctx, const pb_seqset *reads, const pb_seqset *ref, const LocateView &lv, int64_t nkept,
+                    const std::vector<int32_t> &kept_lens, double R, int maxn, int maxm, const uint8_t *d_survive,
+                    const int32_t *d_rej_cells, pb_locate_rec *d_recs, uint8_t *d_ops, const int64_t *d_ops_off,
+                    unsigned long long *d_stats);
+int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t n, double R, int maxn, int maxm,
+                   pb_align_out *d_out, uint8_t *d_ops, const int64_t *d_ops_off);
+
+// host-side mirror of seq_aligner.h:94-102 (also used to size scratch)
+static inline void pb_align_params(int a_len, int b_len, double R, int *len_a, int *len_b, int *max_dst)
+{
+    if (b_len >= a_len) {
+        *len_a = a_len;
+        *max_dst = 1 + (int)(a_len * R);
+        *len_b = b_len < *len_a + *max_dst ? b_len : *len_a + *max_dst;
+    } else {
+        *len_b = b_len;
+        *max_dst = 1 + (int)(b_len * R);
+        *len_a = a_len < *len_b + *max_dst ? a_len : *len_b + *max_dst;
+    }
+}

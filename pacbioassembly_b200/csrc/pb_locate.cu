@@ -1,0 +1,251 @@
+// pb_locate.cu -- the locate loop (locator.cpp:70-92) and the batched align entry point, as pipelines over
+// K1 (seeds) -> K2 (probe/gather) -> K3a (prefix filter) -> K3 (banded aligner, first success in list order).
+#include <algorithm>
+
+#include "pb_internal.cuh"
+
+extern "C" void pb_locate_default_params(pb_locate_params *p)
+{
+    if (!p) return;
+    p->R = 0.15;     // locator.cpp:68
+    p->ntrial = 50;  // locator.cpp:74
+    p->minlen = 500; // locator.cpp:72
+    p->maxn = 40000; // locator.cpp:23
+    p->maxm = 6000;  // locator.cpp:24
+    p->want_ops = 0;
+    p->reserved = 0;
+}
+
+static int check_regular(pb_ctx *ctx, const pb_seqset *s, const char *what)
+{
+    for (int64_t i = 0; i < s->n; ++i)
+        if (s->flags[i] & PB_FLAG_IRREGULAR)
+            return pb_fail(ctx, PB_ERR_ALPHABET, "%s %lld holds bytes outside {A,C,G,T}; the banded aligner compares raw bytes "
+                           "(seq_aligner.h:136) and only takes plain ACGT input", what, (long long)i);
+    return PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pb_align_batch
+// ---------------------------------------------------------------------------------------------
+
+extern "C" int pb_align_batch(pb_ctx *ctx, const char *a_text, const int64_t *a_off, const int32_t *a_len, const int32_t *a_stride,
+                              const char *b_text, const int64_t *b_off, const int32_t *b_len, const int32_t *b_stride, int64_t n,
+                              double R, int maxn, int maxm, pb_align_out *out, uint8_t *ops, const int64_t *ops_off)
+{
+    if (!ctx || n < 0 || (n && (!a_text || !a_off || !a_len || !b_text || !b_off || !b_len || !out)) || (ops && !ops_off))
+        return pb_fail(ctx, PB_ERR_ARG, "pb_align_batch: bad argument");
+    if (!n) return PB_OK;
+    if (n > INT32_MAX) return pb_fail(ctx, PB_ERR_ARG, "pb_align_batch: too many pairs in one call");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    pb_timer_reset(ctx);
+    pb_timer_begin(ctx, PB_T_TOTAL);
+    pb_seqset *A = nullptr, *B = nullptr;
+    int r = pb_seqset_from_text(ctx, a_text, a_off, a_len, a_stride, n, &A);
+    if (r == PB_OK) r = pb_seqset_from_text(ctx, b_text, b_off, b_len, b_stride, n, &B);
+    if (r == PB_OK) r = check_regular(ctx, A, "seg_a of pair");
+    if (r == PB_OK) r = check_regular(ctx, B, "seg_b of pair");
+    DevBuf d_out, d_ops, d_ops_off;
+    int64_t extent = 0;
+    if (r == PB_OK) r = d_out.alloc_zero(ctx, (size_t)n * sizeof(pb_align_out));
+    if (r == PB_OK && ops) {
+        for (int64_t i = 0; i < n; ++i) {
+            if (ops_off[i] < 0) { r = pb_fail(ctx, PB_ERR_ARG, "negative ops offset"); break; }
+            extent = std::max<int64_t>(extent, ops_off[i] + a_len[i] + b_len[i] + 1);
+        }
+        if (r == PB_OK) r = d_ops.alloc(ctx, (size_t)extent + 16);
+        if (r == PB_OK) r = d_ops_off.alloc(ctx, (size_t)n * 8);
+        if (r == PB_OK) r = pb_h2d(ctx, d_ops_off.p, ops_off, (size_t)n * 8);
+    }
+    if (r == PB_OK) {
+        pb_timer_begin(ctx, PB_T_ALIGN);
+        r = pb_align_pairs(ctx, A, B, n, R, maxn, maxm, d_out.as<pb_align_out>(), ops ? d_ops.as<uint8_t>() : nullptr,
+                           ops ? d_ops_off.as<int64_t>() : nullptr);
+        pb_timer_end(ctx, PB_T_ALIGN);
+    }
+    if (r == PB_OK) {
+        pb_timer_begin(ctx, PB_T_D2H);
+        r = pb_d2h(ctx, out, d_out.p, (size_t)n * sizeof(pb_align_out));
+        // transcripts: copy each pair's slot (nedit is only known after the records arrive, so copy whole slots)
+        if (r == PB_OK && ops) {
+            int64_t lo = INT64_MAX;
+            for (int64_t i = 0; i < n; ++i) lo = std::min(lo, ops_off[i]);
+            r = pb_d2h(ctx, ops + lo, d_ops.as<uint8_t>() + lo, (size_t)(extent - lo));
+        }
+        pb_timer_end(ctx, PB_T_D2H);
+    }
+    pb_timer_end(ctx, PB_T_TOTAL);
+    int rs = pb_sync(ctx);
+    if (r == PB_OK) r = rs;
+    if (r == PB_OK) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) r = pb_fail(ctx, PB_ERR_CUDA, "align kernels failed: %s", cudaGetErrorString(e));
+    }
+    pb_timer_collect(ctx);
+    if (A) pb_seqset_free(A);
+    if (B) pb_seqset_free(B);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// locate
+// ---------------------------------------------------------------------------------------------
+
+struct pb_locate_job {
+    pb_ctx *ctx = nullptr;
+    int64_t nkept = 0, ncand = 0;
+    int want_ops = 0;
+    std::vector<int64_t> ops_off;
+    int64_t extent = 0;
+    DevBuf d_recs, d_ops, d_stats;
+    mutable unsigned long long stats[2] = {0, 0};
+};
+
+extern "C" int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const pb_seqset *reads,
+                             const pb_locate_params *prm, const int64_t *ops_off, pb_locate_job **out)
+{
+    if (!ctx || !ix || !ref || !reads || !prm || !out || ref_seq < 0 || ref_seq >= ref->n)
+        return pb_fail(ctx, PB_ERR_ARG, "pb_locate_run: bad argument");
+    if (prm->ntrial < 1 || prm->ntrial > 4096) return pb_fail(ctx, PB_ERR_ARG, "ntrial %d out of range", prm->ntrial);
+    if (prm->minlen < prm->ntrial + 15)
+        return pb_fail(ctx, PB_ERR_ARG, "minlen %d < ntrial+15: encode(read+j) would read past the read (locator.cpp:75)", prm->minlen);
+    if (reads->n * (int64_t)prm->ntrial > INT32_MAX) return pb_fail(ctx, PB_ERR_DOMAIN, "too many reads in one batch");
+    if (ref->len[ref_seq] != ix->ref_len) return pb_fail(ctx, PB_ERR_ARG, "index was built over a different sequence");
+    *out = nullptr;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PB_TRY(check_regular(ctx, reads, "read"));
+    if (ref->flags[ref_seq] & PB_FLAG_IRREGULAR)
+        return pb_fail(ctx, PB_ERR_ALPHABET, "the contig holds bytes outside {A,C,G,T}");
+
+    pb_locate_job *job = new pb_locate_job();
+    job->ctx = ctx;
+    job->want_ops = prm->want_ops;
+    int r = PB_OK;
+#define TRYJ(x) do { r = (x); if (r != PB_OK) { delete job; return r; } } while (0)
+    // kept reads: len >= minlen, nseq = rank among kept (locator.cpp:72, SURVEY Q-L1)
+    std::vector<int32_t> kept, kept_lens;
+    for (int64_t i = 0; i < reads->n; ++i)
+        if (reads->len[i] >= prm->minlen) { kept.push_back((int32_t)i); kept_lens.push_back(reads->len[i]); }
+    const int64_t nkept = (int64_t)kept.size();
+    job->nkept = nkept;
+    TRYJ(job->d_recs.alloc_zero(ctx, (size_t)std::max<int64_t>(nkept, 1) * sizeof(pb_locate_rec)));
+    TRYJ(job->d_stats.alloc_zero(ctx, 16));
+    if (nkept == 0) { *out = job; return PB_OK; }
+
+    DevBuf d_kept, d_survive, d_rej, d_ops_off;
+    TRYJ(d_kept.alloc(ctx, (size_t)nkept * 4));
+    TRYJ(pb_h2d(ctx, d_kept.p, kept.data(), (size_t)nkept * 4));
+    if (prm->want_ops) {
+        job->ops_off.resize((size_t)nkept);
+        int64_t ext = 0;
+        for (int64_t k = 0; k < nkept; ++k) {
+            const int64_t slot = ((int64_t)2 * kept_lens[k] + prm->maxm + 16 + 15) & ~(int64_t)15;
+            if (ops_off) {
+                if (ops_off[k] < 0) { delete job; return pb_fail(ctx, PB_ERR_ARG, "negative ops offset"); }
+                job->ops_off[k] = ops_off[k];
+                ext = std::max(ext, ops_off[k] + slot);
+            } else {
+                job->ops_off[k] = ext;
+                ext += slot;
+            }
+        }
+        job->extent = ext;
+        TRYJ(job->d_ops.alloc(ctx, (size_t)ext + 16));
+        TRYJ(d_ops_off.alloc(ctx, (size_t)nkept * 8));
+        TRYJ(pb_h2d(ctx, d_ops_off.p, job->ops_off.data(), (size_t)nkept * 8));
+    }
+    ProbeOut po;
+    TRYJ(pb_locate_seed_probe(ctx, ix, reads, d_kept.as<int32_t>(), nkept, prm->ntrial, &po));
+    job->ncand = po.ncand;
+    LocateView lv;
+    lv.d_kept = d_kept.as<int32_t>();
+    lv.d_qoff = po.d_qoff.as<int64_t>();
+    lv.d_cand_pos = po.d_cand_pos.as<int32_t>();
+    lv.d_cand_q = po.d_cand_q.as<int32_t>();
+    lv.ntrial = prm->ntrial;
+    lv.ref_base = ref->base[ref_seq];
+    lv.ref_len = ref->len[ref_seq];
+    TRYJ(d_survive.alloc(ctx, (size_t)std::max<int64_t>(po.ncand, 1)));
+    TRYJ(d_rej.alloc(ctx, (size_t)std::max<int64_t>(po.ncand, 1) * 4));
+    pb_timer_begin(ctx, PB_T_PREFILTER);
+    TRYJ(pb_prefilter(ctx, reads, ref, lv, po.ncand, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(), d_rej.as<int32_t>()));
+    pb_timer_end(ctx, PB_T_PREFILTER);
+    pb_timer_begin(ctx, PB_T_ALIGN);
+    TRYJ(pb_align_locate(ctx, reads, ref, lv, nkept, kept_lens, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(),
+                         d_rej.as<int32_t>(), job->d_recs.as<pb_locate_rec>(), prm->want_ops ? job->d_ops.as<uint8_t>() : nullptr,
+                         prm->want_ops ? d_ops_off.as<int64_t>() : nullptr, job->d_stats.as<unsigned long long>()));
+    pb_timer_end(ctx, PB_T_ALIGN);
+#undef TRYJ
+    *out = job;
+    return PB_OK;
+}
+
+extern "C" int64_t pb_locate_job_nkept(const pb_locate_job *job) { return job ? job->nkept : 0; }
+extern "C" int64_t pb_locate_job_ncand(const pb_locate_job *job) { return job ? job->ncand : 0; }
+
+extern "C" int pb_locate_job_stats(const pb_locate_job *job, int64_t *out)
+{
+    if (!job || !out) return PB_ERR_ARG;
+    out[0] = job->ncand;
+    out[1] = (int64_t)job->stats[1];
+    out[2] = (int64_t)job->stats[0];
+    out[3] = 0;
+    return PB_OK;
+}
+
+extern "C" int pb_locate_job_ops_layout(const pb_locate_job *job, int64_t *ops_off, int64_t *extent)
+{
+    if (!job) return PB_ERR_ARG;
+    if (ops_off) for (size_t k = 0; k < job->ops_off.size(); ++k) ops_off[k] = job->ops_off[k];
+    if (extent) *extent = job->extent;
+    return PB_OK;
+}
+
+extern "C" int pb_locate_fetch(pb_ctx *ctx, const pb_locate_job *job, pb_locate_rec *recs, uint8_t *ops)
+{
+    if (!ctx || !job || (job->nkept && !recs)) return pb_fail(ctx, PB_ERR_ARG, "pb_locate_fetch: bad argument");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    pb_timer_begin(ctx, PB_T_D2H);
+    PB_TRY(pb_d2h(ctx, recs, job->d_recs.p, (size_t)job->nkept * sizeof(pb_locate_rec)));
+    PB_TRY(pb_d2h(ctx, job->stats, job->d_stats.p, 16));
+    if (ops && job->want_ops && job->extent) PB_TRY(pb_d2h(ctx, ops, job->d_ops.p, (size_t)job->extent));
+    pb_timer_end(ctx, PB_T_D2H);
+    PB_TRY(pb_sync(ctx));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return pb_fail(ctx, PB_ERR_CUDA, "locate kernels failed: %s", cudaGetErrorString(e));
+    pb_timer_collect(ctx);
+    return PB_OK;
+}
+
+extern "C" void pb_locate_job_free(pb_locate_job *job)
+{
+    if (!job) return;
+    cudaSetDevice(job->ctx->device);
+    delete job;
+}
+
+extern "C" int pb_locate_batch(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const char *reads_text,
+                               const int64_t *off, const int32_t *len, int64_t nreads, const pb_locate_params *prm,
+                               pb_locate_rec *recs, int64_t *nkept, uint8_t *ops, const int64_t *ops_off)
+{
+    if (!ctx || !prm || nreads < 0 || (nreads && (!reads_text || !off || !len)))
+        return pb_fail(ctx, PB_ERR_ARG, "pb_locate_batch: bad argument");
+    if (prm->want_ops && (!ops || !ops_off)) return pb_fail(ctx, PB_ERR_ARG, "want_ops needs ops and ops_off");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    pb_timer_reset(ctx);
+    pb_timer_begin(ctx, PB_T_TOTAL);
+    pb_seqset *rs = nullptr;
+    PB_TRY(pb_seqset_from_text(ctx, reads_text, off, len, nullptr, nreads, &rs));
+    pb_locate_job *job = nullptr;
+    int r = pb_locate_run(ctx, ix, ref, ref_seq, rs, prm, prm->want_ops ? ops_off : nullptr, &job);
+    if (r == PB_OK) {
+        if (nkept) *nkept = job->nkept;
+        r = pb_locate_fetch(ctx, job, recs, prm->want_ops ? ops : nullptr);
+    }
+    pb_timer_end(ctx, PB_T_TOTAL);
+    if (r == PB_OK) r = pb_sync(ctx);
+    pb_timer_collect(ctx);
+    pb_locate_job_free(job);
+    pb_seqset_free(rs);
+    return r;
+}

@@ -1,0 +1,658 @@
+// pb_seed.cu -- L1: spaced-seed extraction (K1), seed index build, probe/gather (K2).
+//
+// Replaces dna_seq::encode called in a loop (locator.cpp:62-66, ref_seq.h:291-311), the
+// __gnu_cxx::hash_map<unsigned, std::list<int>> seed map (common.h:54) and hash_table::find
+// (locator.cpp:76, spaced_seed.cpp:265).
+//
+// Index layout in HBM: direct-address CSR.  bucket(key) compresses the key's bits under the spaced
+// mask (weight 11/12 seeds -> 2^22 / 2^24 buckets, injective, so no key compare on probe); masks with
+// more than 24 care bits or more than PB_MAX_RUNS runs fall back to a multiplicative hash plus a stored
+// key per entry.  Within a bucket, entries are in the reference's list order (insertion order), which
+// is what makes "first successful candidate" (locator.cpp:79-88) reproducible.
+#include <algorithm>
+
+#include "pb_internal.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// K1: bulk seed extraction.  HBM-bound: 0.25 B read + 4 B written per position.
+// A warp turns 32 coalesced packed words (512 bases) into 512 keys; every lane stores uint4
+// (4 consecutive keys), so each store instruction writes one contiguous 512-byte run.
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// seed word at base offset o (0..15) of the big-endian-bit stream (h0:h1): equals dna_seq::encode(text+p)
+__device__ __forceinline__ uint32_t seed_from_be(uint32_t h0, uint32_t h1, int o)
+{
+    return bswap32(__funnelshift_l(h1, h0, 2 * o));
+}
+
+__global__ void __launch_bounds__(256)
+seed_bulk_kernel(const uint32_t *__restrict__ pw, int64_t first_word, int64_t last_word, int64_t count, uint32_t mask,
+                 uint32_t *__restrict__ keys)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nchunks = (count + 511) >> 9;
+    for (int64_t c = warp0; c < nchunks; c += nwarps) {
+        const int64_t w0 = first_word + c * 32;
+        const uint32_t hw = bswap32(__ldg(pw + min(w0 + lane, last_word)));
+        const uint32_t hx = bswap32(__ldg(pw + min(w0 + 32, last_word)));
+        const int o = 4 * (lane & 3);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int src = 8 * r + (lane >> 2);
+            const uint32_t wa = __shfl_sync(0xffffffffu, hw, src);
+            uint32_t wb = __shfl_sync(0xffffffffu, hw, (src + 1) & 31);
+            if (src == 31) wb = hx;
+            uint4 k;
+            k.x = seed_from_be(wa, wb, o) & mask;
+            k.y = seed_from_be(wa, wb, o + 1) & mask;
+            k.z = seed_from_be(wa, wb, o + 2) & mask;
+            k.w = seed_from_be(wa, wb, o + 3) & mask;
+            const int64_t idx = (c << 9) + 128 * r + 4 * lane;
+            if (idx + 3 < count) {
+                *reinterpret_cast<uint4 *>(keys + idx) = k;
+            } else {
+                if (idx < count) keys[idx] = k.x;
+                if (idx + 1 < count) keys[idx + 1] = k.y;
+                if (idx + 2 < count) keys[idx + 2] = k.z;
+            }
+        }
+    }
+}
+
+// keys for positions [first_base, first_base+count) of the padded line (first_base % 16 == 0)
+int pb_seed_bulk_device(pb_ctx *ctx, const pb_seqset *s, int64_t first_base, int64_t count, uint32_t mask, uint32_t *d_keys)
+{
+    if (count <= 0) return PB_OK;
+    if (first_base & 15) return pb_fail(ctx, PB_ERR_ARG, "seed extraction must start on a 16-base boundary");
+    const int64_t nchunks = (count + 511) >> 9;
+    int64_t blocks = std::min<int64_t>((nchunks + 7) / 8, (int64_t)ctx->sm_count * 8);
+    seed_bulk_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(s->d_packed.as<uint32_t>(), first_base >> 4,
+                                                                2 * s->nwords() + 7, count, mask, d_keys);
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
+
+extern "C" int pb_seed_extract(pb_ctx *ctx, const pb_seqset *s, int64_t i, uint32_t mask, uint32_t *keys)
+{
+    if (!ctx || !s || i < 0 || i >= s->n || !keys) return pb_fail(ctx, PB_ERR_ARG, "pb_seed_extract: bad argument");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t L = s->len[i];
+    if (!L) return PB_OK;
+    DevBuf d;
+    PB_TRY(d.alloc(ctx, (size_t)L * 4 + 64));
+    pb_timer_begin(ctx, PB_T_SEED);
+    PB_TRY(pb_seed_bulk_device(ctx, s, s->base[i], L, mask, d.as<uint32_t>()));
+    pb_timer_end(ctx, PB_T_SEED);
+    PB_TRY(pb_d2h(ctx, keys, d.p, (size_t)L * 4));
+    PB_TRY(pb_sync(ctx));
+    pb_timer_collect(ctx);
+    return PB_OK;
+}
+
+extern "C" int pb_seed_extract_all_device(pb_ctx *ctx, const pb_seqset *s, uint32_t mask, int64_t *nkeys, float *kernel_ms)
+{
+    if (!ctx || !s) return pb_fail(ctx, PB_ERR_ARG, "pb_seed_extract_all_device: bad argument");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t count = s->base[s->n];
+    DevBuf d;
+    PB_TRY(d.alloc(ctx, (size_t)count * 4 + 64));
+    pb_timer_reset(ctx);
+    pb_timer_begin(ctx, PB_T_SEED);
+    PB_TRY(pb_seed_bulk_device(ctx, s, 0, count, mask, d.as<uint32_t>()));
+    pb_timer_end(ctx, PB_T_SEED);
+    PB_TRY(pb_sync(ctx));
+    pb_timer_collect(ctx);
+    if (nkeys) *nkeys = count;
+    if (kernel_ms) *kernel_ms = ctx->times[PB_T_SEED];
+    return PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan (three phases; block = 256 threads x 16 items)
+// ---------------------------------------------------------------------------------------------
+
+#define SCAN_ITEMS 16
+#define SCAN_BLOCK 256
+#define SCAN_TILE (SCAN_ITEMS * SCAN_BLOCK)
+
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long *total)
+{
+    __shared__ unsigned long long wsum[SCAN_BLOCK / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    unsigned long long off = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_BLOCK / 32; ++k) {
+        unsigned long long t = wsum[k];
+        if (k < wid) off += t;
+        tot += t;
+    }
+    __syncthreads();
+    *total = tot;
+    return off + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_sums_kernel(const uint32_t *__restrict__ in, int64_t n, unsigned long long *bsum)
+{
+    const int64_t t0 = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (t0 + k < n) s += in[t0 + k];
+    unsigned long long tot;
+    block_exclusive_scan(s, &tot);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+__global__ void scan_bsum_kernel(unsigned long long *bsum, int64_t nb)
+{ // one warp, sequential over chunks of 32
+    const int lane = threadIdx.x;
+    unsigned long long carry = 0;
+    for (int64_t b0 = 0; b0 < nb; b0 += 32) {
+        unsigned long long v = b0 + lane < nb ? bsum[b0 + lane] : 0, x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (b0 + lane < nb) bsum[b0 + lane] = carry + x - v;
+        carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane == 0) bsum[nb] = carry;
+}
+
+template <class OutT>
+__global__ void __launch_bounds__(SCAN_BLOCK)
+scan_write_kernel(const uint32_t *__restrict__ in, int64_t n, const unsigned long long *__restrict__ bsum, int64_t nb,
+                  OutT *__restrict__ out)
+{
+    const int64_t t0 = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = t0 + k < n ? in[t0 + k] : 0u;
+        s += v[k];
+    }
+    unsigned long long tot;
+    unsigned long long off = block_exclusive_scan(s, &tot) + bsum[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (t0 + k < n) out[t0 + k] = (OutT)off;
+        off += v[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = (OutT)bsum[nb];
+}
+
+template <class OutT> static int scan_impl(pb_ctx *ctx, const uint32_t *d_in, OutT *d_out, int64_t n, DevBuf &tmp)
+{
+    const int64_t nb = std::max<int64_t>(1, (n + SCAN_TILE - 1) / SCAN_TILE);
+    PB_TRY(tmp.alloc(ctx, (size_t)(nb + 1) * sizeof(unsigned long long)));
+    scan_sums_kernel<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(d_in, n, tmp.as<unsigned long long>());
+    PB_LAUNCH_CHECK(ctx);
+    scan_bsum_kernel<<<1, 32, 0, ctx->stream>>>(tmp.as<unsigned long long>(), nb);
+    PB_LAUNCH_CHECK(ctx);
+    scan_write_kernel<OutT><<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(d_in, n, tmp.as<unsigned long long>(), nb, d_out);
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
+
+int pb_scan_u32(pb_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, int64_t n, DevBuf &tmp) { return scan_impl<uint32_t>(ctx, d_in, d_out, n, tmp); }
+int pb_scan_i64(pb_ctx *ctx, const uint32_t *d_in, int64_t *d_out, int64_t n, DevBuf &tmp) { return scan_impl<int64_t>(ctx, d_in, d_out, n, tmp); }
+
+// ---------------------------------------------------------------------------------------------
+// index build
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t bucket_of(const BucketFn &fn, uint32_t key)
+{
+    if (fn.exact) {
+        uint32_t b = 0;
+#pragma unroll 4
+        for (int r = 0; r < fn.nruns; ++r) b |= (key & fn.run_mask[r]) >> fn.run_shift[r];
+        return b;
+    }
+    return (key * 0x9E3779B1u) >> (32 - fn.bits);
+}
+
+static BucketFn make_bucket_fn(uint32_t mask)
+{
+    BucketFn fn;
+    memset(&fn, 0, sizeof fn);
+    int pop = __builtin_popcount(mask), nruns = 0, outbit = 0;
+    bool ok = pop <= 24;
+    uint32_t m = mask;
+    while (m && ok) {
+        int lo = __builtin_ctz(m);
+        uint32_t run = m >> lo;
+        int rl = __builtin_ctz(~run);
+        uint32_t rm = (rl >= 32 ? 0xFFFFFFFFu : ((1u << rl) - 1u)) << lo;
+        if (nruns == PB_MAX_RUNS) { ok = false; break; }
+        fn.run_mask[nruns] = rm;
+        fn.run_shift[nruns] = (uint8_t)(lo - outbit);
+        ++nruns;
+        outbit += rl;
+        m &= ~rm;
+    }
+    if (ok) {
+        fn.exact = 1;
+        fn.nruns = nruns;
+        fn.bits = pop;
+    } else {
+        fn.exact = 0;
+        fn.nruns = 0;
+        fn.bits = 24;
+    }
+    return fn;
+}
+
+struct EntryMap { // scan order e -> reference position (ref_seq.h:291-311 for REFSEQ; identity for LOCATOR)
+    int64_t nhead, len;
+    __host__ __device__ int64_t pos(int64_t e) const { return e < nhead ? e : len - 16 - (e - nhead); }
+};
+
+__global__ void index_count_kernel(const uint32_t *__restrict__ keys_all, EntryMap em, int64_t nscan, BucketFn fn,
+                                   uint32_t *__restrict__ count)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nscan) return;
+    const uint32_t key = keys_all[em.pos(e)];
+    if (key) atomicAdd(&count[bucket_of(fn, key)], 1u);
+}
+
+__global__ void index_scatter_kernel(const uint32_t *__restrict__ keys_all, EntryMap em, int64_t nscan, BucketFn fn,
+                                     uint32_t *__restrict__ cursor, int32_t *__restrict__ ent)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nscan) return;
+    const uint32_t key = keys_all[em.pos(e)];
+    if (!key) return;
+    const uint32_t slot = atomicAdd(&cursor[bucket_of(fn, key)], 1u);
+    ent[slot] = (int32_t)e;
+}
+
+#define SMALL_BUCKET 48
+
+// restore insertion order inside each bucket (the atomic scatter is unordered)
+__global__ void index_sort_small_kernel(const uint32_t *__restrict__ start, int64_t nbuckets, int32_t *__restrict__ ent,
+                                        uint32_t *__restrict__ big_list, uint32_t *__restrict__ nbig)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbuckets) return;
+    const uint32_t s = start[b], c = start[b + 1] - s;
+    if (c < 2) return;
+    if (c > SMALL_BUCKET) {
+        big_list[atomicAdd(nbig, 1u)] = (uint32_t)b;
+        return;
+    }
+    int32_t *p = ent + s;
+    for (uint32_t i = 1; i < c; ++i) {
+        int32_t v = p[i];
+        uint32_t j = i;
+        while (j > 0 && p[j - 1] > v) { p[j] = p[j - 1]; --j; }
+        p[j] = v;
+    }
+}
+
+// one CTA per big bucket: bitonic sort of a power-of-two padded copy in global scratch
+__global__ void __launch_bounds__(256)
+index_sort_big_kernel(const uint32_t *__restrict__ start, const uint32_t *__restrict__ big_list,
+                      const unsigned long long *__restrict__ tmp_off, int32_t *__restrict__ ent, int32_t *__restrict__ tmp)
+{
+    const uint32_t b = big_list[blockIdx.x];
+    const uint32_t s = start[b], c = start[b + 1] - s;
+    uint32_t P = 1;
+    while (P < c) P <<= 1;
+    int32_t *t = tmp + tmp_off[blockIdx.x];
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) t[i] = i < c ? ent[s + i] : INT32_MAX;
+    __syncthreads();
+    for (uint32_t k = 2; k <= P; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+                uint32_t l = i ^ j;
+                if (l > i) {
+                    int32_t x = t[i], y = t[l];
+                    bool up = (i & k) == 0;
+                    if ((x > y) == up) { t[i] = y; t[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) ent[s + i] = t[i];
+}
+
+__global__ void big_sizes_kernel(const uint32_t *__restrict__ start, const uint32_t *__restrict__ big_list, uint32_t nbig,
+                                 uint32_t *__restrict__ sizes)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbig) return;
+    const uint32_t b = big_list[i], c = start[b + 1] - start[b];
+    uint32_t P = 1;
+    while (P < c) P <<= 1;
+    sizes[i] = P;
+}
+
+__global__ void index_finalize_kernel(const uint32_t *__restrict__ keys_all, EntryMap em, int64_t nentries,
+                                      int32_t *__restrict__ ent, uint32_t *__restrict__ ekey)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nentries) return;
+    const int64_t p = em.pos(ent[i]);
+    ent[i] = (int32_t)p;
+    if (ekey) ekey[i] = keys_all[p];
+}
+
+__global__ void index_nkeys_kernel(const uint32_t *__restrict__ start, int64_t nbuckets, const uint32_t *__restrict__ ekey,
+                                   unsigned long long *__restrict__ nkeys)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long mine = 0;
+    if (b < nbuckets) {
+        const uint32_t s = start[b], c = start[b + 1] - s;
+        if (!ekey) mine = c ? 1 : 0;
+        else
+            for (uint32_t i = 0; i < c; ++i) { // distinct keys in the bucket (hashed buckets are tiny)
+                bool first = true;
+                for (uint32_t j = 0; j < i && first; ++j) first = ekey[s + j] != ekey[s + i];
+                mine += first;
+            }
+    }
+    for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(nkeys, mine);
+}
+
+extern "C" int pb_index_build(pb_ctx *ctx, const pb_seqset *ref, int64_t seq, uint32_t mask, int policy, pb_index **out)
+{
+    if (!ctx || !ref || !out || seq < 0 || seq >= ref->n) return pb_fail(ctx, PB_ERR_ARG, "pb_index_build: bad argument");
+    if (policy != PB_POLICY_LOCATOR && policy != PB_POLICY_REFSEQ) return pb_fail(ctx, PB_ERR_ARG, "unknown index policy %d", policy);
+    *out = nullptr;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    pb_timer_reset(ctx);
+    const int64_t len = ref->len[seq];
+    EntryMap em;
+    em.len = len;
+    int64_t nscan;
+    if (policy == PB_POLICY_LOCATOR) {
+        em.nhead = len;
+        nscan = len;
+    } else { // ref_seq.h:291-311
+        const int64_t nmax = len - 16;
+        em.nhead = std::max<int64_t>(0, std::min<int64_t>(nmax, 20000));
+        int64_t ntail = std::min<int64_t>(len - 20000 - 16, 20000);
+        nscan = em.nhead + std::max<int64_t>(ntail, 0);
+    }
+    pb_index *ix = new pb_index();
+    ix->ctx = ctx;
+    ix->mask = mask;
+    ix->policy = policy;
+    ix->ref_len = len;
+    ix->nscanned = nscan;
+    ix->fn = make_bucket_fn(mask);
+    ix->nbuckets = (int64_t)1 << ix->fn.bits;
+    const int64_t nb = ix->nbuckets;
+    int r;
+#define TRYI(x) do { r = (x); if (r != PB_OK) { delete ix; return r; } } while (0)
+    DevBuf d_keys, d_count, d_cursor, tmp, d_big, d_nbig, d_nkeys;
+    TRYI(d_keys.alloc(ctx, (size_t)std::max<int64_t>(len, 1) * 4 + 64));
+    pb_timer_begin(ctx, PB_T_SEED);
+    TRYI(pb_seed_bulk_device(ctx, ref, ref->base[seq], len, mask, d_keys.as<uint32_t>()));
+    pb_timer_end(ctx, PB_T_SEED);
+    pb_timer_begin(ctx, PB_T_INDEX);
+    TRYI(d_count.alloc_zero(ctx, (size_t)(nb + 1) * 4));
+    TRYI(ix->d_start.alloc(ctx, (size_t)(nb + 2) * 4));
+    const unsigned gscan = (unsigned)std::max<int64_t>(1, (nscan + 255) / 256);
+    if (nscan > 0) {
+        index_count_kernel<<<gscan, 256, 0, ctx->stream>>>(d_keys.as<uint32_t>(), em, nscan, ix->fn, d_count.as<uint32_t>());
+        ctx->launches++;
+    }
+    TRYI(pb_scan_u32(ctx, d_count.as<uint32_t>(), ix->d_start.as<uint32_t>(), nb, tmp));
+    uint32_t nent32 = 0;
+    TRYI(pb_d2h(ctx, &nent32, ix->d_start.as<uint32_t>() + nb, 4));
+    TRYI(pb_sync(ctx));
+    ix->nentries = nent32;
+    TRYI(ix->d_pos.alloc(ctx, (size_t)std::max<int64_t>(ix->nentries, 1) * 4));
+    if (!ix->fn.exact) TRYI(ix->d_key.alloc(ctx, (size_t)std::max<int64_t>(ix->nentries, 1) * 4));
+    if (ix->nentries > 0) {
+        TRYI(d_cursor.alloc(ctx, (size_t)nb * 4));
+        if (cudaMemcpyAsync(d_cursor.p, ix->d_start.p, (size_t)nb * 4, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) {
+            delete ix;
+            return pb_fail(ctx, PB_ERR_CUDA, "cursor copy failed");
+        }
+        index_scatter_kernel<<<gscan, 256, 0, ctx->stream>>>(d_keys.as<uint32_t>(), em, nscan, ix->fn, d_cursor.as<uint32_t>(), ix->d_pos.as<int32_t>());
+        ctx->launches++;
+        // big buckets are rare (degenerate repeats); the list can hold at most nentries/SMALL_BUCKET of them
+        const int64_t maxbig = ix->nentries / SMALL_BUCKET + 1;
+        TRYI(d_big.alloc(ctx, (size_t)maxbig * 4));
+        TRYI(d_nbig.alloc_zero(ctx, 16));
+        index_sort_small_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(ix->d_start.as<uint32_t>(), nb, ix->d_pos.as<int32_t>(), d_big.as<uint32_t>(), d_nbig.as<uint32_t>());
+        ctx->launches++;
+        uint32_t nbig = 0;
+        TRYI(pb_d2h(ctx, &nbig, d_nbig.p, 4));
+        TRYI(pb_sync(ctx));
+        if (nbig) {
+            DevBuf d_sizes, d_off, d_tmp, tmp2;
+            TRYI(d_sizes.alloc(ctx, (size_t)(nbig + 1) * 4));
+            TRYI(d_off.alloc(ctx, (size_t)(nbig + 2) * 8));
+            big_sizes_kernel<<<(nbig + 255) / 256, 256, 0, ctx->stream>>>(ix->d_start.as<uint32_t>(), d_big.as<uint32_t>(), nbig, d_sizes.as<uint32_t>());
+            ctx->launches++;
+            TRYI(pb_scan_i64(ctx, d_sizes.as<uint32_t>(), d_off.as<int64_t>(), nbig, tmp2));
+            int64_t tot = 0;
+            TRYI(pb_d2h(ctx, &tot, d_off.as<int64_t>() + nbig, 8));
+            TRYI(pb_sync(ctx));
+            TRYI(d_tmp.alloc(ctx, (size_t)tot * 4 + 16));
+            index_sort_big_kernel<<<nbig, 256, 0, ctx->stream>>>(ix->d_start.as<uint32_t>(), d_big.as<uint32_t>(), d_off.as<unsigned long long>(), ix->d_pos.as<int32_t>(), d_tmp.as<int32_t>());
+            ctx->launches++;
+            TRYI(pb_sync(ctx));
+        }
+        index_finalize_kernel<<<(unsigned)((ix->nentries + 255) / 256), 256, 0, ctx->stream>>>(d_keys.as<uint32_t>(), em, ix->nentries, ix->d_pos.as<int32_t>(), ix->fn.exact ? nullptr : ix->d_key.as<uint32_t>());
+        ctx->launches++;
+    }
+    TRYI(d_nkeys.alloc_zero(ctx, 16));
+    index_nkeys_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(ix->d_start.as<uint32_t>(), nb, ix->fn.exact ? nullptr : ix->d_key.as<uint32_t>(), d_nkeys.as<unsigned long long>());
+    ctx->launches++;
+    pb_timer_end(ctx, PB_T_INDEX);
+    unsigned long long nk = 0;
+    TRYI(pb_d2h(ctx, &nk, d_nkeys.p, 8));
+    TRYI(pb_sync(ctx));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { delete ix; return pb_fail(ctx, PB_ERR_CUDA, "index build failed: %s", cudaGetErrorString(e)); }
+    ix->nkeys = (int64_t)nk;
+    pb_timer_collect(ctx);
+#undef TRYI
+    *out = ix;
+    return PB_OK;
+}
+
+extern "C" void pb_index_free(pb_index *ix)
+{
+    if (!ix) return;
+    cudaSetDevice(ix->ctx->device);
+    delete ix;
+}
+extern "C" int64_t pb_index_nkeys(const pb_index *ix) { return ix ? ix->nkeys : 0; }
+extern "C" int64_t pb_index_nentries(const pb_index *ix) { return ix ? ix->nentries : 0; }
+extern "C" int64_t pb_index_nscanned(const pb_index *ix) { return ix ? ix->nscanned : 0; }
+extern "C" uint32_t pb_index_mask(const pb_index *ix) { return ix ? ix->mask : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// K2: probe + gather
+// ---------------------------------------------------------------------------------------------
+
+struct IndexView {
+    const uint32_t *start;
+    const int32_t *pos;
+    const uint32_t *key; // NULL when exact
+    BucketFn fn;
+};
+
+// bucket range of a query and the number of entries that really carry its key
+__device__ __forceinline__ void probe_one(const IndexView &iv, uint32_t key, uint32_t *s, uint32_t *blen, uint32_t *cnt)
+{
+    if (!key) { *s = 0; *blen = 0; *cnt = 0; return; } // keys with (sd & mask) == 0 are never inserted (locator.cpp:64)
+    const uint32_t b = bucket_of(iv.fn, key);
+    const uint32_t s0 = __ldg(iv.start + b), c = __ldg(iv.start + b + 1) - s0;
+    uint32_t m = c;
+    if (iv.key) {
+        m = 0;
+        for (uint32_t t = 0; t < c; ++t) m += __ldg(iv.key + s0 + t) == key;
+    }
+    *s = s0; *blen = c; *cnt = m;
+}
+
+__global__ void probe_count_kernel(IndexView iv, const uint32_t *__restrict__ keys, int64_t nq, uint32_t *__restrict__ cnt)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint32_t s, bl, c;
+    probe_one(iv, keys[q], &s, &bl, &c);
+    cnt[q] = c;
+}
+
+__global__ void probe_gather_kernel(IndexView iv, const uint32_t *__restrict__ keys, int64_t nq, const int64_t *__restrict__ qoff,
+                                    int32_t *__restrict__ cand_pos, int32_t *__restrict__ cand_q)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const int64_t o0 = qoff[q];
+    if (qoff[q + 1] == o0) return;
+    const uint32_t key = keys[q];
+    uint32_t s, bl, c;
+    probe_one(iv, key, &s, &bl, &c);
+    int64_t o = o0;
+    for (uint32_t t = 0; t < bl; ++t) {
+        if (iv.key && __ldg(iv.key + s + t) != key) continue;
+        cand_pos[o] = __ldg(iv.pos + s + t);
+        cand_q[o] = (int32_t)q;
+        ++o;
+    }
+}
+
+// seeds at the first ntrial offsets of every kept read: key = encode(read + j) & mask (locator.cpp:75)
+__global__ void locate_seed_kernel(const uint32_t *__restrict__ pw, const int64_t *__restrict__ base, const int32_t *__restrict__ kept,
+                                   int64_t nkept, int ntrial, uint32_t mask, uint32_t *__restrict__ keys)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nkept * ntrial) return;
+    const int64_t k = q / ntrial;
+    const int j = (int)(q - k * ntrial);
+    const int64_t g = base[kept[k]] + j;
+    const uint32_t h0 = bswap32(__ldg(pw + (g >> 4))), h1 = bswap32(__ldg(pw + (g >> 4) + 1));
+    keys[q] = seed_from_be(h0, h1, (int)(g & 15)) & mask;
+}
+
+static IndexView view_of(const pb_index *ix)
+{
+    IndexView iv;
+    iv.start = ix->d_start.as<uint32_t>();
+    iv.pos = ix->d_pos.as<int32_t>();
+    iv.key = ix->fn.exact ? nullptr : ix->d_key.as<uint32_t>();
+    iv.fn = ix->fn;
+    return iv;
+}
+
+int pb_locate_seed_probe(pb_ctx *ctx, const pb_index *ix, const pb_seqset *reads, const int32_t *d_kept, int64_t nkept,
+                         int ntrial, ProbeOut *po)
+{
+    const int64_t nq = nkept * ntrial;
+    po->ncand = 0;
+    PB_TRY(po->d_qoff.alloc(ctx, (size_t)(nq + 2) * 8));
+    if (nq == 0) {
+        PB_CUDA(ctx, cudaMemsetAsync(po->d_qoff.p, 0, 16, ctx->stream));
+        PB_TRY(po->d_cand_pos.alloc(ctx, 16));
+        PB_TRY(po->d_cand_q.alloc(ctx, 16));
+        return PB_OK;
+    }
+    DevBuf d_keys, d_cnt, tmp;
+    PB_TRY(d_keys.alloc(ctx, (size_t)nq * 4));
+    PB_TRY(d_cnt.alloc(ctx, (size_t)nq * 4));
+    const unsigned grid = (unsigned)((nq + 255) / 256);
+    pb_timer_begin(ctx, PB_T_SEED);
+    locate_seed_kernel<<<grid, 256, 0, ctx->stream>>>(reads->d_packed.as<uint32_t>(), reads->d_base.as<int64_t>(), d_kept, nkept, ntrial, ix->mask, d_keys.as<uint32_t>());
+    PB_LAUNCH_CHECK(ctx);
+    pb_timer_end(ctx, PB_T_SEED);
+    pb_timer_begin(ctx, PB_T_PROBE);
+    IndexView iv = view_of(ix);
+    probe_count_kernel<<<grid, 256, 0, ctx->stream>>>(iv, d_keys.as<uint32_t>(), nq, d_cnt.as<uint32_t>());
+    PB_LAUNCH_CHECK(ctx);
+    PB_TRY(pb_scan_i64(ctx, d_cnt.as<uint32_t>(), po->d_qoff.as<int64_t>(), nq, tmp));
+    int64_t ncand = 0;
+    PB_TRY(pb_d2h(ctx, &ncand, po->d_qoff.as<int64_t>() + nq, 8));
+    PB_TRY(pb_sync(ctx));
+    if (ncand > (int64_t)INT32_MAX) return pb_fail(ctx, PB_ERR_DOMAIN, "%lld candidates in one batch; split the read batch", (long long)ncand);
+    po->ncand = ncand;
+    PB_TRY(po->d_cand_pos.alloc(ctx, (size_t)std::max<int64_t>(ncand, 1) * 4));
+    PB_TRY(po->d_cand_q.alloc(ctx, (size_t)std::max<int64_t>(ncand, 1) * 4));
+    if (ncand) {
+        probe_gather_kernel<<<grid, 256, 0, ctx->stream>>>(iv, d_keys.as<uint32_t>(), nq, po->d_qoff.as<int64_t>(), po->d_cand_pos.as<int32_t>(), po->d_cand_q.as<int32_t>());
+        PB_LAUNCH_CHECK(ctx);
+    }
+    pb_timer_end(ctx, PB_T_PROBE);
+    return PB_OK;
+}
+
+__global__ void find_write_kernel(IndexView iv, const uint32_t *__restrict__ keys, int64_t n, const int64_t *__restrict__ pos_off,
+                                  int64_t cap_each, int32_t *__restrict__ out)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const uint32_t key = keys[q];
+    uint32_t s, bl, c;
+    probe_one(iv, key, &s, &bl, &c);
+    int64_t w = 0;
+    for (uint32_t t = 0; t < bl && w < cap_each; ++t) {
+        if (iv.key && __ldg(iv.key + s + t) != key) continue;
+        out[pos_off[q] + w] = __ldg(iv.pos + s + t);
+        ++w;
+    }
+}
+
+extern "C" int pb_index_find_batch(pb_ctx *ctx, const pb_index *ix, const uint32_t *keys, int64_t n, int64_t *count, int32_t *pos,
+                                   const int64_t *pos_off, int64_t cap_each)
+{
+    if (!ctx || !ix || n < 0 || (n && (!keys || !count))) return pb_fail(ctx, PB_ERR_ARG, "pb_index_find_batch: bad argument");
+    if (!n) return PB_OK;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf d_keys, d_cnt;
+    PB_TRY(d_keys.alloc(ctx, (size_t)n * 4));
+    PB_TRY(d_cnt.alloc(ctx, (size_t)n * 4));
+    PB_TRY(pb_h2d(ctx, d_keys.p, keys, (size_t)n * 4));
+    IndexView iv = view_of(ix);
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    probe_count_kernel<<<grid, 256, 0, ctx->stream>>>(iv, d_keys.as<uint32_t>(), n, d_cnt.as<uint32_t>());
+    PB_LAUNCH_CHECK(ctx);
+    std::vector<uint32_t> cnt((size_t)n);
+    PB_TRY(pb_d2h(ctx, cnt.data(), d_cnt.p, (size_t)n * 4));
+    PB_TRY(pb_sync(ctx));
+    int64_t maxend = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        count[i] = cnt[i];
+        if (pos && pos_off) maxend = std::max<int64_t>(maxend, pos_off[i] + std::min<int64_t>(cnt[i], cap_each));
+    }
+    if (pos && pos_off && maxend > 0) {
+        DevBuf d_off, d_out;
+        PB_TRY(d_off.alloc(ctx, (size_t)n * 8));
+        PB_TRY(d_out.alloc_zero(ctx, (size_t)maxend * 4));
+        PB_TRY(pb_h2d(ctx, d_off.p, pos_off, (size_t)n * 8));
+        find_write_kernel<<<grid, 256, 0, ctx->stream>>>(iv, d_keys.as<uint32_t>(), n, d_off.as<int64_t>(), cap_each, d_out.as<int32_t>());
+        PB_LAUNCH_CHECK(ctx);
+        std::vector<int32_t> host((size_t)maxend);
+        PB_TRY(pb_d2h(ctx, host.data(), d_out.p, (size_t)maxend * 4));
+        PB_TRY(pb_sync(ctx));
+        for (int64_t i = 0; i < n; ++i) {
+            int64_t m = std::min<int64_t>(cnt[i], cap_each);
+            if (m > 0) memcpy(pos + pos_off[i], host.data() + pos_off[i], (size_t)m * 4);
+        }
+    }
+    return PB_OK;
+}

@@ -1,0 +1,409 @@
+// pb_seq.cu -- L0: sequence representation on the device (replaces src/dna_seq.h).
+//
+// Ingest kernel: text (or the reference's packed .bin records) -> padded line in three views
+// (2-bit packed bytes, hi/lo bit planes).  One warp produces one 32-base word of the line:
+// coalesced 1 B/base reads, ballot-built plane words, shuffle-combined packed words.
+#include <algorithm>
+
+#include "pb_internal.cuh"
+
+// C2I, dna_seq.h:21 : A->0 C->1 G->2 anything else->3
+__device__ __forceinline__ uint32_t c2i(uint32_t ch) { return ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : 3u; }
+
+struct IngestSrc {
+    const uint8_t *text;    // device blob
+    const int64_t *toff;    // [n] offset of element 0 (text mode) or of the record's first body byte (packed mode)
+    const int32_t *tstride; // [n] +1/-1, or NULL
+    int packed;             // 1: source is 4-bases-per-byte records (dna_seq.h:113-127)
+};
+
+__global__ void __launch_bounds__(256)
+ingest_kernel(IngestSrc src, const int64_t *__restrict__ base, const int32_t *__restrict__ len, int64_t n,
+              int64_t nwords, uint32_t *__restrict__ hi, uint32_t *__restrict__ lo, uint32_t *__restrict__ packed,
+              uint32_t *__restrict__ flags)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = warp0; w < nwords; w += nwarps) {
+        const int64_t g0 = w * 32;
+        // sequence that owns this word: largest i with base[i] <= g0 (bases are multiples of 32)
+        int64_t a = 0, b = n;
+        while (b - a > 1) {
+            int64_t m = (a + b) >> 1;
+            if (base[m] <= g0) a = m; else b = m;
+        }
+        const int64_t rel = g0 + lane - base[a];
+        const bool valid = n > 0 && rel < (int64_t)len[a];
+        uint32_t code = 3u;
+        bool irregular = false;
+        if (valid) {
+            if (src.packed) {
+                uint32_t byte = src.text[src.toff[a] + (rel >> 2)];
+                code = (byte >> (6 - 2 * (rel & 3))) & 3u;
+            } else {
+                int64_t st = src.tstride ? (int64_t)src.tstride[a] : 1;
+                uint32_t ch = src.text[src.toff[a] + rel * st];
+                code = c2i(ch);
+                irregular = !(ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T');
+            }
+        }
+        const uint32_t whi = __ballot_sync(0xffffffffu, code & 2u);
+        const uint32_t wlo = __ballot_sync(0xffffffffu, code & 1u);
+        const uint32_t irr = __ballot_sync(0xffffffffu, irregular);
+        // packed: byte (lane>>2) of the 8 output bytes; first base of a byte in bits 7:6; bytes little-endian in u32
+        uint32_t v = code << (6 - 2 * (lane & 3));
+        v <<= 8 * ((lane >> 2) & 3);
+        v |= __shfl_xor_sync(0xffffffffu, v, 1);
+        v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        v |= __shfl_xor_sync(0xffffffffu, v, 4);
+        v |= __shfl_xor_sync(0xffffffffu, v, 8);
+        if (lane == 0) {
+            hi[w] = whi;
+            lo[w] = wlo;
+            packed[2 * w] = v;
+            if (irr) atomicOr(&flags[a], PB_FLAG_IRREGULAR);
+        }
+        if (lane == 16) packed[2 * w + 1] = v;
+    }
+}
+
+int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, const int32_t *h_len,
+                    const int32_t *h_stride, int64_t n, bool packed_src, pb_seqset **out)
+{
+    pb_seqset *s = new pb_seqset();
+    s->ctx = ctx;
+    s->n = n;
+    s->base.resize(n + 1);
+    s->len.assign(h_len, h_len + n);
+    int64_t g = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (h_len[i] < 0) { delete s; return pb_fail(ctx, PB_ERR_ARG, "sequence %lld has negative length", (long long)i); }
+        s->base[i] = g;
+        g = (g + h_len[i] + 16 + 31) & ~(int64_t)31;
+    }
+    s->base[n] = g;
+    s->total = ((g + 127) & ~(int64_t)127) + 128;
+    const int64_t nw = s->nwords();
+    int r;
+#define TRYS(x) do { r = (x); if (r != PB_OK) { delete s; return r; } } while (0)
+    TRYS(s->d_base.alloc(ctx, (n + 1) * sizeof(int64_t)));
+    TRYS(s->d_len.alloc(ctx, (n + 1) * sizeof(int32_t)));
+    TRYS(s->d_flags.alloc_zero(ctx, (n + 1) * sizeof(uint32_t)));
+    TRYS(s->d_hi.alloc(ctx, (nw + 4) * sizeof(uint32_t)));
+    TRYS(s->d_lo.alloc(ctx, (nw + 4) * sizeof(uint32_t)));
+    TRYS(s->d_packed.alloc(ctx, (2 * nw + 8) * sizeof(uint32_t)));
+    DevBuf d_toff, d_stride;
+    TRYS(d_toff.alloc(ctx, (n + 1) * sizeof(int64_t)));
+    TRYS(pb_h2d(ctx, s->d_base.p, s->base.data(), (n + 1) * sizeof(int64_t)));
+    TRYS(pb_h2d(ctx, s->d_len.p, s->len.data(), n * sizeof(int32_t)));
+    TRYS(pb_h2d(ctx, d_toff.p, h_toff, n * sizeof(int64_t)));
+    if (h_stride) {
+        TRYS(d_stride.alloc(ctx, (n + 1) * sizeof(int32_t)));
+        TRYS(pb_h2d(ctx, d_stride.p, h_stride, n * sizeof(int32_t)));
+    }
+    // guard words past the line read as code 3
+    cudaMemsetAsync(s->d_hi.as<uint32_t>() + nw, 0xff, 4 * sizeof(uint32_t), ctx->stream);
+    cudaMemsetAsync(s->d_lo.as<uint32_t>() + nw, 0xff, 4 * sizeof(uint32_t), ctx->stream);
+    cudaMemsetAsync(s->d_packed.as<uint32_t>() + 2 * nw, 0xff, 8 * sizeof(uint32_t), ctx->stream);
+    IngestSrc src;
+    src.text = (const uint8_t *)d_text;
+    src.toff = d_toff.as<int64_t>();
+    src.tstride = h_stride ? d_stride.as<int32_t>() : nullptr;
+    src.packed = packed_src ? 1 : 0;
+    int64_t blocks = std::min<int64_t>((nw + 7) / 8, (int64_t)ctx->sm_count * 16);
+    if (blocks < 1) blocks = 1;
+    pb_timer_begin(ctx, PB_T_INGEST);
+    ingest_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(src, s->d_base.as<int64_t>(), s->d_len.as<int32_t>(), n, nw,
+                                                             s->d_hi.as<uint32_t>(), s->d_lo.as<uint32_t>(),
+                                                             s->d_packed.as<uint32_t>(), s->d_flags.as<uint32_t>());
+    pb_timer_end(ctx, PB_T_INGEST);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { delete s; return pb_fail(ctx, PB_ERR_CUDA, "ingest launch failed: %s", cudaGetErrorString(e)); }
+    s->flags.resize(n);
+    TRYS(pb_d2h(ctx, s->flags.data(), s->d_flags.p, n * sizeof(uint32_t)));
+    TRYS(pb_sync(ctx)); // d_toff/d_stride are released after the kernel (stream-ordered) but flags are needed now
+#undef TRYS
+    *out = s;
+    return PB_OK;
+}
+
+// text blob extent touched by the views: [lo, hi)
+static bool text_extent(const int64_t *off, const int32_t *len, const int32_t *stride, int64_t n, int64_t *lo, int64_t *hi)
+{
+    int64_t a = INT64_MAX, b = INT64_MIN;
+    for (int64_t i = 0; i < n; ++i) {
+        if (len[i] <= 0) continue;
+        int64_t st = stride ? stride[i] : 1;
+        if (st != 1 && st != -1) return false;
+        int64_t first = off[i], last = off[i] + (int64_t)(len[i] - 1) * st;
+        a = std::min(a, std::min(first, last));
+        b = std::max(b, std::max(first, last) + 1);
+    }
+    if (a > b) { a = 0; b = 0; }
+    *lo = a; *hi = b;
+    return true;
+}
+
+extern "C" int pb_seqset_from_text(pb_ctx *ctx, const char *text, const int64_t *off, const int32_t *len,
+                                   const int32_t *stride, int64_t n, pb_seqset **out)
+{
+    if (!ctx || !out || n < 0 || (n > 0 && (!text || !off || !len))) return pb_fail(ctx, PB_ERR_ARG, "pb_seqset_from_text: bad argument");
+    *out = nullptr;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int64_t lo, hi;
+    if (!text_extent(off, len, stride, n, &lo, &hi)) return pb_fail(ctx, PB_ERR_ARG, "stride must be +1 or -1");
+    DevBuf d_text;
+    PB_TRY(d_text.alloc(ctx, (size_t)(hi - lo) + 16));
+    pb_timer_begin(ctx, PB_T_H2D);
+    PB_TRY(pb_h2d(ctx, d_text.p, text + lo, (size_t)(hi - lo)));
+    pb_timer_end(ctx, PB_T_H2D);
+    std::vector<int64_t> rel(off, off + n);
+    for (auto &x : rel) x -= lo;
+    return pb_seqset_build(ctx, d_text.p, rel.data(), len, stride, n, false, out);
+}
+
+extern "C" int pb_seqset_from_device_text(pb_ctx *ctx, const void *d_text, size_t text_bytes, const int64_t *off,
+                                          const int32_t *len, const int32_t *stride, int64_t n, pb_seqset **out)
+{
+    if (!ctx || !out || n < 0 || (n > 0 && (!d_text || !off || !len))) return pb_fail(ctx, PB_ERR_ARG, "pb_seqset_from_device_text: bad argument");
+    *out = nullptr;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int64_t lo, hi;
+    if (!text_extent(off, len, stride, n, &lo, &hi)) return pb_fail(ctx, PB_ERR_ARG, "stride must be +1 or -1");
+    if (lo < 0 || (size_t)hi > text_bytes) return pb_fail(ctx, PB_ERR_ARG, "views reach outside the device text blob");
+    return pb_seqset_build(ctx, d_text, off, len, stride, n, false, out);
+}
+
+extern "C" int pb_seqset_from_bin(pb_ctx *ctx, const uint8_t *bin, size_t nbytes, int min_excl, int max_excl,
+                                  pb_seqset **out)
+{
+    if (!ctx || !out || (!bin && nbytes)) return pb_fail(ctx, PB_ERR_ARG, "pb_seqset_from_bin: bad argument");
+    *out = nullptr;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    // record walk, spaced_seed.cpp:330-342: u32 length, ceil(len/4) body bytes, records back to back
+    std::vector<int64_t> off;
+    std::vector<int32_t> len;
+    size_t p = 0;
+    while (p + 4 <= nbytes) {
+        uint32_t l;
+        memcpy(&l, bin + p, 4);
+        size_t body = ((size_t)l + 3) / 4;
+        if (p + 4 + body > nbytes) return pb_fail(ctx, PB_ERR_ARG, "truncated .bin record at byte %zu", p);
+        if ((int64_t)l > min_excl && (int64_t)l < max_excl) {
+            off.push_back((int64_t)p + 4);
+            len.push_back((int32_t)l);
+        }
+        p += 4 + body;
+    }
+    DevBuf d_bin;
+    PB_TRY(d_bin.alloc(ctx, nbytes + 16));
+    pb_timer_begin(ctx, PB_T_H2D);
+    PB_TRY(pb_h2d(ctx, d_bin.p, bin, nbytes));
+    pb_timer_end(ctx, PB_T_H2D);
+    return pb_seqset_build(ctx, d_bin.p, off.data(), len.data(), nullptr, (int64_t)off.size(), true, out);
+}
+
+extern "C" void pb_seqset_free(pb_seqset *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    delete s;
+}
+
+extern "C" int64_t pb_seqset_count(const pb_seqset *s) { return s ? s->n : 0; }
+extern "C" int32_t pb_seqset_length(const pb_seqset *s, int64_t i) { return (s && i >= 0 && i < s->n) ? s->len[i] : -1; }
+
+// ---- decode back to text (bin2text, dna_seq.h:133-145) and raw packed access --------------------------------
+
+__global__ void unpack_text_kernel(const uint8_t *__restrict__ packed, int64_t first_base, int64_t count, char *out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    int64_t g = first_base + i;
+    uint32_t code = (packed[g >> 2] >> (6 - 2 * (g & 3))) & 3u;
+    out[i] = code == 0 ? 'A' : code == 1 ? 'C' : code == 2 ? 'G' : 'T';
+}
+
+extern "C" int pb_seqset_text(pb_ctx *ctx, const pb_seqset *s, int64_t i, char *out, size_t cap)
+{
+    if (!ctx || !s || !out || i < 0 || i >= s->n) return pb_fail(ctx, PB_ERR_ARG, "pb_seqset_text: bad argument");
+    const int64_t L = s->len[i];
+    if (cap <= (size_t)L) return pb_fail(ctx, PB_ERR_ARG, "pb_seqset_text: cap %zu <= length %lld", cap, (long long)L);
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf d;
+    PB_TRY(d.alloc(ctx, (size_t)L + 16));
+    if (L > 0) {
+        unpack_text_kernel<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(s->d_packed.as<uint8_t>(), s->base[i], L, d.as<char>());
+        PB_LAUNCH_CHECK(ctx);
+        PB_TRY(pb_d2h(ctx, out, d.p, (size_t)L));
+    }
+    PB_TRY(pb_sync(ctx));
+    out[L] = '\0';
+    return PB_OK;
+}
+
+__global__ void mask_tail_kernel(uint8_t *body, int64_t len)
+{ // text2bin zero-pads the last byte (dna_seq.h:147-159); the padded line holds code 3 there
+    if (threadIdx.x == 0 && blockIdx.x == 0 && (len & 3)) body[len >> 2] &= (uint8_t)(0xFF << (8 - 2 * (len & 3)));
+}
+
+extern "C" int pb_seqset_packed(pb_ctx *ctx, const pb_seqset *s, int64_t i, uint8_t *out, size_t cap)
+{
+    if (!ctx || !s || !out || i < 0 || i >= s->n) return pb_fail(ctx, PB_ERR_ARG, "pb_seqset_packed: bad argument");
+    const int64_t L = s->len[i];
+    const size_t nb = (size_t)(L + 3) / 4;
+    if (cap < nb) return pb_fail(ctx, PB_ERR_ARG, "pb_seqset_packed: cap too small");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf d;
+    PB_TRY(d.alloc(ctx, nb + 16));
+    if (nb) {
+        PB_CUDA(ctx, cudaMemcpyAsync(d.p, s->d_packed.as<uint8_t>() + (s->base[i] >> 2), nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        mask_tail_kernel<<<1, 32, 0, ctx->stream>>>(d.as<uint8_t>(), L);
+        PB_LAUNCH_CHECK(ctx);
+        PB_TRY(pb_d2h(ctx, out, d.p, nb));
+    }
+    return pb_sync(ctx);
+}
+
+// ---- dna_seq statics as batched device calls -------------------------------------------------------------
+
+extern "C" int pb_text2bin(pb_ctx *ctx, const char *text, size_t tlen, uint8_t *out, size_t cap, size_t *written)
+{
+    if (!ctx || (!text && tlen) || !out) return pb_fail(ctx, PB_ERR_ARG, "pb_text2bin: bad argument");
+    const size_t blen = 4 + (tlen + 3) / 4;
+    if (cap < blen) return pb_fail(ctx, PB_ERR_ARG, "pb_text2bin: buffer of %zu bytes < record of %zu (dna_seq.h:118 asserts)", cap, blen);
+    int64_t off = 0;
+    int32_t len = (int32_t)tlen;
+    pb_seqset *s = nullptr;
+    PB_TRY(pb_seqset_from_text(ctx, text ? text : "", &off, &len, nullptr, 1, &s));
+    uint32_t l32 = (uint32_t)tlen;
+    memcpy(out, &l32, 4);
+    int r = pb_seqset_packed(ctx, s, 0, out + 4, cap - 4);
+    pb_seqset_free(s);
+    if (written) *written = blen;
+    return r;
+}
+
+extern "C" int pb_bin2text(pb_ctx *ctx, const uint8_t *rec, char *out, size_t cap, size_t *tlen)
+{
+    if (!ctx || !rec || !out) return pb_fail(ctx, PB_ERR_ARG, "pb_bin2text: bad argument");
+    uint32_t l;
+    memcpy(&l, rec, 4);
+    if (cap <= l) return pb_fail(ctx, PB_ERR_ARG, "pb_bin2text: buffer of %zu bytes <= length %u (dna_seq.h:138 asserts)", cap, l);
+    pb_seqset *s = nullptr;
+    PB_TRY(pb_seqset_from_bin(ctx, rec, 4 + ((size_t)l + 3) / 4, -1, INT32_MAX, &s));
+    int r = pb_seqset_text(ctx, s, 0, out, cap);
+    pb_seqset_free(s);
+    if (tlen) *tlen = l;
+    return r;
+}
+
+__global__ void decode_kernel(const uint32_t *__restrict__ codes, int64_t n, char *__restrict__ out)
+{ // dna_seq::decode, dna_seq.h:101-107: byte k of the word holds bases 4k..4k+3, first base in bits 7:6
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 16) return;
+    uint32_t w = codes[i >> 4];
+    int k = (int)(i & 15);
+    uint32_t code = (w >> (8 * (k >> 2) + 6 - 2 * (k & 3))) & 3u;
+    out[i] = code == 0 ? 'A' : code == 1 ? 'C' : code == 2 ? 'G' : 'T';
+}
+
+extern "C" int pb_decode_batch(pb_ctx *ctx, const uint32_t *codes, int64_t n, char *out16)
+{
+    if (!ctx || n < 0 || (n && (!codes || !out16))) return pb_fail(ctx, PB_ERR_ARG, "pb_decode_batch: bad argument");
+    if (!n) return PB_OK;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf dc, dout;
+    PB_TRY(dc.alloc(ctx, n * 4));
+    PB_TRY(dout.alloc(ctx, n * 16));
+    PB_TRY(pb_h2d(ctx, dc.p, codes, n * 4));
+    decode_kernel<<<(unsigned)((n * 16 + 255) / 256), 256, 0, ctx->stream>>>(dc.as<uint32_t>(), n, dout.as<char>());
+    PB_LAUNCH_CHECK(ctx);
+    PB_TRY(pb_d2h(ctx, out16, dout.p, n * 16));
+    return pb_sync(ctx);
+}
+
+__global__ void encode_kernel(const uint8_t *__restrict__ text, int64_t text_len, const int64_t *__restrict__ off, int64_t n,
+                              uint32_t *__restrict__ out)
+{ // dna_seq::encode, dna_seq.h:86-96
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t o = off[i];
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        int64_t p = o + k;
+        uint32_t ch = (p >= 0 && p < text_len) ? text[p] : 0u;
+        w |= c2i(ch) << (8 * (k >> 2) + 6 - 2 * (k & 3));
+    }
+    out[i] = w;
+}
+
+extern "C" int pb_encode_batch(pb_ctx *ctx, const char *text, size_t text_len, const int64_t *off, int64_t n, uint32_t *out)
+{
+    if (!ctx || n < 0 || (n && (!off || !out)) || (!text && text_len)) return pb_fail(ctx, PB_ERR_ARG, "pb_encode_batch: bad argument");
+    if (!n) return PB_OK;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf dt, doff, dout;
+    PB_TRY(dt.alloc(ctx, text_len + 16));
+    PB_TRY(doff.alloc(ctx, n * 8));
+    PB_TRY(dout.alloc(ctx, n * 4));
+    PB_TRY(pb_h2d(ctx, dt.p, text, text_len));
+    PB_TRY(pb_h2d(ctx, doff.p, off, n * 8));
+    encode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dt.as<uint8_t>(), (int64_t)text_len, doff.as<int64_t>(), n, dout.as<uint32_t>());
+    PB_LAUNCH_CHECK(ctx);
+    PB_TRY(pb_d2h(ctx, out, dout.p, n * 4));
+    return pb_sync(ctx);
+}
+
+__global__ void seed_at_kernel(const uint8_t *__restrict__ rec, int64_t rec_bytes, const int32_t *__restrict__ pos, int64_t n,
+                               int quirk, uint32_t *__restrict__ out)
+{ // dna_seq::seed_at, dna_seq.h:62-76
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = pos[i];
+    auto byte_at = [&](int64_t o) -> uint32_t { return (o >= 0 && o < rec_bytes) ? rec[o] : 0u; };
+    uint32_t w = 0;
+    if (quirk && (p & 3) == 0) { // Q-S1: *((unsigned*)(pbin + 4 + pos))
+        for (int k = 0; k < 4; ++k) w |= byte_at(4 + (int64_t)p + k) << (8 * k);
+    } else {
+        const int64_t b0 = 4 + (p >> 2);
+        const unsigned ls = (p & 3) << 1, rs = 8 - ls;
+        for (int k = 0; k < 4; ++k) {
+            uint32_t v = ((byte_at(b0 + k) << ls) | (ls ? (byte_at(b0 + k + 1) >> rs) : 0u)) & 0xFFu;
+            w |= v << (8 * k);
+        }
+    }
+    out[i] = w;
+}
+
+extern "C" int pb_seed_at_batch(pb_ctx *ctx, const uint8_t *rec, size_t rec_bytes, const int32_t *pos, int64_t n, int quirk,
+                                uint32_t *out)
+{
+    if (!ctx || n < 0 || (n && (!rec || !pos || !out))) return pb_fail(ctx, PB_ERR_ARG, "pb_seed_at_batch: bad argument");
+    if (!n) return PB_OK;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf dr, dp, dout;
+    PB_TRY(dr.alloc(ctx, rec_bytes + 16));
+    PB_TRY(dp.alloc(ctx, n * 4));
+    PB_TRY(dout.alloc(ctx, n * 4));
+    PB_TRY(pb_h2d(ctx, dr.p, rec, rec_bytes));
+    PB_TRY(pb_h2d(ctx, dp.p, pos, n * 4));
+    seed_at_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dr.as<uint8_t>(), (int64_t)rec_bytes, dp.as<int32_t>(), n, quirk, dout.as<uint32_t>());
+    PB_LAUNCH_CHECK(ctx);
+    PB_TRY(pb_d2h(ctx, out, dout.p, n * 4));
+    return pb_sync(ctx);
+}
+
+extern "C" uint32_t pb_parse_pattern(const char *pattern)
+{ // spaced_seed.cpp:166-180: '1' -> 'T' (bits 11), anything else -> 'A' (00), padded with A to 16, truncated at 16
+    uint32_t w = 0;
+    if (!pattern) return 0;
+    size_t len = strlen(pattern);
+    if (len > 16) len = 16;
+    for (size_t k = 0; k < len; ++k)
+        if (pattern[k] == '1') w |= 3u << (8 * (k >> 2) + 6 - 2 * (k & 3));
+    return w;
+}

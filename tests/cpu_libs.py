@@ -202,6 +202,32 @@ class Ref:
         L.pbref_locate.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32,
                                    C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
 
+        L.pbref_locator_open.restype = C.c_void_p
+        L.pbref_locator_open.argtypes = [C.c_void_p, C.c_long, C.c_uint32]
+        L.pbref_locator_close.argtypes = [C.c_void_p]
+        L.pbref_locator_run.restype = C.c_int64
+        L.pbref_locator_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int,
+                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+
+    def locator_open(self, ref: np.ndarray, mask: int):
+        """locator.cpp:57-66 (contig + seed map), built once"""
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        return self.lib.pbref_locator_open(ref.ctypes.data, len(ref), mask)
+
+    def locator_close(self, h):
+        self.lib.pbref_locator_close(h)
+
+    def locator_run(self, h, reads, offs, lens, R=0.15, ntrial=50, minlen=500, nthreads=1):
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        nk = int((lens >= minlen).sum())
+        recs = np.zeros(nk, dtype=LOCATE_DTYPE)
+        n = self.lib.pbref_locator_run(h, reads.ctypes.data, offs.ctypes.data, lens.ctypes.data, len(lens), R, ntrial,
+                                       minlen, nthreads, recs.ctypes.data, None, None)
+        assert n == nk
+        return recs
+
     def encode(self, text: bytes) -> int:
         return self.lib.pbref_encode(text + b"\0" * 17)
 

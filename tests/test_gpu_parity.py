@@ -1,0 +1,415 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle and the golden vectors
+(outputs of the unmodified reference).  Bit-exact: these are integer / byte / index results."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import workload
+from cpu_libs import DELETE, INSERT, MATCH
+
+pytestmark = pytest.mark.gpu
+
+MASKS = [0xff3c3ffc, 0xff33f3fc, 0xfff0ccfc, 0x3fcfccf3, 0xffccc3f3, 0xffccf3fc, 0x3fcff3fc, 0x3fcfc3fc]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from pacbioassembly_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def ops_str(ops):
+    return "".join(chr(48 + int(x)) for x in ops)
+
+
+# ---------------------------------------------------------------------------------------------
+# L0
+# ---------------------------------------------------------------------------------------------
+
+def test_codec_golden(ctx, golden, oracle):
+    for e in golden["encode"]:
+        assert int(ctx.encode(e["text"].encode("latin1"))[0]) == e["code"]
+    codes = [e["code"] for e in golden["encode"]]
+    for e, txt in zip(golden["encode"], ctx.decode(codes)):
+        assert txt == e["decoded"].encode("latin1")
+    for p in golden["packed"]:
+        t = p["text"].encode()
+        rec = ctx.text2bin(t)
+        assert rec.hex() == p["bin"]
+        assert ctx.bin2text(rec) == t
+        if p["seed_at"]:
+            pos = list(range(len(p["seed_at"])))
+            assert ctx.seed_at(rec, pos, quirk=True).tolist() == p["seed_at"]
+            assert ctx.seed_at(rec, pos).tolist() == [oracle.encode(t[q:q + 16]) for q in pos]
+    # dna_test.cpp:20-30
+    rec = ctx.text2bin(b"ACGTGTCATCGGATCAACCGGTT")
+    assert len(rec) == 10
+    assert ctx.seed_at(rec, [0, 1, 2, 7]).tolist() == [0x34DAB41B, 0xD068D36E, 0x41A34DBB, 0xAF058D36]
+    with pytest.raises(Exception):
+        ctx.text2bin(b"ACGTACGT", cap=5)  # the reference asserts (dna_seq.h:118)
+
+
+def test_encode_tail_and_nonacgt(ctx, oracle):
+    t = b"ACGTNNacgtXGATTACAGATTACA"
+    offs = list(range(len(t)))
+    got = ctx.encode(t, offs).tolist()
+    assert got == [oracle.encode(t[o:]) for o in offs]
+
+
+def test_seqset_roundtrip_and_views(ctx, oracle):
+    g = workload.reference(5, 1000)
+    txt = g.tobytes()
+    offs = [0, 10, 999, 500, 64]
+    lens = [1000, 33, 1000, 0, 1]
+    strides = [1, 1, -1, 1, 1]
+    s = ctx.seqset(g, offs, lens, strides)
+    assert len(s) == 5
+    assert s.text(0) == txt
+    assert s.text(1) == txt[10:43]
+    assert s.text(2) == txt[::-1]
+    assert s.text(3) == b""
+    assert s.text(4) == txt[64:65]
+    assert s.packed(1) == oracle.text2bin(txt[10:43])[4:]
+    image = b"".join(oracle.text2bin(workload.reference(100 + k, n).tobytes()) for k, n in enumerate((600, 20, 501, 20000, 777)))
+    sb = ctx.seqset_from_bin(image)  # keeps 500 < len < 20000 (spaced_seed.cpp:336)
+    assert len(sb) == 3 and [sb.length(i) for i in range(3)] == [600, 501, 777]
+    assert sb.text(2) == workload.reference(104, 777).tobytes()
+
+
+# ---------------------------------------------------------------------------------------------
+# L1
+# ---------------------------------------------------------------------------------------------
+
+def test_seed_extract_all_positions(ctx, oracle):
+    g = workload.reference(6, 5000)
+    g[100:140] = ord("A")
+    g[777] = ord("N")
+    s = ctx.seqset_one(g)
+    txt = g.tobytes()
+    for mask in (MASKS[0], MASKS[3], 0xFFFFFFFF):
+        got = s.seeds(0, mask)
+        want = np.array([oracle.encode(txt[p:p + 16]) & mask for p in range(len(txt))], dtype=np.uint32)
+        assert (got == want).all()  # the last 15 positions read code 3 past the end (Q-S3)
+    # several sequences in one set: windows never leak into a neighbour
+    parts = [workload.reference(50 + k, n) for k, n in enumerate((17, 512, 31, 1000))]
+    blob = np.concatenate(parts)
+    offs = np.cumsum([0] + [len(p) for p in parts[:-1]])
+    ms = ctx.seqset(blob, offs, [len(p) for p in parts])
+    for k, p in enumerate(parts):
+        t = p.tobytes()
+        want = [oracle.encode(t[q:q + 16]) & MASKS[1] for q in range(len(t))]
+        assert ms.seeds(k, MASKS[1]).tolist() == want
+
+
+def _digest(find_batch, keys):
+    keys = sorted(keys)
+    lists = find_batch(keys)
+    h = hashlib.sha256()
+    for k, lst in zip(keys, lists):
+        h.update(np.array([k, len(lst)] + lst, dtype=np.int64).tobytes())
+    return h.hexdigest()
+
+
+def test_index_golden(ctx, golden, oracle):
+    from test_oracle import golden_index_ref
+    for g in golden["index"]:
+        ref = golden_index_ref(g)
+        s = ctx.seqset_one(ref)
+        ix = ctx.index(s, g["mask"], g["policy"])
+        assert ix.nkeys == g["nkeys"]
+        got = ix.find_batch([x["key"] for x in g["sample"]])
+        assert got == [x["pos"] for x in g["sample"]]
+        txt = ref.tobytes()
+        keys = {oracle.encode(txt[i:i + 16]) & g["mask"] for i in range(len(txt))}
+        keys.discard(0)
+        lists = ix.find_batch(sorted(keys))
+        present = [k for k, l in zip(sorted(keys), lists) if l]
+        assert _digest(ix.find_batch, present) == g["digest"]
+        assert ix.find(0) == []
+        ix.free()
+
+
+def test_index_ref_test_basic(ctx):
+    """test/ref_test.cpp:119-128 through the device index."""
+    txt = b"ACGTAACCGGTTAAACCCGGGTTTTGCAAAAAAAAAAAAAAAA"
+    s = ctx.seqset_one(txt)
+    ix = ctx.index(s, 0xFFFFFFFF, policy=1)
+    sz = len(txt)
+    assert ix.nkeys == sz - 15 - 1
+    keys = ctx.encode(txt, list(range(sz - 16)) + [sz - 15]).tolist()
+    lists = ix.find_batch(keys)
+    assert all(lists[i] for i in range(sz - 16))
+    assert lists[-1] == []
+
+
+def test_index_vs_oracle_large(ctx, oracle):
+    g = workload.reference(41, 300000)
+    g[5000:5600] = ord("T")  # a repeat: one bucket far above the small-bucket sort threshold
+    g[9000:9100] = np.frombuffer(b"AC" * 50, dtype=np.uint8)
+    s = ctx.seqset_one(g)
+    for policy, mask in ((0, MASKS[0]), (0, MASKS[2]), (1, MASKS[4]), (0, 0xFFFFFFFF)):
+        ix = ctx.index(s, mask, policy)
+        oix = oracle.index_build(g, mask, policy)
+        nk, ne = oracle.index_stats(oix)
+        assert (ix.nkeys, ix.nentries) == (nk, ne)
+        rng = np.random.default_rng(policy + mask % 7)
+        probe = rng.integers(0, len(g) - 16, 400).tolist() + [5100, 9010, len(g) - 3, len(g) - 16, 0]
+        txt = g.tobytes()
+        keys = [oracle.encode(txt[i:i + 16]) & mask for i in probe] + [0x12345678 & mask, 0]
+        got = ix.find_batch(keys)
+        for k, lst in zip(keys, got):
+            assert lst == oracle.index_find(oix, k), (policy, hex(mask), hex(k))
+        oracle.index_free(oix)
+        ix.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# L2
+# ---------------------------------------------------------------------------------------------
+
+def check_against(d, want, keys=("ret", "len_a", "len_b", "max_dst", "matlen_a", "matlen_b", "cost", "diag_cost", "nedit")):
+    assert d["ret"] == want["ret"]
+    if want["ret"] >= 0:
+        for k in keys:
+            assert d[k] == want[k], (k, d[k], want[k])
+
+
+def test_aligner_test_cases(ctx):
+    """test/aligner_test.cpp:44-98 through the CUDA aligner."""
+    dna_ref, seg1, seg2, seg3 = b"ACGTAACCGGTT", b"CGTAAGC", b"GTAACGGGTTAA", b"TCGTAAC"
+
+    def edit_tester(ref_elems, d):
+        j = 0
+        for op, val in zip(d["ops"], d["vals"]):
+            if op in (MATCH, INSERT):
+                assert ref_elems[j] == val
+                j += 1
+
+    d = ctx.align(seg1[:6], dna_ref[:7]); assert 6 <= d["ret"] <= 7 and d["cost"] == 2; edit_tester(dna_ref[:7], d)
+    d = ctx.align(seg1[:7], dna_ref[:8]); assert d["ret"] == 7 and d["cost"] == 2; edit_tester(dna_ref[:8], d)
+    d = ctx.align(seg3[:7], dna_ref[:8]); assert d["ret"] == 7 and d["cost"] == 1; edit_tester(dna_ref[:8], d)
+    d = ctx.align(seg1[:7], dna_ref[1:8], a_fwd=False, b_fwd=False)
+    assert d["ret"] == 7 and d["cost"] == 1; edit_tester(dna_ref[1:8][::-1], d)
+    d = ctx.align(seg2, dna_ref[2:12]); assert d["ret"] == 10 and d["cost"] == 1; edit_tester(dna_ref[2:12], d)
+    d = ctx.align(dna_ref[1:10], dna_ref[:10])
+    assert d["ret"] == 10 and d["nedit"] == 10 and d["ops"][0] == INSERT and d["cost"] == 1
+    d = ctx.align(dna_ref[:10], dna_ref[1:10])
+    assert d["ret"] == 9 and d["nedit"] == 10 and d["ops"][0] == DELETE and d["cost"] == 1
+
+
+def test_align_golden(ctx, golden):
+    from pacbioassembly_b200 import PbError
+    n_ok = 0
+    for x in golden["real_align"] + golden["random_align"]:
+        a, b = x["a"].encode("latin1"), x["b"].encode("latin1")
+        maxn, maxm = (26000, 6000) if x["which"] == 0 else (40000, 6000)
+        if set(a + b) - set(b"ACGT"):
+            with pytest.raises(PbError):
+                ctx.align(a, b, x["R"], x["a_fwd"], x["b_fwd"], maxn, maxm)
+            continue
+        d = ctx.align(a, b, x["R"], x["a_fwd"], x["b_fwd"], maxn, maxm)
+        check_against(d, x)
+        if x["ret"] >= 0:
+            assert ops_str(d["ops"]) == x["ops"]
+            assert bytes(d["vals"]).decode("latin1") == x["vals"]
+            n_ok += 1
+    assert n_ok > 80
+
+
+def make_pairs(rng, n, maxlen, rates=(0.0, 0.03, 0.1, 0.2)):
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    A, B = [], []
+    for case in range(n):
+        m = int(rng.integers(1, maxlen))
+        a = rng.integers(0, 4, m)
+        rate = float(rng.choice(rates))
+        u = rng.random(m)
+        out = []
+        for ch, uu in zip(a.tolist(), u.tolist()):
+            if uu < rate * 0.5:
+                out += [int(rng.integers(0, 4)), ch]
+            elif uu < rate * 0.8:
+                continue
+            elif uu < rate:
+                out.append((ch + 1 + int(rng.integers(0, 3))) & 3)
+            else:
+                out.append(ch)
+        extra = int(rng.integers(0, maxlen // 3 + 1)) if case % 3 else 0
+        b = np.array(out + rng.integers(0, 4, extra).tolist(), dtype=np.int64)
+        if case % 5 == 0 and len(b) > 4:
+            b = b[: len(b) - int(rng.integers(0, len(b) // 3))]
+        if len(b) == 0:
+            b = np.array([0])
+        at, bt = acgt[a].tobytes(), acgt[b].tobytes()
+        if case % 2:
+            at, bt = bt, at
+        A.append(at)
+        B.append(bt)
+    return A, B
+
+
+def run_batch_vs_oracle(ctx, oracle, A, B, R, maxn=26000, maxm=6000, fwd=True):
+    a_blob, b_blob = b"".join(A), b"".join(B)
+    a_len, b_len = [len(x) for x in A], [len(x) for x in B]
+    a_off = np.cumsum([0] + a_len[:-1])
+    b_off = np.cumsum([0] + b_len[:-1])
+    if fwd:
+        recs, ops = ctx.align_batch(a_blob, a_off, a_len, b_blob, b_off, b_len, R, maxn, maxm)
+    else:
+        recs, ops = ctx.align_batch(a_blob, a_off + np.array(a_len) - 1, a_len, b_blob, b_off + np.array(b_len) - 1, b_len, R,
+                                    maxn, maxm, a_stride=[-1] * len(A), b_stride=[-1] * len(B))
+    nsucc = 0
+    for i, (a, b) in enumerate(zip(A, B)):
+        w = oracle.align(a, b, R, fwd, fwd, maxn, maxm)
+        for k in ("ret", "len_a", "len_b", "max_dst", "matlen_a", "matlen_b", "cost", "diag_cost", "nedit", "fail_row", "cells"):
+            assert int(recs[k][i]) == w[k], (i, k, int(recs[k][i]), w[k], len(a), len(b))
+        if w["ret"] >= 0:
+            assert (ops[i] == w["ops"]).all(), i
+            nsucc += 1
+    return nsucc
+
+
+def test_align_random_small(ctx, oracle):
+    rng = np.random.default_rng(11)
+    A, B = make_pairs(rng, 400, 300)
+    assert run_batch_vs_oracle(ctx, oracle, A, B, 0.3) > 100
+    assert run_batch_vs_oracle(ctx, oracle, A[:150], B[:150], 0.15, 40000, 6000) > 20
+    assert run_batch_vs_oracle(ctx, oracle, A[:150], B[:150], 0.3, fwd=False) > 20
+    assert run_batch_vs_oracle(ctx, oracle, A[:100], B[:100], 0.05) >= 0
+
+
+def test_align_random_multiword(ctx, oracle):
+    """bands of 1k..4k bits: several words per lane, carries crossing lanes"""
+    rng = np.random.default_rng(12)
+    A, B = make_pairs(rng, 60, 6000, rates=(0.0, 0.05, 0.12))
+    assert run_batch_vs_oracle(ctx, oracle, A, B, 0.3) > 15
+
+
+def test_align_domain_limits(ctx, oracle):
+    """seq_aligner.h:104-107 with the Q-D3 domain: len_a >= maxn or max_dst >= maxm -> -1"""
+    g = workload.reference(77, 3000).tobytes()
+    A, B = [g[:2000], g[:1500], g[:100]], [g[:2100], g[:1500], g[:100]]
+    assert run_batch_vs_oracle(ctx, oracle, A, B, 0.3, maxn=1800, maxm=6000) == 2
+    assert run_batch_vs_oracle(ctx, oracle, A, B, 0.3, maxn=26000, maxm=500) == 2
+    assert run_batch_vs_oracle(ctx, oracle, A, B, 0.3, maxn=50, maxm=10) == 0
+
+
+def test_align_clr_reads_all_band_classes(ctx, oracle):
+    """CLR-like reads against their true locus, 0.5-20 kbp, R=0.3: every band class up to 12 words per lane"""
+    g = workload.reference(31, 400000)
+    lens = np.array([600, 1500, 2500, 3400, 4800, 5200, 6500, 8000, 9900, 12000, 15000, 19999], dtype=np.int32)
+    txt, offs, lens, starts = workload.reads(32, g, lens, 0.05, 0.03, 0.02, nthreads=1)
+    A = [txt[offs[k]: offs[k] + lens[k]].tobytes() for k in range(len(lens))]
+    B = [g[starts[k]:].tobytes()[: int(lens[k] * 1.4) + 50] for k in range(len(lens))]
+    assert run_batch_vs_oracle(ctx, oracle, A, B, 0.3) >= 9
+    assert run_batch_vs_oracle(ctx, oracle, B[:6], A[:6], 0.3) >= 4  # seg_a longer than seg_b: last-column goal
+
+
+# ---------------------------------------------------------------------------------------------
+# locate
+# ---------------------------------------------------------------------------------------------
+
+def test_locate_golden(ctx, golden):
+    from test_oracle import golden_locate_inputs
+    for g in golden["locate"]:
+        ref, txt, offs, lens = golden_locate_inputs(g)
+        rs = ctx.seqset_one(ref)
+        ix = ctx.index(rs, g["mask"])
+        recs, ops = ctx.locate(ix, txt, offs, lens, want_ops=True, R=g["R"])
+        assert len(recs) == len(g["records"])
+        for k, row in enumerate(g["records"]):
+            for n in ("nseq", "found", "j", "pos", "cost", "seg_len", "diag_cost", "matlen_a", "matlen_b", "nedit"):
+                assert int(recs[n][k]) == row[n], (k, n)
+            assert hashlib.sha256(ops[k].tobytes()).hexdigest()[:16] == row["ops_sha"]
+
+
+def locate_vs_oracle(ctx, oracle, ref, txt, offs, lens, mask, R, nthreads=8, **kw):
+    rs = ctx.seqset_one(ref)
+    ix = ctx.index(rs, mask)
+    recs, ops = ctx.locate(ix, txt, offs, lens, want_ops=True, R=R, **kw)
+    oix = oracle.index_build(ref, mask, 0)
+    want, wops = oracle.locate(oix, ref, txt, offs, lens, mask, R=R, nthreads=nthreads, want_ops=True, **kw)
+    oracle.index_free(oix)
+    assert len(recs) == len(want)
+    for n in ("nseq", "found", "j", "pos", "cost", "seg_len", "diag_cost", "matlen_a", "matlen_b", "nedit", "ncand", "cells"):
+        bad = np.nonzero(recs[n] != want[n])[0]
+        assert len(bad) == 0, (n, bad[:5], recs[n][bad[:5]], want[n][bad[:5]])
+    for k in range(len(recs)):
+        assert (ops[k] == wops[k]).all(), k
+    return recs
+
+
+def test_locate_config1(ctx, oracle):
+    """BASELINE config 1 (scaled to CPU-oracle seconds): 1 Mbp reference, reads 500-3000 at 5 % error, two masks, both R"""
+    ref = workload.reference(1, 1_000_000)
+    lens = workload.read_lengths(7, 240, mean=1500.0, sigma_log=0.5, lo=300, hi=3000)
+    txt, offs, lens, _ = workload.reads(8, ref, lens, 0.025, 0.015, 0.01)
+    found = 0
+    for mask, R in ((MASKS[0], 0.15), (MASKS[3], 0.3)):
+        recs = locate_vs_oracle(ctx, oracle, ref, txt, offs, lens, mask, R)
+        found += int(recs["found"].sum())
+    assert found > 200
+
+
+def test_locate_clr_and_edges(ctx, oracle):
+    """CLR error model (ins 9 / del 4 / sub 2 %), R=0.3; plus empty batch, all-short batch, reads at the contig end"""
+    ref = workload.reference(2, 400_000)
+    lens = workload.read_lengths(3, 96, mean=3000.0, sigma_log=0.5, lo=500, hi=9000)
+    txt, offs, lens, _ = workload.reads(3, ref, lens)
+    recs = locate_vs_oracle(ctx, oracle, ref, txt, offs, lens, MASKS[0], 0.3)
+    assert 10 < recs["found"].sum() < len(recs)
+    # reads cut from the very end of the contig: seg_a longer than what is left of the reference
+    tail = ref[-2600:]
+    t2 = np.concatenate([tail[:2000], tail[300:2600], tail[1000:2600], ref[:400]])
+    o2 = np.array([0, 2000, 4300, 5900])
+    l2 = np.array([2000, 2300, 1600, 400], dtype=np.int32)
+    recs = locate_vs_oracle(ctx, oracle, ref, t2, o2, l2, MASKS[0], 0.15)
+    assert len(recs) == 3 and recs["found"].sum() >= 2
+    rs = ctx.seqset_one(ref)
+    ix = ctx.index(rs, MASKS[0])
+    assert len(ctx.locate(ix, np.zeros(0, np.uint8), [], [])) == 0
+    assert len(ctx.locate(ix, ref[:900], [0, 400], [400, 499])) == 0
+    # custom trial count / minimum length
+    recs = locate_vs_oracle(ctx, oracle, ref, txt, offs, lens, MASKS[5], 0.3, ntrial=8, minlen=1000)
+
+
+def test_locate_properties_at_scale(ctx):
+    """Size-independent properties on a batch too large for the CPU oracle: transcripts replay to the right lengths and
+    costs, error-free reads map to their true position with cost 0, and the run is deterministic."""
+    ref = workload.reference(2, 4_600_000)
+    lens = workload.read_lengths(3, 3000, mean=5000.0, sigma_log=0.5, lo=500, hi=19999)
+    txt, offs, lens, starts = workload.reads(3, ref, lens)
+    rs = ctx.seqset_one(ref)
+    ix = ctx.index(rs, MASKS[0])
+    recs, ops = ctx.locate(ix, txt, offs, lens, want_ops=True, R=0.3)
+    recs2 = ctx.locate(ix, txt, offs, lens, R=0.3)
+    for n in recs.dtype.names:
+        assert (recs[n] == recs2[n]).all()
+    f = recs["found"] == 1
+    assert 0.3 < f.mean() < 0.9
+    g = ref.tobytes()
+    for k in np.nonzero(f)[0][:400]:
+        o = ops[k]
+        n_m, n_i, n_d = int((o == MATCH).sum()), int((o == INSERT).sum()), int((o == DELETE).sum())
+        assert n_m + n_d == recs["matlen_a"][k] and n_m + n_i == recs["matlen_b"][k]
+        a = txt[offs[k] + recs["j"][k]: offs[k] + lens[k]]
+        b = ref[recs["pos"][k]: recs["pos"][k] + recs["matlen_b"][k]]
+        i = j = cost = 0
+        for op in o.tolist():
+            if op == MATCH:
+                cost += int(a[i] != b[j]); i += 1; j += 1
+            elif op == INSERT:
+                cost += 1; j += 1
+            else:
+                cost += 1; i += 1
+        assert cost == recs["cost"][k]
+        assert abs(int(recs["pos"][k]) - int(recs["j"][k]) - int(starts[k])) < 0.35 * lens[k]
+    # error-free reads
+    l0 = np.full(64, 2000, dtype=np.int32)
+    t0, o0, l0, s0 = workload.reads(9, ref, l0, 0.0, 0.0, 0.0)
+    r0 = ctx.locate(ix, t0, o0, l0, R=0.15)
+    assert (r0["found"] == 1).all() and (r0["cost"] == 0).all() and (r0["j"] == 0).all()
+    assert (r0["pos"] == s0).all()
