@@ -248,7 +248,7 @@ def main():
 
     def step_device():
         s = ctx.seqset_from_device(d_txt.data_ptr(), d_txt.numel(), offs, lens)
-        job = ctx.locate_run(index, s)
+        job = ctx.locate_run(index, s, R=R)
         recs = job.fetch(recs=recs_host)
         t = ctx.timings()
         state["stats"], state["timings"], state["recs"] = job.stats(), t, recs

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -138,9 +139,12 @@ class Context:
             raise PbError(rc, (self._L.pb_last_error(None) or b"").decode())
         self.h = h
         self.device = device
+        self._children = weakref.WeakSet()  # handles must be released before the context they live in
 
     def close(self):
         if getattr(self, "h", None):
+            for child in list(self._children):
+                child.free()
             self._L.pb_ctx_destroy(self.h)
             self.h = None
 
@@ -326,9 +330,10 @@ class Context:
 class SeqSet:
     def __init__(self, ctx: Context, h):
         self.ctx, self.h = ctx, h
+        ctx._children.add(self)
 
     def free(self):
-        if self.h:
+        if self.h and self.ctx.h:
             self.ctx._L.pb_seqset_free(self.h)
             self.h = None
 
@@ -373,9 +378,10 @@ class Index:
 
     def __init__(self, ctx: Context, h, ref: SeqSet, seq: int):
         self.ctx, self.h, self.ref, self.seq = ctx, h, ref, seq
+        ctx._children.add(self)
 
     def free(self):
-        if self.h:
+        if self.h and self.ctx.h:
             self.ctx._L.pb_index_free(self.h)
             self.h = None
 
@@ -421,9 +427,10 @@ class Index:
 class LocateJob:
     def __init__(self, ctx: Context, h):
         self.ctx, self.h = ctx, h
+        ctx._children.add(self)
 
     def free(self):
-        if self.h:
+        if self.h and self.ctx.h:
             self.ctx._L.pb_locate_job_free(self.h)
             self.h = None
 

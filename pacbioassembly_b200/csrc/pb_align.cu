@@ -325,28 +325,68 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
     res.diag_cost = (a_len <= len_a && a_len <= len_b) ? cii : 0; // locator.cpp:86 (Q-L2)
     if ((double)matlen_b < len_b * (1 - R)) return; // seq_aligner.h:114
 
-    // ---- find_path, seq_aligner.h:214-233: walk the parent planes back from the goal cell
+    // ---- find_path, seq_aligner.h:214-233: walk the parent planes back from the goal cell.
+    // Warp-cooperative: lane r holds the parent words of row i0-r around the path's band position (3 words per
+    // plane), the next 32 rows are prefetched while the current ones are walked, and runs of MATCH along a
+    // diagonal (same band bit, consecutive rows) are found with one ballot and written by as many lanes.
     __syncwarp();
+    auto par_word = [&](int row, int w, int plane) -> uint32_t {
+        if (row < 1 || w < 0 || w >= NW) return 0u;
+        const int L = w / S, s = w - L * S;
+        return __ldcg(par + (size_t)(row - 1) * (2 * T) + plane * T + s * 32 + L);
+    };
     int n = 0;
-    if (lane == 0) {
+    {
         int i = matlen_a, j = matlen_b;
         const int guard = len_a + len_b + 1; // a path can never be longer; keeps a corrupted plane from hanging the GPU
-        while ((i | j) && n < guard && i >= 0 && j >= 0) {
-            int op;
-            if (i == 0) op = PB_INSERT;      // init_cell row 0
-            else if (j == 0) op = PB_DELETE; // init_cell column 0
-            else {
-                const int k = j - i + D, w = k >> 5, L = w / S, s = w % S;
-                const uint32_t *prow = par + (size_t)(i - 1) * (2 * T) + s * 32 + L;
-                if ((__ldcg(prow) >> (k & 31)) & 1u) op = PB_MATCH;
-                else if ((__ldcg(prow + T) >> (k & 31)) & 1u) op = PB_INSERT;
-                else op = PB_DELETE;
+        int cur_i0 = -1, cur_wb = 0, nxt_i0 = -1, nxt_wb = 0;
+        uint32_t cm0 = 0, cm1 = 0, cm2 = 0, ch0 = 0, ch1 = 0, ch2 = 0;
+        uint32_t nm0 = 0, nm1 = 0, nm2 = 0, nh0 = 0, nh1 = 0, nh2 = 0;
+        while ((i | j) != 0 && n < guard) {
+            if (i == 0) { // init_cell row 0: INSERT all the way
+                for (int t = lane; t < j; t += 32) opsrev[n + t] = (uint8_t)PB_INSERT;
+                n += j; j = 0;
+                break;
             }
-            opsrev[n++] = (uint8_t)op;
-            if (op == PB_MATCH) { --i; --j; } else if (op == PB_INSERT) --j; else --i;
+            if (j == 0) { // init_cell column 0: DELETE all the way
+                for (int t = lane; t < i; t += 32) opsrev[n + t] = (uint8_t)PB_DELETE;
+                n += i; i = 0;
+                break;
+            }
+            const int k = j - i + D, w = k >> 5;
+            if (cur_i0 < 0 || cur_i0 - i >= 32 || w < cur_wb || w > cur_wb + 2) {
+                if (nxt_i0 == i && w >= nxt_wb && w <= nxt_wb + 2) {
+                    cur_i0 = nxt_i0; cur_wb = nxt_wb;
+                    cm0 = nm0; cm1 = nm1; cm2 = nm2; ch0 = nh0; ch1 = nh1; ch2 = nh2;
+                } else {
+                    cur_i0 = i; cur_wb = w - 1;
+                    const int row = cur_i0 - lane;
+                    cm0 = par_word(row, cur_wb, 0); cm1 = par_word(row, cur_wb + 1, 0); cm2 = par_word(row, cur_wb + 2, 0);
+                    ch0 = par_word(row, cur_wb, 1); ch1 = par_word(row, cur_wb + 1, 1); ch2 = par_word(row, cur_wb + 2, 1);
+                }
+                nxt_i0 = cur_i0 - 32; nxt_wb = w - 1;
+                const int row = nxt_i0 - lane;
+                nm0 = par_word(row, nxt_wb, 0); nm1 = par_word(row, nxt_wb + 1, 0); nm2 = par_word(row, nxt_wb + 2, 0);
+                nh0 = par_word(row, nxt_wb, 1); nh1 = par_word(row, nxt_wb + 1, 1); nh2 = par_word(row, nxt_wb + 2, 1);
+            }
+            const int r0 = cur_i0 - i; // lane that holds the current row
+            const int x = w - cur_wb;
+            const uint32_t mw = x == 0 ? cm0 : (x == 1 ? cm1 : cm2);
+            const uint32_t B = __ballot_sync(FULL, (mw >> (k & 31)) & 1u) >> r0; // bit t: cell (i-t, j-t) is MATCH
+            int run = (~B) ? __ffs(~B) - 1 : 32;
+            run = min(min(run, 32 - r0), min(i, j));
+            if (run > 0) {
+                if (lane < run) opsrev[n + lane] = (uint8_t)PB_MATCH;
+                n += run; i -= run; j -= run;
+                continue;
+            }
+            const uint32_t hw = x == 0 ? ch0 : (x == 1 ? ch1 : ch2);
+            const uint32_t hb = (__shfl_sync(FULL, hw, r0) >> (k & 31)) & 1u;
+            if (lane == 0) opsrev[n] = (uint8_t)(hb ? PB_INSERT : PB_DELETE);
+            ++n;
+            if (hb) --j; else --i;
         }
     }
-    n = __shfl_sync(FULL, n, 0);
     __syncwarp();
     if (ops_out)
         for (int k = lane; k < n; k += 32) ops_out[k] = __ldcg(opsrev + (n - 1 - k));
