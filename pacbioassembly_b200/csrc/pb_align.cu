@@ -142,6 +142,94 @@ struct AlnRes {
     long long cells;
 };
 
+// multi-word add helpers: the carry chain lives in the PTX condition code between consecutive statements
+__device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t addc_cc(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t addc(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+
+// One band row for the S words of this lane.  pl points at this lane's first Eq word of the row's plane, sh is the
+// row's bit offset inside those words; prow is this lane's column of the row's parent block.  Returns the D0 word of
+// slot sd (the main diagonal lives there in one lane); leaves the row's vertical deltas in Vp/Vn.
+template <int S>
+__device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S], const uint32_t (&force)[S], uint32_t (&Vp)[S],
+                                             uint32_t (&Vn)[S], const uint32_t *__restrict__ pl, unsigned sh, int lane, int nst,
+                                             int sd, uint32_t *__restrict__ prow)
+{
+    constexpr int T = 32 * S;
+    // phase A: slide the band one bit (across words and lanes), fetch Eq, block add with carry-in 0
+    uint32_t nx = __shfl_down_sync(FULL, (Hp[0] & 1u) | ((Hn[0] & 1u) << 1), 1);
+    if (lane == 31) nx = 1u;
+    uint32_t Eq[S], x[S], sum[S];
+    uint32_t plw = pl[0];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const uint32_t hp_hi = (s + 1 < S) ? Hp[s + 1] : (nx & 1u);
+        const uint32_t hn_hi = (s + 1 < S) ? Hn[s + 1] : (nx >> 1);
+        Hp[s] = __funnelshift_r(Hp[s], hp_hi, 1) | force[s];
+        Hn[s] = __funnelshift_r(Hn[s], hn_hi, 1) & ~force[s];
+        const uint32_t nxt = pl[s + 1];
+        Eq[s] = __funnelshift_r(plw, nxt, sh);
+        plw = nxt;
+        x[s] = Eq[s] & Hp[s];
+    }
+    sum[0] = add_cc(x[0], Hp[0]);
+#pragma unroll
+    for (int s = 1; s < S; ++s) sum[s] = addc_cc(x[s], Hp[s]);
+    const uint32_t carry = addc(0u, 0u);
+    uint32_t ones = sum[0];
+#pragma unroll
+    for (int s = 1; s < S; ++s) ones &= sum[s];
+    const uint32_t G = __ballot_sync(FULL, carry);
+    const uint32_t P = __ballot_sync(FULL, ones == 0xffffffffu);
+    const uint32_t cin = ((((G | P) + G) ^ P) >> lane) & 1u; // carry into this lane's block
+    sum[0] = add_cc(sum[0], cin);
+#pragma unroll
+    for (int s = 1; s < S; ++s) sum[s] = addc_cc(sum[s], 0u);
+
+    // phase B: vertical deltas, D0, MATCH plane
+    uint32_t d0w = 0u;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const uint32_t Xv = (sum[s] ^ Hp[s]) | Eq[s];
+        Vp[s] = Hn[s] | ~(Xv | Hp[s]);
+        Vn[s] = Hp[s] & Xv;
+        const uint32_t D0 = Xv | Hn[s];
+        if (s < nst) prow[s * 32] = Eq[s] | ~D0;
+        if (s == sd) d0w = D0;
+    }
+    uint32_t pv = __shfl_up_sync(FULL, (Vp[S - 1] >> 31) | ((Vn[S - 1] >> 31) << 1), 1);
+    if (lane == 0) pv = 1u; // vin = +1 at the band's left edge (and at column 0)
+
+    // phase C: new horizontal deltas, INSERT plane
+    uint32_t pprev = pv << 31, nprev = (pv >> 1) << 31; // bit 31 = delta entering this word from the left
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const uint32_t vps = __funnelshift_l(pprev, Vp[s], 1), vns = __funnelshift_l(nprev, Vn[s], 1);
+        pprev = Vp[s];
+        nprev = Vn[s];
+        const uint32_t Xh = Eq[s] | Hn[s];
+        Hp[s] = vns | ~(Xh | vps);
+        Hn[s] = vps & Xh;
+        if (s < nst) prow[T + s * 32] = Hp[s];
+    }
+    return d0w;
+}
+
 template <int S>
 __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_len, const SeqView &B, int64_t b_bit, int b_len,
                                        double R, int maxn, int maxm, uint32_t *__restrict__ planes, int PW,
@@ -200,88 +288,58 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
         force[s] = f;
     }
     const int wd = D >> 5, Ld = wd / S, sd = wd % S; // owner of the main-diagonal bit k = D
+    const int nst = min(max(NW - lane * S, 0), S);      // band words of this lane that carry real cells
 
-    int cii = 0;                          // cost(i,i)
+    int cii = 0;                          // cost(i,i), warp-uniform, advanced once per 32-row block
     int colc = 0, colbest = 0, col_i = 0; // cost(i,len_b) tracking when len_a > len_b
     int fail_row = 0;
-    uint32_t awin_hi = 0, awin_lo = 0;
     int rows_done = 0;
+    uint32_t Vp[S], Vn[S];
 
-    for (int i = 1; i <= len_a; ++i) {
-        const int t = (i - 1) & 31;
-        if (t == 0) { // next 32 bases of seg_a (warp-uniform loads)
-            awin_hi = load_window(A.hi, A.nwords, a_bit + i - 1);
-            awin_lo = load_window(A.lo, A.nwords, a_bit + i - 1);
+    // ---- rows 1..min(len_a,len_b) in blocks of 32: the early-failure test (seq_aligner.h:185) is evaluated once
+    // per block from the block's 32 diagonal D0 bits; a failing block reports its first failing row exactly.
+    const int nfast = min(len_a, len_b);
+    for (int i0 = 1; i0 <= nfast; i0 += 32) {
+        const int tmax = min(32, nfast - i0 + 1);
+        const uint32_t awh = load_window(A.hi, A.nwords, a_bit + i0 - 1); // next 32 bases of seg_a (warp-uniform)
+        const uint32_t awl = load_window(A.lo, A.nwords, a_bit + i0 - 1);
+        const int thr = (int)((i0 + lane) * R); // cost > i*R  <=>  cost > floor(i*R) for an integer cost
+        const uint32_t *plq = planes + ((i0 - 1) >> 5) + lane * S;
+        uint32_t *prow = par + (size_t)(i0 - 1) * (2 * T) + lane;
+        uint32_t hist = 0u;
+        for (int t = 0; t < tmax; ++t) {
+            const int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
+            const uint32_t d0w = row_step<S>(Hp, Hn, force, Vp, Vn, plq + ca * PW, (unsigned)t, lane, nst, sd, prow);
+            hist |= ((d0w >> (D & 31)) & 1u) << t; // meaningful in the diagonal's owner lane
+            prow += 2 * T;
         }
-        const int ca = (int)(((awin_hi >> t) & 1u) * 2u + ((awin_lo >> t) & 1u));
-        const uint32_t *pl = planes + ca * PW + ((i - 1) >> 5) + lane * S;
-        uint32_t *prow = par + (size_t)(i - 1) * (2 * T);
-
-        // phase A: slide the band (1-bit right shift across words and lanes), fetch Eq, block add with carry-in 0
-        uint32_t nx = __shfl_down_sync(FULL, (Hp[0] & 1u) | ((Hn[0] & 1u) << 1), 1);
-        if (lane == 31) nx = 1u;
-        uint32_t Eq[S], sum[S];
-        uint32_t carry = 0u, ones = 0xffffffffu;
-        uint32_t plw = pl[0];
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const uint32_t hp_hi = (s + 1 < S) ? Hp[s + 1] : (nx & 1u);
-            const uint32_t hn_hi = (s + 1 < S) ? Hn[s + 1] : (nx >> 1);
-            Hp[s] = __funnelshift_r(Hp[s], hp_hi, 1) | force[s];
-            Hn[s] = __funnelshift_r(Hn[s], hn_hi, 1) & ~force[s];
-            const uint32_t nxt = pl[s + 1];
-            Eq[s] = __funnelshift_r(plw, nxt, t);
-            plw = nxt;
-            const uint32_t x = Eq[s] & Hp[s];
-            const uint32_t s1 = x + Hp[s];
-            const uint32_t s2 = s1 + carry;
-            carry = (uint32_t)(s1 < x) | (uint32_t)(s2 < s1);
-            sum[s] = s2;
-            ones &= s2;
-        }
-        const uint32_t G = __ballot_sync(FULL, carry);
-        const uint32_t P = __ballot_sync(FULL, ones == 0xffffffffu);
-        uint32_t cin = ((((G | P) + G) ^ P) >> lane) & 1u; // carry into this lane's block
-
-        // phase B: vertical deltas, D0, MATCH plane
-        uint32_t Vp[S], Vn[S];
-        uint32_t d0w = 0u;
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const uint32_t v = sum[s] + cin;
-            cin &= (uint32_t)(v == 0u);
-            const uint32_t Xv = (v ^ Hp[s]) | Eq[s];
-            Vp[s] = Hn[s] | ~(Xv | Hp[s]);
-            Vn[s] = Hp[s] & Xv;
-            const uint32_t D0 = Xv | Hn[s];
-            if (lane * S + s < NW) prow[s * 32 + lane] = Eq[s] | ~D0;
-            if (s == sd) d0w = D0;
-        }
-        uint32_t pv = __shfl_up_sync(FULL, (Vp[S - 1] >> 31) | ((Vn[S - 1] >> 31) << 1), 1);
-        if (lane == 0) pv = 1u; // vin = +1 at the band's left edge (and at column 0)
-
-        // phase C: new horizontal deltas, INSERT plane
-        uint32_t pin = pv & 1u, nin = pv >> 1;
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const uint32_t vps = (Vp[s] << 1) | pin, vns = (Vn[s] << 1) | nin;
-            pin = Vp[s] >> 31;
-            nin = Vn[s] >> 31;
-            const uint32_t Xh = Eq[s] | Hn[s];
-            Hp[s] = vns | ~(Xh | vps);
-            Hn[s] = vps & Xh;
-            if (lane * S + s < NW) prow[T + s * 32 + lane] = Hp[s];
-        }
-
-        const uint32_t d0bit = (__shfl_sync(FULL, d0w, Ld) >> (D & 31)) & 1u;
-        cii += 1 - (int)d0bit;
-        rows_done = i;
-        if (i > 10 && i <= len_b && (double)cii > i * R) { // seq_aligner.h:185; cell unwritten for i > len_b reads 0 (Q-D2)
-            fail_row = i;
+        hist = __shfl_sync(FULL, hist, Ld);
+        const int cdiag = cii + (lane + 1) - __popc(hist & (0xffffffffu >> (31 - lane))); // cost(i0+lane, i0+lane)
+        const uint32_t badm = __ballot_sync(FULL, lane < tmax && i0 + lane > 10 && cdiag > thr);
+        if (badm) {
+            fail_row = i0 + __ffs(badm) - 1;
+            rows_done = fail_row;
             break;
         }
-        if (i == len_b) { colc = colbest = cii; col_i = i; }
-        if (i > len_b) { // vertical delta at column len_b (only when len_a > len_b)
+        cii += tmax - __popc(hist & (0xffffffffu >> (32 - tmax)));
+        rows_done = i0 + tmax - 1;
+    }
+
+    // ---- rows len_b+1..len_a (only when seg_a outruns seg_b): no failure test there (the cell is never written,
+    // Q-D2); follow cost(i, len_b) down the last column through the vertical deltas
+    if (!fail_row && len_a > len_b) {
+        colc = colbest = cii;
+        col_i = len_b;
+        uint32_t awh = 0u, awl = 0u;
+        for (int i = len_b + 1; i <= len_a; ++i) {
+            const int t = (i - 1) & 31;
+            if (t == 0 || i == len_b + 1) {
+                awh = load_window(A.hi, A.nwords, a_bit + (i - 1 - t));
+                awl = load_window(A.lo, A.nwords, a_bit + (i - 1 - t));
+            }
+            const int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
+            row_step<S>(Hp, Hn, force, Vp, Vn, planes + ca * PW + ((i - 1) >> 5) + lane * S, (unsigned)t, lane, nst, sd,
+                        par + (size_t)(i - 1) * (2 * T) + lane);
             const int k = len_b - i + D, wk = k >> 5, Lk = wk / S, sk = wk % S;
             uint32_t vpw = 0u, vnw = 0u;
 #pragma unroll
@@ -291,6 +349,7 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
             vnw = __shfl_sync(FULL, vnw, Lk);
             colc += (int)((vpw >> (k & 31)) & 1u) - (int)((vnw >> (k & 31)) & 1u);
             if (colc < colbest) { colbest = colc; col_i = i; }
+            rows_done = i;
         }
     }
     res.cells = cells_upto(rows_done, D, len_b);
@@ -586,14 +645,22 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
 {
     if (plans.empty()) return PB_OK;
     const size_t budget = scratch_budget(ctx);
-    // geometry per class, one scratch buffer reused by the (stream-ordered) launches
+    // geometry per class; every class gets its own scratch region so that the launches can overlap
     std::map<int, LaunchGeom> geoms;
     size_t need = 0;
     for (auto &kv : plans) {
         LaunchGeom g;
         PB_TRY(plan_launch(ctx, kClasses[kv.first], kv.second, locate, budget, &g));
         geoms[kv.first] = g;
-        need = std::max(need, (size_t)g.blocks * ALIGN_WPB * g.slot_words * 4);
+        need += (size_t)g.blocks * ALIGN_WPB * g.slot_words * 4;
+    }
+    if (need > budget) { // shrink every grid by the same factor (at least one CTA each)
+        const double f = (double)budget / (double)need;
+        need = 0;
+        for (auto &kv : geoms) {
+            kv.second.blocks = std::max(1, (int)(kv.second.blocks * f));
+            need += (size_t)kv.second.blocks * ALIGN_WPB * kv.second.slot_words * 4;
+        }
     }
     DevBuf scratch, d_order, d_queue;
     PB_TRY(scratch.alloc(ctx, need + 256));
@@ -601,23 +668,44 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
     for (auto &kv : plans) nitems += kv.second.items.size();
     PB_TRY(d_order.alloc(ctx, nitems * 4 + 16));
     PB_TRY(d_queue.alloc_zero(ctx, (size_t)plans.size() * 4 + 16));
-    size_t off = 0;
+    {
+        std::vector<int32_t> all;
+        all.reserve(nitems);
+        for (auto it = plans.rbegin(); it != plans.rend(); ++it) all.insert(all.end(), it->second.items.begin(), it->second.items.end());
+        PB_TRY(pb_h2d(ctx, d_order.p, all.data(), nitems * 4));
+    }
+    // one stream per band class: a class with few, long alignments no longer leaves the other SMs idle
+    while (ctx->aux_streams.size() < plans.size()) {
+        cudaStream_t st;
+        cudaEvent_t ev;
+        PB_CUDA(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        PB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->aux_streams.push_back(st);
+        ctx->aux_events.push_back(ev);
+    }
+    if (!ctx->fork_event) PB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+    PB_CUDA(ctx, cudaEventRecord(ctx->fork_event, ctx->stream));
+    size_t off = 0, soff = 0;
     int ci = 0;
     // widest band first: those alignments are the longest running
     for (auto it = plans.rbegin(); it != plans.rend(); ++it, ++ci) {
         ClassPlan &cp = it->second;
         const LaunchGeom &g = geoms[it->first];
-        PB_TRY(pb_h2d(ctx, d_order.as<int32_t>() + off, cp.items.data(), cp.items.size() * 4));
         AlignLaunch p = base;
         p.PW = g.PW;
         p.slot_words = g.slot_words;
         p.par_words = g.par_words;
-        p.scratch = scratch.as<uint32_t>();
+        p.scratch = scratch.as<uint32_t>() + soff;
         p.queue = d_queue.as<int>() + ci;
         p.order = d_order.as<int32_t>() + off;
         p.nitems = (int)cp.items.size();
-        PB_TRY(launch(kClasses[it->first], p, g));
+        cudaStream_t st = ctx->aux_streams[ci];
+        PB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->fork_event, 0));
+        PB_TRY(launch(kClasses[it->first], p, g, st));
+        PB_CUDA(ctx, cudaEventRecord(ctx->aux_events[ci], st));
+        PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->aux_events[ci], 0));
         off += cp.items.size();
+        soff += (size_t)g.blocks * ALIGN_WPB * g.slot_words;
     }
     return PB_OK;
 }
@@ -651,9 +739,9 @@ int pb_align_locate(pb_ctx *ctx, const pb_seqset *reads, const pb_seqset *ref, c
     base.R = R; base.maxn = maxn; base.maxm = maxm;
     base.ops = d_ops; base.ops_off = d_ops_off;
     base.stats = d_stats;
-    return run_classes(ctx, plans, true, base, [&](int S, const AlignLaunch &p, const LaunchGeom &g) -> int {
+    return run_classes(ctx, plans, true, base, [&](int S, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
         void *args[] = {(void *)&p, (void *)&lv, (void *)&d_survive, (void *)&d_rej_cells, (void *)&d_recs};
-        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(S, true), dim3(g.blocks), dim3(ALIGN_WPB * 32), args, g.smem_bytes, ctx->stream));
+        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(S, true), dim3(g.blocks), dim3(ALIGN_WPB * 32), args, g.smem_bytes, st));
         ctx->launches++;
         return PB_OK;
     });
@@ -692,9 +780,9 @@ int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t 
     base.B = seq_view(B);
     base.R = R; base.maxn = maxn; base.maxm = maxm;
     base.ops = d_ops; base.ops_off = d_ops_off;
-    return run_classes(ctx, plans, false, base, [&](int S, const AlignLaunch &p, const LaunchGeom &g) -> int {
+    return run_classes(ctx, plans, false, base, [&](int S, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
         void *args[] = {(void *)&p, (void *)&d_out};
-        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(S, false), dim3(g.blocks), dim3(ALIGN_WPB * 32), args, g.smem_bytes, ctx->stream));
+        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(S, false), dim3(g.blocks), dim3(ALIGN_WPB * 32), args, g.smem_bytes, st));
         ctx->launches++;
         return PB_OK;
     });

@@ -80,6 +80,9 @@ extern "C" void pb_ctx_destroy(pb_ctx *ctx)
     for (int i = 0; i < 2 * PB_T_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    for (auto st : ctx->aux_streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (auto ev : ctx->aux_events) cudaEventDestroy(ev);
+    if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -28,6 +28,10 @@ struct pb_ctx {
     // pinned staging for small host<->device exchanges
     void *h_pin = nullptr;
     size_t h_pin_bytes = 0;
+    // one extra stream per band class of the aligner (forked from / joined back into `stream`)
+    std::vector<cudaStream_t> aux_streams;
+    std::vector<cudaEvent_t> aux_events;
+    cudaEvent_t fork_event = nullptr;
 };
 
 void pb_set_error(pb_ctx *ctx, const char *fmt, ...);
