@@ -584,6 +584,7 @@ static int class_for_band(int D)
 struct ClassPlan {
     std::vector<int32_t> items;
     int max_rows = 0, max_D = 0;
+    double work = 0; // sum of rows x band width over the items: the class's share of the DP cells
 };
 
 template <int S> struct KernelSel {
@@ -654,12 +655,27 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
         geoms[kv.first] = g;
         need += (size_t)g.blocks * ALIGN_WPB * g.slot_words * 4;
     }
-    if (need > budget) { // shrink every grid by the same factor (at least one CTA each)
-        const double f = (double)budget / (double)need;
+    // The classes run concurrently and share the SMs, so give each a share of the resident warps (and of the
+    // scratch) in proportion to its share of the DP cells: they then drain at about the same time.
+    {
+        double total_work = 0;
+        for (auto &kv : plans) total_work += kv.second.work;
+        const double warp_slots = (double)ctx->sm_count * 24.0;
         need = 0;
         for (auto &kv : geoms) {
-            kv.second.blocks = std::max(1, (int)(kv.second.blocks * f));
+            const ClassPlan &cp = plans[kv.first];
+            const double share = total_work > 0 ? cp.work / total_work : 1.0 / plans.size();
+            const int want = (int)(warp_slots * share / ALIGN_WPB + 0.999);
+            kv.second.blocks = std::max(1, std::min(kv.second.blocks, want));
             need += (size_t)kv.second.blocks * ALIGN_WPB * kv.second.slot_words * 4;
+        }
+        if (need > budget) { // still too much scratch: shrink every grid by the same factor (at least one CTA each)
+            const double f = (double)budget / (double)need;
+            need = 0;
+            for (auto &kv : geoms) {
+                kv.second.blocks = std::max(1, (int)(kv.second.blocks * f));
+                need += (size_t)kv.second.blocks * ALIGN_WPB * kv.second.slot_words * 4;
+            }
         }
     }
     DevBuf scratch, d_order, d_queue;
@@ -731,6 +747,7 @@ int pb_align_locate(pb_ctx *ctx, const pb_seqset *reads, const pb_seqset *ref, c
         cp.items.push_back(k);
         cp.max_rows = std::max(cp.max_rows, std::min(L, std::max(maxn - 1, 1)));
         cp.max_D = std::max(cp.max_D, D);
+        cp.work += (double)L * (2.0 * D + 1.0);
     }
     AlignLaunch base;
     memset(&base, 0, sizeof base);
@@ -772,6 +789,7 @@ int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t 
         if (!rejected) {
             cp.max_rows = std::max(cp.max_rows, la[k]);
             cp.max_D = std::max(cp.max_D, D[k]);
+            cp.work += (double)la[k] * (2.0 * D[k] + 1.0);
         }
     }
     AlignLaunch base;
