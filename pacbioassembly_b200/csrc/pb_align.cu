@@ -12,6 +12,8 @@
 //
 // Per cell the kernel touches 2 bits of HBM (the two parent planes, written once, coalesced 128 B per
 // store instruction) -- versus 8 bytes in the reference.  No tensor cores: this is integer/bit work.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <map>
 
@@ -614,7 +616,7 @@ static int plan_launch(pb_ctx *ctx, int S, const ClassPlan &cp, bool locate, siz
     g->PW = ((cp.max_rows + 31) >> 5) + T + 2;
     g->smem_bytes = (size_t)ALIGN_WPB * 4 * g->PW * sizeof(uint32_t);
     g->par_words = (size_t)std::max(cp.max_rows, 1) * 2 * T;
-    const size_t ops_bytes = ((size_t)2 * cp.max_rows + cp.max_D + 64 + 15) & ~(size_t)15;
+    const size_t ops_bytes = ((size_t)2 * cp.max_rows + cp.max_D + 64 + 127) & ~(size_t)127; // keeps every slot 128 B aligned
     g->slot_words = g->par_words + ops_bytes / 4;
     const void *fn = kernel_ptr(S, locate);
     if (g->smem_bytes > 200 * 1024) return pb_fail(ctx, PB_ERR_DOMAIN, "sequence of %d rows needs %zu bytes of shared memory per CTA", cp.max_rows, g->smem_bytes);
@@ -660,7 +662,8 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
     {
         double total_work = 0;
         for (auto &kv : plans) total_work += kv.second.work;
-        const double warp_slots = (double)ctx->sm_count * 24.0;
+        const char *wenv = getenv("PB_WARPS_PER_SM"); // tuning knob: resident aligner warps per SM shared by all classes
+        const double warp_slots = (double)ctx->sm_count * (wenv ? atof(wenv) : 24.0);
         need = 0;
         for (auto &kv : geoms) {
             const ClassPlan &cp = plans[kv.first];
@@ -700,6 +703,9 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
         ctx->aux_events.push_back(ev);
     }
     if (!ctx->fork_event) PB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+    const bool trace = getenv("PB_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    std::vector<std::string> tdesc;
     PB_CUDA(ctx, cudaEventRecord(ctx->fork_event, ctx->stream));
     size_t off = 0, soff = 0;
     int ci = 0;
@@ -717,11 +723,32 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
         p.nitems = (int)cp.items.size();
         cudaStream_t st = ctx->aux_streams[ci];
         PB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->fork_event, 0));
+        if (trace) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            tev.push_back(a); tev.push_back(b);
+            char buf[256];
+            snprintf(buf, sizeof buf, "S=%d items=%zu blocks=%d rows<=%d band<=%d slotMB=%.2f work=%.3g", kClasses[it->first], cp.items.size(), g.blocks, cp.max_rows, cp.max_D, g.slot_words * 4 / 1048576.0, cp.work);
+            tdesc.push_back(buf);
+            cudaEventRecord(a, st);
+        }
         PB_TRY(launch(kClasses[it->first], p, g, st));
+        if (trace) cudaEventRecord(tev.back(), st);
         PB_CUDA(ctx, cudaEventRecord(ctx->aux_events[ci], st));
         PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->aux_events[ci], 0));
         off += cp.items.size();
         soff += (size_t)g.blocks * ALIGN_WPB * g.slot_words;
+    }
+    if (trace) { // PB_TRACE=1: per-class device times (classes overlap, so they do not add up)
+        cudaStreamSynchronize(ctx->stream);
+        for (size_t c = 0; c < tdesc.size(); ++c) {
+            float ms = 0, ms0 = 0;
+            cudaEventElapsedTime(&ms, tev[2 * c], tev[2 * c + 1]);
+            cudaEventElapsedTime(&ms0, tev[0], tev[2 * c]);
+            fprintf(stderr, "[pb_trace] %s start=+%.2fms dur=%.2fms\n", tdesc[c].c_str(), ms0, ms);
+            cudaEventDestroy(tev[2 * c]); cudaEventDestroy(tev[2 * c + 1]);
+        }
+        fprintf(stderr, "[pb_trace] scratch %.2f GB of budget %.2f GB\n", need / 1e9, budget / 1e9);
     }
     return PB_OK;
 }
