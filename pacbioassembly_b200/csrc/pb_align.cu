@@ -165,18 +165,20 @@ __device__ __forceinline__ uint32_t addc(uint32_t a, uint32_t b)
 }
 
 // One band row for the S words of this lane.  pl points at this lane's first Eq word of the row's plane, sh is the
-// row's bit offset inside those words; prow is this lane's column of the row's parent block.  Returns the D0 word of
+// row's bit offset inside those words; prow is this lane's pair column (row base + 2*lane) of the row's parent block.  Returns the D0 word of
 // slot sd (the main diagonal lives there in one lane); leaves the row's vertical deltas in Vp/Vn.
 template <int S>
 __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S], const uint32_t (&force)[S], uint32_t (&Vp)[S],
-                                             uint32_t (&Vn)[S], const uint32_t *__restrict__ pl, unsigned sh, int lane, int nst,
-                                             int sd, uint32_t *__restrict__ prow)
+                                             uint32_t (&Vn)[S], const uint32_t *__restrict__ pl, int thrs, unsigned sh, int lane,
+                                             int nst, int sd, uint32_t *__restrict__ prow)
 {
-    constexpr int T = 32 * S;
     // phase A: slide the band one bit (across words and lanes), fetch Eq, block add with carry-in 0
     uint32_t nx = __shfl_down_sync(FULL, (Hp[0] & 1u) | ((Hn[0] & 1u) << 1), 1);
     if (lane == 31) nx = 1u;
     uint32_t Eq[S], x[S], sum[S];
+    // Eq words: logical words x0..x0+S of the plane; for even S the plane is stored with one pad word per S words
+    // (bank-conflict-free for the lane stride S), which shows up here as a +1 from slot `thrs` on
+    constexpr bool PAD = (S % 2) == 0;
     uint32_t plw = pl[0];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -184,7 +186,7 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
         const uint32_t hn_hi = (s + 1 < S) ? Hn[s + 1] : (nx >> 1);
         Hp[s] = __funnelshift_r(Hp[s], hp_hi, 1) | force[s];
         Hn[s] = __funnelshift_r(Hn[s], hn_hi, 1) & ~force[s];
-        const uint32_t nxt = pl[s + 1];
+        const uint32_t nxt = PAD ? pl[s + 1 + ((s + 1 >= thrs) ? 1 : 0)] : pl[s + 1];
         Eq[s] = __funnelshift_r(plw, nxt, sh);
         plw = nxt;
         x[s] = Eq[s] & Hp[s];
@@ -205,13 +207,14 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
 
     // phase B: vertical deltas, D0, MATCH plane
     uint32_t d0w = 0u;
+    uint32_t Mw[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
         const uint32_t Xv = (sum[s] ^ Hp[s]) | Eq[s];
         Vp[s] = Hn[s] | ~(Xv | Hp[s]);
         Vn[s] = Hp[s] & Xv;
         const uint32_t D0 = Xv | Hn[s];
-        if (s < nst) prow[s * 32] = Eq[s] | ~D0;
+        Mw[s] = Eq[s] | ~D0;
         if (s == sd) d0w = D0;
     }
     uint32_t pv = __shfl_up_sync(FULL, (Vp[S - 1] >> 31) | ((Vn[S - 1] >> 31) << 1), 1);
@@ -227,7 +230,8 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
         const uint32_t Xh = Eq[s] | Hn[s];
         Hp[s] = vns | ~(Xh | vps);
         Hn[s] = vps & Xh;
-        if (s < nst) prow[T + s * 32] = Hp[s];
+        // parents of band word w = lane*S+s: {MATCH plane, INSERT plane} as one 8-byte pair at pair index s*32+lane
+        if (s < nst) reinterpret_cast<uint2 *>(prow)[s * 32] = make_uint2(Mw[s], Hp[s]);
     }
     return d0w;
 }
@@ -250,6 +254,7 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
     const int NW = (2 * D + 1 + 31) >> 5; // band words that carry real cells (NW <= T guaranteed by the host)
 
     // ---- Eq planes of seg_b in shared memory: plane c, bit t <-> (b[t - D] == c), zero outside [0,len_b)
+    constexpr bool PAD = (S % 2) == 0; // see row_step: physical index of logical word x is x + x/S for even S
     const int PWn = ((len_a + 31) >> 5) + T + 1;
     for (int x = lane; x < PWn; x += 32) {
         const int bidx0 = 32 * x - D; // b index of bit 0 of this word
@@ -265,10 +270,11 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
             hi = load_window(B.hi, B.nwords, b_bit + bidx0);
             lo = load_window(B.lo, B.nwords, b_bit + bidx0);
         }
-        planes[0 * PW + x] = ~hi & ~lo & valid;
-        planes[1 * PW + x] = ~hi & lo & valid;
-        planes[2 * PW + x] = hi & ~lo & valid;
-        planes[3 * PW + x] = hi & lo & valid;
+        const int px = PAD ? x + x / S : x;
+        planes[0 * PW + px] = ~hi & ~lo & valid;
+        planes[1 * PW + px] = ~hi & lo & valid;
+        planes[2 * PW + px] = hi & ~lo & valid;
+        planes[3 * PW + px] = hi & lo & valid;
     }
     __syncwarp();
 
@@ -306,12 +312,14 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
         const uint32_t awh = load_window(A.hi, A.nwords, a_bit + i0 - 1); // next 32 bases of seg_a (warp-uniform)
         const uint32_t awl = load_window(A.lo, A.nwords, a_bit + i0 - 1);
         const int thr = (int)((i0 + lane) * R); // cost > i*R  <=>  cost > floor(i*R) for an integer cost
-        const uint32_t *plq = planes + ((i0 - 1) >> 5) + lane * S;
-        uint32_t *prow = par + (size_t)(i0 - 1) * (2 * T) + lane;
+        const int q = (i0 - 1) >> 5; // first plane word of the block's rows (logical index)
+        const uint32_t *plq = planes + q + lane * S + (PAD ? lane + q / S : 0);
+        const int thrs = S - q % S;
+        uint32_t *prow = par + (size_t)(i0 - 1) * (2 * T) + 2 * lane;
         uint32_t hist = 0u;
         for (int t = 0; t < tmax; ++t) {
             const int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
-            const uint32_t d0w = row_step<S>(Hp, Hn, force, Vp, Vn, plq + ca * PW, (unsigned)t, lane, nst, sd, prow);
+            const uint32_t d0w = row_step<S>(Hp, Hn, force, Vp, Vn, plq + ca * PW, thrs, (unsigned)t, lane, nst, sd, prow);
             hist |= ((d0w >> (D & 31)) & 1u) << t; // meaningful in the diagonal's owner lane
             prow += 2 * T;
         }
@@ -340,8 +348,9 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
                 awl = load_window(A.lo, A.nwords, a_bit + (i - 1 - t));
             }
             const int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
-            row_step<S>(Hp, Hn, force, Vp, Vn, planes + ca * PW + ((i - 1) >> 5) + lane * S, (unsigned)t, lane, nst, sd,
-                        par + (size_t)(i - 1) * (2 * T) + lane);
+            const int q = (i - 1) >> 5;
+            row_step<S>(Hp, Hn, force, Vp, Vn, planes + ca * PW + q + lane * S + (PAD ? lane + q / S : 0), S - q % S, (unsigned)t,
+                        lane, nst, sd, par + (size_t)(i - 1) * (2 * T) + 2 * lane);
             const int k = len_b - i + D, wk = k >> 5, Lk = wk / S, sk = wk % S;
             uint32_t vpw = 0u, vnw = 0u;
 #pragma unroll
@@ -387,22 +396,23 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
     if ((double)matlen_b < len_b * (1 - R)) return; // seq_aligner.h:114
 
     // ---- find_path, seq_aligner.h:214-233: walk the parent planes back from the goal cell.
-    // Warp-cooperative: lane r holds the parent words of row i0-r around the path's band position (3 words per
-    // plane), the next 32 rows are prefetched while the current ones are walked, and runs of MATCH along a
+    // Warp-cooperative: lane r holds the parent pairs of row i0-r around the path's band position (2 band words,
+    // 16 bytes), the next 32 rows are prefetched while the current ones are walked, and runs of MATCH along a
     // diagonal (same band bit, consecutive rows) are found with one ballot and written by as many lanes.
     __syncwarp();
-    auto par_word = [&](int row, int w, int plane) -> uint32_t {
-        if (row < 1 || w < 0 || w >= NW) return 0u;
+    auto par_pair = [&](int row, int w) -> uint2 { // {MATCH word, INSERT word} of band word w of DP row `row`
+        if (row < 1 || w < 0 || w >= NW) return make_uint2(0u, 0u);
         const int L = w / S, s = w - L * S;
-        return __ldcg(par + (size_t)(row - 1) * (2 * T) + plane * T + s * 32 + L);
+        return __ldcg(reinterpret_cast<const uint2 *>(par + (size_t)(row - 1) * (2 * T)) + s * 32 + L);
     };
+    // window = the band word under the path plus the neighbour the path is closer to
+    auto window_base = [](int k) -> int { return (k >> 5) - ((k & 31) < 16 ? 1 : 0); };
     int n = 0;
     {
         int i = matlen_a, j = matlen_b;
         const int guard = len_a + len_b + 1; // a path can never be longer; keeps a corrupted plane from hanging the GPU
         int cur_i0 = -1, cur_wb = 0, nxt_i0 = -1, nxt_wb = 0;
-        uint32_t cm0 = 0, cm1 = 0, cm2 = 0, ch0 = 0, ch1 = 0, ch2 = 0;
-        uint32_t nm0 = 0, nm1 = 0, nm2 = 0, nh0 = 0, nh1 = 0, nh2 = 0;
+        uint2 c0 = make_uint2(0u, 0u), c1 = c0, n0 = c0, n1 = c0;
         while ((i | j) != 0 && n < guard) {
             if (i == 0) { // init_cell row 0: INSERT all the way
                 for (int t = lane; t < j; t += 32) opsrev[n + t] = (uint8_t)PB_INSERT;
@@ -415,25 +425,22 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
                 break;
             }
             const int k = j - i + D, w = k >> 5;
-            if (cur_i0 < 0 || cur_i0 - i >= 32 || w < cur_wb || w > cur_wb + 2) {
-                if (nxt_i0 == i && w >= nxt_wb && w <= nxt_wb + 2) {
+            if (cur_i0 < 0 || cur_i0 - i >= 32 || w < cur_wb || w > cur_wb + 1) {
+                if (nxt_i0 == i && w >= nxt_wb && w <= nxt_wb + 1) {
                     cur_i0 = nxt_i0; cur_wb = nxt_wb;
-                    cm0 = nm0; cm1 = nm1; cm2 = nm2; ch0 = nh0; ch1 = nh1; ch2 = nh2;
+                    c0 = n0; c1 = n1;
                 } else {
-                    cur_i0 = i; cur_wb = w - 1;
-                    const int row = cur_i0 - lane;
-                    cm0 = par_word(row, cur_wb, 0); cm1 = par_word(row, cur_wb + 1, 0); cm2 = par_word(row, cur_wb + 2, 0);
-                    ch0 = par_word(row, cur_wb, 1); ch1 = par_word(row, cur_wb + 1, 1); ch2 = par_word(row, cur_wb + 2, 1);
+                    cur_i0 = i; cur_wb = window_base(k);
+                    c0 = par_pair(cur_i0 - lane, cur_wb);
+                    c1 = par_pair(cur_i0 - lane, cur_wb + 1);
                 }
-                nxt_i0 = cur_i0 - 32; nxt_wb = w - 1;
-                const int row = nxt_i0 - lane;
-                nm0 = par_word(row, nxt_wb, 0); nm1 = par_word(row, nxt_wb + 1, 0); nm2 = par_word(row, nxt_wb + 2, 0);
-                nh0 = par_word(row, nxt_wb, 1); nh1 = par_word(row, nxt_wb + 1, 1); nh2 = par_word(row, nxt_wb + 2, 1);
+                nxt_i0 = cur_i0 - 32; nxt_wb = window_base(k);
+                n0 = par_pair(nxt_i0 - lane, nxt_wb);
+                n1 = par_pair(nxt_i0 - lane, nxt_wb + 1);
             }
             const int r0 = cur_i0 - i; // lane that holds the current row
-            const int x = w - cur_wb;
-            const uint32_t mw = x == 0 ? cm0 : (x == 1 ? cm1 : cm2);
-            const uint32_t B = __ballot_sync(FULL, (mw >> (k & 31)) & 1u) >> r0; // bit t: cell (i-t, j-t) is MATCH
+            const uint2 cw = (w == cur_wb) ? c0 : c1;
+            const uint32_t B = __ballot_sync(FULL, (cw.x >> (k & 31)) & 1u) >> r0; // bit t: cell (i-t, j-t) is MATCH
             int run = (~B) ? __ffs(~B) - 1 : 32;
             run = min(min(run, 32 - r0), min(i, j));
             if (run > 0) {
@@ -441,8 +448,7 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
                 n += run; i -= run; j -= run;
                 continue;
             }
-            const uint32_t hw = x == 0 ? ch0 : (x == 1 ? ch1 : ch2);
-            const uint32_t hb = (__shfl_sync(FULL, hw, r0) >> (k & 31)) & 1u;
+            const uint32_t hb = (__shfl_sync(FULL, cw.y, r0) >> (k & 31)) & 1u;
             if (lane == 0) opsrev[n] = (uint8_t)(hb ? PB_INSERT : PB_DELETE);
             ++n;
             if (hb) --j; else --i;
@@ -613,7 +619,8 @@ struct LaunchGeom {
 static int plan_launch(pb_ctx *ctx, int S, const ClassPlan &cp, bool locate, size_t scratch_budget, LaunchGeom *g)
 {
     const int T = 32 * S;
-    g->PW = ((cp.max_rows + 31) >> 5) + T + 2;
+    const int logical = ((cp.max_rows + 31) >> 5) + T + 2;
+    g->PW = logical + ((S % 2) == 0 ? logical / S + 2 : 0); // even S: one pad word per S words (bank conflicts)
     g->smem_bytes = (size_t)ALIGN_WPB * 4 * g->PW * sizeof(uint32_t);
     g->par_words = (size_t)std::max(cp.max_rows, 1) * 2 * T;
     const size_t ops_bytes = ((size_t)2 * cp.max_rows + cp.max_D + 64 + 127) & ~(size_t)127; // keeps every slot 128 B aligned
@@ -746,8 +753,8 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
             cudaEventElapsedTime(&ms, tev[2 * c], tev[2 * c + 1]);
             cudaEventElapsedTime(&ms0, tev[0], tev[2 * c]);
             fprintf(stderr, "[pb_trace] %s start=+%.2fms dur=%.2fms\n", tdesc[c].c_str(), ms0, ms);
-            cudaEventDestroy(tev[2 * c]); cudaEventDestroy(tev[2 * c + 1]);
         }
+        for (auto e : tev) cudaEventDestroy(e);
         fprintf(stderr, "[pb_trace] scratch %.2f GB of budget %.2f GB\n", need / 1e9, budget / 1e9);
     }
     return PB_OK;
