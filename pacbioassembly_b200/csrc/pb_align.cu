@@ -307,10 +307,12 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
     // ---- rows 1..min(len_a,len_b) in blocks of 32: the early-failure test (seq_aligner.h:185) is evaluated once
     // per block from the block's 32 diagonal D0 bits; a failing block reports its first failing row exactly.
     const int nfast = min(len_a, len_b);
+    uint32_t awh_n = load_window(A.hi, A.nwords, a_bit), awl_n = load_window(A.lo, A.nwords, a_bit);
     for (int i0 = 1; i0 <= nfast; i0 += 32) {
         const int tmax = min(32, nfast - i0 + 1);
-        const uint32_t awh = load_window(A.hi, A.nwords, a_bit + i0 - 1); // next 32 bases of seg_a (warp-uniform)
-        const uint32_t awl = load_window(A.lo, A.nwords, a_bit + i0 - 1);
+        const uint32_t awh = awh_n, awl = awl_n; // this block's 32 bases of seg_a (warp-uniform); fetch the next block's now
+        awh_n = load_window(A.hi, A.nwords, a_bit + i0 + 31);
+        awl_n = load_window(A.lo, A.nwords, a_bit + i0 + 31);
         const int thr = (int)((i0 + lane) * R); // cost > i*R  <=>  cost > floor(i*R) for an integer cost
         const int q = (i0 - 1) >> 5; // first plane word of the block's rows (logical index)
         const uint32_t *plq = planes + q + lane * S + (PAD ? lane + q / S : 0);
@@ -592,7 +594,7 @@ static int class_for_band(int D)
 struct ClassPlan {
     std::vector<int32_t> items;
     int max_rows = 0, max_D = 0;
-    double work = 0; // sum of rows x band width over the items: the class's share of the DP cells
+    double work = 0; // estimated instruction count of the class: its share of the machine
 };
 
 template <int S> struct KernelSel {
@@ -645,7 +647,7 @@ static size_t scratch_budget(pb_ctx *ctx)
 {
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); fr = (size_t)8 << 30; }
-    size_t b = (size_t)((double)fr * 0.4);
+    size_t b = (size_t)((double)(fr + ctx->scratch_bytes) * 0.4); // what we already hold counts as available
     if (ctx->scratch_limit && ctx->scratch_limit < b) b = ctx->scratch_limit;
     return b;
 }
@@ -688,8 +690,20 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
             }
         }
     }
-    DevBuf scratch, d_order, d_queue;
-    PB_TRY(scratch.alloc(ctx, need + 256));
+    DevBuf d_order, d_queue;
+    if (need + 256 > ctx->scratch_bytes) { // grow-only, kept across calls
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->scratch) cudaFree(ctx->scratch);
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        const size_t want = need + need / 8 + 256;
+        cudaError_t e = cudaMalloc(&ctx->scratch, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return pb_fail(ctx, PB_ERR_NOMEM, "aligner scratch of %zu bytes: %s", want, cudaGetErrorString(e));
+        }
+        ctx->scratch_bytes = want;
+    }
     size_t nitems = 0;
     for (auto &kv : plans) nitems += kv.second.items.size();
     PB_TRY(d_order.alloc(ctx, nitems * 4 + 16));
@@ -724,7 +738,7 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
         p.PW = g.PW;
         p.slot_words = g.slot_words;
         p.par_words = g.par_words;
-        p.scratch = scratch.as<uint32_t>() + soff;
+        p.scratch = reinterpret_cast<uint32_t *>(ctx->scratch) + soff;
         p.queue = d_queue.as<int>() + ci;
         p.order = d_order.as<int32_t>() + off;
         p.nitems = (int)cp.items.size();
@@ -781,7 +795,7 @@ int pb_align_locate(pb_ctx *ctx, const pb_seqset *reads, const pb_seqset *ref, c
         cp.items.push_back(k);
         cp.max_rows = std::max(cp.max_rows, std::min(L, std::max(maxn - 1, 1)));
         cp.max_D = std::max(cp.max_D, D);
-        cp.work += (double)L * (2.0 * D + 1.0);
+        cp.work += (double)L * (30.0 * kClasses[cls] + 60.0); // ~instructions: rows x (per-word + per-row cost)
     }
     AlignLaunch base;
     memset(&base, 0, sizeof base);
@@ -823,7 +837,7 @@ int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t 
         if (!rejected) {
             cp.max_rows = std::max(cp.max_rows, la[k]);
             cp.max_D = std::max(cp.max_D, D[k]);
-            cp.work += (double)la[k] * (2.0 * D[k] + 1.0);
+            cp.work += (double)la[k] * (30.0 * kClasses[cls] + 60.0);
         }
     }
     AlignLaunch base;

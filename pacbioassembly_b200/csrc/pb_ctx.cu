@@ -83,6 +83,7 @@ extern "C" void pb_ctx_destroy(pb_ctx *ctx)
     for (auto st : ctx->aux_streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     for (auto ev : ctx->aux_events) cudaEventDestroy(ev);
     if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
+    if (ctx->scratch) cudaFree(ctx->scratch);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

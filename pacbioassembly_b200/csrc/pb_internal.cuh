@@ -32,6 +32,9 @@ struct pb_ctx {
     std::vector<cudaStream_t> aux_streams;
     std::vector<cudaEvent_t> aux_events;
     cudaEvent_t fork_event = nullptr;
+    // grow-only scratch for the aligner's parent planes (kept across calls: no per-step allocation)
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
 };
 
 void pb_set_error(pb_ctx *ctx, const char *fmt, ...);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """One locate step on a slice of the config-2 workload, for ncu (B200_PROFILING.md): small, no torch, no CPU legs.
 
-    python tools/profile_step.py [nreads] [steps]
+    python tools/profile_step.py [nreads] [steps] [lo hi]     (lo hi: uniform read lengths instead of the CLR log-normal)
 """
 import os
 import sys
@@ -20,7 +20,10 @@ def main():
     nreads = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     ref = workload.reference(2, 4_600_000)
-    lens = workload.read_lengths(3, nreads, mean=5000.0, sigma_log=0.5, lo=500, hi=19999)
+    if len(sys.argv) > 4:
+        lens = workload.read_lengths(3, nreads, sigma_log=0.0, lo=int(sys.argv[3]), hi=int(sys.argv[4]))
+    else:
+        lens = workload.read_lengths(3, nreads, mean=5000.0, sigma_log=0.5, lo=500, hi=19999)
     txt, offs, lens, _ = workload.reads(3, ref, lens)
     ctx = Context(0)
     rs = ctx.seqset_one(ref)
