@@ -168,9 +168,9 @@ __device__ __forceinline__ uint32_t addc(uint32_t a, uint32_t b)
 // row's bit offset inside those words; prow is this lane's pair column (row base + 2*lane) of the row's parent block.  Returns the D0 word of
 // slot sd (the main diagonal lives there in one lane); leaves the row's vertical deltas in Vp/Vn.
 template <int S>
-__device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S], const uint32_t (&force)[S], uint32_t (&Vp)[S],
+__device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S], const uint32_t (&keep)[S], uint32_t (&Vp)[S],
                                              uint32_t (&Vn)[S], const uint32_t *__restrict__ pl, int thrs, unsigned sh, int lane,
-                                             int nst, int sd, uint32_t *__restrict__ prow)
+                                             int sd, uint32_t *__restrict__ prow)
 {
     // phase A: slide the band one bit (across words and lanes), fetch Eq, block add with carry-in 0
     uint32_t nx = __shfl_down_sync(FULL, (Hp[0] & 1u) | ((Hn[0] & 1u) << 1), 1);
@@ -184,10 +184,10 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
     for (int s = 0; s < S; ++s) {
         const uint32_t hp_hi = (s + 1 < S) ? Hp[s + 1] : (nx & 1u);
         const uint32_t hn_hi = (s + 1 < S) ? Hn[s + 1] : (nx >> 1);
-        Hp[s] = __funnelshift_r(Hp[s], hp_hi, 1) | force[s];
-        Hn[s] = __funnelshift_r(Hn[s], hn_hi, 1) & ~force[s];
+        Hp[s] = __funnelshift_r(Hp[s], hp_hi, 1);
+        Hn[s] = __funnelshift_r(Hn[s], hn_hi, 1);
         const uint32_t nxt = PAD ? pl[s + 1 + ((s + 1 >= thrs) ? 1 : 0)] : pl[s + 1];
-        Eq[s] = __funnelshift_r(plw, nxt, sh);
+        Eq[s] = __funnelshift_r(plw, nxt, sh) & keep[s]; // no matches beyond the band's upper edge (see align_one)
         plw = nxt;
         x[s] = Eq[s] & Hp[s];
     }
@@ -231,7 +231,7 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
         Hp[s] = vns | ~(Xh | vps);
         Hn[s] = vps & Xh;
         // parents of band word w = lane*S+s: {MATCH plane, INSERT plane} as one 8-byte pair at pair index s*32+lane
-        if (s < nst) reinterpret_cast<uint2 *>(prow)[s * 32] = make_uint2(Mw[s], Hp[s]);
+        reinterpret_cast<uint2 *>(prow)[s * 32] = make_uint2(Mw[s], Hp[s]); // words past the band land in the row's padding
     }
     return d0w;
 }
@@ -251,7 +251,6 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
     res.cells = 0;
     if (len_a >= maxn || D >= maxm) return; // seq_aligner.h:104-107
 
-    const int NW = (2 * D + 1 + 31) >> 5; // band words that carry real cells (NW <= T guaranteed by the host)
 
     // ---- Eq planes of seg_b in shared memory: plane c, bit t <-> (b[t - D] == c), zero outside [0,len_b)
     constexpr bool PAD = (S % 2) == 0; // see row_step: physical index of logical word x is x + x/S for even S
@@ -278,8 +277,12 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
     }
     __syncwarp();
 
-    // ---- row 0: h = -1 for (fake) columns j <= 0, +1 for j >= 1; bits k >= 2D are pinned to +1 every row
-    uint32_t Hp[S], Hn[S], force[S];
+    // ---- row 0: h = -1 for (fake) columns j <= 0, +1 for j >= 1.
+    // Upper band edge: cell (i, i+D) must not see its "up" neighbour (seq_aligner.h:170).  Band bits k > 2D are
+    // computed like ordinary cells but with Eq forced to 0; by induction over rows their cost is then
+    // cost(i, i+D) + (k - 2D), i.e. h = +1 all the way up, so the bit that slides into k = 2D every row is the
+    // +1 a pinned edge would hold and U+1 = Dg+2 never beats Dg+m.  (tools/bitpar_model.c checks this.)
+    uint32_t Hp[S], Hn[S], keep[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
         const int k0 = 32 * (lane * S + s);
@@ -289,14 +292,13 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
         else hn = 0xffffffffu >> (31 - (D - k0));
         Hn[s] = hn;
         Hp[s] = ~hn;
-        uint32_t f;
-        if (k0 >= 2 * D) f = 0xffffffffu;
-        else if (k0 + 31 < 2 * D) f = 0u;
-        else f = 0xffffffffu << (2 * D - k0);
-        force[s] = f;
+        uint32_t kp; // bits k <= 2D
+        if (k0 > 2 * D) kp = 0u;
+        else if (k0 + 31 <= 2 * D) kp = 0xffffffffu;
+        else kp = 0xffffffffu >> (31 - (2 * D - k0));
+        keep[s] = kp;
     }
     const int wd = D >> 5, Ld = wd / S, sd = wd % S; // owner of the main-diagonal bit k = D
-    const int nst = min(max(NW - lane * S, 0), S);      // band words of this lane that carry real cells
 
     int cii = 0;                          // cost(i,i), warp-uniform, advanced once per 32-row block
     int colc = 0, colbest = 0, col_i = 0; // cost(i,len_b) tracking when len_a > len_b
@@ -321,7 +323,7 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
         uint32_t hist = 0u;
         for (int t = 0; t < tmax; ++t) {
             const int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
-            const uint32_t d0w = row_step<S>(Hp, Hn, force, Vp, Vn, plq + ca * PW, thrs, (unsigned)t, lane, nst, sd, prow);
+            const uint32_t d0w = row_step<S>(Hp, Hn, keep, Vp, Vn, plq + ca * PW, thrs, (unsigned)t, lane, sd, prow);
             hist |= ((d0w >> (D & 31)) & 1u) << t; // meaningful in the diagonal's owner lane
             prow += 2 * T;
         }
@@ -351,8 +353,8 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
             }
             const int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
             const int q = (i - 1) >> 5;
-            row_step<S>(Hp, Hn, force, Vp, Vn, planes + ca * PW + q + lane * S + (PAD ? lane + q / S : 0), S - q % S, (unsigned)t,
-                        lane, nst, sd, par + (size_t)(i - 1) * (2 * T) + 2 * lane);
+            row_step<S>(Hp, Hn, keep, Vp, Vn, planes + ca * PW + q + lane * S + (PAD ? lane + q / S : 0), S - q % S, (unsigned)t,
+                        lane, sd, par + (size_t)(i - 1) * (2 * T) + 2 * lane);
             const int k = len_b - i + D, wk = k >> 5, Lk = wk / S, sk = wk % S;
             uint32_t vpw = 0u, vnw = 0u;
 #pragma unroll
@@ -403,7 +405,7 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
     // diagonal (same band bit, consecutive rows) are found with one ballot and written by as many lanes.
     __syncwarp();
     auto par_pair = [&](int row, int w) -> uint2 { // {MATCH word, INSERT word} of band word w of DP row `row`
-        if (row < 1 || w < 0 || w >= NW) return make_uint2(0u, 0u);
+        if (row < 1 || w < 0 || w >= T) return make_uint2(0u, 0u);
         const int L = w / S, s = w - L * S;
         return __ldcg(reinterpret_cast<const uint2 *>(par + (size_t)(row - 1) * (2 * T)) + s * 32 + L);
     };
@@ -413,8 +415,8 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
     {
         int i = matlen_a, j = matlen_b;
         const int guard = len_a + len_b + 1; // a path can never be longer; keeps a corrupted plane from hanging the GPU
-        int cur_i0 = -1, cur_wb = 0, nxt_i0 = -1, nxt_wb = 0;
-        uint2 c0 = make_uint2(0u, 0u), c1 = c0, n0 = c0, n1 = c0;
+        int cur_i0 = -1, cur_wb = 0, nxt_i0 = -1, nxt_wb = 0, nx2_i0 = -1, nx2_wb = 0;
+        uint2 c0 = make_uint2(0u, 0u), c1 = c0, n0 = c0, n1 = c0, m0 = c0, m1 = c0;
         while ((i | j) != 0 && n < guard) {
             if (i == 0) { // init_cell row 0: INSERT all the way
                 for (int t = lane; t < j; t += 32) opsrev[n + t] = (uint8_t)PB_INSERT;
@@ -428,17 +430,23 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
             }
             const int k = j - i + D, w = k >> 5;
             if (cur_i0 < 0 || cur_i0 - i >= 32 || w < cur_wb || w > cur_wb + 1) {
-                if (nxt_i0 == i && w >= nxt_wb && w <= nxt_wb + 1) {
+                const int wb = window_base(k);
+                if (nxt_i0 == i && w >= nxt_wb && w <= nxt_wb + 1) { // the usual case: 32 rows consumed, prediction held
                     cur_i0 = nxt_i0; cur_wb = nxt_wb;
                     c0 = n0; c1 = n1;
-                } else {
-                    cur_i0 = i; cur_wb = window_base(k);
+                    nxt_i0 = nx2_i0; nxt_wb = nx2_wb;
+                    n0 = m0; n1 = m1;
+                } else { // cold start or the path left the predicted words: fetch now
+                    cur_i0 = i; cur_wb = wb;
                     c0 = par_pair(cur_i0 - lane, cur_wb);
                     c1 = par_pair(cur_i0 - lane, cur_wb + 1);
+                    nxt_i0 = cur_i0 - 32; nxt_wb = wb;
+                    n0 = par_pair(nxt_i0 - lane, nxt_wb);
+                    n1 = par_pair(nxt_i0 - lane, nxt_wb + 1);
                 }
-                nxt_i0 = cur_i0 - 32; nxt_wb = window_base(k);
-                n0 = par_pair(nxt_i0 - lane, nxt_wb);
-                n1 = par_pair(nxt_i0 - lane, nxt_wb + 1);
+                nx2_i0 = cur_i0 - 64; nx2_wb = wb; // two windows ahead: DRAM latency under load is several windows long
+                m0 = par_pair(nx2_i0 - lane, nx2_wb);
+                m1 = par_pair(nx2_i0 - lane, nx2_wb + 1);
             }
             const int r0 = cur_i0 - i; // lane that holds the current row
             const uint2 cw = (w == cur_wb) ? c0 : c1;
@@ -479,8 +487,11 @@ struct AlignLaunch {
     unsigned long long *stats; // [0] DP cells computed by K3, [1] alignments run by K3 (may be NULL)
 };
 
+// resident CTAs per SM the register allocation is held to (more warps hide the shuffle / ballot latencies of a row)
+template <int S> struct MinBlocks { static constexpr int v = S <= 3 ? 6 : (S <= 5 ? 5 : (S <= 12 ? 4 : 3)); };
+
 template <int S>
-__global__ void __launch_bounds__(ALIGN_WPB * 32)
+__global__ void __launch_bounds__(ALIGN_WPB * 32, MinBlocks<S>::v)
 align_locate_kernel(AlignLaunch p, LocateView lv, const uint8_t *__restrict__ survive, const int32_t *__restrict__ rej_cells,
                     pb_locate_rec *__restrict__ recs)
 {
@@ -547,7 +558,7 @@ align_locate_kernel(AlignLaunch p, LocateView lv, const uint8_t *__restrict__ su
 }
 
 template <int S>
-__global__ void __launch_bounds__(ALIGN_WPB * 32)
+__global__ void __launch_bounds__(ALIGN_WPB * 32, MinBlocks<S>::v)
 align_pairs_kernel(AlignLaunch p, pb_align_out *__restrict__ out)
 {
     extern __shared__ uint32_t smem[];

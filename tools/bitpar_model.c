@@ -12,8 +12,10 @@
  *
  * Derivation (band half-width D = max_dst, band bit k of row i <-> column j = i - D + k):
  *   state  Hp/Hn : h_{i-1}(j) = cost(i-1,j) - cost(i-1,j-1) = +1 / -1, re-aligned to row i by a 1-bit
- *                  right shift; the bit that enters at k = 2D is forced to +1 (a fake out-of-band
- *                  cell that can never win: U+1 >= Dg+2 > Dg+m), vin = +1 at k = 0 likewise.
+ *                  right shift.  Bits k > 2D are computed like cells but with Eq = 0 (`force` below is that
+ *                  keep-mask); by induction their cost is cost(i,i+D) + (k-2D), so the bit sliding into
+ *                  k = 2D is always +1: a fake out-of-band cell that can never win (U+1 >= Dg+2 > Dg+m).
+ *                  vin = +1 at k = 0 likewise.
  *   Eq           : b[j-1] == a[i-1]
  *   Xv = (((Eq & Hp) + Hp) ^ Hp) | Eq ;  D0 = Xv | Hn            (cost(i,j) == cost(i-1,j-1))
  *   Vp = Hn | ~(Xv | Hp) ; Vn = Hp & Xv                            (vertical deltas of row i)
@@ -80,7 +82,7 @@ int model_align(const char *a, int a_len, const char *b, int b_len, double R, in
             for (int bit = 0; bit < 32; ++bit) {
                 int k = w * 32 + bit;
                 if (k > D) hp |= 1u << bit; else hn |= 1u << bit;
-                if (k >= 2 * D) f |= 1u << bit;
+                if (k <= 2 * D) f |= 1u << bit; /* keep mask: Eq is forced to 0 above the band's upper edge */
                 if (k == D) dm |= 1u << bit;
             }
             Hp[L][s] = hp; Hn[L][s] = hn; force[L][s] = f; diagm[L][s] = dm;
@@ -106,14 +108,14 @@ int model_align(const char *a, int a_len, const char *b, int b_len, double R, in
             for (int s = 0; s < S; ++s) {
                 uint32_t hp_hi = s + 1 < S ? Hp[L][s + 1] : nx_hp[L];
                 uint32_t hn_hi = s + 1 < S ? Hn[L][s + 1] : nx_hn[L];
-                Hp[L][s] = funnel_r(Hp[L][s], hp_hi, 1) | force[L][s];
-                Hn[L][s] = funnel_r(Hn[L][s], hn_hi, 1) & ~force[L][s];
+                Hp[L][s] = funnel_r(Hp[L][s], hp_hi, 1);
+                Hn[L][s] = funnel_r(Hn[L][s], hn_hi, 1);
             }
             /* Eq words and the block add with carry-in 0 */
             uint32_t carry = 0, allones = 1;
             for (int s = 0; s < S; ++s) {
                 int w = L * S + s;
-                Eq[L][s] = funnel_r(pl[q + w], pl[q + w + 1], sh);
+                Eq[L][s] = funnel_r(pl[q + w], pl[q + w + 1], sh) & force[L][s];
                 uint64_t t = (uint64_t)(Eq[L][s] & Hp[L][s]) + Hp[L][s] + carry;
                 sum[L][s] = (uint32_t)t;
                 carry = (uint32_t)(t >> 32);
