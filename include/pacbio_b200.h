@@ -72,7 +72,7 @@ PB_API const char *pb_last_error(const pb_ctx *ctx);
 PB_API void *pb_ctx_stream(pb_ctx *ctx);
 /* number of kernels launched by this context since creation (bench.py reports the per-step difference) */
 PB_API int64_t pb_ctx_launch_count(const pb_ctx *ctx);
-/* upper bound on device scratch (bytes) the aligner may claim for parent matrices; 0 = default (40% of free) */
+/* upper bound on device scratch (bytes) the aligner may claim for parent matrices; 0 = default (50% of free) */
 PB_API int pb_ctx_set_scratch_limit(pb_ctx *ctx, size_t bytes);
 
 /* named device timings (milliseconds, CUDA events on the context stream) of the most recent call */

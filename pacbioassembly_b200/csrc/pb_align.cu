@@ -626,7 +626,8 @@ static const void *kernel_ptr(int S, bool locate)
 struct LaunchGeom {
     int PW;
     size_t smem_bytes, slot_words, par_words;
-    int blocks;
+    int blocks;     // CTAs to launch
+    int max_blocks; // min(full occupancy, one warp per item)
 };
 
 static int plan_launch(pb_ctx *ctx, int S, const ClassPlan &cp, bool locate, size_t scratch_budget, LaunchGeom *g)
@@ -651,6 +652,7 @@ static int plan_launch(pb_ctx *ctx, int S, const ClassPlan &cp, bool locate, siz
     if (by_mem < 1) return pb_fail(ctx, PB_ERR_NOMEM, "scratch budget %zu too small for one CTA (%zu bytes per alignment)", scratch_budget, slot_bytes);
     blocks = std::max<int64_t>(1, std::min(blocks, by_mem));
     g->blocks = (int)blocks;
+    g->max_blocks = (int)blocks;
     return PB_OK;
 }
 
@@ -658,7 +660,7 @@ static size_t scratch_budget(pb_ctx *ctx)
 {
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); fr = (size_t)8 << 30; }
-    size_t b = (size_t)((double)(fr + ctx->scratch_bytes) * 0.4); // what we already hold counts as available
+    size_t b = (size_t)((double)(fr + ctx->scratch_bytes) * 0.5); // what we already hold counts as available
     if (ctx->scratch_limit && ctx->scratch_limit < b) b = ctx->scratch_limit;
     return b;
 }
@@ -698,6 +700,17 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
             for (auto &kv : geoms) {
                 kv.second.blocks = std::max(1, (int)(kv.second.blocks * f));
                 need += (size_t)kv.second.blocks * ALIGN_WPB * kv.second.slot_words * 4;
+            }
+        } else {
+            // Spend what is left of the budget on extra CTAs for the narrow-band classes (cheap slots): they wait behind
+            // the wide-band kernels launched before them and move onto SMs as those drain, which balances the tail.
+            for (auto &kv : geoms) { // ascending band class
+                LaunchGeom &g = kv.second;
+                const size_t per_block = (size_t)ALIGN_WPB * g.slot_words * 4;
+                const int64_t room = (int64_t)((budget - need) / per_block);
+                const int extra = (int)std::max<int64_t>(0, std::min<int64_t>(room, (int64_t)g.max_blocks - g.blocks));
+                g.blocks += extra;
+                need += (size_t)extra * per_block;
             }
         }
     }
