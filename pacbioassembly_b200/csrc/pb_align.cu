@@ -402,7 +402,8 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
     if ((double)matlen_b < len_b * (1 - R)) return; // seq_aligner.h:114
 
     // ---- find_path, seq_aligner.h:214-233: walk the parent planes back from the goal cell.
-    // Warp-cooperative: lane r holds the parent pair of row i0-r at the path's band word, the next 64 rows are prefetched while the current ones are walked, and runs of MATCH along a
+    // Warp-cooperative: lane r holds the parent pairs of row i0-r around the path's band position (2 band words,
+    // 16 bytes), the next 64 rows are prefetched while the current ones are walked, and runs of MATCH along a
     // diagonal (same band bit, consecutive rows) are found with one ballot and written by as many lanes.
     __syncwarp();
     auto par_pair = [&](int row, int w) -> uint2 { // {MATCH word, INSERT word} of band word w of DP row `row`
@@ -410,14 +411,14 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
         const int L = w / S, s = w - L * S;
         return __ldcg(reinterpret_cast<const uint2 *>(par + (size_t)(row - 1) * (2 * T)) + s * 32 + L);
     };
+    // window = the band word under the path plus the neighbour the path is closer to
+    auto window_base = [](int k) -> int { return (k >> 5) - ((k & 31) < 16 ? 1 : 0); };
     int n = 0;
     {
         int i = matlen_a, j = matlen_b;
         const int guard = len_a + len_b + 1; // a path can never be longer; keeps a corrupted plane from hanging the GPU
-        // window = the band word under the path for 32 consecutive rows (one 8-byte pair per lane); the two following
-        // windows are already in flight.  A path that wanders into the neighbouring word costs one exposed fetch.
-        int cur_i0 = -1, cur_w = 0, nxt_i0 = -1, nxt_w = 0, nx2_i0 = -1, nx2_w = 0;
-        uint2 cw = make_uint2(0u, 0u), nw = cw, mw = cw;
+        int cur_i0 = -1, cur_wb = 0, nxt_i0 = -1, nxt_wb = 0, nx2_i0 = -1, nx2_wb = 0;
+        uint2 c0 = make_uint2(0u, 0u), c1 = c0, n0 = c0, n1 = c0, m0 = c0, m1 = c0;
         while ((i | j) != 0 && n < guard) {
             if (i == 0) { // init_cell row 0: INSERT all the way
                 for (int t = lane; t < j; t += 32) opsrev[n + t] = (uint8_t)PB_INSERT;
@@ -430,20 +431,27 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
                 break;
             }
             const int k = j - i + D, w = k >> 5;
-            if (cur_i0 < 0 || cur_i0 - i >= 32 || w != cur_w) {
-                if (nxt_i0 == i && w == nxt_w) { // the usual case: 32 rows consumed, prediction held
-                    cur_i0 = nxt_i0; cur_w = nxt_w; cw = nw;
-                    nxt_i0 = nx2_i0; nxt_w = nx2_w; nw = mw;
-                } else { // cold start, or the path left the predicted word: fetch now
-                    cur_i0 = i; cur_w = w;
-                    cw = par_pair(cur_i0 - lane, cur_w);
-                    nxt_i0 = cur_i0 - 32; nxt_w = w;
-                    nw = par_pair(nxt_i0 - lane, nxt_w);
+            if (cur_i0 < 0 || cur_i0 - i >= 32 || w < cur_wb || w > cur_wb + 1) {
+                const int wb = window_base(k);
+                if (nxt_i0 == i && w >= nxt_wb && w <= nxt_wb + 1) { // the usual case: 32 rows consumed, prediction held
+                    cur_i0 = nxt_i0; cur_wb = nxt_wb;
+                    c0 = n0; c1 = n1;
+                    nxt_i0 = nx2_i0; nxt_wb = nx2_wb;
+                    n0 = m0; n1 = m1;
+                } else { // cold start or the path left the predicted words: fetch now
+                    cur_i0 = i; cur_wb = wb;
+                    c0 = par_pair(cur_i0 - lane, cur_wb);
+                    c1 = par_pair(cur_i0 - lane, cur_wb + 1);
+                    nxt_i0 = cur_i0 - 32; nxt_wb = wb;
+                    n0 = par_pair(nxt_i0 - lane, nxt_wb);
+                    n1 = par_pair(nxt_i0 - lane, nxt_wb + 1);
                 }
-                nx2_i0 = cur_i0 - 64; nx2_w = w;
-                mw = par_pair(nx2_i0 - lane, nx2_w);
+                nx2_i0 = cur_i0 - 64; nx2_wb = wb; // two windows ahead: DRAM latency under load is several windows long
+                m0 = par_pair(nx2_i0 - lane, nx2_wb);
+                m1 = par_pair(nx2_i0 - lane, nx2_wb + 1);
             }
             const int r0 = cur_i0 - i; // lane that holds the current row
+            const uint2 cw = (w == cur_wb) ? c0 : c1;
             const uint32_t B = __ballot_sync(FULL, (cw.x >> (k & 31)) & 1u) >> r0; // bit t: cell (i-t, j-t) is MATCH
             int run = (~B) ? __ffs(~B) - 1 : 32;
             run = min(min(run, 32 - r0), min(i, j));

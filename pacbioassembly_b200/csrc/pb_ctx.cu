@@ -1,5 +1,6 @@
 // pb_ctx.cu -- context, error reporting, stage timers, device buffers.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "pb_internal.cuh"
 
@@ -58,6 +59,12 @@ extern "C" int pb_ctx_create(int device, pb_ctx **out)
                        prop.major, prop.minor);
     }
     ctx->sm_count = prop.multiProcessorCount;
+    // The traceback reads 8-byte parent pairs scattered over rows: keep DRAM->L2 fills at sector size (a hint)
+    {
+        const char *g = getenv("PB_L2_FETCH");
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g ? (size_t)atoi(g) : 32);
+        cudaGetLastError();
+    }
     PB_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2 * PB_T_COUNT; ++i) PB_CUDA(nullptr, cudaEventCreate(&ctx->ev[i]));
     // keep freed blocks in the pool: per-step allocations become pointer bumps
