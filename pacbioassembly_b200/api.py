@@ -12,7 +12,7 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpacbio_b200.so")
+LIB_PATH = os.environ.get("PB_LIB") or os.path.join(_HERE, "libpacbio_b200.so")  # PB_LIB: experiment builds
 
 MATCH, INSERT, DELETE = 1, 2, 3
 POLICY_LOCATOR, POLICY_REFSEQ = 0, 1

@@ -20,7 +20,17 @@
 #include "pb_internal.cuh"
 
 #define FULL 0xffffffffu
+#ifndef PB_SHIFT_FMA
+#define PB_PLANE_PADBIT 0
+#else
+#define PB_PLANE_PADBIT 1 // one pad bit in front of the Eq planes: the per-row shift becomes 1..32, i.e. a multiply by 2^31..2^0
+#endif
+#ifndef ALIGN_WPB
 #define ALIGN_WPB 4 // warps (alignments in flight) per CTA
+#endif
+#ifndef PB_MINB3
+#define PB_MINB3 6 // resident CTAs per SM asked of ptxas for the narrow-band classes
+#endif
 
 struct SeqView {
     const uint32_t *hi, *lo;
@@ -164,13 +174,37 @@ __device__ __forceinline__ uint32_t addc(uint32_t a, uint32_t b)
     return r;
 }
 
+// Experiment switch -DPB_SHIFT_FMA: issue the five funnel shifts per band word on the FMA pipe as multiplies by powers
+// of two, (lo >> n) | (hi << (32-n)) == mul.hi(lo, 2^(32-n)) + mul.lo(hi, 2^(32-n)), to relieve the integer ALU pipe
+// (ncu: ~86 % busy while the FMA pipe idles).  Measured on B200 (A/B, saturated S=3 launch): 9.3 ms vs 8.4 ms with plain
+// SHF -- two IMADs per shift cost more issue slots than the ALU pipe gains, so the default stays on SHF.
+__device__ __forceinline__ uint32_t mul_hi(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+#ifndef PB_SHIFT_FMA
+#define PB_FUNNEL_R1(lo, hi, c31) __funnelshift_r((lo), (hi), 1)
+#define PB_FUNNEL_L1(lo, hi, c2) __funnelshift_l((lo), (hi), 1)
+#else
+#define PB_FUNNEL_R1(lo, hi, c31) mad_lo((hi), (c31), mul_hi((lo), (c31)))  /* (lo >> 1) | (hi << 31) */
+#define PB_FUNNEL_L1(lo, hi, c2) mad_lo((hi), (c2), mul_hi((lo), (c2)))     /* (hi << 1) | (lo >> 31) */
+#endif
+
 // One band row for the S words of this lane.  pl points at this lane's first Eq word of the row's plane, sh is the
 // row's bit offset inside those words; prow is this lane's pair column (row base + 2*lane) of the row's parent block.  Returns the D0 word of
 // slot sd (the main diagonal lives there in one lane); leaves the row's vertical deltas in Vp/Vn.
 template <int S>
 __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S], const uint32_t (&keep)[S], uint32_t (&Vp)[S],
                                              uint32_t (&Vn)[S], const uint32_t *__restrict__ pl, int thrs, unsigned sh, int lane,
-                                             int sd, bool stores, uint32_t *__restrict__ prow)
+                                             int sd, bool stores, uint32_t *__restrict__ prow, uint32_t c31, uint32_t c2)
 {
     // phase A: slide the band one bit (across words and lanes), fetch Eq, block add with carry-in 0
     uint32_t nx = __shfl_down_sync(FULL, (Hp[0] & 1u) | ((Hn[0] & 1u) << 1), 1);
@@ -179,15 +213,20 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
     // Eq words: logical words x0..x0+S of the plane; for even S the plane is stored with one pad word per S words
     // (bank-conflict-free for the lane stride S), which shows up here as a +1 from slot `thrs` on
     constexpr bool PAD = (S % 2) == 0;
+    const uint32_t eqm = 0x80000000u >> sh; // 2^(31-sh)
     uint32_t plw = pl[0];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
         const uint32_t hp_hi = (s + 1 < S) ? Hp[s + 1] : (nx & 1u);
         const uint32_t hn_hi = (s + 1 < S) ? Hn[s + 1] : (nx >> 1);
-        Hp[s] = __funnelshift_r(Hp[s], hp_hi, 1);
-        Hn[s] = __funnelshift_r(Hn[s], hn_hi, 1);
+        Hp[s] = PB_FUNNEL_R1(Hp[s], hp_hi, c31);
+        Hn[s] = PB_FUNNEL_R1(Hn[s], hn_hi, c31);
         const uint32_t nxt = PAD ? pl[s + 1 + ((s + 1 >= thrs) ? 1 : 0)] : pl[s + 1];
+#ifndef PB_SHIFT_FMA
         Eq[s] = __funnelshift_r(plw, nxt, sh) & keep[s]; // no matches beyond the band's upper edge (see align_one)
+#else
+        Eq[s] = mad_lo(nxt, eqm, mul_hi(plw, eqm)) & keep[s]; // (plw >> (sh+1)) | (nxt << (31-sh)); planes carry a 1-bit pad
+#endif
         plw = nxt;
         x[s] = Eq[s] & Hp[s];
     }
@@ -224,7 +263,7 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
     uint32_t pprev = pv << 31, nprev = (pv >> 1) << 31; // bit 31 = delta entering this word from the left
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        const uint32_t vps = __funnelshift_l(pprev, Vp[s], 1), vns = __funnelshift_l(nprev, Vn[s], 1);
+        const uint32_t vps = PB_FUNNEL_L1(pprev, Vp[s], c2), vns = PB_FUNNEL_L1(nprev, Vn[s], c2);
         pprev = Vp[s];
         nprev = Vn[s];
         const uint32_t Xh = Eq[s] | Hn[s];
@@ -241,7 +280,7 @@ template <int S>
 __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_len, const SeqView &B, int64_t b_bit, int b_len,
                                        double R, int maxn, int maxm, uint32_t *__restrict__ planes, int PW,
                                        uint32_t *__restrict__ par, uint8_t *__restrict__ opsrev, uint8_t *__restrict__ ops_out,
-                                       AlnRes &res)
+                                       uint32_t c31, uint32_t c2, AlnRes &res)
 {
     constexpr int T = 32 * S;
     const int lane = threadIdx.x & 31;
@@ -257,7 +296,7 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
     constexpr bool PAD = (S % 2) == 0; // see row_step: physical index of logical word x is x + x/S for even S
     const int PWn = ((len_a + 31) >> 5) + T + 1;
     for (int x = lane; x < PWn; x += 32) {
-        const int bidx0 = 32 * x - D; // b index of bit 0 of this word
+        const int bidx0 = 32 * x - D - PB_PLANE_PADBIT; // b index of bit 0 of this word
         uint32_t valid;
         if (bidx0 >= len_b || bidx0 + 31 < 0) valid = 0u;
         else {
@@ -300,7 +339,11 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
         keep[s] = kp;
     }
     const int wd = D >> 5, Ld = wd / S, sd = wd % S; // owner of the main-diagonal bit k = D
-    const bool stores = 32 * lane * S <= 2 * D;      // this lane holds at least one in-band bit
+#ifdef PB_STORE_PRED
+    const bool stores = 32 * lane * S <= 2 * D; // this lane holds at least one in-band bit
+#else
+    const bool stores = true; // measured: predicating the pair stores costs 40 % (A/B on B200), the padding writes are cheaper
+#endif
 
     int cii = 0;                          // cost(i,i), warp-uniform, advanced once per 32-row block
     int colc = 0, colbest = 0, col_i = 0; // cost(i,len_b) tracking when len_a > len_b
@@ -325,7 +368,7 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
         uint32_t hist = 0u;
         for (int t = 0; t < tmax; ++t) {
             const int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
-            const uint32_t d0w = row_step<S>(Hp, Hn, keep, Vp, Vn, plq + ca * PW, thrs, (unsigned)t, lane, sd, stores, prow);
+            const uint32_t d0w = row_step<S>(Hp, Hn, keep, Vp, Vn, plq + ca * PW, thrs, (unsigned)t, lane, sd, stores, prow, c31, c2);
             hist |= ((d0w >> (D & 31)) & 1u) << t; // meaningful in the diagonal's owner lane
             prow += 2 * T;
         }
@@ -356,7 +399,7 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
             const int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
             const int q = (i - 1) >> 5;
             row_step<S>(Hp, Hn, keep, Vp, Vn, planes + ca * PW + q + lane * S + (PAD ? lane + q / S : 0), S - q % S, (unsigned)t,
-                        lane, sd, stores, par + (size_t)(i - 1) * (2 * T) + 2 * lane);
+                        lane, sd, stores, par + (size_t)(i - 1) * (2 * T) + 2 * lane, c31, c2);
             const int k = len_b - i + D, wk = k >> 5, Lk = wk / S, sk = wk % S;
             uint32_t vpw = 0u, vnw = 0u;
 #pragma unroll
@@ -487,10 +530,11 @@ struct AlignLaunch {
     uint8_t *ops;
     const int64_t *ops_off;
     unsigned long long *stats; // [0] DP cells computed by K3, [1] alignments run by K3 (may be NULL)
+    uint32_t c31, c2;          // 0x80000000 and 2: shift multipliers handed in as parameters (see mul_hi / mad_lo)
 };
 
 // resident CTAs per SM the register allocation is held to (more warps hide the shuffle / ballot latencies of a row)
-template <int S> struct MinBlocks { static constexpr int v = S <= 3 ? 6 : (S <= 5 ? 5 : (S <= 12 ? 4 : 3)); };
+template <int S> struct MinBlocks { static constexpr int v = (S <= 3 ? PB_MINB3 : (S <= 5 ? 5 : (S <= 12 ? 4 : 3))) * 4 / ALIGN_WPB; };
 
 template <int S>
 __global__ void __launch_bounds__(ALIGN_WPB * 32, MinBlocks<S>::v)
@@ -533,7 +577,7 @@ align_locate_kernel(AlignLaunch p, LocateView lv, const uint8_t *__restrict__ su
                 const int j = q - k * lv.ntrial;
                 const int pos = lv.d_cand_pos[cb + f];
                 align_one<S>(p.A, rbase + j, rlen - j, p.B, lv.ref_base + pos, lv.ref_len - pos, p.R, p.maxn, p.maxm, planes,
-                             p.PW, par, opsrev, p.ops ? p.ops + p.ops_off[k] : nullptr, res);
+                             p.PW, par, opsrev, p.ops ? p.ops + p.ops_off[k] : nullptr, p.c31, p.c2, res);
                 cells += res.cells;
                 if (lane == 0 && p.stats) { atomicAdd(p.stats, (unsigned long long)res.cells); atomicAdd(p.stats + 1, 1ull); }
                 done = f + 1;
@@ -577,7 +621,7 @@ align_pairs_kernel(AlignLaunch p, pb_align_out *__restrict__ out)
         const int k = p.order[idx];
         AlnRes res;
         align_one<S>(p.A, p.A.base[k], p.A.len[k], p.B, p.B.base[k], p.B.len[k], p.R, p.maxn, p.maxm, planes, p.PW, par, opsrev,
-                     p.ops ? p.ops + p.ops_off[k] : nullptr, res);
+                     p.ops ? p.ops + p.ops_off[k] : nullptr, p.c31, p.c2, res);
         if (lane == 0 && p.stats) { atomicAdd(p.stats, (unsigned long long)res.cells); atomicAdd(p.stats + 1, 1ull); }
         if (lane == 0) {
             pb_align_out o;
@@ -830,6 +874,7 @@ int pb_align_locate(pb_ctx *ctx, const pb_seqset *reads, const pb_seqset *ref, c
     base.R = R; base.maxn = maxn; base.maxm = maxm;
     base.ops = d_ops; base.ops_off = d_ops_off;
     base.stats = d_stats;
+    base.c31 = 0x80000000u; base.c2 = 2u;
     return run_classes(ctx, plans, true, base, [&](int S, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
         void *args[] = {(void *)&p, (void *)&lv, (void *)&d_survive, (void *)&d_rej_cells, (void *)&d_recs};
         PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(S, true), dim3(g.blocks), dim3(ALIGN_WPB * 32), args, g.smem_bytes, st));
@@ -872,6 +917,7 @@ int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t 
     base.B = seq_view(B);
     base.R = R; base.maxn = maxn; base.maxm = maxm;
     base.ops = d_ops; base.ops_off = d_ops_off;
+    base.c31 = 0x80000000u; base.c2 = 2u;
     return run_classes(ctx, plans, false, base, [&](int S, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
         void *args[] = {(void *)&p, (void *)&d_out};
         PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(S, false), dim3(g.blocks), dim3(ALIGN_WPB * 32), args, g.smem_bytes, st));

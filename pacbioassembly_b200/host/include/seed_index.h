@@ -8,6 +8,7 @@
 #pragma once
 
 #include <cstring>
+#include <memory>
 #include <list>
 #include <utility>
 #include <vector>
