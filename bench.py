@@ -228,21 +228,15 @@ def main():
 
     kept = int((lens >= 500).sum())
     recs_host = torch.empty(kept * LOCATE_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True).numpy().view(LOCATE_DTYPE)
-    counters = torch.zeros(4, dtype=torch.int64, device="cuda")
+
+    from pacbioassembly_b200 import shard
 
     def final_reduction(recs):
         """the path's only collective: hit/score counters all-reduced, records gathered on rank 0"""
-        f = recs["found"] == 1
-        c = torch.tensor([int(f.sum()), int(recs["cost"][f].sum()), int(recs["cells"].sum()), len(recs)], dtype=torch.int64)
-        counters.copy_(c)
+        tot = shard.reduce_counters(recs, device="cuda")
         if world > 1:
-            dist.all_reduce(counters)
-            buf = torch.zeros(nreads * LOCATE_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
-            raw = torch.from_numpy(recs.view(np.uint8).reshape(-1))
-            buf[: raw.numel()].copy_(raw)
-            gl = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
-            dist.gather(buf, gl, dst=0)
-        return counters.cpu().numpy()
+            shard.gather_records(recs, device="cuda")
+        return tot
 
     state = {}
 
