@@ -17,6 +17,8 @@ struct IngestSrc {
     int packed;             // 1: source is 4-bases-per-byte records (dna_seq.h:113-127)
 };
 
+#define INGEST_RUN 64 // consecutive 32-base words handled by one warp: one owner search, then a forward walk
+
 __global__ void __launch_bounds__(256)
 ingest_kernel(IngestSrc src, const int64_t *__restrict__ base, const int32_t *__restrict__ len, int64_t n,
               int64_t nwords, uint32_t *__restrict__ hi, uint32_t *__restrict__ lo, uint32_t *__restrict__ packed,
@@ -25,46 +27,61 @@ ingest_kernel(IngestSrc src, const int64_t *__restrict__ base, const int32_t *__
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t w = warp0; w < nwords; w += nwarps) {
-        const int64_t g0 = w * 32;
-        // sequence that owns this word: largest i with base[i] <= g0 (bases are multiples of 32)
+    const int64_t nruns = (nwords + INGEST_RUN - 1) / INGEST_RUN;
+    for (int64_t run = warp0; run < nruns; run += nwarps) {
+        const int64_t w_begin = run * INGEST_RUN, w_end = min(nwords, w_begin + INGEST_RUN);
+        // sequence that owns the first word: largest i with base[i] <= g0 (bases are multiples of 32, base[n] = end)
         int64_t a = 0, b = n;
         while (b - a > 1) {
             int64_t m = (a + b) >> 1;
-            if (base[m] <= g0) a = m; else b = m;
+            if (__ldg(base + m) <= w_begin * 32) a = m; else b = m;
         }
-        const int64_t rel = g0 + lane - base[a];
-        const bool valid = n > 0 && rel < (int64_t)len[a];
-        uint32_t code = 3u;
-        bool irregular = false;
-        if (valid) {
-            if (src.packed) {
-                uint32_t byte = src.text[src.toff[a] + (rel >> 2)];
-                code = (byte >> (6 - 2 * (rel & 3))) & 3u;
-            } else {
-                int64_t st = src.tstride ? (int64_t)src.tstride[a] : 1;
-                uint32_t ch = src.text[src.toff[a] + rel * st];
-                code = c2i(ch);
-                irregular = !(ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T');
+        int64_t a_base = n > 0 ? __ldg(base + a) : 0, a_next = n > 0 ? __ldg(base + a + 1) : 0;
+        int64_t a_len = n > 0 ? __ldg(len + a) : 0, a_off = n > 0 ? __ldg(src.toff + a) : 0;
+        int64_t a_st = (n > 0 && src.tstride) ? (int64_t)__ldg(src.tstride + a) : 1;
+        uint32_t irr_acc = 0u;
+        for (int64_t w = w_begin; w < w_end; ++w) {
+            const int64_t g0 = w * 32;
+            while (n > 0 && a + 1 < n && g0 >= a_next) { // walk to the next sequence (warp-uniform)
+                if (irr_acc && lane == 0) atomicOr(&flags[a], PB_FLAG_IRREGULAR);
+                irr_acc = 0u;
+                ++a;
+                a_base = a_next; a_next = __ldg(base + a + 1);
+                a_len = __ldg(len + a); a_off = __ldg(src.toff + a);
+                a_st = src.tstride ? (int64_t)__ldg(src.tstride + a) : 1;
             }
+            const int64_t rel = g0 + lane - a_base;
+            const bool valid = n > 0 && rel < a_len;
+            uint32_t code = 3u;
+            bool irregular = false;
+            if (valid) {
+                if (src.packed) {
+                    uint32_t byte = src.text[a_off + (rel >> 2)];
+                    code = (byte >> (6 - 2 * (rel & 3))) & 3u;
+                } else {
+                    uint32_t ch = src.text[a_off + rel * a_st];
+                    code = c2i(ch);
+                    irregular = !(ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T');
+                }
+            }
+            const uint32_t whi = __ballot_sync(0xffffffffu, code & 2u);
+            const uint32_t wlo = __ballot_sync(0xffffffffu, code & 1u);
+            irr_acc |= __ballot_sync(0xffffffffu, irregular);
+            // packed: byte (lane>>2) of the 8 output bytes; first base of a byte in bits 7:6; bytes little-endian in u32
+            uint32_t v = code << (6 - 2 * (lane & 3));
+            v <<= 8 * ((lane >> 2) & 3);
+            v |= __shfl_xor_sync(0xffffffffu, v, 1);
+            v |= __shfl_xor_sync(0xffffffffu, v, 2);
+            v |= __shfl_xor_sync(0xffffffffu, v, 4);
+            v |= __shfl_xor_sync(0xffffffffu, v, 8);
+            if (lane == 0) {
+                hi[w] = whi;
+                lo[w] = wlo;
+                packed[2 * w] = v;
+            }
+            if (lane == 16) packed[2 * w + 1] = v;
         }
-        const uint32_t whi = __ballot_sync(0xffffffffu, code & 2u);
-        const uint32_t wlo = __ballot_sync(0xffffffffu, code & 1u);
-        const uint32_t irr = __ballot_sync(0xffffffffu, irregular);
-        // packed: byte (lane>>2) of the 8 output bytes; first base of a byte in bits 7:6; bytes little-endian in u32
-        uint32_t v = code << (6 - 2 * (lane & 3));
-        v <<= 8 * ((lane >> 2) & 3);
-        v |= __shfl_xor_sync(0xffffffffu, v, 1);
-        v |= __shfl_xor_sync(0xffffffffu, v, 2);
-        v |= __shfl_xor_sync(0xffffffffu, v, 4);
-        v |= __shfl_xor_sync(0xffffffffu, v, 8);
-        if (lane == 0) {
-            hi[w] = whi;
-            lo[w] = wlo;
-            packed[2 * w] = v;
-            if (irr) atomicOr(&flags[a], PB_FLAG_IRREGULAR);
-        }
-        if (lane == 16) packed[2 * w + 1] = v;
+        if (irr_acc && lane == 0 && n > 0) atomicOr(&flags[a], PB_FLAG_IRREGULAR);
     }
 }
 
@@ -111,7 +128,7 @@ int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, cons
     src.toff = d_toff.as<int64_t>();
     src.tstride = h_stride ? d_stride.as<int32_t>() : nullptr;
     src.packed = packed_src ? 1 : 0;
-    int64_t blocks = std::min<int64_t>((nw + 7) / 8, (int64_t)ctx->sm_count * 16);
+    int64_t blocks = std::min<int64_t>(((nw + INGEST_RUN - 1) / INGEST_RUN + 7) / 8, (int64_t)ctx->sm_count * 16);
     if (blocks < 1) blocks = 1;
     pb_timer_begin(ctx, PB_T_INGEST);
     ingest_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(src, s->d_base.as<int64_t>(), s->d_len.as<int32_t>(), n, nw,
