@@ -293,6 +293,14 @@ def main():
 
     # roofline of the dominant kernel (K3 banded aligner): 2 parent bits written per DP cell
     peak, peak_src = peaks()
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one step's K3 launches, from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "r01_k3_traffic.json")) as f:
+            tj = json.load(f)
+        if args.reads == 100_000:
+            traffic = float(tj["dram_bytes_total"])
+    except Exception:
+        pass
     k3_ms = float(np.mean(align_ms))
     k3_cells = float(np.mean(dp_cells))
     alg_bytes = 0.25 * k3_cells
@@ -357,7 +365,8 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "align_locate_kernel<S> (K3 banded bit-parallel DP + traceback)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": "profiles/r01_k3_traffic.json (ncu, same workload, one step)",
+                         "peak_source": peak_src,
                          "algorithmic": "0.25 B (2 parent bits) per DP cell x cells of the alignments K3 ran",
                          "kernel_ms": k3_ms, "cells_per_step": k3_cells},
             "gcups": gcups,

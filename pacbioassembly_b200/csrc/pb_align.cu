@@ -213,7 +213,9 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
     // Eq words: logical words x0..x0+S of the plane; for even S the plane is stored with one pad word per S words
     // (bank-conflict-free for the lane stride S), which shows up here as a +1 from slot `thrs` on
     constexpr bool PAD = (S % 2) == 0;
+#ifdef PB_SHIFT_FMA
     const uint32_t eqm = 0x80000000u >> sh; // 2^(31-sh)
+#endif
     uint32_t plw = pl[0];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -637,7 +639,7 @@ align_pairs_kernel(AlignLaunch p, pb_align_out *__restrict__ out)
 // host side: size classes, scratch, launches
 // ---------------------------------------------------------------------------------------------
 
-static const int kClasses[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
+static const int kClasses[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16};
 static const int kNumClasses = (int)(sizeof(kClasses) / sizeof(kClasses[0]));
 
 static int class_for_band(int D)
@@ -663,7 +665,7 @@ static const void *kernel_ptr(int S, bool locate)
 {
     switch (S) {
 #define CASE(s) case s: return locate ? KernelSel<s>::locate() : KernelSel<s>::pairs();
-        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(8) CASE(10) CASE(12) CASE(16)
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(14) CASE(16)
 #undef CASE
     }
     return nullptr;

@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""BASELINE config 3: banded-DP sweep, band 32..512 x read length 1..20 kbp, unit costs (the reference's scoring;
+`quality.cpp` is not a scoring function).  Pairs: a = mutated copy of b's prefix with edits spaced so the
+early-failure line cost(i,i) <= i*R is respected (otherwise the pair aborts after ~11 rows and "GCUPS" means nothing),
+R = (band - 0.5) / len so that max_dst == band.
+
+    python tools/dp_sweep.py [npairs] [--check N]     -> JSON lines + a summary table; --check compares N pairs per
+                                                          point with the CPU oracle (bit-exact, transcripts included)
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import workload  # noqa: E402
+from pacbioassembly_b200 import Context  # noqa: E402
+
+
+def main():
+    npairs = int(sys.argv[1]) if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else 4096
+    ncheck = int(sys.argv[sys.argv.index("--check") + 1]) if "--check" in sys.argv else 0
+    ctx = Context(0)
+    oracle = None
+    if ncheck:
+        import cpu_libs
+        oracle = cpu_libs.oracle()
+    rows = []
+    for alen in (1000, 2000, 5000, 10000, 19999):
+        for band in (32, 64, 128, 256, 512):
+            A, B = [], []
+            R = (band - 0.5) / alen
+            t0 = time.time()
+            for k in range(npairs):
+                a, b, R = workload.sweep_pair(1000 * band + alen, k, alen, band)
+                A.append(a)
+                B.append(b)
+            a_blob, b_blob = b"".join(A), b"".join(B)
+            a_len = np.array([len(x) for x in A], dtype=np.int32)
+            b_len = np.array([len(x) for x in B], dtype=np.int32)
+            a_off = np.zeros(npairs, dtype=np.int64); np.cumsum(a_len[:-1], out=a_off[1:])
+            b_off = np.zeros(npairs, dtype=np.int64); np.cumsum(b_len[:-1], out=b_off[1:])
+            best = None
+            for rep in range(3):
+                recs, ops = ctx.align_batch(a_blob, a_off, a_len, b_blob, b_off, b_len, R, 26000, 6000, want_ops=(rep == 0))
+                t = ctx.timings()
+                if rep == 0:
+                    keep_ops = ops
+                best = t["align"] if best is None else min(best, t["align"])
+            cells = int(recs["cells"].sum())
+            ok = int((recs["ret"] >= 0).sum())
+            assert (recs["max_dst"] == band).all(), (alen, band, recs["max_dst"][:4])
+            checked = 0
+            for k in range(min(ncheck, npairs)):
+                w = oracle.align(A[k], B[k], R)
+                for f in ("ret", "matlen_a", "matlen_b", "cost", "diag_cost", "nedit", "fail_row", "cells"):
+                    assert int(recs[f][k]) == w[f], (alen, band, k, f)
+                if w["ret"] >= 0:
+                    assert (keep_ops[k] == w["ops"]).all()
+                checked += 1
+            row = {"len": alen, "band": band, "pairs": npairs, "aligned": ok, "cells": cells, "k3_ms": best,
+                   "gcups": cells / (best / 1e3) / 1e9, "mean_cost": float(recs["cost"][recs["ret"] >= 0].mean()) if ok else None,
+                   "checked_vs_oracle": checked, "gen_s": round(time.time() - t0, 2)}
+            rows.append(row)
+            print(json.dumps(row), flush=True)
+    print("\nlen \\ band " + "".join(f"{b:>9d}" for b in (32, 64, 128, 256, 512)) + "    (GCUPS, K3 kernel time, unit costs)")
+    for alen in (1000, 2000, 5000, 10000, 19999):
+        print(f"{alen:>10d} " + "".join(f"{r['gcups']:9.0f}" for r in rows if r["len"] == alen))
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
