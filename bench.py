@@ -22,6 +22,9 @@ import time
 
 import numpy as np
 
+# one hardware queue per aligner band-class stream (must be set before CUDA is initialised in this process)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:

@@ -780,10 +780,15 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
     for (auto &kv : plans) nitems += kv.second.items.size();
     PB_TRY(d_order.alloc(ctx, nitems * 4 + 16));
     PB_TRY(d_queue.alloc_zero(ctx, (size_t)plans.size() * 4 + 16));
+    // launch order: the class with the most work first (if the device runs fewer kernels concurrently than there are
+    // classes, the light ones are the ones that wait)
+    std::vector<int> launch_order;
+    for (auto &kv : plans) launch_order.push_back(kv.first);
+    std::sort(launch_order.begin(), launch_order.end(), [&](int x, int y) { return plans[x].work > plans[y].work; });
     {
         std::vector<int32_t> all;
         all.reserve(nitems);
-        for (auto it = plans.rbegin(); it != plans.rend(); ++it) all.insert(all.end(), it->second.items.begin(), it->second.items.end());
+        for (int c : launch_order) all.insert(all.end(), plans[c].items.begin(), plans[c].items.end());
         PB_TRY(pb_h2d(ctx, d_order.p, all.data(), nitems * 4));
     }
     // one stream per band class: a class with few, long alignments no longer leaves the other SMs idle
@@ -802,10 +807,9 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
     PB_CUDA(ctx, cudaEventRecord(ctx->fork_event, ctx->stream));
     size_t off = 0, soff = 0;
     int ci = 0;
-    // widest band first: those alignments are the longest running
-    for (auto it = plans.rbegin(); it != plans.rend(); ++it, ++ci) {
-        ClassPlan &cp = it->second;
-        const LaunchGeom &g = geoms[it->first];
+    for (int cls : launch_order) {
+        ClassPlan &cp = plans[cls];
+        const LaunchGeom &g = geoms[cls];
         AlignLaunch p = base;
         p.PW = g.PW;
         p.slot_words = g.slot_words;
@@ -821,16 +825,17 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
             cudaEventCreate(&a); cudaEventCreate(&b);
             tev.push_back(a); tev.push_back(b);
             char buf[256];
-            snprintf(buf, sizeof buf, "S=%d items=%zu blocks=%d rows<=%d band<=%d slotMB=%.2f work=%.3g", kClasses[it->first], cp.items.size(), g.blocks, cp.max_rows, cp.max_D, g.slot_words * 4 / 1048576.0, cp.work);
+            snprintf(buf, sizeof buf, "S=%d items=%zu blocks=%d rows<=%d band<=%d slotMB=%.2f work=%.3g", kClasses[cls], cp.items.size(), g.blocks, cp.max_rows, cp.max_D, g.slot_words * 4 / 1048576.0, cp.work);
             tdesc.push_back(buf);
             cudaEventRecord(a, st);
         }
-        PB_TRY(launch(kClasses[it->first], p, g, st));
+        PB_TRY(launch(kClasses[cls], p, g, st));
         if (trace) cudaEventRecord(tev.back(), st);
         PB_CUDA(ctx, cudaEventRecord(ctx->aux_events[ci], st));
         PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->aux_events[ci], 0));
         off += cp.items.size();
         soff += (size_t)g.blocks * ALIGN_WPB * g.slot_words;
+        ++ci;
     }
     if (trace) { // PB_TRACE=1: per-class device times (classes overlap, so they do not add up)
         cudaStreamSynchronize(ctx->stream);

@@ -43,6 +43,9 @@ extern "C" int pb_ctx_create(int device, pb_ctx **out)
 {
     if (!out) return pb_fail(nullptr, PB_ERR_ARG, "pb_ctx_create: out is NULL");
     *out = nullptr;
+    // The aligner runs one kernel per band class on its own stream (up to 14); the default of 8 hardware queues would
+    // serialise the rest.  Only effective if CUDA has not been initialised in this process yet (bench.py sets it too).
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = pb_device_count();
     if (n <= 0)
         return pb_fail(nullptr, PB_ERR_NO_DEVICE,
