@@ -780,11 +780,11 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
     for (auto &kv : plans) nitems += kv.second.items.size();
     PB_TRY(d_order.alloc(ctx, nitems * 4 + 16));
     PB_TRY(d_queue.alloc_zero(ctx, (size_t)plans.size() * 4 + 16));
-    // launch order: the class with the most work first (if the device runs fewer kernels concurrently than there are
-    // classes, the light ones are the ones that wait)
+    // launch order: widest band first.  Those kernels have few, long-running alignments and must be resident from the
+    // start; the narrow-band kernels behind them are oversubscribed and fill the SMs as CTAs retire.  (Measured: launching
+    // the heaviest class first starves the wide classes, 134 ms vs 105 ms per config-2 step.)
     std::vector<int> launch_order;
-    for (auto &kv : plans) launch_order.push_back(kv.first);
-    std::sort(launch_order.begin(), launch_order.end(), [&](int x, int y) { return plans[x].work > plans[y].work; });
+    for (auto it = plans.rbegin(); it != plans.rend(); ++it) launch_order.push_back(it->first);
     {
         std::vector<int32_t> all;
         all.reserve(nitems);
