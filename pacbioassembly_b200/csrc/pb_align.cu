@@ -37,6 +37,12 @@ struct SeqView {
     const int64_t *base;
     const int32_t *len;
     int64_t nwords; // addressable words (line + guard)
+    // bytes outside {A,C,G,T} (byte-exact DP path): position plane, sorted exception list, per-sequence value tables
+    const uint32_t *irr;
+    const int64_t *exc_pos;
+    const uint8_t *exc_val;
+    int64_t nexc;
+    const uint32_t *tab;
 };
 
 static SeqView seq_view(const pb_seqset *s)
@@ -47,6 +53,11 @@ static SeqView seq_view(const pb_seqset *s)
     v.base = s->d_base.as<int64_t>();
     v.len = s->d_len.as<int32_t>();
     v.nwords = s->nwords() + 4;
+    v.irr = s->d_irr.as<uint32_t>();
+    v.exc_pos = s->d_exc_pos.as<int64_t>();
+    v.exc_val = s->d_exc_val.as<uint8_t>();
+    v.nexc = s->nexc;
+    v.tab = s->d_tab.as<uint32_t>();
     return v;
 }
 
@@ -58,6 +69,33 @@ __device__ __forceinline__ uint32_t load_window(const uint32_t *__restrict__ arr
     const uint32_t w0 = (wi >= 0 && wi < nwords) ? __ldg(arr + wi) : 0u;
     const uint32_t w1 = (wi + 1 >= 0 && wi + 1 < nwords) ? __ldg(arr + wi + 1) : 0u;
     return __funnelshift_r(w0, w1, sh);
+}
+
+// first exception with line position >= g
+__device__ __forceinline__ int64_t exc_lower_bound(const SeqView &V, int64_t g)
+{
+    int64_t a = 0, b = V.nexc;
+    while (a < b) {
+        const int64_t m = (a + b) >> 1;
+        if (__ldg(V.exc_pos + m) < g) a = m + 1; else b = m;
+    }
+    return a;
+}
+// slot (0..3) of byte v in a sequence's table of non-ACGT values, or -1
+__device__ __forceinline__ int tab_slot(uint32_t tab, uint32_t v)
+{
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        if (((tab >> (8 * t)) & 0xFFu) == v) return t;
+    return -1;
+}
+
+// Eq plane (4..7) for a row whose seg_a element is a non-ACGT byte: look the byte up in the exception list
+__device__ __forceinline__ int irr_plane(const SeqView &A, int64_t g, uint32_t a_tab)
+{
+    const int64_t e = exc_lower_bound(A, g);
+    const int slot = (e < A.nexc && __ldg(A.exc_pos + e) == g) ? tab_slot(a_tab, A.exc_val[e]) : -1;
+    return 4 + (slot < 0 ? 0 : slot); // slot < 0 cannot happen for a sequence the host admitted (<= 4 distinct values)
 }
 
 // seq_aligner.h:94-102
@@ -114,6 +152,11 @@ prefilter_kernel(SeqView A, SeqView B, LocateView lv, int64_t ncand, double R, i
         return;
     }
     const int K = min(min(32, D), min(len_a, len_b));
+    if (load_window(A.irr, A.nwords, a_bit) | load_window(B.irr, B.nwords, b_bit)) { // raw-byte compare needed: not here
+        survive[c] = 1;
+        rej_cells[c] = 0;
+        return;
+    }
     const uint32_t ahi = load_window(A.hi, A.nwords, a_bit), alo = load_window(A.lo, A.nwords, a_bit);
     const uint32_t bhi = load_window(B.hi, B.nwords, b_bit), blo = load_window(B.lo, B.nwords, b_bit);
     const uint32_t peq0 = ~bhi & ~blo, peq1 = ~bhi & blo, peq2 = bhi & ~blo, peq3 = bhi & blo;
@@ -278,8 +321,8 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
     return d0w;
 }
 
-template <int S>
-__device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_len, const SeqView &B, int64_t b_bit, int b_len,
+template <int S, bool IRR>
+__device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_len, uint32_t a_tab, const SeqView &B, int64_t b_bit, int b_len,
                                        double R, int maxn, int maxm, uint32_t *__restrict__ planes, int PW,
                                        uint32_t *__restrict__ par, uint8_t *__restrict__ opsrev, uint8_t *__restrict__ ops_out,
                                        uint32_t c31, uint32_t c2, AlnRes &res)
@@ -310,12 +353,28 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
         if (valid) {
             hi = load_window(B.hi, B.nwords, b_bit + bidx0);
             lo = load_window(B.lo, B.nwords, b_bit + bidx0);
+            if (IRR) valid &= ~load_window(B.irr, B.nwords, b_bit + bidx0); // a non-ACGT byte equals none of A,C,G,T
         }
         const int px = PAD ? x + x / S : x;
         planes[0 * PW + px] = ~hi & ~lo & valid;
         planes[1 * PW + px] = ~hi & lo & valid;
         planes[2 * PW + px] = hi & ~lo & valid;
         planes[3 * PW + px] = hi & lo & valid;
+        if (IRR) {
+            planes[4 * PW + px] = 0u; planes[5 * PW + px] = 0u; planes[6 * PW + px] = 0u; planes[7 * PW + px] = 0u;
+        }
+    }
+    if (IRR) { // planes 4..7: seg_b equals the k-th non-ACGT byte value of seg_a's sequence (raw compare, seq_aligner.h:136)
+        __syncwarp();
+        const int64_t e0 = exc_lower_bound(B, b_bit), e1 = exc_lower_bound(B, b_bit + len_b);
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            const int slot = tab_slot(a_tab, B.exc_val[e]);
+            if (slot >= 0) { // unused table slots hold 'A', which never shows up in the exception list
+                const int t = (int)(B.exc_pos[e] - b_bit) + D + PB_PLANE_PADBIT;
+                const int x = t >> 5, px = PAD ? x + x / S : x;
+                atomicOr(&planes[(4 + slot) * PW + px], 1u << (t & 31));
+            }
+        }
     }
     __syncwarp();
 
@@ -362,6 +421,7 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
         const uint32_t awh = awh_n, awl = awl_n; // this block's 32 bases of seg_a (warp-uniform); fetch the next block's now
         awh_n = load_window(A.hi, A.nwords, a_bit + i0 + 31);
         awl_n = load_window(A.lo, A.nwords, a_bit + i0 + 31);
+        const uint32_t awi = IRR ? load_window(A.irr, A.nwords, a_bit + i0 - 1) : 0u;
         const int thr = (int)((i0 + lane) * R); // cost > i*R  <=>  cost > floor(i*R) for an integer cost
         const int q = (i0 - 1) >> 5; // first plane word of the block's rows (logical index)
         const uint32_t *plq = planes + q + lane * S + (PAD ? lane + q / S : 0);
@@ -369,7 +429,8 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
         uint32_t *prow = par + (size_t)(i0 - 1) * (2 * T) + 2 * lane;
         uint32_t hist = 0u;
         for (int t = 0; t < tmax; ++t) {
-            const int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
+            int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
+            if (IRR && ((awi >> t) & 1u)) ca = irr_plane(A, a_bit + i0 - 1 + t, a_tab);
             const uint32_t d0w = row_step<S>(Hp, Hn, keep, Vp, Vn, plq + ca * PW, thrs, (unsigned)t, lane, sd, stores, prow, c31, c2);
             hist |= ((d0w >> (D & 31)) & 1u) << t; // meaningful in the diagonal's owner lane
             prow += 2 * T;
@@ -391,14 +452,16 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
     if (!fail_row && len_a > len_b) {
         colc = colbest = cii;
         col_i = len_b;
-        uint32_t awh = 0u, awl = 0u;
+        uint32_t awh = 0u, awl = 0u, awi = 0u;
         for (int i = len_b + 1; i <= len_a; ++i) {
             const int t = (i - 1) & 31;
             if (t == 0 || i == len_b + 1) {
                 awh = load_window(A.hi, A.nwords, a_bit + (i - 1 - t));
                 awl = load_window(A.lo, A.nwords, a_bit + (i - 1 - t));
+                if (IRR) awi = load_window(A.irr, A.nwords, a_bit + (i - 1 - t));
             }
-            const int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
+            int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
+            if (IRR && ((awi >> t) & 1u)) ca = irr_plane(A, a_bit + i - 1, a_tab);
             const int q = (i - 1) >> 5;
             row_step<S>(Hp, Hn, keep, Vp, Vn, planes + ca * PW + q + lane * S + (PAD ? lane + q / S : 0), S - q % S, (unsigned)t,
                         lane, sd, stores, par + (size_t)(i - 1) * (2 * T) + 2 * lane, c31, c2);
@@ -538,14 +601,14 @@ struct AlignLaunch {
 // resident CTAs per SM the register allocation is held to (more warps hide the shuffle / ballot latencies of a row)
 template <int S> struct MinBlocks { static constexpr int v = (S <= 3 ? PB_MINB3 : (S <= 5 ? 5 : (S <= 12 ? 4 : 3))) * 4 / ALIGN_WPB; };
 
-template <int S>
+template <int S, bool IRR>
 __global__ void __launch_bounds__(ALIGN_WPB * 32, MinBlocks<S>::v)
 align_locate_kernel(AlignLaunch p, LocateView lv, const uint8_t *__restrict__ survive, const int32_t *__restrict__ rej_cells,
                     pb_locate_rec *__restrict__ recs)
 {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *planes = smem + (size_t)warp * 4 * p.PW;
+    uint32_t *planes = smem + (size_t)warp * (IRR ? 8 : 4) * p.PW;
     const size_t slot = (size_t)blockIdx.x * ALIGN_WPB + warp;
     uint32_t *par = p.scratch + slot * p.slot_words;
     uint8_t *opsrev = reinterpret_cast<uint8_t *>(par + p.par_words);
@@ -578,7 +641,7 @@ align_locate_kernel(AlignLaunch p, LocateView lv, const uint8_t *__restrict__ su
                 const int q = lv.d_cand_q[cb + f];
                 const int j = q - k * lv.ntrial;
                 const int pos = lv.d_cand_pos[cb + f];
-                align_one<S>(p.A, rbase + j, rlen - j, p.B, lv.ref_base + pos, lv.ref_len - pos, p.R, p.maxn, p.maxm, planes,
+                align_one<S, IRR>(p.A, rbase + j, rlen - j, IRR ? p.A.tab[r] : 0u, p.B, lv.ref_base + pos, lv.ref_len - pos, p.R, p.maxn, p.maxm, planes,
                              p.PW, par, opsrev, p.ops ? p.ops + p.ops_off[k] : nullptr, p.c31, p.c2, res);
                 cells += res.cells;
                 if (lane == 0 && p.stats) { atomicAdd(p.stats, (unsigned long long)res.cells); atomicAdd(p.stats + 1, 1ull); }
@@ -605,13 +668,13 @@ align_locate_kernel(AlignLaunch p, LocateView lv, const uint8_t *__restrict__ su
     }
 }
 
-template <int S>
+template <int S, bool IRR>
 __global__ void __launch_bounds__(ALIGN_WPB * 32, MinBlocks<S>::v)
 align_pairs_kernel(AlignLaunch p, pb_align_out *__restrict__ out)
 {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *planes = smem + (size_t)warp * 4 * p.PW;
+    uint32_t *planes = smem + (size_t)warp * (IRR ? 8 : 4) * p.PW;
     const size_t slot = (size_t)blockIdx.x * ALIGN_WPB + warp;
     uint32_t *par = p.scratch + slot * p.slot_words;
     uint8_t *opsrev = reinterpret_cast<uint8_t *>(par + p.par_words);
@@ -622,7 +685,7 @@ align_pairs_kernel(AlignLaunch p, pb_align_out *__restrict__ out)
         if (idx >= p.nitems) break;
         const int k = p.order[idx];
         AlnRes res;
-        align_one<S>(p.A, p.A.base[k], p.A.len[k], p.B, p.B.base[k], p.B.len[k], p.R, p.maxn, p.maxm, planes, p.PW, par, opsrev,
+        align_one<S, IRR>(p.A, p.A.base[k], p.A.len[k], IRR ? p.A.tab[k] : 0u, p.B, p.B.base[k], p.B.len[k], p.R, p.maxn, p.maxm, planes, p.PW, par, opsrev,
                      p.ops ? p.ops + p.ops_off[k] : nullptr, p.c31, p.c2, res);
         if (lane == 0 && p.stats) { atomicAdd(p.stats, (unsigned long long)res.cells); atomicAdd(p.stats + 1, 1ull); }
         if (lane == 0) {
@@ -639,14 +702,23 @@ align_pairs_kernel(AlignLaunch p, pb_align_out *__restrict__ out)
 // host side: size classes, scratch, launches
 // ---------------------------------------------------------------------------------------------
 
+// Band classes.  A class key is S (band words per lane) for plain ACGT input, 1000 + S for the byte-exact variant
+// (8 Eq planes) that pairs holding other bytes take; such input is rare, so three sizes are enough there.
 static const int kClasses[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16};
-static const int kNumClasses = (int)(sizeof(kClasses) / sizeof(kClasses[0]));
+static const int kIrrClasses[] = {2, 6, 16};
+static inline int key_S(int key) { return key % 1000; }
+static inline bool key_irr(int key) { return key >= 1000; }
 
-static int class_for_band(int D)
-{ // smallest S with 32*S words >= ceil((2D+1)/32)
+static int class_for_band(int D, bool irr)
+{ // smallest S with 32*S words >= ceil((2D+1)/32); returns the class key or -1
     const int NW = (2 * D + 1 + 31) >> 5;
-    for (int c = 0; c < kNumClasses; ++c)
-        if (32 * kClasses[c] >= NW) return c;
+    if (irr) {
+        for (int S : kIrrClasses)
+            if (32 * S >= NW) return 1000 + S;
+        return -1;
+    }
+    for (int S : kClasses)
+        if (32 * S >= NW) return S;
     return -1;
 }
 
@@ -656,15 +728,24 @@ struct ClassPlan {
     double work = 0; // estimated instruction count of the class: its share of the machine
 };
 
-template <int S> struct KernelSel {
-    static const void *locate() { return (const void *)align_locate_kernel<S>; }
-    static const void *pairs() { return (const void *)align_pairs_kernel<S>; }
+template <int S, bool IRR> struct KernelSel {
+    static const void *locate() { return (const void *)align_locate_kernel<S, IRR>; }
+    static const void *pairs() { return (const void *)align_pairs_kernel<S, IRR>; }
 };
 
-static const void *kernel_ptr(int S, bool locate)
+static const void *kernel_ptr(int key, bool locate)
 {
+    const int S = key_S(key);
+    if (key_irr(key)) {
+        switch (S) {
+#define CASE(s) case s: return locate ? KernelSel<s, true>::locate() : KernelSel<s, true>::pairs();
+            CASE(2) CASE(6) CASE(16)
+#undef CASE
+        }
+        return nullptr;
+    }
     switch (S) {
-#define CASE(s) case s: return locate ? KernelSel<s>::locate() : KernelSel<s>::pairs();
+#define CASE(s) case s: return locate ? KernelSel<s, false>::locate() : KernelSel<s, false>::pairs();
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(14) CASE(16)
 #undef CASE
     }
@@ -678,16 +759,16 @@ struct LaunchGeom {
     int max_blocks; // min(full occupancy, one warp per item)
 };
 
-static int plan_launch(pb_ctx *ctx, int S, const ClassPlan &cp, bool locate, size_t scratch_budget, LaunchGeom *g)
+static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, bool locate, size_t scratch_budget, LaunchGeom *g)
 {
-    const int T = 32 * S;
+    const int S = key_S(key), T = 32 * S;
     const int logical = ((cp.max_rows + 31) >> 5) + T + 2;
     g->PW = logical + ((S % 2) == 0 ? logical / S + 2 : 0); // even S: one pad word per S words (bank conflicts)
-    g->smem_bytes = (size_t)ALIGN_WPB * 4 * g->PW * sizeof(uint32_t);
+    g->smem_bytes = (size_t)ALIGN_WPB * (key_irr(key) ? 8 : 4) * g->PW * sizeof(uint32_t);
     g->par_words = (size_t)std::max(cp.max_rows, 1) * 2 * T;
     const size_t ops_bytes = ((size_t)2 * cp.max_rows + cp.max_D + 64 + 127) & ~(size_t)127; // keeps every slot 128 B aligned
     g->slot_words = g->par_words + ops_bytes / 4;
-    const void *fn = kernel_ptr(S, locate);
+    const void *fn = kernel_ptr(key, locate);
     if (g->smem_bytes > 200 * 1024) return pb_fail(ctx, PB_ERR_DOMAIN, "sequence of %d rows needs %zu bytes of shared memory per CTA", cp.max_rows, g->smem_bytes);
     PB_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes));
     int occ = 0;
@@ -723,7 +804,7 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
     size_t need = 0;
     for (auto &kv : plans) {
         LaunchGeom g;
-        PB_TRY(plan_launch(ctx, kClasses[kv.first], kv.second, locate, budget, &g));
+        PB_TRY(plan_launch(ctx, kv.first, kv.second, locate, budget, &g));
         geoms[kv.first] = g;
         need += (size_t)g.blocks * ALIGN_WPB * g.slot_words * 4;
     }
@@ -825,11 +906,11 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
             cudaEventCreate(&a); cudaEventCreate(&b);
             tev.push_back(a); tev.push_back(b);
             char buf[256];
-            snprintf(buf, sizeof buf, "S=%d items=%zu blocks=%d rows<=%d band<=%d slotMB=%.2f work=%.3g", kClasses[cls], cp.items.size(), g.blocks, cp.max_rows, cp.max_D, g.slot_words * 4 / 1048576.0, cp.work);
+            snprintf(buf, sizeof buf, "S=%d%s items=%zu blocks=%d rows<=%d band<=%d slotMB=%.2f work=%.3g", key_S(cls), key_irr(cls) ? "x" : "", cp.items.size(), g.blocks, cp.max_rows, cp.max_D, g.slot_words * 4 / 1048576.0, cp.work);
             tdesc.push_back(buf);
             cudaEventRecord(a, st);
         }
-        PB_TRY(launch(kClasses[cls], p, g, st));
+        PB_TRY(launch(cls, p, g, st));
         if (trace) cudaEventRecord(tev.back(), st);
         PB_CUDA(ctx, cudaEventRecord(ctx->aux_events[ci], st));
         PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->aux_events[ci], 0));
@@ -852,9 +933,9 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
 }
 
 int pb_align_locate(pb_ctx *ctx, const pb_seqset *reads, const pb_seqset *ref, const LocateView &lv, int64_t nkept,
-                    const std::vector<int32_t> &kept_lens, double R, int maxn, int maxm, const uint8_t *d_survive,
-                    const int32_t *d_rej_cells, pb_locate_rec *d_recs, uint8_t *d_ops, const int64_t *d_ops_off,
-                    unsigned long long *d_stats)
+                    const std::vector<int32_t> &kept_lens, const std::vector<uint8_t> &kept_irr, double R, int maxn, int maxm,
+                    const uint8_t *d_survive, const int32_t *d_rej_cells, pb_locate_rec *d_recs, uint8_t *d_ops,
+                    const int64_t *d_ops_off, unsigned long long *d_stats)
 {
     if (nkept == 0) return PB_OK;
     std::map<int, ClassPlan> plans;
@@ -866,13 +947,13 @@ int pb_align_locate(pb_ctx *ctx, const pb_seqset *reads, const pb_seqset *ref, c
         // widest band / longest seg_a any candidate of this read can reach the DP with: len_a <= L, and the domain
         // check (seq_aligner.h:104) turns away len_a >= maxn or max_dst >= maxm before any row is computed
         const int D = std::min(1 + (int)(L * R), maxm - 1);
-        const int cls = class_for_band(std::max(D, 1));
+        const int cls = class_for_band(std::max(D, 1), kept_irr[k] != 0); // reads (or a contig) with non-ACGT bytes: byte-exact variant
         if (cls < 0) return pb_fail(ctx, PB_ERR_DOMAIN, "band half-width %d exceeds PB_MAX_BAND", D);
         ClassPlan &cp = plans[cls];
         cp.items.push_back(k);
         cp.max_rows = std::max(cp.max_rows, std::min(L, std::max(maxn - 1, 1)));
         cp.max_D = std::max(cp.max_D, D);
-        cp.work += (double)L * (30.0 * kClasses[cls] + 60.0); // ~instructions: rows x (per-word + per-row cost)
+        cp.work += (double)L * (30.0 * key_S(cls) + 60.0); // ~instructions: rows x (per-word + per-row cost)
     }
     AlignLaunch base;
     memset(&base, 0, sizeof base);
@@ -882,9 +963,9 @@ int pb_align_locate(pb_ctx *ctx, const pb_seqset *reads, const pb_seqset *ref, c
     base.ops = d_ops; base.ops_off = d_ops_off;
     base.stats = d_stats;
     base.c31 = 0x80000000u; base.c2 = 2u;
-    return run_classes(ctx, plans, true, base, [&](int S, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
+    return run_classes(ctx, plans, true, base, [&](int key, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
         void *args[] = {(void *)&p, (void *)&lv, (void *)&d_survive, (void *)&d_rej_cells, (void *)&d_recs};
-        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(S, true), dim3(g.blocks), dim3(ALIGN_WPB * 32), args, g.smem_bytes, st));
+        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(key, true), dim3(g.blocks), dim3(ALIGN_WPB * 32), args, g.smem_bytes, st));
         ctx->launches++;
         return PB_OK;
     });
@@ -905,9 +986,9 @@ int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t 
     std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return (int64_t)la[x] * D[x] > (int64_t)la[y] * D[y]; });
     for (int32_t k : order) {
         const bool rejected = la[k] >= maxn || D[k] >= maxm;
-        int cls = 0;
+        int cls = 1; // rejected by the domain check: any kernel will do, nothing is computed
         if (!rejected) {
-            cls = class_for_band(D[k]);
+            cls = class_for_band(D[k], ((A->flags[k] | B->flags[k]) & PB_FLAG_IRREGULAR) != 0);
             if (cls < 0) return pb_fail(ctx, PB_ERR_DOMAIN, "band half-width %d exceeds PB_MAX_BAND", D[k]);
         }
         ClassPlan &cp = plans[cls];
@@ -915,7 +996,7 @@ int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t 
         if (!rejected) {
             cp.max_rows = std::max(cp.max_rows, la[k]);
             cp.max_D = std::max(cp.max_D, D[k]);
-            cp.work += (double)la[k] * (30.0 * kClasses[cls] + 60.0);
+            cp.work += (double)la[k] * (30.0 * key_S(cls) + 60.0);
         }
     }
     AlignLaunch base;
@@ -925,9 +1006,9 @@ int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t 
     base.R = R; base.maxn = maxn; base.maxm = maxm;
     base.ops = d_ops; base.ops_off = d_ops_off;
     base.c31 = 0x80000000u; base.c2 = 2u;
-    return run_classes(ctx, plans, false, base, [&](int S, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
+    return run_classes(ctx, plans, false, base, [&](int key, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
         void *args[] = {(void *)&p, (void *)&d_out};
-        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(S, false), dim3(g.blocks), dim3(ALIGN_WPB * 32), args, g.smem_bytes, st));
+        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(key, false), dim3(g.blocks), dim3(ALIGN_WPB * 32), args, g.smem_bytes, st));
         ctx->launches++;
         return PB_OK;
     });

@@ -106,9 +106,13 @@ struct pb_seqset {
     std::vector<int32_t> len;
     std::vector<uint32_t> flags;
     DevBuf d_base, d_len, d_flags, d_hi, d_lo, d_packed;
-    // optional raw text kept on the device for the byte-exact path: element k of sequence i is
-    // d_text[toff[i] + k*tstride[i]]
-    DevBuf d_text, d_toff, d_tstride;
+    // Bytes outside {A,C,G,T}: they seed as code 3 exactly like the reference (C2I), but the DP compares raw bytes
+    // (seq_aligner.h:136).  d_irr marks their positions on the line (bit plane); the bytes themselves are kept as a
+    // sorted exception list (line position, value); tab[i] holds the (at most 4) distinct such values of sequence i.
+    DevBuf d_irr, d_exc_pos, d_exc_val, d_tab;
+    int64_t nexc = 0;
+    std::vector<uint32_t> tab;      // 4 byte values packed little-endian
+    std::vector<uint8_t> tab_count; // 0..4, 255 = more than four distinct values
     int64_t nwords() const { return total / 32; }
 };
 
@@ -178,7 +182,8 @@ struct LocateView { // everything the aligner needs to derive candidate (a,b) vi
 int pb_prefilter(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, const LocateView &lv, int64_t ncand, double R,
                  int maxn, int maxm, uint8_t *d_survive, int32_t *d_rej_cells);
 int pb_align_locate(pb_ctx *ctx, const pb_seqset *reads, const pb_seqset *ref, const LocateView &lv, int64_t nkept,
-                    const std::vector<int32_t> &kept_lens, double R, int maxn, int maxm, const uint8_t *d_survive,
+                    const std::vector<int32_t> &kept_lens, const std::vector<uint8_t> &kept_irr, double R, int maxn, int maxm,
+                    const uint8_t *d_survive,
                     const int32_t *d_rej_cells, pb_locate_rec *d_recs, uint8_t *d_ops, const int64_t *d_ops_off,
                     unsigned long long *d_stats);
 int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t n, double R, int maxn, int maxm,

@@ -16,12 +16,12 @@ extern "C" void pb_locate_default_params(pb_locate_params *p)
     p->reserved = 0;
 }
 
-static int check_regular(pb_ctx *ctx, const pb_seqset *s, const char *what)
+// The byte-exact aligner variant keeps one Eq plane per distinct non-ACGT byte value of seg_a's sequence, four at most.
+static int check_tables(pb_ctx *ctx, const pb_seqset *s, const char *what)
 {
     for (int64_t i = 0; i < s->n; ++i)
-        if (s->flags[i] & PB_FLAG_IRREGULAR)
-            return pb_fail(ctx, PB_ERR_ALPHABET, "%s %lld holds bytes outside {A,C,G,T}; the banded aligner compares raw bytes "
-                           "(seq_aligner.h:136) and only takes plain ACGT input", what, (long long)i);
+        if (s->tab_count[i] == 255)
+            return pb_fail(ctx, PB_ERR_ALPHABET, "%s %lld holds more than four distinct byte values outside {A,C,G,T}", what, (long long)i);
     return PB_OK;
 }
 
@@ -43,8 +43,7 @@ extern "C" int pb_align_batch(pb_ctx *ctx, const char *a_text, const int64_t *a_
     pb_seqset *A = nullptr, *B = nullptr;
     int r = pb_seqset_from_text(ctx, a_text, a_off, a_len, a_stride, n, &A);
     if (r == PB_OK) r = pb_seqset_from_text(ctx, b_text, b_off, b_len, b_stride, n, &B);
-    if (r == PB_OK) r = check_regular(ctx, A, "seg_a of pair");
-    if (r == PB_OK) r = check_regular(ctx, B, "seg_b of pair");
+    if (r == PB_OK) r = check_tables(ctx, A, "seg_a of pair");
     DevBuf d_out, d_ops, d_ops_off;
     int64_t extent = 0;
     if (r == PB_OK) r = d_out.alloc_zero(ctx, (size_t)n * sizeof(pb_align_out));
@@ -113,9 +112,7 @@ extern "C" int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *r
     if (ref->len[ref_seq] != ix->ref_len) return pb_fail(ctx, PB_ERR_ARG, "index was built over a different sequence");
     *out = nullptr;
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
-    PB_TRY(check_regular(ctx, reads, "read"));
-    if (ref->flags[ref_seq] & PB_FLAG_IRREGULAR)
-        return pb_fail(ctx, PB_ERR_ALPHABET, "the contig holds bytes outside {A,C,G,T}");
+    PB_TRY(check_tables(ctx, reads, "read"));
 
     pb_locate_job *job = new pb_locate_job();
     job->ctx = ctx;
@@ -124,8 +121,14 @@ extern "C" int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *r
 #define TRYJ(x) do { r = (x); if (r != PB_OK) { delete job; return r; } } while (0)
     // kept reads: len >= minlen, nseq = rank among kept (locator.cpp:72, SURVEY Q-L1)
     std::vector<int32_t> kept, kept_lens;
+    std::vector<uint8_t> kept_irr;
+    const bool ref_irr = (ref->flags[ref_seq] & PB_FLAG_IRREGULAR) != 0;
     for (int64_t i = 0; i < reads->n; ++i)
-        if (reads->len[i] >= prm->minlen) { kept.push_back((int32_t)i); kept_lens.push_back(reads->len[i]); }
+        if (reads->len[i] >= prm->minlen) {
+            kept.push_back((int32_t)i);
+            kept_lens.push_back(reads->len[i]);
+            kept_irr.push_back((ref_irr || (reads->flags[i] & PB_FLAG_IRREGULAR)) ? 1 : 0);
+        }
     const int64_t nkept = (int64_t)kept.size();
     job->nkept = nkept;
     TRYJ(job->d_recs.alloc_zero(ctx, (size_t)std::max<int64_t>(nkept, 1) * sizeof(pb_locate_rec)));
@@ -171,7 +174,7 @@ extern "C" int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *r
     TRYJ(pb_prefilter(ctx, reads, ref, lv, po.ncand, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(), d_rej.as<int32_t>()));
     pb_timer_end(ctx, PB_T_PREFILTER);
     pb_timer_begin(ctx, PB_T_ALIGN);
-    TRYJ(pb_align_locate(ctx, reads, ref, lv, nkept, kept_lens, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(),
+    TRYJ(pb_align_locate(ctx, reads, ref, lv, nkept, kept_lens, kept_irr, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(),
                          d_rej.as<int32_t>(), job->d_recs.as<pb_locate_rec>(), prm->want_ops ? job->d_ops.as<uint8_t>() : nullptr,
                          prm->want_ops ? d_ops_off.as<int64_t>() : nullptr, job->d_stats.as<unsigned long long>()));
     pb_timer_end(ctx, PB_T_ALIGN);

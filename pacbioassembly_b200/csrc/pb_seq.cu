@@ -22,7 +22,7 @@ struct IngestSrc {
 __global__ void __launch_bounds__(256)
 ingest_kernel(IngestSrc src, const int64_t *__restrict__ base, const int32_t *__restrict__ len, int64_t n,
               int64_t nwords, uint32_t *__restrict__ hi, uint32_t *__restrict__ lo, uint32_t *__restrict__ packed,
-              uint32_t *__restrict__ flags)
+              uint32_t *__restrict__ irr, uint32_t *__restrict__ flags, unsigned long long *__restrict__ nirr)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -66,7 +66,8 @@ ingest_kernel(IngestSrc src, const int64_t *__restrict__ base, const int32_t *__
             }
             const uint32_t whi = __ballot_sync(0xffffffffu, code & 2u);
             const uint32_t wlo = __ballot_sync(0xffffffffu, code & 1u);
-            irr_acc |= __ballot_sync(0xffffffffu, irregular);
+            const uint32_t wirr = __ballot_sync(0xffffffffu, irregular);
+            irr_acc |= wirr;
             // packed: byte (lane>>2) of the 8 output bytes; first base of a byte in bits 7:6; bytes little-endian in u32
             uint32_t v = code << (6 - 2 * (lane & 3));
             v <<= 8 * ((lane >> 2) & 3);
@@ -77,11 +78,40 @@ ingest_kernel(IngestSrc src, const int64_t *__restrict__ base, const int32_t *__
             if (lane == 0) {
                 hi[w] = whi;
                 lo[w] = wlo;
+                irr[w] = wirr;
                 packed[2 * w] = v;
+                if (wirr) atomicAdd(nirr, (unsigned long long)__popc(wirr));
             }
             if (lane == 16) packed[2 * w + 1] = v;
         }
         if (irr_acc && lane == 0 && n > 0) atomicOr(&flags[a], PB_FLAG_IRREGULAR);
+    }
+}
+
+// second pass, only when the set holds bytes outside {A,C,G,T}: list them as (line position, byte)
+__global__ void __launch_bounds__(256)
+collect_exceptions_kernel(IngestSrc src, const int64_t *__restrict__ base, const int32_t *__restrict__ len, int64_t n,
+                          int64_t nwords, const uint32_t *__restrict__ irr, unsigned long long *__restrict__ cursor,
+                          int64_t *__restrict__ exc_pos, uint8_t *__restrict__ exc_val, int32_t *__restrict__ exc_seq)
+{
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwords) return;
+    uint32_t m = irr[w];
+    if (!m) return;
+    int64_t a = 0, b = n;
+    while (b - a > 1) {
+        int64_t mid = (a + b) >> 1;
+        if (base[mid] <= w * 32) a = mid; else b = mid;
+    }
+    const int64_t st = src.tstride ? (int64_t)src.tstride[a] : 1;
+    while (m) {
+        const int t = __ffs(m) - 1;
+        m &= m - 1;
+        const int64_t g = w * 32 + t, rel = g - base[a];
+        const unsigned long long slot = atomicAdd(cursor, 1ull);
+        exc_pos[slot] = g;
+        exc_val[slot] = src.text[src.toff[a] + rel * st];
+        exc_seq[slot] = (int32_t)a;
     }
 }
 
@@ -110,7 +140,9 @@ int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, cons
     TRYS(s->d_hi.alloc(ctx, (nw + 4) * sizeof(uint32_t)));
     TRYS(s->d_lo.alloc(ctx, (nw + 4) * sizeof(uint32_t)));
     TRYS(s->d_packed.alloc(ctx, (2 * nw + 8) * sizeof(uint32_t)));
-    DevBuf d_toff, d_stride;
+    TRYS(s->d_irr.alloc(ctx, (nw + 4) * sizeof(uint32_t)));
+    DevBuf d_toff, d_stride, d_nirr;
+    TRYS(d_nirr.alloc_zero(ctx, 16));
     TRYS(d_toff.alloc(ctx, (n + 1) * sizeof(int64_t)));
     TRYS(pb_h2d(ctx, s->d_base.p, s->base.data(), (n + 1) * sizeof(int64_t)));
     TRYS(pb_h2d(ctx, s->d_len.p, s->len.data(), n * sizeof(int32_t)));
@@ -123,6 +155,7 @@ int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, cons
     cudaMemsetAsync(s->d_hi.as<uint32_t>() + nw, 0xff, 4 * sizeof(uint32_t), ctx->stream);
     cudaMemsetAsync(s->d_lo.as<uint32_t>() + nw, 0xff, 4 * sizeof(uint32_t), ctx->stream);
     cudaMemsetAsync(s->d_packed.as<uint32_t>() + 2 * nw, 0xff, 8 * sizeof(uint32_t), ctx->stream);
+    cudaMemsetAsync(s->d_irr.as<uint32_t>() + nw, 0, 4 * sizeof(uint32_t), ctx->stream);
     IngestSrc src;
     src.text = (const uint8_t *)d_text;
     src.toff = d_toff.as<int64_t>();
@@ -133,14 +166,65 @@ int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, cons
     pb_timer_begin(ctx, PB_T_INGEST);
     ingest_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(src, s->d_base.as<int64_t>(), s->d_len.as<int32_t>(), n, nw,
                                                              s->d_hi.as<uint32_t>(), s->d_lo.as<uint32_t>(),
-                                                             s->d_packed.as<uint32_t>(), s->d_flags.as<uint32_t>());
+                                                             s->d_packed.as<uint32_t>(), s->d_irr.as<uint32_t>(),
+                                                             s->d_flags.as<uint32_t>(), d_nirr.as<unsigned long long>());
     pb_timer_end(ctx, PB_T_INGEST);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { delete s; return pb_fail(ctx, PB_ERR_CUDA, "ingest launch failed: %s", cudaGetErrorString(e)); }
     s->flags.resize(n);
+    unsigned long long nirr = 0;
     TRYS(pb_d2h(ctx, s->flags.data(), s->d_flags.p, n * sizeof(uint32_t)));
+    TRYS(pb_d2h(ctx, &nirr, d_nirr.p, 8));
     TRYS(pb_sync(ctx)); // d_toff/d_stride are released after the kernel (stream-ordered) but flags are needed now
+    s->tab.assign((size_t)n, 0x41414141u); // unused slots hold 'A': a value the exception list never contains
+    s->tab_count.assign((size_t)n, 0);
+    if (nirr > 0 && !packed_src) {
+        // rare path: list the offending bytes, sort them by line position on the host, build the per-sequence tables
+        DevBuf d_cursor, d_pos, d_val, d_seq;
+        TRYS(d_cursor.alloc_zero(ctx, 16));
+        TRYS(d_pos.alloc(ctx, nirr * 8));
+        TRYS(d_val.alloc(ctx, nirr + 16));
+        TRYS(d_seq.alloc(ctx, nirr * 4));
+        collect_exceptions_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, ctx->stream>>>(
+            src, s->d_base.as<int64_t>(), s->d_len.as<int32_t>(), n, nw, s->d_irr.as<uint32_t>(), d_cursor.as<unsigned long long>(),
+            d_pos.as<int64_t>(), d_val.as<uint8_t>(), d_seq.as<int32_t>());
+        ctx->launches++;
+        std::vector<int64_t> pos((size_t)nirr);
+        std::vector<uint8_t> val((size_t)nirr);
+        std::vector<int32_t> seq((size_t)nirr);
+        TRYS(pb_d2h(ctx, pos.data(), d_pos.p, nirr * 8));
+        TRYS(pb_d2h(ctx, val.data(), d_val.p, nirr));
+        TRYS(pb_d2h(ctx, seq.data(), d_seq.p, nirr * 4));
+        TRYS(pb_sync(ctx));
+        std::vector<size_t> order((size_t)nirr);
+        for (size_t k = 0; k < order.size(); ++k) order[k] = k;
+        std::sort(order.begin(), order.end(), [&](size_t x, size_t y) { return pos[x] < pos[y]; });
+        std::vector<int64_t> spos((size_t)nirr);
+        std::vector<uint8_t> sval((size_t)nirr);
+        for (size_t k = 0; k < order.size(); ++k) {
+            spos[k] = pos[order[k]];
+            sval[k] = val[order[k]];
+            const int32_t q = seq[order[k]];
+            uint8_t &cnt = s->tab_count[q];
+            if (cnt == 255) continue;
+            bool seen = false;
+            for (int t = 0; t < cnt; ++t) seen = seen || ((s->tab[q] >> (8 * t)) & 0xFF) == sval[k];
+            if (!seen) {
+                if (cnt == 4) cnt = 255;
+                else { s->tab[q] = (s->tab[q] & ~(0xFFu << (8 * cnt))) | ((uint32_t)sval[k] << (8 * cnt)); ++cnt; }
+            }
+        }
+        s->nexc = (int64_t)nirr;
+        TRYS(s->d_exc_pos.alloc(ctx, nirr * 8));
+        TRYS(s->d_exc_val.alloc(ctx, nirr + 16));
+        TRYS(pb_h2d(ctx, s->d_exc_pos.p, spos.data(), nirr * 8));
+        TRYS(pb_h2d(ctx, s->d_exc_val.p, sval.data(), nirr));
+        TRYS(pb_sync(ctx));
+    }
+    TRYS(s->d_tab.alloc(ctx, (size_t)(n + 1) * 4));
+    TRYS(pb_h2d(ctx, s->d_tab.p, s->tab.data(), (size_t)n * 4));
+    TRYS(pb_sync(ctx));
 #undef TRYS
     *out = s;
     return PB_OK;

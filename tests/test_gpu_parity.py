@@ -201,22 +201,18 @@ def test_aligner_test_cases(ctx):
 
 
 def test_align_golden(ctx, golden):
-    from pacbioassembly_b200 import PbError
-    n_ok = 0
+    n_ok = n_irr = 0
     for x in golden["real_align"] + golden["random_align"]:
         a, b = x["a"].encode("latin1"), x["b"].encode("latin1")
         maxn, maxm = (26000, 6000) if x["which"] == 0 else (40000, 6000)
-        if set(a + b) - set(b"ACGT"):
-            with pytest.raises(PbError):
-                ctx.align(a, b, x["R"], x["a_fwd"], x["b_fwd"], maxn, maxm)
-            continue
+        n_irr += bool(set(a + b) - set(b"ACGT"))  # raw-byte compare (seq_aligner.h:136): the byte-exact aligner variant
         d = ctx.align(a, b, x["R"], x["a_fwd"], x["b_fwd"], maxn, maxm)
         check_against(d, x)
         if x["ret"] >= 0:
             assert ops_str(d["ops"]) == x["ops"]
             assert bytes(d["vals"]).decode("latin1") == x["vals"]
             n_ok += 1
-    assert n_ok > 80
+    assert n_ok > 80 and n_irr >= 10
 
 
 def make_pairs(rng, n, maxlen, rates=(0.0, 0.03, 0.1, 0.2)):
@@ -286,6 +282,36 @@ def test_align_random_multiword(ctx, oracle):
     rng = np.random.default_rng(12)
     A, B = make_pairs(rng, 60, 6000, rates=(0.0, 0.05, 0.12))
     assert run_batch_vs_oracle(ctx, oracle, A, B, 0.3) > 15
+
+
+def test_align_non_acgt_bytes(ctx, oracle):
+    """N, lower case and other bytes compare by raw value in the DP (seq_aligner.h:136) while seeding maps them to
+    code 3 (dna_seq.h:21): pairs that hold them take the byte-exact aligner variant"""
+    from pacbioassembly_b200 import PbError
+    rng = np.random.default_rng(21)
+    A, B = make_pairs(rng, 120, 900)
+    A2, B2 = [], []
+    for k, (a, b) in enumerate(zip(A, B)):
+        a, b = bytearray(a), bytearray(b)
+        for seq in (a, b):
+            for _ in range(int(rng.integers(0, 6))):
+                seq[int(rng.integers(0, len(seq)))] = int(rng.choice(list(b"NNNnacgt-")))
+        if k % 7 == 0:  # the same unusual byte on both sides at aligned places must MATCH
+            m = min(len(a), len(b))
+            for q in range(0, m, 37):
+                a[q] = b[q] = ord("N")
+        A2.append(bytes(a)); B2.append(bytes(b))
+    for R in (0.3, 0.15):
+        assert run_batch_vs_oracle(ctx, oracle, A2, B2, R) > 20
+    assert run_batch_vs_oracle(ctx, oracle, A2[:40], B2[:40], 0.3, fwd=False) > 5
+    # long pair with N runs (multi-word band, class S=6/16 of the byte-exact variant)
+    g = bytearray(workload.reference(91, 9000).tobytes())
+    a = bytearray(g[:6000]); a[1000:1010] = b"N" * 10; a[3000] = ord("n")
+    b = bytearray(g[:8000]); b[1003:1007] = b"NNNN"; b[5000:5003] = b"nnn"
+    assert run_batch_vs_oracle(ctx, oracle, [bytes(a), bytes(b[:5000])], [bytes(b), bytes(a)], 0.3) >= 1
+    # more than four distinct unusual byte values in seg_a: refused loudly
+    with pytest.raises(PbError):
+        ctx.align(b"ACGTNXYZWACGT" * 5, b"ACGTACGTACGT" * 5)
 
 
 def test_align_domain_limits(ctx, oracle):
@@ -374,6 +400,22 @@ def test_locate_clr_and_edges(ctx, oracle):
     assert len(ctx.locate(ix, ref[:900], [0, 400], [400, 499])) == 0
     # custom trial count / minimum length
     recs = locate_vs_oracle(ctx, oracle, ref, txt, offs, lens, MASKS[5], 0.3, ntrial=8, minlen=1000)
+
+
+def test_locate_with_n_in_reads_and_contig(ctx, oracle):
+    """real contigs carry N runs and locator.cpp's N->A loop never runs (Q-S4): seeds see code 3, the DP sees raw bytes"""
+    ref = workload.reference(33, 120_000)
+    ref[40_000:40_050] = ord("N")
+    ref[77_777] = ord("n")
+    lens = workload.read_lengths(34, 60, mean=1200.0, sigma_log=0.4, lo=500, hi=3000)
+    txt, offs, lens, starts = workload.reads(35, ref, lens, 0.02, 0.01, 0.01)
+    txt = txt.copy()
+    for k in range(0, 60, 3):
+        txt[offs[k] + 100 + k] = ord("N")
+    recs = locate_vs_oracle(ctx, oracle, ref, txt, offs, lens, MASKS[0], 0.15)
+    assert recs["found"].sum() > 30
+    clean = workload.reference(33, 120_000)
+    recs = locate_vs_oracle(ctx, oracle, clean, txt, offs, lens, MASKS[3], 0.3)  # N only in the reads
 
 
 def test_locate_properties_at_scale(ctx):
