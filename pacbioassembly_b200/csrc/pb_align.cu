@@ -787,9 +787,15 @@ static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, bool locate, s
 
 static size_t scratch_budget(pb_ctx *ctx)
 {
+    if (ctx->scratch_budget_cached) { // fixed after the first call: a moving budget would re-plan (and re-allocate) every step
+        size_t b = ctx->scratch_budget_cached;
+        if (ctx->scratch_limit && ctx->scratch_limit < b) b = ctx->scratch_limit;
+        return b;
+    }
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); fr = (size_t)8 << 30; }
     size_t b = (size_t)((double)(fr + ctx->scratch_bytes) * 0.5); // what we already hold counts as available
+    ctx->scratch_budget_cached = b;
     if (ctx->scratch_limit && ctx->scratch_limit < b) b = ctx->scratch_limit;
     return b;
 }

@@ -35,6 +35,7 @@ struct pb_ctx {
     // grow-only scratch for the aligner's parent planes (kept across calls: no per-step allocation)
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+    size_t scratch_budget_cached = 0;
 };
 
 void pb_set_error(pb_ctx *ctx, const char *fmt, ...);

@@ -295,7 +295,7 @@ def test_align_non_acgt_bytes(ctx, oracle):
         a, b = bytearray(a), bytearray(b)
         for seq in (a, b):
             for _ in range(int(rng.integers(0, 6))):
-                seq[int(rng.integers(0, len(seq)))] = int(rng.choice(list(b"NNNnacgt-")))
+                seq[int(rng.integers(0, len(seq)))] = int(rng.choice(list(b"NNNnx-")))  # four distinct values at most
         if k % 7 == 0:  # the same unusual byte on both sides at aligned places must MATCH
             m = min(len(a), len(b))
             for q in range(0, m, 37):
