@@ -220,6 +220,45 @@ PB_API int pb_locate_job_ops_layout(const pb_locate_job *job, int64_t *ops_off /
 PB_API int pb_locate_fetch(pb_ctx *ctx, const pb_locate_job *job, pb_locate_rec *recs, uint8_t *ops);
 PB_API void pb_locate_job_free(pb_locate_job *job);
 
+/* ---- assembler-side probe / verify (spaced_seed.cpp:261-299, 424-436; ref_seq.h:259-266) -------------------- */
+
+typedef struct {
+    int32_t id;        /* rank of the read in the set (seq_index::id) */
+    int32_t found;     /* 0/1 */
+    int32_t j;         /* trial number of the success */
+    int32_t ref_pos;   /* seed-map position (*it) of the success */
+    int32_t cost;      /* final_cost(), the "found <id> at cost c" line (spaced_seed.cpp:429-431) */
+    int32_t read_pos;  /* the pos argument of try_align: j (forward) or len-j-16 (backward) */
+    int32_t dir;       /* +1 head / forward, -1 tail / backward */
+    int32_t matlen_a;  /* ref_ml */
+    int32_t matlen_b;  /* seg_ml */
+    int32_t nedit;
+    int32_t ncand;     /* ref_seq::try_align calls the reference would have made for this read */
+    int32_t _pad;
+    int64_t cells;
+} pb_overlap_rec;
+
+typedef struct {
+    double R;              /* 0.3 (MAXR, common.h:37; spaced_seed -r) */
+    int32_t max_trial;     /* 32, spaced_seed.cpp:93 (-t) */
+    int32_t min_overlap;   /* 64, OVERLAP_MIN (common.h:39): segment length and matlen_a gates */
+    int32_t maxn, maxm;    /* t_aligner = seq_aligner<26000,6000>, seq_aligner.h:260 */
+    int32_t seed_at_quirk; /* 1: dna_seq::seed_at's shipped pos%4==0 branch (byte offset pos, SURVEY Q-S1); needs a set made
+                              by pb_seqset_from_bin (the raw image is what that branch reads); 0: encode(text+pos) */
+    int32_t want_ops;
+    int32_t reserved;
+} pb_overlap_params;
+
+PB_API void pb_overlap_default_params(pb_overlap_params *p);
+
+/* For every sequence of `reads`: for j < max_trial: try_align(read, j, +1) || try_align(read, len-j-16, -1), i.e. probe
+ * seed_at(read,pos) & mask in `ix` (built with PB_POLICY_REFSEQ over ref/ref_seq), and take the first list entry for which
+ * align(ref view, read view) >= 0 and matlen_a >= min_overlap -- forward views, or backward views anchored at the seed's
+ * last base (spaced_seed.cpp:274-285).  The reference is treated as locked (no voting / growth, ref_seq.h:266).
+ * recs: one entry per sequence of `reads`.  ops/ops_off as in pb_align_batch, slots of 3*len + 2*maxm + 16 bytes. */
+PB_API int pb_overlap_batch(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const pb_seqset *reads,
+                            const pb_overlap_params *prm, pb_overlap_rec *recs, uint8_t *ops, const int64_t *ops_off);
+
 #ifdef __cplusplus
 }
 #endif

@@ -436,3 +436,105 @@ int64_t pbo_locate(const pbo_index *ix, const char *ref, size_t ref_len,
     free(jobs); free(th); free(kept);
     return nk;
 }
+
+/* ------------------------------------------------------------------------- */
+/* assembler-side trial loop (spaced_seed.cpp:261-299, 424-436)              */
+/* ------------------------------------------------------------------------- */
+
+typedef struct {
+    const pbo_index *ix; const char *ref; size_t ref_len;
+    const uint8_t *bin; size_t bin_bytes; const size_t *rec_off; int64_t k0, k1;
+    uint32_t mask; double R; int max_trial, min_overlap, maxn, maxm, quirk;
+    pbo_overlap_rec *recs;
+} overlap_job;
+
+static uint32_t image_seed_at(const uint8_t *bin, size_t bin_bytes, size_t rec, int pos, int quirk)
+{ /* dna_seq::seed_at over the whole image: bytes past the image read 0 */
+    return pbo_seed_at(bin + rec, bin_bytes - rec, pos, quirk);
+}
+
+static void *overlap_thread(void *arg)
+{
+    overlap_job *jb = (overlap_job *)arg;
+    dp_ws ws = {0, 0, 0};
+    char *txt = NULL; size_t txt_cap = 0;
+    for (int64_t k = jb->k0; k < jb->k1; ++k) {
+        const size_t rec = jb->rec_off[k];
+        uint32_t slen;
+        memcpy(&slen, jb->bin + rec, 4);
+        pbo_overlap_rec *out = &jb->recs[k];
+        memset(out, 0, sizeof *out);
+        out->id = (int32_t)k;
+        if (slen + 2 > txt_cap) { free(txt); txt_cap = slen + 64; txt = (char *)malloc(txt_cap); }
+        pbo_bin2text(jb->bin + rec, txt, txt_cap); /* set_active_seg, spaced_seed.cpp:109-118 */
+        int found = 0;
+        for (int j = 0; j < jb->max_trial && !found; ++j) {
+            for (int side = 0; side < 2 && !found; ++side) { /* spaced_seed.cpp:426 */
+                const int forward = side == 0;
+                const long pos = forward ? j : (long)slen - j - 16;
+                const uint32_t key = image_seed_at(jb->bin, jb->bin_bytes, rec, (int)pos, jb->quirk) & jb->mask;
+                const int32_t *plist;
+                const size_t cnt = pbo_index_find(jb->ix, key, &plist);
+                if (!cnt) continue;
+                const long s_offset = forward ? pos : pos + 15;
+                const long s_len = forward ? (long)slen - s_offset : s_offset + 1;
+                if (s_len < jb->min_overlap) continue; /* spaced_seed.cpp:280 */
+                for (size_t c = 0; c < cnt && !found; ++c) {
+                    const long r_offset = forward ? plist[c] : plist[c] + 15;
+                    const long r_len = forward ? (long)jb->ref_len - r_offset : r_offset + 1; /* ref_seq.h:282-286 */
+                    pbo_align_out ao;
+                    out->ncand++;
+                    /* note the argument order: a = reference view, b = read view (ref_seq.h:264) */
+                    const int ret = align_ws(&ws, jb->ref + r_offset, (int)r_len, forward ? 1 : -1, txt + s_offset, (int)s_len,
+                                             forward ? 1 : -1, jb->R, jb->maxn, jb->maxm, &ao, NULL, NULL, 0);
+                    out->cells += ao.cells;
+                    if (ret < 0) continue;
+                    if (ao.matlen_a < jb->min_overlap) continue; /* ref_seq.h:265 */
+                    found = 1;
+                    out->found = 1; out->j = j; out->ref_pos = plist[c]; out->cost = ao.cost; out->read_pos = (int32_t)pos;
+                    out->dir = forward ? 1 : -1; out->matlen_a = ao.matlen_a; out->matlen_b = ao.matlen_b; out->nedit = ao.nedit;
+                }
+            }
+        }
+    }
+    free(txt);
+    dp_ws_free(&ws);
+    return NULL;
+}
+
+int64_t pbo_overlap(const pbo_index *ix, const char *ref, size_t ref_len, const uint8_t *bin, size_t bin_bytes,
+                    int min_excl, int max_excl, uint32_t mask, double R, int max_trial, int min_overlap, int maxn,
+                    int maxm, int quirk, int nthreads, pbo_overlap_rec *recs)
+{
+    size_t cap = 1024, nk = 0;
+    size_t *rec_off = (size_t *)malloc(cap * sizeof *rec_off);
+    for (size_t p = 0; p + 4 <= bin_bytes;) { /* open_binary, spaced_seed.cpp:330-342 */
+        uint32_t l;
+        memcpy(&l, bin + p, 4);
+        if ((long)l > min_excl && (long)l < max_excl) {
+            if (nk == cap) { cap *= 2; rec_off = (size_t *)realloc(rec_off, cap * sizeof *rec_off); }
+            rec_off[nk++] = p;
+        }
+        p += 4 + ((size_t)l + 3) / 4;
+    }
+    if (recs) {
+        if (nthreads < 1) nthreads = 1;
+        if ((size_t)nthreads > nk) nthreads = nk ? (int)nk : 1;
+        overlap_job *jobs = (overlap_job *)calloc((size_t)nthreads, sizeof *jobs);
+        pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof *th);
+        for (int t = 0; t < nthreads; ++t) {
+            overlap_job *jb = &jobs[t];
+            jb->ix = ix; jb->ref = ref; jb->ref_len = ref_len; jb->bin = bin; jb->bin_bytes = bin_bytes; jb->rec_off = rec_off;
+            jb->k0 = (int64_t)(nk * t / nthreads); jb->k1 = (int64_t)(nk * (t + 1) / nthreads);
+            jb->mask = mask; jb->R = R; jb->max_trial = max_trial; jb->min_overlap = min_overlap;
+            jb->maxn = maxn; jb->maxm = maxm; jb->quirk = quirk; jb->recs = recs;
+            if (nthreads == 1) overlap_thread(jb);
+            else pthread_create(&th[t], NULL, overlap_thread, jb);
+        }
+        if (nthreads > 1)
+            for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+        free(jobs); free(th);
+    }
+    free(rec_off);
+    return (int64_t)nk;
+}

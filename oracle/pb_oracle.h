@@ -125,6 +125,34 @@ int64_t pbo_locate(const pbo_index *ix, const char *ref, size_t ref_len,
                    int maxn, int maxm, int nthreads, pbo_locate_rec *recs,
                    uint8_t *ops_out, const int64_t *ops_off);
 
+/* ---- assembler-side probe / verify: try_align + trial loop (spaced_seed.cpp:261-299, 424-436) ---------------- */
+
+typedef struct {
+    int32_t id;        /* rank among kept reads (seq_index::id) */
+    int32_t found;
+    int32_t j;         /* trial number of the success */
+    int32_t ref_pos;   /* seed-map position *it of the success */
+    int32_t cost;      /* final_cost() */
+    int32_t read_pos;  /* the `pos` argument of try_align */
+    int32_t dir;       /* +1 head / forward, -1 tail / backward */
+    int32_t matlen_a;  /* ref_ml */
+    int32_t matlen_b;  /* seg_ml */
+    int32_t nedit;
+    int32_t ncand;     /* ref_seq::try_align calls made for this read */
+    int32_t _pad;
+    int64_t cells;
+} pbo_overlap_rec;
+
+/* For every record of the .bin image `bin` with min_excl < len < max_excl (open_binary, spaced_seed.cpp:330-342):
+ * for j < max_trial: try_align(read, j, +1) || try_align(read, slen-j-16, -1)   (spaced_seed.cpp:424-426), where
+ * try_align probes seed_at(read,pos) & mask in the REFSEQ-policy index `ix` of `ref`, requires a segment of at least
+ * min_overlap elements, and accepts the first list entry for which align(ref_view, read_view) >= 0 and matlen_a >=
+ * min_overlap (ref_seq.h:264-265, locked reference: no voting).  quirk != 0 reproduces dna_seq::seed_at's pos%4==0
+ * branch, reading the u32 at byte offset pos of the record body straight from the image (zero past its end). */
+int64_t pbo_overlap(const pbo_index *ix, const char *ref, size_t ref_len, const uint8_t *bin, size_t bin_bytes,
+                    int min_excl, int max_excl, uint32_t mask, double R, int max_trial, int min_overlap, int maxn,
+                    int maxm, int quirk, int nthreads, pbo_overlap_rec *recs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -277,4 +277,70 @@ int64_t pbref_locate(const char *ref, long ref_len, const char *reads, const int
     return nk;
 }
 
+/* ---- assembler-side trial loop driven through the reference's OWN code ----------------------------------------
+ * ref_seq (locked: no voting / growth), ref_seq::get_seedmap, dna_seq::seed_at, dna_seq::bin2text, ref_seq::try_align
+ * and seq_aligner::align are the reference's; only the two loops of spaced_seed.cpp:424-436 and :261-299 are
+ * restated, so that the fresh-state shim (Q-D2) can be applied before every align. */
+struct overlap_rec {
+    int32_t id, found, j, ref_pos, cost, read_pos, dir, matlen_a, matlen_b, nedit, ncand, _pad;
+    int64_t cells;
+};
+
+int64_t pbref_overlap(const char *ref_text, long ref_len, unsigned char *bin, long bin_bytes, int min_excl, int max_excl,
+                      unsigned mask, double R, int max_trial, overlap_rec *recs)
+{
+    if (ref_len >= MAX_SEQ_LEN) return -1;
+    ref_seq *pr = new ref_seq(ref_text, (int)ref_len, true); /* locked */
+    hash_table *map = new hash_table(1 << 20);
+    pr->get_seedmap(*map, mask); /* ref_seq.h:291-311 */
+    t_aligner *al = fresh_aligner<t_aligner>(R);
+    char *txt = (char *)malloc(MAX_READ_LEN + 64);
+    int64_t k = 0;
+    for (long off = 0; off + 4 <= bin_bytes;) { /* open_binary, spaced_seed.cpp:330-342 */
+        unsigned slen = *((unsigned *)(bin + off));
+        if (slen > (unsigned)min_excl && slen < (unsigned)max_excl) {
+            overlap_rec *out = &recs[k];
+            memset(out, 0, sizeof *out);
+            out->id = (int32_t)k;
+            dna_seq::bin2text(bin + off, txt, slen + 1); /* set_active_seg */
+            bool found = false;
+            for (int j = 0; j < max_trial && !found; ++j)
+                for (int side = 0; side < 2 && !found; ++side) {
+                    bool forward = side == 0;
+                    long pos = forward ? j : (long)slen - j - 16;
+                    sm_it sit = map->find(dna_seq::seed_at(bin + off, (int)pos) & mask); /* spaced_seed.cpp:265 */
+                    if (sit == map->end()) continue;
+                    int s_offset = forward ? pos : pos + 16 - 1;
+                    int s_len = forward ? (int)slen - s_offset : s_offset + 1;
+                    seq_accessor ac_seg(txt + s_offset, forward, s_len);
+                    if (s_len < OVERLAP_MIN) continue;
+                    for (std::list<int>::iterator it = sit->second.begin(); it != sit->second.end() && !found; ++it) {
+                        int r_offset = forward ? (*it) : (*it) + 16 - 1;
+                        /* fresh-state shim: zero the cells align() will read without writing (Q-D2) */
+                        seq_accessor ac_ref = pr->get_accessor(r_offset, forward);
+                        int la, lb, md;
+                        if (ac_seg.length() >= ac_ref.length()) { la = ac_ref.length(); md = 1 + (int)(la * R); lb = std::min(ac_seg.length(), la + md); }
+                        else { lb = ac_seg.length(); md = 1 + (int)(lb * R); la = std::min(ac_ref.length(), lb + md); }
+                        out->ncand++;
+                        if (la < MAX_READ_LEN + MAX_DIFF_LEN && md < MAX_DIFF_LEN) {
+                            al->max_dst = md;
+                            for (int i = lb + 1; i <= la; ++i) al->set_cost(i, i, 0);
+                        }
+                        al->R = R;
+                        if (pr->try_align(al, r_offset, &ac_seg)) { /* ref_seq.h:259-266 */
+                            found = true;
+                            out->found = 1; out->j = j; out->ref_pos = *it; out->cost = al->final_cost(); out->read_pos = (int32_t)pos;
+                            out->dir = forward ? 1 : -1; out->matlen_a = al->matlen_a; out->matlen_b = al->matlen_b; out->nedit = al->nedit;
+                        }
+                    }
+                }
+            ++k;
+        }
+        off += 4 + ((long)slen + 3) / 4;
+    }
+    free(txt); free(al);
+    delete map; delete pr;
+    return k;
+}
+
 } /* extern "C" */

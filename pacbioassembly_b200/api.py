@@ -22,12 +22,19 @@ ALIGN_DTYPE = np.dtype([(n, np.int32) for n in ("ret", "len_a", "len_b", "max_ds
                                                  "diag_cost", "nedit", "fail_row")] + [("cells", np.int64)])
 LOCATE_DTYPE = np.dtype([(n, np.int32) for n in ("nseq", "found", "j", "pos", "cost", "seg_len", "diag_cost", "matlen_a",
                                                   "matlen_b", "nedit", "ncand", "_pad")] + [("cells", np.int64)])
-assert ALIGN_DTYPE.itemsize == 48 and LOCATE_DTYPE.itemsize == 56
+OVERLAP_DTYPE = np.dtype([(n, np.int32) for n in ("id", "found", "j", "ref_pos", "cost", "read_pos", "dir", "matlen_a",
+                                                   "matlen_b", "nedit", "ncand", "_pad")] + [("cells", np.int64)])
+assert ALIGN_DTYPE.itemsize == 48 and LOCATE_DTYPE.itemsize == 56 and OVERLAP_DTYPE.itemsize == 56
 
 
 class LocateParams(C.Structure):
     _fields_ = [("R", C.c_double), ("ntrial", C.c_int32), ("minlen", C.c_int32), ("maxn", C.c_int32),
                 ("maxm", C.c_int32), ("want_ops", C.c_int32), ("reserved", C.c_int32)]
+
+
+class OverlapParams(C.Structure):
+    _fields_ = [("R", C.c_double), ("max_trial", C.c_int32), ("min_overlap", C.c_int32), ("maxn", C.c_int32),
+                ("maxm", C.c_int32), ("seed_at_quirk", C.c_int32), ("want_ops", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PbError(RuntimeError):
@@ -93,6 +100,8 @@ def lib() -> C.CDLL:
         "pb_locate_job_stats": (C.c_int, [vp, vp]),
         "pb_locate_fetch": (C.c_int, [vp, vp, vp, vp]),
         "pb_locate_job_free": (None, [vp]),
+        "pb_overlap_default_params": (None, [P(OverlapParams)]),
+        "pb_overlap_batch": (C.c_int, [vp, vp, vp, i64, vp, P(OverlapParams), vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -318,6 +327,29 @@ class Context:
         assert got.value == nk
         if want_ops:
             return recs, [ops[ops_off[k]: ops_off[k] + int(recs["nedit"][k])] for k in range(nk)]
+        return recs
+
+    def overlap(self, index: "Index", reads: "SeqSet", want_ops: bool = False, **params):
+        """spaced_seed.cpp:424-436 / try_align: head and tail trials of every read against a REFSEQ-policy index"""
+        prm = OverlapParams()
+        self._L.pb_overlap_default_params(C.byref(prm))
+        prm.want_ops = int(want_ops)
+        for k, v in params.items():
+            setattr(prm, k, v)
+        n = len(reads)
+        recs = np.zeros(n, dtype=OVERLAP_DTYPE)
+        ops = ops_off = None
+        if want_ops:
+            lens = np.array([reads.length(i) for i in range(n)], dtype=np.int64)
+            slots = (3 * lens + 2 * prm.maxm + 16 + 15) & ~15
+            ops_off = np.zeros(n, dtype=np.int64)
+            if n:
+                np.cumsum(slots[:-1], out=ops_off[1:])
+            ops = np.zeros(int(slots.sum()) + 16, dtype=np.uint8)
+        self.check(self._L.pb_overlap_batch(self.h, index.h, index.ref.h, index.seq, reads.h, C.byref(prm), _ptr(recs),
+                                            _ptr(ops), _ptr(ops_off)))
+        if want_ops:
+            return recs, [ops[ops_off[k]: ops_off[k] + int(recs["nedit"][k])] for k in range(n)]
         return recs
 
     def locate_run(self, index: "Index", reads: "SeqSet", want_ops: bool = False, **params) -> "LocateJob":

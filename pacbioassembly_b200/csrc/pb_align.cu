@@ -98,6 +98,44 @@ __device__ __forceinline__ int irr_plane(const SeqView &A, int64_t g, uint32_t a
     return 4 + (slot < 0 ? 0 : slot); // slot < 0 cannot happen for a sequence the host admitted (<= 4 distinct values)
 }
 
+// The four sequence views an alignment can draw from: reads / ref and, in overlap mode, their reversed copies.
+struct PairViews { SeqView A, B, A2, B2; }; // A = reads, B = ref, A2 = reads reversed, B2 = ref reversed
+
+struct CandView {
+    const SeqView *a, *b; // seg_a, seg_b of seq_aligner::align
+    int64_t a_bit, b_bit;
+    int a_len, b_len;
+    uint32_t a_tab;
+    int j, read_pos, dir;
+};
+
+// candidate = (read r of length rlen at line offset rbase, query q of kept read k, seed-map position refpos)
+__device__ __forceinline__ void derive_views(const PairViews &pv, const LocateView &lv, int k, int r, int rlen, int64_t rbase, int q,
+                                             int refpos, bool irr, CandView &cv)
+{
+    const int t = q - k * lv.ntrial;
+    if (lv.mode == PB_MODE_LOCATE) { // locator.cpp:78-82: align(read[j:], ref[pos:])
+        cv.j = t; cv.read_pos = t; cv.dir = 1;
+        cv.a = &pv.A; cv.a_bit = rbase + t; cv.a_len = rlen - t;
+        cv.b = &pv.B; cv.b_bit = lv.ref_base + refpos; cv.b_len = lv.ref_len - refpos;
+        cv.a_tab = irr ? pv.A.tab[r] : 0u;
+        return;
+    }
+    // spaced_seed.cpp:274-285 + ref_seq.h:264,282-286: align(ref view, read view), both forward or both backward
+    const bool forward = (t & 1) == 0;
+    cv.j = t >> 1; cv.dir = forward ? 1 : -1;
+    cv.read_pos = forward ? cv.j : rlen - cv.j - 16;
+    cv.a_tab = 0u;
+    if (forward) {
+        cv.a = &pv.B; cv.a_bit = lv.ref_base + refpos; cv.a_len = lv.ref_len - refpos;
+        cv.b = &pv.A; cv.b_bit = rbase + cv.read_pos; cv.b_len = rlen - cv.read_pos;
+    } else { // element k of a backward accessor at offset o is text[o - k]: position len-1-o of the reversed copy
+        const int r_off = refpos + 15, s_off = cv.read_pos + 15;
+        cv.a = &pv.B2; cv.a_bit = lv.ref_base + (lv.ref_len - 1 - r_off); cv.a_len = r_off + 1;
+        cv.b = &pv.A2; cv.b_bit = rbase + (rlen - 1 - s_off); cv.b_len = s_off + 1;
+    }
+}
+
 // seq_aligner.h:94-102
 __device__ __forceinline__ void derive_params(int a_len, int b_len, double R, int &len_a, int &len_b, int &D)
 {
@@ -131,19 +169,19 @@ __device__ __forceinline__ long long cells_upto(int n, int D, int len_b)
 // ---------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256)
-prefilter_kernel(SeqView A, SeqView B, LocateView lv, int64_t ncand, double R, int maxn, int maxm,
+prefilter_kernel(PairViews pv, LocateView lv, int64_t ncand, double R, int maxn, int maxm,
                  uint8_t *__restrict__ survive, int32_t *__restrict__ rej_cells)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncand) return;
     const int q = lv.d_cand_q[c];
-    const int k = q / lv.ntrial, j = q - k * lv.ntrial;
+    const int k = q / lv.ntrial;
     const int r = lv.d_kept[k];
-    const int a_len = A.len[r] - j;
-    const int64_t a_bit = A.base[r] + j;
-    const int pos = lv.d_cand_pos[c];
-    const int b_len = lv.ref_len - pos;
-    const int64_t b_bit = lv.ref_base + pos;
+    CandView cv;
+    derive_views(pv, lv, k, r, pv.A.len[r], pv.A.base[r], q, lv.d_cand_pos[c], false, cv);
+    const SeqView &A = *cv.a, &B = *cv.b;
+    const int a_len = cv.a_len, b_len = cv.b_len;
+    const int64_t a_bit = cv.a_bit, b_bit = cv.b_bit;
     int len_a, len_b, D;
     derive_params(a_len, b_len, R, len_a, len_b, D);
     if (len_a >= maxn || D >= maxm) { // seq_aligner.h:104-107 (domain per SURVEY Q-D3)
@@ -179,11 +217,21 @@ prefilter_kernel(SeqView A, SeqView B, LocateView lv, int64_t ncand, double R, i
     rej_cells[c] = fail ? (int32_t)cells_upto(fail, D, len_b) : 0;
 }
 
-int pb_prefilter(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, const LocateView &lv, int64_t ncand, double R,
+static PairViews pair_views(const SeqSets &ss)
+{
+    PairViews pv;
+    pv.A = seq_view(ss.reads);
+    pv.B = seq_view(ss.ref);
+    pv.A2 = seq_view(ss.reads_rev ? ss.reads_rev : ss.reads);
+    pv.B2 = seq_view(ss.ref_rev ? ss.ref_rev : ss.ref);
+    return pv;
+}
+
+int pb_prefilter(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_t ncand, double R,
                  int maxn, int maxm, uint8_t *d_survive, int32_t *d_rej_cells)
 {
     if (ncand <= 0) return PB_OK;
-    prefilter_kernel<<<(unsigned)((ncand + 255) / 256), 256, 0, ctx->stream>>>(seq_view(A), seq_view(B), lv, ncand, R, maxn, maxm, d_survive, d_rej_cells);
+    prefilter_kernel<<<(unsigned)((ncand + 255) / 256), 256, 0, ctx->stream>>>(pair_views(ss), lv, ncand, R, maxn, maxm, d_survive, d_rej_cells);
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
 }
@@ -582,7 +630,8 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
 }
 
 struct AlignLaunch {
-    SeqView A, B;
+    SeqView A, B;   // pairs mode: seg_a / seg_b sets; locate modes: reads / ref
+    SeqView A2, B2; // overlap mode: reversed reads / ref
     double R;
     int maxn, maxm;
     int PW;              // plane stride (words) for this launch
@@ -626,7 +675,7 @@ align_locate_kernel(AlignLaunch p, LocateView lv, const uint8_t *__restrict__ su
         int ncand = 0;
         bool found = false;
         AlnRes res;
-        int win_j = 0, win_pos = 0;
+        int win_j = 0, win_pos = 0, win_rpos = 0, win_dir = 0;
         for (int64_t cb = c0; cb < c1 && !found; cb += 32) {
             const int64_t c = cb + lane;
             const int nvalid = (int)min((int64_t)32, c1 - cb);
@@ -639,15 +688,18 @@ align_locate_kernel(AlignLaunch p, LocateView lv, const uint8_t *__restrict__ su
                 cells += __reduce_add_sync(FULL, (lane >= done && lane < f) ? rc : 0);
                 ncand += f - done + 1;
                 const int q = lv.d_cand_q[cb + f];
-                const int j = q - k * lv.ntrial;
                 const int pos = lv.d_cand_pos[cb + f];
-                align_one<S, IRR>(p.A, rbase + j, rlen - j, IRR ? p.A.tab[r] : 0u, p.B, lv.ref_base + pos, lv.ref_len - pos, p.R, p.maxn, p.maxm, planes,
+                CandView cv;
+                derive_views(*reinterpret_cast<const PairViews *>(&p.A), lv, k, r, rlen, rbase, q, pos, IRR, cv);
+                align_one<S, IRR>(*cv.a, cv.a_bit, cv.a_len, cv.a_tab, *cv.b, cv.b_bit, cv.b_len, p.R, p.maxn, p.maxm, planes,
                              p.PW, par, opsrev, p.ops ? p.ops + p.ops_off[k] : nullptr, p.c31, p.c2, res);
                 cells += res.cells;
                 if (lane == 0 && p.stats) { atomicAdd(p.stats, (unsigned long long)res.cells); atomicAdd(p.stats + 1, 1ull); }
                 done = f + 1;
                 mask &= mask - 1;
-                if (res.ret > 0) { found = true; win_j = j; win_pos = pos; break; } // locator.cpp:82
+                const bool ok = lv.mode == PB_MODE_LOCATE ? res.ret > 0                                      // locator.cpp:82
+                                                          : (res.ret >= 0 && res.matlen_a >= lv.min_overlap); // ref_seq.h:264-265
+                if (ok) { found = true; win_j = cv.j; win_pos = pos; win_rpos = cv.read_pos; win_dir = cv.dir; break; }
             }
             if (!found) {
                 cells += __reduce_add_sync(FULL, (lane >= done && lane < nvalid) ? rc : 0);
@@ -658,8 +710,10 @@ align_locate_kernel(AlignLaunch p, LocateView lv, const uint8_t *__restrict__ su
             pb_locate_rec rec;
             rec.nseq = k; rec.found = found ? 1 : 0;
             rec.j = found ? win_j : 0; rec.pos = found ? win_pos : 0;
-            rec.cost = found ? res.cost : 0; rec.seg_len = found ? rlen - win_j : 0;
-            rec.diag_cost = found ? res.diag_cost : 0;
+            rec.cost = found ? res.cost : 0;
+            // locator: len - j and cost(len-j,len-j) (locator.cpp:85-86); overlap: try_align's pos and direction
+            rec.seg_len = !found ? 0 : (lv.mode == PB_MODE_LOCATE ? rlen - win_j : win_rpos);
+            rec.diag_cost = !found ? 0 : (lv.mode == PB_MODE_LOCATE ? res.diag_cost : win_dir);
             rec.matlen_a = found ? res.matlen_a : 0; rec.matlen_b = found ? res.matlen_b : 0;
             rec.nedit = found ? res.nedit : 0;
             rec.ncand = ncand; rec._pad = 0; rec.cells = cells;
@@ -938,7 +992,7 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
     return PB_OK;
 }
 
-int pb_align_locate(pb_ctx *ctx, const pb_seqset *reads, const pb_seqset *ref, const LocateView &lv, int64_t nkept,
+int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_t nkept,
                     const std::vector<int32_t> &kept_lens, const std::vector<uint8_t> &kept_irr, double R, int maxn, int maxm,
                     const uint8_t *d_survive, const int32_t *d_rej_cells, pb_locate_rec *d_recs, uint8_t *d_ops,
                     const int64_t *d_ops_off, unsigned long long *d_stats)
@@ -957,14 +1011,18 @@ int pb_align_locate(pb_ctx *ctx, const pb_seqset *reads, const pb_seqset *ref, c
         if (cls < 0) return pb_fail(ctx, PB_ERR_DOMAIN, "band half-width %d exceeds PB_MAX_BAND", D);
         ClassPlan &cp = plans[cls];
         cp.items.push_back(k);
-        cp.max_rows = std::max(cp.max_rows, std::min(L, std::max(maxn - 1, 1)));
+        // rows = len_a: the read itself (locator), or the reference view cut to len_b + max_dst (overlap, seq_aligner.h:100)
+        const int rows = lv.mode == PB_MODE_LOCATE ? L : L + D;
+        cp.max_rows = std::max(cp.max_rows, std::min(rows, std::max(maxn - 1, 1)));
         cp.max_D = std::max(cp.max_D, D);
         cp.work += (double)L * (30.0 * key_S(cls) + 60.0); // ~instructions: rows x (per-word + per-row cost)
     }
     AlignLaunch base;
     memset(&base, 0, sizeof base);
-    base.A = seq_view(reads);
-    base.B = seq_view(ref);
+    {
+        PairViews pv = pair_views(ss);
+        base.A = pv.A; base.B = pv.B; base.A2 = pv.A2; base.B2 = pv.B2;
+    }
     base.R = R; base.maxn = maxn; base.maxm = maxm;
     base.ops = d_ops; base.ops_off = d_ops_off;
     base.stats = d_stats;

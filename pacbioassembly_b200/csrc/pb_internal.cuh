@@ -111,6 +111,9 @@ struct pb_seqset {
     // (seq_aligner.h:136).  d_irr marks their positions on the line (bit plane); the bytes themselves are kept as a
     // sorted exception list (line position, value); tab[i] holds the (at most 4) distinct such values of sequence i.
     DevBuf d_irr, d_exc_pos, d_exc_val, d_tab;
+    // sets made from a .bin image keep it (the reference's seed_at quirk reads raw image bytes, SURVEY Q-S1)
+    DevBuf d_image, d_recoff;
+    int64_t image_bytes = 0;
     int64_t nexc = 0;
     std::vector<uint32_t> tab;      // 4 byte values packed little-endian
     std::vector<uint8_t> tab_count; // 0..4, 255 = more than four distinct values
@@ -152,7 +155,11 @@ struct pb_index {
 
 // pb_seq.cu
 int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, const int32_t *h_len,
-                    const int32_t *h_stride, int64_t n, bool keep_text_ref, pb_seqset **out);
+                    const int32_t *h_stride, int64_t n, int src_mode, pb_seqset **out);
+#define PB_SRC_TEXT 0     // bytes of text, element k at toff + k*stride
+#define PB_SRC_PACKED 1   // 4 bases per byte (dna_seq.h:113-127 body), first byte at toff
+#define PB_SRC_REVLINE 2  // another set's packed line, sequence read backwards; toff = its base offset (in bases)
+int pb_seqset_reversed(pb_ctx *ctx, const pb_seqset *s, pb_seqset **out);
 
 // pb_seed.cu
 int pb_seed_bulk_device(pb_ctx *ctx, const pb_seqset *s, int64_t first_base, int64_t count, uint32_t mask,
@@ -169,6 +176,9 @@ struct ProbeOut {
 // keys of the first ntrial offsets of every kept read, then probe + gather
 int pb_locate_seed_probe(pb_ctx *ctx, const pb_index *ix, const pb_seqset *reads, const int32_t *d_kept, int64_t nkept,
                          int ntrial, ProbeOut *po);
+// overlap mode: per read 2*max_trial queries (j forward at pos j, j backward at pos len-j-16), spaced_seed.cpp:424-426
+int pb_overlap_seed_probe(pb_ctx *ctx, const pb_index *ix, const pb_seqset *reads, const int32_t *d_kept, int64_t nkept,
+                          int max_trial, int min_overlap, int quirk, ProbeOut *po);
 
 // pb_align.cu
 struct LocateView { // everything the aligner needs to derive candidate (a,b) views in locate mode
@@ -176,13 +186,20 @@ struct LocateView { // everything the aligner needs to derive candidate (a,b) vi
     const int64_t *d_qoff;
     const int32_t *d_cand_pos;
     const int32_t *d_cand_q;
-    int ntrial;
+    int ntrial;       // queries per read: ntrial (locator) or 2*max_trial (overlap: head/forward and tail/backward per j)
     int64_t ref_base; // base offset of the reference sequence inside its seqset
     int32_t ref_len;
+    int mode;         // PB_MODE_LOCATE: a = read[j:], b = ref[pos:] (locator.cpp:78-82)
+                      // PB_MODE_OVERLAP: a = ref view, b = read view, forward or backward (spaced_seed.cpp:274-285, ref_seq.h:264)
+    int min_overlap;  // OVERLAP_MIN gate on matlen_a (ref_seq.h:265), overlap mode only
 };
-int pb_prefilter(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, const LocateView &lv, int64_t ncand, double R,
+#define PB_MODE_LOCATE 0
+#define PB_MODE_OVERLAP 1
+// reads / ref and (overlap mode only, else NULL) their reversed copies for the backward views
+struct SeqSets { const pb_seqset *reads, *ref, *reads_rev, *ref_rev; };
+int pb_prefilter(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_t ncand, double R,
                  int maxn, int maxm, uint8_t *d_survive, int32_t *d_rej_cells);
-int pb_align_locate(pb_ctx *ctx, const pb_seqset *reads, const pb_seqset *ref, const LocateView &lv, int64_t nkept,
+int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_t nkept,
                     const std::vector<int32_t> &kept_lens, const std::vector<uint8_t> &kept_irr, double R, int maxn, int maxm,
                     const uint8_t *d_survive,
                     const int32_t *d_rej_cells, pb_locate_rec *d_recs, uint8_t *d_ops, const int64_t *d_ops_off,

@@ -168,13 +168,16 @@ extern "C" int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *r
     lv.ntrial = prm->ntrial;
     lv.ref_base = ref->base[ref_seq];
     lv.ref_len = ref->len[ref_seq];
+    lv.mode = PB_MODE_LOCATE;
+    lv.min_overlap = 0;
+    SeqSets ss = {reads, ref, nullptr, nullptr};
     TRYJ(d_survive.alloc(ctx, (size_t)std::max<int64_t>(po.ncand, 1)));
     TRYJ(d_rej.alloc(ctx, (size_t)std::max<int64_t>(po.ncand, 1) * 4));
     pb_timer_begin(ctx, PB_T_PREFILTER);
-    TRYJ(pb_prefilter(ctx, reads, ref, lv, po.ncand, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(), d_rej.as<int32_t>()));
+    TRYJ(pb_prefilter(ctx, ss, lv, po.ncand, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(), d_rej.as<int32_t>()));
     pb_timer_end(ctx, PB_T_PREFILTER);
     pb_timer_begin(ctx, PB_T_ALIGN);
-    TRYJ(pb_align_locate(ctx, reads, ref, lv, nkept, kept_lens, kept_irr, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(),
+    TRYJ(pb_align_locate(ctx, ss, lv, nkept, kept_lens, kept_irr, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(),
                          d_rej.as<int32_t>(), job->d_recs.as<pb_locate_rec>(), prm->want_ops ? job->d_ops.as<uint8_t>() : nullptr,
                          prm->want_ops ? d_ops_off.as<int64_t>() : nullptr, job->d_stats.as<unsigned long long>()));
     pb_timer_end(ctx, PB_T_ALIGN);
@@ -250,5 +253,108 @@ extern "C" int pb_locate_batch(pb_ctx *ctx, const pb_index *ix, const pb_seqset 
     pb_timer_collect(ctx);
     pb_locate_job_free(job);
     pb_seqset_free(rs);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// assembler-side probe / verify: the trial loop of spaced_seed.cpp:424-436 with try_align (:261-299)
+// ---------------------------------------------------------------------------------------------
+
+extern "C" void pb_overlap_default_params(pb_overlap_params *p)
+{
+    if (!p) return;
+    p->R = 0.3;            // MAXR, common.h:37 (spaced_seed -r)
+    p->max_trial = 32;     // spaced_seed.cpp:93
+    p->min_overlap = 64;   // OVERLAP_MIN, common.h:39
+    p->maxn = 26000;       // t_aligner = seq_aligner<MAX_READ_LEN+MAX_DIFF_LEN, MAX_DIFF_LEN>, seq_aligner.h:260
+    p->maxm = 6000;
+    p->seed_at_quirk = 0;
+    p->want_ops = 0;
+    p->reserved = 0;
+}
+
+extern "C" int pb_overlap_batch(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const pb_seqset *reads,
+                                const pb_overlap_params *prm, pb_overlap_rec *recs, uint8_t *ops, const int64_t *ops_off)
+{
+    if (!ctx || !ix || !ref || !reads || !prm || ref_seq < 0 || ref_seq >= ref->n || (reads->n && !recs))
+        return pb_fail(ctx, PB_ERR_ARG, "pb_overlap_batch: bad argument");
+    if (prm->max_trial < 1 || prm->max_trial > 2048) return pb_fail(ctx, PB_ERR_ARG, "max_trial %d out of range", prm->max_trial);
+    if (prm->want_ops && (!ops || !ops_off)) return pb_fail(ctx, PB_ERR_ARG, "want_ops needs ops and ops_off");
+    if (ref->len[ref_seq] != ix->ref_len) return pb_fail(ctx, PB_ERR_ARG, "index was built over a different sequence");
+    if (reads->n * (int64_t)prm->max_trial * 2 > INT32_MAX) return pb_fail(ctx, PB_ERR_DOMAIN, "too many reads in one batch");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    pb_timer_reset(ctx);
+    pb_timer_begin(ctx, PB_T_TOTAL);
+    const int64_t n = reads->n;
+    if (n == 0) return PB_OK;
+    for (int64_t i = 0; i < n; ++i)
+        if (reads->len[i] < prm->max_trial + 16)
+            return pb_fail(ctx, PB_ERR_ARG, "read %lld is shorter than max_trial+16: seed_at(read, len-j-16) would start before the read "
+                           "(the reference only keeps reads longer than 500, spaced_seed.cpp:336)", (long long)i);
+    // backward trials align reversed views: build the reversed copies once per call
+    pb_seqset *reads_rev = nullptr, *ref_rev = nullptr;
+    int r = pb_seqset_reversed(ctx, reads, &reads_rev);
+    if (r == PB_OK) r = pb_seqset_reversed(ctx, ref, &ref_rev);
+    DevBuf d_kept, d_survive, d_rej, d_recs, d_ops, d_ops_off, d_stats;
+    ProbeOut po;
+    std::vector<int32_t> kept((size_t)n), kept_lens(reads->len.begin(), reads->len.end());
+    std::vector<uint8_t> kept_irr((size_t)n, 0);
+    for (int64_t i = 0; i < n; ++i) kept[i] = (int32_t)i;
+    int64_t extent = 0;
+    if (r == PB_OK) r = d_kept.alloc(ctx, (size_t)n * 4);
+    if (r == PB_OK) r = pb_h2d(ctx, d_kept.p, kept.data(), (size_t)n * 4);
+    if (r == PB_OK) r = d_recs.alloc_zero(ctx, (size_t)n * sizeof(pb_overlap_rec));
+    if (r == PB_OK) r = d_stats.alloc_zero(ctx, 16);
+    if (r == PB_OK && prm->want_ops) {
+        for (int64_t k = 0; k < n && r == PB_OK; ++k) {
+            if (ops_off[k] < 0) r = pb_fail(ctx, PB_ERR_ARG, "negative ops offset");
+            extent = std::max<int64_t>(extent, ops_off[k] + 3 * (int64_t)kept_lens[k] + 2 * prm->maxm + 16);
+        }
+        if (r == PB_OK) r = d_ops.alloc(ctx, (size_t)extent + 16);
+        if (r == PB_OK) r = d_ops_off.alloc(ctx, (size_t)n * 8);
+        if (r == PB_OK) r = pb_h2d(ctx, d_ops_off.p, ops_off, (size_t)n * 8);
+    }
+    if (r == PB_OK) r = pb_overlap_seed_probe(ctx, ix, reads, d_kept.as<int32_t>(), n, prm->max_trial, prm->min_overlap, prm->seed_at_quirk, &po);
+    if (r == PB_OK) {
+        LocateView lv;
+        lv.d_kept = d_kept.as<int32_t>();
+        lv.d_qoff = po.d_qoff.as<int64_t>();
+        lv.d_cand_pos = po.d_cand_pos.as<int32_t>();
+        lv.d_cand_q = po.d_cand_q.as<int32_t>();
+        lv.ntrial = 2 * prm->max_trial;
+        lv.ref_base = ref->base[ref_seq];
+        lv.ref_len = ref->len[ref_seq];
+        lv.mode = PB_MODE_OVERLAP;
+        lv.min_overlap = prm->min_overlap;
+        SeqSets ss = {reads, ref, reads_rev, ref_rev};
+        r = d_survive.alloc(ctx, (size_t)std::max<int64_t>(po.ncand, 1));
+        if (r == PB_OK) r = d_rej.alloc(ctx, (size_t)std::max<int64_t>(po.ncand, 1) * 4);
+        pb_timer_begin(ctx, PB_T_PREFILTER);
+        if (r == PB_OK) r = pb_prefilter(ctx, ss, lv, po.ncand, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(), d_rej.as<int32_t>());
+        pb_timer_end(ctx, PB_T_PREFILTER);
+        pb_timer_begin(ctx, PB_T_ALIGN);
+        // the record layouts of the two modes coincide field by field (pb_locate_rec / pb_overlap_rec, both 56 bytes)
+        if (r == PB_OK)
+            r = pb_align_locate(ctx, ss, lv, n, kept_lens, kept_irr, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(), d_rej.as<int32_t>(),
+                                reinterpret_cast<pb_locate_rec *>(d_recs.p), prm->want_ops ? d_ops.as<uint8_t>() : nullptr,
+                                prm->want_ops ? d_ops_off.as<int64_t>() : nullptr, d_stats.as<unsigned long long>());
+        pb_timer_end(ctx, PB_T_ALIGN);
+    }
+    if (r == PB_OK) {
+        pb_timer_begin(ctx, PB_T_D2H);
+        r = pb_d2h(ctx, recs, d_recs.p, (size_t)n * sizeof(pb_overlap_rec));
+        if (r == PB_OK && prm->want_ops && extent) r = pb_d2h(ctx, ops, d_ops.p, (size_t)extent);
+        pb_timer_end(ctx, PB_T_D2H);
+    }
+    pb_timer_end(ctx, PB_T_TOTAL);
+    int rs = pb_sync(ctx);
+    if (r == PB_OK) r = rs;
+    if (r == PB_OK) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) r = pb_fail(ctx, PB_ERR_CUDA, "overlap kernels failed: %s", cudaGetErrorString(e));
+    }
+    pb_timer_collect(ctx);
+    if (reads_rev) pb_seqset_free(reads_rev);
+    if (ref_rev) pb_seqset_free(ref_rev);
     return r;
 }

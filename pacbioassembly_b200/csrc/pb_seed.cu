@@ -551,6 +551,42 @@ __global__ void locate_seed_kernel(const uint32_t *__restrict__ pw, const int64_
     keys[q] = seed_from_be(h0, h1, (int)(g & 15)) & mask;
 }
 
+// assembler-side trials (spaced_seed.cpp:424-426, try_align :261-281): query t of read k is trial j = t/2, forward from
+// pos = j (t even) or backward from pos = len-j-16 (t odd); key = seed_at(read, pos) & mask.  quirk: the reference's
+// seed_at returns the u32 at BYTE offset pos of the record body when pos%4==0 (Q-S1) -- read from the kept .bin image,
+// zero past its end.  A segment shorter than min_overlap is not probed (:280): its key is forced to 0 (= never found).
+__global__ void overlap_seed_kernel(const uint32_t *__restrict__ pw, const int64_t *__restrict__ base, const int32_t *__restrict__ len,
+                                    const int32_t *__restrict__ kept, int64_t nkept, int max_trial, int min_overlap, uint32_t mask,
+                                    const uint8_t *__restrict__ image, int64_t image_bytes, const int64_t *__restrict__ recoff,
+                                    int quirk, uint32_t *__restrict__ keys)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ntr = 2 * max_trial;
+    if (q >= nkept * ntr) return;
+    const int64_t k = q / ntr;
+    const int t = (int)(q - k * ntr), j = t >> 1;
+    const bool forward = (t & 1) == 0;
+    const int r = kept[k];
+    const int slen = len[r];
+    const int pos = forward ? j : slen - j - 16;
+    const int s_len = forward ? slen - pos : pos + 16;
+    uint32_t key = 0u;
+    if (pos >= 0 && s_len >= min_overlap) {
+        if (quirk && (pos & 3) == 0 && image) {
+            const int64_t o = recoff[r] + pos;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (o + b < image_bytes) key |= (uint32_t)image[o + b] << (8 * b);
+        } else {
+            const int64_t g = base[r] + pos;
+            const uint32_t h0 = bswap32(__ldg(pw + (g >> 4))), h1 = bswap32(__ldg(pw + (g >> 4) + 1));
+            key = seed_from_be(h0, h1, (int)(g & 15));
+        }
+        key &= mask;
+    }
+    keys[q] = key;
+}
+
 static IndexView view_of(const pb_index *ix)
 {
     IndexView iv;
@@ -561,29 +597,15 @@ static IndexView view_of(const pb_index *ix)
     return iv;
 }
 
-int pb_locate_seed_probe(pb_ctx *ctx, const pb_index *ix, const pb_seqset *reads, const int32_t *d_kept, int64_t nkept,
-                         int ntrial, ProbeOut *po)
+// keys (one per query, already on the device) -> counts -> exclusive offsets -> candidate arrays
+static int probe_and_gather(pb_ctx *ctx, const pb_index *ix, const uint32_t *d_keys, int64_t nq, ProbeOut *po)
 {
-    const int64_t nq = nkept * ntrial;
-    po->ncand = 0;
-    PB_TRY(po->d_qoff.alloc(ctx, (size_t)(nq + 2) * 8));
-    if (nq == 0) {
-        PB_CUDA(ctx, cudaMemsetAsync(po->d_qoff.p, 0, 16, ctx->stream));
-        PB_TRY(po->d_cand_pos.alloc(ctx, 16));
-        PB_TRY(po->d_cand_q.alloc(ctx, 16));
-        return PB_OK;
-    }
-    DevBuf d_keys, d_cnt, tmp;
-    PB_TRY(d_keys.alloc(ctx, (size_t)nq * 4));
+    DevBuf d_cnt, tmp;
     PB_TRY(d_cnt.alloc(ctx, (size_t)nq * 4));
     const unsigned grid = (unsigned)((nq + 255) / 256);
-    pb_timer_begin(ctx, PB_T_SEED);
-    locate_seed_kernel<<<grid, 256, 0, ctx->stream>>>(reads->d_packed.as<uint32_t>(), reads->d_base.as<int64_t>(), d_kept, nkept, ntrial, ix->mask, d_keys.as<uint32_t>());
-    PB_LAUNCH_CHECK(ctx);
-    pb_timer_end(ctx, PB_T_SEED);
     pb_timer_begin(ctx, PB_T_PROBE);
     IndexView iv = view_of(ix);
-    probe_count_kernel<<<grid, 256, 0, ctx->stream>>>(iv, d_keys.as<uint32_t>(), nq, d_cnt.as<uint32_t>());
+    probe_count_kernel<<<grid, 256, 0, ctx->stream>>>(iv, d_keys, nq, d_cnt.as<uint32_t>());
     PB_LAUNCH_CHECK(ctx);
     PB_TRY(pb_scan_i64(ctx, d_cnt.as<uint32_t>(), po->d_qoff.as<int64_t>(), nq, tmp));
     int64_t ncand = 0;
@@ -594,11 +616,54 @@ int pb_locate_seed_probe(pb_ctx *ctx, const pb_index *ix, const pb_seqset *reads
     PB_TRY(po->d_cand_pos.alloc(ctx, (size_t)std::max<int64_t>(ncand, 1) * 4));
     PB_TRY(po->d_cand_q.alloc(ctx, (size_t)std::max<int64_t>(ncand, 1) * 4));
     if (ncand) {
-        probe_gather_kernel<<<grid, 256, 0, ctx->stream>>>(iv, d_keys.as<uint32_t>(), nq, po->d_qoff.as<int64_t>(), po->d_cand_pos.as<int32_t>(), po->d_cand_q.as<int32_t>());
+        probe_gather_kernel<<<grid, 256, 0, ctx->stream>>>(iv, d_keys, nq, po->d_qoff.as<int64_t>(), po->d_cand_pos.as<int32_t>(), po->d_cand_q.as<int32_t>());
         PB_LAUNCH_CHECK(ctx);
     }
     pb_timer_end(ctx, PB_T_PROBE);
     return PB_OK;
+}
+
+static int empty_probe(pb_ctx *ctx, ProbeOut *po)
+{
+    PB_CUDA(ctx, cudaMemsetAsync(po->d_qoff.p, 0, 16, ctx->stream));
+    PB_TRY(po->d_cand_pos.alloc(ctx, 16));
+    PB_TRY(po->d_cand_q.alloc(ctx, 16));
+    return PB_OK;
+}
+
+int pb_locate_seed_probe(pb_ctx *ctx, const pb_index *ix, const pb_seqset *reads, const int32_t *d_kept, int64_t nkept,
+                         int ntrial, ProbeOut *po)
+{
+    const int64_t nq = nkept * ntrial;
+    po->ncand = 0;
+    PB_TRY(po->d_qoff.alloc(ctx, (size_t)(nq + 2) * 8));
+    if (nq == 0) return empty_probe(ctx, po);
+    DevBuf d_keys;
+    PB_TRY(d_keys.alloc(ctx, (size_t)nq * 4));
+    pb_timer_begin(ctx, PB_T_SEED);
+    locate_seed_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(reads->d_packed.as<uint32_t>(), reads->d_base.as<int64_t>(), d_kept, nkept, ntrial, ix->mask, d_keys.as<uint32_t>());
+    PB_LAUNCH_CHECK(ctx);
+    pb_timer_end(ctx, PB_T_SEED);
+    return probe_and_gather(ctx, ix, d_keys.as<uint32_t>(), nq, po);
+}
+
+int pb_overlap_seed_probe(pb_ctx *ctx, const pb_index *ix, const pb_seqset *reads, const int32_t *d_kept, int64_t nkept,
+                          int max_trial, int min_overlap, int quirk, ProbeOut *po)
+{
+    const int64_t nq = nkept * 2 * max_trial;
+    po->ncand = 0;
+    PB_TRY(po->d_qoff.alloc(ctx, (size_t)(nq + 2) * 8));
+    if (nq == 0) return empty_probe(ctx, po);
+    DevBuf d_keys;
+    PB_TRY(d_keys.alloc(ctx, (size_t)nq * 4));
+    pb_timer_begin(ctx, PB_T_SEED);
+    overlap_seed_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(
+        reads->d_packed.as<uint32_t>(), reads->d_base.as<int64_t>(), reads->d_len.as<int32_t>(), d_kept, nkept, max_trial, min_overlap,
+        ix->mask, reads->image_bytes ? reads->d_image.as<uint8_t>() : nullptr, reads->image_bytes,
+        reads->image_bytes ? reads->d_recoff.as<int64_t>() : nullptr, quirk, d_keys.as<uint32_t>());
+    PB_LAUNCH_CHECK(ctx);
+    pb_timer_end(ctx, PB_T_SEED);
+    return probe_and_gather(ctx, ix, d_keys.as<uint32_t>(), nq, po);
 }
 
 __global__ void find_write_kernel(IndexView iv, const uint32_t *__restrict__ keys, int64_t n, const int64_t *__restrict__ pos_off,

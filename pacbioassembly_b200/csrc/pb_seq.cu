@@ -14,7 +14,7 @@ struct IngestSrc {
     const uint8_t *text;    // device blob
     const int64_t *toff;    // [n] offset of element 0 (text mode) or of the record's first body byte (packed mode)
     const int32_t *tstride; // [n] +1/-1, or NULL
-    int packed;             // 1: source is 4-bases-per-byte records (dna_seq.h:113-127)
+    int packed;             // PB_SRC_TEXT / PB_SRC_PACKED / PB_SRC_REVLINE
 };
 
 #define INGEST_RUN 64 // consecutive 32-base words handled by one warp: one owner search, then a forward walk
@@ -55,9 +55,13 @@ ingest_kernel(IngestSrc src, const int64_t *__restrict__ base, const int32_t *__
             uint32_t code = 3u;
             bool irregular = false;
             if (valid) {
-                if (src.packed) {
+                if (src.packed == PB_SRC_PACKED) {
                     uint32_t byte = src.text[a_off + (rel >> 2)];
                     code = (byte >> (6 - 2 * (rel & 3))) & 3u;
+                } else if (src.packed == PB_SRC_REVLINE) {
+                    const int64_t gs = a_off + (a_len - 1 - rel); // same sequence of the source line, last base first
+                    uint32_t byte = src.text[gs >> 2];
+                    code = (byte >> (6 - 2 * (gs & 3))) & 3u;
                 } else {
                     uint32_t ch = src.text[a_off + rel * a_st];
                     code = c2i(ch);
@@ -116,7 +120,7 @@ collect_exceptions_kernel(IngestSrc src, const int64_t *__restrict__ base, const
 }
 
 int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, const int32_t *h_len,
-                    const int32_t *h_stride, int64_t n, bool packed_src, pb_seqset **out)
+                    const int32_t *h_stride, int64_t n, int src_mode, pb_seqset **out)
 {
     pb_seqset *s = new pb_seqset();
     s->ctx = ctx;
@@ -160,7 +164,7 @@ int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, cons
     src.text = (const uint8_t *)d_text;
     src.toff = d_toff.as<int64_t>();
     src.tstride = h_stride ? d_stride.as<int32_t>() : nullptr;
-    src.packed = packed_src ? 1 : 0;
+    src.packed = src_mode;
     int64_t blocks = std::min<int64_t>(((nw + INGEST_RUN - 1) / INGEST_RUN + 7) / 8, (int64_t)ctx->sm_count * 16);
     if (blocks < 1) blocks = 1;
     pb_timer_begin(ctx, PB_T_INGEST);
@@ -179,7 +183,7 @@ int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, cons
     TRYS(pb_sync(ctx)); // d_toff/d_stride are released after the kernel (stream-ordered) but flags are needed now
     s->tab.assign((size_t)n, 0x41414141u); // unused slots hold 'A': a value the exception list never contains
     s->tab_count.assign((size_t)n, 0);
-    if (nirr > 0 && !packed_src) {
+    if (nirr > 0 && src_mode == PB_SRC_TEXT) {
         // rare path: list the offending bytes, sort them by line position on the host, build the per-sequence tables
         DevBuf d_cursor, d_pos, d_val, d_seq;
         TRYS(d_cursor.alloc_zero(ctx, 16));
@@ -262,7 +266,7 @@ extern "C" int pb_seqset_from_text(pb_ctx *ctx, const char *text, const int64_t 
     pb_timer_end(ctx, PB_T_H2D);
     std::vector<int64_t> rel(off, off + n);
     for (auto &x : rel) x -= lo;
-    return pb_seqset_build(ctx, d_text.p, rel.data(), len, stride, n, false, out);
+    return pb_seqset_build(ctx, d_text.p, rel.data(), len, stride, n, PB_SRC_TEXT, out);
 }
 
 extern "C" int pb_seqset_from_device_text(pb_ctx *ctx, const void *d_text, size_t text_bytes, const int64_t *off,
@@ -274,7 +278,7 @@ extern "C" int pb_seqset_from_device_text(pb_ctx *ctx, const void *d_text, size_
     int64_t lo, hi;
     if (!text_extent(off, len, stride, n, &lo, &hi)) return pb_fail(ctx, PB_ERR_ARG, "stride must be +1 or -1");
     if (lo < 0 || (size_t)hi > text_bytes) return pb_fail(ctx, PB_ERR_ARG, "views reach outside the device text blob");
-    return pb_seqset_build(ctx, d_text, off, len, stride, n, false, out);
+    return pb_seqset_build(ctx, d_text, off, len, stride, n, PB_SRC_TEXT, out);
 }
 
 extern "C" int pb_seqset_from_bin(pb_ctx *ctx, const uint8_t *bin, size_t nbytes, int min_excl, int max_excl,
@@ -303,7 +307,25 @@ extern "C" int pb_seqset_from_bin(pb_ctx *ctx, const uint8_t *bin, size_t nbytes
     pb_timer_begin(ctx, PB_T_H2D);
     PB_TRY(pb_h2d(ctx, d_bin.p, bin, nbytes));
     pb_timer_end(ctx, PB_T_H2D);
-    return pb_seqset_build(ctx, d_bin.p, off.data(), len.data(), nullptr, (int64_t)off.size(), true, out);
+    PB_TRY(pb_seqset_build(ctx, d_bin.p, off.data(), len.data(), nullptr, (int64_t)off.size(), PB_SRC_PACKED, out));
+    // keep the image: dna_seq::seed_at's pos%4==0 branch reads raw bytes of it, possibly of later records (SURVEY Q-S1)
+    pb_seqset *s = *out;
+    s->image_bytes = (int64_t)nbytes;
+    s->d_image.p = d_bin.p; s->d_image.bytes = d_bin.bytes; s->d_image.ctx = ctx;
+    d_bin.p = nullptr; d_bin.bytes = 0;
+    int r = s->d_recoff.alloc(ctx, (off.size() + 1) * sizeof(int64_t));
+    if (r == PB_OK) r = pb_h2d(ctx, s->d_recoff.p, off.data(), off.size() * sizeof(int64_t));
+    if (r == PB_OK) r = pb_sync(ctx);
+    if (r != PB_OK) { pb_seqset_free(s); *out = nullptr; }
+    return r;
+}
+
+int pb_seqset_reversed(pb_ctx *ctx, const pb_seqset *s, pb_seqset **out)
+{ // every sequence read backwards (seq_accessor with forward == false, dna_seq.h:185-233), same line layout
+    for (int64_t i = 0; i < s->n; ++i)
+        if (s->flags[i] & PB_FLAG_IRREGULAR)
+            return pb_fail(ctx, PB_ERR_ALPHABET, "backward views of sequences with bytes outside {A,C,G,T} are not supported");
+    return pb_seqset_build(ctx, s->d_packed.p, s->base.data(), s->len.data(), nullptr, s->n, PB_SRC_REVLINE, out);
 }
 
 extern "C" void pb_seqset_free(pb_seqset *s)

@@ -40,6 +40,11 @@ LOCATE_DTYPE = np.dtype([(n, np.int32) for n in
                           "nedit", "ncand")] + [("_pad", np.int32), ("cells", np.int64)])
 assert LOCATE_DTYPE.itemsize == C.sizeof(LocateRec) == 56
 
+OVERLAP_DTYPE = np.dtype([(n, np.int32) for n in
+                          ("id", "found", "j", "ref_pos", "cost", "read_pos", "dir", "matlen_a", "matlen_b", "nedit",
+                           "ncand", "_pad")] + [("cells", np.int64)])
+assert OVERLAP_DTYPE.itemsize == 56
+
 
 def build_oracle(with_ref: bool = True) -> None:
     subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "all"])
@@ -80,6 +85,23 @@ class Oracle:
         L.pbo_locate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                  C.c_uint32, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_void_p]
+
+        L.pbo_overlap.restype = C.c_int64
+        L.pbo_overlap.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32,
+                                  C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+
+    def overlap(self, ix, ref: np.ndarray, image: bytes, mask: int, R: float = 0.3, max_trial: int = 32, min_overlap: int = 64,
+                maxn: int = 26000, maxm: int = 6000, quirk: bool = False, nthreads: int = 1, min_excl: int = 500,
+                max_excl: int = 20000):
+        """spaced_seed.cpp:424-436 + try_align :261-299 over a .bin image against a REFSEQ-policy index"""
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        img = np.frombuffer(image, dtype=np.uint8)
+        args = (ix, ref.ctypes.data, len(ref), img.ctypes.data, len(img), min_excl, max_excl, mask, R, max_trial, min_overlap,
+                maxn, maxm, int(quirk), nthreads)
+        nk = self.lib.pbo_overlap(*args, None)
+        recs = np.zeros(nk, dtype=OVERLAP_DTYPE)
+        self.lib.pbo_overlap(*args, recs.ctypes.data)
+        return recs
 
     # -- L0 --
     def encode(self, text: bytes) -> int:
@@ -208,6 +230,26 @@ class Ref:
         L.pbref_locator_run.restype = C.c_int64
         L.pbref_locator_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int,
                                         C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+
+    def overlap(self, ref: np.ndarray, image: bytes, mask: int, R: float = 0.3, max_trial: int = 32, min_excl: int = 500,
+                max_excl: int = 20000):
+        """the reference's own try_align machinery (locked ref_seq, get_seedmap, seed_at incl. its pos%4==0 branch)"""
+        self.lib.pbref_overlap.restype = C.c_int64
+        self.lib.pbref_overlap.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_uint32, C.c_double,
+                                           C.c_int, C.c_void_p]
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        img = np.frombuffer(image + b"\0" * 65536, dtype=np.uint8).copy()  # the over-reads of seed_at land in zeros
+        nrec = 0
+        p = 0
+        while p + 4 <= len(image):
+            l = int.from_bytes(image[p:p + 4], "little")
+            nrec += min_excl < l < max_excl
+            p += 4 + (l + 3) // 4
+        recs = np.zeros(nrec, dtype=OVERLAP_DTYPE)
+        n = self.lib.pbref_overlap(ref.ctypes.data, len(ref), img.ctypes.data, len(image), min_excl, max_excl, mask, R, max_trial,
+                                   recs.ctypes.data)
+        assert n == nrec
+        return recs
 
     def locator_open(self, ref: np.ndarray, mask: int):
         """locator.cpp:57-66 (contig + seed map), built once"""

@@ -455,3 +455,60 @@ def test_locate_properties_at_scale(ctx):
     r0 = ctx.locate(ix, t0, o0, l0, R=0.15)
     assert (r0["found"] == 1).all() and (r0["cost"] == 0).all() and (r0["j"] == 0).all()
     assert (r0["pos"] == s0).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# assembler-side trial loop (spaced_seed.cpp:424-436, try_align :261-299)
+# ---------------------------------------------------------------------------------------------
+
+OV_FIELDS = ("id", "found", "j", "ref_pos", "cost", "read_pos", "dir", "matlen_a", "matlen_b", "nedit", "ncand")
+
+
+def test_overlap_golden_and_oracle(ctx, golden, oracle):
+    from test_oracle import overlap_workload
+    for g in golden["overlap"]:
+        ref, image = overlap_workload(g["seed"], g["ref_len"], g["nreads"])
+        rs = ctx.seqset_one(ref)
+        ix = ctx.index(rs, g["mask"], policy=1)
+        reads = ctx.seqset_from_bin(image)
+        # the shipped behaviour (seed_at reads byte offset pos when pos%4==0): against the reference's own output
+        got = ctx.overlap(ix, reads, R=g["R"], seed_at_quirk=1)
+        assert len(got) == len(g["records"])
+        for k, row in enumerate(g["records"]):
+            for n, v in row.items():
+                assert int(got[n][k]) == v, (k, n, int(got[n][k]), v)
+        # the intended behaviour (seed at base pos): against the oracle, transcripts included
+        got, ops = ctx.overlap(ix, reads, R=g["R"], want_ops=True)
+        oix = oracle.index_build(ref, g["mask"], policy=1)
+        want = oracle.overlap(oix, ref, image, g["mask"], R=g["R"], quirk=False, nthreads=4)
+        oracle.index_free(oix)
+        for n in OV_FIELDS + ("cells",):
+            assert (got[n] == want[n]).all(), n
+        f = got["found"] == 1
+        assert f.sum() > 5 and (got["dir"][f] == -1).any() and (got["dir"][f] == 1).any()
+        for k in np.nonzero(f)[0]:
+            o = ops[k]
+            assert len(o) == got["nedit"][k]
+            assert int((o != INSERT).sum()) == got["matlen_a"][k] and int((o != DELETE).sum()) == got["matlen_b"][k]
+
+
+def test_overlap_longer_reads(ctx, oracle):
+    """5 kbp-class CLR reads against a 45 kbp reference (head and tail windows of get_seedmap both populated)"""
+    from test_oracle import overlap_workload
+    ref, image = overlap_workload(91, 45000, 30)
+    import cpu_libs
+    o = cpu_libs.oracle()
+    lens = workload.read_lengths(92, 30, mean=4000.0, sigma_log=0.4, lo=600, hi=12000)
+    txt, offs, lens, _ = workload.reads(93, ref, lens, 0.05, 0.03, 0.02, nthreads=1)
+    image = b"".join(o.text2bin(txt[offs[k]: offs[k] + lens[k]].tobytes()) for k in range(len(lens)))
+    rs = ctx.seqset_one(ref)
+    for quirk in (0, 1):
+        ix = ctx.index(rs, MASKS[0], policy=1)
+        reads = ctx.seqset_from_bin(image)
+        got = ctx.overlap(ix, reads, R=0.3, seed_at_quirk=quirk)
+        oix = oracle.index_build(ref, MASKS[0], policy=1)
+        want = oracle.overlap(oix, ref, image, MASKS[0], R=0.3, quirk=bool(quirk), nthreads=8)
+        oracle.index_free(oix)
+        for n in OV_FIELDS + ("cells",):
+            assert (got[n] == want[n]).all(), (quirk, n)
+    assert got["found"].sum() > 3

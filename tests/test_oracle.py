@@ -309,3 +309,42 @@ def test_live_encode_c2i(oracle, ref):
     for _ in range(300):
         t = bytes(rng.integers(1, 256, 16).tolist())
         assert ref.encode(t) == oracle.encode(t)
+
+
+def overlap_workload(seed=81, ref_len=30000, nreads=40):
+    """a contig and reads drawn from it, as a .bin image (binary_test.cpp:55-63 layout: records back to back)"""
+    import cpu_libs
+    o = cpu_libs.oracle()
+    ref = workload.reference(seed, ref_len)
+    lens = workload.read_lengths(seed + 1, nreads, mean=1500.0, sigma_log=0.4, lo=300, hi=4000)
+    txt, offs, lens, _ = workload.reads(seed + 2, ref, lens, 0.04, 0.02, 0.01, nthreads=1)
+    image = b"".join(o.text2bin(txt[offs[k]: offs[k] + lens[k]].tobytes()) for k in range(nreads))
+    return ref, image
+
+
+def test_live_overlap_trial_loop(oracle, ref):
+    """spaced_seed.cpp:424-436 / try_align :261-299 through the reference's own ref_seq::try_align, seed_at (with its
+    pos%4==0 branch, Q-S1) and get_seedmap, against the restatement"""
+    g, image = overlap_workload()
+    for mask in (0xff3c3ffc, 0x3fcfccf3):
+        want = ref.overlap(g, image, mask, R=0.3)
+        ix = oracle.index_build(g, mask, policy=1)
+        got = oracle.overlap(ix, g, image, mask, R=0.3, quirk=True, nthreads=2)
+        oracle.index_free(ix)
+        assert len(got) == len(want) > 20
+        for n in ("id", "found", "j", "ref_pos", "cost", "read_pos", "dir", "matlen_a", "matlen_b", "nedit", "ncand"):
+            assert (got[n] == want[n]).all(), n
+        assert want["found"].sum() > 5
+        assert (want["dir"][want["found"] == 1] == -1).any() and (want["dir"][want["found"] == 1] == 1).any()
+
+
+def test_golden_overlap(oracle, golden):
+    for g in golden["overlap"]:
+        ref, image = overlap_workload(g["seed"], g["ref_len"], g["nreads"])
+        ix = oracle.index_build(ref, g["mask"], policy=1)
+        got = oracle.overlap(ix, ref, image, g["mask"], R=g["R"], quirk=True)
+        oracle.index_free(ix)
+        assert len(got) == len(g["records"])
+        for k, row in enumerate(g["records"]):
+            for n, v in row.items():
+                assert int(got[n][k]) == v, (k, n)
