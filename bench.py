@@ -356,7 +356,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 bit-vectors (int32 costs)", "data": "synthetic",
+            "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"config2: {REF_LEN} bp iid reference, {args.reads} CLR reads per GPU (mean 5 kbp, "
                                    f"ins 9/del 4/sub 2 %), mask {MASK:08x}, R={R}, ntrial 50, locator.cpp semantics",
                        "l2": "inputs (0.5 GB of reads per step) exceed the 126 MB L2; no explicit flush",

@@ -216,6 +216,10 @@ PB_API int64_t pb_locate_job_ncand(const pb_locate_job *job); /* seed hits (cand
 /* after pb_locate_fetch: out[0] = candidates gathered (K2), out[1] = alignments the banded aligner (K3) ran,
  * out[2] = DP cells K3 computed (reference cell count of those alignments), out[3] = 0 */
 PB_API int pb_locate_job_stats(const pb_locate_job *job, int64_t *out /* [4] */);
+/* Diagonal-bin tally of each kept read's seed hits (K2): votes[k] = hits whose diagonal pos - j falls in the fullest
+ * 256-base bin, best_diag[k] = that bin's first diagonal.  A diagnostic of how concentrated the hits are; candidates are
+ * never reordered or pruned by it (the reference takes the first success in list order).  Either pointer may be NULL. */
+PB_API int pb_locate_job_votes(pb_ctx *ctx, const pb_locate_job *job, int32_t *votes, int32_t *best_diag);
 PB_API int pb_locate_job_ops_layout(const pb_locate_job *job, int64_t *ops_off /* [nkept] or NULL */, int64_t *extent);
 PB_API int pb_locate_fetch(pb_ctx *ctx, const pb_locate_job *job, pb_locate_rec *recs, uint8_t *ops);
 PB_API void pb_locate_job_free(pb_locate_job *job);

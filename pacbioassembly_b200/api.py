@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
         "pb_locate_job_ncand": (i64, [vp]),
         "pb_locate_job_ops_layout": (C.c_int, [vp, vp, P(i64)]),
         "pb_locate_job_stats": (C.c_int, [vp, vp]),
+        "pb_locate_job_votes": (C.c_int, [vp, vp, vp, vp]),
         "pb_locate_fetch": (C.c_int, [vp, vp, vp, vp]),
         "pb_locate_job_free": (None, [vp]),
         "pb_overlap_default_params": (None, [P(OverlapParams)]),
@@ -485,6 +486,13 @@ class LocateJob:
         out = np.zeros(4, dtype=np.int64)
         self.ctx.check(self.ctx._L.pb_locate_job_stats(self.h, _ptr(out)))
         return {"ncand": int(out[0]), "dp_alignments": int(out[1]), "dp_cells": int(out[2])}
+
+    def votes(self):
+        """(votes, best_diag) per kept read: the diagonal-bin tally of its seed hits (diagnostic only)"""
+        v = np.zeros(max(self.nkept, 1), dtype=np.int32)
+        d = np.zeros(max(self.nkept, 1), dtype=np.int32)
+        self.ctx.check(self.ctx._L.pb_locate_job_votes(self.ctx.h, self.h, _ptr(v), _ptr(d)))
+        return v[: self.nkept], d[: self.nkept]
 
     def ops_layout(self):
         off = np.zeros(max(self.nkept, 1), dtype=np.int64)

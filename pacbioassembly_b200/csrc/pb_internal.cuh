@@ -176,6 +176,8 @@ struct ProbeOut {
 // keys of the first ntrial offsets of every kept read, then probe + gather
 int pb_locate_seed_probe(pb_ctx *ctx, const pb_index *ix, const pb_seqset *reads, const int32_t *d_kept, int64_t nkept,
                          int ntrial, ProbeOut *po);
+// diagonal-bin tally per read (diagnostic; never used to prune): votes in the fullest 256-base bin and that bin's diagonal
+int pb_vote(pb_ctx *ctx, const ProbeOut *po, int64_t nkept, int ntrial, int32_t *d_votes, int32_t *d_best_diag);
 // overlap mode: per read 2*max_trial queries (j forward at pos j, j backward at pos len-j-16), spaced_seed.cpp:424-426
 int pb_overlap_seed_probe(pb_ctx *ctx, const pb_index *ix, const pb_seqset *reads, const int32_t *d_kept, int64_t nkept,
                           int max_trial, int min_overlap, int quirk, ProbeOut *po);

@@ -96,7 +96,7 @@ struct pb_locate_job {
     int want_ops = 0;
     std::vector<int64_t> ops_off;
     int64_t extent = 0;
-    DevBuf d_recs, d_ops, d_stats;
+    DevBuf d_recs, d_ops, d_stats, d_votes, d_best_diag;
     mutable unsigned long long stats[2] = {0, 0};
 };
 
@@ -160,6 +160,9 @@ extern "C" int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *r
     ProbeOut po;
     TRYJ(pb_locate_seed_probe(ctx, ix, reads, d_kept.as<int32_t>(), nkept, prm->ntrial, &po));
     job->ncand = po.ncand;
+    TRYJ(job->d_votes.alloc(ctx, (size_t)nkept * 4));
+    TRYJ(job->d_best_diag.alloc(ctx, (size_t)nkept * 4));
+    TRYJ(pb_vote(ctx, &po, nkept, prm->ntrial, job->d_votes.as<int32_t>(), job->d_best_diag.as<int32_t>()));
     LocateView lv;
     lv.d_kept = d_kept.as<int32_t>();
     lv.d_qoff = po.d_qoff.as<int64_t>();
@@ -197,6 +200,16 @@ extern "C" int pb_locate_job_stats(const pb_locate_job *job, int64_t *out)
     out[2] = (int64_t)job->stats[0];
     out[3] = 0;
     return PB_OK;
+}
+
+extern "C" int pb_locate_job_votes(pb_ctx *ctx, const pb_locate_job *job, int32_t *votes, int32_t *best_diag)
+{
+    if (!ctx || !job) return pb_fail(ctx, PB_ERR_ARG, "pb_locate_job_votes: bad argument");
+    if (job->nkept == 0) return PB_OK;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (votes) PB_TRY(pb_d2h(ctx, votes, job->d_votes.p, (size_t)job->nkept * 4));
+    if (best_diag) PB_TRY(pb_d2h(ctx, best_diag, job->d_best_diag.p, (size_t)job->nkept * 4));
+    return pb_sync(ctx);
 }
 
 extern "C" int pb_locate_job_ops_layout(const pb_locate_job *job, int64_t *ops_off, int64_t *extent)

@@ -538,6 +538,62 @@ __global__ void probe_gather_kernel(IndexView iv, const uint32_t *__restrict__ k
     }
 }
 
+// Diagonal-bin voting: one warp per read tallies its candidates' diagonals (pos - j) in 256-base bins with a
+// shared-memory histogram; __match_any_sync groups the lanes that hit the same bin so each group issues one shared-memory
+// atomic, then a shuffle reduction picks the fullest bin.  The tally is reported per read (votes / best diagonal); it is
+// NOT used to reorder or prune candidates -- the reference takes the first success in list order, so
+// pruning would change results.  It tells a caller how concentrated a read's seed hits are.
+#define VOTE_BINS 256
+__global__ void __launch_bounds__(128)
+vote_kernel(const int64_t *__restrict__ qoff, const int32_t *__restrict__ cand_pos, const int32_t *__restrict__ cand_q, int64_t nkept,
+            int ntrial, int32_t *__restrict__ votes, int32_t *__restrict__ best_diag)
+{
+    __shared__ int hist[4][VOTE_BINS];
+    __shared__ int tag[4][VOTE_BINS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t k = (int64_t)blockIdx.x * 4 + warp;
+    if (k >= nkept) return;
+    for (int b = lane; b < VOTE_BINS; b += 32) { hist[warp][b] = 0; tag[warp][b] = -1; }
+    __syncwarp();
+    const int64_t c0 = qoff[k * ntrial], c1 = qoff[(k + 1) * ntrial];
+    for (int64_t cb = c0; cb < c1; cb += 32) {
+        const int64_t c = cb + lane;
+        const bool valid = c < c1;
+        int bin = -1;
+        if (valid) {
+            const int j = cand_q[c] - (int)(k * ntrial);
+            bin = (cand_pos[c] - j) >> 8; // 256-base diagonal bins (arithmetic shift: negative diagonals have their own bins)
+        }
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const unsigned peers = __match_any_sync(act, bin);
+            if (lane == __ffs(peers) - 1) { // one shared-memory atomic per distinct bin in this batch of 32
+                const int slot = (unsigned)bin % VOTE_BINS;
+                atomicAdd(&hist[warp][slot], __popc(peers));
+                tag[warp][slot] = bin; // bins that collide in the table share a slot: an upper bound, fine for a tally
+            }
+        }
+        __syncwarp();
+    }
+    int best = 0, bdiag = 0;
+    for (int b = lane; b < VOTE_BINS; b += 32)
+        if (hist[warp][b] > best) { best = hist[warp][b]; bdiag = tag[warp][b]; }
+    for (int d = 16; d; d >>= 1) {
+        const int ob = __shfl_xor_sync(0xffffffffu, best, d), od = __shfl_xor_sync(0xffffffffu, bdiag, d);
+        if (ob > best || (ob == best && od < bdiag)) { best = ob; bdiag = od; }
+    }
+    if (lane == 0) { votes[k] = best; best_diag[k] = bdiag << 8; }
+}
+
+int pb_vote(pb_ctx *ctx, const ProbeOut *po, int64_t nkept, int ntrial, int32_t *d_votes, int32_t *d_best_diag)
+{
+    if (nkept <= 0) return PB_OK;
+    vote_kernel<<<(unsigned)((nkept + 3) / 4), 128, 0, ctx->stream>>>(po->d_qoff.as<int64_t>(), po->d_cand_pos.as<int32_t>(),
+                                                                     po->d_cand_q.as<int32_t>(), nkept, ntrial, d_votes, d_best_diag);
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
+
 // seeds at the first ntrial offsets of every kept read: key = encode(read + j) & mask (locator.cpp:75)
 __global__ void locate_seed_kernel(const uint32_t *__restrict__ pw, const int64_t *__restrict__ base, const int32_t *__restrict__ kept,
                                    int64_t nkept, int ntrial, uint32_t mask, uint32_t *__restrict__ keys)

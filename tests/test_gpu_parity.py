@@ -449,6 +449,17 @@ def test_locate_properties_at_scale(ctx):
                 cost += 1; i += 1
         assert cost == recs["cost"][k]
         assert abs(int(recs["pos"][k]) - int(recs["j"][k]) - int(starts[k])) < 0.35 * lens[k]
+    # diagonal-bin tally (K2 voting, diagnostic): located reads' fullest bin sits on their true diagonal
+    s_all = ctx.seqset(txt, offs, lens)
+    job = ctx.locate_run(ix, s_all, R=0.3)
+    r3 = job.fetch()
+    votes, bdiag = job.votes()
+    for n in recs.dtype.names:
+        assert (r3[n] == recs[n]).all()
+    ok = np.nonzero(f & (votes >= 3))[0]
+    assert len(ok) > 500
+    assert (np.abs(bdiag[ok].astype(np.int64) - starts[ok]) < 0.1 * lens[ok] + 512).mean() > 0.98
+    job.free(); s_all.free()
     # error-free reads
     l0 = np.full(64, 2000, dtype=np.int32)
     t0, o0, l0, s0 = workload.reads(9, ref, l0, 0.0, 0.0, 0.0)
