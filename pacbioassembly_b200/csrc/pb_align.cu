@@ -245,6 +245,35 @@ struct AlnRes {
     long long cells;
 };
 
+// ---- 1-D bulk TMA: global -> shared, completion on an mbarrier (cp.async.bulk, SASS UBLKCP) -----------------------
+// Each warp stages the bit-plane words of its seg_b window with one bulk copy per plane instead of per-lane loads;
+// the Eq planes are then built from shared memory.  16-byte aligned source / destination / size.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase)
+{
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(phase)
+                 : "memory");
+    return ok != 0;
+}
+
 // multi-word add helpers: the carry chain lives in the PTX condition code between consecutive statements
 __device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b)
 {
@@ -373,7 +402,8 @@ template <int S, bool IRR>
 __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_len, uint32_t a_tab, const SeqView &B, int64_t b_bit, int b_len,
                                        double R, int maxn, int maxm, uint32_t *__restrict__ planes, int PW,
                                        uint32_t *__restrict__ par, uint8_t *__restrict__ opsrev, uint8_t *__restrict__ ops_out,
-                                       uint32_t c31, uint32_t c2, AlnRes &res)
+                                       uint32_t c31, uint32_t c2, uint32_t *__restrict__ raw, int RW, uint64_t *bar, uint32_t &phase,
+                                       AlnRes &res)
 {
     constexpr int T = 32 * S;
     const int lane = threadIdx.x & 31;
@@ -388,6 +418,38 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
     // ---- Eq planes of seg_b in shared memory: plane c, bit t <-> (b[t - D] == c), zero outside [0,len_b)
     constexpr bool PAD = (S % 2) == 0; // see row_step: physical index of logical word x is x + x/S for even S
     const int PWn = ((len_a + 31) >> 5) + T + 1;
+    // stage the plane words that cover seg_b = line bits [b_bit, b_bit + len_b) with bulk TMA copies (16-byte granules)
+    const int64_t w_first = (b_bit >> 5) & ~(int64_t)3;
+    int n_raw = (int)((((b_bit + len_b + 31) >> 5) + 1 - w_first + 3) & ~(int64_t)3);
+    n_raw = (int)min((int64_t)n_raw, B.nwords - w_first);
+#ifdef PB_NO_TMA
+    const bool staged = false;
+#else
+    const bool staged = n_raw > 0 && n_raw <= RW;
+#endif
+    if (staged) {
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic reads of `raw` before the async writes
+            const uint32_t bytes = (uint32_t)n_raw * 4u;
+            mbar_expect_tx(bar, bytes * (IRR ? 3u : 2u));
+            tma_load_1d(raw, B.hi + w_first, bytes, bar);
+            tma_load_1d(raw + RW, B.lo + w_first, bytes, bar);
+            if (IRR) tma_load_1d(raw + 2 * RW, B.irr + w_first, bytes, bar);
+        }
+        int spins = 0;
+        while (!mbar_try_wait(bar, phase)) {
+            if (++spins > (1 << 22)) __trap(); // a copy that never lands must not hang the GPU
+        }
+        phase ^= 1u;
+    }
+    // 32 bits of a staged plane starting at line bit g (only called for words with at least one valid bit)
+    auto staged_window = [&](const uint32_t *pl, int64_t g) -> uint32_t {
+        const int64_t wi = (g >> 5) - w_first;
+        const unsigned sh = (unsigned)(g & 31);
+        const uint32_t w0 = (wi >= 0 && wi < n_raw) ? pl[wi] : 0u;
+        const uint32_t w1 = (wi + 1 >= 0 && wi + 1 < n_raw) ? pl[wi + 1] : 0u;
+        return __funnelshift_r(w0, w1, sh);
+    };
     for (int x = lane; x < PWn; x += 32) {
         const int bidx0 = 32 * x - D - PB_PLANE_PADBIT; // b index of bit 0 of this word
         uint32_t valid;
@@ -399,9 +461,15 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
         }
         uint32_t hi = 0u, lo = 0u;
         if (valid) {
-            hi = load_window(B.hi, B.nwords, b_bit + bidx0);
-            lo = load_window(B.lo, B.nwords, b_bit + bidx0);
-            if (IRR) valid &= ~load_window(B.irr, B.nwords, b_bit + bidx0); // a non-ACGT byte equals none of A,C,G,T
+            if (staged) {
+                hi = staged_window(raw, b_bit + bidx0);
+                lo = staged_window(raw + RW, b_bit + bidx0);
+                if (IRR) valid &= ~staged_window(raw + 2 * RW, b_bit + bidx0); // a non-ACGT byte equals none of A,C,G,T
+            } else { // window larger than the staging area (cannot happen for host-planned launches): plain loads
+                hi = load_window(B.hi, B.nwords, b_bit + bidx0);
+                lo = load_window(B.lo, B.nwords, b_bit + bidx0);
+                if (IRR) valid &= ~load_window(B.irr, B.nwords, b_bit + bidx0);
+            }
         }
         const int px = PAD ? x + x / S : x;
         planes[0 * PW + px] = ~hi & ~lo & valid;
@@ -635,6 +703,8 @@ struct AlignLaunch {
     double R;
     int maxn, maxm;
     int PW;              // plane stride (words) for this launch
+    int RW;              // staging stride (words) per raw plane
+    int warp_words;      // shared-memory words per warp (planes + staging)
     size_t slot_words;   // scratch words per warp slot
     size_t par_words;    // of which parent planes
     uint32_t *scratch;
@@ -655,9 +725,16 @@ __global__ void __launch_bounds__(ALIGN_WPB * 32, MinBlocks<S>::v)
 align_locate_kernel(AlignLaunch p, LocateView lv, const uint8_t *__restrict__ survive, const int32_t *__restrict__ rej_cells,
                     pb_locate_rec *__restrict__ recs)
 {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ __align__(8) uint64_t bars[ALIGN_WPB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *planes = smem + (size_t)warp * (IRR ? 8 : 4) * p.PW;
+    // per warp: Eq planes, then the TMA staging area for seg_b's raw plane words
+    uint32_t *planes = smem + (size_t)warp * p.warp_words;
+    uint32_t *raw = planes + (size_t)(IRR ? 8 : 4) * p.PW;
+    uint64_t *bar = &bars[warp];
+    uint32_t phase = 0u;
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
     const size_t slot = (size_t)blockIdx.x * ALIGN_WPB + warp;
     uint32_t *par = p.scratch + slot * p.slot_words;
     uint8_t *opsrev = reinterpret_cast<uint8_t *>(par + p.par_words);
@@ -692,7 +769,7 @@ align_locate_kernel(AlignLaunch p, LocateView lv, const uint8_t *__restrict__ su
                 CandView cv;
                 derive_views(*reinterpret_cast<const PairViews *>(&p.A), lv, k, r, rlen, rbase, q, pos, IRR, cv);
                 align_one<S, IRR>(*cv.a, cv.a_bit, cv.a_len, cv.a_tab, *cv.b, cv.b_bit, cv.b_len, p.R, p.maxn, p.maxm, planes,
-                             p.PW, par, opsrev, p.ops ? p.ops + p.ops_off[k] : nullptr, p.c31, p.c2, res);
+                             p.PW, par, opsrev, p.ops ? p.ops + p.ops_off[k] : nullptr, p.c31, p.c2, raw, p.RW, bar, phase, res);
                 cells += res.cells;
                 if (lane == 0 && p.stats) { atomicAdd(p.stats, (unsigned long long)res.cells); atomicAdd(p.stats + 1, 1ull); }
                 done = f + 1;
@@ -726,9 +803,16 @@ template <int S, bool IRR>
 __global__ void __launch_bounds__(ALIGN_WPB * 32, MinBlocks<S>::v)
 align_pairs_kernel(AlignLaunch p, pb_align_out *__restrict__ out)
 {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ __align__(8) uint64_t bars[ALIGN_WPB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *planes = smem + (size_t)warp * (IRR ? 8 : 4) * p.PW;
+    // per warp: Eq planes, then the TMA staging area for seg_b's raw plane words
+    uint32_t *planes = smem + (size_t)warp * p.warp_words;
+    uint32_t *raw = planes + (size_t)(IRR ? 8 : 4) * p.PW;
+    uint64_t *bar = &bars[warp];
+    uint32_t phase = 0u;
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
     const size_t slot = (size_t)blockIdx.x * ALIGN_WPB + warp;
     uint32_t *par = p.scratch + slot * p.slot_words;
     uint8_t *opsrev = reinterpret_cast<uint8_t *>(par + p.par_words);
@@ -740,7 +824,7 @@ align_pairs_kernel(AlignLaunch p, pb_align_out *__restrict__ out)
         const int k = p.order[idx];
         AlnRes res;
         align_one<S, IRR>(p.A, p.A.base[k], p.A.len[k], IRR ? p.A.tab[k] : 0u, p.B, p.B.base[k], p.B.len[k], p.R, p.maxn, p.maxm, planes, p.PW, par, opsrev,
-                     p.ops ? p.ops + p.ops_off[k] : nullptr, p.c31, p.c2, res);
+                     p.ops ? p.ops + p.ops_off[k] : nullptr, p.c31, p.c2, raw, p.RW, bar, phase, res);
         if (lane == 0 && p.stats) { atomicAdd(p.stats, (unsigned long long)res.cells); atomicAdd(p.stats + 1, 1ull); }
         if (lane == 0) {
             pb_align_out o;
@@ -807,7 +891,7 @@ static const void *kernel_ptr(int key, bool locate)
 }
 
 struct LaunchGeom {
-    int PW;
+    int PW, RW, warp_words;
     size_t smem_bytes, slot_words, par_words;
     int blocks;     // CTAs to launch
     int max_blocks; // min(full occupancy, one warp per item)
@@ -818,7 +902,10 @@ static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, bool locate, s
     const int S = key_S(key), T = 32 * S;
     const int logical = ((cp.max_rows + 31) >> 5) + T + 2;
     g->PW = logical + ((S % 2) == 0 ? logical / S + 2 : 0); // even S: one pad word per S words (bank conflicts)
-    g->smem_bytes = (size_t)ALIGN_WPB * (key_irr(key) ? 8 : 4) * g->PW * sizeof(uint32_t);
+    g->PW = (g->PW + 3) & ~3; // 16-byte aligned sub-arrays (TMA destination)
+    g->RW = (((cp.max_rows + cp.max_D + 31) >> 5) + 12 + 3) & ~3; // seg_b is at most len_a + max_dst long (seq_aligner.h:97)
+    g->warp_words = (key_irr(key) ? 8 : 4) * g->PW + (key_irr(key) ? 3 : 2) * g->RW;
+    g->smem_bytes = (size_t)ALIGN_WPB * g->warp_words * sizeof(uint32_t);
     g->par_words = (size_t)std::max(cp.max_rows, 1) * 2 * T;
     const size_t ops_bytes = ((size_t)2 * cp.max_rows + cp.max_D + 64 + 127) & ~(size_t)127; // keeps every slot 128 B aligned
     g->slot_words = g->par_words + ops_bytes / 4;
@@ -953,6 +1040,8 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
         const LaunchGeom &g = geoms[cls];
         AlignLaunch p = base;
         p.PW = g.PW;
+        p.RW = g.RW;
+        p.warp_words = g.warp_words;
         p.slot_words = g.slot_words;
         p.par_words = g.par_words;
         p.scratch = reinterpret_cast<uint32_t *>(ctx->scratch) + soff;
