@@ -465,7 +465,7 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
                 hi = staged_window(raw, b_bit + bidx0);
                 lo = staged_window(raw + RW, b_bit + bidx0);
                 if (IRR) valid &= ~staged_window(raw + 2 * RW, b_bit + bidx0); // a non-ACGT byte equals none of A,C,G,T
-            } else { // window larger than the staging area (cannot happen for host-planned launches): plain loads
+            } else { // window larger than the staging area (reads beyond ~16 kbp): plain loads
                 hi = load_window(B.hi, B.nwords, b_bit + bidx0);
                 lo = load_window(B.lo, B.nwords, b_bit + bidx0);
                 if (IRR) valid &= ~load_window(B.irr, B.nwords, b_bit + bidx0);
@@ -903,7 +903,9 @@ static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, bool locate, s
     const int logical = ((cp.max_rows + 31) >> 5) + T + 2;
     g->PW = logical + ((S % 2) == 0 ? logical / S + 2 : 0); // even S: one pad word per S words (bank conflicts)
     g->PW = (g->PW + 3) & ~3; // 16-byte aligned sub-arrays (TMA destination)
-    g->RW = (((cp.max_rows + cp.max_D + 31) >> 5) + 12 + 3) & ~3; // seg_b is at most len_a + max_dst long (seq_aligner.h:97)
+    // seg_b is at most len_a + max_dst long (seq_aligner.h:97); windows beyond 512 words (16 kbp) are read with plain loads
+    // instead, so that the staging area never costs the wide-band classes a resident CTA
+    g->RW = std::min(512, (((cp.max_rows + cp.max_D + 31) >> 5) + 12 + 3) & ~3);
     g->warp_words = (key_irr(key) ? 8 : 4) * g->PW + (key_irr(key) ? 3 : 2) * g->RW;
     g->smem_bytes = (size_t)ALIGN_WPB * g->warp_words * sizeof(uint32_t);
     g->par_words = (size_t)std::max(cp.max_rows, 1) * 2 * T;
