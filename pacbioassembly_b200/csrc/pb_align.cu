@@ -169,7 +169,7 @@ __device__ __forceinline__ long long cells_upto(int n, int D, int len_b)
 // ---------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256)
-prefilter_kernel(PairViews pv, LocateView lv, int64_t ncand, double R, int maxn, int maxm,
+prefilter_kernel(const __grid_constant__ PairViews pv, const __grid_constant__ LocateView lv, int64_t ncand, double R, int maxn, int maxm,
                  uint8_t *__restrict__ survive, int32_t *__restrict__ rej_cells)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -722,7 +722,8 @@ template <int S> struct MinBlocks { static constexpr int v = (S <= 3 ? PB_MINB3 
 
 template <int S, bool IRR>
 __global__ void __launch_bounds__(ALIGN_WPB * 32, MinBlocks<S>::v)
-align_locate_kernel(AlignLaunch p, LocateView lv, const uint8_t *__restrict__ survive, const int32_t *__restrict__ rej_cells,
+align_locate_kernel(const __grid_constant__ AlignLaunch p, const __grid_constant__ LocateView lv, const uint8_t *__restrict__ survive,
+                    const int32_t *__restrict__ rej_cells,
                     pb_locate_rec *__restrict__ recs)
 {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -801,7 +802,7 @@ align_locate_kernel(AlignLaunch p, LocateView lv, const uint8_t *__restrict__ su
 
 template <int S, bool IRR>
 __global__ void __launch_bounds__(ALIGN_WPB * 32, MinBlocks<S>::v)
-align_pairs_kernel(AlignLaunch p, pb_align_out *__restrict__ out)
+align_pairs_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *__restrict__ out)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ __align__(8) uint64_t bars[ALIGN_WPB];
