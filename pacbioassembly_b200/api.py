@@ -105,7 +105,12 @@ def lib() -> C.CDLL:
         "pb_overlap_batch": (C.c_int, [vp, vp, vp, i64, vp, P(OverlapParams), vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
-        fn = getattr(L, name)
+        try:
+            fn = getattr(L, name)
+        except AttributeError:
+            if os.environ.get("PB_LIB"):
+                continue  # an older experiment build may lack newer entry points
+            raise
         fn.restype = res
         fn.argtypes = args
     L._declared = sorted(sig)

@@ -12,6 +12,7 @@
 //
 // Per cell the kernel touches 2 bits of HBM (the two parent planes, written once, coalesced 128 B per
 // store instruction) -- versus 8 bytes in the reference.  No tensor cores: this is integer/bit work.
+#include <limits.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -20,6 +21,7 @@
 #include "pb_internal.cuh"
 
 #define FULL 0xffffffffu
+#define PB_STAGE_WORDS 128 // staging buffer per plane (words): 4 kbp of seg_b per TMA chunk
 #ifndef PB_SHIFT_FMA
 #define PB_PLANE_PADBIT 0
 #else
@@ -418,59 +420,55 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
     // ---- Eq planes of seg_b in shared memory: plane c, bit t <-> (b[t - D] == c), zero outside [0,len_b)
     constexpr bool PAD = (S % 2) == 0; // see row_step: physical index of logical word x is x + x/S for even S
     const int PWn = ((len_a + 31) >> 5) + T + 1;
-    // stage the plane words that cover seg_b = line bits [b_bit, b_bit + len_b) with bulk TMA copies (16-byte granules)
-    const int64_t w_first = (b_bit >> 5) & ~(int64_t)3;
-    int n_raw = (int)((((b_bit + len_b + 31) >> 5) + 1 - w_first + 3) & ~(int64_t)3);
-    n_raw = (int)min((int64_t)n_raw, B.nwords - w_first);
-#ifdef PB_NO_TMA
-    const bool staged = false;
-#else
-    const bool staged = n_raw > 0 && n_raw <= RW;
-#endif
-    if (staged) {
+    // The plane words that cover seg_b = line bits [b_bit, b_bit + len_b) come in through a small staging buffer filled by
+    // bulk TMA copies (16-byte granules), PB_STAGE_WORDS words of each plane at a time; consecutive chunks overlap by four
+    // words because a 32-bit window straddles two words.
+    const int64_t g0 = b_bit - D - PB_PLANE_PADBIT;             // line bit of bit 0 of plane word 0 (may be negative)
+    const int64_t w_first = max((int64_t)0, g0 >> 5) & ~(int64_t)3; // first staged line word
+    const int64_t w_end = min(B.nwords, (((b_bit + len_b + 31) >> 5) + 1 + 3) & ~(int64_t)3);
+    const int k0 = (int)((g0 >> 5) - w_first);                   // raw word index (relative to w_first) under plane word 0
+    for (int64_t cw = w_first; cw < w_end; cw += PB_STAGE_WORDS - 4) {
+        const int n_raw = (int)min((int64_t)PB_STAGE_WORDS, w_end - cw);
+        __syncwarp();
         if (lane == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic reads of `raw` before the async writes
             const uint32_t bytes = (uint32_t)n_raw * 4u;
             mbar_expect_tx(bar, bytes * (IRR ? 3u : 2u));
-            tma_load_1d(raw, B.hi + w_first, bytes, bar);
-            tma_load_1d(raw + RW, B.lo + w_first, bytes, bar);
-            if (IRR) tma_load_1d(raw + 2 * RW, B.irr + w_first, bytes, bar);
+            tma_load_1d(raw, B.hi + cw, bytes, bar);
+            tma_load_1d(raw + RW, B.lo + cw, bytes, bar);
+            if (IRR) tma_load_1d(raw + 2 * RW, B.irr + cw, bytes, bar);
         }
         int spins = 0;
         while (!mbar_try_wait(bar, phase)) {
             if (++spins > (1 << 22)) __trap(); // a copy that never lands must not hang the GPU
         }
         phase ^= 1u;
-    }
-    // 32 bits of a staged plane starting at line bit g (only called for words with at least one valid bit)
-    auto staged_window = [&](const uint32_t *pl, int64_t g) -> uint32_t {
-        const int64_t wi = (g >> 5) - w_first;
-        const unsigned sh = (unsigned)(g & 31);
-        const uint32_t w0 = (wi >= 0 && wi < n_raw) ? pl[wi] : 0u;
-        const uint32_t w1 = (wi + 1 >= 0 && wi + 1 < n_raw) ? pl[wi + 1] : 0u;
-        return __funnelshift_r(w0, w1, sh);
-    };
-    for (int x = lane; x < PWn; x += 32) {
-        const int bidx0 = 32 * x - D - PB_PLANE_PADBIT; // b index of bit 0 of this word
-        uint32_t valid;
-        if (bidx0 >= len_b || bidx0 + 31 < 0) valid = 0u;
-        else {
-            valid = 0xffffffffu;
-            if (bidx0 < 0) valid &= 0xffffffffu << (-bidx0);
-            if (bidx0 + 31 >= len_b) valid &= 0xffffffffu >> (bidx0 + 32 - len_b);
-        }
-        uint32_t hi = 0u, lo = 0u;
-        if (valid) {
-            if (staged) {
-                hi = staged_window(raw, b_bit + bidx0);
-                lo = staged_window(raw + RW, b_bit + bidx0);
-                if (IRR) valid &= ~staged_window(raw + 2 * RW, b_bit + bidx0); // a non-ACGT byte equals none of A,C,G,T
-            } else { // window larger than the staging area (reads beyond ~16 kbp): plain loads
-                hi = load_window(B.hi, B.nwords, b_bit + bidx0);
-                lo = load_window(B.lo, B.nwords, b_bit + bidx0);
-                if (IRR) valid &= ~load_window(B.irr, B.nwords, b_bit + bidx0);
+        // plane words whose first raw word lies in this chunk (the last chunk also takes what is left)
+        const int c_lo = (int)(cw - w_first), c_hi = (cw + PB_STAGE_WORDS - 4 >= w_end) ? INT_MAX : c_lo + PB_STAGE_WORDS - 4;
+        const int x_lo = (cw == w_first) ? 0 : max(0, c_lo - k0); // the first chunk also takes the words in front of the line
+        const int x_hi = (c_hi == INT_MAX) ? PWn : min(PWn, max(0, c_hi - k0));
+        for (int x = x_lo + lane; x < x_hi; x += 32) {
+            const int bidx0 = 32 * x - D - PB_PLANE_PADBIT; // b index of bit 0 of this word
+            uint32_t valid;
+            if (bidx0 >= len_b || bidx0 + 31 < 0) valid = 0u;
+            else {
+                valid = 0xffffffffu;
+                if (bidx0 < 0) valid &= 0xffffffffu << (-bidx0);
+                if (bidx0 + 31 >= len_b) valid &= 0xffffffffu >> (bidx0 + 32 - len_b);
             }
-        }
+            uint32_t hi = 0u, lo = 0u;
+            if (valid) {
+                const int wi = x + k0 - c_lo; // index into the staged chunk
+                const unsigned sh = (unsigned)(g0 & 31);
+                auto win = [&](const uint32_t *pl) -> uint32_t {
+                    const uint32_t w0 = (wi >= 0 && wi < n_raw) ? pl[wi] : 0u;
+                    const uint32_t w1 = (wi + 1 >= 0 && wi + 1 < n_raw) ? pl[wi + 1] : 0u;
+                    return __funnelshift_r(w0, w1, sh);
+                };
+                hi = win(raw);
+                lo = win(raw + RW);
+                if (IRR) valid &= ~win(raw + 2 * RW); // a non-ACGT byte equals none of A,C,G,T
+            }
         const int px = PAD ? x + x / S : x;
         planes[0 * PW + px] = ~hi & ~lo & valid;
         planes[1 * PW + px] = ~hi & lo & valid;
@@ -478,6 +476,7 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
         planes[3 * PW + px] = hi & lo & valid;
         if (IRR) {
             planes[4 * PW + px] = 0u; planes[5 * PW + px] = 0u; planes[6 * PW + px] = 0u; planes[7 * PW + px] = 0u;
+        }
         }
     }
     if (IRR) { // planes 4..7: seg_b equals the k-th non-ACGT byte value of seg_a's sequence (raw compare, seq_aligner.h:136)
@@ -904,9 +903,7 @@ static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, bool locate, s
     const int logical = ((cp.max_rows + 31) >> 5) + T + 2;
     g->PW = logical + ((S % 2) == 0 ? logical / S + 2 : 0); // even S: one pad word per S words (bank conflicts)
     g->PW = (g->PW + 3) & ~3; // 16-byte aligned sub-arrays (TMA destination)
-    // seg_b is at most len_a + max_dst long (seq_aligner.h:97); windows beyond 512 words (16 kbp) are read with plain loads
-    // instead, so that the staging area never costs the wide-band classes a resident CTA
-    g->RW = std::min(512, (((cp.max_rows + cp.max_D + 31) >> 5) + 12 + 3) & ~3);
+    g->RW = PB_STAGE_WORDS; // TMA staging buffer per raw plane
     g->warp_words = (key_irr(key) ? 8 : 4) * g->PW + (key_irr(key) ? 3 : 2) * g->RW;
     g->smem_bytes = (size_t)ALIGN_WPB * g->warp_words * sizeof(uint32_t);
     g->par_words = (size_t)std::max(cp.max_rows, 1) * 2 * T;
