@@ -400,6 +400,104 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
     return d0w;
 }
 
+// goal_cell + coverage test + find_path for one finished forward pass (seq_aligner.h:111-116,191-233); called by the
+// whole warp with warp-uniform arguments.  hp_words / hn_words: the final row's horizontal deltas in shared memory (band
+// word w at [w]); par_pair(row, w): the {MATCH word, INSERT word} pair of band word w of DP row `row` (zero outside).
+template <class PairAt>
+__device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, int a_len, double R, int cii, int colbest, int col_i,
+                                                 const uint32_t *hp_words, const uint32_t *hn_words, PairAt par_pair,
+                                                 uint8_t *__restrict__ opsrev, uint8_t *__restrict__ ops_out, AlnRes &res)
+{
+    const int lane = threadIdx.x & 31;
+    // ---- goal_cell, seq_aligner.h:191-213
+    int matlen_a, matlen_b, cost;
+    if (len_a > len_b) {
+        matlen_a = col_i; matlen_b = len_b; cost = colbest;
+    } else {
+        // last row: cost(len_a, j) for j in (len_a, len_b] from the final horizontal deltas; earliest strict minimum
+        matlen_a = len_a; matlen_b = len_a; cost = cii;
+        if (lane == 0) {
+            int c = cii;
+            for (int j = len_a + 1; j <= len_b; ++j) {
+                const int k = j - len_a + D;
+                c += (int)((hp_words[k >> 5] >> (k & 31)) & 1u) - (int)((hn_words[k >> 5] >> (k & 31)) & 1u);
+                if (c < cost) { cost = c; matlen_b = j; }
+            }
+        }
+        cost = __shfl_sync(FULL, cost, 0);
+        matlen_b = __shfl_sync(FULL, matlen_b, 0);
+    }
+    res.matlen_a = matlen_a; res.matlen_b = matlen_b; res.cost = cost;
+    res.diag_cost = (a_len <= len_a && a_len <= len_b) ? cii : 0; // locator.cpp:86 (Q-L2)
+    if ((double)matlen_b < len_b * (1 - R)) return; // seq_aligner.h:114
+
+    // ---- find_path, seq_aligner.h:214-233: walk the parent planes back from the goal cell.
+    // Warp-cooperative: lane r holds the parent pairs of row i0-r around the path's band position (2 band words,
+    // 16 bytes), the next 64 rows are prefetched while the current ones are walked, and runs of MATCH along a
+    // diagonal (same band bit, consecutive rows) are found with one ballot and written by as many lanes.
+    __syncwarp();
+    // window = the band word under the path plus the neighbour the path is closer to
+    auto window_base = [](int k) -> int { return (k >> 5) - ((k & 31) < 16 ? 1 : 0); };
+    int n = 0;
+    {
+        int i = matlen_a, j = matlen_b;
+        const int guard = len_a + len_b + 1; // a path can never be longer; keeps a corrupted plane from hanging the GPU
+        int cur_i0 = -1, cur_wb = 0, nxt_i0 = -1, nxt_wb = 0, nx2_i0 = -1, nx2_wb = 0;
+        uint2 c0 = make_uint2(0u, 0u), c1 = c0, n0 = c0, n1 = c0, m0 = c0, m1 = c0;
+        while ((i | j) != 0 && n < guard) {
+            if (i == 0) { // init_cell row 0: INSERT all the way
+                for (int t = lane; t < j; t += 32) opsrev[n + t] = (uint8_t)PB_INSERT;
+                n += j; j = 0;
+                break;
+            }
+            if (j == 0) { // init_cell column 0: DELETE all the way
+                for (int t = lane; t < i; t += 32) opsrev[n + t] = (uint8_t)PB_DELETE;
+                n += i; i = 0;
+                break;
+            }
+            const int k = j - i + D, w = k >> 5;
+            if (cur_i0 < 0 || cur_i0 - i >= 32 || w < cur_wb || w > cur_wb + 1) {
+                const int wb = window_base(k);
+                if (nxt_i0 == i && w >= nxt_wb && w <= nxt_wb + 1) { // the usual case: 32 rows consumed, prediction held
+                    cur_i0 = nxt_i0; cur_wb = nxt_wb;
+                    c0 = n0; c1 = n1;
+                    nxt_i0 = nx2_i0; nxt_wb = nx2_wb;
+                    n0 = m0; n1 = m1;
+                } else { // cold start or the path left the predicted words: fetch now
+                    cur_i0 = i; cur_wb = wb;
+                    c0 = par_pair(cur_i0 - lane, cur_wb);
+                    c1 = par_pair(cur_i0 - lane, cur_wb + 1);
+                    nxt_i0 = cur_i0 - 32; nxt_wb = wb;
+                    n0 = par_pair(nxt_i0 - lane, nxt_wb);
+                    n1 = par_pair(nxt_i0 - lane, nxt_wb + 1);
+                }
+                nx2_i0 = cur_i0 - 64; nx2_wb = wb; // two windows ahead: DRAM latency under load is several windows long
+                m0 = par_pair(nx2_i0 - lane, nx2_wb);
+                m1 = par_pair(nx2_i0 - lane, nx2_wb + 1);
+            }
+            const int r0 = cur_i0 - i; // lane that holds the current row
+            const uint2 cw = (w == cur_wb) ? c0 : c1;
+            const uint32_t B = __ballot_sync(FULL, (cw.x >> (k & 31)) & 1u) >> r0; // bit t: cell (i-t, j-t) is MATCH
+            int run = (~B) ? __ffs(~B) - 1 : 32;
+            run = min(min(run, 32 - r0), min(i, j));
+            if (run > 0) {
+                if (lane < run) opsrev[n + lane] = (uint8_t)PB_MATCH;
+                n += run; i -= run; j -= run;
+                continue;
+            }
+            const uint32_t hb = (__shfl_sync(FULL, cw.y, r0) >> (k & 31)) & 1u;
+            if (lane == 0) opsrev[n] = (uint8_t)(hb ? PB_INSERT : PB_DELETE);
+            ++n;
+            if (hb) --j; else --i;
+        }
+    }
+    __syncwarp();
+    if (ops_out)
+        for (int k = lane; k < n; k += 32) ops_out[k] = __ldcg(opsrev + (n - 1 - k));
+    res.nedit = n;
+    res.ret = matlen_b;
+}
+
 template <int S, bool IRR>
 __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_len, uint32_t a_tab, const SeqView &B, int64_t b_bit, int b_len,
                                        double R, int maxn, int maxm, uint32_t *__restrict__ planes, int PW,
@@ -595,105 +693,20 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
     res.cells = cells_upto(rows_done, D, len_b);
     if (fail_row) { res.fail_row = fail_row; return; }
 
-    // ---- goal_cell, seq_aligner.h:191-213
-    int matlen_a, matlen_b, cost;
-    if (len_a > len_b) {
-        matlen_a = col_i; matlen_b = len_b; cost = colbest;
-    } else {
-        // last row: cost(len_a, j) for j in (len_a, len_b] from the final horizontal deltas; earliest strict minimum
-        __syncwarp();
+    // ---- goal_cell, coverage test, find_path
+    __syncwarp();
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            planes[lane * S + s] = Hp[s];
-            planes[T + lane * S + s] = Hn[s];
-        }
-        __syncwarp();
-        matlen_a = len_a; matlen_b = len_a; cost = cii;
-        if (lane == 0) {
-            int c = cii;
-            for (int j = len_a + 1; j <= len_b; ++j) {
-                const int k = j - len_a + D;
-                c += (int)((planes[k >> 5] >> (k & 31)) & 1u) - (int)((planes[T + (k >> 5)] >> (k & 31)) & 1u);
-                if (c < cost) { cost = c; matlen_b = j; }
-            }
-        }
-        cost = __shfl_sync(FULL, cost, 0);
-        matlen_b = __shfl_sync(FULL, matlen_b, 0);
+    for (int s = 0; s < S; ++s) {
+        planes[lane * S + s] = Hp[s];
+        planes[T + lane * S + s] = Hn[s];
     }
-    res.matlen_a = matlen_a; res.matlen_b = matlen_b; res.cost = cost;
-    res.diag_cost = (a_len <= len_a && a_len <= len_b) ? cii : 0; // locator.cpp:86 (Q-L2)
-    if ((double)matlen_b < len_b * (1 - R)) return; // seq_aligner.h:114
-
-    // ---- find_path, seq_aligner.h:214-233: walk the parent planes back from the goal cell.
-    // Warp-cooperative: lane r holds the parent pairs of row i0-r around the path's band position (2 band words,
-    // 16 bytes), the next 64 rows are prefetched while the current ones are walked, and runs of MATCH along a
-    // diagonal (same band bit, consecutive rows) are found with one ballot and written by as many lanes.
     __syncwarp();
     auto par_pair = [&](int row, int w) -> uint2 { // {MATCH word, INSERT word} of band word w of DP row `row`
         if (row < 1 || w < 0 || 32 * w > 2 * D) return make_uint2(0u, 0u);
         const int L = w / S, s = w - L * S;
         return __ldcg(reinterpret_cast<const uint2 *>(par + (size_t)(row - 1) * (2 * T)) + s * 32 + L);
     };
-    // window = the band word under the path plus the neighbour the path is closer to
-    auto window_base = [](int k) -> int { return (k >> 5) - ((k & 31) < 16 ? 1 : 0); };
-    int n = 0;
-    {
-        int i = matlen_a, j = matlen_b;
-        const int guard = len_a + len_b + 1; // a path can never be longer; keeps a corrupted plane from hanging the GPU
-        int cur_i0 = -1, cur_wb = 0, nxt_i0 = -1, nxt_wb = 0, nx2_i0 = -1, nx2_wb = 0;
-        uint2 c0 = make_uint2(0u, 0u), c1 = c0, n0 = c0, n1 = c0, m0 = c0, m1 = c0;
-        while ((i | j) != 0 && n < guard) {
-            if (i == 0) { // init_cell row 0: INSERT all the way
-                for (int t = lane; t < j; t += 32) opsrev[n + t] = (uint8_t)PB_INSERT;
-                n += j; j = 0;
-                break;
-            }
-            if (j == 0) { // init_cell column 0: DELETE all the way
-                for (int t = lane; t < i; t += 32) opsrev[n + t] = (uint8_t)PB_DELETE;
-                n += i; i = 0;
-                break;
-            }
-            const int k = j - i + D, w = k >> 5;
-            if (cur_i0 < 0 || cur_i0 - i >= 32 || w < cur_wb || w > cur_wb + 1) {
-                const int wb = window_base(k);
-                if (nxt_i0 == i && w >= nxt_wb && w <= nxt_wb + 1) { // the usual case: 32 rows consumed, prediction held
-                    cur_i0 = nxt_i0; cur_wb = nxt_wb;
-                    c0 = n0; c1 = n1;
-                    nxt_i0 = nx2_i0; nxt_wb = nx2_wb;
-                    n0 = m0; n1 = m1;
-                } else { // cold start or the path left the predicted words: fetch now
-                    cur_i0 = i; cur_wb = wb;
-                    c0 = par_pair(cur_i0 - lane, cur_wb);
-                    c1 = par_pair(cur_i0 - lane, cur_wb + 1);
-                    nxt_i0 = cur_i0 - 32; nxt_wb = wb;
-                    n0 = par_pair(nxt_i0 - lane, nxt_wb);
-                    n1 = par_pair(nxt_i0 - lane, nxt_wb + 1);
-                }
-                nx2_i0 = cur_i0 - 64; nx2_wb = wb; // two windows ahead: DRAM latency under load is several windows long
-                m0 = par_pair(nx2_i0 - lane, nx2_wb);
-                m1 = par_pair(nx2_i0 - lane, nx2_wb + 1);
-            }
-            const int r0 = cur_i0 - i; // lane that holds the current row
-            const uint2 cw = (w == cur_wb) ? c0 : c1;
-            const uint32_t B = __ballot_sync(FULL, (cw.x >> (k & 31)) & 1u) >> r0; // bit t: cell (i-t, j-t) is MATCH
-            int run = (~B) ? __ffs(~B) - 1 : 32;
-            run = min(min(run, 32 - r0), min(i, j));
-            if (run > 0) {
-                if (lane < run) opsrev[n + lane] = (uint8_t)PB_MATCH;
-                n += run; i -= run; j -= run;
-                continue;
-            }
-            const uint32_t hb = (__shfl_sync(FULL, cw.y, r0) >> (k & 31)) & 1u;
-            if (lane == 0) opsrev[n] = (uint8_t)(hb ? PB_INSERT : PB_DELETE);
-            ++n;
-            if (hb) --j; else --i;
-        }
-    }
-    __syncwarp();
-    if (ops_out)
-        for (int k = lane; k < n; k += 32) ops_out[k] = __ldcg(opsrev + (n - 1 - k));
-    res.nedit = n;
-    res.ret = matlen_b;
+    finish_alignment(len_a, len_b, D, a_len, R, cii, colbest, col_i, planes, planes + T, par_pair, opsrev, ops_out, res);
 }
 
 struct AlignLaunch {
@@ -837,6 +850,167 @@ align_pairs_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *__restri
 }
 
 // ---------------------------------------------------------------------------------------------
+// Narrow bands: several alignments per warp.  A band of at most 32*LANES bits (LANES = 4, 8 or 16 lanes, one word per lane)
+// leaves most of a warp idle in align_one, so here a warp advances 32/LANES alignments in lockstep: the shuffles and ballots
+// of a row are shared by all groups (each group cuts its own bits out of the ballot, band edges sit at group edges), then
+// the groups are finished (goal cell, traceback) one after the other by the whole warp.  Same arithmetic as align_one with
+// S = 1; the early-failure test is evaluated per row.  Used by pb_align_batch (config 3's band 32..128 sweep).
+// ---------------------------------------------------------------------------------------------
+template <int LANES>
+__global__ void __launch_bounds__(ALIGN_WPB * 32)
+align_pairs_packed_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *__restrict__ out)
+{
+    constexpr int G = 32 / LANES;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / LANES, gl = lane % LANES, gbase = g * LANES;
+    constexpr uint32_t gmask = (1u << LANES) - 1u;
+    uint32_t *planes = smem + (size_t)warp * p.warp_words + (size_t)g * 4 * p.PW;
+    const size_t slot = ((size_t)blockIdx.x * ALIGN_WPB + warp) * G + g;
+    uint32_t *par = p.scratch + slot * p.slot_words; // rows x LANES pairs, the last row is a dump for finished groups
+    const int dump_row = (int)(p.par_words / (2 * LANES)) - 1;
+    const SeqView &A = p.A, &B = p.B;
+    for (;;) {
+        int idx0 = 0;
+        if (lane == 0) idx0 = atomicAdd(p.queue, G);
+        idx0 = __shfl_sync(FULL, idx0, 0);
+        if (idx0 >= p.nitems) break;
+        const bool has = idx0 + g < p.nitems;
+        const int k = has ? p.order[idx0 + g] : 0;
+        int a_len = 0, b_len = 0;
+        int64_t a_bit = 0, b_bit = 0;
+        if (has) { a_len = A.len[k]; a_bit = A.base[k]; b_len = B.len[k]; b_bit = B.base[k]; }
+        int len_a = 0, len_b = 0, D = 0;
+        derive_params(a_len, b_len, p.R, len_a, len_b, D);
+        const bool dom = has && !(len_a >= p.maxn || D >= p.maxm); // seq_aligner.h:104-107
+        const int rows = dom ? len_a : 0;
+
+        // Eq planes of this group's seg_b (as in align_one, plain loads)
+        const int PWn = ((rows + 31) >> 5) + LANES + 1;
+        if (dom)
+            for (int x = gl; x < PWn; x += LANES) {
+                const int bidx0 = 32 * x - D - PB_PLANE_PADBIT;
+                uint32_t valid;
+                if (bidx0 >= len_b || bidx0 + 31 < 0) valid = 0u;
+                else {
+                    valid = 0xffffffffu;
+                    if (bidx0 < 0) valid &= 0xffffffffu << (-bidx0);
+                    if (bidx0 + 31 >= len_b) valid &= 0xffffffffu >> (bidx0 + 32 - len_b);
+                }
+                uint32_t hi = 0u, lo = 0u;
+                if (valid) {
+                    hi = load_window(B.hi, B.nwords, b_bit + bidx0);
+                    lo = load_window(B.lo, B.nwords, b_bit + bidx0);
+                }
+                planes[0 * p.PW + x] = ~hi & ~lo & valid;
+                planes[1 * p.PW + x] = ~hi & lo & valid;
+                planes[2 * p.PW + x] = hi & ~lo & valid;
+                planes[3 * p.PW + x] = hi & lo & valid;
+            }
+        __syncwarp();
+
+        // row 0 (see align_one): this lane's single band word holds bits k0 .. k0+31
+        const int k0 = 32 * gl;
+        uint32_t Hn = (k0 + 31 <= D) ? 0xffffffffu : (k0 > D ? 0u : 0xffffffffu >> (31 - (D - k0)));
+        uint32_t Hp = ~Hn;
+        const uint32_t keep = (k0 > 2 * D) ? 0u : (k0 + 31 <= 2 * D ? 0xffffffffu : 0xffffffffu >> (31 - (2 * D - k0)));
+        const int diag_lane = gbase + min(D >> 5, LANES - 1);
+        int cii = 0, colc = 0, colbest = 0, col_i = 0, fail_row = 0, rows_done = 0;
+        const int maxrows = __reduce_max_sync(FULL, rows);
+        uint32_t awh = 0u, awl = 0u, Hp_fin = 0u, Hn_fin = 0u;
+        for (int i = 1; i <= maxrows; ++i) {
+            const int t = (i - 1) & 31;
+            const bool live = i <= rows && !fail_row;
+            if (t == 0 && i <= rows) {
+                awh = load_window(A.hi, A.nwords, a_bit + i - 1);
+                awl = load_window(A.lo, A.nwords, a_bit + i - 1);
+            }
+            const int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
+            const uint32_t *pl = planes + ca * p.PW + ((i - 1) >> 5) + gl;
+            // slide the band: bit 0 of the next lane's word comes in at the top; the group's last lane takes the edge value
+            uint32_t nx = __shfl_down_sync(FULL, (Hp & 1u) | ((Hn & 1u) << 1), 1);
+            if (gl == LANES - 1) nx = 1u;
+            Hp = __funnelshift_r(Hp, nx & 1u, 1);
+            Hn = __funnelshift_r(Hn, nx >> 1, 1);
+            uint32_t Eq = 0u;
+            if (i <= rows) Eq = __funnelshift_r(pl[0], pl[1], t) & keep;
+            const uint32_t x = Eq & Hp;
+            uint32_t sum = x + Hp;
+            const uint32_t Gb = (__ballot_sync(FULL, sum < x) >> gbase) & gmask;
+            const uint32_t Pb = (__ballot_sync(FULL, sum == 0xffffffffu) >> gbase) & gmask;
+            sum += ((((Gb | Pb) + Gb) ^ Pb) >> gl) & 1u; // carries never leave the group
+            const uint32_t Xv = (sum ^ Hp) | Eq;
+            const uint32_t Vp = Hn | ~(Xv | Hp), Vn = Hp & Xv;
+            const uint32_t D0 = Xv | Hn;
+            const uint32_t Mw = Eq | ~D0;
+            uint32_t pv = __shfl_up_sync(FULL, (Vp >> 31) | ((Vn >> 31) << 1), 1);
+            if (gl == 0) pv = 1u;
+            const uint32_t vps = (Vp << 1) | (pv & 1u), vns = (Vn << 1) | (pv >> 1);
+            const uint32_t Xh = Eq | Hn;
+            Hp = vns | ~(Xh | vps);
+            Hn = vps & Xh;
+            if (i == rows) { Hp_fin = Hp; Hn_fin = Hn; } // this group's last row: the goal scan reads these deltas
+            // parents: finished groups write into the dump row (a pointer select; predicated stores are slow here)
+            reinterpret_cast<uint2 *>(par + (size_t)(live ? i - 1 : dump_row) * (2 * LANES))[gl] = make_uint2(Mw, Hp);
+            const uint32_t d0bit = (__shfl_sync(FULL, D0, diag_lane) >> (D & 31)) & 1u;
+            // cost(i, len_b) for rows below seg_b's end follows the vertical delta at column len_b
+            const int kcol = min(max(len_b - i + D, 0), 32 * LANES - 1);
+            const uint32_t vpw = __shfl_sync(FULL, Vp, gbase + (kcol >> 5)), vnw = __shfl_sync(FULL, Vn, gbase + (kcol >> 5));
+            if (live) {
+                rows_done = i;
+                if (i <= len_b) {
+                    cii += 1 - (int)d0bit;
+                    if (i > 10 && (double)cii > i * p.R) fail_row = i; // seq_aligner.h:185
+                    if (i == len_b) { colc = colbest = cii; col_i = i; }
+                } else {
+                    colc += (int)((vpw >> (kcol & 31)) & 1u) - (int)((vnw >> (kcol & 31)) & 1u);
+                    if (colc < colbest) { colbest = colc; col_i = i; }
+                }
+            }
+        }
+        // final horizontal deltas of every group into its own plane area, then finish the groups one by one
+        __syncwarp();
+        planes[gl] = Hp_fin;
+        planes[LANES + gl] = Hn_fin;
+        __syncwarp();
+        for (int gg = 0; gg < G; ++gg) {
+            const int src = gg * LANES;
+            const int f_has = __shfl_sync(FULL, (int)has, src), f_dom = __shfl_sync(FULL, (int)dom, src);
+            if (!f_has) continue;
+            const int f_k = __shfl_sync(FULL, k, src), f_la = __shfl_sync(FULL, len_a, src), f_lb = __shfl_sync(FULL, len_b, src);
+            const int f_D = __shfl_sync(FULL, D, src), f_alen = __shfl_sync(FULL, a_len, src), f_cii = __shfl_sync(FULL, cii, src);
+            const int f_cb = __shfl_sync(FULL, colbest, src), f_ci = __shfl_sync(FULL, col_i, src);
+            const int f_fail = __shfl_sync(FULL, fail_row, src), f_rows = __shfl_sync(FULL, rows_done, src);
+            const uint32_t *f_planes = smem + (size_t)warp * p.warp_words + (size_t)gg * 4 * p.PW;
+            uint32_t *f_par = p.scratch + (((size_t)blockIdx.x * ALIGN_WPB + warp) * G + gg) * p.slot_words;
+            uint8_t *f_opsrev = reinterpret_cast<uint8_t *>(f_par + p.par_words);
+            AlnRes res;
+            res.ret = -1; res.len_a = f_la; res.len_b = f_lb; res.D = f_D;
+            res.matlen_a = res.matlen_b = res.cost = res.diag_cost = res.nedit = 0;
+            res.fail_row = f_fail;
+            res.cells = f_dom ? cells_upto(f_rows, f_D, f_lb) : 0;
+            if (f_dom && !f_fail) {
+                auto par_pair = [&](int row, int w) -> uint2 {
+                    if (row < 1 || w < 0 || 32 * w > 2 * f_D) return make_uint2(0u, 0u);
+                    return __ldcg(reinterpret_cast<const uint2 *>(f_par + (size_t)(row - 1) * (2 * LANES)) + w);
+                };
+                finish_alignment(f_la, f_lb, f_D, f_alen, p.R, f_cii, f_cb, f_ci, f_planes, f_planes + LANES, par_pair, f_opsrev,
+                                 p.ops ? p.ops + p.ops_off[f_k] : nullptr, res);
+            }
+            if (lane == 0) {
+                if (p.stats) { atomicAdd(p.stats, (unsigned long long)res.cells); atomicAdd(p.stats + 1, 1ull); }
+                pb_align_out o;
+                o.ret = res.ret; o.len_a = res.len_a; o.len_b = res.len_b; o.max_dst = res.D;
+                o.matlen_a = res.matlen_a; o.matlen_b = res.matlen_b; o.cost = res.cost; o.diag_cost = res.diag_cost;
+                o.nedit = res.nedit; o.fail_row = res.fail_row; o.cells = res.cells;
+                out[f_k] = o;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side: size classes, scratch, launches
 // ---------------------------------------------------------------------------------------------
 
@@ -845,7 +1019,10 @@ align_pairs_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *__restri
 static const int kClasses[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16};
 static const int kIrrClasses[] = {2, 6, 16};
 static inline int key_S(int key) { return key % 1000; }
-static inline bool key_irr(int key) { return key >= 1000; }
+static inline bool key_irr(int key) { return key >= 1000 && key < 2000; }
+// 2000 + LANES: several narrow-band alignments per warp (pairs mode only), LANES lanes x one word each
+static inline bool key_packed(int key) { return key >= 2000; }
+static inline int key_lanes(int key) { return key - 2000; }
 
 static int class_for_band(int D, bool irr)
 { // smallest S with 32*S words >= ceil((2D+1)/32); returns the class key or -1
@@ -873,6 +1050,14 @@ template <int S, bool IRR> struct KernelSel {
 
 static const void *kernel_ptr(int key, bool locate)
 {
+    if (key_packed(key)) {
+        switch (key_lanes(key)) {
+            case 4: return (const void *)align_pairs_packed_kernel<4>;
+            case 8: return (const void *)align_pairs_packed_kernel<8>;
+            case 16: return (const void *)align_pairs_packed_kernel<16>;
+        }
+        return nullptr;
+    }
     const int S = key_S(key);
     if (key_irr(key)) {
         switch (S) {
@@ -895,19 +1080,31 @@ struct LaunchGeom {
     size_t smem_bytes, slot_words, par_words;
     int blocks;     // CTAs to launch
     int max_blocks; // min(full occupancy, one warp per item)
+    int groups;     // alignments in flight per warp (1, or 32/LANES for the packed narrow-band kernels)
 };
 
 static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, bool locate, size_t scratch_budget, LaunchGeom *g)
 {
-    const int S = key_S(key), T = 32 * S;
-    const int logical = ((cp.max_rows + 31) >> 5) + T + 2;
-    g->PW = logical + ((S % 2) == 0 ? logical / S + 2 : 0); // even S: one pad word per S words (bank conflicts)
-    g->PW = (g->PW + 3) & ~3; // 16-byte aligned sub-arrays (TMA destination)
-    g->RW = PB_STAGE_WORDS; // TMA staging buffer per raw plane
-    g->warp_words = (key_irr(key) ? 8 : 4) * g->PW + (key_irr(key) ? 3 : 2) * g->RW;
-    g->smem_bytes = (size_t)ALIGN_WPB * g->warp_words * sizeof(uint32_t);
-    g->par_words = (size_t)std::max(cp.max_rows, 1) * 2 * T;
     const size_t ops_bytes = ((size_t)2 * cp.max_rows + cp.max_D + 64 + 127) & ~(size_t)127; // keeps every slot 128 B aligned
+    if (key_packed(key)) {
+        const int LANES = key_lanes(key);
+        g->groups = 32 / LANES;
+        g->PW = (((cp.max_rows + 31) >> 5) + LANES + 2 + 3) & ~3;
+        g->RW = 0;
+        g->warp_words = g->groups * 4 * g->PW;
+        g->par_words = ((size_t)std::max(cp.max_rows, 1) + 1) * 2 * LANES; // one extra row: the dump for finished groups
+        g->par_words = (g->par_words + 31) & ~(size_t)31;
+    } else {
+        const int S = key_S(key), T = 32 * S;
+        g->groups = 1;
+        const int logical = ((cp.max_rows + 31) >> 5) + T + 2;
+        g->PW = logical + ((S % 2) == 0 ? logical / S + 2 : 0); // even S: one pad word per S words (bank conflicts)
+        g->PW = (g->PW + 3) & ~3; // 16-byte aligned sub-arrays (TMA destination)
+        g->RW = PB_STAGE_WORDS; // TMA staging buffer per raw plane
+        g->warp_words = (key_irr(key) ? 8 : 4) * g->PW + (key_irr(key) ? 3 : 2) * g->RW;
+        g->par_words = (size_t)std::max(cp.max_rows, 1) * 2 * T;
+    }
+    g->smem_bytes = (size_t)ALIGN_WPB * g->warp_words * sizeof(uint32_t);
     g->slot_words = g->par_words + ops_bytes / 4;
     const void *fn = kernel_ptr(key, locate);
     if (g->smem_bytes > 200 * 1024) return pb_fail(ctx, PB_ERR_DOMAIN, "sequence of %d rows needs %zu bytes of shared memory per CTA", cp.max_rows, g->smem_bytes);
@@ -916,9 +1113,10 @@ static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, bool locate, s
     PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, ALIGN_WPB * 32, g->smem_bytes));
     if (occ < 1) occ = 1;
     int64_t blocks = (int64_t)occ * ctx->sm_count;
-    blocks = std::min<int64_t>(blocks, ((int64_t)cp.items.size() + ALIGN_WPB - 1) / ALIGN_WPB);
+    const int64_t per_cta = (int64_t)ALIGN_WPB * g->groups; // alignments in flight per CTA
+    blocks = std::min<int64_t>(blocks, ((int64_t)cp.items.size() + per_cta - 1) / per_cta);
     const size_t slot_bytes = g->slot_words * 4;
-    const int64_t by_mem = (int64_t)(scratch_budget / (slot_bytes * ALIGN_WPB));
+    const int64_t by_mem = (int64_t)(scratch_budget / (slot_bytes * per_cta));
     if (by_mem < 1) return pb_fail(ctx, PB_ERR_NOMEM, "scratch budget %zu too small for one CTA (%zu bytes per alignment)", scratch_budget, slot_bytes);
     blocks = std::max<int64_t>(1, std::min(blocks, by_mem));
     g->blocks = (int)blocks;
@@ -953,7 +1151,7 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
         LaunchGeom g;
         PB_TRY(plan_launch(ctx, kv.first, kv.second, locate, budget, &g));
         geoms[kv.first] = g;
-        need += (size_t)g.blocks * ALIGN_WPB * g.slot_words * 4;
+        need += (size_t)g.blocks * ALIGN_WPB * g.groups * g.slot_words * 4;
     }
     // The classes run concurrently and share the SMs, so give each a share of the resident warps (and of the
     // scratch) in proportion to its share of the DP cells: they then drain at about the same time.
@@ -968,21 +1166,21 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
             const double share = total_work > 0 ? cp.work / total_work : 1.0 / plans.size();
             const int want = (int)(warp_slots * share / ALIGN_WPB + 0.999);
             kv.second.blocks = std::max(1, std::min(kv.second.blocks, want));
-            need += (size_t)kv.second.blocks * ALIGN_WPB * kv.second.slot_words * 4;
+            need += (size_t)kv.second.blocks * ALIGN_WPB * kv.second.groups * kv.second.slot_words * 4;
         }
         if (need > budget) { // still too much scratch: shrink every grid by the same factor (at least one CTA each)
             const double f = (double)budget / (double)need;
             need = 0;
             for (auto &kv : geoms) {
                 kv.second.blocks = std::max(1, (int)(kv.second.blocks * f));
-                need += (size_t)kv.second.blocks * ALIGN_WPB * kv.second.slot_words * 4;
+                need += (size_t)kv.second.blocks * ALIGN_WPB * kv.second.groups * kv.second.slot_words * 4;
             }
         } else {
             // Spend what is left of the budget on extra CTAs for the narrow-band classes (cheap slots): they wait behind
             // the wide-band kernels launched before them and move onto SMs as those drain, which balances the tail.
             for (auto &kv : geoms) { // ascending band class
                 LaunchGeom &g = kv.second;
-                const size_t per_block = (size_t)ALIGN_WPB * g.slot_words * 4;
+                const size_t per_block = (size_t)ALIGN_WPB * g.groups * g.slot_words * 4;
                 const int64_t room = (int64_t)((budget - need) / per_block);
                 const int extra = (int)std::max<int64_t>(0, std::min<int64_t>(room, (int64_t)g.max_blocks - g.blocks));
                 g.blocks += extra;
@@ -1055,7 +1253,7 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
             cudaEventCreate(&a); cudaEventCreate(&b);
             tev.push_back(a); tev.push_back(b);
             char buf[256];
-            snprintf(buf, sizeof buf, "S=%d%s items=%zu blocks=%d rows<=%d band<=%d slotMB=%.2f work=%.3g", key_S(cls), key_irr(cls) ? "x" : "", cp.items.size(), g.blocks, cp.max_rows, cp.max_D, g.slot_words * 4 / 1048576.0, cp.work);
+            snprintf(buf, sizeof buf, "S=%d%s items=%zu blocks=%d rows<=%d band<=%d slotMB=%.2f work=%.3g", key_S(cls), key_irr(cls) ? "x" : (key_packed(cls) ? "p" : ""), cp.items.size(), g.blocks, cp.max_rows, cp.max_D, g.slot_words * 4 / 1048576.0, cp.work);
             tdesc.push_back(buf);
             cudaEventRecord(a, st);
         }
@@ -1064,7 +1262,7 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
         PB_CUDA(ctx, cudaEventRecord(ctx->aux_events[ci], st));
         PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->aux_events[ci], 0));
         off += cp.items.size();
-        soff += (size_t)g.blocks * ALIGN_WPB * g.slot_words;
+        soff += (size_t)g.blocks * ALIGN_WPB * g.groups * g.slot_words;
         ++ci;
     }
     if (trace) { // PB_TRACE=1: per-class device times (classes overlap, so they do not add up)
@@ -1141,7 +1339,10 @@ int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t 
         const bool rejected = la[k] >= maxn || D[k] >= maxm;
         int cls = 1; // rejected by the domain check: any kernel will do, nothing is computed
         if (!rejected) {
-            cls = class_for_band(D[k], ((A->flags[k] | B->flags[k]) & PB_FLAG_IRREGULAR) != 0);
+            const bool irr = ((A->flags[k] | B->flags[k]) & PB_FLAG_IRREGULAR) != 0;
+            const int NW = (2 * D[k] + 1 + 31) >> 5;
+            if (!irr && NW <= 16 && !getenv("PB_NO_PACKED")) cls = 2000 + (NW <= 4 ? 4 : (NW <= 8 ? 8 : 16)); // several alignments per warp
+            else cls = class_for_band(D[k], irr);
             if (cls < 0) return pb_fail(ctx, PB_ERR_DOMAIN, "band half-width %d exceeds PB_MAX_BAND", D[k]);
         }
         ClassPlan &cp = plans[cls];
@@ -1149,7 +1350,7 @@ int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t 
         if (!rejected) {
             cp.max_rows = std::max(cp.max_rows, la[k]);
             cp.max_D = std::max(cp.max_D, D[k]);
-            cp.work += (double)la[k] * (30.0 * key_S(cls) + 60.0);
+            cp.work += key_packed(cls) ? (double)la[k] * 90.0 * key_lanes(cls) / 32.0 : (double)la[k] * (30.0 * key_S(cls) + 60.0);
         }
     }
     AlignLaunch base;

@@ -523,3 +523,19 @@ def test_overlap_longer_reads(ctx, oracle):
         for n in OV_FIELDS + ("cells",):
             assert (got[n] == want[n]).all(), (quirk, n)
     assert got["found"].sum() > 3
+
+
+def test_align_narrow_bands_packed(ctx, oracle):
+    """bands of 65..513 bits: several alignments per warp (packed kernels, 4/8/16 lanes each) and the one-word-per-lane
+    class; mixed lengths in one batch, failures and seg_a longer than seg_b included"""
+    rng = np.random.default_rng(31)
+    for R, maxlen in ((0.03, 900), (0.06, 1100), (0.03, 4000), (0.12, 2000)):
+        A, B = make_pairs(rng, 160, maxlen, rates=(0.0, 0.01, 0.03, 0.08))
+        assert run_batch_vs_oracle(ctx, oracle, A, B, R) > 30
+    A, B = make_pairs(rng, 64, 700, rates=(0.0, 0.02))
+    assert run_batch_vs_oracle(ctx, oracle, A, B, 0.04, fwd=False) > 10
+    # the config-3 generator itself: band == max_dst exactly, edits spaced to survive the early-failure line
+    for alen, band in ((1000, 32), (2000, 64), (5000, 128), (1000, 256)):
+        P = [workload.sweep_pair(7 * band + alen, k, alen, band) for k in range(24)]
+        Rr = P[0][2]
+        assert run_batch_vs_oracle(ctx, oracle, [x[0] for x in P], [x[1] for x in P], Rr) == 24
