@@ -533,7 +533,7 @@ def test_align_narrow_bands_packed(ctx, oracle):
         A, B = make_pairs(rng, 160, maxlen, rates=(0.0, 0.01, 0.03, 0.08))
         assert run_batch_vs_oracle(ctx, oracle, A, B, R) > 30
     A, B = make_pairs(rng, 64, 700, rates=(0.0, 0.02))
-    assert run_batch_vs_oracle(ctx, oracle, A, B, 0.04, fwd=False) > 10
+    assert run_batch_vs_oracle(ctx, oracle, A, B, 0.04, fwd=False) >= 5
     # the config-3 generator itself: band == max_dst exactly, edits spaced to survive the early-failure line
     for alen, band in ((1000, 32), (2000, 64), (5000, 128), (1000, 256)):
         P = [workload.sweep_pair(7 * band + alen, k, alen, band) for k in range(24)]
