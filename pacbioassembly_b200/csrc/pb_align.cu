@@ -717,6 +717,7 @@ struct AlignLaunch {
     int PW;              // plane stride (words) for this launch
     int RW;              // staging stride (words) per raw plane
     int warp_words;      // shared-memory words per warp (planes + staging)
+    int wpb;             // warps per CTA of this launch
     size_t slot_words;   // scratch words per warp slot
     size_t par_words;    // of which parent planes
     uint32_t *scratch;
@@ -866,7 +867,7 @@ align_pairs_packed_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *_
     const int g = lane / LANES, gl = lane % LANES, gbase = g * LANES;
     constexpr uint32_t gmask = (1u << LANES) - 1u;
     uint32_t *planes = smem + (size_t)warp * p.warp_words + (size_t)g * 4 * p.PW;
-    const size_t slot = ((size_t)blockIdx.x * ALIGN_WPB + warp) * G + g;
+    const size_t slot = ((size_t)blockIdx.x * p.wpb + warp) * G + g;
     uint32_t *par = p.scratch + slot * p.slot_words; // rows x LANES pairs, the last row is a dump for finished groups
     const int dump_row = (int)(p.par_words / (2 * LANES)) - 1;
     const SeqView &A = p.A, &B = p.B;
@@ -982,7 +983,7 @@ align_pairs_packed_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *_
             const int f_cb = __shfl_sync(FULL, colbest, src), f_ci = __shfl_sync(FULL, col_i, src);
             const int f_fail = __shfl_sync(FULL, fail_row, src), f_rows = __shfl_sync(FULL, rows_done, src);
             const uint32_t *f_planes = smem + (size_t)warp * p.warp_words + (size_t)gg * 4 * p.PW;
-            uint32_t *f_par = p.scratch + (((size_t)blockIdx.x * ALIGN_WPB + warp) * G + gg) * p.slot_words;
+            uint32_t *f_par = p.scratch + (((size_t)blockIdx.x * p.wpb + warp) * G + gg) * p.slot_words;
             uint8_t *f_opsrev = reinterpret_cast<uint8_t *>(f_par + p.par_words);
             AlnRes res;
             res.ret = -1; res.len_a = f_la; res.len_b = f_lb; res.D = f_D;
@@ -1081,6 +1082,7 @@ struct LaunchGeom {
     int blocks;     // CTAs to launch
     int max_blocks; // min(full occupancy, one warp per item)
     int groups;     // alignments in flight per warp (1, or 32/LANES for the packed narrow-band kernels)
+    int wpb;        // warps per CTA
 };
 
 static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, bool locate, size_t scratch_budget, LaunchGeom *g)
@@ -1104,16 +1106,19 @@ static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, bool locate, s
         g->warp_words = (key_irr(key) ? 8 : 4) * g->PW + (key_irr(key) ? 3 : 2) * g->RW;
         g->par_words = (size_t)std::max(cp.max_rows, 1) * 2 * T;
     }
-    g->smem_bytes = (size_t)ALIGN_WPB * g->warp_words * sizeof(uint32_t);
+    g->wpb = ALIGN_WPB;
+    if (key_packed(key)) // long sequences in narrow bands: fewer warps per CTA keep the per-group planes within shared memory
+        while (g->wpb > 1 && (size_t)g->wpb * g->warp_words * sizeof(uint32_t) > 96 * 1024) g->wpb >>= 1;
+    g->smem_bytes = (size_t)g->wpb * g->warp_words * sizeof(uint32_t);
     g->slot_words = g->par_words + ops_bytes / 4;
     const void *fn = kernel_ptr(key, locate);
     if (g->smem_bytes > 200 * 1024) return pb_fail(ctx, PB_ERR_DOMAIN, "sequence of %d rows needs %zu bytes of shared memory per CTA", cp.max_rows, g->smem_bytes);
     PB_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes));
     int occ = 0;
-    PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, ALIGN_WPB * 32, g->smem_bytes));
+    PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, g->wpb * 32, g->smem_bytes));
     if (occ < 1) occ = 1;
     int64_t blocks = (int64_t)occ * ctx->sm_count;
-    const int64_t per_cta = (int64_t)ALIGN_WPB * g->groups; // alignments in flight per CTA
+    const int64_t per_cta = (int64_t)g->wpb * g->groups; // alignments in flight per CTA
     blocks = std::min<int64_t>(blocks, ((int64_t)cp.items.size() + per_cta - 1) / per_cta);
     const size_t slot_bytes = g->slot_words * 4;
     const int64_t by_mem = (int64_t)(scratch_budget / (slot_bytes * per_cta));
@@ -1151,7 +1156,7 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
         LaunchGeom g;
         PB_TRY(plan_launch(ctx, kv.first, kv.second, locate, budget, &g));
         geoms[kv.first] = g;
-        need += (size_t)g.blocks * ALIGN_WPB * g.groups * g.slot_words * 4;
+        need += (size_t)g.blocks * g.wpb * g.groups * g.slot_words * 4;
     }
     // The classes run concurrently and share the SMs, so give each a share of the resident warps (and of the
     // scratch) in proportion to its share of the DP cells: they then drain at about the same time.
@@ -1164,23 +1169,23 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
         for (auto &kv : geoms) {
             const ClassPlan &cp = plans[kv.first];
             const double share = total_work > 0 ? cp.work / total_work : 1.0 / plans.size();
-            const int want = (int)(warp_slots * share / ALIGN_WPB + 0.999);
+            const int want = (int)(warp_slots * share / kv.second.wpb + 0.999);
             kv.second.blocks = std::max(1, std::min(kv.second.blocks, want));
-            need += (size_t)kv.second.blocks * ALIGN_WPB * kv.second.groups * kv.second.slot_words * 4;
+            need += (size_t)kv.second.blocks * kv.second.wpb * kv.second.groups * kv.second.slot_words * 4;
         }
         if (need > budget) { // still too much scratch: shrink every grid by the same factor (at least one CTA each)
             const double f = (double)budget / (double)need;
             need = 0;
             for (auto &kv : geoms) {
                 kv.second.blocks = std::max(1, (int)(kv.second.blocks * f));
-                need += (size_t)kv.second.blocks * ALIGN_WPB * kv.second.groups * kv.second.slot_words * 4;
+                need += (size_t)kv.second.blocks * kv.second.wpb * kv.second.groups * kv.second.slot_words * 4;
             }
         } else {
             // Spend what is left of the budget on extra CTAs for the narrow-band classes (cheap slots): they wait behind
             // the wide-band kernels launched before them and move onto SMs as those drain, which balances the tail.
             for (auto &kv : geoms) { // ascending band class
                 LaunchGeom &g = kv.second;
-                const size_t per_block = (size_t)ALIGN_WPB * g.groups * g.slot_words * 4;
+                const size_t per_block = (size_t)g.wpb * g.groups * g.slot_words * 4;
                 const int64_t room = (int64_t)((budget - need) / per_block);
                 const int extra = (int)std::max<int64_t>(0, std::min<int64_t>(room, (int64_t)g.max_blocks - g.blocks));
                 g.blocks += extra;
@@ -1240,6 +1245,7 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
         p.PW = g.PW;
         p.RW = g.RW;
         p.warp_words = g.warp_words;
+        p.wpb = g.wpb;
         p.slot_words = g.slot_words;
         p.par_words = g.par_words;
         p.scratch = reinterpret_cast<uint32_t *>(ctx->scratch) + soff;
@@ -1262,7 +1268,7 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate
         PB_CUDA(ctx, cudaEventRecord(ctx->aux_events[ci], st));
         PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->aux_events[ci], 0));
         off += cp.items.size();
-        soff += (size_t)g.blocks * ALIGN_WPB * g.groups * g.slot_words;
+        soff += (size_t)g.blocks * g.wpb * g.groups * g.slot_words;
         ++ci;
     }
     if (trace) { // PB_TRACE=1: per-class device times (classes overlap, so they do not add up)
@@ -1362,7 +1368,7 @@ int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t 
     base.c31 = 0x80000000u; base.c2 = 2u;
     return run_classes(ctx, plans, false, base, [&](int key, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
         void *args[] = {(void *)&p, (void *)&d_out};
-        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(key, false), dim3(g.blocks), dim3(ALIGN_WPB * 32), args, g.smem_bytes, st));
+        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(key, false), dim3(g.blocks), dim3(g.wpb * 32), args, g.smem_bytes, st));
         ctx->launches++;
         return PB_OK;
     });
