@@ -918,6 +918,7 @@ align_pairs_packed_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *_
         const int diag_lane = gbase + min(D >> 5, LANES - 1);
         int cii = 0, colc = 0, colbest = 0, col_i = 0, fail_row = 0, rows_done = 0;
         const int maxrows = __reduce_max_sync(FULL, rows);
+        const int min_lb = __reduce_min_sync(FULL, dom ? len_b : INT_MAX); // first row at which some group follows its last column
         uint32_t awh = 0u, awl = 0u, Hp_fin = 0u, Hn_fin = 0u;
         for (int i = 1; i <= maxrows; ++i) {
             const int t = (i - 1) & 31;
@@ -956,7 +957,11 @@ align_pairs_packed_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *_
             const uint32_t d0bit = (__shfl_sync(FULL, D0, diag_lane) >> (D & 31)) & 1u;
             // cost(i, len_b) for rows below seg_b's end follows the vertical delta at column len_b
             const int kcol = min(max(len_b - i + D, 0), 32 * LANES - 1);
-            const uint32_t vpw = __shfl_sync(FULL, Vp, gbase + (kcol >> 5)), vnw = __shfl_sync(FULL, Vn, gbase + (kcol >> 5));
+            uint32_t vpw = 0u, vnw = 0u;
+            if (i > min_lb) { // warp-uniform: only rows past some group's seg_b pay for these
+                vpw = __shfl_sync(FULL, Vp, gbase + (kcol >> 5));
+                vnw = __shfl_sync(FULL, Vn, gbase + (kcol >> 5));
+            }
             if (live) {
                 rows_done = i;
                 if (i <= len_b) {
