@@ -24,6 +24,9 @@ import numpy as np
 
 # one hardware queue per aligner band-class stream (must be set before CUDA is initialised in this process)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "tests")):
@@ -232,16 +235,17 @@ def main():
     kept = int((lens >= 500).sum())
     recs_host = torch.empty(kept * LOCATE_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True).numpy().view(LOCATE_DTYPE)
 
+    state = {}
     from pacbioassembly_b200 import shard
+
+    reducer = shard.FinalReduction(nreads, device="cuda")
 
     def final_reduction(recs):
         """the path's only collective: hit/score counters all-reduced, records gathered on rank 0"""
-        tot = shard.reduce_counters(recs, device="cuda")
-        if world > 1:
-            shard.gather_records(recs, device="cuda")
+        tot, allrecs = reducer(recs)
+        state["gathered"] = None if allrecs is None else len(allrecs)
         return tot
 
-    state = {}
 
     def step_device():
         s = ctx.seqset_from_device(d_txt.data_ptr(), d_txt.numel(), offs, lens)

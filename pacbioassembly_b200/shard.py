@@ -69,3 +69,62 @@ def gather_records(recs: np.ndarray, device: torch.device | str = "cpu", dst: in
         base += counts[r]
         parts.append(a)
     return np.concatenate(parts) if parts else np.zeros(0, dtype=LOCATE_DTYPE)
+
+
+class FinalReduction:
+    """The path's one exchange, with its buffers allocated once: all-reduce of the four counters and a gather of every
+    rank's 56-byte records on rank 0 (fixed-size slots of `cap` records; the kept count travels in the counters' gather).
+    Works over NCCL (device="cuda") or gloo (device="cpu")."""
+
+    def __init__(self, cap: int, device="cpu", dst: int = 0):
+        self.cap, self.device, self.dst = int(cap), device, dst
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        nbytes = self.cap * LOCATE_DTYPE.itemsize + 8  # 8-byte header: number of valid records
+        cuda = str(device).startswith("cuda")
+        self.h_send = torch.empty(nbytes, dtype=torch.uint8, pin_memory=cuda)
+        self.d_send = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.counters = torch.zeros(4, dtype=torch.int64, device=device)
+        self.h_counters = torch.zeros(4, dtype=torch.int64, pin_memory=cuda)
+        if self.rank == dst and self.world > 1:
+            self.d_recv = [torch.empty(nbytes, dtype=torch.uint8, device=device) for _ in range(self.world)]
+            self.h_recv = torch.empty(self.world * nbytes, dtype=torch.uint8, pin_memory=cuda)
+        else:
+            self.d_recv = None
+
+    def __call__(self, recs: np.ndarray, want_records: bool = True):
+        """returns (summed counters as numpy int64[4], concatenated records on dst or None)"""
+        self.h_counters.numpy()[:] = counters_of(recs)
+        self.counters.copy_(self.h_counters, non_blocking=True)
+        if self.world == 1:
+            if str(self.device).startswith("cuda"):
+                torch.cuda.current_stream().synchronize()
+            return self.h_counters.numpy().copy(), (recs if want_records else None)
+        dist.all_reduce(self.counters)
+        n = len(recs)
+        assert n <= self.cap
+        hs = self.h_send.numpy()
+        hs[:8].view(np.int64)[0] = n
+        hs[8: 8 + n * LOCATE_DTYPE.itemsize] = recs.view(np.uint8).reshape(-1)
+        self.d_send.copy_(self.h_send, non_blocking=True)
+        dist.gather(self.d_send, self.d_recv, dst=self.dst)
+        tot = self.counters.cpu().numpy()
+        if self.rank != self.dst:
+            return tot, None
+        nbytes = self.d_send.numel()
+        for r in range(self.world):
+            self.h_recv[r * nbytes: (r + 1) * nbytes].copy_(self.d_recv[r], non_blocking=True)
+        if str(self.device).startswith("cuda"):
+            torch.cuda.current_stream().synchronize()
+        if not want_records:
+            return tot, None
+        hr = self.h_recv.numpy()
+        parts, base = [], 0
+        for r in range(self.world):
+            blk = hr[r * nbytes: (r + 1) * nbytes]
+            cnt = int(blk[:8].view(np.int64)[0])
+            a = blk[8: 8 + cnt * LOCATE_DTYPE.itemsize].view(LOCATE_DTYPE).copy()
+            a["nseq"] += base  # prefix sum of the kept counts of the earlier shards (SURVEY Q-L1)
+            base += cnt
+            parts.append(a)
+        return tot, np.concatenate(parts)

@@ -38,6 +38,10 @@ def _worker(rank, world, port, q):
             recs[n] = mine[n]
     tot = shard.reduce_counters(recs)
     allrecs = shard.gather_records(recs)
+    tot2, allrecs2 = shard.FinalReduction(len(lens))(recs)  # the buffered variant bench.py uses
+    assert tot2.tolist() == tot.tolist()
+    if rank == 0:
+        assert all((allrecs2[n] == allrecs[n]).all() for n in allrecs.dtype.names)
     if rank == 0:
         whole = o.locate(ix, ref, txt, offs, lens, mask, R=0.3)
         ok = len(allrecs) == len(whole)
