@@ -28,7 +28,7 @@
 #define PB_PLANE_PADBIT 1 // one pad bit in front of the Eq planes: the per-row shift becomes 1..32, i.e. a multiply by 2^31..2^0
 #endif
 #ifndef ALIGN_WPB
-#define ALIGN_WPB 4 // warps (alignments in flight) per CTA
+#define ALIGN_WPB 8 // warps (alignments in flight) per CTA, at most: launches that need more shared memory use fewer
 #endif
 #ifndef PB_MINB3
 #define PB_MINB3 6 // resident CTAs per SM asked of ptxas for the narrow-band classes
@@ -749,7 +749,7 @@ align_locate_kernel(const __grid_constant__ AlignLaunch p, const __grid_constant
     uint32_t phase = 0u;
     if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
-    const size_t slot = (size_t)blockIdx.x * ALIGN_WPB + warp;
+    const size_t slot = (size_t)blockIdx.x * p.wpb + warp;
     uint32_t *par = p.scratch + slot * p.slot_words;
     uint8_t *opsrev = reinterpret_cast<uint8_t *>(par + p.par_words);
     for (;;) {
@@ -827,7 +827,7 @@ align_pairs_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *__restri
     uint32_t phase = 0u;
     if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
-    const size_t slot = (size_t)blockIdx.x * ALIGN_WPB + warp;
+    const size_t slot = (size_t)blockIdx.x * p.wpb + warp;
     uint32_t *par = p.scratch + slot * p.slot_words;
     uint8_t *opsrev = reinterpret_cast<uint8_t *>(par + p.par_words);
     for (;;) {
@@ -1111,9 +1111,11 @@ static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, bool locate, s
         g->warp_words = (key_irr(key) ? 8 : 4) * g->PW + (key_irr(key) ? 3 : 2) * g->RW;
         g->par_words = (size_t)std::max(cp.max_rows, 1) * 2 * T;
     }
+    // fewer warps per CTA when the per-warp planes are large (long sequences): the packed kernels stay under 96 KB so that two
+    // CTAs fit an SM, the others under the 200 KB a CTA may ask for
     g->wpb = ALIGN_WPB;
-    if (key_packed(key)) // long sequences in narrow bands: fewer warps per CTA keep the per-group planes within shared memory
-        while (g->wpb > 1 && (size_t)g->wpb * g->warp_words * sizeof(uint32_t) > 96 * 1024) g->wpb >>= 1;
+    const size_t smem_cap = key_packed(key) ? 96 * 1024 : 200 * 1024;
+    while (g->wpb > 1 && (size_t)g->wpb * g->warp_words * sizeof(uint32_t) > smem_cap) g->wpb >>= 1;
     g->smem_bytes = (size_t)g->wpb * g->warp_words * sizeof(uint32_t);
     g->slot_words = g->par_words + ops_bytes / 4;
     const void *fn = kernel_ptr(key, locate);
@@ -1327,7 +1329,7 @@ int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_
     base.c31 = 0x80000000u; base.c2 = 2u;
     return run_classes(ctx, plans, true, base, [&](int key, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
         void *args[] = {(void *)&p, (void *)&lv, (void *)&d_survive, (void *)&d_rej_cells, (void *)&d_recs};
-        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(key, true), dim3(g.blocks), dim3(ALIGN_WPB * 32), args, g.smem_bytes, st));
+        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(key, true), dim3(g.blocks), dim3(g.wpb * 32), args, g.smem_bytes, st));
         ctx->launches++;
         return PB_OK;
     });
