@@ -1116,8 +1116,9 @@ static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, bool locate, s
     g->wpb = ALIGN_WPB;
     const size_t smem_cap = key_packed(key) ? 96 * 1024 : 200 * 1024;
     while (g->wpb > 1 && (size_t)g->wpb * g->warp_words * sizeof(uint32_t) > smem_cap) g->wpb >>= 1;
-    // few items: spread them over more, smaller CTAs rather than leave SMs without work
-    while (g->wpb > 2 && (int64_t)cp.items.size() < (int64_t)g->wpb * g->groups * ctx->sm_count) g->wpb >>= 1;
+    // packed kernels, few items: spread them over more, smaller CTAs rather than leave SMs without work.  (Not for the
+    // one-alignment-per-warp kernels: measured on config 2, smaller CTAs for the sparse wide-band classes cost 5 %.)
+    while (key_packed(key) && g->wpb > 2 && (int64_t)cp.items.size() < (int64_t)g->wpb * g->groups * ctx->sm_count) g->wpb >>= 1;
     g->smem_bytes = (size_t)g->wpb * g->warp_words * sizeof(uint32_t);
     g->slot_words = g->par_words + ops_bytes / 4;
     const void *fn = kernel_ptr(key, locate);
