@@ -130,6 +130,12 @@ PB_API int pb_seed_extract(pb_ctx *ctx, const pb_seqset *s, int64_t i, uint32_t 
  * through *nkeys and the kernel time in ms through *kernel_ms (either may be NULL). */
 PB_API int pb_seed_extract_all_device(pb_ctx *ctx, const pb_seqset *s, uint32_t mask, int64_t *nkeys, float *kernel_ms);
 
+/* K1 + K2 bulk over every position of `s` as a query against `ix`, everything left on the device (bandwidth measurement of the
+ * probe/gather kernels).  Algorithmic bytes: 4 B key + 8 B bucket header per query (count pass); key + header + 4 B per
+ * position read + 8 B per candidate written (gather pass).  Any output pointer may be NULL. */
+PB_API int pb_probe_bulk_device(pb_ctx *ctx, const pb_index *ix, const pb_seqset *s, int64_t *nqueries, int64_t *ncand,
+                                float *ms_seed, float *ms_count, float *ms_gather);
+
 /* key = encode(ref+i) & mask; if (key) map[key].push_back(i)   (locator.cpp:62-66 / ref_seq.h:291-311) */
 PB_API int pb_index_build(pb_ctx *ctx, const pb_seqset *ref, int64_t seq, uint32_t mask, int policy, pb_index **out);
 PB_API void pb_index_free(pb_index *ix);

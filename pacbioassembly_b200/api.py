@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
         "pb_seqset_packed": (C.c_int, [vp, vp, i64, vp, sz]),
         "pb_seed_extract": (C.c_int, [vp, vp, i64, u32, vp]),
         "pb_seed_extract_all_device": (C.c_int, [vp, vp, u32, P(i64), P(C.c_float)]),
+        "pb_probe_bulk_device": (C.c_int, [vp, vp, vp, P(i64), P(i64), P(C.c_float), P(C.c_float), P(C.c_float)]),
         "pb_index_build": (C.c_int, [vp, vp, i64, u32, C.c_int, P(vp)]),
         "pb_index_free": (None, [vp]),
         "pb_index_nkeys": (i64, [vp]),
@@ -444,6 +445,14 @@ class Index:
     @property
     def mask(self) -> int:
         return int(self.ctx._L.pb_index_mask(self.h))
+
+    def probe_bulk(self, s: "SeqSet") -> dict:
+        """every position of `s` probed against this index on the device (K1 bulk + K2 count/gather); sizes and kernel times"""
+        nq, nc = C.c_int64(0), C.c_int64(0)
+        a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
+        self.ctx.check(self.ctx._L.pb_probe_bulk_device(self.ctx.h, self.h, s.h, C.byref(nq), C.byref(nc), C.byref(a), C.byref(b),
+                                                        C.byref(c)))
+        return {"queries": nq.value, "candidates": nc.value, "seed_ms": a.value, "count_ms": b.value, "gather_ms": c.value}
 
     def find_batch(self, keys) -> list[list[int]]:
         keys = np.ascontiguousarray(keys, dtype=np.uint32).reshape(-1)

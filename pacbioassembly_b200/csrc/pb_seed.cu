@@ -722,6 +722,54 @@ int pb_overlap_seed_probe(pb_ctx *ctx, const pb_index *ix, const pb_seqset *read
     return probe_and_gather(ctx, ix, d_keys.as<uint32_t>(), nq, po);
 }
 
+// Bulk probe (bandwidth measurement): every position of the set is a query -- K1 bulk keys, then probe_count, scan,
+// probe_gather, all on the device.  Reports queries, candidates and the times of the three stages.
+extern "C" int pb_probe_bulk_device(pb_ctx *ctx, const pb_index *ix, const pb_seqset *s, int64_t *nqueries, int64_t *ncand,
+                                    float *ms_seed, float *ms_count, float *ms_gather)
+{
+    if (!ctx || !ix || !s) return pb_fail(ctx, PB_ERR_ARG, "pb_probe_bulk_device: bad argument");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t nq = s->base[s->n];
+    if (nq <= 0) return pb_fail(ctx, PB_ERR_ARG, "empty set");
+    DevBuf d_keys, d_cnt, d_qoff, d_pos, d_q, tmp;
+    PB_TRY(d_keys.alloc(ctx, (size_t)nq * 4 + 64));
+    PB_TRY(d_cnt.alloc(ctx, (size_t)nq * 4));
+    PB_TRY(d_qoff.alloc(ctx, (size_t)(nq + 2) * 8));
+    cudaEvent_t ev[6];
+    for (auto &e : ev) PB_CUDA(ctx, cudaEventCreate(&e));
+    IndexView iv = view_of(ix);
+    const unsigned grid = (unsigned)((nq + 255) / 256);
+    cudaEventRecord(ev[0], ctx->stream);
+    PB_TRY(pb_seed_bulk_device(ctx, s, 0, nq, ix->mask, d_keys.as<uint32_t>()));
+    cudaEventRecord(ev[1], ctx->stream);
+    cudaEventRecord(ev[2], ctx->stream);
+    probe_count_kernel<<<grid, 256, 0, ctx->stream>>>(iv, d_keys.as<uint32_t>(), nq, d_cnt.as<uint32_t>());
+    PB_LAUNCH_CHECK(ctx);
+    cudaEventRecord(ev[3], ctx->stream);
+    PB_TRY(pb_scan_i64(ctx, d_cnt.as<uint32_t>(), d_qoff.as<int64_t>(), nq, tmp));
+    int64_t nc = 0;
+    PB_TRY(pb_d2h(ctx, &nc, d_qoff.as<int64_t>() + nq, 8));
+    PB_TRY(pb_sync(ctx));
+    PB_TRY(d_pos.alloc(ctx, (size_t)std::max<int64_t>(nc, 1) * 4));
+    PB_TRY(d_q.alloc(ctx, (size_t)std::max<int64_t>(nc, 1) * 4));
+    cudaEventRecord(ev[4], ctx->stream);
+    probe_gather_kernel<<<grid, 256, 0, ctx->stream>>>(iv, d_keys.as<uint32_t>(), nq, d_qoff.as<int64_t>(), d_pos.as<int32_t>(), d_q.as<int32_t>());
+    PB_LAUNCH_CHECK(ctx);
+    cudaEventRecord(ev[5], ctx->stream);
+    PB_TRY(pb_sync(ctx));
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, ev[0], ev[1]);
+    cudaEventElapsedTime(&b, ev[2], ev[3]);
+    cudaEventElapsedTime(&c, ev[4], ev[5]);
+    for (auto &e : ev) cudaEventDestroy(e);
+    if (nqueries) *nqueries = nq;
+    if (ncand) *ncand = nc;
+    if (ms_seed) *ms_seed = a;
+    if (ms_count) *ms_count = b;
+    if (ms_gather) *ms_gather = c;
+    return PB_OK;
+}
+
 __global__ void find_write_kernel(IndexView iv, const uint32_t *__restrict__ keys, int64_t n, const int64_t *__restrict__ pos_off,
                                   int64_t cap_each, int32_t *__restrict__ out)
 {
