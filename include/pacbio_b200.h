@@ -269,6 +269,52 @@ PB_API void pb_overlap_default_params(pb_overlap_params *p);
 PB_API int pb_overlap_batch(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const pb_seqset *reads,
                             const pb_overlap_params *prm, pb_overlap_rec *recs, uint8_t *ops, const int64_t *ops_off);
 
+/* ---- all-vs-all overlap detection (BASELINE config 5) --------------------------------- */
+
+/* The reference has no all-vs-all driver.  This is its trial loop (spaced_seed.cpp:424-436) with every sequence T of the set
+ * taking the locked reference's place in turn: for each ordered pair (T, Q), T != Q, the result is what
+ *     seedmap = T.get_seedmap(mask);  for j < max_trial: try_align(Q, j, +1) || try_align(Q, len-j-16, -1)
+ * returns (try_align: spaced_seed.cpp:261-299, ref_seq::try_align: ref_seq.h:259-266, get_seedmap: ref_seq.h:291-311).  One
+ * index over the whole set replaces the per-T seed maps. */
+
+/* seed index of EVERY sequence of `set`, each indexed as ref_seq::get_seedmap indexes a reference of at most
+ * MAX_READ_LEN+16 = 20016 bases (head pass only, positions 0..len-17 ascending; longer sequences: PB_ERR_DOMAIN).
+ * pb_index_nscanned = sum of the per-sequence get_seedmap return values.  Usable with pb_overlap_all_run only. */
+PB_API int pb_index_build_set(pb_ctx *ctx, const pb_seqset *set, uint32_t mask, pb_index **out);
+
+typedef struct {
+    int32_t read_id;   /* Q: the read whose head / tail seeds were probed (rank in the set) */
+    int32_t found;     /* 0/1 */
+    int32_t j;         /* trial number of the success */
+    int32_t ref_pos;   /* seed-map position (*it) inside T */
+    int32_t cost;      /* final_cost() */
+    int32_t read_pos;  /* the pos argument of try_align: j (forward) or len-j-16 (backward) */
+    int32_t dir;       /* +1 head / forward, -1 tail / backward */
+    int32_t matlen_a;  /* ref_ml (elements of T consumed) */
+    int32_t matlen_b;  /* seg_ml (elements of Q consumed) */
+    int32_t nedit;
+    int32_t ncand;     /* ref_seq::try_align calls the reference would have made for this (T, Q) pair */
+    int32_t ref_id;    /* T: the sequence acting as the locked reference (rank in the set) */
+    int64_t cells;     /* DP cells the reference would have evaluated for this pair */
+} pb_pair_rec;
+
+typedef struct pb_pairs_job pb_pairs_job;
+
+/* Probe the head / tail trial seeds of reads [q_first, q_first+q_count) of `set` against `ix` (pb_index_build_set over the
+ * same set) and verify every (T, Q) pair that shares a seed, first success in (trial, direction, list) order per pair.
+ * A query sub-range is how callers bound memory per call and shard the work over GPUs (the index is replicated).
+ * prm: as pb_overlap_batch (want_ops must be 0).  Synchronous; results stay on the device until pb_pairs_job_fetch. */
+PB_API int pb_overlap_all_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *set, int64_t q_first, int64_t q_count,
+                              const pb_overlap_params *prm, pb_pairs_job **job);
+/* out[0] seed hits gathered (K2), [1] (T,Q) pairs with at least one hit, [2] pairs that reached the banded aligner (a
+ * candidate survived the exact 32-row prefix filter), [3] pairs found, [4] try_align calls the reference would have made
+ * over all pairs, [5] DP cells it would have evaluated, [6] alignments K3 ran, [7] DP cells K3 computed */
+PB_API int pb_pairs_job_stats(const pb_pairs_job *job, int64_t *out /* [8] */);
+/* found_only != 0: the successful pairs; 0: every pair that reached the aligner (found or not, with ncand / cells).
+ * Records come in ascending (read_id, ref_id).  recs == NULL: only *n is set.  cap = room in recs (records). */
+PB_API int pb_pairs_job_fetch(pb_ctx *ctx, const pb_pairs_job *job, int found_only, pb_pair_rec *recs, int64_t cap, int64_t *n);
+PB_API void pb_pairs_job_free(pb_pairs_job *job);
+
 #ifdef __cplusplus
 }
 #endif

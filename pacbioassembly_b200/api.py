@@ -24,7 +24,10 @@ LOCATE_DTYPE = np.dtype([(n, np.int32) for n in ("nseq", "found", "j", "pos", "c
                                                   "matlen_b", "nedit", "ncand", "_pad")] + [("cells", np.int64)])
 OVERLAP_DTYPE = np.dtype([(n, np.int32) for n in ("id", "found", "j", "ref_pos", "cost", "read_pos", "dir", "matlen_a",
                                                    "matlen_b", "nedit", "ncand", "_pad")] + [("cells", np.int64)])
-assert ALIGN_DTYPE.itemsize == 48 and LOCATE_DTYPE.itemsize == 56 and OVERLAP_DTYPE.itemsize == 56
+PAIR_DTYPE = np.dtype([(n, np.int32) for n in ("read_id", "found", "j", "ref_pos", "cost", "read_pos", "dir", "matlen_a",
+                                               "matlen_b", "nedit", "ncand", "ref_id")] + [("cells", np.int64)])
+PAIR_STATS = ("seed_hits", "pairs", "pairs_aligned", "pairs_found", "try_align_calls", "ref_cells", "k3_alignments", "k3_cells")
+assert ALIGN_DTYPE.itemsize == 48 and LOCATE_DTYPE.itemsize == 56 and OVERLAP_DTYPE.itemsize == 56 and PAIR_DTYPE.itemsize == 56
 
 
 class LocateParams(C.Structure):
@@ -104,6 +107,11 @@ def lib() -> C.CDLL:
         "pb_locate_job_free": (None, [vp]),
         "pb_overlap_default_params": (None, [P(OverlapParams)]),
         "pb_overlap_batch": (C.c_int, [vp, vp, vp, i64, vp, P(OverlapParams), vp, vp, vp]),
+        "pb_index_build_set": (C.c_int, [vp, vp, u32, P(vp)]),
+        "pb_overlap_all_run": (C.c_int, [vp, vp, vp, i64, i64, P(OverlapParams), P(vp)]),
+        "pb_pairs_job_stats": (C.c_int, [vp, vp]),
+        "pb_pairs_job_fetch": (C.c_int, [vp, vp, C.c_int, vp, i64, P(i64)]),
+        "pb_pairs_job_free": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         try:
@@ -358,6 +366,37 @@ class Context:
         if want_ops:
             return recs, [ops[ops_off[k]: ops_off[k] + int(recs["nedit"][k])] for k in range(n)]
         return recs
+
+    # ---- all-vs-all ------------------------------------------------------------------------------
+    def index_set(self, seqs: "SeqSet", mask: int) -> "Index":
+        """one seed index over every sequence of the set (get_seedmap's head pass per sequence, ref_seq.h:291-300)"""
+        h = C.c_void_p()
+        self.check(self._L.pb_index_build_set(self.h, seqs.h, mask, C.byref(h)))
+        return Index(self, h, seqs, -1)
+
+    def overlap_all(self, index: "Index", q_first: int = 0, q_count: int | None = None, found_only: bool = True, **params):
+        """the trial loop of spaced_seed.cpp:424-436 with every read of the set as the locked reference in turn;
+        returns (records[PAIR_DTYPE], stats dict)"""
+        prm = OverlapParams()
+        self._L.pb_overlap_default_params(C.byref(prm))
+        for k, v in params.items():
+            setattr(prm, k, v)
+        seqs = index.ref
+        if q_count is None:
+            q_count = len(seqs) - q_first
+        h = C.c_void_p()
+        self.check(self._L.pb_overlap_all_run(self.h, index.h, seqs.h, q_first, q_count, C.byref(prm), C.byref(h)))
+        try:
+            st = (C.c_int64 * 8)()
+            self.check(self._L.pb_pairs_job_stats(h, st))
+            stats = dict(zip(PAIR_STATS, (int(x) for x in st)))
+            n = C.c_int64(0)
+            self.check(self._L.pb_pairs_job_fetch(self.h, h, int(found_only), None, 0, C.byref(n)))
+            recs = np.zeros(n.value, dtype=PAIR_DTYPE)
+            self.check(self._L.pb_pairs_job_fetch(self.h, h, int(found_only), _ptr(recs), n.value, C.byref(n)))
+        finally:
+            self._L.pb_pairs_job_free(h)
+        return recs, stats
 
     def locate_run(self, index: "Index", reads: "SeqSet", want_ops: bool = False, **params) -> "LocateJob":
         prm = default_locate_params(want_ops=int(want_ops), **params)

@@ -112,14 +112,14 @@ struct CandView {
 };
 
 // candidate = (read r of length rlen at line offset rbase, query q of kept read k, seed-map position refpos)
-__device__ __forceinline__ void derive_views(const PairViews &pv, const LocateView &lv, int k, int r, int rlen, int64_t rbase, int q,
-                                             int refpos, bool irr, CandView &cv)
+// t = trial (query number within the read); the reference sequence sits at line offset ref_base with ref_len elements
+__device__ __forceinline__ void derive_views(const PairViews &pv, const LocateView &lv, int t, int r, int rlen, int64_t rbase,
+                                             int64_t ref_base, int ref_len, int refpos, bool irr, CandView &cv)
 {
-    const int t = q - k * lv.ntrial;
     if (lv.mode == PB_MODE_LOCATE) { // locator.cpp:78-82: align(read[j:], ref[pos:])
         cv.j = t; cv.read_pos = t; cv.dir = 1;
         cv.a = &pv.A; cv.a_bit = rbase + t; cv.a_len = rlen - t;
-        cv.b = &pv.B; cv.b_bit = lv.ref_base + refpos; cv.b_len = lv.ref_len - refpos;
+        cv.b = &pv.B; cv.b_bit = ref_base + refpos; cv.b_len = ref_len - refpos;
         cv.a_tab = irr ? pv.A.tab[r] : 0u;
         return;
     }
@@ -129,11 +129,11 @@ __device__ __forceinline__ void derive_views(const PairViews &pv, const LocateVi
     cv.read_pos = forward ? cv.j : rlen - cv.j - 16;
     cv.a_tab = 0u;
     if (forward) {
-        cv.a = &pv.B; cv.a_bit = lv.ref_base + refpos; cv.a_len = lv.ref_len - refpos;
+        cv.a = &pv.B; cv.a_bit = ref_base + refpos; cv.a_len = ref_len - refpos;
         cv.b = &pv.A; cv.b_bit = rbase + cv.read_pos; cv.b_len = rlen - cv.read_pos;
     } else { // element k of a backward accessor at offset o is text[o - k]: position len-1-o of the reversed copy
         const int r_off = refpos + 15, s_off = cv.read_pos + 15;
-        cv.a = &pv.B2; cv.a_bit = lv.ref_base + (lv.ref_len - 1 - r_off); cv.a_len = r_off + 1;
+        cv.a = &pv.B2; cv.a_bit = ref_base + (ref_len - 1 - r_off); cv.a_len = r_off + 1;
         cv.b = &pv.A2; cv.b_bit = rbase + (rlen - 1 - s_off); cv.b_len = s_off + 1;
     }
 }
@@ -177,10 +177,23 @@ prefilter_kernel(const __grid_constant__ PairViews pv, const __grid_constant__ L
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncand) return;
     const int q = lv.d_cand_q[c];
-    const int k = q / lv.ntrial;
+    int k, t;
+    int64_t ref_base = lv.ref_base;
+    int ref_len = lv.ref_len;
+    if (lv.d_cand_item) { // all-vs-all: candidates carry their (reference, read) pair and their trial number
+        k = lv.d_cand_item[c];
+        if (k < 0) { survive[c] = 0; rej_cells[c] = 0; return; } // slot of a dropped self hit
+        t = q;
+        const int T = lv.d_item_ref[k];
+        ref_base = pv.B.base[T];
+        ref_len = pv.B.len[T];
+    } else {
+        k = q / lv.ntrial;
+        t = q - k * lv.ntrial;
+    }
     const int r = lv.d_kept[k];
     CandView cv;
-    derive_views(pv, lv, k, r, pv.A.len[r], pv.A.base[r], q, lv.d_cand_pos[c], false, cv);
+    derive_views(pv, lv, t, r, pv.A.len[r], pv.A.base[r], ref_base, ref_len, lv.d_cand_pos[c], false, cv);
     const SeqView &A = *cv.a, &B = *cv.b;
     const int a_len = cv.a_len, b_len = cv.b_len;
     const int64_t a_bit = cv.a_bit, b_bit = cv.b_bit;
@@ -733,7 +746,9 @@ struct AlignLaunch {
 // resident CTAs per SM the register allocation is held to (more warps hide the shuffle / ballot latencies of a row)
 template <int S> struct MinBlocks { static constexpr int v = (S <= 3 ? PB_MINB3 : (S <= 5 ? 5 : (S <= 12 ? 4 : 3))) * 4 / ALIGN_WPB; };
 
-template <int S, bool IRR>
+// PAIRS = all-vs-all items (pb_overlap_all_run): a separate instantiation, so the single-reference kernels keep their
+// register allocation
+template <int S, bool IRR, bool PAIRS>
 __global__ void __launch_bounds__(ALIGN_WPB * 32, MinBlocks<S>::v)
 align_locate_kernel(const __grid_constant__ AlignLaunch p, const __grid_constant__ LocateView lv, const uint8_t *__restrict__ survive,
                     const int32_t *__restrict__ rej_cells,
@@ -761,7 +776,12 @@ align_locate_kernel(const __grid_constant__ AlignLaunch p, const __grid_constant
         const int r = lv.d_kept[k];
         const int rlen = p.A.len[r];
         const int64_t rbase = p.A.base[r];
-        const int64_t c0 = lv.d_qoff[(int64_t)k * lv.ntrial], c1 = lv.d_qoff[(int64_t)(k + 1) * lv.ntrial];
+        // all-vs-all: item = (reference T, read r) with its own candidate range
+        const int64_t c0 = PAIRS ? lv.d_item_beg[k] : lv.d_qoff[(int64_t)k * lv.ntrial];
+        const int64_t c1 = PAIRS ? lv.d_item_end[k] : lv.d_qoff[(int64_t)(k + 1) * lv.ntrial];
+        const int T = PAIRS ? lv.d_item_ref[k] : 0;
+        const int64_t ref_base = PAIRS ? p.B.base[T] : lv.ref_base;
+        const int ref_len = PAIRS ? p.B.len[T] : lv.ref_len;
         long long cells = 0;
         int ncand = 0;
         bool found = false;
@@ -781,7 +801,8 @@ align_locate_kernel(const __grid_constant__ AlignLaunch p, const __grid_constant
                 const int q = lv.d_cand_q[cb + f];
                 const int pos = lv.d_cand_pos[cb + f];
                 CandView cv;
-                derive_views(*reinterpret_cast<const PairViews *>(&p.A), lv, k, r, rlen, rbase, q, pos, IRR, cv);
+                derive_views(*reinterpret_cast<const PairViews *>(&p.A), lv, PAIRS ? q : q - k * lv.ntrial, r, rlen, rbase, ref_base,
+                             ref_len, pos, IRR, cv);
                 align_one<S, IRR>(*cv.a, cv.a_bit, cv.a_len, cv.a_tab, *cv.b, cv.b_bit, cv.b_len, p.R, p.maxn, p.maxm, planes,
                              p.PW, par, opsrev, p.ops ? p.ops + p.ops_off[k] : nullptr, p.c31, p.c2, raw, p.RW, bar, phase, res);
                 cells += res.cells;
@@ -799,7 +820,7 @@ align_locate_kernel(const __grid_constant__ AlignLaunch p, const __grid_constant
         }
         if (lane == 0) {
             pb_locate_rec rec;
-            rec.nseq = k; rec.found = found ? 1 : 0;
+            rec.nseq = PAIRS ? r : k; rec.found = found ? 1 : 0;
             rec.j = found ? win_j : 0; rec.pos = found ? win_pos : 0;
             rec.cost = found ? res.cost : 0;
             // locator: len - j and cost(len-j,len-j) (locator.cpp:85-86); overlap: try_align's pos and direction
@@ -807,7 +828,7 @@ align_locate_kernel(const __grid_constant__ AlignLaunch p, const __grid_constant
             rec.diag_cost = !found ? 0 : (lv.mode == PB_MODE_LOCATE ? res.diag_cost : win_dir);
             rec.matlen_a = found ? res.matlen_a : 0; rec.matlen_b = found ? res.matlen_b : 0;
             rec.nedit = found ? res.nedit : 0;
-            rec.ncand = ncand; rec._pad = 0; rec.cells = cells;
+            rec.ncand = ncand; rec._pad = T; rec.cells = cells; // all-vs-all: pb_pair_rec::ref_id
             recs[k] = rec;
         }
     }
@@ -1050,11 +1071,13 @@ struct ClassPlan {
 };
 
 template <int S, bool IRR> struct KernelSel {
-    static const void *locate() { return (const void *)align_locate_kernel<S, IRR>; }
+    static const void *locate() { return (const void *)align_locate_kernel<S, IRR, false>; }
+    static const void *locate_pairs() { return (const void *)align_locate_kernel<S, false, true>; }
     static const void *pairs() { return (const void *)align_pairs_kernel<S, IRR>; }
 };
 
-static const void *kernel_ptr(int key, bool locate)
+// locate: 0 = pairs of sequences (pb_align_batch), 1 = locate / overlap items, 2 = all-vs-all items
+static const void *kernel_ptr(int key, int locate)
 {
     if (key_packed(key)) {
         switch (key_lanes(key)) {
@@ -1074,7 +1097,7 @@ static const void *kernel_ptr(int key, bool locate)
         return nullptr;
     }
     switch (S) {
-#define CASE(s) case s: return locate ? KernelSel<s, false>::locate() : KernelSel<s, false>::pairs();
+#define CASE(s) case s: return locate == 2 ? KernelSel<s, false>::locate_pairs() : (locate ? KernelSel<s, false>::locate() : KernelSel<s, false>::pairs());
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(14) CASE(16)
 #undef CASE
     }
@@ -1090,7 +1113,7 @@ struct LaunchGeom {
     int wpb;        // warps per CTA
 };
 
-static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, bool locate, size_t scratch_budget, LaunchGeom *g)
+static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, int locate, size_t scratch_budget, LaunchGeom *g)
 {
     const size_t ops_bytes = ((size_t)2 * cp.max_rows + cp.max_D + 64 + 127) & ~(size_t)127; // keeps every slot 128 B aligned
     if (key_packed(key)) {
@@ -1155,7 +1178,7 @@ static size_t scratch_budget(pb_ctx *ctx)
 }
 
 template <class LaunchFn>
-static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, bool locate, AlignLaunch base, LaunchFn &&launch)
+static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, int locate, AlignLaunch base, LaunchFn &&launch)
 {
     if (plans.empty()) return PB_OK;
     const size_t budget = scratch_budget(ctx);
@@ -1302,9 +1325,16 @@ int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_
 {
     if (nkept == 0) return PB_OK;
     std::map<int, ClassPlan> plans;
+    // longest first, ties in input order: a counting sort (all-vs-all batches hold millions of items)
     std::vector<int32_t> order((size_t)nkept);
-    for (int64_t k = 0; k < nkept; ++k) order[k] = (int32_t)k;
-    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return kept_lens[x] > kept_lens[y]; });
+    {
+        int maxlen = 0;
+        for (int64_t k = 0; k < nkept; ++k) maxlen = std::max(maxlen, kept_lens[k]);
+        std::vector<int64_t> first((size_t)maxlen + 2, 0);
+        for (int64_t k = 0; k < nkept; ++k) first[(size_t)(maxlen - kept_lens[k]) + 1]++;
+        for (size_t l = 1; l < first.size(); ++l) first[l] += first[l - 1];
+        for (int64_t k = 0; k < nkept; ++k) order[(size_t)first[(size_t)(maxlen - kept_lens[k])]++] = (int32_t)k;
+    }
     for (int32_t k : order) {
         const int L = kept_lens[k];
         // widest band / longest seg_a any candidate of this read can reach the DP with: len_a <= L, and the domain
@@ -1330,9 +1360,10 @@ int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_
     base.ops = d_ops; base.ops_off = d_ops_off;
     base.stats = d_stats;
     base.c31 = 0x80000000u; base.c2 = 2u;
-    return run_classes(ctx, plans, true, base, [&](int key, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
+    const int kmode = lv.d_item_ref ? 2 : 1;
+    return run_classes(ctx, plans, kmode, base, [&](int key, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
         void *args[] = {(void *)&p, (void *)&lv, (void *)&d_survive, (void *)&d_rej_cells, (void *)&d_recs};
-        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(key, true), dim3(g.blocks), dim3(g.wpb * 32), args, g.smem_bytes, st));
+        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(key, kmode), dim3(g.blocks), dim3(g.wpb * 32), args, g.smem_bytes, st));
         ctx->launches++;
         return PB_OK;
     });
@@ -1376,9 +1407,9 @@ int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t 
     base.R = R; base.maxn = maxn; base.maxm = maxm;
     base.ops = d_ops; base.ops_off = d_ops_off;
     base.c31 = 0x80000000u; base.c2 = 2u;
-    return run_classes(ctx, plans, false, base, [&](int key, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
+    return run_classes(ctx, plans, 0, base, [&](int key, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
         void *args[] = {(void *)&p, (void *)&d_out};
-        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(key, false), dim3(g.blocks), dim3(g.wpb * 32), args, g.smem_bytes, st));
+        PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(key, 0), dim3(g.blocks), dim3(g.wpb * 32), args, g.smem_bytes, st));
         ctx->launches++;
         return PB_OK;
     });

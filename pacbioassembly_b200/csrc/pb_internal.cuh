@@ -143,6 +143,7 @@ struct pb_index {
     int64_t nbuckets = 0;
     int64_t nentries = 0, nkeys = 0, nscanned = 0;
     int64_t ref_len = 0;
+    bool whole_set = false; // built by pb_index_build_set: entries are positions on the set's padded line
     BucketFn fn;
     DevBuf d_start; // [nbuckets+1] u32
     DevBuf d_pos;   // [nentries] i32, per bucket in the reference's list order
@@ -194,6 +195,13 @@ struct LocateView { // everything the aligner needs to derive candidate (a,b) vi
     int mode;         // PB_MODE_LOCATE: a = read[j:], b = ref[pos:] (locator.cpp:78-82)
                       // PB_MODE_OVERLAP: a = ref view, b = read view, forward or backward (spaced_seed.cpp:274-285, ref_seq.h:264)
     int min_overlap;  // OVERLAP_MIN gate on matlen_a (ref_seq.h:265), overlap mode only
+    // all-vs-all (pb_overlap_all_run): work item k = one (reference sequence, read) pair.  d_kept[k] = the read, d_item_ref[k] =
+    // the sequence acting as reference (in ss.ref), candidates [d_item_beg[k], d_item_end[k]) in (trial, list) order with
+    // d_cand_q = trial number and d_cand_pos = position inside that reference; d_cand_item (prefilter only) = item of a
+    // candidate slot, -1 for a dropped one.  All NULL in the single-reference modes.
+    const int32_t *d_item_ref = nullptr;
+    const int64_t *d_item_beg = nullptr, *d_item_end = nullptr;
+    const int32_t *d_cand_item = nullptr;
 };
 #define PB_MODE_LOCATE 0
 #define PB_MODE_OVERLAP 1

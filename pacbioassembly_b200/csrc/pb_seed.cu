@@ -282,6 +282,40 @@ __global__ void index_scatter_kernel(const uint32_t *__restrict__ keys_all, Entr
     ent[slot] = (int32_t)e;
 }
 
+// Whole-set variants (all-vs-all, pb_index_build_set): every sequence is indexed the way ref_seq::get_seedmap indexes a
+// reference no longer than MAX_READ_LEN+16 (ref_seq.h:291-300: head positions 0..len-17, no tail pass); an entry is the
+// position on the set's padded line, so ascending entries = ascending (sequence, position) = each sequence's list order.
+// One CTA walks one sequence at a time: no owner search, coalesced key loads.
+__global__ void __launch_bounds__(256)
+set_index_count_kernel(const uint32_t *__restrict__ keys_all, const int64_t *__restrict__ base, const int32_t *__restrict__ len,
+                       int64_t nseq, BucketFn fn, uint32_t *__restrict__ count)
+{
+    for (int64_t i = blockIdx.x; i < nseq; i += gridDim.x) {
+        const int64_t b = base[i];
+        const int nhead = len[i] - 16;
+        for (int o = threadIdx.x; o < nhead; o += blockDim.x) {
+            const uint32_t key = keys_all[b + o];
+            if (key) atomicAdd(&count[bucket_of(fn, key)], 1u);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+set_index_scatter_kernel(const uint32_t *__restrict__ keys_all, const int64_t *__restrict__ base, const int32_t *__restrict__ len,
+                         int64_t nseq, BucketFn fn, uint32_t *__restrict__ cursor, int32_t *__restrict__ ent)
+{
+    for (int64_t i = blockIdx.x; i < nseq; i += gridDim.x) {
+        const int64_t b = base[i];
+        const int nhead = len[i] - 16;
+        for (int o = threadIdx.x; o < nhead; o += blockDim.x) {
+            const uint32_t key = keys_all[b + o];
+            if (!key) continue;
+            const uint32_t slot = atomicAdd(&cursor[bucket_of(fn, key)], 1u);
+            ent[slot] = (int32_t)(b + o);
+        }
+    }
+}
+
 #define SMALL_BUCKET 48
 
 // restore insertion order inside each bucket (the atomic scatter is unordered)
@@ -372,18 +406,21 @@ __global__ void index_nkeys_kernel(const uint32_t *__restrict__ start, int64_t n
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(nkeys, mine);
 }
 
-extern "C" int pb_index_build(pb_ctx *ctx, const pb_seqset *ref, int64_t seq, uint32_t mask, int policy, pb_index **out)
+// seq >= 0: one sequence under `policy`; seq < 0: every sequence of the set (get_seedmap's head pass per sequence)
+static int index_build_impl(pb_ctx *ctx, const pb_seqset *ref, int64_t seq, uint32_t mask, int policy, pb_index **out)
 {
-    if (!ctx || !ref || !out || seq < 0 || seq >= ref->n) return pb_fail(ctx, PB_ERR_ARG, "pb_index_build: bad argument");
-    if (policy != PB_POLICY_LOCATOR && policy != PB_POLICY_REFSEQ) return pb_fail(ctx, PB_ERR_ARG, "unknown index policy %d", policy);
     *out = nullptr;
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     pb_timer_reset(ctx);
-    const int64_t len = ref->len[seq];
+    const bool whole_set = seq < 0;
+    const int64_t len = whole_set ? ref->base[ref->n] : ref->len[seq];
     EntryMap em;
     em.len = len;
     int64_t nscan;
-    if (policy == PB_POLICY_LOCATOR) {
+    if (whole_set) {
+        em.nhead = len; // entries are line positions already
+        nscan = len;
+    } else if (policy == PB_POLICY_LOCATOR) {
         em.nhead = len;
         nscan = len;
     } else { // ref_seq.h:291-311
@@ -396,7 +433,8 @@ extern "C" int pb_index_build(pb_ctx *ctx, const pb_seqset *ref, int64_t seq, ui
     ix->ctx = ctx;
     ix->mask = mask;
     ix->policy = policy;
-    ix->ref_len = len;
+    ix->ref_len = whole_set ? -1 : len;
+    ix->whole_set = whole_set;
     ix->nscanned = nscan;
     ix->fn = make_bucket_fn(mask);
     ix->nbuckets = (int64_t)1 << ix->fn.bits;
@@ -406,13 +444,20 @@ extern "C" int pb_index_build(pb_ctx *ctx, const pb_seqset *ref, int64_t seq, ui
     DevBuf d_keys, d_count, d_cursor, tmp, d_big, d_nbig, d_nkeys;
     TRYI(d_keys.alloc(ctx, (size_t)std::max<int64_t>(len, 1) * 4 + 64));
     pb_timer_begin(ctx, PB_T_SEED);
-    TRYI(pb_seed_bulk_device(ctx, ref, ref->base[seq], len, mask, d_keys.as<uint32_t>()));
+    TRYI(pb_seed_bulk_device(ctx, ref, whole_set ? 0 : ref->base[seq], len, mask, d_keys.as<uint32_t>()));
     pb_timer_end(ctx, PB_T_SEED);
     pb_timer_begin(ctx, PB_T_INDEX);
     TRYI(d_count.alloc_zero(ctx, (size_t)(nb + 1) * 4));
     TRYI(ix->d_start.alloc(ctx, (size_t)(nb + 2) * 4));
     const unsigned gscan = (unsigned)std::max<int64_t>(1, (nscan + 255) / 256);
-    if (nscan > 0) {
+    const unsigned gset = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ref->n, (int64_t)ctx->sm_count * 8));
+    if (whole_set) {
+        int64_t ns = 0;
+        for (int64_t i = 0; i < ref->n; ++i) ns += std::max(0, ref->len[i] - 16);
+        ix->nscanned = ns;
+        set_index_count_kernel<<<gset, 256, 0, ctx->stream>>>(d_keys.as<uint32_t>(), ref->d_base.as<int64_t>(), ref->d_len.as<int32_t>(), ref->n, ix->fn, d_count.as<uint32_t>());
+        ctx->launches++;
+    } else if (nscan > 0) {
         index_count_kernel<<<gscan, 256, 0, ctx->stream>>>(d_keys.as<uint32_t>(), em, nscan, ix->fn, d_count.as<uint32_t>());
         ctx->launches++;
     }
@@ -429,7 +474,10 @@ extern "C" int pb_index_build(pb_ctx *ctx, const pb_seqset *ref, int64_t seq, ui
             delete ix;
             return pb_fail(ctx, PB_ERR_CUDA, "cursor copy failed");
         }
-        index_scatter_kernel<<<gscan, 256, 0, ctx->stream>>>(d_keys.as<uint32_t>(), em, nscan, ix->fn, d_cursor.as<uint32_t>(), ix->d_pos.as<int32_t>());
+        if (whole_set)
+            set_index_scatter_kernel<<<gset, 256, 0, ctx->stream>>>(d_keys.as<uint32_t>(), ref->d_base.as<int64_t>(), ref->d_len.as<int32_t>(), ref->n, ix->fn, d_cursor.as<uint32_t>(), ix->d_pos.as<int32_t>());
+        else
+            index_scatter_kernel<<<gscan, 256, 0, ctx->stream>>>(d_keys.as<uint32_t>(), em, nscan, ix->fn, d_cursor.as<uint32_t>(), ix->d_pos.as<int32_t>());
         ctx->launches++;
         // big buckets are rare (degenerate repeats); the list can hold at most nentries/SMALL_BUCKET of them
         const int64_t maxbig = ix->nentries / SMALL_BUCKET + 1;
@@ -472,6 +520,24 @@ extern "C" int pb_index_build(pb_ctx *ctx, const pb_seqset *ref, int64_t seq, ui
 #undef TRYI
     *out = ix;
     return PB_OK;
+}
+
+extern "C" int pb_index_build(pb_ctx *ctx, const pb_seqset *ref, int64_t seq, uint32_t mask, int policy, pb_index **out)
+{
+    if (!ctx || !ref || !out || seq < 0 || seq >= ref->n) return pb_fail(ctx, PB_ERR_ARG, "pb_index_build: bad argument");
+    if (policy != PB_POLICY_LOCATOR && policy != PB_POLICY_REFSEQ) return pb_fail(ctx, PB_ERR_ARG, "unknown index policy %d", policy);
+    return index_build_impl(ctx, ref, seq, mask, policy, out);
+}
+
+extern "C" int pb_index_build_set(pb_ctx *ctx, const pb_seqset *set, uint32_t mask, pb_index **out)
+{
+    if (!ctx || !set || !out || set->n < 1) return pb_fail(ctx, PB_ERR_ARG, "pb_index_build_set: bad argument");
+    if (set->base[set->n] > (int64_t)INT32_MAX) return pb_fail(ctx, PB_ERR_DOMAIN, "set of %lld padded bases: index positions are 32-bit; split the set", (long long)set->base[set->n]);
+    for (int64_t i = 0; i < set->n; ++i)
+        if (set->len[i] > 20016)
+            return pb_fail(ctx, PB_ERR_DOMAIN, "sequence %lld has %d bases: a reference longer than MAX_READ_LEN+16 gets get_seedmap's tail pass "
+                           "(ref_seq.h:301-308); index it on its own with pb_index_build(PB_POLICY_REFSEQ)", (long long)i, set->len[i]);
+    return index_build_impl(ctx, set, -1, mask, PB_POLICY_REFSEQ, out);
 }
 
 extern "C" void pb_index_free(pb_index *ix)

@@ -539,3 +539,90 @@ def test_align_narrow_bands_packed(ctx, oracle):
         P = [workload.sweep_pair(7 * band + alen, k, alen, band) for k in range(24)]
         Rr = P[0][2]
         assert run_batch_vs_oracle(ctx, oracle, [x[0] for x in P], [x[1] for x in P], Rr) == 24
+
+
+# ---------------------------------------------------------------------------------------------
+# all-vs-all overlap detection (BASELINE config 5): pb_index_build_set + pb_overlap_all_run
+# ---------------------------------------------------------------------------------------------
+
+def check_allpairs(ctx, oracle, texts, image, mask, R=0.3, quirk=0, golden_row=None, splits=1):
+    from allpairs_util import PAIR_FIELDS, expected_pairs, oracle_overlap_fn
+    reads = ctx.seqset_from_bin(image)
+    ix = ctx.index_set(reads, mask)
+    n = len(reads)
+    recs_l, stats_l = [], []
+    for s in range(splits):  # query sub-ranges: how callers bound memory and shard over GPUs
+        q0, q1 = n * s // splits, n * (s + 1) // splits
+        recs, stats = ctx.overlap_all(ix, q0, q1 - q0, found_only=False, R=R, seed_at_quirk=quirk)
+        assert ((recs["read_id"] >= q0) & (recs["read_id"] < q1)).all()
+        recs_l.append(recs)
+        stats_l.append(stats)
+    recs = np.concatenate(recs_l)
+    stats = {k: sum(s[k] for s in stats_l) for k in stats_l[0]}
+    want, tot_ncand, tot_cells = expected_pairs(oracle_overlap_fn(oracle, mask, R=R, quirk=bool(quirk)), texts, image)
+    # totals over every (T, Q) pair with a seed hit, aligned or not
+    assert stats["pairs"] == len(want) and stats["try_align_calls"] == tot_ncand and stats["ref_cells"] == tot_cells
+    assert stats["pairs_aligned"] == len(recs)
+    key = list(zip(recs["read_id"].tolist(), recs["ref_id"].tolist()))
+    assert key == sorted(key) and len(set(key)) == len(key)
+    for rec in recs:  # every pair that reached the aligner, found or not
+        w = want[(int(rec["ref_id"]), int(rec["read_id"]))]
+        for f in ("found", "ncand", "cells") + PAIR_FIELDS:
+            assert int(rec[f]) == int(w[f]), (int(rec["ref_id"]), int(rec["read_id"]), f, int(rec[f]), int(w[f]))
+    got_found = {(int(r["ref_id"]), int(r["read_id"])) for r in recs if r["found"]}
+    assert got_found == {k for k, v in want.items() if v["found"]}
+    assert stats["pairs_found"] == len(got_found)
+    f2, st2 = ctx.overlap_all(ix, found_only=True, R=R, seed_at_quirk=quirk)
+    assert len(f2) == len(got_found) == st2["pairs_found"] and (f2["found"] == 1).all()
+    if golden_row is not None:  # the compiled reference's own output
+        assert len(f2) == len(golden_row["found"]) and st2["try_align_calls"] == golden_row["try_align_calls"]
+        assert st2["pairs"] == golden_row["pairs_with_calls"]
+        for rec, row in zip(f2, golden_row["found"]):
+            for f in ("ref_id", "read_id") + PAIR_FIELDS:
+                assert int(rec[f]) == row[f], (row, f)
+    ix.free()
+    reads.free()
+    return len(got_found)
+
+
+def test_allpairs_golden_and_oracle(ctx, golden, oracle):
+    from allpairs_util import allpairs_workload
+    for g in golden["allpairs"]:
+        texts, image = allpairs_workload(g["seed"], g["genome_len"], g["nreads"])
+        # shipped seed_at behaviour: against the compiled reference's output and the oracle
+        assert check_allpairs(ctx, oracle, texts, image, g["mask"], R=g["R"], quirk=1, golden_row=g) > 100
+        # intended behaviour (seed at base pos): against the oracle
+        assert check_allpairs(ctx, oracle, texts, image, g["mask"], R=g["R"], quirk=0, splits=3) > 100
+
+
+def test_allpairs_clr_reads(ctx, oracle):
+    """CLR-like error (ins 9 / del 4 / sub 2 %), longer reads, high coverage: many seed hits per pair, dir = -1 and +1"""
+    from allpairs_util import allpairs_workload
+    texts, image = allpairs_workload(341, 20000, 60, mean=3000.0, lo=520, hi=9000, err=(0.09, 0.04, 0.02))
+    assert check_allpairs(ctx, oracle, texts, image, MASKS[0], splits=2) > 30
+    # a read set with a short read (len <= 500 is dropped by open_binary) and a duplicate read
+    texts2 = texts[:20] + [texts[3], texts[5][:400]]
+    import cpu_libs
+    o = cpu_libs.oracle()
+    image2 = b"".join(o.text2bin(t) for t in texts2)
+    assert check_allpairs(ctx, oracle, texts2, image2, MASKS[1]) > 5
+
+
+def test_allpairs_errors(ctx):
+    from allpairs_util import allpairs_workload
+    from pacbioassembly_b200 import PbError
+    texts, image = allpairs_workload(351, 3000, 8)
+    reads = ctx.seqset_from_bin(image)
+    single = ctx.index(reads, MASKS[0], policy=1, seq=0)
+    with pytest.raises(PbError):
+        ctx.overlap_all(single)  # not a whole-set index
+    ix = ctx.index_set(reads, MASKS[0])
+    with pytest.raises(PbError):
+        ctx.overlap(ix, reads)  # and a whole-set index is not a single-reference one
+    with pytest.raises(PbError):
+        ctx.overlap_all(ix, 0, len(reads) + 1)
+    recs, st = ctx.overlap_all(ix, 0, 0)
+    assert len(recs) == 0 and st["pairs"] == 0
+    long_ref = ctx.seqset_one(workload.reference(5, 20017))
+    with pytest.raises(PbError):
+        ctx.index_set(long_ref, MASKS[0])

@@ -348,3 +348,38 @@ def test_golden_overlap(oracle, golden):
         for k, row in enumerate(g["records"]):
             for n, v in row.items():
                 assert int(got[n][k]) == v, (k, n)
+
+
+# ---------------------------------------------------------------------------------------------
+# all-vs-all (BASELINE config 5): the trial loop once per target read, the target as the locked reference
+# ---------------------------------------------------------------------------------------------
+
+def test_golden_allpairs(oracle, golden):
+    """the restatement against the compiled reference's output (shipped seed_at behaviour): successful pairs field by
+    field, number of pairs with a try_align call, number of calls"""
+    from allpairs_util import PAIR_FIELDS, allpairs_workload, expected_pairs, oracle_overlap_fn
+    for g in golden["allpairs"]:
+        texts, image = allpairs_workload(g["seed"], g["genome_len"], g["nreads"])
+        pairs, tot_ncand, _ = expected_pairs(oracle_overlap_fn(oracle, g["mask"], R=g["R"], quirk=True), texts, image)
+        assert len(pairs) == g["pairs_with_calls"] and tot_ncand == g["try_align_calls"]
+        found = {k: v for k, v in pairs.items() if v["found"]}
+        assert len(found) == len(g["found"]) > 100
+        for row in g["found"]:
+            rec = found[(row["ref_id"], row["read_id"])]
+            for n in PAIR_FIELDS:
+                assert int(rec[n]) == row[n], (row, n)
+
+
+def test_live_allpairs(oracle, ref):
+    """same, live against the compiled reference, on a different workload and with transposed roles checked:
+    overlap(T, Q) and overlap(Q, T) are separate results (T is indexed whole, Q only probes its head / tail trials)"""
+    from allpairs_util import PAIR_FIELDS, allpairs_workload, expected_pairs, oracle_overlap_fn
+    texts, image = allpairs_workload(331, 6000, 30)
+    mask = 0xff3c3ffc
+    want, wn, _ = expected_pairs(lambda t, img: ref.overlap(t, img, mask, R=0.3), texts, image)
+    got, gn, _ = expected_pairs(oracle_overlap_fn(oracle, mask, quirk=True), texts, image)
+    assert sorted(want) == sorted(got) and wn == gn
+    for k in want:
+        for n in ("found", "ncand") + PAIR_FIELDS:
+            assert int(want[k][n]) == int(got[k][n]), (k, n)
+    assert any((q, t) not in want for (t, q) in want)
