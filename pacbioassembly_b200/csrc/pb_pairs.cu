@@ -174,21 +174,35 @@ pairs_emit_kernel(const int64_t *__restrict__ qoff, int64_t nq_reads, int ntr, c
 
 // P4: an item whose candidates all fail the prefix filter is finished: it adds its try_align calls and their DP cells to the
 // totals [0], [1]; the others are flagged for the aligner.
+// For a live item, bound[it] = the longest min(|a|,|b|) over its surviving candidate views (spaced_seed.cpp:274-276, ref_seq.h:282-286):
+// it fixes the widest band (max_dst = 1 + min*R, seq_aligner.h:94-102) the item can ask of the aligner, i.e. its band class.
 __global__ void __launch_bounds__(256)
 pairs_live_kernel(const int64_t *__restrict__ item_beg, const int64_t *__restrict__ item_end, int64_t nitems,
+                  const int32_t *__restrict__ item_q, const int32_t *__restrict__ item_ref, const int32_t *__restrict__ len,
+                  const int32_t *__restrict__ s_pos, const int32_t *__restrict__ s_t,
                   const uint8_t *__restrict__ survive, const int32_t *__restrict__ rej_cells, uint32_t *__restrict__ live,
-                  unsigned long long *__restrict__ totals)
+                  int32_t *__restrict__ bound, unsigned long long *__restrict__ totals)
 {
     const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long nc = 0, cells = 0;
     if (it < nitems) {
         bool any = false;
+        int bnd = 0;
+        const int lenq = len[item_q[it]], lent = len[item_ref[it]];
         for (int64_t c = item_beg[it]; c < item_end[it]; ++c) {
-            any |= survive[c] != 0;
+            if (survive[c]) {
+                any = true;
+                const int t = s_t[c], j = t >> 1, pos = s_pos[c];
+                const bool forward = (t & 1) == 0;
+                const int a_len = forward ? lent - pos : pos + 16;
+                const int b_len = lenq - j; // forward: len - pos with pos = j; backward: pos + 16 with pos = len-j-16
+                bnd = max(bnd, min(a_len, b_len));
+            }
             cells += (unsigned long long)rej_cells[c];
             ++nc;
         }
         live[it] = any ? 1u : 0u;
+        bound[it] = bnd;
         if (any) { nc = 0; cells = 0; }
     }
     for (int d = 16; d; d >>= 1) {
@@ -201,12 +215,13 @@ pairs_live_kernel(const int64_t *__restrict__ item_beg, const int64_t *__restric
 __global__ void __launch_bounds__(256)
 pairs_compact_kernel(const uint32_t *__restrict__ live, const int64_t *__restrict__ live_off, int64_t nitems, const int32_t *__restrict__ item_q,
                      const int32_t *__restrict__ item_ref, const int64_t *__restrict__ item_beg, const int64_t *__restrict__ item_end,
-                     int32_t *__restrict__ l_q, int32_t *__restrict__ l_ref, int64_t *__restrict__ l_beg, int64_t *__restrict__ l_end)
+                     const int32_t *__restrict__ bound, int32_t *__restrict__ l_q, int32_t *__restrict__ l_ref, int64_t *__restrict__ l_beg,
+                     int64_t *__restrict__ l_end, int32_t *__restrict__ l_bound)
 {
     const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= nitems || !live[it]) return;
     const int64_t o = live_off[it];
-    l_q[o] = item_q[it]; l_ref[o] = item_ref[it]; l_beg[o] = item_beg[it]; l_end[o] = item_end[it];
+    l_q[o] = item_q[it]; l_ref[o] = item_ref[it]; l_beg[o] = item_beg[it]; l_end[o] = item_end[it]; l_bound[o] = bound[it];
 }
 
 // P5: totals over the aligned items ([0] try_align calls, [1] cells) and the found flags
@@ -265,7 +280,7 @@ extern "C" int pb_overlap_all_run(pb_ctx *ctx, const pb_index *ix, const pb_seqs
     const int ntr = 2 * prm->max_trial;
     const int64_t nq = q_count;
     DevBuf d_kept, d_key, d_spos, d_st, d_sref, d_srank, d_nvalid, d_nitems, d_ibase, tmp, d_cand_item, d_iq, d_iref, d_ibeg, d_iend;
-    DevBuf d_survive, d_rej, d_live, d_loff, d_lq, d_lref, d_lbeg, d_lend, d_tot, d_stats, d_flag, d_foff;
+    DevBuf d_survive, d_rej, d_live, d_loff, d_lq, d_lref, d_lbeg, d_lend, d_tot, d_stats, d_flag, d_foff, d_bound, d_lbound;
     ProbeOut po;
     unsigned long long tot[2] = {0, 0}, tot2[2] = {0, 0}, k3[2] = {0, 0};
 #define STEP(x) do { if (r == PB_OK) r = (x); } while (0)
@@ -353,11 +368,14 @@ extern "C" int pb_overlap_all_run(pb_ctx *ctx, const pb_index *ix, const pb_seqs
             pb_timer_begin(ctx, PB_T_PREFILTER);
             STEP(pb_prefilter(ctx, ss, lv, nc, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(), d_rej.as<int32_t>()));
             STEP(d_live.alloc(ctx, (size_t)nitems * 4));
+            STEP(d_bound.alloc(ctx, (size_t)nitems * 4));
             STEP(d_loff.alloc(ctx, (size_t)(nitems + 2) * 8));
             STEP(d_tot.alloc_zero(ctx, 32));
             if (r == PB_OK) {
-                pairs_live_kernel<<<grid_for(nitems), 256, 0, ctx->stream>>>(d_ibeg.as<int64_t>(), d_iend.as<int64_t>(), nitems, d_survive.as<uint8_t>(),
-                                                                          d_rej.as<int32_t>(), d_live.as<uint32_t>(), d_tot.as<unsigned long long>());
+                pairs_live_kernel<<<grid_for(nitems), 256, 0, ctx->stream>>>(d_ibeg.as<int64_t>(), d_iend.as<int64_t>(), nitems, d_iq.as<int32_t>(),
+                                                                          d_iref.as<int32_t>(), set->d_len.as<int32_t>(), d_spos.as<int32_t>(),
+                                                                          d_st.as<int32_t>(), d_survive.as<uint8_t>(), d_rej.as<int32_t>(),
+                                                                          d_live.as<uint32_t>(), d_bound.as<int32_t>(), d_tot.as<unsigned long long>());
                 CHECK_LAUNCH();
             }
             STEP(pb_scan_i64(ctx, d_live.as<uint32_t>(), d_loff.as<int64_t>(), nitems, tmp));
@@ -373,19 +391,18 @@ extern "C" int pb_overlap_all_run(pb_ctx *ctx, const pb_index *ix, const pb_seqs
                 STEP(d_lref.alloc(ctx, (size_t)nlive * 4));
                 STEP(d_lbeg.alloc(ctx, (size_t)nlive * 8));
                 STEP(d_lend.alloc(ctx, (size_t)nlive * 8));
+                STEP(d_lbound.alloc(ctx, (size_t)nlive * 4));
                 if (r == PB_OK) {
                     pairs_compact_kernel<<<grid_for(nitems), 256, 0, ctx->stream>>>(d_live.as<uint32_t>(), d_loff.as<int64_t>(), nitems, d_iq.as<int32_t>(),
                                                                                  d_iref.as<int32_t>(), d_ibeg.as<int64_t>(), d_iend.as<int64_t>(),
-                                                                                 d_lq.as<int32_t>(), d_lref.as<int32_t>(), d_lbeg.as<int64_t>(),
-                                                                                 d_lend.as<int64_t>());
+                                                                                 d_bound.as<int32_t>(), d_lq.as<int32_t>(), d_lref.as<int32_t>(),
+                                                                                 d_lbeg.as<int64_t>(), d_lend.as<int64_t>(), d_lbound.as<int32_t>());
                     CHECK_LAUNCH();
                 }
-                std::vector<int32_t> lq((size_t)nlive), lref((size_t)nlive), bound((size_t)nlive);
-                STEP(pb_d2h(ctx, lq.data(), d_lq.p, (size_t)nlive * 4));
-                STEP(pb_d2h(ctx, lref.data(), d_lref.p, (size_t)nlive * 4));
+                // the host plans the band classes from each pair's bound (the aligner takes min(|a|,|b|) as its `read length`)
+                std::vector<int32_t> bound((size_t)nlive);
+                STEP(pb_d2h(ctx, bound.data(), d_lbound.p, (size_t)nlive * 4));
                 STEP(pb_sync(ctx));
-                // every candidate view of the pair is a suffix (or prefix) of the two sequences: min(|a|,|b|) <= min(len Q, len T)
-                for (int64_t i = 0; r == PB_OK && i < nlive; ++i) bound[i] = std::min(set->len[lq[i]], set->len[lref[i]]);
                 std::vector<uint8_t> irr((size_t)nlive, 0);
                 STEP(job->d_recs.alloc_zero(ctx, (size_t)nlive * sizeof(pb_pair_rec)));
                 STEP(d_stats.alloc_zero(ctx, 16));

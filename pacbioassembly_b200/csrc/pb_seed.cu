@@ -9,6 +9,8 @@
 // more than 24 care bits or more than PB_MAX_RUNS runs fall back to a multiplicative hash plus a stored
 // key per entry.  Within a bucket, entries are in the reference's list order (insertion order), which
 // is what makes "first successful candidate" (locator.cpp:79-88) reproducible.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "pb_internal.cuh"
@@ -585,10 +587,10 @@ __global__ void probe_count_kernel(IndexView iv, const uint32_t *__restrict__ ke
     cnt[q] = c;
 }
 
-__global__ void probe_gather_kernel(IndexView iv, const uint32_t *__restrict__ keys, int64_t nq, const int64_t *__restrict__ qoff,
-                                    int32_t *__restrict__ cand_pos, int32_t *__restrict__ cand_q)
+__global__ void probe_gather_tail_kernel(IndexView iv, const uint32_t *__restrict__ keys, int64_t q0, int64_t nq, const int64_t *__restrict__ qoff,
+                                         int32_t *__restrict__ cand_pos, int32_t *__restrict__ cand_q)
 {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t q = q0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; // queries [q0, nq)
     if (q >= nq) return;
     const int64_t o0 = qoff[q];
     if (qoff[q + 1] == o0) return;
@@ -601,6 +603,61 @@ __global__ void probe_gather_kernel(IndexView iv, const uint32_t *__restrict__ k
         cand_pos[o] = __ldg(iv.pos + s + t);
         cand_q[o] = (int32_t)q;
         ++o;
+    }
+}
+
+// Four queries per thread (exact, direct-address indexes).  One query per thread leaves the kernel latency-bound: a key load
+// from HBM, then two dependent random reads of the bucket table, with nothing else in flight.  Here a thread loads four
+// consecutive keys as one uint4 and issues the eight bucket-header loads back to back before it uses any of them, so four times
+// as many random reads are in flight per resident thread; counts leave as one uint4 store.
+__global__ void __launch_bounds__(256)
+probe_count4_kernel(IndexView iv, const uint4 *__restrict__ keys4, int64_t nq4, uint4 *__restrict__ cnt4)
+{
+    const int64_t q4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q4 >= nq4) return;
+    const uint4 k = keys4[q4];
+    const uint32_t b0 = bucket_of(iv.fn, k.x), b1 = bucket_of(iv.fn, k.y), b2 = bucket_of(iv.fn, k.z), b3 = bucket_of(iv.fn, k.w);
+    const uint32_t s0 = __ldg(iv.start + b0), e0 = __ldg(iv.start + b0 + 1);
+    const uint32_t s1 = __ldg(iv.start + b1), e1 = __ldg(iv.start + b1 + 1);
+    const uint32_t s2 = __ldg(iv.start + b2), e2 = __ldg(iv.start + b2 + 1);
+    const uint32_t s3 = __ldg(iv.start + b3), e3 = __ldg(iv.start + b3 + 1);
+    uint4 c; // keys with (sd & mask) == 0 are never inserted (locator.cpp:64)
+    c.x = k.x ? e0 - s0 : 0u;
+    c.y = k.y ? e1 - s1 : 0u;
+    c.z = k.z ? e2 - s2 : 0u;
+    c.w = k.w ? e3 - s3 : 0u;
+    cnt4[q4] = c;
+}
+
+__global__ void __launch_bounds__(256)
+probe_gather4_kernel(IndexView iv, const uint4 *__restrict__ keys4, int64_t nq4, const int64_t *__restrict__ qoff,
+                     int32_t *__restrict__ cand_pos, int32_t *__restrict__ cand_q)
+{
+    const int64_t q4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q4 >= nq4) return;
+    const int64_t q = q4 * 4;
+    int64_t o[5];
+#pragma unroll
+    for (int t = 0; t < 5; ++t) o[t] = qoff[q + t];
+    if (o[4] == o[0]) return; // none of the four has a candidate
+    const uint4 k4 = keys4[q4];
+    const uint32_t k[4] = {k4.x, k4.y, k4.z, k4.w};
+    uint32_t s[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) s[t] = o[t + 1] > o[t] ? __ldg(iv.start + bucket_of(iv.fn, k[t])) : 0u;
+    int32_t first[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) first[t] = o[t + 1] > o[t] ? __ldg(iv.pos + s[t]) : 0; // most lists hold one position
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int64_t n = o[t + 1] - o[t];
+        if (n <= 0) continue;
+        cand_pos[o[t]] = first[t];
+        cand_q[o[t]] = (int32_t)(q + t);
+        for (int64_t i = 1; i < n; ++i) {
+            cand_pos[o[t] + i] = __ldg(iv.pos + s[t] + i);
+            cand_q[o[t] + i] = (int32_t)(q + t);
+        }
     }
 }
 
@@ -719,16 +776,51 @@ static IndexView view_of(const pb_index *ix)
     return iv;
 }
 
+// count / gather launches: four queries per thread where the index is direct-address and the arrays are 16-byte aligned, the
+// remainder (and hashed indexes) one query per thread
+static int launch_probe_count(pb_ctx *ctx, const IndexView &iv, const uint32_t *d_keys, int64_t nq, uint32_t *d_cnt)
+{
+    int64_t done = 0;
+    if (!iv.key && nq >= 4 && (((uintptr_t)d_keys | (uintptr_t)d_cnt) & 15) == 0 && !getenv("PB_PROBE1")) {
+        const int64_t nq4 = nq / 4;
+        probe_count4_kernel<<<(unsigned)((nq4 + 255) / 256), 256, 0, ctx->stream>>>(iv, reinterpret_cast<const uint4 *>(d_keys), nq4,
+                                                                                 reinterpret_cast<uint4 *>(d_cnt));
+        PB_LAUNCH_CHECK(ctx);
+        done = nq4 * 4;
+    }
+    if (done < nq) {
+        probe_count_kernel<<<(unsigned)((nq - done + 255) / 256), 256, 0, ctx->stream>>>(iv, d_keys + done, nq - done, d_cnt + done);
+        PB_LAUNCH_CHECK(ctx);
+    }
+    return PB_OK;
+}
+
+static int launch_probe_gather(pb_ctx *ctx, const IndexView &iv, const uint32_t *d_keys, int64_t nq, const int64_t *d_qoff,
+                               int32_t *d_cand_pos, int32_t *d_cand_q)
+{
+    int64_t done = 0;
+    if (!iv.key && nq >= 4 && ((uintptr_t)d_keys & 15) == 0 && !getenv("PB_PROBE1")) {
+        const int64_t nq4 = nq / 4;
+        probe_gather4_kernel<<<(unsigned)((nq4 + 255) / 256), 256, 0, ctx->stream>>>(iv, reinterpret_cast<const uint4 *>(d_keys), nq4, d_qoff,
+                                                                                  d_cand_pos, d_cand_q);
+        PB_LAUNCH_CHECK(ctx);
+        done = nq4 * 4;
+    }
+    if (done < nq) {
+        probe_gather_tail_kernel<<<(unsigned)((nq - done + 255) / 256), 256, 0, ctx->stream>>>(iv, d_keys, done, nq, d_qoff, d_cand_pos, d_cand_q);
+        PB_LAUNCH_CHECK(ctx);
+    }
+    return PB_OK;
+}
+
 // keys (one per query, already on the device) -> counts -> exclusive offsets -> candidate arrays
 static int probe_and_gather(pb_ctx *ctx, const pb_index *ix, const uint32_t *d_keys, int64_t nq, ProbeOut *po)
 {
     DevBuf d_cnt, tmp;
     PB_TRY(d_cnt.alloc(ctx, (size_t)nq * 4));
-    const unsigned grid = (unsigned)((nq + 255) / 256);
     pb_timer_begin(ctx, PB_T_PROBE);
     IndexView iv = view_of(ix);
-    probe_count_kernel<<<grid, 256, 0, ctx->stream>>>(iv, d_keys, nq, d_cnt.as<uint32_t>());
-    PB_LAUNCH_CHECK(ctx);
+    PB_TRY(launch_probe_count(ctx, iv, d_keys, nq, d_cnt.as<uint32_t>()));
     PB_TRY(pb_scan_i64(ctx, d_cnt.as<uint32_t>(), po->d_qoff.as<int64_t>(), nq, tmp));
     int64_t ncand = 0;
     PB_TRY(pb_d2h(ctx, &ncand, po->d_qoff.as<int64_t>() + nq, 8));
@@ -738,8 +830,7 @@ static int probe_and_gather(pb_ctx *ctx, const pb_index *ix, const uint32_t *d_k
     PB_TRY(po->d_cand_pos.alloc(ctx, (size_t)std::max<int64_t>(ncand, 1) * 4));
     PB_TRY(po->d_cand_q.alloc(ctx, (size_t)std::max<int64_t>(ncand, 1) * 4));
     if (ncand) {
-        probe_gather_kernel<<<grid, 256, 0, ctx->stream>>>(iv, d_keys, nq, po->d_qoff.as<int64_t>(), po->d_cand_pos.as<int32_t>(), po->d_cand_q.as<int32_t>());
-        PB_LAUNCH_CHECK(ctx);
+        PB_TRY(launch_probe_gather(ctx, iv, d_keys, nq, po->d_qoff.as<int64_t>(), po->d_cand_pos.as<int32_t>(), po->d_cand_q.as<int32_t>()));
     }
     pb_timer_end(ctx, PB_T_PROBE);
     return PB_OK;
@@ -804,13 +895,11 @@ extern "C" int pb_probe_bulk_device(pb_ctx *ctx, const pb_index *ix, const pb_se
     cudaEvent_t ev[6];
     for (auto &e : ev) PB_CUDA(ctx, cudaEventCreate(&e));
     IndexView iv = view_of(ix);
-    const unsigned grid = (unsigned)((nq + 255) / 256);
     cudaEventRecord(ev[0], ctx->stream);
     PB_TRY(pb_seed_bulk_device(ctx, s, 0, nq, ix->mask, d_keys.as<uint32_t>()));
     cudaEventRecord(ev[1], ctx->stream);
     cudaEventRecord(ev[2], ctx->stream);
-    probe_count_kernel<<<grid, 256, 0, ctx->stream>>>(iv, d_keys.as<uint32_t>(), nq, d_cnt.as<uint32_t>());
-    PB_LAUNCH_CHECK(ctx);
+    PB_TRY(launch_probe_count(ctx, iv, d_keys.as<uint32_t>(), nq, d_cnt.as<uint32_t>()));
     cudaEventRecord(ev[3], ctx->stream);
     PB_TRY(pb_scan_i64(ctx, d_cnt.as<uint32_t>(), d_qoff.as<int64_t>(), nq, tmp));
     int64_t nc = 0;
@@ -819,8 +908,7 @@ extern "C" int pb_probe_bulk_device(pb_ctx *ctx, const pb_index *ix, const pb_se
     PB_TRY(d_pos.alloc(ctx, (size_t)std::max<int64_t>(nc, 1) * 4));
     PB_TRY(d_q.alloc(ctx, (size_t)std::max<int64_t>(nc, 1) * 4));
     cudaEventRecord(ev[4], ctx->stream);
-    probe_gather_kernel<<<grid, 256, 0, ctx->stream>>>(iv, d_keys.as<uint32_t>(), nq, d_qoff.as<int64_t>(), d_pos.as<int32_t>(), d_q.as<int32_t>());
-    PB_LAUNCH_CHECK(ctx);
+    PB_TRY(launch_probe_gather(ctx, iv, d_keys.as<uint32_t>(), nq, d_qoff.as<int64_t>(), d_pos.as<int32_t>(), d_q.as<int32_t>()));
     cudaEventRecord(ev[5], ctx->stream);
     PB_TRY(pb_sync(ctx));
     float a = 0, b = 0, c = 0;

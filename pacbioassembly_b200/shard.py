@@ -9,7 +9,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .api import LOCATE_DTYPE
+from .api import LOCATE_DTYPE, PAIR_DTYPE, PAIR_STATS
 
 
 def shard_ranges(lens: np.ndarray, world: int) -> list[tuple[int, int]]:
@@ -69,6 +69,38 @@ def gather_records(recs: np.ndarray, device: torch.device | str = "cpu", dst: in
         base += counts[r]
         parts.append(a)
     return np.concatenate(parts) if parts else np.zeros(0, dtype=LOCATE_DTYPE)
+
+
+# ---- all-vs-all (config 5): the QUERY reads are sharded, the set and its index are replicated -----------------------
+
+def reduce_pair_stats(stats: dict, device: torch.device | str = "cpu") -> dict:
+    """all-reduce (sum) of pb_pairs_job_stats over the ranks"""
+    t = torch.tensor([int(stats.get(k, 0)) for k in PAIR_STATS], dtype=torch.int64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t)
+    return dict(zip(PAIR_STATS, (int(x) for x in t.cpu().tolist())))
+
+
+def gather_pair_records(recs: np.ndarray, device: torch.device | str = "cpu", dst: int = 0):
+    """Gather every rank's pair records on `dst`.  Shards are contiguous query ranges and each rank's records come in ascending
+    (read_id, ref_id), so the concatenation in rank order is globally sorted; ids are set-wide already (no renumbering)."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return recs.copy()
+    rank = dist.get_rank()
+    n = torch.tensor([len(recs)], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1) * PAIR_DTYPE.itemsize
+    buf = torch.zeros(cap, dtype=torch.uint8, device=device)
+    raw = torch.from_numpy(np.ascontiguousarray(recs).view(np.uint8).reshape(-1).copy())
+    buf[: raw.numel()].copy_(raw)
+    out = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+    dist.gather(buf, out, dst=dst)
+    if rank != dst:
+        return None
+    return np.concatenate([out[r].cpu().numpy()[: counts[r] * PAIR_DTYPE.itemsize].view(PAIR_DTYPE).copy() for r in range(world)])
 
 
 class FinalReduction:

@@ -74,3 +74,99 @@ def test_locator_cli_matches_oracle(tmp_path, oracle):
         assert r.stdout.decode().splitlines() == lines
         assert len(lines) > 30
         assert b"totally %d sequences processed" % len(want) in r.stderr
+
+
+# ---------------------------------------------------------------------------------------------
+# assembler-side callers: spaced_seed -l ... -d dump  ->  visual_align
+# ---------------------------------------------------------------------------------------------
+
+def _kept_records(image, min_excl=500, max_excl=20000):
+    recs, p = [], 0
+    while p + 4 <= len(image):
+        l = int.from_bytes(image[p:p + 4], "little")
+        n = 4 + (l + 3) // 4
+        if min_excl < l < max_excl:
+            recs.append(image[p:p + n])
+        p += n
+    return recs
+
+
+def _dump_view(text, o, forward, n):
+    return bytes(text[o + i] if forward else text[o - i] for i in range(n))
+
+
+def test_spaced_seed_cli_locked_rounds(tmp_path, oracle):
+    """spaced_seed -l -f ref -d dump bin seedfile: per round the found lines, the dump file and stdout against the oracle's
+    trial loop (shipped seed_at behaviour) over the reads still in the pool; rounds end when every seed failed in a row"""
+    import re
+    from test_oracle import overlap_workload
+    ref, image = overlap_workload(401, 24000, 60)
+    (tmp_path / "reads.bin").write_bytes(image)
+    (tmp_path / "ref.txt").write_bytes(ref.tobytes() + b"\n3\n")
+    patterns = ["111**111*11*1111", "*111*11**11*1111*1"]
+    (tmp_path / "seeds.txt").write_text("".join(p + "\n" for p in patterns))
+    env = dict(os.environ, PB_SRAND="7")
+    r = subprocess.run([os.path.join(HOST, "spaced_seed"), "-l", "-f", "ref.txt", "-d", "dump.txt", "-r", "0.3", "reads.bin", "seeds.txt"],
+                       cwd=str(tmp_path), capture_output=True, timeout=600, env=env) if os.path.exists(os.path.join(HOST, "spaced_seed")) \
+        else pytest.skip("spaced_seed not built")
+    err = r.stderr.decode()
+    assert r.returncode == 0, err
+    masks = [oracle.parse_pattern(p.encode()) for p in patterns]
+    pool = list(enumerate(_kept_records(image)))
+    assert f"indices: size {len(pool)}\n" in err and f"ref_len: {len(ref)}\n" in err and "reference weight: 3\n" in err
+    rounds = re.split(r"-+ round \d+ -+\n", err)[1:]
+    assert len(rounds) >= 3  # at least one productive round, then both seeds failing in a row
+    dump_want, nfail, stdout_lines = [], 0, 0
+    for k, blk in enumerate(rounds):
+        seed = int(re.search(r"seed: ([0-9a-f]{8})", blk).group(1), 16)
+        assert seed in masks and (nfail == 0 or seed == masks[nfail - 1])  # spaced_seed.cpp:411
+        found_lines = re.findall(r"found (\d+) at cost (\d+):\tref_ml=(\d+),\tseg_ml=(\d+)", blk)
+        ix = oracle.index_build(ref, seed, policy=1)
+        want = oracle.overlap(ix, ref, b"".join(rec for _, rec in pool), seed, R=0.3, quirk=True, nthreads=4)
+        oracle.index_free(ix)
+        assert len(want) == len(pool)
+        exp = [(str(pool[i][0]), str(w["cost"]), str(w["matlen_a"]), str(w["matlen_b"])) for i, w in enumerate(want) if w["found"]]
+        assert [tuple(x) for x in found_lines] == exp, k
+        assert f"#matches: {len(exp)}\n" in blk
+        for i, w in enumerate(want):
+            if w["found"]:
+                fwd = w["dir"] == 1
+                seg = oracle.bin2text(pool[i][1])
+                dump_want.append(_dump_view(ref.tobytes(), int(w["ref_pos"]) + (0 if fwd else 15), fwd, int(w["matlen_a"])))
+                dump_want.append(_dump_view(seg, int(w["read_pos"]) + (0 if fwd else 15), fwd, int(w["matlen_b"])))
+        pool = [p for p, w in zip(pool, want) if not w["found"]]
+        nfail = 0 if exp else nfail + 1
+        if nfail == len(masks):
+            assert k == len(rounds) - 1
+            break
+        stdout_lines += 1
+    assert nfail == len(masks)
+    assert (tmp_path / "dump.txt").read_bytes() == b"".join(x + b"\n" for x in dump_want) and len(dump_want) > 20
+    assert r.stdout == (ref.tobytes() + b"\n") * stdout_lines  # a locked reference never evolves: the consensus is the reference
+    # unlocked mode is refused, not emulated
+    r2 = subprocess.run([os.path.join(HOST, "spaced_seed"), "-f", "ref.txt", "reads.bin", "seeds.txt"], cwd=str(tmp_path), capture_output=True)
+    assert r2.returncode != 0 and b"locked" in r2.stderr
+
+    # the dump feeds visual_align: ours, the reference's own source compiled against our headers, and the oracle's transcript
+    pairs = [(dump_want[i], dump_want[i + 1]) for i in range(0, len(dump_want), 2)]
+    good, expect = [], []
+    for rf, sg in pairs[:24]:
+        a = oracle.align(sg, rf, R=0.3)  # visual_align.cpp:41: align(&seg, &ref)
+        if a["ret"] <= 0:
+            continue
+        gr, gs, ir, isg = bytearray(), bytearray(), 0, 0
+        for op in a["ops"]:
+            if op == 1:
+                gr.append(rf[ir]); gs.append(sg[isg]); ir += 1; isg += 1
+            elif op == 2:
+                gr.append(rf[ir]); gs += b"-"; ir += 1
+            else:
+                gr += b"-"; gs.append(sg[isg]); isg += 1
+        good.append(rf + b"\n" + sg + b"\n")
+        expect.append(b"%d\n%s\n%s\n" % (a["cost"], bytes(gr), bytes(gs)))
+    assert len(good) > 10
+    v = run("visual_align", stdin=b"".join(good))
+    assert v.returncode == 0 and v.stdout == b"".join(expect)
+    if os.path.exists(os.path.join(HOST, "ref_visual_align")):
+        v2 = run("ref_visual_align", stdin=b"".join(good))
+        assert v2.returncode == 0 and v2.stdout == v.stdout

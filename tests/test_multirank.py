@@ -79,3 +79,62 @@ def test_world2_gloo_reduction_and_gather():
         p.join(180)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+# ---- all-vs-all (config 5): query reads sharded, set replicated ------------------------------------------------------
+
+def _pairs_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import cpu_libs
+    from allpairs_util import PAIR_FIELDS, allpairs_workload, expected_pairs, kept_texts, oracle_overlap_fn
+    from pacbioassembly_b200 import shard
+    from pacbioassembly_b200.api import PAIR_DTYPE
+
+    texts, image = allpairs_workload(361, 5000, 24)
+    kt = kept_texts(texts)
+    pairs, tot_ncand, tot_cells = expected_pairs(oracle_overlap_fn(cpu_libs.oracle(), 0xff3c3ffc), texts, image)
+
+    def records(lo, hi):  # what a rank's pb_overlap_all_run(q_first=lo, q_count=hi-lo) returns with found_only
+        rows = sorted((Q, T) for (T, Q), r in pairs.items() if lo <= Q < hi and r["found"])
+        out = np.zeros(len(rows), dtype=PAIR_DTYPE)
+        for i, (Q, T) in enumerate(rows):
+            r = pairs[(T, Q)]
+            out[i]["read_id"], out[i]["ref_id"], out[i]["found"] = Q, T, 1
+            for n in PAIR_FIELDS + ("ncand", "cells"):
+                out[i][n] = r[n]
+        return out
+
+    def stats(lo, hi):
+        mine = {k: r for k, r in pairs.items() if lo <= k[1] < hi}
+        return {"pairs": len(mine), "pairs_found": sum(int(r["found"]) for r in mine.values()),
+                "try_align_calls": sum(int(r["ncand"]) for r in mine.values()), "ref_cells": sum(int(r["cells"]) for r in mine.values())}
+
+    lens = np.array([len(t) for t in kt], dtype=np.int32)
+    lo, hi = shard.shard_ranges(lens, world)[rank]
+    tot = shard.reduce_pair_stats(stats(lo, hi))
+    allrecs = shard.gather_pair_records(records(lo, hi))
+    if rank == 0:
+        whole = records(0, len(kt))
+        ok = len(allrecs) == len(whole) > 20 and all((allrecs[n] == whole[n]).all() for n in PAIR_DTYPE.names)
+        ok = ok and tot["pairs"] == len(pairs) and tot["try_align_calls"] == tot_ncand and tot["ref_cells"] == tot_cells
+        ok = ok and tot["pairs_found"] == len(whole)
+        q.put(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_allpairs_sharding():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_pairs_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
