@@ -148,6 +148,11 @@ struct pb_index {
     DevBuf d_start; // [nbuckets+1] u32
     DevBuf d_pos;   // [nentries] i32, per bucket in the reference's list order
     DevBuf d_key;   // [nentries] u32 (only when !fn.exact)
+    // packed bucket headers (exact indexes): pk[b] = start[b] | min(count, pk_esc) << pk_shift -- one random 4-byte read per
+    // probe instead of two; a count of pk_esc or more is re-read exactly from start[]
+    DevBuf d_pk;
+    int pk_shift = 0;
+    uint32_t pk_esc = 0;
 };
 
 // ---------------------------------------------------------------------------------------------

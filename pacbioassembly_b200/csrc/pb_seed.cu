@@ -389,6 +389,14 @@ __global__ void index_finalize_kernel(const uint32_t *__restrict__ keys_all, Ent
     if (ekey) ekey[i] = keys_all[p];
 }
 
+__global__ void index_pack_kernel(const uint32_t *__restrict__ start, int64_t nbuckets, int shift, uint32_t esc, uint32_t *__restrict__ pk)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbuckets) return;
+    const uint32_t s = start[b], c = start[b + 1] - s;
+    pk[b] = s | (min(c, esc) << shift);
+}
+
 __global__ void index_nkeys_kernel(const uint32_t *__restrict__ start, int64_t nbuckets, const uint32_t *__restrict__ ekey,
                                    unsigned long long *__restrict__ nkeys)
 {
@@ -508,6 +516,19 @@ static int index_build_impl(pb_ctx *ctx, const pb_seqset *ref, int64_t seq, uint
         index_finalize_kernel<<<(unsigned)((ix->nentries + 255) / 256), 256, 0, ctx->stream>>>(d_keys.as<uint32_t>(), em, ix->nentries, ix->d_pos.as<int32_t>(), ix->fn.exact ? nullptr : ix->d_key.as<uint32_t>());
         ctx->launches++;
     }
+    if (ix->fn.exact) { // packed headers need at least 2 count bits above the start offset
+        int shift = 1;
+        while (shift < 32 && ((uint64_t)1 << shift) <= (uint64_t)ix->nentries) ++shift;
+        const char *force = getenv("PB_PK_SHIFT"); // test knob: fewer count bits, so that short lists already take the escape path
+        if (force && atoi(force) >= shift && atoi(force) <= 30) shift = atoi(force);
+        if (shift <= 30) {
+            ix->pk_shift = shift;
+            ix->pk_esc = (1u << (32 - shift)) - 1u;
+            TRYI(ix->d_pk.alloc(ctx, (size_t)nb * 4));
+            index_pack_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(ix->d_start.as<uint32_t>(), nb, shift, ix->pk_esc, ix->d_pk.as<uint32_t>());
+            ctx->launches++;
+        }
+    }
     TRYI(d_nkeys.alloc_zero(ctx, 16));
     index_nkeys_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(ix->d_start.as<uint32_t>(), nb, ix->fn.exact ? nullptr : ix->d_key.as<uint32_t>(), d_nkeys.as<unsigned long long>());
     ctx->launches++;
@@ -561,6 +582,9 @@ struct IndexView {
     const uint32_t *start;
     const int32_t *pos;
     const uint32_t *key; // NULL when exact
+    const uint32_t *pk;  // packed bucket headers, NULL when absent
+    int pk_shift;
+    uint32_t pk_esc;
     BucketFn fn;
 };
 
@@ -610,23 +634,48 @@ __global__ void probe_gather_tail_kernel(IndexView iv, const uint32_t *__restric
 // from HBM, then two dependent random reads of the bucket table, with nothing else in flight.  Here a thread loads four
 // consecutive keys as one uint4 and issues the eight bucket-header loads back to back before it uses any of them, so four times
 // as many random reads are in flight per resident thread; counts leave as one uint4 store.
+template <int V> // V uint4 groups (4*V queries) per thread
 __global__ void __launch_bounds__(256)
 probe_count4_kernel(IndexView iv, const uint4 *__restrict__ keys4, int64_t nq4, uint4 *__restrict__ cnt4)
 {
-    const int64_t q4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q4 >= nq4) return;
-    const uint4 k = keys4[q4];
-    const uint32_t b0 = bucket_of(iv.fn, k.x), b1 = bucket_of(iv.fn, k.y), b2 = bucket_of(iv.fn, k.z), b3 = bucket_of(iv.fn, k.w);
-    const uint32_t s0 = __ldg(iv.start + b0), e0 = __ldg(iv.start + b0 + 1);
-    const uint32_t s1 = __ldg(iv.start + b1), e1 = __ldg(iv.start + b1 + 1);
-    const uint32_t s2 = __ldg(iv.start + b2), e2 = __ldg(iv.start + b2 + 1);
-    const uint32_t s3 = __ldg(iv.start + b3), e3 = __ldg(iv.start + b3 + 1);
-    uint4 c; // keys with (sd & mask) == 0 are never inserted (locator.cpp:64)
-    c.x = k.x ? e0 - s0 : 0u;
-    c.y = k.y ? e1 - s1 : 0u;
-    c.z = k.z ? e2 - s2 : 0u;
-    c.w = k.w ? e3 - s3 : 0u;
-    cnt4[q4] = c;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+    if (g0 >= nq4) return;
+    uint32_t k[4 * V], s[4 * V], e[4 * V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const uint4 x = keys4[min(g0 + v, nq4 - 1)];
+        k[4 * v] = x.x; k[4 * v + 1] = x.y; k[4 * v + 2] = x.z; k[4 * v + 3] = x.w;
+    }
+    if (iv.pk) { // one random read per query: start and (capped) count in one word
+#pragma unroll
+        for (int t = 0; t < 4 * V; ++t) s[t] = __ldg(iv.pk + bucket_of(iv.fn, k[t]));
+#pragma unroll
+        for (int t = 0; t < 4 * V; ++t) {
+            uint32_t c = s[t] >> iv.pk_shift;
+            if (c == iv.pk_esc) { // long list: exact count from the offsets
+                const uint32_t b = bucket_of(iv.fn, k[t]);
+                c = __ldg(iv.start + b + 1) - __ldg(iv.start + b);
+            }
+            e[t] = c;
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4 * V; ++t) {
+            const uint32_t b = bucket_of(iv.fn, k[t]);
+            s[t] = __ldg(iv.start + b);
+            e[t] = __ldg(iv.start + b + 1) - s[t];
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        if (g0 + v >= nq4) break;
+        uint4 c; // keys with (sd & mask) == 0 are never inserted (locator.cpp:64)
+        c.x = k[4 * v] ? e[4 * v] : 0u;
+        c.y = k[4 * v + 1] ? e[4 * v + 1] : 0u;
+        c.z = k[4 * v + 2] ? e[4 * v + 2] : 0u;
+        c.w = k[4 * v + 3] ? e[4 * v + 3] : 0u;
+        cnt4[g0 + v] = c;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -644,7 +693,8 @@ probe_gather4_kernel(IndexView iv, const uint4 *__restrict__ keys4, int64_t nq4,
     const uint32_t k[4] = {k4.x, k4.y, k4.z, k4.w};
     uint32_t s[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) s[t] = o[t + 1] > o[t] ? __ldg(iv.start + bucket_of(iv.fn, k[t])) : 0u;
+    for (int t = 0; t < 4; ++t)
+        s[t] = o[t + 1] > o[t] ? (iv.pk ? __ldg(iv.pk + bucket_of(iv.fn, k[t])) & ((1u << iv.pk_shift) - 1u) : __ldg(iv.start + bucket_of(iv.fn, k[t]))) : 0u;
     int32_t first[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) first[t] = o[t + 1] > o[t] ? __ldg(iv.pos + s[t]) : 0; // most lists hold one position
@@ -772,6 +822,9 @@ static IndexView view_of(const pb_index *ix)
     iv.start = ix->d_start.as<uint32_t>();
     iv.pos = ix->d_pos.as<int32_t>();
     iv.key = ix->fn.exact ? nullptr : ix->d_key.as<uint32_t>();
+    iv.pk = ix->pk_esc ? ix->d_pk.as<uint32_t>() : nullptr;
+    iv.pk_shift = ix->pk_shift;
+    iv.pk_esc = ix->pk_esc;
     iv.fn = ix->fn;
     return iv;
 }
@@ -783,8 +836,16 @@ static int launch_probe_count(pb_ctx *ctx, const IndexView &iv, const uint32_t *
     int64_t done = 0;
     if (!iv.key && nq >= 4 && (((uintptr_t)d_keys | (uintptr_t)d_cnt) & 15) == 0 && !getenv("PB_PROBE1")) {
         const int64_t nq4 = nq / 4;
-        probe_count4_kernel<<<(unsigned)((nq4 + 255) / 256), 256, 0, ctx->stream>>>(iv, reinterpret_cast<const uint4 *>(d_keys), nq4,
-                                                                                 reinterpret_cast<uint4 *>(d_cnt));
+        const char *pv = getenv("PB_PROBE_V");
+        const int V = pv ? atoi(pv) : 2;
+        if (V >= 2) {
+            const int64_t nthr = (nq4 + 1) / 2;
+            probe_count4_kernel<2><<<(unsigned)((nthr + 255) / 256), 256, 0, ctx->stream>>>(iv, reinterpret_cast<const uint4 *>(d_keys), nq4,
+                                                                                        reinterpret_cast<uint4 *>(d_cnt));
+        } else {
+            probe_count4_kernel<1><<<(unsigned)((nq4 + 255) / 256), 256, 0, ctx->stream>>>(iv, reinterpret_cast<const uint4 *>(d_keys), nq4,
+                                                                                       reinterpret_cast<uint4 *>(d_cnt));
+        }
         PB_LAUNCH_CHECK(ctx);
         done = nq4 * 4;
     }

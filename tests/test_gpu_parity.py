@@ -1,6 +1,7 @@
 """GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle and the golden vectors
 (outputs of the unmodified reference).  Bit-exact: these are integer / byte / index results."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -626,3 +627,37 @@ def test_allpairs_errors(ctx):
     long_ref = ctx.seqset_one(workload.reference(5, 20017))
     with pytest.raises(PbError):
         ctx.index_set(long_ref, MASKS[0])
+
+
+def test_allpairs_long_runs(ctx, oracle):
+    """a tiny genome at very high coverage: every probe hits nearly every other read, so a query read's run of hits exceeds
+    the 8192 keys the regrouping sort holds in shared memory (in-place global-memory network), and every pair has hits"""
+    from allpairs_util import allpairs_workload
+    texts, image = allpairs_workload(371, 800, 150, mean=540.0, lo=520, hi=600, err=(0.01, 0.005, 0.005))
+    assert check_allpairs(ctx, oracle, texts, image, MASKS[0]) > 20000
+
+
+def test_packed_bucket_headers_escape(ctx, oracle):
+    """probe kernels read one packed word per query (start | capped count); with PB_PK_SHIFT=30 the cap is 3, so the
+    repeats of this reference take the exact-count escape path; results must not change"""
+    rng = np.random.default_rng(5)
+    unit = workload.reference(77, 3000)
+    ref = np.concatenate([unit] * 6 + [workload.reference(78, 20000)])  # every seed of `unit` has 6 positions
+    lens = workload.read_lengths(79, 40, mean=1200.0, sigma_log=0.4, lo=520, hi=3000)
+    txt, offs, lens, _ = workload.reads(80, ref, lens, 0.03, 0.02, 0.01, nthreads=1)
+    oix = oracle.index_build(ref, MASKS[0], 0)
+    want = oracle.locate(oix, ref, txt, offs, lens, MASKS[0], R=0.3, nthreads=4)
+    oracle.index_free(oix)
+    rs = ctx.seqset_one(ref)
+    for shift in (None, "30"):
+        if shift:
+            os.environ["PB_PK_SHIFT"] = shift
+        try:
+            ix = ctx.index(rs, MASKS[0])
+        finally:
+            os.environ.pop("PB_PK_SHIFT", None)
+        got = ctx.locate(ix, txt, offs, lens, R=0.3)
+        for n in ("nseq", "found", "j", "pos", "cost", "seg_len", "diag_cost", "matlen_a", "matlen_b", "nedit", "ncand", "cells"):
+            assert (got[n] == want[n]).all(), (shift, n)
+        ix.free()
+    assert want["found"].sum() > 10 and want["ncand"].max() >= 6

@@ -130,6 +130,7 @@ def main():
 
     # sampled targets against the CPU oracle
     checked = 0
+    cpu_s, cpu_targets = 0.0, 0
     if a.targets > 0:
         import cpu_libs
         o = cpu_libs.oracle()
@@ -151,13 +152,20 @@ def main():
                 for f in ("j", "ref_pos", "cost", "read_pos", "dir", "matlen_a", "matlen_b", "nedit", "ncand", "cells"):
                     assert int(got[q][f]) == int(w[f]), (t, q, f, int(got[q][f]), int(w[f]))
             checked += len(wf)
+            cpu_s += time.time() - t0
+            cpu_targets += 1
             print(f"target {t} (len {lens[t]}): {len(wf)} overlapping reads, bit-exact vs oracle ({time.time() - t0:.1f}s CPU)", flush=True)
     line = {"config": f"config5: all-vs-all, {a.reads} CLR reads (mean {a.mean:.0f}, ins 9/del 4/sub 2 %) from a {a.genome} bp genome, "
                       f"mask {a.mask}, R={R}, max_trial 32, queries {nq}",
             "n_gpus": world, "seconds": dt, "query_reads_per_s": nq / dt, "pairs_found": tot.get("pairs_found"),
             "stats": tot, "rank0_stage_ms": tm, "gpu_launches": launches, "index_build_s": t_index,
             "tcups_k3": tot.get("k3_cells", 0) / max(sum(v for k, v in tm.items() if k == "align"), 1e-9) / 1e9 if world == 1 else None,
-            "oracle_checked_pairs": checked}
+            "oracle_checked_pairs": checked,
+            # the reference's way to do this job: one seed map + one trial loop over all reads per target read (C port of the
+            # reference, all host threads); a reported baseline next to the GPU figure, extrapolated from the sampled targets
+            "cpu_baseline": None if not cpu_targets else {
+                "kind": "port", "cores": os.cpu_count(), "sample": f"{cpu_targets} target reads x {nq} query reads",
+                "seconds_per_target": cpu_s / cpu_targets, "est_seconds_all_targets": cpu_s / cpu_targets * a.reads}}
     print(json.dumps(line), flush=True)
     if a.out:
         with open(a.out, "w") as f:
