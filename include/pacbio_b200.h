@@ -256,7 +256,9 @@ typedef struct {
     int32_t seed_at_quirk; /* 1: dna_seq::seed_at's shipped pos%4==0 branch (byte offset pos, SURVEY Q-S1); needs a set made
                               by pb_seqset_from_bin (the raw image is what that branch reads); 0: encode(text+pos) */
     int32_t want_ops;
-    int32_t reserved;
+    int32_t ref_shift;     /* 0, or beg - pre of a grown reference (ref_seq.h:363-367): `ix` was built over the text [beg, end) of
+                              the current iteration while `ref` holds the whole readable text [pre, post); seed-map positions are
+                              then relative to beg and views are taken at position + ref_shift (ref_seq::get_accessor, :282-286) */
 } pb_overlap_params;
 
 PB_API void pb_overlap_default_params(pb_overlap_params *p);
@@ -268,6 +270,35 @@ PB_API void pb_overlap_default_params(pb_overlap_params *p);
  * recs: one entry per sequence of `reads`.  ops/ops_off as in pb_align_batch, slots of 3*len + 2*maxm + 16 bytes. */
 PB_API int pb_overlap_batch(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const pb_seqset *reads,
                             const pb_overlap_params *prm, pb_overlap_rec *recs, uint8_t *ops, const int64_t *ops_off);
+
+/* ---- consensus voting (ref_seq.h:25-41 apply_edits, :47-183 base_vote / vote_box, :207-256 ctor / append / prepend,
+ *      :317-362 evolve / elect) ---------------------------------------------------------------------------------- */
+
+typedef struct pb_consensus pb_consensus; /* ref_seq's voting state on the device: the text [pre, post) and one vote box per base */
+
+/* ref_seq(const char *ptxt, int len, bool l, int w): every base starts with `weight` votes and total = 1 (ref_seq.h:218-225) */
+PB_API int pb_consensus_create(pb_ctx *ctx, const char *text, int64_t len, int weight, pb_consensus **out);
+PB_API void pb_consensus_free(pb_consensus *c);
+PB_API int64_t pb_consensus_length(const pb_consensus *c); /* ref_seq::length() = end - beg */
+/* *before = beg - pre (text grown in front of the current iteration's origin), *total = post - pre */
+PB_API int pb_consensus_extent(const pb_consensus *c, int64_t *before, int64_t *total);
+/* the text [beg, end) (full == 0) or [pre, post) (full != 0), NUL-terminated; cap > its length */
+PB_API int pb_consensus_text(pb_ctx *ctx, const pb_consensus *c, int full, char *out, size_t cap);
+/* the same text as a one-sequence pb_seqset (device to device): what pb_index_build / pb_overlap_batch take as reference */
+PB_API int pb_consensus_seqset(pb_ctx *ctx, const pb_consensus *c, int full, pb_seqset **out);
+/* ref_seq::append / prepend (ref_seq.h:227-243): the text a read contributes beyond an end of the reference */
+PB_API int pb_consensus_append(pb_ctx *ctx, pb_consensus *c, const char *seg, int32_t len);
+PB_API int pb_consensus_prepend(pb_ctx *ctx, pb_consensus *c, const char *seg, int32_t len);
+/* ref_seq::elect (ref_seq.h:351-361) for every found record of a pb_overlap_batch call made with want_ops: recs / ops / ops_off
+ * as that call returned them, `reads` the set it ran on (edit.val = the read's base).  All matches must have been aligned against
+ * the text as it is now; votes commute, so the batch is one launch. */
+PB_API int pb_consensus_elect_batch(pb_ctx *ctx, pb_consensus *c, const pb_seqset *reads, const pb_overlap_rec *recs, int64_t n,
+                                    const uint8_t *ops, const int64_t *ops_off);
+/* ref_seq::evolve (ref_seq.h:317-348): suppliments above half the votes become bases, bases at or below half are dropped
+ * (their votes move to the suppliment in front of them), the text is rewritten from the winners; pre = beg, post = end after */
+PB_API int pb_consensus_evolve(pb_ctx *ctx, pb_consensus *c);
+/* the vote boxes of [pre, post), nine ints each: selection A,C,G,T, suppliment A,C,G,T, total */
+PB_API int pb_consensus_votes(pb_ctx *ctx, const pb_consensus *c, int32_t *out9, int64_t cap_boxes);
 
 /* ---- all-vs-all overlap detection (BASELINE config 5) --------------------------------- */
 

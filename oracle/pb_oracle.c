@@ -538,3 +538,223 @@ int64_t pbo_overlap(const pbo_index *ix, const char *ref, size_t ref_len, const 
     free(rec_off);
     return (int64_t)nk;
 }
+
+/* ============================================================================================================
+ * Consensus voting and the UNLOCKED assembler rounds (ref_seq.h:25-41 apply_edits, :47-183 base_vote / vote_box,
+ * :207-256 ref_seq ctor / append / prepend, :259-276 try_align, :317-362 evolve / elect; spaced_seed.cpp:408-453).
+ * ============================================================================================================ */
+
+typedef struct { uint16_t sel[4], sup[4]; int32_t total; } vbox; /* vote_box: selection, suppliment (unsigned short), total */
+
+struct pbo_cons {
+    char *txt;          /* txt_buf: [pre, post) is readable; beg/end delimit the current iteration's reference */
+    size_t cap;         /* txt has 3*cap bytes; beg starts at cap (MAX_SEQ_LEN in the reference) */
+    long beg, end, pre, post;
+    vbox *box;          /* consensus list, box[0] <-> txt[pre] */
+    size_t nbox, boxcap;
+};
+
+static int vmax(const uint16_t *v) { int m = v[0]; for (int k = 1; k < 4; ++k) if (v[k] > m) m = v[k]; return m; }
+static char vwinner(const uint16_t *v) { int m = vmax(v); return m == v[0] ? 'A' : (m == v[1] ? 'C' : (m == v[2] ? 'G' : 'T')); } /* :94-98 */
+
+static void cons_reserve(pbo_cons *c, size_t n)
+{
+    if (n <= c->boxcap) return;
+    size_t nc = c->boxcap ? c->boxcap : 1024;
+    while (nc < n) nc *= 2;
+    c->box = (vbox *)realloc(c->box, nc * sizeof(vbox));
+    c->boxcap = nc;
+}
+
+pbo_cons *pbo_cons_create(const char *text, size_t len, int weight, size_t cap)
+{ /* ref_seq(const char*, int, bool, int w), ref_seq.h:218-225: vote_box(c, w) has selection[C2I(c)] = w and total = 1 */
+    pbo_cons *c = (pbo_cons *)calloc(1, sizeof *c);
+    c->cap = cap < len + 16 ? len + 16 : cap;
+    c->txt = (char *)calloc(3 * c->cap, 1);
+    c->beg = c->pre = (long)c->cap;
+    c->end = c->post = c->beg + (long)len;
+    memcpy(c->txt + c->beg, text, len);
+    cons_reserve(c, len + 1);
+    for (size_t i = 0; i < len; ++i) {
+        vbox b; memset(&b, 0, sizeof b);
+        b.sel[pbo_c2i(text[i])] = (uint16_t)weight;
+        b.total = 1;
+        c->box[i] = b;
+    }
+    c->nbox = len;
+    return c;
+}
+void pbo_cons_free(pbo_cons *c) { if (c) { free(c->txt); free(c->box); free(c); } }
+size_t pbo_cons_length(const pbo_cons *c) { return (size_t)(c->end - c->beg); }     /* ref_seq::length() */
+size_t pbo_cons_extent(const pbo_cons *c, long *before) { if (before) *before = c->beg - c->pre; return (size_t)(c->post - c->pre); }
+const char *pbo_cons_text(const pbo_cons *c) { return c->txt + c->beg; }
+
+void pbo_cons_append(pbo_cons *c, const char *seg, int len)
+{ /* ref_seq.h:227-233 */
+    if (len <= 0) return;
+    memmove(c->txt + c->post, seg, (size_t)len);
+    c->post += len;
+    cons_reserve(c, c->nbox + (size_t)len);
+    for (int i = 0; i < len; ++i) {
+        vbox b; memset(&b, 0, sizeof b);
+        b.sel[pbo_c2i(seg[i])] = 1; b.total = 1;
+        c->box[c->nbox++] = b;
+    }
+}
+void pbo_cons_prepend(pbo_cons *c, const char *seg, int len)
+{ /* ref_seq.h:235-243: the text is copied in order, the boxes are pushed to the front last char first */
+    if (len <= 0) return;
+    c->pre -= len;
+    memmove(c->txt + c->pre, seg, (size_t)len);
+    cons_reserve(c, c->nbox + (size_t)len);
+    memmove(c->box + len, c->box, c->nbox * sizeof(vbox));
+    for (int i = 0; i < len; ++i) {
+        vbox b; memset(&b, 0, sizeof b);
+        b.sel[pbo_c2i(seg[i])] = 1; b.total = 1;
+        c->box[i] = b;
+    }
+    c->nbox += (size_t)len;
+}
+
+void pbo_cons_elect(pbo_cons *c, int pos, const uint8_t *ops, const char *vals, int nedit, int forward)
+{ /* elect (ref_seq.h:351-361) + apply_edits (:25-41): both iterators start on the box of text position pos */
+    long idx = pos + c->beg - c->pre;
+    const long step = forward ? 1 : -1;
+    for (int k = 0; k < nedit; ++k) {
+        if (ops[k] == PBO_DELETE) { c->box[idx].total++; idx += step; }
+        else if (ops[k] == PBO_MATCH) { c->box[idx].sel[pbo_c2i(vals[k])]++; c->box[idx].total++; idx += step; }
+        else { /* INSERT: forward "--it; supply; ++it" = the box before; a reverse_iterator supplies the box it stands on */
+            const long t = forward ? idx - 1 : idx;
+            if (t >= 0 && t < (long)c->nbox) c->box[t].sup[pbo_c2i(vals[k])]++; /* t < 0 is undefined behaviour in the reference */
+        }
+    }
+}
+
+void pbo_cons_evolve(pbo_cons *c)
+{ /* ref_seq.h:317-348 */
+    vbox *out = (vbox *)malloc((2 * c->nbox + 2) * sizeof(vbox));
+    size_t no = 0; /* boxes kept so far = the list in front of `cur` */
+    c->end = c->pre = c->beg = (long)c->cap;
+    char *p = c->txt + c->beg;
+    for (size_t i = 0; i < c->nbox; ++i) {
+        vbox cur = c->box[i], ins;
+        int has_ins = 0;
+        if (2 * vmax(cur.sup) > cur.total) { /* has_supply(0.5): split the suppliment off as a box of its own, right after */
+            memset(&ins, 0, sizeof ins);
+            memcpy(ins.sel, cur.sup, sizeof cur.sup);
+            ins.total = cur.total;
+            memset(cur.sup, 0, sizeof cur.sup);
+            has_ins = 1;
+        }
+        if (2 * vmax(cur.sel) > cur.total) { /* is_valid(0.5) */
+            *p++ = vwinner(cur.sel); ++c->end;
+            out[no++] = cur;
+        } else if (no > 0) { /* erased: its selection is absorbed by the previous box's suppliment */
+            for (int k = 0; k < 4; ++k) out[no - 1].sup[k] = (uint16_t)(out[no - 1].sup[k] + cur.sel[k]);
+        }
+        if (has_ins) { /* visited next: no suppliment, and valid by the same inequality that created it */
+            *p++ = vwinner(ins.sel); ++c->end;
+            out[no++] = ins;
+        }
+    }
+    c->post = c->end;
+    free(c->box);
+    c->box = out; c->nbox = no; c->boxcap = 2 * c->nbox + 2;
+    if (c->boxcap < no) c->boxcap = no;
+}
+
+int64_t pbo_cons_votes(const pbo_cons *c, int32_t *out9)
+{ /* dump of the list for tests: per box sel[4], sup[4], total */
+    if (out9)
+        for (size_t i = 0; i < c->nbox; ++i) {
+            for (int k = 0; k < 4; ++k) { out9[9 * i + k] = c->box[i].sel[k]; out9[9 * i + 4 + k] = c->box[i].sup[k]; }
+            out9[9 * i + 8] = c->box[i].total;
+        }
+    return (int64_t)c->nbox;
+}
+
+/* The assembler's rounds with an UNLOCKED reference (spaced_seed.cpp:408-453): round r uses round_masks[r] (the reference
+ * draws them with rand()); every remaining read runs the trial loop against the CURRENT text -- a success votes
+ * (elect) and, when the whole reference view was consumed, grows the text (append / prepend), so later reads of the same
+ * round see the longer text (ref_seq.h:266-276); found reads leave the pool; evolve() closes the round.
+ * cons_out receives each round's consensus (cons_stride bytes apart, cons_len[r] chars); found_round[k] = round (1-based) in
+ * which kept read k was found (0: never), recs[k] = the record of that success.  Returns the number of kept reads. */
+int64_t pbo_assemble(const char *ref_text, size_t ref_len, int weight, const uint8_t *bin, size_t bin_bytes, int min_excl,
+                     int max_excl, const uint32_t *round_masks, int nrounds, double R, int max_trial, int min_overlap,
+                     int maxn, int maxm, int quirk, char *cons_out, size_t cons_stride, int32_t *cons_len,
+                     int32_t *found_round, pbo_overlap_rec *recs)
+{
+    size_t cap = 1024, nk = 0;
+    size_t *rec_off = (size_t *)malloc(cap * sizeof *rec_off);
+    for (size_t p = 0; p + 4 <= bin_bytes;) {
+        uint32_t l;
+        memcpy(&l, bin + p, 4);
+        if ((long)l > min_excl && (long)l < max_excl) {
+            if (nk == cap) { cap *= 2; rec_off = (size_t *)realloc(rec_off, cap * sizeof *rec_off); }
+            rec_off[nk++] = p;
+        }
+        p += 4 + ((size_t)l + 3) / 4;
+    }
+    if (!cons_out) { free(rec_off); return (int64_t)nk; }
+    for (size_t k = 0; k < nk; ++k) { found_round[k] = 0; memset(&recs[k], 0, sizeof recs[k]); recs[k].id = (int32_t)k; }
+    pbo_cons *c = pbo_cons_create(ref_text, ref_len, weight, 800000);
+    dp_ws ws = {0, 0, 0};
+    char *txt = (char *)malloc((size_t)max_excl + 64);
+    size_t ecap = (size_t)max_excl * 2 + (size_t)maxm + 64;
+    uint8_t *ops = (uint8_t *)malloc(ecap);
+    char *vals = (char *)malloc(ecap);
+    for (int r = 0; r < nrounds; ++r) {
+        const uint32_t mask = round_masks[r];
+        pbo_index *ix = pbo_index_build(c->txt + c->beg, (size_t)(c->end - c->beg), mask, 1); /* get_seedmap */
+        for (size_t k = 0; k < nk; ++k) {
+            if (found_round[k]) continue; /* erased from indices */
+            const size_t rec = rec_off[k];
+            uint32_t slen;
+            memcpy(&slen, bin + rec, 4);
+            pbo_bin2text(bin + rec, txt, (size_t)max_excl + 64);
+            int found = 0;
+            for (int j = 0; j < max_trial && !found; ++j)
+                for (int side = 0; side < 2 && !found; ++side) {
+                    const int forward = side == 0;
+                    const long pos = forward ? j : (long)slen - j - 16;
+                    const uint32_t key = image_seed_at(bin, bin_bytes, rec, (int)pos, quirk) & mask;
+                    const int32_t *plist;
+                    const size_t cnt = pbo_index_find(ix, key, &plist);
+                    if (!cnt) continue;
+                    const long s_offset = forward ? pos : pos + 15;
+                    const long s_len = forward ? (long)slen - s_offset : s_offset + 1;
+                    if (s_len < min_overlap) continue;
+                    for (size_t q = 0; q < cnt && !found; ++q) {
+                        const long r_offset = forward ? plist[q] : plist[q] + 15;
+                        /* get_accessor (ref_seq.h:282-286) on the text as it is NOW */
+                        const long r_len = forward ? c->post - c->beg - r_offset : r_offset + c->beg - c->pre + 1;
+                        pbo_align_out ao;
+                        recs[k].ncand++;
+                        const int ret = align_ws(&ws, c->txt + c->beg + r_offset, (int)r_len, forward ? 1 : -1, txt + s_offset, (int)s_len,
+                                                 forward ? 1 : -1, R, maxn, maxm, &ao, ops, vals, ecap);
+                        recs[k].cells += ao.cells;
+                        if (ret < 0 || ao.matlen_a < min_overlap) continue;
+                        found = 1;
+                        pbo_cons_elect(c, (int)r_offset, ops, vals, ao.nedit, forward); /* ref_seq.h:266 */
+                        if (ao.matlen_a == r_len) { /* the read runs past the reference: grow (ref_seq.h:267-275) */
+                            const int add_len = (int)s_len - ao.matlen_b;
+                            if (forward) pbo_cons_append(c, txt + s_offset + ao.matlen_b, add_len);
+                            else pbo_cons_prepend(c, txt, add_len); /* pt(length-1) of a backward accessor = the read's first base */
+                        }
+                        found_round[k] = r + 1;
+                        recs[k].found = 1; recs[k].j = j; recs[k].ref_pos = plist[q]; recs[k].cost = ao.cost; recs[k].read_pos = (int32_t)pos;
+                        recs[k].dir = forward ? 1 : -1; recs[k].matlen_a = ao.matlen_a; recs[k].matlen_b = ao.matlen_b; recs[k].nedit = ao.nedit;
+                    }
+                }
+        }
+        pbo_index_free(ix);
+        pbo_cons_evolve(c);
+        const size_t n = (size_t)(c->end - c->beg);
+        cons_len[r] = (int32_t)n;
+        memcpy(cons_out + (size_t)r * cons_stride, c->txt + c->beg, n < cons_stride ? n : cons_stride);
+    }
+    free(txt); free(ops); free(vals); free(rec_off);
+    dp_ws_free(&ws);
+    pbo_cons_free(c);
+    return (int64_t)nk;
+}

@@ -153,6 +153,27 @@ int64_t pbo_overlap(const pbo_index *ix, const char *ref, size_t ref_len, const 
                     int min_excl, int max_excl, uint32_t mask, double R, int max_trial, int min_overlap, int maxn,
                     int maxm, int quirk, int nthreads, pbo_overlap_rec *recs);
 
+/* ---- consensus voting and the unlocked assembler rounds (ref_seq.h:25-41,47-183,207-276,317-362; spaced_seed.cpp:408-453) ---- */
+
+typedef struct pbo_cons pbo_cons; /* ref_seq's voting state: text buffer with pre/beg/end/post and the vote_box list */
+
+pbo_cons *pbo_cons_create(const char *text, size_t len, int weight, size_t cap); /* ref_seq(text, len, false, w) */
+void pbo_cons_free(pbo_cons *c);
+size_t pbo_cons_length(const pbo_cons *c);                 /* ref_seq::length() = end - beg */
+size_t pbo_cons_extent(const pbo_cons *c, long *before);   /* post - pre; *before = beg - pre */
+const char *pbo_cons_text(const pbo_cons *c);              /* txt_buf + beg */
+void pbo_cons_append(pbo_cons *c, const char *seg, int len);
+void pbo_cons_prepend(pbo_cons *c, const char *seg, int len);
+/* elect(pos, edits, nedit, forward): ops/vals as produced by pbo_align (vals[k] = seg_b's element under MATCH / INSERT) */
+void pbo_cons_elect(pbo_cons *c, int pos, const uint8_t *ops, const char *vals, int nedit, int forward);
+void pbo_cons_evolve(pbo_cons *c);
+int64_t pbo_cons_votes(const pbo_cons *c, int32_t *out9);  /* per box: sel[4], sup[4], total; returns the number of boxes */
+
+int64_t pbo_assemble(const char *ref_text, size_t ref_len, int weight, const uint8_t *bin, size_t bin_bytes, int min_excl,
+                     int max_excl, const uint32_t *round_masks, int nrounds, double R, int max_trial, int min_overlap,
+                     int maxn, int maxm, int quirk, char *cons_out, size_t cons_stride, int32_t *cons_len,
+                     int32_t *found_round, pbo_overlap_rec *recs);
+
 #ifdef __cplusplus
 }
 #endif

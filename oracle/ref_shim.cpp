@@ -22,6 +22,7 @@
 #include <stdint.h>
 #include <pthread.h>
 #include <new>
+#include <vector>
 
 /* spaced_seed.cpp is a program; rename its main so parse_pattern() (spaced_seed.cpp:166-180)
  * can be called as compiled from the reference source. */
@@ -341,6 +342,80 @@ int64_t pbref_overlap(const char *ref_text, long ref_len, unsigned char *bin, lo
     free(txt); free(al);
     delete map; delete pr;
     return k;
+}
+
+/* ---- unlocked assembler rounds through the reference's OWN ref_seq (voting, growth, evolve) --------------------------
+ * ref_seq::try_align (elect / append / prepend, ref_seq.h:259-276), ref_seq::evolve (:317-348), get_seedmap, seed_at, bin2text
+ * and align are the reference's; the loops of spaced_seed.cpp:408-453 and :261-299 are restated (fresh-state shim before every
+ * align, seeds given per round instead of rand()).  Same outputs as pbo_assemble. */
+int64_t pbref_assemble(const char *ref_text, long ref_len, int weight, unsigned char *bin, long bin_bytes, int min_excl, int max_excl,
+                       const unsigned *round_masks, int nrounds, double R, int max_trial, char *cons_out, long cons_stride,
+                       int32_t *cons_len, int32_t *found_round, overlap_rec *recs)
+{
+    if (ref_len >= MAX_SEQ_LEN) return -1;
+    std::vector<long> rec_off;
+    for (long off = 0; off + 4 <= bin_bytes;) {
+        unsigned slen = *((unsigned *)(bin + off));
+        if (slen > (unsigned)min_excl && slen < (unsigned)max_excl) rec_off.push_back(off);
+        off += 4 + ((long)slen + 3) / 4;
+    }
+    const int64_t nk = (int64_t)rec_off.size();
+    if (!cons_out) return nk;
+    for (int64_t k = 0; k < nk; ++k) { found_round[k] = 0; memset(&recs[k], 0, sizeof recs[k]); recs[k].id = (int32_t)k; }
+    ref_seq *pr = new ref_seq(ref_text, (int)ref_len, false, weight); /* unlocked */
+    hash_table *map = new hash_table(1 << 20);
+    t_aligner *al = fresh_aligner<t_aligner>(R);
+    char *txt = (char *)malloc(MAX_READ_LEN + 64);
+    for (int r = 0; r < nrounds; ++r) {
+        const unsigned mask = round_masks[r];
+        pr->get_seedmap(*map, mask);
+        for (int64_t k = 0; k < nk; ++k) {
+            if (found_round[k]) continue;
+            const long off = rec_off[k];
+            unsigned slen = *((unsigned *)(bin + off));
+            dna_seq::bin2text(bin + off, txt, slen + 1);
+            overlap_rec *out = &recs[k];
+            bool found = false;
+            for (int j = 0; j < max_trial && !found; ++j)
+                for (int side = 0; side < 2 && !found; ++side) {
+                    bool forward = side == 0;
+                    long pos = forward ? j : (long)slen - j - 16;
+                    sm_it sit = map->find(dna_seq::seed_at(bin + off, (int)pos) & mask);
+                    if (sit == map->end()) continue;
+                    int s_offset = forward ? pos : pos + 16 - 1;
+                    int s_len = forward ? (int)slen - s_offset : s_offset + 1;
+                    seq_accessor ac_seg(txt + s_offset, forward, s_len);
+                    if (s_len < OVERLAP_MIN) continue;
+                    for (std::list<int>::iterator it = sit->second.begin(); it != sit->second.end() && !found; ++it) {
+                        int r_offset = forward ? (*it) : (*it) + 16 - 1;
+                        seq_accessor ac_ref = pr->get_accessor(r_offset, forward);
+                        int la, lb, md;
+                        if (ac_seg.length() >= ac_ref.length()) { la = ac_ref.length(); md = 1 + (int)(la * R); lb = std::min(ac_seg.length(), la + md); }
+                        else { lb = ac_seg.length(); md = 1 + (int)(lb * R); la = std::min(ac_ref.length(), lb + md); }
+                        out->ncand++;
+                        if (la < MAX_READ_LEN + MAX_DIFF_LEN && md < MAX_DIFF_LEN) {
+                            al->max_dst = md;
+                            for (int i = lb + 1; i <= la; ++i) al->set_cost(i, i, 0);
+                        }
+                        al->R = R;
+                        if (pr->try_align(al, r_offset, &ac_seg)) { /* votes and grows */
+                            found = true;
+                            found_round[k] = r + 1;
+                            out->found = 1; out->j = j; out->ref_pos = *it; out->cost = al->final_cost(); out->read_pos = (int32_t)pos;
+                            out->dir = forward ? 1 : -1; out->matlen_a = al->matlen_a; out->matlen_b = al->matlen_b; out->nedit = al->nedit;
+                        }
+                    }
+                }
+        }
+        pr->evolve();
+        const int n = (int)pr->length();
+        cons_len[r] = n;
+        seq_accessor ac = pr->get_accessor(0, true);
+        for (int i = 0; i < n && i < cons_stride; ++i) cons_out[(long)r * cons_stride + i] = ac.next();
+    }
+    free(txt); free(al);
+    delete map; delete pr;
+    return nk;
 }
 
 } /* extern "C" */

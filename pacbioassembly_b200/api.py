@@ -37,7 +37,7 @@ class LocateParams(C.Structure):
 
 class OverlapParams(C.Structure):
     _fields_ = [("R", C.c_double), ("max_trial", C.c_int32), ("min_overlap", C.c_int32), ("maxn", C.c_int32),
-                ("maxm", C.c_int32), ("seed_at_quirk", C.c_int32), ("want_ops", C.c_int32), ("reserved", C.c_int32)]
+                ("maxm", C.c_int32), ("seed_at_quirk", C.c_int32), ("want_ops", C.c_int32), ("ref_shift", C.c_int32)]
 
 
 class PbError(RuntimeError):
@@ -107,6 +107,17 @@ def lib() -> C.CDLL:
         "pb_locate_job_free": (None, [vp]),
         "pb_overlap_default_params": (None, [P(OverlapParams)]),
         "pb_overlap_batch": (C.c_int, [vp, vp, vp, i64, vp, P(OverlapParams), vp, vp, vp]),
+        "pb_consensus_create": (C.c_int, [vp, vp, i64, C.c_int, P(vp)]),
+        "pb_consensus_free": (None, [vp]),
+        "pb_consensus_length": (i64, [vp]),
+        "pb_consensus_extent": (C.c_int, [vp, P(i64), P(i64)]),
+        "pb_consensus_text": (C.c_int, [vp, vp, C.c_int, vp, sz]),
+        "pb_consensus_seqset": (C.c_int, [vp, vp, C.c_int, P(vp)]),
+        "pb_consensus_append": (C.c_int, [vp, vp, vp, i32]),
+        "pb_consensus_prepend": (C.c_int, [vp, vp, vp, i32]),
+        "pb_consensus_elect_batch": (C.c_int, [vp, vp, vp, vp, i64, vp, vp]),
+        "pb_consensus_evolve": (C.c_int, [vp, vp]),
+        "pb_consensus_votes": (C.c_int, [vp, vp, vp, i64]),
         "pb_index_build_set": (C.c_int, [vp, vp, u32, P(vp)]),
         "pb_overlap_all_run": (C.c_int, [vp, vp, vp, i64, i64, P(OverlapParams), P(vp)]),
         "pb_pairs_job_stats": (C.c_int, [vp, vp]),
@@ -344,11 +355,12 @@ class Context:
             return recs, [ops[ops_off[k]: ops_off[k] + int(recs["nedit"][k])] for k in range(nk)]
         return recs
 
-    def overlap(self, index: "Index", reads: "SeqSet", want_ops: bool = False, **params):
-        """spaced_seed.cpp:424-436 / try_align: head and tail trials of every read against a REFSEQ-policy index"""
+    def overlap(self, index: "Index", reads: "SeqSet", want_ops: bool = False, ref: "SeqSet | None" = None, **params):
+        """spaced_seed.cpp:424-436 / try_align: head and tail trials of every read against a REFSEQ-policy index.
+        ref (with ref_shift=beg-pre): the whole text of a reference that has grown beyond the indexed [beg, end)."""
         prm = OverlapParams()
         self._L.pb_overlap_default_params(C.byref(prm))
-        prm.want_ops = int(want_ops)
+        prm.want_ops = 1 if want_ops else 0
         for k, v in params.items():
             setattr(prm, k, v)
         n = len(reads)
@@ -361,11 +373,20 @@ class Context:
             if n:
                 np.cumsum(slots[:-1], out=ops_off[1:])
             ops = np.zeros(int(slots.sum()) + 16, dtype=np.uint8)
-        self.check(self._L.pb_overlap_batch(self.h, index.h, index.ref.h, index.seq, reads.h, C.byref(prm), _ptr(recs),
+        self.check(self._L.pb_overlap_batch(self.h, index.h, (ref or index.ref).h, 0 if ref else index.seq, reads.h, C.byref(prm), _ptr(recs),
                                             _ptr(ops), _ptr(ops_off)))
+        if want_ops == "raw":  # the buffers as pb_consensus_elect_batch takes them
+            return recs, ops, ops_off
         if want_ops:
             return recs, [ops[ops_off[k]: ops_off[k] + int(recs["nedit"][k])] for k in range(n)]
         return recs
+
+    # ---- consensus voting ---------------------------------------------------------------------------
+    def consensus(self, text, weight: int = 1) -> "Consensus":
+        t = _u8(text)
+        h = C.c_void_p()
+        self.check(self._L.pb_consensus_create(self.h, _ptr(t) if len(t) else None, len(t), weight, C.byref(h)))
+        return Consensus(self, h)
 
     # ---- all-vs-all ------------------------------------------------------------------------------
     def index_set(self, seqs: "SeqSet", mask: int) -> "Index":
@@ -449,6 +470,68 @@ class SeqSet:
         n, ms = C.c_int64(0), C.c_float(0)
         self.ctx.check(self.ctx._L.pb_seed_extract_all_device(self.ctx.h, self.h, mask, C.byref(n), C.byref(ms)))
         return n.value, ms.value
+
+
+class Consensus:
+    """ref_seq's voting state on the device (ref_seq.h:47-183, 317-362): text [pre, post) + one vote box per base."""
+
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+        ctx._children.add(self)
+
+    def free(self):
+        if self.h and self.ctx.h:
+            self.ctx._L.pb_consensus_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return int(self.ctx._L.pb_consensus_length(self.h))
+
+    def extent(self) -> tuple[int, int]:
+        """(beg - pre, post - pre)"""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self.ctx.check(self.ctx._L.pb_consensus_extent(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def text(self, full: bool = False) -> bytes:
+        n = self.extent()[1] if full else len(self)
+        out = np.zeros(n + 1, dtype=np.uint8)
+        self.ctx.check(self.ctx._L.pb_consensus_text(self.ctx.h, self.h, int(full), _ptr(out), n + 1))
+        return out[:n].tobytes()
+
+    def seqset(self, full: bool = False) -> "SeqSet":
+        h = C.c_void_p()
+        self.ctx.check(self.ctx._L.pb_consensus_seqset(self.ctx.h, self.h, int(full), C.byref(h)))
+        return SeqSet(self.ctx, h)
+
+    def append(self, seg):
+        t = _u8(seg)
+        self.ctx.check(self.ctx._L.pb_consensus_append(self.ctx.h, self.h, _ptr(t) if len(t) else None, len(t)))
+
+    def prepend(self, seg):
+        t = _u8(seg)
+        self.ctx.check(self.ctx._L.pb_consensus_prepend(self.ctx.h, self.h, _ptr(t) if len(t) else None, len(t)))
+
+    def elect(self, reads: "SeqSet", recs: np.ndarray, ops: np.ndarray, ops_off: np.ndarray):
+        recs = np.ascontiguousarray(recs)
+        ops_off = np.ascontiguousarray(ops_off, dtype=np.int64)
+        assert recs.dtype == OVERLAP_DTYPE and len(ops_off) == len(recs)
+        self.ctx.check(self.ctx._L.pb_consensus_elect_batch(self.ctx.h, self.h, reads.h, _ptr(recs), len(recs), _ptr(ops), _ptr(ops_off)))
+
+    def evolve(self):
+        self.ctx.check(self.ctx._L.pb_consensus_evolve(self.ctx.h, self.h))
+
+    def votes(self) -> np.ndarray:
+        n = self.extent()[1]
+        out = np.zeros((max(n, 1), 9), dtype=np.int32)
+        self.ctx.check(self.ctx._L.pb_consensus_votes(self.ctx.h, self.h, _ptr(out), max(n, 1)))
+        return out[:n]
 
 
 class Index:

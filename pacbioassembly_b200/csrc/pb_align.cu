@@ -124,6 +124,7 @@ __device__ __forceinline__ void derive_views(const PairViews &pv, const LocateVi
         return;
     }
     // spaced_seed.cpp:274-285 + ref_seq.h:264,282-286: align(ref view, read view), both forward or both backward
+    refpos += lv.ref_shift; // get_accessor(pos): txt_buf + beg + pos, with pre <= beg once the reference has grown in front
     const bool forward = (t & 1) == 0;
     cv.j = t >> 1; cv.dir = forward ? 1 : -1;
     cv.read_pos = forward ? cv.j : rlen - cv.j - 16;

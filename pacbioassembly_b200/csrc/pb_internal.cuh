@@ -200,6 +200,7 @@ struct LocateView { // everything the aligner needs to derive candidate (a,b) vi
     int mode;         // PB_MODE_LOCATE: a = read[j:], b = ref[pos:] (locator.cpp:78-82)
                       // PB_MODE_OVERLAP: a = ref view, b = read view, forward or backward (spaced_seed.cpp:274-285, ref_seq.h:264)
     int min_overlap;  // OVERLAP_MIN gate on matlen_a (ref_seq.h:265), overlap mode only
+    int ref_shift = 0; // overlap mode: candidate positions are relative to ref position ref_shift (a reference grown in front, beg - pre)
     // all-vs-all (pb_overlap_all_run): work item k = one (reference sequence, read) pair.  d_kept[k] = the read, d_item_ref[k] =
     // the sequence acting as reference (in ss.ref), candidates [d_item_beg[k], d_item_end[k]) in (trial, list) order with
     // d_cand_q = trial number and d_cand_pos = position inside that reference; d_cand_item (prefilter only) = item of a

@@ -283,7 +283,7 @@ extern "C" void pb_overlap_default_params(pb_overlap_params *p)
     p->maxm = 6000;
     p->seed_at_quirk = 0;
     p->want_ops = 0;
-    p->reserved = 0;
+    p->ref_shift = 0;
 }
 
 extern "C" int pb_overlap_batch(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const pb_seqset *reads,
@@ -293,7 +293,8 @@ extern "C" int pb_overlap_batch(pb_ctx *ctx, const pb_index *ix, const pb_seqset
         return pb_fail(ctx, PB_ERR_ARG, "pb_overlap_batch: bad argument");
     if (prm->max_trial < 1 || prm->max_trial > 2048) return pb_fail(ctx, PB_ERR_ARG, "max_trial %d out of range", prm->max_trial);
     if (prm->want_ops && (!ops || !ops_off)) return pb_fail(ctx, PB_ERR_ARG, "want_ops needs ops and ops_off");
-    if (ref->len[ref_seq] != ix->ref_len) return pb_fail(ctx, PB_ERR_ARG, "index was built over a different sequence");
+    if (prm->ref_shift < 0 || ix->ref_len < 0 || ref->len[ref_seq] < ix->ref_len + prm->ref_shift || (!prm->ref_shift && ref->len[ref_seq] != ix->ref_len))
+        return pb_fail(ctx, PB_ERR_ARG, "index was built over a different sequence");
     if (reads->n * (int64_t)prm->max_trial * 2 > INT32_MAX) return pb_fail(ctx, PB_ERR_DOMAIN, "too many reads in one batch");
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     pb_timer_reset(ctx);
@@ -339,6 +340,7 @@ extern "C" int pb_overlap_batch(pb_ctx *ctx, const pb_index *ix, const pb_seqset
         lv.ref_len = ref->len[ref_seq];
         lv.mode = PB_MODE_OVERLAP;
         lv.min_overlap = prm->min_overlap;
+        lv.ref_shift = prm->ref_shift;
         SeqSets ss = {reads, ref, reads_rev, ref_rev};
         r = d_survive.alloc(ctx, (size_t)std::max<int64_t>(po.ncand, 1));
         if (r == PB_OK) r = d_rej.alloc(ctx, (size_t)std::max<int64_t>(po.ncand, 1) * 4);

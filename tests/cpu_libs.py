@@ -103,6 +103,70 @@ class Oracle:
         self.lib.pbo_overlap(*args, recs.ctypes.data)
         return recs
 
+    def assemble(self, ref: np.ndarray, image: bytes, round_masks, weight: int = 1, R: float = 0.3, max_trial: int = 32,
+                 min_overlap: int = 64, maxn: int = 26000, maxm: int = 6000, quirk: bool = False, min_excl: int = 500,
+                 max_excl: int = 20000):
+        """unlocked assembler rounds (spaced_seed.cpp:408-453 with ref_seq voting / growth / evolve):
+        returns (list of consensus bytes per round, found_round int32[nkept], OVERLAP_DTYPE records)"""
+        L = self.lib
+        L.pbo_assemble.restype = C.c_int64
+        L.pbo_assemble.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                   C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        img = np.frombuffer(image, dtype=np.uint8)
+        masks = np.ascontiguousarray(round_masks, dtype=np.uint32)
+        head = (ref.ctypes.data, len(ref), weight, img.ctypes.data, len(img), min_excl, max_excl, masks.ctypes.data, len(masks), R,
+                max_trial, min_overlap, maxn, maxm, int(quirk))
+        nk = L.pbo_assemble(*head, None, 0, None, None, None)
+        stride = 800000
+        cons = np.zeros(len(masks) * stride, dtype=np.uint8)
+        clen = np.zeros(len(masks), dtype=np.int32)
+        fr = np.zeros(nk, dtype=np.int32)
+        recs = np.zeros(nk, dtype=OVERLAP_DTYPE)
+        L.pbo_assemble(*head, cons.ctypes.data, stride, clen.ctypes.data, fr.ctypes.data, recs.ctypes.data)
+        return [cons[r * stride: r * stride + clen[r]].tobytes() for r in range(len(masks))], fr, recs
+
+    # ref_seq's voting state, piece by piece (the GPU consensus primitives are checked against these)
+    def cons_create(self, text: bytes, weight: int = 1):
+        L = self.lib
+        L.pbo_cons_create.restype = C.c_void_p
+        L.pbo_cons_create.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_size_t]
+        L.pbo_cons_free.argtypes = [C.c_void_p]
+        L.pbo_cons_length.restype = C.c_size_t
+        L.pbo_cons_length.argtypes = [C.c_void_p]
+        L.pbo_cons_extent.restype = C.c_size_t
+        L.pbo_cons_extent.argtypes = [C.c_void_p, C.c_void_p]
+        L.pbo_cons_text.restype = C.c_void_p
+        L.pbo_cons_text.argtypes = [C.c_void_p]
+        L.pbo_cons_append.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.pbo_cons_prepend.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.pbo_cons_elect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.pbo_cons_evolve.argtypes = [C.c_void_p]
+        L.pbo_cons_votes.restype = C.c_int64
+        L.pbo_cons_votes.argtypes = [C.c_void_p, C.c_void_p]
+        return L.pbo_cons_create(text, len(text), weight, 800000)
+
+    def cons_text(self, c) -> bytes:
+        return C.string_at(self.lib.pbo_cons_text(c), self.lib.pbo_cons_length(c))
+
+    def cons_full_text(self, c):
+        """(text of [pre, post), beg - pre)"""
+        before = C.c_long(0)
+        n = self.lib.pbo_cons_extent(c, C.byref(before))
+        return C.string_at(self.lib.pbo_cons_text(c) - before.value, n), before.value
+
+    def cons_votes(self, c) -> np.ndarray:
+        n = self.lib.pbo_cons_votes(c, None)
+        out = np.zeros((n, 9), dtype=np.int32)
+        self.lib.pbo_cons_votes(c, out.ctypes.data)
+        return out
+
+    def cons_elect(self, c, pos: int, ops: np.ndarray, vals: np.ndarray, forward: bool):
+        ops = np.ascontiguousarray(ops, dtype=np.uint8)
+        vals = np.ascontiguousarray(vals, dtype=np.uint8)
+        self.lib.pbo_cons_elect(c, pos, ops.ctypes.data, vals.ctypes.data, len(ops), int(forward))
+
     # -- L0 --
     def encode(self, text: bytes) -> int:
         return self.lib.pbo_encode(text, len(text))
@@ -250,6 +314,27 @@ class Ref:
                                    recs.ctypes.data)
         assert n == nrec
         return recs
+
+    def assemble(self, ref: np.ndarray, image: bytes, round_masks, weight: int = 1, R: float = 0.3, max_trial: int = 32,
+                 min_excl: int = 500, max_excl: int = 20000):
+        """unlocked rounds through the reference's own ref_seq (try_align votes / grows, evolve); same outputs as Oracle.assemble"""
+        L = self.lib
+        L.pbref_assemble.restype = C.c_int64
+        L.pbref_assemble.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                     C.c_double, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        img = np.frombuffer(image + b"\0" * 65536, dtype=np.uint8).copy()
+        masks = np.ascontiguousarray(round_masks, dtype=np.uint32)
+        head = (ref.ctypes.data, len(ref), weight, img.ctypes.data, len(image), min_excl, max_excl, masks.ctypes.data, len(masks), R,
+                max_trial)
+        nk = L.pbref_assemble(*head, None, 0, None, None, None)
+        stride = 800000
+        cons = np.zeros(len(masks) * stride, dtype=np.uint8)
+        clen = np.zeros(len(masks), dtype=np.int32)
+        fr = np.zeros(nk, dtype=np.int32)
+        recs = np.zeros(nk, dtype=OVERLAP_DTYPE)
+        L.pbref_assemble(*head, cons.ctypes.data, stride, clen.ctypes.data, fr.ctypes.data, recs.ctypes.data)
+        return [cons[r * stride: r * stride + clen[r]].tobytes() for r in range(len(masks))], fr, recs
 
     def locator_open(self, ref: np.ndarray, mask: int):
         """locator.cpp:57-66 (contig + seed map), built once"""

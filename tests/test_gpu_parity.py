@@ -661,3 +661,80 @@ def test_packed_bucket_headers_escape(ctx, oracle):
             assert (got[n] == want[n]).all(), (shift, n)
         ix.free()
     assert want["found"].sum() > 10 and want["ncand"].max() >= 6
+
+
+# ---------------------------------------------------------------------------------------------
+# consensus voting: pb_consensus_* against the oracle's ref_seq restatement and the reference's own output
+# ---------------------------------------------------------------------------------------------
+
+def test_consensus_primitives(ctx, oracle):
+    """create / elect / append / prepend / evolve, box by box: one batch of matches voted on the GPU in one launch against the
+    same matches voted one by one through the oracle's elect (transcripts from the oracle's own align)"""
+    from test_oracle import overlap_workload
+    ref, image = overlap_workload(601, 9000, 50)
+    mask = MASKS[0]
+    cons = ctx.consensus(ref, weight=2)
+    oc = oracle.cons_create(ref.tobytes(), 2)
+    assert (cons.votes() == oracle.cons_votes(oc)).all() and len(cons) == len(ref)
+    reads = ctx.seqset_from_bin(image)
+    cur = cons.seqset()
+    ix = ctx.index(cur, mask, policy=1)
+    recs, ops, ops_off = ctx.overlap(ix, reads, want_ops="raw", R=0.3)
+    assert recs["found"].sum() > 10 and (recs["dir"][recs["found"] == 1] == -1).any()
+    cons.elect(reads, recs, ops, ops_off)
+    from pacbioassembly_b200.assemble import kept_records
+    rec_bytes = kept_records(image)
+    for k in np.nonzero(recs["found"] == 1)[0]:
+        r = recs[k]
+        fwd = r["dir"] == 1
+        text = oracle.bin2text(rec_bytes[k])
+        r_off = int(r["ref_pos"]) + (0 if fwd else 15)
+        s_off = int(r["read_pos"]) + (0 if fwd else 15)
+        a = ref.tobytes()[r_off:] if fwd else ref.tobytes()[: r_off + 1]
+        b = text[s_off:] if fwd else text[: s_off + 1]
+        al = oracle.align(a, b, R=0.3, a_fwd=fwd, b_fwd=fwd)
+        assert al["nedit"] == r["nedit"] and (al["ops"] == ops[ops_off[k]: ops_off[k] + r["nedit"]]).all()
+        oracle.cons_elect(oc, r_off, al["ops"], al["vals"], fwd)
+    assert (cons.votes() == oracle.cons_votes(oc)).all()
+    # growth at both ends, then evolve; twice (the second evolve sees the suppliments the first one left behind)
+    for rnd in range(2):
+        cons.append(b"ACGTTGCAAC" * (rnd + 1))
+        cons.prepend(b"TTGACCA")
+        oracle.lib.pbo_cons_append(oc, b"ACGTTGCAAC" * (rnd + 1), 10 * (rnd + 1))
+        oracle.lib.pbo_cons_prepend(oc, b"TTGACCA", 7)
+        full, before = oracle.cons_full_text(oc)
+        assert cons.text(full=True) == full and cons.extent() == (before, len(full))
+        assert (cons.votes() == oracle.cons_votes(oc)).all()
+        cons.evolve()
+        oracle.lib.pbo_cons_evolve(oc)
+        assert cons.text() == oracle.cons_text(oc) and cons.extent() == (0, len(cons))
+        assert (cons.votes() == oracle.cons_votes(oc)).all()
+    assert cons.text() != ref.tobytes()  # votes changed the text (insertions / deletions took effect)
+    oracle.lib.pbo_cons_free(oc)
+
+
+def test_assemble_unlocked_rounds(ctx, golden, oracle):
+    """the assembler's rounds with voting and growth (pacbioassembly_b200/assemble.py over pb_overlap_batch with ref_shift,
+    pb_consensus_elect_batch / append / prepend / evolve): consensus of every round, who was found when and the records, against
+    the compiled reference's own output (golden) and the oracle"""
+    import hashlib
+    from pacbioassembly_b200.assemble import assemble_rounds
+    from test_oracle import ASM_FIELDS, assemble_workload
+    for g in golden["assemble"]:
+        ref0, image = assemble_workload(g["seed"], g["genome_len"], g["nreads"], g["ref_read"])
+        cons, fr, recs, passes = assemble_rounds(ctx, ref0, image, g["masks"], weight=g["weight"], seed_at_quirk=1)
+        assert [len(c) for c in cons] == g["consensus_len"]
+        assert [hashlib.sha1(c).hexdigest() for c in cons] == g["consensus_sha1"]
+        assert fr.tolist() == g["found_round"]
+        wc, wf, wr = oracle.assemble(ref0, image, g["masks"], weight=g["weight"], quirk=True)
+        for n in ASM_FIELDS:
+            assert (recs[n] == wr[n]).all(), n
+        assert max(passes) > 3  # growth really happened inside rounds
+    # intended seed_at behaviour (no golden: the compiled reference only has the shipped one)
+    ref0, image = assemble_workload(541, 8000, 50, 7)
+    masks = [MASKS[0], MASKS[3], MASKS[1]]
+    cons, fr, recs, _ = assemble_rounds(ctx, ref0, image, masks, seed_at_quirk=0)
+    wc, wf, wr = oracle.assemble(ref0, image, masks, quirk=False)
+    assert cons == wc and (fr == wf).all()
+    for n in ASM_FIELDS:
+        assert (recs[n] == wr[n]).all(), n

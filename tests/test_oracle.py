@@ -383,3 +383,38 @@ def test_live_allpairs(oracle, ref):
         for n in ("found", "ncand") + PAIR_FIELDS:
             assert int(want[k][n]) == int(got[k][n]), (k, n)
     assert any((q, t) not in want for (t, q) in want)
+
+
+# ---------------------------------------------------------------------------------------------
+# consensus voting and the unlocked assembler rounds (ref_seq.h:25-41,47-183,207-276,317-362; spaced_seed.cpp:408-453)
+# ---------------------------------------------------------------------------------------------
+
+def assemble_workload(seed=501, genome_len=12000, nreads=80, ref_read=5):
+    from allpairs_util import allpairs_workload
+    texts, image = allpairs_workload(seed, genome_len, nreads, mean=1500.0, lo=520, hi=4000)
+    return np.frombuffer(texts[ref_read], dtype=np.uint8), image
+
+
+ASM_FIELDS = ("found", "j", "ref_pos", "cost", "read_pos", "dir", "matlen_a", "matlen_b", "nedit", "ncand")
+
+
+def test_live_assemble_unlocked(oracle, ref):
+    """the reference's own ref_seq (try_align votes and grows, evolve rewrites the text) over four rounds that grow a 1.5 kbp
+    read into an ~11 kbp contig, against the restatement: consensus text of every round, who was found when, the records"""
+    ref0, image = assemble_workload()
+    masks = [0xff3c3ffc, 0x3fcfccf3, 0xff3c3ffc, 0xfff0ccfc]
+    for weight in (1, 3):
+        cw, fw, rw = ref.assemble(ref0, image, masks, weight=weight)
+        cg, fg, rg = oracle.assemble(ref0, image, masks, weight=weight, quirk=True)
+        assert cw == cg and (fw == fg).all()
+        for n in ASM_FIELDS:
+            assert (rw[n] == rg[n]).all(), n
+        assert len(cw[-1]) > 4 * len(ref0) and (fw > 0).sum() > 60 and len(set(fw.tolist())) >= 4
+
+
+def test_golden_assemble(oracle, golden):
+    for g in golden["assemble"]:
+        ref0, image = assemble_workload(g["seed"], g["genome_len"], g["nreads"], g["ref_read"])
+        cons, fr, recs = oracle.assemble(ref0, image, g["masks"], weight=g["weight"], quirk=True)
+        assert [hashlib.sha1(c).hexdigest() for c in cons] == g["consensus_sha1"] and [len(c) for c in cons] == g["consensus_len"]
+        assert fr.tolist() == g["found_round"]
