@@ -270,6 +270,12 @@ PB_API void pb_overlap_default_params(pb_overlap_params *p);
  * recs: one entry per sequence of `reads`.  ops/ops_off as in pb_align_batch, slots of 3*len + 2*maxm + 16 bytes. */
 PB_API int pb_overlap_batch(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const pb_seqset *reads,
                             const pb_overlap_params *prm, pb_overlap_rec *recs, uint8_t *ops, const int64_t *ops_off);
+/* The same for the nids sequences ids[0..nids) of `reads` only, in that order (the pool of reads still unmatched,
+ * spaced_seed.cpp:419-437): recs[k] / ops_off[k] belong to read ids[k], recs[k].id = ids[k].  The set stays the whole .bin image, so
+ * the shipped seed_at (which reads raw image bytes past the record at pos%4==0, SURVEY Q-S1) sees what the reference sees. */
+PB_API int pb_overlap_subset(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const pb_seqset *reads,
+                             const int32_t *ids, int64_t nids, const pb_overlap_params *prm, pb_overlap_rec *recs, uint8_t *ops,
+                             const int64_t *ops_off);
 
 /* ---- consensus voting (ref_seq.h:25-41 apply_edits, :47-183 base_vote / vote_box, :207-256 ctor / append / prepend,
  *      :317-362 evolve / elect) ---------------------------------------------------------------------------------- */

@@ -713,6 +713,7 @@ int64_t pbo_assemble(const char *ref_text, size_t ref_len, int weight, const uin
             memcpy(&slen, bin + rec, 4);
             pbo_bin2text(bin + rec, txt, (size_t)max_excl + 64);
             int found = 0;
+            recs[k].ncand = 0; recs[k].cells = 0; /* per round: the record describes the round in which the read was found */
             for (int j = 0; j < max_trial && !found; ++j)
                 for (int side = 0; side < 2 && !found; ++side) {
                     const int forward = side == 0;

@@ -376,6 +376,7 @@ int64_t pbref_assemble(const char *ref_text, long ref_len, int weight, unsigned 
             dna_seq::bin2text(bin + off, txt, slen + 1);
             overlap_rec *out = &recs[k];
             bool found = false;
+            out->ncand = 0; /* per round */
             for (int j = 0; j < max_trial && !found; ++j)
                 for (int side = 0; side < 2 && !found; ++side) {
                     bool forward = side == 0;

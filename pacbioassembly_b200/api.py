@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
         "pb_locate_job_free": (None, [vp]),
         "pb_overlap_default_params": (None, [P(OverlapParams)]),
         "pb_overlap_batch": (C.c_int, [vp, vp, vp, i64, vp, P(OverlapParams), vp, vp, vp]),
+        "pb_overlap_subset": (C.c_int, [vp, vp, vp, i64, vp, vp, i64, P(OverlapParams), vp, vp, vp]),
         "pb_consensus_create": (C.c_int, [vp, vp, i64, C.c_int, P(vp)]),
         "pb_consensus_free": (None, [vp]),
         "pb_consensus_length": (i64, [vp]),
@@ -355,26 +356,29 @@ class Context:
             return recs, [ops[ops_off[k]: ops_off[k] + int(recs["nedit"][k])] for k in range(nk)]
         return recs
 
-    def overlap(self, index: "Index", reads: "SeqSet", want_ops: bool = False, ref: "SeqSet | None" = None, **params):
+    def overlap(self, index: "Index", reads: "SeqSet", want_ops: bool = False, ref: "SeqSet | None" = None, ids=None, **params):
         """spaced_seed.cpp:424-436 / try_align: head and tail trials of every read against a REFSEQ-policy index.
-        ref (with ref_shift=beg-pre): the whole text of a reference that has grown beyond the indexed [beg, end)."""
+        ref (with ref_shift=beg-pre): the whole text of a reference that has grown beyond the indexed [beg, end).
+        ids: only these reads of the set, in this order (pb_overlap_subset)."""
         prm = OverlapParams()
         self._L.pb_overlap_default_params(C.byref(prm))
         prm.want_ops = 1 if want_ops else 0
         for k, v in params.items():
             setattr(prm, k, v)
-        n = len(reads)
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int32)
+        n = len(reads) if ids is None else len(ids)
         recs = np.zeros(n, dtype=OVERLAP_DTYPE)
         ops = ops_off = None
         if want_ops:
-            lens = np.array([reads.length(i) for i in range(n)], dtype=np.int64)
+            lens = np.array([reads.length(int(i)) for i in (range(n) if ids is None else ids)], dtype=np.int64)
             slots = (3 * lens + 2 * prm.maxm + 16 + 15) & ~15
             ops_off = np.zeros(n, dtype=np.int64)
             if n:
                 np.cumsum(slots[:-1], out=ops_off[1:])
             ops = np.zeros(int(slots.sum()) + 16, dtype=np.uint8)
-        self.check(self._L.pb_overlap_batch(self.h, index.h, (ref or index.ref).h, 0 if ref else index.seq, reads.h, C.byref(prm), _ptr(recs),
-                                            _ptr(ops), _ptr(ops_off)))
+        self.check(self._L.pb_overlap_subset(self.h, index.h, (index.ref if ref is None else ref).h, index.seq if ref is None else 0,
+                                             reads.h, _ptr(ids), n, C.byref(prm), _ptr(recs), _ptr(ops), _ptr(ops_off)))
         if want_ops == "raw":  # the buffers as pb_consensus_elect_batch takes them
             return recs, ops, ops_off
         if want_ops:

@@ -34,6 +34,7 @@ def assemble_rounds(ctx: Context, ref_text, image: bytes, round_masks, weight: i
     records = kept_records(image, min_excl, max_excl)
     nk = len(records)
     cons = ctx.consensus(ref_text, weight)
+    reads = ctx.seqset_from_bin(image, min_excl, max_excl)  # once: passes name the reads they visit by id (pb_overlap_subset)
     pool = list(range(nk))
     found_round = np.zeros(nk, dtype=np.int32)
     out = np.zeros(nk, dtype=OVERLAP_DTYPE)
@@ -44,11 +45,12 @@ def assemble_rounds(ctx: Context, ref_text, image: bytes, round_masks, weight: i
         ix = ctx.index(cur, int(mask), policy=POLICY_REFSEQ)  # ref_seq::get_seedmap over [beg, end)
         pending = list(pool)
         npass = 0
+        window = 256  # reads per pass: what lies behind a growing read is recomputed, so look ahead only as far as growth is rare
         while pending:
             before, total = cons.extent()
             full = cons.seqset(full=True)
-            reads = ctx.seqset_from_bin(b"".join(records[k] for k in pending), min_excl, max_excl)
-            recs, ops, ops_off = ctx.overlap(ix, reads, want_ops="raw", ref=full, ref_shift=before, R=R, max_trial=max_trial,
+            chunk = pending[:window]
+            recs, ops, ops_off = ctx.overlap(ix, reads, want_ops="raw", ref=full, ids=chunk, ref_shift=before, R=R, max_trial=max_trial,
                                              seed_at_quirk=seed_at_quirk)
             npass += 1
             # the first match that consumes its whole reference view grows the text (ref_seq.h:267): results behind it are void
@@ -56,7 +58,8 @@ def assemble_rounds(ctx: Context, ref_text, image: bytes, round_masks, weight: i
             r_off = np.where(fwd, recs["ref_pos"], recs["ref_pos"] + 15).astype(np.int64)
             a_len = np.where(fwd, (total - before) - r_off, r_off + before + 1)
             grows = np.nonzero((recs["found"] == 1) & (recs["matlen_a"] == a_len))[0]
-            stop = int(grows[0]) + 1 if len(grows) else len(pending)
+            stop = int(grows[0]) + 1 if len(grows) else len(chunk)
+            window = max(64, window // 2) if len(grows) else window * 4
             batch = recs[:stop].copy()
             cons.elect(reads, batch, ops, ops_off[:stop])
             if len(grows):
@@ -72,19 +75,17 @@ def assemble_rounds(ctx: Context, ref_text, image: bytes, round_masks, weight: i
             for i in np.nonzero(batch["found"] == 1)[0]:
                 k = pending[i]
                 found_round[k] = rnd + 1
-                rec = batch[i].copy()
-                rec["id"] = k
-                out[k] = rec
+                out[k] = batch[i]
                 if log:
-                    log(f"found {k} at cost {int(rec['cost'])}:\tref_ml={int(rec['matlen_a'])},\tseg_ml={int(rec['matlen_b'])}")
+                    log(f"found {k} at cost {int(batch[i]['cost'])}:\tref_ml={int(batch[i]['matlen_a'])},\tseg_ml={int(batch[i]['matlen_b'])}")
             pool = [k for k in pool if not found_round[k]]
             pending = pending[stop:]
-            reads.free()
             full.free()
         ix.free()
         cur.free()
         cons.evolve()
         texts.append(cons.text())
         passes.append(npass)
+    reads.free()
     cons.free()
     return texts, found_round, out, passes

@@ -27,6 +27,13 @@
 #else
 #define PB_PLANE_PADBIT 1 // one pad bit in front of the Eq planes: the per-row shift becomes 1..32, i.e. a multiply by 2^31..2^0
 #endif
+#ifndef PB_PAD_MOD
+// Band classes with S % PB_PAD_MOD == 0 keep their Eq planes padded (one word per S words) so that the lane stride S+1 is free of
+// shared-memory bank conflicts.  The padding costs ~4 ALU instructions per band word and row (the window of a lane crosses one
+// pad word at a position that changes every 32 rows), and the kernel is bound by the ALU pipe, not by shared memory: measured on
+// config 2 (A/B builds, same box), padding every even class 100.3 ms, only S=8,16 98.1 ms, only S=16 94.9 ms per step of K3.
+#define PB_PAD_MOD 16
+#endif
 #ifndef ALIGN_WPB
 #define ALIGN_WPB 8 // warps (alignments in flight) per CTA, at most: launches that need more shared memory use fewer
 #endif
@@ -348,7 +355,7 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
     uint32_t Eq[S], x[S], sum[S];
     // Eq words: logical words x0..x0+S of the plane; for even S the plane is stored with one pad word per S words
     // (bank-conflict-free for the lane stride S), which shows up here as a +1 from slot `thrs` on
-    constexpr bool PAD = (S % 2) == 0;
+    constexpr bool PAD = (S % PB_PAD_MOD) == 0;
 #ifdef PB_SHIFT_FMA
     const uint32_t eqm = 0x80000000u >> sh; // 2^(31-sh)
 #endif
@@ -530,7 +537,7 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
 
 
     // ---- Eq planes of seg_b in shared memory: plane c, bit t <-> (b[t - D] == c), zero outside [0,len_b)
-    constexpr bool PAD = (S % 2) == 0; // see row_step: physical index of logical word x is x + x/S for even S
+    constexpr bool PAD = (S % PB_PAD_MOD) == 0; // see row_step: physical index of logical word x is x + x/S in the padded classes
     const int PWn = ((len_a + 31) >> 5) + T + 1;
     // The plane words that cover seg_b = line bits [b_bit, b_bit + len_b) come in through a small staging buffer filled by
     // bulk TMA copies (16-byte granules), PB_STAGE_WORDS words of each plane at a time; consecutive chunks overlap by four
@@ -659,9 +666,10 @@ __device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_le
             int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
             if (IRR && ((awi >> t) & 1u)) ca = irr_plane(A, a_bit + i0 - 1 + t, a_tab);
             const uint32_t d0w = row_step<S>(Hp, Hn, keep, Vp, Vn, plq + ca * PW, thrs, (unsigned)t, lane, sd, stores, prow, c31, c2);
-            hist |= ((d0w >> (D & 31)) & 1u) << t; // meaningful in the diagonal's owner lane
+            hist = __funnelshift_r(hist, d0w >> (D & 31), 1); // row t's diagonal D0 bit enters at bit 31 (meaningful in the diagonal's owner lane)
             prow += 2 * T;
         }
+        hist >>= 32 - tmax; // row t of the block now sits at bit t
         hist = __shfl_sync(FULL, hist, Ld);
         const int cdiag = cii + (lane + 1) - __popc(hist & (0xffffffffu >> (31 - lane))); // cost(i0+lane, i0+lane)
         const uint32_t badm = __ballot_sync(FULL, lane < tmax && i0 + lane > 10 && cdiag > thr);
@@ -1129,7 +1137,7 @@ static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, int locate, si
         const int S = key_S(key), T = 32 * S;
         g->groups = 1;
         const int logical = ((cp.max_rows + 31) >> 5) + T + 2;
-        g->PW = logical + ((S % 2) == 0 ? logical / S + 2 : 0); // even S: one pad word per S words (bank conflicts)
+        g->PW = logical + ((S % PB_PAD_MOD) == 0 ? logical / S + 2 : 0); // padded classes: one pad word per S words (bank conflicts)
         g->PW = (g->PW + 3) & ~3; // 16-byte aligned sub-arrays (TMA destination)
         g->RW = PB_STAGE_WORDS; // TMA staging buffer per raw plane
         g->warp_words = (key_irr(key) ? 8 : 4) * g->PW + (key_irr(key) ? 3 : 2) * g->RW;

@@ -289,31 +289,45 @@ extern "C" void pb_overlap_default_params(pb_overlap_params *p)
 extern "C" int pb_overlap_batch(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const pb_seqset *reads,
                                 const pb_overlap_params *prm, pb_overlap_rec *recs, uint8_t *ops, const int64_t *ops_off)
 {
-    if (!ctx || !ix || !ref || !reads || !prm || ref_seq < 0 || ref_seq >= ref->n || (reads->n && !recs))
+    return pb_overlap_subset(ctx, ix, ref, ref_seq, reads, nullptr, reads ? reads->n : 0, prm, recs, ops, ops_off);
+}
+
+extern "C" int pb_overlap_subset(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const pb_seqset *reads,
+                                 const int32_t *ids, int64_t nids, const pb_overlap_params *prm, pb_overlap_rec *recs, uint8_t *ops,
+                                 const int64_t *ops_off)
+{
+    if (!ctx || !ix || !ref || !reads || !prm || ref_seq < 0 || ref_seq >= ref->n || nids < 0 || (nids && !recs) || (!ids && nids != reads->n))
         return pb_fail(ctx, PB_ERR_ARG, "pb_overlap_batch: bad argument");
     if (prm->max_trial < 1 || prm->max_trial > 2048) return pb_fail(ctx, PB_ERR_ARG, "max_trial %d out of range", prm->max_trial);
     if (prm->want_ops && (!ops || !ops_off)) return pb_fail(ctx, PB_ERR_ARG, "want_ops needs ops and ops_off");
-    if (prm->ref_shift < 0 || ix->ref_len < 0 || ref->len[ref_seq] < ix->ref_len + prm->ref_shift || (!prm->ref_shift && ref->len[ref_seq] != ix->ref_len))
+    // the reference may be longer than the indexed text at both ends: a grown ref_seq is indexed over [beg, end) only (ref_seq.h:291-293)
+    if (prm->ref_shift < 0 || ix->ref_len < 0 || ref->len[ref_seq] < ix->ref_len + prm->ref_shift)
         return pb_fail(ctx, PB_ERR_ARG, "index was built over a different sequence");
-    if (reads->n * (int64_t)prm->max_trial * 2 > INT32_MAX) return pb_fail(ctx, PB_ERR_DOMAIN, "too many reads in one batch");
+    if (nids * (int64_t)prm->max_trial * 2 > INT32_MAX) return pb_fail(ctx, PB_ERR_DOMAIN, "too many reads in one batch");
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     pb_timer_reset(ctx);
     pb_timer_begin(ctx, PB_T_TOTAL);
-    const int64_t n = reads->n;
+    const int64_t n = nids;
     if (n == 0) return PB_OK;
-    for (int64_t i = 0; i < n; ++i)
+    for (int64_t k = 0; k < n; ++k) {
+        const int64_t i = ids ? ids[k] : k;
+        if (i < 0 || i >= reads->n) return pb_fail(ctx, PB_ERR_ARG, "read id %lld outside the set of %lld", (long long)i, (long long)reads->n);
         if (reads->len[i] < prm->max_trial + 16)
             return pb_fail(ctx, PB_ERR_ARG, "read %lld is shorter than max_trial+16: seed_at(read, len-j-16) would start before the read "
                            "(the reference only keeps reads longer than 500, spaced_seed.cpp:336)", (long long)i);
+    }
     // backward trials align reversed views: build the reversed copies once per call
     pb_seqset *reads_rev = nullptr, *ref_rev = nullptr;
     int r = pb_seqset_reversed(ctx, reads, &reads_rev);
     if (r == PB_OK) r = pb_seqset_reversed(ctx, ref, &ref_rev);
     DevBuf d_kept, d_survive, d_rej, d_recs, d_ops, d_ops_off, d_stats;
     ProbeOut po;
-    std::vector<int32_t> kept((size_t)n), kept_lens(reads->len.begin(), reads->len.end());
+    std::vector<int32_t> kept((size_t)n), kept_lens((size_t)n);
     std::vector<uint8_t> kept_irr((size_t)n, 0);
-    for (int64_t i = 0; i < n; ++i) kept[i] = (int32_t)i;
+    for (int64_t k = 0; k < n; ++k) {
+        kept[k] = ids ? ids[k] : (int32_t)k;
+        kept_lens[k] = reads->len[kept[k]];
+    }
     int64_t extent = 0;
     if (r == PB_OK) r = d_kept.alloc(ctx, (size_t)n * 4);
     if (r == PB_OK) r = pb_h2d(ctx, d_kept.p, kept.data(), (size_t)n * 4);
@@ -369,6 +383,8 @@ extern "C" int pb_overlap_batch(pb_ctx *ctx, const pb_index *ix, const pb_seqset
         if (e != cudaSuccess) r = pb_fail(ctx, PB_ERR_CUDA, "overlap kernels failed: %s", cudaGetErrorString(e));
     }
     pb_timer_collect(ctx);
+    if (r == PB_OK && ids)
+        for (int64_t k = 0; k < n; ++k) recs[k].id = ids[k]; // the kernels number the records by rank in the batch
     if (reads_rev) pb_seqset_free(reads_rev);
     if (ref_rev) pb_seqset_free(ref_rev);
     return r;

@@ -122,9 +122,9 @@ def test_spaced_seed_cli_locked_rounds(tmp_path, oracle):
         assert seed in masks and (nfail == 0 or seed == masks[nfail - 1])  # spaced_seed.cpp:411
         found_lines = re.findall(r"found (\d+) at cost (\d+):\tref_ml=(\d+),\tseg_ml=(\d+)", blk)
         ix = oracle.index_build(ref, seed, policy=1)
-        want = oracle.overlap(ix, ref, b"".join(rec for _, rec in pool), seed, R=0.3, quirk=True, nthreads=4)
+        allrecs = oracle.overlap(ix, ref, image, seed, R=0.3, quirk=True, nthreads=4)  # the whole image: seed_at reads past record ends
         oracle.index_free(ix)
-        assert len(want) == len(pool)
+        want = allrecs[[i for i, _ in pool]]
         exp = [(str(pool[i][0]), str(w["cost"]), str(w["matlen_a"]), str(w["matlen_b"])) for i, w in enumerate(want) if w["found"]]
         assert [tuple(x) for x in found_lines] == exp, k
         assert f"#matches: {len(exp)}\n" in blk
@@ -143,9 +143,6 @@ def test_spaced_seed_cli_locked_rounds(tmp_path, oracle):
     assert nfail == len(masks)
     assert (tmp_path / "dump.txt").read_bytes() == b"".join(x + b"\n" for x in dump_want) and len(dump_want) > 20
     assert r.stdout == (ref.tobytes() + b"\n") * stdout_lines  # a locked reference never evolves: the consensus is the reference
-    # unlocked mode is refused, not emulated
-    r2 = subprocess.run([os.path.join(HOST, "spaced_seed"), "-f", "ref.txt", "reads.bin", "seeds.txt"], cwd=str(tmp_path), capture_output=True)
-    assert r2.returncode != 0 and b"locked" in r2.stderr
 
     # the dump feeds visual_align: ours, the reference's own source compiled against our headers, and the oracle's transcript
     pairs = [(dump_want[i], dump_want[i + 1]) for i in range(0, len(dump_want), 2)]
@@ -170,3 +167,43 @@ def test_spaced_seed_cli_locked_rounds(tmp_path, oracle):
     if os.path.exists(os.path.join(HOST, "ref_visual_align")):
         v2 = run("ref_visual_align", stdin=b"".join(good))
         assert v2.returncode == 0 and v2.stdout == v.stdout
+
+
+def test_spaced_seed_cli_unlocked_rounds(tmp_path, oracle):
+    """spaced_seed -f ref bin seedfile (no -l): votes, growth and evolve on the GPU; every round's consensus on stdout, the
+    found lines and the dump against the oracle's unlocked rounds run with the seeds the driver drew"""
+    import re
+    from test_oracle import assemble_workload
+    exe = os.path.join(HOST, "spaced_seed")
+    if not os.path.exists(exe):
+        pytest.skip("spaced_seed not built")
+    ref0, image = assemble_workload(561, 9000, 60, 4)
+    (tmp_path / "reads.bin").write_bytes(image)
+    (tmp_path / "ref.txt").write_bytes(ref0.tobytes() + b"\n2\n")
+    patterns = ["111**111*11*1111", "*111*11**11*1111"]
+    (tmp_path / "seeds.txt").write_text("".join(p + "\n" for p in patterns))
+    r = subprocess.run([exe, "-f", "ref.txt", "-d", "dump.txt", "-m", "4", "reads.bin", "seeds.txt"], cwd=str(tmp_path), capture_output=True,
+                       timeout=900, env=dict(os.environ, PB_SRAND="11"))
+    err = r.stderr.decode()
+    assert r.returncode == 0, err
+    assert "reference weight: 2\n" in err and f"ref_len: {len(ref0)}\n" in err
+    rounds = re.split(r"-+ round \d+ -+\n", err)[1:]
+    masks = [int(re.search(r"seed: ([0-9a-f]{8})", blk).group(1), 16) for blk in rounds]
+    lines = r.stdout.split(b"\n")[:-1]
+    assert len(rounds) == 4 and len(lines) == 4  # -m 4; a round without a match still evolves and prints (spaced_seed.cpp:443-452)
+    cons, fr, recs = oracle.assemble(ref0, image, masks, weight=2, quirk=True)
+    assert lines == cons
+    lens = [len(ref0)] + [len(c) for c in cons]
+    for k, blk in enumerate(rounds):
+        assert f"reference length: {lens[k]}\n" in blk
+        found = re.findall(r"found (\d+) at cost (\d+):\tref_ml=(\d+),\tseg_ml=(\d+)", blk)
+        exp = [(str(i), str(recs["cost"][i]), str(recs["matlen_a"][i]), str(recs["matlen_b"][i])) for i in np.nonzero(fr == k + 1)[0]]
+        assert [tuple(x) for x in found] == exp, k
+        assert f"#matches: {len(exp)}\n" in blk
+    assert lens[-1] > 3 * lens[0] and (fr > 0).sum() > 20  # the reference grew
+    dump = (tmp_path / "dump.txt").read_bytes().split(b"\n")[:-1]
+    assert len(dump) == 2 * int((fr > 0).sum())
+    # each dumped pair is (matlen_a reference elements, matlen_b read elements) of a found read, in found order
+    order = [i for k in range(4) for i in np.nonzero(fr == k + 1)[0]]
+    for n, i in enumerate(order):
+        assert len(dump[2 * n]) == recs["matlen_a"][i] and len(dump[2 * n + 1]) == recs["matlen_b"][i]
