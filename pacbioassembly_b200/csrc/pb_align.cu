@@ -519,8 +519,13 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
     res.ret = matlen_b;
 }
 
+// Inlined into its one call site per kernel: as a separate function the row loop re-materialised the global-store descriptor
+// from vector registers before every store (two R2UR per parent pair); measured 95.0 -> 91.2 ms of K3 per config-2 step.
+#ifndef PB_ALIGN_ONE_ATTR
+#define PB_ALIGN_ONE_ATTR __forceinline__
+#endif
 template <int S, bool IRR>
-__device__ __noinline__ void align_one(const SeqView &A, int64_t a_bit, int a_len, uint32_t a_tab, const SeqView &B, int64_t b_bit, int b_len,
+__device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int a_len, uint32_t a_tab, const SeqView &B, int64_t b_bit, int b_len,
                                        double R, int maxn, int maxm, uint32_t *__restrict__ planes, int PW,
                                        uint32_t *__restrict__ par, uint8_t *__restrict__ opsrev, uint8_t *__restrict__ ops_out,
                                        uint32_t c31, uint32_t c2, uint32_t *__restrict__ raw, int RW, uint64_t *bar, uint32_t &phase,
