@@ -27,6 +27,12 @@
 #else
 #define PB_PLANE_PADBIT 1 // one pad bit in front of the Eq planes: the per-row shift becomes 1..32, i.e. a multiply by 2^31..2^0
 #endif
+#ifndef PB_TB_WINDOWS
+// traceback: 32-row parent windows in flight per warp (the one being walked + prefetched ones).  The backward walk is 19 % of K3
+// (measured by skipping it: 91.1 -> 74.2 ms) and it is DRAM traffic, not latency: every 8-byte pair it reads sits in its own
+// 128-byte line of a row written long ago.  Deeper prefetch only adds traffic: 3 windows 89.9 ms, 5 windows 91.7, 8 windows 98.9.
+#define PB_TB_WINDOWS 3
+#endif
 #ifndef PB_PAD_MOD
 // Band classes with S % PB_PAD_MOD == 0 keep their Eq planes padded (one word per S words) so that the lane stride S+1 is free of
 // shared-memory bank conflicts.  The padding costs ~4 ALU instructions per band word and row (the window of a lane crosses one
@@ -452,6 +458,10 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
     res.diag_cost = (a_len <= len_a && a_len <= len_b) ? cii : 0; // locator.cpp:86 (Q-L2)
     if ((double)matlen_b < len_b * (1 - R)) return; // seq_aligner.h:114
 
+#ifdef PB_SKIP_TRACEBACK // timing experiment only (results lose their transcripts): how much of K3 is the backward walk
+    res.nedit = 0; res.ret = matlen_b;
+    return;
+#endif
     // ---- find_path, seq_aligner.h:214-233: walk the parent planes back from the goal cell.
     // Warp-cooperative: lane r holds the parent pairs of row i0-r around the path's band position (2 band words,
     // 16 bytes), the next 64 rows are prefetched while the current ones are walked, and runs of MATCH along a
@@ -463,8 +473,11 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
     {
         int i = matlen_a, j = matlen_b;
         const int guard = len_a + len_b + 1; // a path can never be longer; keeps a corrupted plane from hanging the GPU
-        int cur_i0 = -1, cur_wb = 0, nxt_i0 = -1, nxt_wb = 0, nx2_i0 = -1, nx2_wb = 0;
-        uint2 c0 = make_uint2(0u, 0u), c1 = c0, n0 = c0, n1 = c0, m0 = c0, m1 = c0;
+        // windows in flight: [0] is the one being walked, [1..] are fetched ahead (DRAM latency under load is several windows long)
+        int wi0[PB_TB_WINDOWS], wwb[PB_TB_WINDOWS];
+        uint2 wp0[PB_TB_WINDOWS], wp1[PB_TB_WINDOWS];
+#pragma unroll
+        for (int t = 0; t < PB_TB_WINDOWS; ++t) { wi0[t] = -1; wwb[t] = 0; wp0[t] = make_uint2(0u, 0u); wp1[t] = wp0[t]; }
         while ((i | j) != 0 && n < guard) {
             if (i == 0) { // init_cell row 0: INSERT all the way
                 for (int t = lane; t < j; t += 32) opsrev[n + t] = (uint8_t)PB_INSERT;
@@ -477,39 +490,41 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
                 break;
             }
             const int k = j - i + D, w = k >> 5;
-            if (cur_i0 < 0 || cur_i0 - i >= 32 || w < cur_wb || w > cur_wb + 1) {
+            if (wi0[0] < 0 || wi0[0] - i >= 32 || w < wwb[0] || w > wwb[0] + 1) {
                 const int wb = window_base(k);
-                if (nxt_i0 == i && w >= nxt_wb && w <= nxt_wb + 1) { // the usual case: 32 rows consumed, prediction held
-                    cur_i0 = nxt_i0; cur_wb = nxt_wb;
-                    c0 = n0; c1 = n1;
-                    nxt_i0 = nx2_i0; nxt_wb = nx2_wb;
-                    n0 = m0; n1 = m1;
+                if (wi0[1] == i && w >= wwb[1] && w <= wwb[1] + 1) { // the usual case: 32 rows consumed, prediction held
+#pragma unroll
+                    for (int t = 0; t + 1 < PB_TB_WINDOWS; ++t) { wi0[t] = wi0[t + 1]; wwb[t] = wwb[t + 1]; wp0[t] = wp0[t + 1]; wp1[t] = wp1[t + 1]; }
+                    wi0[PB_TB_WINDOWS - 1] = wi0[0] - 32 * (PB_TB_WINDOWS - 1);
+                    wwb[PB_TB_WINDOWS - 1] = wb;
+                    wp0[PB_TB_WINDOWS - 1] = par_pair(wi0[PB_TB_WINDOWS - 1] - lane, wb);
+                    wp1[PB_TB_WINDOWS - 1] = par_pair(wi0[PB_TB_WINDOWS - 1] - lane, wb + 1);
                 } else { // cold start or the path left the predicted words: fetch now
-                    cur_i0 = i; cur_wb = wb;
-                    c0 = par_pair(cur_i0 - lane, cur_wb);
-                    c1 = par_pair(cur_i0 - lane, cur_wb + 1);
-                    nxt_i0 = cur_i0 - 32; nxt_wb = wb;
-                    n0 = par_pair(nxt_i0 - lane, nxt_wb);
-                    n1 = par_pair(nxt_i0 - lane, nxt_wb + 1);
+#pragma unroll
+                    for (int t = 0; t < PB_TB_WINDOWS; ++t) {
+                        wi0[t] = i - 32 * t; wwb[t] = wb;
+                        wp0[t] = par_pair(wi0[t] - lane, wb);
+                        wp1[t] = par_pair(wi0[t] - lane, wb + 1);
+                    }
                 }
-                nx2_i0 = cur_i0 - 64; nx2_wb = wb; // two windows ahead: DRAM latency under load is several windows long
-                m0 = par_pair(nx2_i0 - lane, nx2_wb);
-                m1 = par_pair(nx2_i0 - lane, nx2_wb + 1);
             }
+            const int cur_i0 = wi0[0], cur_wb = wwb[0];
+            const uint2 c0 = wp0[0], c1 = wp1[0];
             const int r0 = cur_i0 - i; // lane that holds the current row
             const uint2 cw = (w == cur_wb) ? c0 : c1;
             const uint32_t B = __ballot_sync(FULL, (cw.x >> (k & 31)) & 1u) >> r0; // bit t: cell (i-t, j-t) is MATCH
             int run = (~B) ? __ffs(~B) - 1 : 32;
-            run = min(min(run, 32 - r0), min(i, j));
-            if (run > 0) {
-                if (lane < run) opsrev[n + lane] = (uint8_t)PB_MATCH;
-                n += run; i -= run; j -= run;
-                continue;
+            const int lim = min(32 - r0, min(i, j)); // rows left in this window / cells left on this diagonal
+            const bool indel = run < lim;            // the run ends on a non-MATCH cell that this window still holds
+            run = min(run, lim);
+            if (lane < run) opsrev[n + lane] = (uint8_t)PB_MATCH;
+            n += run; i -= run; j -= run;
+            if (indel) { // same diagonal, so same band word and bit: the cell's pair sits in lane r0 + run
+                const uint32_t hb = (__shfl_sync(FULL, cw.y, r0 + run) >> (k & 31)) & 1u;
+                if (lane == 0) opsrev[n] = (uint8_t)(hb ? PB_INSERT : PB_DELETE);
+                ++n;
+                if (hb) --j; else --i;
             }
-            const uint32_t hb = (__shfl_sync(FULL, cw.y, r0) >> (k & 31)) & 1u;
-            if (lane == 0) opsrev[n] = (uint8_t)(hb ? PB_INSERT : PB_DELETE);
-            ++n;
-            if (hb) --j; else --i;
         }
     }
     __syncwarp();

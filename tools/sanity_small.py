@@ -1,8 +1,6 @@
 #!/usr/bin/env python
-"""A small pass through every pipeline (locate, overlap, all-vs-all, consensus rounds) for compute-sanitizer:
-
-    compute-sanitizer --tool memcheck python tools/sanity_small.py
-"""
+"""A small pass through every pipeline (locate, all-vs-all, consensus rounds, bulk probe): a quick whole-library smoke,
+sized for a run under a checker (compute-sanitizer is closed on this pool: it answered exit 86 without running)."""
 import os
 import sys
 
