@@ -353,7 +353,7 @@ __device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c)
 template <int S>
 __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S], const uint32_t (&keep)[S], uint32_t (&Vp)[S],
                                              uint32_t (&Vn)[S], const uint32_t *__restrict__ pl, int thrs, unsigned sh, int lane,
-                                             int sd, bool stores, uint32_t *__restrict__ prow, uint32_t c31, uint32_t c2)
+                                             int sd, bool stores, uint32_t *__restrict__ prow, uint32_t c31, uint32_t c2, int LN = 32)
 {
     // phase A: slide the band one bit (across words and lanes), fetch Eq, block add with carry-in 0
     uint32_t nx = __shfl_down_sync(FULL, (Hp[0] & 1u) | ((Hn[0] & 1u) << 1), 1);
@@ -422,7 +422,7 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
         Hn[s] = vps & Xh;
         // parents of band word w = lane*S+s: {MATCH plane, INSERT plane} as one 8-byte pair at pair index s*32+lane
         // lanes whose words all lie past the band skip the store; a partly used lane writes its S words (row padding)
-        if (stores) reinterpret_cast<uint2 *>(prow)[s * 32] = make_uint2(Mw[s], Hp[s]);
+        if (stores) reinterpret_cast<uint2 *>(prow)[s * LN] = make_uint2(Mw[s], Hp[s]);
     }
     return d0w;
 }
@@ -654,11 +654,18 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
         keep[s] = kp;
     }
     const int wd = D >> 5, Ld = wd / S, sd = wd % S; // owner of the main-diagonal bit k = D
-#ifdef PB_STORE_PRED
-    const bool stores = 32 * lane * S <= 2 * D; // this lane holds at least one in-band bit
+#ifdef PB_COMPACT_ROWS
+    // Experiment switch: parent rows hold only the lanes that own band bits, rounded up to whole 32-byte sectors (4 lanes),
+    // row = [slot][lane < LN] -- ~13 % fewer bytes written on config 2, bit-exact, and slower (92.8 vs 90.0 ms of K3): the
+    // forward pass is bound by instruction issue, not by the bytes it writes.  (Predicating the stores while keeping the
+    // 32-lane row stride left holes of partly written lines and cost 40 %.)
+    const int LN = min(32, (((((2 * D + 1 + 31) >> 5) + S - 1) / S) + 3) & ~3);
+    const bool stores = lane < LN;
 #else
+    const int LN = 32;
     const bool stores = true; // measured: predicating the pair stores costs 40 % (A/B on B200), the padding writes are cheaper
 #endif
+    const size_t rstride = (size_t)2 * LN * S; // words per parent row
 
     int cii = 0;                          // cost(i,i), warp-uniform, advanced once per 32-row block
     int colc = 0, colbest = 0, col_i = 0; // cost(i,len_b) tracking when len_a > len_b
@@ -680,14 +687,14 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
         const int q = (i0 - 1) >> 5; // first plane word of the block's rows (logical index)
         const uint32_t *plq = planes + q + lane * S + (PAD ? lane + q / S : 0);
         const int thrs = S - q % S;
-        uint32_t *prow = par + (size_t)(i0 - 1) * (2 * T) + 2 * lane;
+        uint32_t *prow = par + (size_t)(i0 - 1) * rstride + 2 * lane;
         uint32_t hist = 0u;
         for (int t = 0; t < tmax; ++t) {
             int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
             if (IRR && ((awi >> t) & 1u)) ca = irr_plane(A, a_bit + i0 - 1 + t, a_tab);
-            const uint32_t d0w = row_step<S>(Hp, Hn, keep, Vp, Vn, plq + ca * PW, thrs, (unsigned)t, lane, sd, stores, prow, c31, c2);
+            const uint32_t d0w = row_step<S>(Hp, Hn, keep, Vp, Vn, plq + ca * PW, thrs, (unsigned)t, lane, sd, stores, prow, c31, c2, LN);
             hist = __funnelshift_r(hist, d0w >> (D & 31), 1); // row t's diagonal D0 bit enters at bit 31 (meaningful in the diagonal's owner lane)
-            prow += 2 * T;
+            prow += rstride;
         }
         hist >>= 32 - tmax; // row t of the block now sits at bit t
         hist = __shfl_sync(FULL, hist, Ld);
@@ -719,7 +726,7 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
             if (IRR && ((awi >> t) & 1u)) ca = irr_plane(A, a_bit + i - 1, a_tab);
             const int q = (i - 1) >> 5;
             row_step<S>(Hp, Hn, keep, Vp, Vn, planes + ca * PW + q + lane * S + (PAD ? lane + q / S : 0), S - q % S, (unsigned)t,
-                        lane, sd, stores, par + (size_t)(i - 1) * (2 * T) + 2 * lane, c31, c2);
+                        lane, sd, stores, par + (size_t)(i - 1) * rstride + 2 * lane, c31, c2, LN);
             const int k = len_b - i + D, wk = k >> 5, Lk = wk / S, sk = wk % S;
             uint32_t vpw = 0u, vnw = 0u;
 #pragma unroll
@@ -746,7 +753,7 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
     auto par_pair = [&](int row, int w) -> uint2 { // {MATCH word, INSERT word} of band word w of DP row `row`
         if (row < 1 || w < 0 || 32 * w > 2 * D) return make_uint2(0u, 0u);
         const int L = w / S, s = w - L * S;
-        return __ldcg(reinterpret_cast<const uint2 *>(par + (size_t)(row - 1) * (2 * T)) + s * 32 + L);
+        return __ldcg(reinterpret_cast<const uint2 *>(par + (size_t)(row - 1) * rstride) + s * LN + L);
     };
     finish_alignment(len_a, len_b, D, a_len, R, cii, colbest, col_i, planes, planes + T, par_pair, opsrev, ops_out, res);
 }
