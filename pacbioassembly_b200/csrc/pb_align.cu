@@ -29,8 +29,10 @@
 #endif
 #ifndef PB_TB_WINDOWS
 // traceback: 32-row parent windows in flight per warp (the one being walked + prefetched ones).  The backward walk is 19 % of K3
-// (measured by skipping it: 91.1 -> 74.2 ms) and it is DRAM traffic, not latency: every 8-byte pair it reads sits in its own
-// 128-byte line of a row written long ago.  Deeper prefetch only adds traffic: 3 windows 89.9 ms, 5 windows 91.7, 8 windows 98.9.
+// (measured by skipping it: 91.1 -> 74.2 ms).  It is neither its instruction count (a loop with a third fewer instructions per
+// step ran in the same time) nor latency (deeper prefetch is slower: 3 windows 89.9 ms, 5 windows 91.7, 8 windows 98.9): every
+// 8-byte pair it reads sits in its own 128-byte line of a row written long ago, and those scattered reads land in a stream of
+// writes that already runs at ~75 % of the HBM peak.
 #define PB_TB_WINDOWS 3
 #endif
 #ifndef PB_PAD_MOD
@@ -478,21 +480,13 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
         uint2 wp0[PB_TB_WINDOWS], wp1[PB_TB_WINDOWS];
 #pragma unroll
         for (int t = 0; t < PB_TB_WINDOWS; ++t) { wi0[t] = -1; wwb[t] = 0; wp0[t] = make_uint2(0u, 0u); wp1[t] = wp0[t]; }
-        while ((i | j) != 0 && n < guard) {
-            if (i == 0) { // init_cell row 0: INSERT all the way
-                for (int t = lane; t < j; t += 32) opsrev[n + t] = (uint8_t)PB_INSERT;
-                n += j; j = 0;
-                break;
-            }
-            if (j == 0) { // init_cell column 0: DELETE all the way
-                for (int t = lane; t < i; t += 32) opsrev[n + t] = (uint8_t)PB_DELETE;
-                n += i; i = 0;
-                break;
-            }
-            const int k = j - i + D, w = k >> 5;
-            if (wi0[0] < 0 || wi0[0] - i >= 32 || w < wwb[0] || w > wwb[0] + 1) {
-                const int wb = window_base(k);
-                if (wi0[1] == i && w >= wwb[1] && w <= wwb[1] + 1) { // the usual case: 32 rows consumed, prediction held
+        int kbase = 0, wend = 0; // the current window covers band bits [kbase, kbase+64) of rows (wend, wend+32]
+        bool have = false;
+        while (i > 0 && j > 0 && n < guard) {
+            const int k = j - i + D;
+            if (!have || i <= wend || (unsigned)(k - kbase) >= 64u) {
+                const int w = k >> 5, wb = window_base(k);
+                if (have && wi0[1] == i && w >= wwb[1] && w <= wwb[1] + 1) { // the usual case: 32 rows consumed, prediction held
 #pragma unroll
                     for (int t = 0; t + 1 < PB_TB_WINDOWS; ++t) { wi0[t] = wi0[t + 1]; wwb[t] = wwb[t + 1]; wp0[t] = wp0[t + 1]; wp1[t] = wp1[t + 1]; }
                     wi0[PB_TB_WINDOWS - 1] = wi0[0] - 32 * (PB_TB_WINDOWS - 1);
@@ -507,12 +501,14 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
                         wp1[t] = par_pair(wi0[t] - lane, wb + 1);
                     }
                 }
+                have = true;
+                kbase = 32 * wwb[0];
+                wend = wi0[0] - 32;
             }
-            const int cur_i0 = wi0[0], cur_wb = wwb[0];
-            const uint2 c0 = wp0[0], c1 = wp1[0];
-            const int r0 = cur_i0 - i; // lane that holds the current row
-            const uint2 cw = (w == cur_wb) ? c0 : c1;
-            const uint32_t B = __ballot_sync(FULL, (cw.x >> (k & 31)) & 1u) >> r0; // bit t: cell (i-t, j-t) is MATCH
+            const int r0 = wi0[0] - i;   // lane that holds the current row
+            const int kb = k - kbase;    // 0..63: bit inside the two-word window
+            const uint32_t mword = kb < 32 ? wp0[0].x : wp1[0].x;
+            const uint32_t B = __ballot_sync(FULL, (mword >> (kb & 31)) & 1u) >> r0; // bit t: cell (i-t, j-t) is MATCH
             int run = (~B) ? __ffs(~B) - 1 : 32;
             const int lim = min(32 - r0, min(i, j)); // rows left in this window / cells left on this diagonal
             const bool indel = run < lim;            // the run ends on a non-MATCH cell that this window still holds
@@ -520,10 +516,20 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
             if (lane < run) opsrev[n + lane] = (uint8_t)PB_MATCH;
             n += run; i -= run; j -= run;
             if (indel) { // same diagonal, so same band word and bit: the cell's pair sits in lane r0 + run
-                const uint32_t hb = (__shfl_sync(FULL, cw.y, r0 + run) >> (k & 31)) & 1u;
+                const uint32_t iword = kb < 32 ? wp0[0].y : wp1[0].y;
+                const uint32_t hb = (__shfl_sync(FULL, iword, r0 + run) >> (kb & 31)) & 1u;
                 if (lane == 0) opsrev[n] = (uint8_t)(hb ? PB_INSERT : PB_DELETE);
                 ++n;
                 if (hb) --j; else --i;
+            }
+        }
+        if (n < guard) {
+            if (i == 0 && j > 0) { // init_cell row 0: INSERT all the way
+                for (int t = lane; t < j; t += 32) opsrev[n + t] = (uint8_t)PB_INSERT;
+                n += j;
+            } else if (j == 0 && i > 0) { // init_cell column 0: DELETE all the way
+                for (int t = lane; t < i; t += 32) opsrev[n + t] = (uint8_t)PB_DELETE;
+                n += i;
             }
         }
     }
