@@ -35,6 +35,10 @@
 // writes that already runs at ~75 % of the HBM peak.
 #define PB_TB_WINDOWS 3
 #endif
+#ifndef PB_TB_RING
+#define PB_TB_RING 6 // traceback windows in the shared-memory ring (the one being walked + asynchronous prefetches)
+#endif
+#define PB_TB_RING_WORDS (PB_TB_RING * 128 + 2 * PB_TB_RING + 2)
 #ifndef PB_PAD_MOD
 // Band classes with S % PB_PAD_MOD == 0 keep their Eq planes padded (one word per S words) so that the lane stride S+1 is free of
 // shared-memory bank conflicts.  The padding costs ~4 ALU instructions per band word and row (the window of a lane crosses one
@@ -305,6 +309,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase)
     return ok != 0;
 }
 
+// ---- cp.async (LDGSTS): global -> shared without a register in between.  Experiment (-DPB_TB_ASYNC): the traceback prefetches its
+// parent windows into a shared-memory ring with it, because a prefetch that lands in registers has to be complete before the
+// registers can be rotated to the next window (ncu: 64 % of the traceback's stalls are long-scoreboard waits on the first use of a
+// window).  Bit-exact, and no faster: 4 windows 92.2 ms, 6 windows 94.3, 10 windows 100.9 against 92.4 ms for the register walk on
+// the same box.  The path leaves its two predicted band words every 10-20 windows and every window fetched ahead is then thrown
+// away, so depth buys DRAM traffic (each 8-byte pair costs a 128-byte line) faster than it hides latency.  What the walk needs is
+// a parent layout that keeps consecutive rows of a band word in one line -- see DESIGN.md.
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src, int src_bytes) // src_bytes 0: zero-fill
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // multi-word add helpers: the carry chain lives in the PTX condition code between consecutive statements
 __device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b)
 {
@@ -432,9 +450,12 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
 // goal_cell + coverage test + find_path for one finished forward pass (seq_aligner.h:111-116,191-233); called by the
 // whole warp with warp-uniform arguments.  hp_words / hn_words: the final row's horizontal deltas in shared memory (band
 // word w at [w]); par_pair(row, w): the {MATCH word, INSERT word} pair of band word w of DP row `row` (zero outside).
-template <class PairAt>
+// par_addr(row, w): the pair's address in global memory (NULL outside) and ring: PB_TB_RING_WORDS words of this warp's shared
+// memory for the asynchronous window prefetch; ring == NULL walks with register prefetch through par_pair instead.
+template <class PairAt, class PairAddr>
 __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, int a_len, double R, int cii, int colbest, int col_i,
-                                                 const uint32_t *hp_words, const uint32_t *hn_words, PairAt par_pair,
+                                                 const uint32_t *hp_words, const uint32_t *hn_words, PairAt par_pair, PairAddr par_addr,
+                                                 uint32_t *ring, const void *gbase,
                                                  uint8_t *__restrict__ opsrev, uint8_t *__restrict__ ops_out, AlnRes &res)
 {
     const int lane = threadIdx.x & 31;
@@ -472,7 +493,84 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
     // window = the band word under the path plus the neighbour the path is closer to
     auto window_base = [](int k) -> int { return (k >> 5) - ((k & 31) < 16 ? 1 : 0); };
     int n = 0;
-    {
+    if (ring) {
+        // ---- walk with asynchronous prefetch: PB_TB_RING windows of 32 rows x 2 band words live in shared memory, filled by
+        // cp.async; slot q: pair of (row i0-lane, word wb+h) at ring[q*128 + h*64 + 2*lane], its (i0, wb) at meta[2q], meta[2q+1]
+        int i = matlen_a, j = matlen_b;
+        const int guard = len_a + len_b + 1;
+        int *meta = reinterpret_cast<int *>(ring + PB_TB_RING * 128);
+        auto fetch = [&](int slot, int i0w, int wb) {
+            const int row = i0w - lane;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint2 *src = par_addr(row, wb + h);
+                cp_async8(ring + slot * 128 + h * 64 + 2 * lane, src ? (const void *)src : gbase, src ? 8 : 0);
+            }
+            if (lane == 0) { meta[2 * slot] = i0w; meta[2 * slot + 1] = wb; }
+            cp_async_commit();
+        };
+        int cur_slot = 0, cur_i0 = 0, kbase = 0, wend = 0;
+        uint2 c0 = make_uint2(0u, 0u), c1 = c0;
+        bool have = false;
+        while (i > 0 && j > 0 && n < guard) {
+            const int k = j - i + D;
+            if (!have || i <= wend || (unsigned)(k - kbase) >= 64u) {
+                const int w = k >> 5, wb = window_base(k);
+                const int nslot = cur_slot + 1 == PB_TB_RING ? 0 : cur_slot + 1;
+                bool usual = have;
+                if (usual) {
+                    const int nwb = meta[2 * nslot + 1];
+                    usual = meta[2 * nslot] == i && w >= nwb && w <= nwb + 1; // 32 rows consumed and the prediction held
+                }
+                __syncwarp();
+                if (usual) { // refill the slot just walked with the window PB_TB_RING-1 ahead of the new current one
+                    fetch(cur_slot, i - 32 * (PB_TB_RING - 1), wb);
+                    cur_slot = nslot;
+                } else { // cold start, or the path left the predicted words
+                    cp_async_wait<0>();
+#pragma unroll
+                    for (int t = 0; t < PB_TB_RING; ++t) fetch(t, i - 32 * t, wb);
+                    cur_slot = 0;
+                }
+                cp_async_wait<PB_TB_RING - 1>(); // groups complete in order: everything but the PB_TB_RING-1 newest has landed
+                __syncwarp();
+                c0 = *reinterpret_cast<const uint2 *>(ring + cur_slot * 128 + 2 * lane);
+                c1 = *reinterpret_cast<const uint2 *>(ring + cur_slot * 128 + 64 + 2 * lane);
+                cur_i0 = meta[2 * cur_slot];
+                kbase = 32 * meta[2 * cur_slot + 1];
+                wend = cur_i0 - 32;
+                have = true;
+            }
+            const int r0 = cur_i0 - i;   // lane that holds the current row
+            const int kb = k - kbase;    // 0..63: bit inside the two-word window
+            const uint32_t mword = kb < 32 ? c0.x : c1.x;
+            const uint32_t B = __ballot_sync(FULL, (mword >> (kb & 31)) & 1u) >> r0; // bit t: cell (i-t, j-t) is MATCH
+            int run = (~B) ? __ffs(~B) - 1 : 32;
+            const int lim = min(32 - r0, min(i, j));
+            const bool indel = run < lim;
+            run = min(run, lim);
+            if (lane < run) opsrev[n + lane] = (uint8_t)PB_MATCH;
+            n += run; i -= run; j -= run;
+            if (indel) {
+                const uint32_t iword = kb < 32 ? c0.y : c1.y;
+                const uint32_t hb = (__shfl_sync(FULL, iword, r0 + run) >> (kb & 31)) & 1u;
+                if (lane == 0) opsrev[n] = (uint8_t)(hb ? PB_INSERT : PB_DELETE);
+                ++n;
+                if (hb) --j; else --i;
+            }
+        }
+        cp_async_wait<0>(); // nothing may still be landing in the ring when the shared memory is reused
+        __syncwarp();
+        if (n < guard) {
+            if (i == 0 && j > 0) { // init_cell row 0: INSERT all the way
+                for (int t = lane; t < j; t += 32) opsrev[n + t] = (uint8_t)PB_INSERT;
+                n += j;
+            } else if (j == 0 && i > 0) { // init_cell column 0: DELETE all the way
+                for (int t = lane; t < i; t += 32) opsrev[n + t] = (uint8_t)PB_DELETE;
+                n += i;
+            }
+        }
+    } else {
         int i = matlen_a, j = matlen_b;
         const int guard = len_a + len_b + 1; // a path can never be longer; keeps a corrupted plane from hanging the GPU
         // windows in flight: [0] is the one being walked, [1..] are fetched ahead (DRAM latency under load is several windows long)
@@ -756,12 +854,21 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
         planes[T + lane * S + s] = Hn[s];
     }
     __syncwarp();
-    auto par_pair = [&](int row, int w) -> uint2 { // {MATCH word, INSERT word} of band word w of DP row `row`
-        if (row < 1 || w < 0 || 32 * w > 2 * D) return make_uint2(0u, 0u);
+    auto par_addr = [&](int row, int w) -> const uint2 * { // {MATCH word, INSERT word} of band word w of DP row `row`
+        if (row < 1 || w < 0 || 32 * w > 2 * D) return nullptr;
         const int L = w / S, s = w - L * S;
-        return __ldcg(reinterpret_cast<const uint2 *>(par + (size_t)(row - 1) * rstride) + s * LN + L);
+        return reinterpret_cast<const uint2 *>(par + (size_t)(row - 1) * rstride) + s * LN + L;
     };
-    finish_alignment(len_a, len_b, D, a_len, R, cii, colbest, col_i, planes, planes + T, par_pair, opsrev, ops_out, res);
+    auto par_pair = [&](int row, int w) -> uint2 {
+        const uint2 *q = par_addr(row, w);
+        return q ? __ldcg(q) : make_uint2(0u, 0u);
+    };
+#ifdef PB_TB_ASYNC // experiment switch, see cp_async8
+    uint32_t *ring = planes + 2 * T; // behind the final deltas; the Eq planes and the staging area are dead by now
+#else
+    uint32_t *ring = nullptr;
+#endif
+    finish_alignment(len_a, len_b, D, a_len, R, cii, colbest, col_i, planes, planes + T, par_pair, par_addr, ring, par, opsrev, ops_out, res);
 }
 
 struct AlignLaunch {
@@ -1063,8 +1170,9 @@ align_pairs_packed_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *_
                     if (row < 1 || w < 0 || 32 * w > 2 * f_D) return make_uint2(0u, 0u);
                     return __ldcg(reinterpret_cast<const uint2 *>(f_par + (size_t)(row - 1) * (2 * LANES)) + w);
                 };
-                finish_alignment(f_la, f_lb, f_D, f_alen, p.R, f_cii, f_cb, f_ci, f_planes, f_planes + LANES, par_pair, f_opsrev,
-                                 p.ops ? p.ops + p.ops_off[f_k] : nullptr, res);
+                auto no_addr = [](int, int) -> const uint2 * { return nullptr; }; // narrow bands: synchronous window loads
+                finish_alignment(f_la, f_lb, f_D, f_alen, p.R, f_cii, f_cb, f_ci, f_planes, f_planes + LANES, par_pair, no_addr,
+                                 (uint32_t *)nullptr, (const void *)nullptr, f_opsrev, p.ops ? p.ops + p.ops_off[f_k] : nullptr, res);
             }
             if (lane == 0) {
                 if (p.stats) { atomicAdd(p.stats, (unsigned long long)res.cells); atomicAdd(p.stats + 1, 1ull); }
@@ -1174,6 +1282,9 @@ static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, int locate, si
         g->PW = (g->PW + 3) & ~3; // 16-byte aligned sub-arrays (TMA destination)
         g->RW = PB_STAGE_WORDS; // TMA staging buffer per raw plane
         g->warp_words = (key_irr(key) ? 8 : 4) * g->PW + (key_irr(key) ? 3 : 2) * g->RW;
+#ifdef PB_TB_ASYNC
+        g->warp_words = std::max(g->warp_words, (2 * T + PB_TB_RING_WORDS + 3) & ~3); // final deltas + the traceback's window ring
+#endif
         g->par_words = (size_t)std::max(cp.max_rows, 1) * 2 * T;
     }
     // fewer warps per CTA when the per-warp planes are large (long sequences): the packed kernels stay under 96 KB so that two
