@@ -35,10 +35,17 @@
 // writes that already runs at ~75 % of the HBM peak.
 #define PB_TB_WINDOWS 3
 #endif
+// Experiment switches for the parent layout and the traceback prefetch ("Where K3's time goes"):
+//   -DPB_UNIT16   parents as 16-byte units of two adjacent band words per lane (one STG.128 per slot pair, one DRAM line per row
+//                 for the walk while the path sits inside a unit)
+//   -DPB_TB_ASYNC traceback windows prefetched into a shared-memory ring with cp.async (no register waits for a load)
+// Each alone changed nothing; both together, 4 windows deep, took K3 from 90.0 to 85.2 ms per config-2 step with identical
+// locate / align results -- but that build faults (illegal address) in the all-vs-all tests, and a 6-deep ring faults on
+// config 2, so neither is on by default until the out-of-bounds access is found.
 #ifndef PB_TB_RING
-#define PB_TB_RING 6 // traceback windows in the shared-memory ring (the one being walked + asynchronous prefetches)
+#define PB_TB_RING 4 // traceback windows in the shared-memory ring (the one being walked + asynchronous prefetches); 5: same, 8: slower
 #endif
-#define PB_TB_RING_WORDS (PB_TB_RING * 128 + 2 * PB_TB_RING + 2)
+#define PB_TB_RING_WORDS (PB_TB_RING * 256 + 8 * PB_TB_RING + 8)
 #ifndef PB_PAD_MOD
 // Band classes with S % PB_PAD_MOD == 0 keep their Eq planes padded (one word per S words) so that the lane stride S+1 is free of
 // shared-memory bank conflicts.  The padding costs ~4 ALU instructions per band word and row (the window of a lane crosses one
@@ -320,6 +327,10 @@ __device__ __forceinline__ void cp_async8(void *dst_smem, const void *src, int s
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, int src_bytes) // L2 only (.cg), src_bytes 0: zero-fill
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -373,7 +384,8 @@ __device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c)
 template <int S>
 __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S], const uint32_t (&keep)[S], uint32_t (&Vp)[S],
                                              uint32_t (&Vn)[S], const uint32_t *__restrict__ pl, int thrs, unsigned sh, int lane,
-                                             int sd, bool stores, uint32_t *__restrict__ prow, uint32_t c31, uint32_t c2, int LN = 32)
+                                             int sd, bool stores, uint32_t *__restrict__ prow, uint32_t c31, uint32_t c2, int LN = 32,
+                                             int tail_off = 0)
 {
     // phase A: slide the band one bit (across words and lanes), fetch Eq, block add with carry-in 0
     uint32_t nx = __shfl_down_sync(FULL, (Hp[0] & 1u) | ((Hn[0] & 1u) << 1), 1);
@@ -432,6 +444,9 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
 
     // phase C: new horizontal deltas, INSERT plane
     uint32_t pprev = pv << 31, nprev = (pv >> 1) << 31; // bit 31 = delta entering this word from the left
+#ifdef PB_UNIT16
+    uint32_t heldM = 0u, heldI = 0u;
+#endif
 #pragma unroll
     for (int s = 0; s < S; ++s) {
         const uint32_t vps = PB_FUNNEL_L1(pprev, Vp[s], c2), vns = PB_FUNNEL_L1(nprev, Vn[s], c2);
@@ -442,7 +457,19 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
         Hn[s] = vps & Xh;
         // parents of band word w = lane*S+s: {MATCH plane, INSERT plane} as one 8-byte pair at pair index s*32+lane
         // lanes whose words all lie past the band skip the store; a partly used lane writes its S words (row padding)
+#ifdef PB_UNIT16
+        // parents as 16-byte units of two adjacent band words per lane: {M[2p], I[2p], M[2p+1], I[2p+1]} at unit p*LN + lane
+        // (one STG.128 per slot pair); the last slot of an odd S follows as 8-byte pairs at tail_off.  prow = row base + 4*lane.
+        if ((s & 1) == 0 && s + 1 < S) {
+            heldM = Mw[s]; heldI = Hp[s];
+        } else if (s & 1) {
+            if (stores) reinterpret_cast<uint4 *>(prow)[(s >> 1) * LN] = make_uint4(heldM, heldI, Mw[s], Hp[s]);
+        } else {
+            if (stores) *reinterpret_cast<uint2 *>(prow + tail_off) = make_uint2(Mw[s], Hp[s]);
+        }
+#else
         if (stores) reinterpret_cast<uint2 *>(prow)[s * LN] = make_uint2(Mw[s], Hp[s]);
+#endif
     }
     return d0w;
 }
@@ -452,11 +479,14 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
 // word w at [w]); par_pair(row, w): the {MATCH word, INSERT word} pair of band word w of DP row `row` (zero outside).
 // par_addr(row, w): the pair's address in global memory (NULL outside) and ring: PB_TB_RING_WORDS words of this warp's shared
 // memory for the asynchronous window prefetch; ring == NULL walks with register prefetch through par_pair instead.
-template <class PairAt, class PairAddr>
+struct NoUnit { __device__ void operator()(int, int &, int &) const {} };
+struct NoUnitLoad { __device__ uint4 operator()(int, int, int) const { return make_uint4(0u, 0u, 0u, 0u); } };
+template <bool UNITS, class PairAt, class PairAddr, class UnitOf = NoUnit, class UnitLoad = NoUnitLoad>
 __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, int a_len, double R, int cii, int colbest, int col_i,
                                                  const uint32_t *hp_words, const uint32_t *hn_words, PairAt par_pair, PairAddr par_addr,
                                                  uint32_t *ring, const void *gbase,
-                                                 uint8_t *__restrict__ opsrev, uint8_t *__restrict__ ops_out, AlnRes &res)
+                                                 uint8_t *__restrict__ opsrev, uint8_t *__restrict__ ops_out, AlnRes &res,
+                                                 UnitOf unit_of = UnitOf(), UnitLoad unit_load = UnitLoad())
 {
     const int lane = threadIdx.x & 31;
     // ---- goal_cell, seq_aligner.h:191-213
@@ -493,7 +523,170 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
     // window = the band word under the path plus the neighbour the path is closer to
     auto window_base = [](int k) -> int { return (k >> 5) - ((k & 31) < 16 ? 1 : 0); };
     int n = 0;
-    if (ring) {
+    if (UNITS && ring) {
+        // ---- units + asynchronous prefetch: slot q of the ring holds, per lane, the primary unit (16 bytes at ring[q*256 + 4*lane])
+        // and the secondary one (ring[q*256 + 128 + 4*lane]); meta[8q..] = i0, b0, n0, b1, n1
+        int i = matlen_a, j = matlen_b;
+        const int guard = len_a + len_b + 1;
+        int *meta = reinterpret_cast<int *>(ring + PB_TB_RING * 256);
+        auto fetch = [&](int slot, int i0w, int pb, int pn, int sb, int sn) {
+            const int row = i0w - lane;
+            const uint2 *q0 = par_addr(row, pb);
+            uint32_t *dst = ring + slot * 256 + 4 * lane;
+            if (pn == 2) cp_async16(dst, q0 ? (const void *)q0 : gbase, q0 ? 16 : 0);
+            else { cp_async8(dst, q0 ? (const void *)q0 : gbase, q0 ? 8 : 0); }
+            if (sn) {
+                const uint2 *q1 = par_addr(row, sb);
+                if (sn == 2) cp_async16(dst + 128, q1 ? (const void *)q1 : gbase, q1 ? 16 : 0);
+                else cp_async8(dst + 128, q1 ? (const void *)q1 : gbase, q1 ? 8 : 0);
+            }
+            if (lane == 0) { int *m = meta + 8 * slot; m[0] = i0w; m[1] = pb; m[2] = pn; m[3] = sb; m[4] = sn; }
+            cp_async_commit();
+        };
+        int cur_slot = 0, cur_i0 = 0, wend = 0, cb0 = 0, cn0 = 0, cb1 = 0, cn1 = 0;
+        uint4 U0 = make_uint4(0u, 0u, 0u, 0u), U1 = U0;
+        bool have = false;
+        while (i > 0 && j > 0 && n < guard) {
+            const int k = j - i + D, w = k >> 5, kb = k & 31;
+            if (!have || i <= wend || !((unsigned)(w - cb0) < (unsigned)cn0 || (unsigned)(w - cb1) < (unsigned)cn1)) {
+                const int nslot = cur_slot + 1 == PB_TB_RING ? 0 : cur_slot + 1;
+                bool usual = have;
+                if (usual) {
+                    const int *m = meta + 8 * nslot;
+                    usual = m[0] == i && ((unsigned)(w - m[1]) < (unsigned)m[2] || (unsigned)(w - m[3]) < (unsigned)m[4]);
+                }
+                __syncwarp();
+                if (usual) { // refill the slot just walked with the window PB_TB_RING-1 ahead, same units as the newest one
+                    const int last = cur_slot == 0 ? PB_TB_RING - 1 : cur_slot - 1;
+                    const int *m = meta + 8 * last;
+                    const int pb = m[1], pn = m[2], sb = m[3], sn = m[4];
+                    __syncwarp();
+                    fetch(cur_slot, i - 32 * (PB_TB_RING - 1), pb, pn, sb, sn);
+                    cur_slot = nslot;
+                } else { // cold start, or the path left the predicted units
+                    cp_async_wait<0>();
+                    int pb, pn, sb = 0, sn = 0;
+                    unit_of(w, pb, pn);
+                    const int pos = (w - pb) * 32 + kb;
+                    if (pos < 8 && pb > 0) unit_of(pb - 1, sb, sn);
+                    else if (pos >= 32 * pn - 8 && 32 * (pb + pn) <= 2 * D) unit_of(pb + pn, sb, sn);
+#pragma unroll
+                    for (int t = 0; t < PB_TB_RING; ++t) fetch(t, i - 32 * t, pb, pn, sb, sn);
+                    cur_slot = 0;
+                }
+                cp_async_wait<PB_TB_RING - 1>();
+                __syncwarp();
+                const int *m = meta + 8 * cur_slot;
+                cur_i0 = m[0]; cb0 = m[1]; cn0 = m[2]; cb1 = m[3]; cn1 = m[4];
+                U0 = *reinterpret_cast<const uint4 *>(ring + cur_slot * 256 + 4 * lane);
+                U1 = cn1 ? *reinterpret_cast<const uint4 *>(ring + cur_slot * 256 + 128 + 4 * lane) : make_uint4(0u, 0u, 0u, 0u);
+                wend = cur_i0 - 32;
+                have = true;
+            }
+            const int r0 = cur_i0 - i;
+            const int d0 = w - cb0;
+            const bool prim = (unsigned)d0 < (unsigned)cn0;
+            const int d = prim ? d0 : w - cb1;
+            const uint4 u = prim ? U0 : U1;
+            const uint32_t mword = d ? u.z : u.x;
+            const uint32_t B = __ballot_sync(FULL, (mword >> kb) & 1u) >> r0;
+            int run = (~B) ? __ffs(~B) - 1 : 32;
+            const int lim = min(32 - r0, min(i, j));
+            const bool indel = run < lim;
+            run = min(run, lim);
+            if (lane < run) opsrev[n + lane] = (uint8_t)PB_MATCH;
+            n += run; i -= run; j -= run;
+            if (indel) {
+                const uint32_t iword = d ? u.w : u.y;
+                const uint32_t hb = (__shfl_sync(FULL, iword, r0 + run) >> kb) & 1u;
+                if (lane == 0) opsrev[n] = (uint8_t)(hb ? PB_INSERT : PB_DELETE);
+                ++n;
+                if (hb) --j; else --i;
+            }
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+        if (n < guard) {
+            if (i == 0 && j > 0) {
+                for (int t = lane; t < j; t += 32) opsrev[n + t] = (uint8_t)PB_INSERT;
+                n += j;
+            } else if (j == 0 && i > 0) {
+                for (int t = lane; t < i; t += 32) opsrev[n + t] = (uint8_t)PB_DELETE;
+                n += i;
+            }
+        }
+    } else if (UNITS) {
+        // ---- walk over 16-byte parent units.  A window is 32 rows of the unit under the path (one load, one DRAM line per row)
+        // and, only while the path is within 8 bits of that unit's edge, the neighbouring unit as well.
+        int i = matlen_a, j = matlen_b;
+        const int guard = len_a + len_b + 1;
+        int wi0[PB_TB_WINDOWS], b0[PB_TB_WINDOWS], n0[PB_TB_WINDOWS], b1[PB_TB_WINDOWS], n1[PB_TB_WINDOWS];
+        uint4 u0[PB_TB_WINDOWS], u1[PB_TB_WINDOWS];
+#pragma unroll
+        for (int t = 0; t < PB_TB_WINDOWS; ++t) { wi0[t] = -1; b0[t] = n0[t] = b1[t] = n1[t] = 0; u0[t] = make_uint4(0u, 0u, 0u, 0u); u1[t] = u0[t]; }
+        bool have = false;
+        int wend = 0;
+        while (i > 0 && j > 0 && n < guard) {
+            const int k = j - i + D, w = k >> 5, kb = k & 31;
+            if (!have || i <= wend || !((unsigned)(w - b0[0]) < (unsigned)n0[0] || (unsigned)(w - b1[0]) < (unsigned)n1[0])) {
+                if (have && wi0[1] == i && ((unsigned)(w - b0[1]) < (unsigned)n0[1] || (unsigned)(w - b1[1]) < (unsigned)n1[1])) {
+                    // the usual case: 32 rows consumed and the prediction held; the new far window copies the one in front of it
+#pragma unroll
+                    for (int t = 0; t + 1 < PB_TB_WINDOWS; ++t) {
+                        wi0[t] = wi0[t + 1]; b0[t] = b0[t + 1]; n0[t] = n0[t + 1]; b1[t] = b1[t + 1]; n1[t] = n1[t + 1];
+                        u0[t] = u0[t + 1]; u1[t] = u1[t + 1];
+                    }
+                    constexpr int Z = PB_TB_WINDOWS - 1;
+                    wi0[Z] = wi0[0] - 32 * Z;
+                    u0[Z] = unit_load(wi0[Z] - lane, b0[Z], n0[Z]);
+                    u1[Z] = n1[Z] ? unit_load(wi0[Z] - lane, b1[Z], n1[Z]) : make_uint4(0u, 0u, 0u, 0u);
+                } else { // cold start, or the path left the predicted units
+                    int pb, pn, sb = 0, sn = 0;
+                    unit_of(w, pb, pn);
+                    const int pos = (w - pb) * 32 + kb;
+                    if (pos < 8 && pb > 0) unit_of(pb - 1, sb, sn);
+                    else if (pos >= 32 * pn - 8 && 32 * (pb + pn) <= 2 * D) unit_of(pb + pn, sb, sn);
+#pragma unroll
+                    for (int t = 0; t < PB_TB_WINDOWS; ++t) {
+                        wi0[t] = i - 32 * t; b0[t] = pb; n0[t] = pn; b1[t] = sb; n1[t] = sn;
+                        u0[t] = unit_load(wi0[t] - lane, pb, pn);
+                        u1[t] = sn ? unit_load(wi0[t] - lane, sb, sn) : make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+                have = true;
+                wend = wi0[0] - 32;
+            }
+            const int r0 = wi0[0] - i; // lane that holds the current row
+            const int d0 = w - b0[0];
+            const bool prim = (unsigned)d0 < (unsigned)n0[0];
+            const int d = prim ? d0 : w - b1[0];
+            const uint4 u = prim ? u0[0] : u1[0];
+            const uint32_t mword = d ? u.z : u.x;
+            const uint32_t B = __ballot_sync(FULL, (mword >> kb) & 1u) >> r0; // bit t: cell (i-t, j-t) is MATCH
+            int run = (~B) ? __ffs(~B) - 1 : 32;
+            const int lim = min(32 - r0, min(i, j));
+            const bool indel = run < lim;
+            run = min(run, lim);
+            if (lane < run) opsrev[n + lane] = (uint8_t)PB_MATCH;
+            n += run; i -= run; j -= run;
+            if (indel) {
+                const uint32_t iword = d ? u.w : u.y;
+                const uint32_t hb = (__shfl_sync(FULL, iword, r0 + run) >> kb) & 1u;
+                if (lane == 0) opsrev[n] = (uint8_t)(hb ? PB_INSERT : PB_DELETE);
+                ++n;
+                if (hb) --j; else --i;
+            }
+        }
+        if (n < guard) {
+            if (i == 0 && j > 0) { // init_cell row 0: INSERT all the way
+                for (int t = lane; t < j; t += 32) opsrev[n + t] = (uint8_t)PB_INSERT;
+                n += j;
+            } else if (j == 0 && i > 0) { // init_cell column 0: DELETE all the way
+                for (int t = lane; t < i; t += 32) opsrev[n + t] = (uint8_t)PB_DELETE;
+                n += i;
+            }
+        }
+    } else if (ring) {
         // ---- walk with asynchronous prefetch: PB_TB_RING windows of 32 rows x 2 band words live in shared memory, filled by
         // cp.async; slot q: pair of (row i0-lane, word wb+h) at ring[q*128 + h*64 + 2*lane], its (i0, wb) at meta[2q], meta[2q+1]
         int i = matlen_a, j = matlen_b;
@@ -770,6 +963,11 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
     const bool stores = true; // measured: predicating the pair stores costs 40 % (A/B on B200), the padding writes are cheaper
 #endif
     const size_t rstride = (size_t)2 * LN * S; // words per parent row
+#ifdef PB_UNIT16
+    const int lane_off = 4 * lane, tail_off = (S / 2) * LN * 4 - 2 * lane; // units of 4 words per lane, then the odd slot's pairs
+#else
+    const int lane_off = 2 * lane, tail_off = 0;
+#endif
 
     int cii = 0;                          // cost(i,i), warp-uniform, advanced once per 32-row block
     int colc = 0, colbest = 0, col_i = 0; // cost(i,len_b) tracking when len_a > len_b
@@ -791,12 +989,12 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
         const int q = (i0 - 1) >> 5; // first plane word of the block's rows (logical index)
         const uint32_t *plq = planes + q + lane * S + (PAD ? lane + q / S : 0);
         const int thrs = S - q % S;
-        uint32_t *prow = par + (size_t)(i0 - 1) * rstride + 2 * lane;
+        uint32_t *prow = par + (size_t)(i0 - 1) * rstride + lane_off;
         uint32_t hist = 0u;
         for (int t = 0; t < tmax; ++t) {
             int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
             if (IRR && ((awi >> t) & 1u)) ca = irr_plane(A, a_bit + i0 - 1 + t, a_tab);
-            const uint32_t d0w = row_step<S>(Hp, Hn, keep, Vp, Vn, plq + ca * PW, thrs, (unsigned)t, lane, sd, stores, prow, c31, c2, LN);
+            const uint32_t d0w = row_step<S>(Hp, Hn, keep, Vp, Vn, plq + ca * PW, thrs, (unsigned)t, lane, sd, stores, prow, c31, c2, LN, tail_off);
             hist = __funnelshift_r(hist, d0w >> (D & 31), 1); // row t's diagonal D0 bit enters at bit 31 (meaningful in the diagonal's owner lane)
             prow += rstride;
         }
@@ -830,7 +1028,7 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
             if (IRR && ((awi >> t) & 1u)) ca = irr_plane(A, a_bit + i - 1, a_tab);
             const int q = (i - 1) >> 5;
             row_step<S>(Hp, Hn, keep, Vp, Vn, planes + ca * PW + q + lane * S + (PAD ? lane + q / S : 0), S - q % S, (unsigned)t,
-                        lane, sd, stores, par + (size_t)(i - 1) * rstride + 2 * lane, c31, c2, LN);
+                        lane, sd, stores, par + (size_t)(i - 1) * rstride + lane_off, c31, c2, LN, tail_off);
             const int k = len_b - i + D, wk = k >> 5, Lk = wk / S, sk = wk % S;
             uint32_t vpw = 0u, vnw = 0u;
 #pragma unroll
@@ -857,7 +1055,25 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
     auto par_addr = [&](int row, int w) -> const uint2 * { // {MATCH word, INSERT word} of band word w of DP row `row`
         if (row < 1 || w < 0 || 32 * w > 2 * D) return nullptr;
         const int L = w / S, s = w - L * S;
+#ifdef PB_UNIT16
+        const uint32_t *rb = par + (size_t)(row - 1) * rstride;
+        if (s < (S & ~1)) return reinterpret_cast<const uint2 *>(rb + ((s >> 1) * LN + L) * 4 + (s & 1) * 2);
+        return reinterpret_cast<const uint2 *>(rb + (S / 2) * LN * 4 + L * 2);
+#else
         return reinterpret_cast<const uint2 *>(par + (size_t)(row - 1) * rstride) + s * LN + L;
+#endif
+    };
+    // the unit that holds band word w: its first word and its width in words (2: a 16-byte unit, 1: a lone pair)
+    auto unit_of = [&](int w, int &b, int &n) {
+        const int s = w % S;
+        if (s < (S & ~1)) { b = w - (s & 1); n = 2; } else { b = w; n = 1; }
+    };
+    auto unit_load = [&](int row, int b, int n) -> uint4 { // one load per row: 16 bytes for a two-word unit, 8 for a lone pair
+        const uint2 *q = par_addr(row, b);
+        if (!q) return make_uint4(0u, 0u, 0u, 0u);
+        if (n == 2) return __ldcg(reinterpret_cast<const uint4 *>(q));
+        const uint2 v = __ldcg(q);
+        return make_uint4(v.x, v.y, 0u, 0u);
     };
     auto par_pair = [&](int row, int w) -> uint2 {
         const uint2 *q = par_addr(row, w);
@@ -868,7 +1084,13 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
 #else
     uint32_t *ring = nullptr;
 #endif
-    finish_alignment(len_a, len_b, D, a_len, R, cii, colbest, col_i, planes, planes + T, par_pair, par_addr, ring, par, opsrev, ops_out, res);
+#ifdef PB_UNIT16
+    finish_alignment<true>(len_a, len_b, D, a_len, R, cii, colbest, col_i, planes, planes + T, par_pair, par_addr, ring, par, opsrev, ops_out, res,
+                           unit_of, unit_load);
+#else
+    (void)unit_of; (void)unit_load;
+    finish_alignment<false>(len_a, len_b, D, a_len, R, cii, colbest, col_i, planes, planes + T, par_pair, par_addr, ring, par, opsrev, ops_out, res);
+#endif
 }
 
 struct AlignLaunch {
@@ -1171,7 +1393,7 @@ align_pairs_packed_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *_
                     return __ldcg(reinterpret_cast<const uint2 *>(f_par + (size_t)(row - 1) * (2 * LANES)) + w);
                 };
                 auto no_addr = [](int, int) -> const uint2 * { return nullptr; }; // narrow bands: synchronous window loads
-                finish_alignment(f_la, f_lb, f_D, f_alen, p.R, f_cii, f_cb, f_ci, f_planes, f_planes + LANES, par_pair, no_addr,
+                finish_alignment<false>(f_la, f_lb, f_D, f_alen, p.R, f_cii, f_cb, f_ci, f_planes, f_planes + LANES, par_pair, no_addr,
                                  (uint32_t *)nullptr, (const void *)nullptr, f_opsrev, p.ops ? p.ops + p.ops_off[f_k] : nullptr, res);
             }
             if (lane == 0) {
