@@ -41,7 +41,14 @@
 //   -DPB_TB_ASYNC traceback windows prefetched into a shared-memory ring with cp.async (no register waits for a load)
 // Each alone changed nothing; both together, 4 windows deep, took K3 from 90.0 to 85.2 ms per config-2 step with identical
 // locate / align results -- but that build faults (illegal address) in the all-vs-all tests, and a 6-deep ring faults on
-// config 2, so neither is on by default until the out-of-bounds access is found.
+// config 2.  Each switch alone passes every test; with -DPB_TB_DEBUG (bounds checks on every prefetch address and on the
+// forward-pass rows, trap on violation) the combined build passes too and no check fires, and the copy flavour (.cg / .ca) does
+// not matter -- so the addresses are right and the fault depends on code generation.  Off by default until it is understood.
+#ifdef PB_TB_DEBUG_PRINT
+#define TBP(...) printf(__VA_ARGS__)
+#else
+#define TBP(...) ((void)0)
+#endif
 #ifndef PB_TB_RING
 #define PB_TB_RING 4 // traceback windows in the shared-memory ring (the one being walked + asynchronous prefetches); 5: same, 8: slower
 #endif
@@ -329,7 +336,11 @@ __device__ __forceinline__ void cp_async8(void *dst_smem, const void *src, int s
 }
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, int src_bytes) // L2 only (.cg), src_bytes 0: zero-fill
 {
+#ifdef PB_TB_CA16
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -533,10 +544,25 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
             const int row = i0w - lane;
             const uint2 *q0 = par_addr(row, pb);
             uint32_t *dst = ring + slot * 256 + 4 * lane;
+#ifdef PB_TB_DEBUG
+            if (q0 && ((const uint8_t *)q0 + (pn == 2 ? 16 : 8) > (const uint8_t *)opsrev || (const void *)q0 < gbase || ((uintptr_t)q0 & (pn == 2 ? 15 : 7)))) {
+                TBP("TBDBG primary: row %d pb %d pn %d i0w %d lane %d off %lld lim %lld D %d len_a %d\n", row, pb, pn, i0w, lane,
+                       (long long)((const uint8_t *)q0 - (const uint8_t *)gbase), (long long)((const uint8_t *)opsrev - (const uint8_t *)gbase), D, len_a);
+                __trap();
+            }
+            if (slot < 0 || slot >= PB_TB_RING) { TBP("TBDBG slot %d\n", slot); __trap(); }
+#endif
             if (pn == 2) cp_async16(dst, q0 ? (const void *)q0 : gbase, q0 ? 16 : 0);
             else { cp_async8(dst, q0 ? (const void *)q0 : gbase, q0 ? 8 : 0); }
             if (sn) {
                 const uint2 *q1 = par_addr(row, sb);
+#ifdef PB_TB_DEBUG
+                if (q1 && ((const uint8_t *)q1 + (sn == 2 ? 16 : 8) > (const uint8_t *)opsrev || (const void *)q1 < gbase || ((uintptr_t)q1 & (sn == 2 ? 15 : 7)))) {
+                    TBP("TBDBG secondary: row %d sb %d sn %d i0w %d lane %d off %lld lim %lld D %d\n", row, sb, sn, i0w, lane,
+                           (long long)((const uint8_t *)q1 - (const uint8_t *)gbase), (long long)((const uint8_t *)opsrev - (const uint8_t *)gbase), D);
+                    __trap();
+                }
+#endif
                 if (sn == 2) cp_async16(dst + 128, q1 ? (const void *)q1 : gbase, q1 ? 16 : 0);
                 else cp_async8(dst + 128, q1 ? (const void *)q1 : gbase, q1 ? 8 : 0);
             }
@@ -990,6 +1016,13 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
         const uint32_t *plq = planes + q + lane * S + (PAD ? lane + q / S : 0);
         const int thrs = S - q % S;
         uint32_t *prow = par + (size_t)(i0 - 1) * rstride + lane_off;
+#ifdef PB_TB_DEBUG
+        if ((const uint8_t *)(par + (size_t)(i0 - 1 + tmax) * rstride) > (const uint8_t *)opsrev) {
+            if (lane == 0) TBP("TBDBG forward: i0 %d tmax %d rstride %lld lim %lld len_a %d len_b %d D %d S %d\n", i0, tmax, (long long)rstride,
+                                  (long long)((const uint8_t *)opsrev - (const uint8_t *)par), len_a, len_b, D, S);
+            __trap();
+        }
+#endif
         uint32_t hist = 0u;
         for (int t = 0; t < tmax; ++t) {
             int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
