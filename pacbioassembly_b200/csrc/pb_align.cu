@@ -35,22 +35,29 @@
 // writes that already runs at ~75 % of the HBM peak.
 #define PB_TB_WINDOWS 3
 #endif
-// Experiment switches for the parent layout and the traceback prefetch ("Where K3's time goes"):
-//   -DPB_UNIT16   parents as 16-byte units of two adjacent band words per lane (one STG.128 per slot pair, one DRAM line per row
-//                 for the walk while the path sits inside a unit)
-//   -DPB_TB_ASYNC traceback windows prefetched into a shared-memory ring with cp.async (no register waits for a load)
-// Each alone changed nothing; both together, 4 windows deep, took K3 from 90.0 to 85.2 ms per config-2 step with identical
-// locate / align results -- but that build faults (illegal address) in the all-vs-all tests, and a 6-deep ring faults on
-// config 2.  Each switch alone passes every test; with -DPB_TB_DEBUG (bounds checks on every prefetch address and on the
-// forward-pass rows, trap on violation) the combined build passes too and no check fires, and the copy flavour (.cg / .ca) does
-// not matter -- so the addresses are right and the fault depends on code generation.  Off by default until it is understood.
+// Parent layout and traceback prefetch ("Where K3's time goes"):
+//   PB_UNIT16    parents as 16-byte units of two adjacent band words per lane (one STG.128 per slot pair, one DRAM line per row
+//                for the walk while the path sits inside a unit); -DPB_NO_UNIT16 restores the 8-byte pairs
+//   PB_TB_ASYNC  traceback windows prefetched into a shared-memory ring with cp.async (no register waits for a load);
+//                -DPB_NO_TB_ASYNC restores the register prefetch
+// Each alone changes nothing; together, 4 windows deep, K3 goes from 90.0 to 85.2 ms per config-2 step (the win is 16-byte
+// L2-only copies: with cp.async.ca, which fills whole L1 lines, it disappears).  One trap found on the way: a zero-fill copy
+// (src-size 0) is NOT safe with a dummy source -- the assembler, knowing the source is ignored, dropped the substituted address
+// and the hardware faulted on the garbage one (only at ptxas -O3, only where windows reach above row 1).  Rows above the matrix
+// are therefore zeroed with plain shared-memory stores.  -DPB_TB_DEBUG adds bounds checks on every prefetch address.
+#ifndef PB_NO_UNIT16
+#define PB_UNIT16
+#endif
+#ifndef PB_NO_TB_ASYNC
+#define PB_TB_ASYNC
+#endif
 #ifdef PB_TB_DEBUG_PRINT
 #define TBP(...) printf(__VA_ARGS__)
 #else
 #define TBP(...) ((void)0)
 #endif
 #ifndef PB_TB_RING
-#define PB_TB_RING 4 // traceback windows in the shared-memory ring (the one being walked + asynchronous prefetches); 5: same, 8: slower
+#define PB_TB_RING 4 // traceback windows in the shared-memory ring (the one being walked + asynchronous prefetches); 5, 6: same or slightly slower, 8: slower
 #endif
 #define PB_TB_RING_WORDS (PB_TB_RING * 256 + 8 * PB_TB_RING + 8)
 #ifndef PB_PAD_MOD
@@ -323,13 +330,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase)
     return ok != 0;
 }
 
-// ---- cp.async (LDGSTS): global -> shared without a register in between.  Experiment (-DPB_TB_ASYNC): the traceback prefetches its
-// parent windows into a shared-memory ring with it, because a prefetch that lands in registers has to be complete before the
-// registers can be rotated to the next window (ncu: 64 % of the traceback's stalls are long-scoreboard waits on the first use of a
-// window).  Bit-exact, and no faster: 4 windows 92.2 ms, 6 windows 94.3, 10 windows 100.9 against 92.4 ms for the register walk on
-// the same box.  The path leaves its two predicted band words every 10-20 windows and every window fetched ahead is then thrown
-// away, so depth buys DRAM traffic (each 8-byte pair costs a 128-byte line) faster than it hides latency.  What the walk needs is
-// a parent layout that keeps consecutive rows of a band word in one line -- see DESIGN.md.
+// ---- cp.async (LDGSTS): global -> shared without a register in between.  The traceback prefetches its parent windows into a
+// shared-memory ring with it, because a prefetch that lands in registers has to be complete before the registers can be rotated
+// to the next window (ncu: 64 % of the traceback's stalls were long-scoreboard waits on the first use of a window).  With 8-byte
+// pairs and .ca copies this bought nothing (4 windows 92.2 ms, 6 windows 94.3, 10 windows 100.9 against 92.4 ms for the register
+// walk on the same box: the path leaves its two predicted band words every 10-20 windows, everything fetched ahead is then thrown
+// away, and each 8-byte pair cost a 128-byte line); with 16-byte units and L2-only .cg copies it does (see PB_UNIT16).
 __device__ __forceinline__ void cp_async8(void *dst_smem, const void *src, int src_bytes) // src_bytes 0: zero-fill
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
@@ -552,8 +558,11 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
             }
             if (slot < 0 || slot >= PB_TB_RING) { TBP("TBDBG slot %d\n", slot); __trap(); }
 #endif
-            if (pn == 2) cp_async16(dst, q0 ? (const void *)q0 : gbase, q0 ? 16 : 0);
-            else { cp_async8(dst, q0 ? (const void *)q0 : gbase, q0 ? 8 : 0); }
+            // rows above the matrix get plain zero stores, not zero-fill copies: a copy whose source is ignored may still be
+            // handed a meaningless address by the assembler, and the hardware faults on it
+            if (!q0) *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);
+            else if (pn == 2) cp_async16(dst, q0, 16);
+            else cp_async8(dst, q0, 8);
             if (sn) {
                 const uint2 *q1 = par_addr(row, sb);
 #ifdef PB_TB_DEBUG
@@ -563,8 +572,9 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
                     __trap();
                 }
 #endif
-                if (sn == 2) cp_async16(dst + 128, q1 ? (const void *)q1 : gbase, q1 ? 16 : 0);
-                else cp_async8(dst + 128, q1 ? (const void *)q1 : gbase, q1 ? 8 : 0);
+                if (!q1) *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(0u, 0u, 0u, 0u);
+                else if (sn == 2) cp_async16(dst + 128, q1, 16);
+                else cp_async8(dst + 128, q1, 8);
             }
             if (lane == 0) { int *m = meta + 8 * slot; m[0] = i0w; m[1] = pb; m[2] = pn; m[3] = sb; m[4] = sn; }
             cp_async_commit();
@@ -723,7 +733,8 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint2 *src = par_addr(row, wb + h);
-                cp_async8(ring + slot * 128 + h * 64 + 2 * lane, src ? (const void *)src : gbase, src ? 8 : 0);
+                if (src) cp_async8(ring + slot * 128 + h * 64 + 2 * lane, src, 8);
+                else *reinterpret_cast<uint2 *>(ring + slot * 128 + h * 64 + 2 * lane) = make_uint2(0u, 0u);
             }
             if (lane == 0) { meta[2 * slot] = i0w; meta[2 * slot + 1] = wb; }
             cp_async_commit();
@@ -1113,7 +1124,10 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
         return q ? __ldcg(q) : make_uint2(0u, 0u);
     };
 #ifdef PB_TB_ASYNC // experiment switch, see cp_async8
-    uint32_t *ring = planes + 2 * T; // behind the final deltas; the Eq planes and the staging area are dead by now
+#ifndef PB_TB_RING_PAD
+#define PB_TB_RING_PAD 0
+#endif
+    uint32_t *ring = planes + 2 * T + PB_TB_RING_PAD; // behind the final deltas; the Eq planes and the staging area are dead by now
 #else
     uint32_t *ring = nullptr;
 #endif
@@ -1538,7 +1552,10 @@ static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, int locate, si
         g->RW = PB_STAGE_WORDS; // TMA staging buffer per raw plane
         g->warp_words = (key_irr(key) ? 8 : 4) * g->PW + (key_irr(key) ? 3 : 2) * g->RW;
 #ifdef PB_TB_ASYNC
-        g->warp_words = std::max(g->warp_words, (2 * T + PB_TB_RING_WORDS + 3) & ~3); // final deltas + the traceback's window ring
+#ifndef PB_TB_RING_PAD
+#define PB_TB_RING_PAD 0
+#endif
+        g->warp_words = std::max(g->warp_words, (2 * T + PB_TB_RING_WORDS + 2 * PB_TB_RING_PAD + 3) & ~3); // final deltas + the traceback's window ring
 #endif
         g->par_words = (size_t)std::max(cp.max_rows, 1) * 2 * T;
     }
