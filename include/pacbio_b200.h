@@ -220,8 +220,10 @@ PB_API int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, 
 PB_API int64_t pb_locate_job_nkept(const pb_locate_job *job);
 PB_API int64_t pb_locate_job_ncand(const pb_locate_job *job); /* seed hits (candidates) gathered for the batch */
 /* after pb_locate_fetch: out[0] = candidates gathered (K2), out[1] = alignments the banded aligner (K3) ran,
- * out[2] = DP cells K3 computed (reference cell count of those alignments), out[3] = 0 */
-PB_API int pb_locate_job_stats(const pb_locate_job *job, int64_t *out /* [4] */);
+ * out[2] = reference cell count of those alignments (what seq_aligner.h:151-190 would have filled for them), out[3] = band
+ * cells K3 actually computed (its first pass runs a certified strip of the band), out[4] = reads the strip
+ * could not certify and the full-band pass ran again, out[5..7] = 0 */
+PB_API int pb_locate_job_stats(const pb_locate_job *job, int64_t *out /* [8] */);
 /* Diagonal-bin tally of each kept read's seed hits (K2): votes[k] = hits whose diagonal pos - j falls in the fullest
  * 256-base bin, best_diag[k] = that bin's first diagonal.  A diagnostic of how concentrated the hits are; candidates are
  * never reordered or pruned by it (the reference takes the first success in list order).  Either pointer may be NULL. */

@@ -623,9 +623,10 @@ class LocateJob:
 
     def stats(self) -> dict:
         """valid after fetch(): candidates gathered, alignments run by K3, DP cells computed by K3"""
-        out = np.zeros(4, dtype=np.int64)
+        out = np.zeros(8, dtype=np.int64)
         self.ctx.check(self.ctx._L.pb_locate_job_stats(self.h, _ptr(out)))
-        return {"ncand": int(out[0]), "dp_alignments": int(out[1]), "dp_cells": int(out[2])}
+        return {"ncand": int(out[0]), "dp_alignments": int(out[1]), "dp_cells": int(out[2]), "band_cells": int(out[3]),
+                "redone": int(out[4])}
 
     def votes(self):
         """(votes, best_diag) per kept read: the diagonal-bin tally of its seed hits (diagnostic only)"""

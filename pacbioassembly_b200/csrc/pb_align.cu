@@ -22,11 +22,6 @@
 
 #define FULL 0xffffffffu
 #define PB_STAGE_WORDS 128 // staging buffer per plane (words): 4 kbp of seg_b per TMA chunk
-#ifndef PB_SHIFT_FMA
-#define PB_PLANE_PADBIT 0
-#else
-#define PB_PLANE_PADBIT 1 // one pad bit in front of the Eq planes: the per-row shift becomes 1..32, i.e. a multiply by 2^31..2^0
-#endif
 #ifndef PB_TB_WINDOWS
 // traceback: 32-row parent windows in flight per warp (the one being walked + prefetched ones).  The backward walk is 19 % of K3
 // (measured by skipping it: 91.1 -> 74.2 ms).  It is neither its instruction count (a loop with a third fewer instructions per
@@ -35,27 +30,11 @@
 // writes that already runs at ~75 % of the HBM peak.
 #define PB_TB_WINDOWS 3
 #endif
-// Parent layout and traceback prefetch ("Where K3's time goes"):
-//   PB_UNIT16    parents as 16-byte units of two adjacent band words per lane (one STG.128 per slot pair, one DRAM line per row
-//                for the walk while the path sits inside a unit); -DPB_NO_UNIT16 restores the 8-byte pairs
-//   PB_TB_ASYNC  traceback windows prefetched into a shared-memory ring with cp.async (no register waits for a load);
-//                -DPB_NO_TB_ASYNC restores the register prefetch
-// Each alone changes nothing; together, 4 windows deep, K3 goes from 90.0 to 85.2 ms per config-2 step (the win is 16-byte
-// L2-only copies: with cp.async.ca, which fills whole L1 lines, it disappears).  One trap found on the way: a zero-fill copy
-// (src-size 0) is NOT safe with a dummy source -- the assembler, knowing the source is ignored, dropped the substituted address
-// and the hardware faulted on the garbage one (only at ptxas -O3, only where windows reach above row 1).  Rows above the matrix
-// are therefore zeroed with plain shared-memory stores.  -DPB_TB_DEBUG adds bounds checks on every prefetch address.
-#ifndef PB_NO_UNIT16
-#define PB_UNIT16
-#endif
-#ifndef PB_NO_TB_ASYNC
-#define PB_TB_ASYNC
-#endif
-#ifdef PB_TB_DEBUG_PRINT
-#define TBP(...) printf(__VA_ARGS__)
-#else
-#define TBP(...) ((void)0)
-#endif
+// Parent layout and traceback prefetch ("Where K3's time goes"): parents are stored as 16-byte units of two
+// adjacent band words per lane (one STG.128 per slot pair, one DRAM line per row for the walk while the path sits inside a
+// unit), and the traceback prefetches its windows into a shared-memory ring with 16-byte L2-only cp.async.cg copies.  Rows above
+// the matrix are zeroed with plain shared-memory stores, never with zero-fill copies: a copy whose source is ignored may still
+// be handed a meaningless address by the assembler (found in round 1: only at ptxas -O3, only where windows reach above row 1).
 #ifndef PB_TB_RING
 #define PB_TB_RING 4 // traceback windows in the shared-memory ring (the one being walked + asynchronous prefetches); 5, 6: same or slightly slower, 8: slower
 #endif
@@ -342,11 +321,7 @@ __device__ __forceinline__ void cp_async8(void *dst_smem, const void *src, int s
 }
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, int src_bytes) // L2 only (.cg), src_bytes 0: zero-fill
 {
-#ifdef PB_TB_CA16
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
-#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
-#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -371,29 +346,6 @@ __device__ __forceinline__ uint32_t addc(uint32_t a, uint32_t b)
     return r;
 }
 
-// Experiment switch -DPB_SHIFT_FMA: issue the five funnel shifts per band word on the FMA pipe as multiplies by powers
-// of two, (lo >> n) | (hi << (32-n)) == mul.hi(lo, 2^(32-n)) + mul.lo(hi, 2^(32-n)), to relieve the integer ALU pipe
-// (ncu: ~86 % busy while the FMA pipe idles).  Measured on B200 (A/B, saturated S=3 launch): 9.3 ms vs 8.4 ms with plain
-// SHF -- two IMADs per shift cost more issue slots than the ALU pipe gains, so the default stays on SHF.
-__device__ __forceinline__ uint32_t mul_hi(uint32_t a, uint32_t b)
-{
-    uint32_t r;
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-    return r;
-}
-__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c)
-{
-    uint32_t r;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-    return r;
-}
-#ifndef PB_SHIFT_FMA
-#define PB_FUNNEL_R1(lo, hi, c31) __funnelshift_r((lo), (hi), 1)
-#define PB_FUNNEL_L1(lo, hi, c2) __funnelshift_l((lo), (hi), 1)
-#else
-#define PB_FUNNEL_R1(lo, hi, c31) mad_lo((hi), (c31), mul_hi((lo), (c31)))  /* (lo >> 1) | (hi << 31) */
-#define PB_FUNNEL_L1(lo, hi, c2) mad_lo((hi), (c2), mul_hi((lo), (c2)))     /* (hi << 1) | (lo >> 31) */
-#endif
 
 // One band row for the S words of this lane.  pl points at this lane's first Eq word of the row's plane, sh is the
 // row's bit offset inside those words; prow is this lane's pair column (row base + 2*lane) of the row's parent block.  Returns the D0 word of
@@ -401,7 +353,7 @@ __device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c)
 template <int S>
 __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S], const uint32_t (&keep)[S], uint32_t (&Vp)[S],
                                              uint32_t (&Vn)[S], const uint32_t *__restrict__ pl, int thrs, unsigned sh, int lane,
-                                             int sd, bool stores, uint32_t *__restrict__ prow, uint32_t c31, uint32_t c2, int LN = 32,
+                                             int sd, bool stores, uint32_t *__restrict__ prow, int LN = 32,
                                              int tail_off = 0)
 {
     // phase A: slide the band one bit (across words and lanes), fetch Eq, block add with carry-in 0
@@ -411,22 +363,15 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
     // Eq words: logical words x0..x0+S of the plane; for even S the plane is stored with one pad word per S words
     // (bank-conflict-free for the lane stride S), which shows up here as a +1 from slot `thrs` on
     constexpr bool PAD = (S % PB_PAD_MOD) == 0;
-#ifdef PB_SHIFT_FMA
-    const uint32_t eqm = 0x80000000u >> sh; // 2^(31-sh)
-#endif
     uint32_t plw = pl[0];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
         const uint32_t hp_hi = (s + 1 < S) ? Hp[s + 1] : (nx & 1u);
         const uint32_t hn_hi = (s + 1 < S) ? Hn[s + 1] : (nx >> 1);
-        Hp[s] = PB_FUNNEL_R1(Hp[s], hp_hi, c31);
-        Hn[s] = PB_FUNNEL_R1(Hn[s], hn_hi, c31);
+        Hp[s] = __funnelshift_r(Hp[s], hp_hi, 1);
+        Hn[s] = __funnelshift_r(Hn[s], hn_hi, 1);
         const uint32_t nxt = PAD ? pl[s + 1 + ((s + 1 >= thrs) ? 1 : 0)] : pl[s + 1];
-#ifndef PB_SHIFT_FMA
         Eq[s] = __funnelshift_r(plw, nxt, sh) & keep[s]; // no matches beyond the band's upper edge (see align_one)
-#else
-        Eq[s] = mad_lo(nxt, eqm, mul_hi(plw, eqm)) & keep[s]; // (plw >> (sh+1)) | (nxt << (31-sh)); planes carry a 1-bit pad
-#endif
         plw = nxt;
         x[s] = Eq[s] & Hp[s];
     }
@@ -461,12 +406,10 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
 
     // phase C: new horizontal deltas, INSERT plane
     uint32_t pprev = pv << 31, nprev = (pv >> 1) << 31; // bit 31 = delta entering this word from the left
-#ifdef PB_UNIT16
     uint32_t heldM = 0u, heldI = 0u;
-#endif
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        const uint32_t vps = PB_FUNNEL_L1(pprev, Vp[s], c2), vns = PB_FUNNEL_L1(nprev, Vn[s], c2);
+        const uint32_t vps = __funnelshift_l(pprev, Vp[s], 1), vns = __funnelshift_l(nprev, Vn[s], 1);
         pprev = Vp[s];
         nprev = Vn[s];
         const uint32_t Xh = Eq[s] | Hn[s];
@@ -474,7 +417,6 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
         Hn[s] = vps & Xh;
         // parents of band word w = lane*S+s: {MATCH plane, INSERT plane} as one 8-byte pair at pair index s*32+lane
         // lanes whose words all lie past the band skip the store; a partly used lane writes its S words (row padding)
-#ifdef PB_UNIT16
         // parents as 16-byte units of two adjacent band words per lane: {M[2p], I[2p], M[2p+1], I[2p+1]} at unit p*LN + lane
         // (one STG.128 per slot pair); the last slot of an odd S follows as 8-byte pairs at tail_off.  prow = row base + 4*lane.
         if ((s & 1) == 0 && s + 1 < S) {
@@ -484,9 +426,6 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
         } else {
             if (stores) *reinterpret_cast<uint2 *>(prow + tail_off) = make_uint2(Mw[s], Hp[s]);
         }
-#else
-        if (stores) reinterpret_cast<uint2 *>(prow)[s * LN] = make_uint2(Mw[s], Hp[s]);
-#endif
     }
     return d0w;
 }
@@ -528,10 +467,6 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
     res.diag_cost = (a_len <= len_a && a_len <= len_b) ? cii : 0; // locator.cpp:86 (Q-L2)
     if ((double)matlen_b < len_b * (1 - R)) return; // seq_aligner.h:114
 
-#ifdef PB_SKIP_TRACEBACK // timing experiment only (results lose their transcripts): how much of K3 is the backward walk
-    res.nedit = 0; res.ret = matlen_b;
-    return;
-#endif
     // ---- find_path, seq_aligner.h:214-233: walk the parent planes back from the goal cell.
     // Warp-cooperative: lane r holds the parent pairs of row i0-r around the path's band position (2 band words,
     // 16 bytes), the next 64 rows are prefetched while the current ones are walked, and runs of MATCH along a
@@ -550,14 +485,6 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
             const int row = i0w - lane;
             const uint2 *q0 = par_addr(row, pb);
             uint32_t *dst = ring + slot * 256 + 4 * lane;
-#ifdef PB_TB_DEBUG
-            if (q0 && ((const uint8_t *)q0 + (pn == 2 ? 16 : 8) > (const uint8_t *)opsrev || (const void *)q0 < gbase || ((uintptr_t)q0 & (pn == 2 ? 15 : 7)))) {
-                TBP("TBDBG primary: row %d pb %d pn %d i0w %d lane %d off %lld lim %lld D %d len_a %d\n", row, pb, pn, i0w, lane,
-                       (long long)((const uint8_t *)q0 - (const uint8_t *)gbase), (long long)((const uint8_t *)opsrev - (const uint8_t *)gbase), D, len_a);
-                __trap();
-            }
-            if (slot < 0 || slot >= PB_TB_RING) { TBP("TBDBG slot %d\n", slot); __trap(); }
-#endif
             // rows above the matrix get plain zero stores, not zero-fill copies: a copy whose source is ignored may still be
             // handed a meaningless address by the assembler, and the hardware faults on it
             if (!q0) *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);
@@ -565,13 +492,6 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
             else cp_async8(dst, q0, 8);
             if (sn) {
                 const uint2 *q1 = par_addr(row, sb);
-#ifdef PB_TB_DEBUG
-                if (q1 && ((const uint8_t *)q1 + (sn == 2 ? 16 : 8) > (const uint8_t *)opsrev || (const void *)q1 < gbase || ((uintptr_t)q1 & (sn == 2 ? 15 : 7)))) {
-                    TBP("TBDBG secondary: row %d sb %d sn %d i0w %d lane %d off %lld lim %lld D %d\n", row, sb, sn, i0w, lane,
-                           (long long)((const uint8_t *)q1 - (const uint8_t *)gbase), (long long)((const uint8_t *)opsrev - (const uint8_t *)gbase), D);
-                    __trap();
-                }
-#endif
                 if (!q1) *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(0u, 0u, 0u, 0u);
                 else if (sn == 2) cp_async16(dst + 128, q1, 16);
                 else cp_async8(dst + 128, q1, 8);
@@ -651,155 +571,6 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
                 n += i;
             }
         }
-    } else if (UNITS) {
-        // ---- walk over 16-byte parent units.  A window is 32 rows of the unit under the path (one load, one DRAM line per row)
-        // and, only while the path is within 8 bits of that unit's edge, the neighbouring unit as well.
-        int i = matlen_a, j = matlen_b;
-        const int guard = len_a + len_b + 1;
-        int wi0[PB_TB_WINDOWS], b0[PB_TB_WINDOWS], n0[PB_TB_WINDOWS], b1[PB_TB_WINDOWS], n1[PB_TB_WINDOWS];
-        uint4 u0[PB_TB_WINDOWS], u1[PB_TB_WINDOWS];
-#pragma unroll
-        for (int t = 0; t < PB_TB_WINDOWS; ++t) { wi0[t] = -1; b0[t] = n0[t] = b1[t] = n1[t] = 0; u0[t] = make_uint4(0u, 0u, 0u, 0u); u1[t] = u0[t]; }
-        bool have = false;
-        int wend = 0;
-        while (i > 0 && j > 0 && n < guard) {
-            const int k = j - i + D, w = k >> 5, kb = k & 31;
-            if (!have || i <= wend || !((unsigned)(w - b0[0]) < (unsigned)n0[0] || (unsigned)(w - b1[0]) < (unsigned)n1[0])) {
-                if (have && wi0[1] == i && ((unsigned)(w - b0[1]) < (unsigned)n0[1] || (unsigned)(w - b1[1]) < (unsigned)n1[1])) {
-                    // the usual case: 32 rows consumed and the prediction held; the new far window copies the one in front of it
-#pragma unroll
-                    for (int t = 0; t + 1 < PB_TB_WINDOWS; ++t) {
-                        wi0[t] = wi0[t + 1]; b0[t] = b0[t + 1]; n0[t] = n0[t + 1]; b1[t] = b1[t + 1]; n1[t] = n1[t + 1];
-                        u0[t] = u0[t + 1]; u1[t] = u1[t + 1];
-                    }
-                    constexpr int Z = PB_TB_WINDOWS - 1;
-                    wi0[Z] = wi0[0] - 32 * Z;
-                    u0[Z] = unit_load(wi0[Z] - lane, b0[Z], n0[Z]);
-                    u1[Z] = n1[Z] ? unit_load(wi0[Z] - lane, b1[Z], n1[Z]) : make_uint4(0u, 0u, 0u, 0u);
-                } else { // cold start, or the path left the predicted units
-                    int pb, pn, sb = 0, sn = 0;
-                    unit_of(w, pb, pn);
-                    const int pos = (w - pb) * 32 + kb;
-                    if (pos < 8 && pb > 0) unit_of(pb - 1, sb, sn);
-                    else if (pos >= 32 * pn - 8 && 32 * (pb + pn) <= 2 * D) unit_of(pb + pn, sb, sn);
-#pragma unroll
-                    for (int t = 0; t < PB_TB_WINDOWS; ++t) {
-                        wi0[t] = i - 32 * t; b0[t] = pb; n0[t] = pn; b1[t] = sb; n1[t] = sn;
-                        u0[t] = unit_load(wi0[t] - lane, pb, pn);
-                        u1[t] = sn ? unit_load(wi0[t] - lane, sb, sn) : make_uint4(0u, 0u, 0u, 0u);
-                    }
-                }
-                have = true;
-                wend = wi0[0] - 32;
-            }
-            const int r0 = wi0[0] - i; // lane that holds the current row
-            const int d0 = w - b0[0];
-            const bool prim = (unsigned)d0 < (unsigned)n0[0];
-            const int d = prim ? d0 : w - b1[0];
-            const uint4 u = prim ? u0[0] : u1[0];
-            const uint32_t mword = d ? u.z : u.x;
-            const uint32_t B = __ballot_sync(FULL, (mword >> kb) & 1u) >> r0; // bit t: cell (i-t, j-t) is MATCH
-            int run = (~B) ? __ffs(~B) - 1 : 32;
-            const int lim = min(32 - r0, min(i, j));
-            const bool indel = run < lim;
-            run = min(run, lim);
-            if (lane < run) opsrev[n + lane] = (uint8_t)PB_MATCH;
-            n += run; i -= run; j -= run;
-            if (indel) {
-                const uint32_t iword = d ? u.w : u.y;
-                const uint32_t hb = (__shfl_sync(FULL, iword, r0 + run) >> kb) & 1u;
-                if (lane == 0) opsrev[n] = (uint8_t)(hb ? PB_INSERT : PB_DELETE);
-                ++n;
-                if (hb) --j; else --i;
-            }
-        }
-        if (n < guard) {
-            if (i == 0 && j > 0) { // init_cell row 0: INSERT all the way
-                for (int t = lane; t < j; t += 32) opsrev[n + t] = (uint8_t)PB_INSERT;
-                n += j;
-            } else if (j == 0 && i > 0) { // init_cell column 0: DELETE all the way
-                for (int t = lane; t < i; t += 32) opsrev[n + t] = (uint8_t)PB_DELETE;
-                n += i;
-            }
-        }
-    } else if (ring) {
-        // ---- walk with asynchronous prefetch: PB_TB_RING windows of 32 rows x 2 band words live in shared memory, filled by
-        // cp.async; slot q: pair of (row i0-lane, word wb+h) at ring[q*128 + h*64 + 2*lane], its (i0, wb) at meta[2q], meta[2q+1]
-        int i = matlen_a, j = matlen_b;
-        const int guard = len_a + len_b + 1;
-        int *meta = reinterpret_cast<int *>(ring + PB_TB_RING * 128);
-        auto fetch = [&](int slot, int i0w, int wb) {
-            const int row = i0w - lane;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint2 *src = par_addr(row, wb + h);
-                if (src) cp_async8(ring + slot * 128 + h * 64 + 2 * lane, src, 8);
-                else *reinterpret_cast<uint2 *>(ring + slot * 128 + h * 64 + 2 * lane) = make_uint2(0u, 0u);
-            }
-            if (lane == 0) { meta[2 * slot] = i0w; meta[2 * slot + 1] = wb; }
-            cp_async_commit();
-        };
-        int cur_slot = 0, cur_i0 = 0, kbase = 0, wend = 0;
-        uint2 c0 = make_uint2(0u, 0u), c1 = c0;
-        bool have = false;
-        while (i > 0 && j > 0 && n < guard) {
-            const int k = j - i + D;
-            if (!have || i <= wend || (unsigned)(k - kbase) >= 64u) {
-                const int w = k >> 5, wb = window_base(k);
-                const int nslot = cur_slot + 1 == PB_TB_RING ? 0 : cur_slot + 1;
-                bool usual = have;
-                if (usual) {
-                    const int nwb = meta[2 * nslot + 1];
-                    usual = meta[2 * nslot] == i && w >= nwb && w <= nwb + 1; // 32 rows consumed and the prediction held
-                }
-                __syncwarp();
-                if (usual) { // refill the slot just walked with the window PB_TB_RING-1 ahead of the new current one
-                    fetch(cur_slot, i - 32 * (PB_TB_RING - 1), wb);
-                    cur_slot = nslot;
-                } else { // cold start, or the path left the predicted words
-                    cp_async_wait<0>();
-#pragma unroll
-                    for (int t = 0; t < PB_TB_RING; ++t) fetch(t, i - 32 * t, wb);
-                    cur_slot = 0;
-                }
-                cp_async_wait<PB_TB_RING - 1>(); // groups complete in order: everything but the PB_TB_RING-1 newest has landed
-                __syncwarp();
-                c0 = *reinterpret_cast<const uint2 *>(ring + cur_slot * 128 + 2 * lane);
-                c1 = *reinterpret_cast<const uint2 *>(ring + cur_slot * 128 + 64 + 2 * lane);
-                cur_i0 = meta[2 * cur_slot];
-                kbase = 32 * meta[2 * cur_slot + 1];
-                wend = cur_i0 - 32;
-                have = true;
-            }
-            const int r0 = cur_i0 - i;   // lane that holds the current row
-            const int kb = k - kbase;    // 0..63: bit inside the two-word window
-            const uint32_t mword = kb < 32 ? c0.x : c1.x;
-            const uint32_t B = __ballot_sync(FULL, (mword >> (kb & 31)) & 1u) >> r0; // bit t: cell (i-t, j-t) is MATCH
-            int run = (~B) ? __ffs(~B) - 1 : 32;
-            const int lim = min(32 - r0, min(i, j));
-            const bool indel = run < lim;
-            run = min(run, lim);
-            if (lane < run) opsrev[n + lane] = (uint8_t)PB_MATCH;
-            n += run; i -= run; j -= run;
-            if (indel) {
-                const uint32_t iword = kb < 32 ? c0.y : c1.y;
-                const uint32_t hb = (__shfl_sync(FULL, iword, r0 + run) >> (kb & 31)) & 1u;
-                if (lane == 0) opsrev[n] = (uint8_t)(hb ? PB_INSERT : PB_DELETE);
-                ++n;
-                if (hb) --j; else --i;
-            }
-        }
-        cp_async_wait<0>(); // nothing may still be landing in the ring when the shared memory is reused
-        __syncwarp();
-        if (n < guard) {
-            if (i == 0 && j > 0) { // init_cell row 0: INSERT all the way
-                for (int t = lane; t < j; t += 32) opsrev[n + t] = (uint8_t)PB_INSERT;
-                n += j;
-            } else if (j == 0 && i > 0) { // init_cell column 0: DELETE all the way
-                for (int t = lane; t < i; t += 32) opsrev[n + t] = (uint8_t)PB_DELETE;
-                n += i;
-            }
-        }
     } else {
         int i = matlen_a, j = matlen_b;
         const int guard = len_a + len_b + 1; // a path can never be longer; keeps a corrupted plane from hanging the GPU
@@ -870,14 +641,11 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
 
 // Inlined into its one call site per kernel: as a separate function the row loop re-materialised the global-store descriptor
 // from vector registers before every store (two R2UR per parent pair); measured 95.0 -> 91.2 ms of K3 per config-2 step.
-#ifndef PB_ALIGN_ONE_ATTR
-#define PB_ALIGN_ONE_ATTR __forceinline__
-#endif
 template <int S, bool IRR>
-__device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int a_len, uint32_t a_tab, const SeqView &B, int64_t b_bit, int b_len,
+__device__ __forceinline__ void align_one(const SeqView &A, int64_t a_bit, int a_len, uint32_t a_tab, const SeqView &B, int64_t b_bit, int b_len,
                                        double R, int maxn, int maxm, uint32_t *__restrict__ planes, int PW,
                                        uint32_t *__restrict__ par, uint8_t *__restrict__ opsrev, uint8_t *__restrict__ ops_out,
-                                       uint32_t c31, uint32_t c2, uint32_t *__restrict__ raw, int RW, uint64_t *bar, uint32_t &phase,
+                                       uint32_t *__restrict__ raw, int RW, uint64_t *bar, uint32_t &phase,
                                        AlnRes &res)
 {
     constexpr int T = 32 * S;
@@ -896,7 +664,7 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
     // The plane words that cover seg_b = line bits [b_bit, b_bit + len_b) come in through a small staging buffer filled by
     // bulk TMA copies (16-byte granules), PB_STAGE_WORDS words of each plane at a time; consecutive chunks overlap by four
     // words because a 32-bit window straddles two words.
-    const int64_t g0 = b_bit - D - PB_PLANE_PADBIT;             // line bit of bit 0 of plane word 0 (may be negative)
+    const int64_t g0 = b_bit - D;             // line bit of bit 0 of plane word 0 (may be negative)
     const int64_t w_first = max((int64_t)0, g0 >> 5) & ~(int64_t)3; // first staged line word
     const int64_t w_end = min(B.nwords, (((b_bit + len_b + 31) >> 5) + 1 + 3) & ~(int64_t)3);
     const int k0 = (int)((g0 >> 5) - w_first);                   // raw word index (relative to w_first) under plane word 0
@@ -921,7 +689,7 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
         const int x_lo = (cw == w_first) ? 0 : max(0, c_lo - k0); // the first chunk also takes the words in front of the line
         const int x_hi = (c_hi == INT_MAX) ? PWn : min(PWn, max(0, c_hi - k0));
         for (int x = x_lo + lane; x < x_hi; x += 32) {
-            const int bidx0 = 32 * x - D - PB_PLANE_PADBIT; // b index of bit 0 of this word
+            const int bidx0 = 32 * x - D; // b index of bit 0 of this word
             uint32_t valid;
             if (bidx0 >= len_b || bidx0 + 31 < 0) valid = 0u;
             else {
@@ -958,7 +726,7 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
         for (int64_t e = e0 + lane; e < e1; e += 32) {
             const int slot = tab_slot(a_tab, B.exc_val[e]);
             if (slot >= 0) { // unused table slots hold 'A', which never shows up in the exception list
-                const int t = (int)(B.exc_pos[e] - b_bit) + D + PB_PLANE_PADBIT;
+                const int t = (int)(B.exc_pos[e] - b_bit) + D;
                 const int x = t >> 5, px = PAD ? x + x / S : x;
                 atomicOr(&planes[(4 + slot) * PW + px], 1u << (t & 31));
             }
@@ -988,23 +756,10 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
         keep[s] = kp;
     }
     const int wd = D >> 5, Ld = wd / S, sd = wd % S; // owner of the main-diagonal bit k = D
-#ifdef PB_COMPACT_ROWS
-    // Experiment switch: parent rows hold only the lanes that own band bits, rounded up to whole 32-byte sectors (4 lanes),
-    // row = [slot][lane < LN] -- ~13 % fewer bytes written on config 2, bit-exact, and slower (92.8 vs 90.0 ms of K3): the
-    // forward pass is bound by instruction issue, not by the bytes it writes.  (Predicating the stores while keeping the
-    // 32-lane row stride left holes of partly written lines and cost 40 %.)
-    const int LN = min(32, (((((2 * D + 1 + 31) >> 5) + S - 1) / S) + 3) & ~3);
-    const bool stores = lane < LN;
-#else
     const int LN = 32;
     const bool stores = true; // measured: predicating the pair stores costs 40 % (A/B on B200), the padding writes are cheaper
-#endif
     const size_t rstride = (size_t)2 * LN * S; // words per parent row
-#ifdef PB_UNIT16
     const int lane_off = 4 * lane, tail_off = (S / 2) * LN * 4 - 2 * lane; // units of 4 words per lane, then the odd slot's pairs
-#else
-    const int lane_off = 2 * lane, tail_off = 0;
-#endif
 
     int cii = 0;                          // cost(i,i), warp-uniform, advanced once per 32-row block
     int colc = 0, colbest = 0, col_i = 0; // cost(i,len_b) tracking when len_a > len_b
@@ -1027,18 +782,11 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
         const uint32_t *plq = planes + q + lane * S + (PAD ? lane + q / S : 0);
         const int thrs = S - q % S;
         uint32_t *prow = par + (size_t)(i0 - 1) * rstride + lane_off;
-#ifdef PB_TB_DEBUG
-        if ((const uint8_t *)(par + (size_t)(i0 - 1 + tmax) * rstride) > (const uint8_t *)opsrev) {
-            if (lane == 0) TBP("TBDBG forward: i0 %d tmax %d rstride %lld lim %lld len_a %d len_b %d D %d S %d\n", i0, tmax, (long long)rstride,
-                                  (long long)((const uint8_t *)opsrev - (const uint8_t *)par), len_a, len_b, D, S);
-            __trap();
-        }
-#endif
         uint32_t hist = 0u;
         for (int t = 0; t < tmax; ++t) {
             int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
             if (IRR && ((awi >> t) & 1u)) ca = irr_plane(A, a_bit + i0 - 1 + t, a_tab);
-            const uint32_t d0w = row_step<S>(Hp, Hn, keep, Vp, Vn, plq + ca * PW, thrs, (unsigned)t, lane, sd, stores, prow, c31, c2, LN, tail_off);
+            const uint32_t d0w = row_step<S>(Hp, Hn, keep, Vp, Vn, plq + ca * PW, thrs, (unsigned)t, lane, sd, stores, prow, LN, tail_off);
             hist = __funnelshift_r(hist, d0w >> (D & 31), 1); // row t's diagonal D0 bit enters at bit 31 (meaningful in the diagonal's owner lane)
             prow += rstride;
         }
@@ -1072,7 +820,7 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
             if (IRR && ((awi >> t) & 1u)) ca = irr_plane(A, a_bit + i - 1, a_tab);
             const int q = (i - 1) >> 5;
             row_step<S>(Hp, Hn, keep, Vp, Vn, planes + ca * PW + q + lane * S + (PAD ? lane + q / S : 0), S - q % S, (unsigned)t,
-                        lane, sd, stores, par + (size_t)(i - 1) * rstride + lane_off, c31, c2, LN, tail_off);
+                        lane, sd, stores, par + (size_t)(i - 1) * rstride + lane_off, LN, tail_off);
             const int k = len_b - i + D, wk = k >> 5, Lk = wk / S, sk = wk % S;
             uint32_t vpw = 0u, vnw = 0u;
 #pragma unroll
@@ -1099,13 +847,9 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
     auto par_addr = [&](int row, int w) -> const uint2 * { // {MATCH word, INSERT word} of band word w of DP row `row`
         if (row < 1 || w < 0 || 32 * w > 2 * D) return nullptr;
         const int L = w / S, s = w - L * S;
-#ifdef PB_UNIT16
         const uint32_t *rb = par + (size_t)(row - 1) * rstride;
         if (s < (S & ~1)) return reinterpret_cast<const uint2 *>(rb + ((s >> 1) * LN + L) * 4 + (s & 1) * 2);
         return reinterpret_cast<const uint2 *>(rb + (S / 2) * LN * 4 + L * 2);
-#else
-        return reinterpret_cast<const uint2 *>(par + (size_t)(row - 1) * rstride) + s * LN + L;
-#endif
     };
     // the unit that holds band word w: its first word and its width in words (2: a 16-byte unit, 1: a lone pair)
     auto unit_of = [&](int w, int &b, int &n) {
@@ -1123,22 +867,12 @@ __device__ PB_ALIGN_ONE_ATTR void align_one(const SeqView &A, int64_t a_bit, int
         const uint2 *q = par_addr(row, w);
         return q ? __ldcg(q) : make_uint2(0u, 0u);
     };
-#ifdef PB_TB_ASYNC // experiment switch, see cp_async8
-#ifndef PB_TB_RING_PAD
-#define PB_TB_RING_PAD 0
-#endif
-    uint32_t *ring = planes + 2 * T + PB_TB_RING_PAD; // behind the final deltas; the Eq planes and the staging area are dead by now
-#else
-    uint32_t *ring = nullptr;
-#endif
-#ifdef PB_UNIT16
+    uint32_t *ring = planes + 2 * T; // behind the final deltas; the Eq planes and the staging area are dead by now
     finish_alignment<true>(len_a, len_b, D, a_len, R, cii, colbest, col_i, planes, planes + T, par_pair, par_addr, ring, par, opsrev, ops_out, res,
                            unit_of, unit_load);
-#else
-    (void)unit_of; (void)unit_load;
-    finish_alignment<false>(len_a, len_b, D, a_len, R, cii, colbest, col_i, planes, planes + T, par_pair, par_addr, ring, par, opsrev, ops_out, res);
-#endif
 }
+
+#include "pb_align_nb.cuh"
 
 struct AlignLaunch {
     SeqView A, B;   // pairs mode: seg_a / seg_b sets; locate modes: reads / ref
@@ -1157,8 +891,11 @@ struct AlignLaunch {
     int nitems;
     uint8_t *ops;
     const int64_t *ops_off;
-    unsigned long long *stats; // [0] DP cells computed by K3, [1] alignments run by K3 (may be NULL)
-    uint32_t c31, c2;          // 0x80000000 and 2: shift multipliers handed in as parameters (see mul_hi / mad_lo)
+    unsigned long long *stats; // [0] reference-equivalent DP cells of the alignments K3 ran, [1] alignments run by K3, [2] band
+                               // cells actually computed (strip width x rows in the first pass), [3] items redone (may be NULL)
+    uint8_t *redo;             // two-pass locate: per item, 1 = the full-band kernel must (still) run it.  The first pass (strip)
+                               // clears or keeps it; the second pass skips items whose flag is 0.  NULL: single pass
+    int g256;                  // first pass: goal-side width of the strip in 1/256 of max_dst (see nb_target)
 };
 
 // resident CTAs per SM the register allocation is held to (more warps hide the shuffle / ballot latencies of a row)
@@ -1191,6 +928,7 @@ align_locate_kernel(const __grid_constant__ AlignLaunch p, const __grid_constant
         idx = __shfl_sync(FULL, idx, 0);
         if (idx >= p.nitems) break;
         const int k = p.order[idx];
+        if (p.redo && !p.redo[k]) continue; // certified by the first pass
         const int r = lv.d_kept[k];
         const int rlen = p.A.len[r];
         const int64_t rbase = p.A.base[r];
@@ -1222,9 +960,12 @@ align_locate_kernel(const __grid_constant__ AlignLaunch p, const __grid_constant
                 derive_views(*reinterpret_cast<const PairViews *>(&p.A), lv, PAIRS ? q : q - k * lv.ntrial, r, rlen, rbase, ref_base,
                              ref_len, pos, IRR, cv);
                 align_one<S, IRR>(*cv.a, cv.a_bit, cv.a_len, cv.a_tab, *cv.b, cv.b_bit, cv.b_len, p.R, p.maxn, p.maxm, planes,
-                             p.PW, par, opsrev, p.ops ? p.ops + p.ops_off[k] : nullptr, p.c31, p.c2, raw, p.RW, bar, phase, res);
+                             p.PW, par, opsrev, p.ops ? p.ops + p.ops_off[k] : nullptr, raw, p.RW, bar, phase, res);
                 cells += res.cells;
-                if (lane == 0 && p.stats) { atomicAdd(p.stats, (unsigned long long)res.cells); atomicAdd(p.stats + 1, 1ull); }
+                if (lane == 0 && p.stats) {
+                    atomicAdd(p.stats, (unsigned long long)res.cells); atomicAdd(p.stats + 1, 1ull);
+                    atomicAdd(p.stats + 2, (unsigned long long)res.cells);
+                }
                 done = f + 1;
                 mask &= mask - 1;
                 const bool ok = lv.mode == PB_MODE_LOCATE ? res.ret > 0                                      // locator.cpp:82
@@ -1248,6 +989,99 @@ align_locate_kernel(const __grid_constant__ AlignLaunch p, const __grid_constant
             rec.nedit = found ? res.nedit : 0;
             rec.ncand = ncand; rec._pad = T; rec.cells = cells; // all-vs-all: pb_pair_rec::ref_id
             recs[k] = rec;
+        }
+    }
+}
+
+// First pass of the two-pass locate (K3n): the same item loop over align_one_nb.  An item whose result is certified gets its
+// record and redo[k] = 0; one with a candidate the strip cannot decide keeps redo[k] = 1 and is run again, from its first
+// candidate, by align_locate_kernel (full band) in the second pass.
+template <int S, bool PAIRS>
+__global__ void __launch_bounds__(ALIGN_WPB * 32, MinBlocks<S>::v)
+align_locate_nb_kernel(const __grid_constant__ AlignLaunch p, const __grid_constant__ LocateView lv, const uint8_t *__restrict__ survive,
+                       const int32_t *__restrict__ rej_cells, pb_locate_rec *__restrict__ recs)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ __align__(8) uint64_t bars[ALIGN_WPB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *planes = smem + (size_t)warp * p.warp_words;
+    uint32_t *raw = planes + (size_t)4 * p.PW;
+    uint64_t *bar = &bars[warp];
+    uint32_t phase = 0u;
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    const size_t slot = (size_t)blockIdx.x * p.wpb + warp;
+    uint32_t *par = p.scratch + slot * p.slot_words;
+    uint8_t *opsrev = reinterpret_cast<uint8_t *>(par + p.par_words);
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(p.queue, 1);
+        idx = __shfl_sync(FULL, idx, 0);
+        if (idx >= p.nitems) break;
+        const int k = p.order[idx];
+        const int r = lv.d_kept[k];
+        const int rlen = p.A.len[r];
+        const int64_t rbase = p.A.base[r];
+        const int64_t c0 = PAIRS ? lv.d_item_beg[k] : lv.d_qoff[(int64_t)k * lv.ntrial];
+        const int64_t c1 = PAIRS ? lv.d_item_end[k] : lv.d_qoff[(int64_t)(k + 1) * lv.ntrial];
+        const int T = PAIRS ? lv.d_item_ref[k] : 0;
+        const int64_t ref_base = PAIRS ? p.B.base[T] : lv.ref_base;
+        const int ref_len = PAIRS ? p.B.len[T] : lv.ref_len;
+        long long cells = 0, k3_cells = 0, band_cells = 0;
+        int ncand = 0, nrun = 0, redo = 0;
+        bool found = false;
+        AlnRes res;
+        int win_j = 0, win_pos = 0, win_rpos = 0, win_dir = 0;
+        for (int64_t cb = c0; cb < c1 && !found && !redo; cb += 32) {
+            const int64_t c = cb + lane;
+            const int nvalid = (int)min((int64_t)32, c1 - cb);
+            int sv = 0, rc = 0;
+            if (lane < nvalid) { sv = survive[c]; rc = rej_cells[c]; }
+            uint32_t mask = __ballot_sync(FULL, sv);
+            int done = 0;
+            while (mask) {
+                const int f = __ffs(mask) - 1;
+                cells += __reduce_add_sync(FULL, (lane >= done && lane < f) ? rc : 0);
+                ncand += f - done + 1;
+                const int q = lv.d_cand_q[cb + f];
+                const int pos = lv.d_cand_pos[cb + f];
+                CandView cv;
+                derive_views(*reinterpret_cast<const PairViews *>(&p.A), lv, PAIRS ? q : q - k * lv.ntrial, r, rlen, rbase, ref_base,
+                             ref_len, pos, false, cv);
+                align_one_nb<S>(*cv.a, cv.a_bit, cv.a_len, *cv.b, cv.b_bit, cv.b_len, p.R, p.maxn, p.maxm, p.g256, planes, p.PW, par,
+                                p.par_words, opsrev, p.ops ? p.ops + p.ops_off[k] : nullptr, raw, p.RW, bar, phase, res, redo, band_cells);
+                if (redo) break;
+                cells += res.cells; k3_cells += res.cells; ++nrun;
+                done = f + 1;
+                mask &= mask - 1;
+                const bool ok = lv.mode == PB_MODE_LOCATE ? res.ret > 0                                      // locator.cpp:82
+                                                          : (res.ret >= 0 && res.matlen_a >= lv.min_overlap); // ref_seq.h:264-265
+                if (ok) { found = true; win_j = cv.j; win_pos = pos; win_rpos = cv.read_pos; win_dir = cv.dir; break; }
+            }
+            if (!found && !redo) {
+                cells += __reduce_add_sync(FULL, (lane >= done && lane < nvalid) ? rc : 0);
+                ncand += nvalid - done;
+            }
+        }
+        if (lane == 0) {
+            if (p.stats) { // what the strip computed counts even when the item has to be redone
+                atomicAdd(p.stats + 2, (unsigned long long)band_cells);
+                if (redo) atomicAdd(p.stats + 3, 1ull);
+                else { atomicAdd(p.stats, (unsigned long long)k3_cells); atomicAdd(p.stats + 1, (unsigned long long)nrun); }
+            }
+            p.redo[k] = (uint8_t)redo;
+            if (!redo) {
+                pb_locate_rec rec;
+                rec.nseq = PAIRS ? r : k; rec.found = found ? 1 : 0;
+                rec.j = found ? win_j : 0; rec.pos = found ? win_pos : 0;
+                rec.cost = found ? res.cost : 0;
+                rec.seg_len = !found ? 0 : (lv.mode == PB_MODE_LOCATE ? rlen - win_j : win_rpos);
+                rec.diag_cost = !found ? 0 : (lv.mode == PB_MODE_LOCATE ? res.diag_cost : win_dir);
+                rec.matlen_a = found ? res.matlen_a : 0; rec.matlen_b = found ? res.matlen_b : 0;
+                rec.nedit = found ? res.nedit : 0;
+                rec.ncand = ncand; rec._pad = T; rec.cells = cells;
+                recs[k] = rec;
+            }
         }
     }
 }
@@ -1277,7 +1111,7 @@ align_pairs_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *__restri
         const int k = p.order[idx];
         AlnRes res;
         align_one<S, IRR>(p.A, p.A.base[k], p.A.len[k], IRR ? p.A.tab[k] : 0u, p.B, p.B.base[k], p.B.len[k], p.R, p.maxn, p.maxm, planes, p.PW, par, opsrev,
-                     p.ops ? p.ops + p.ops_off[k] : nullptr, p.c31, p.c2, raw, p.RW, bar, phase, res);
+                     p.ops ? p.ops + p.ops_off[k] : nullptr, raw, p.RW, bar, phase, res);
         if (lane == 0 && p.stats) { atomicAdd(p.stats, (unsigned long long)res.cells); atomicAdd(p.stats + 1, 1ull); }
         if (lane == 0) {
             pb_align_out o;
@@ -1329,7 +1163,7 @@ align_pairs_packed_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *_
         const int PWn = ((rows + 31) >> 5) + LANES + 1;
         if (dom)
             for (int x = gl; x < PWn; x += LANES) {
-                const int bidx0 = 32 * x - D - PB_PLANE_PADBIT;
+                const int bidx0 = 32 * x - D;
                 uint32_t valid;
                 if (bidx0 >= len_b || bidx0 + 31 < 0) valid = 0u;
                 else {
@@ -1465,10 +1299,36 @@ align_pairs_packed_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *_
 static const int kClasses[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16};
 static const int kIrrClasses[] = {2, 6, 16};
 static inline int key_S(int key) { return key % 1000; }
+static int class_for_band_plain(int D)
+{
+    const int NW = (2 * D + 1 + 31) >> 5;
+    for (int S : kClasses)
+        if (32 * S >= NW) return S;
+    return -1;
+}
 static inline bool key_irr(int key) { return key >= 1000 && key < 2000; }
 // 2000 + LANES: several narrow-band alignments per warp (pairs mode only), LANES lanes x one word each
-static inline bool key_packed(int key) { return key >= 2000; }
+static inline bool key_packed(int key) { return key >= 2000 && key < 3000; }
 static inline int key_lanes(int key) { return key - 2000; }
+// 3000 + S: first pass of the two-pass locate over a certified strip (align_locate_nb_kernel<S>)
+static const int kNarrowClasses[] = {1, 2, 3, 4, 5, 6, 7, 8};
+static inline bool key_narrow(int key) { return key >= 3000; }
+
+// The strip class of an item whose widest band is D: the smallest S whose strip reaches the wanted goal-side width on the side(s)
+// the item's candidates can have their goal on; -1: run the full band only (tiny bands, or no gain).
+static int narrow_class_for_band(int D, int g256, bool both_sides)
+{
+    const int full = class_for_band_plain(D);
+    for (int S : kNarrowClasses) {
+        if (full > 0 && S > full) break;
+        int Wl, NBw, Wg;
+        const int tgt = nb_target(D, g256);
+        if (nb_policy(D, S, 0, tgt, &Wl, &NBw, &Wg) != 2) continue;
+        if (both_sides && nb_policy(D, S, 1, tgt, &Wl, &NBw, &Wg) != 2) continue;
+        return 3000 + S;
+    }
+    return -1;
+}
 
 static int class_for_band(int D, bool irr)
 { // smallest S with 32*S words >= ceil((2D+1)/32); returns the class key or -1
@@ -1494,10 +1354,22 @@ template <int S, bool IRR> struct KernelSel {
     static const void *locate_pairs() { return (const void *)align_locate_kernel<S, false, true>; }
     static const void *pairs() { return (const void *)align_pairs_kernel<S, IRR>; }
 };
+template <int S> struct NarrowSel {
+    static const void *locate() { return (const void *)align_locate_nb_kernel<S, false>; }
+    static const void *locate_pairs() { return (const void *)align_locate_nb_kernel<S, true>; }
+};
 
 // locate: 0 = pairs of sequences (pb_align_batch), 1 = locate / overlap items, 2 = all-vs-all items
 static const void *kernel_ptr(int key, int locate)
 {
+    if (key_narrow(key)) {
+        switch (key_S(key)) {
+#define CASE(s) case s: return locate == 2 ? NarrowSel<s>::locate_pairs() : NarrowSel<s>::locate();
+            CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+        }
+        return nullptr;
+    }
     if (key_packed(key)) {
         switch (key_lanes(key)) {
             case 4: return (const void *)align_pairs_packed_kernel<4>;
@@ -1547,16 +1419,11 @@ static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, int locate, si
         const int S = key_S(key), T = 32 * S;
         g->groups = 1;
         const int logical = ((cp.max_rows + 31) >> 5) + T + 2;
-        g->PW = logical + ((S % PB_PAD_MOD) == 0 ? logical / S + 2 : 0); // padded classes: one pad word per S words (bank conflicts)
+        g->PW = logical + ((S % PB_PAD_MOD) == 0 && !key_narrow(key) ? logical / S + 2 : 0); // padded classes: one pad word per S words (bank conflicts)
         g->PW = (g->PW + 3) & ~3; // 16-byte aligned sub-arrays (TMA destination)
         g->RW = PB_STAGE_WORDS; // TMA staging buffer per raw plane
         g->warp_words = (key_irr(key) ? 8 : 4) * g->PW + (key_irr(key) ? 3 : 2) * g->RW;
-#ifdef PB_TB_ASYNC
-#ifndef PB_TB_RING_PAD
-#define PB_TB_RING_PAD 0
-#endif
-        g->warp_words = std::max(g->warp_words, (2 * T + PB_TB_RING_WORDS + 2 * PB_TB_RING_PAD + 3) & ~3); // final deltas + the traceback's window ring
-#endif
+        g->warp_words = std::max(g->warp_words, (2 * T + PB_TB_RING_WORDS + 3) & ~3); // final deltas + the traceback's window ring
         g->par_words = (size_t)std::max(cp.max_rows, 1) * 2 * T;
     }
     // fewer warps per CTA when the per-warp planes are large (long sequences): the packed kernels stay under 96 KB so that two
@@ -1603,7 +1470,7 @@ static size_t scratch_budget(pb_ctx *ctx)
 }
 
 template <class LaunchFn>
-static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, int locate, AlignLaunch base, LaunchFn &&launch)
+static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, int locate, AlignLaunch base, LaunchFn &&launch, bool spread = true)
 {
     if (plans.empty()) return PB_OK;
     const size_t budget = scratch_budget(ctx);
@@ -1638,7 +1505,7 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, int locate,
                 kv.second.blocks = std::max(1, (int)(kv.second.blocks * f));
                 need += (size_t)kv.second.blocks * kv.second.wpb * kv.second.groups * kv.second.slot_words * 4;
             }
-        } else {
+        } else if (spread) {
             // Spend what is left of the budget on extra CTAs for the narrow-band classes (cheap slots): they wait behind
             // the wide-band kernels launched before them and move onto SMs as those drain, which balances the tail.
             for (auto &kv : geoms) { // ascending band class
@@ -1760,6 +1627,15 @@ int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_
         for (size_t l = 1; l < first.size(); ++l) first[l] += first[l - 1];
         for (int64_t k = 0; k < nkept; ++k) order[(size_t)first[(size_t)(maxlen - kept_lens[k])]++] = (int32_t)k;
     }
+    // Two passes.  First pass (K3n, align_locate_nb_kernel): every plain-ACGT item whose band admits a certified strip runs over
+    // the strip; what it certifies is final.  Second pass (align_locate_kernel, full band): the items the first pass could not
+    // take (byte-exact variant, tiny bands) plus those it flagged -- the kernel skips every item whose redo flag is clear, so the
+    // second pass is planned for the items that are its own plus a small allowance.  PB_NARROW=0 runs the full band only.
+    static const bool narrow_on = !(getenv("PB_NARROW") && atoi(getenv("PB_NARROW")) == 0);
+    static const int g256 = getenv("PB_NARROW_G") ? std::max(128, std::min(256, (int)(atof(getenv("PB_NARROW_G")) * 256.0))) : 205;
+    std::map<int, ClassPlan> narrow_plans;
+    const bool both_sides = lv.mode != PB_MODE_LOCATE;
+    int64_t n_narrow = 0;
     for (int32_t k : order) {
         const int L = kept_lens[k];
         // widest band / longest seg_a any candidate of this read can reach the DP with: len_a <= L, and the domain
@@ -1767,13 +1643,23 @@ int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_
         const int D = std::min(1 + (int)(L * R), maxm - 1);
         const int cls = class_for_band(std::max(D, 1), kept_irr[k] != 0); // reads (or a contig) with non-ACGT bytes: byte-exact variant
         if (cls < 0) return pb_fail(ctx, PB_ERR_DOMAIN, "band half-width %d exceeds PB_MAX_BAND", D);
+        // rows = len_a: the read itself (locator), or the reference view cut to len_b + max_dst (overlap, seq_aligner.h:100)
+        const int rows = std::min(lv.mode == PB_MODE_LOCATE ? L : L + D, std::max(maxn - 1, 1));
+        const int ncls = (narrow_on && !kept_irr[k]) ? narrow_class_for_band(D, g256, both_sides) : -1;
         ClassPlan &cp = plans[cls];
         cp.items.push_back(k);
-        // rows = len_a: the read itself (locator), or the reference view cut to len_b + max_dst (overlap, seq_aligner.h:100)
-        const int rows = lv.mode == PB_MODE_LOCATE ? L : L + D;
-        cp.max_rows = std::max(cp.max_rows, std::min(rows, std::max(maxn - 1, 1)));
+        cp.max_rows = std::max(cp.max_rows, rows);
         cp.max_D = std::max(cp.max_D, D);
-        cp.work += (double)L * (30.0 * key_S(cls) + 60.0); // ~instructions: rows x (per-word + per-row cost)
+        // ~instructions: rows x (per-word + per-row cost); an item of the first pass comes back only when it could not be certified
+        cp.work += (double)L * (30.0 * key_S(cls) + 60.0) * (ncls < 0 ? 1.0 : 0.02);
+        if (ncls >= 0) {
+            ClassPlan &np = narrow_plans[ncls];
+            np.items.push_back(k);
+            np.max_rows = std::max(np.max_rows, rows);
+            np.max_D = std::max(np.max_D, D);
+            np.work += (double)L * (16.0 * key_S(ncls) + 40.0);
+            ++n_narrow;
+        }
     }
     AlignLaunch base;
     memset(&base, 0, sizeof base);
@@ -1784,14 +1670,22 @@ int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_
     base.R = R; base.maxn = maxn; base.maxm = maxm;
     base.ops = d_ops; base.ops_off = d_ops_off;
     base.stats = d_stats;
-    base.c31 = 0x80000000u; base.c2 = 2u;
+    base.g256 = g256;
     const int kmode = lv.d_item_ref ? 2 : 1;
-    return run_classes(ctx, plans, kmode, base, [&](int key, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
+    auto launch = [&](int key, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
         void *args[] = {(void *)&p, (void *)&lv, (void *)&d_survive, (void *)&d_rej_cells, (void *)&d_recs};
         PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(key, kmode), dim3(g.blocks), dim3(g.wpb * 32), args, g.smem_bytes, st));
         ctx->launches++;
         return PB_OK;
-    });
+    };
+    DevBuf d_redo;
+    if (n_narrow > 0) {
+        PB_TRY(d_redo.alloc(ctx, (size_t)nkept + 16));
+        PB_CUDA(ctx, cudaMemsetAsync(d_redo.p, 1, (size_t)nkept, ctx->stream)); // items the first pass never sees stay flagged
+        base.redo = d_redo.as<uint8_t>();
+        PB_TRY(run_classes(ctx, narrow_plans, kmode, base, launch));
+    }
+    return run_classes(ctx, plans, kmode, base, launch, n_narrow == 0); // a second pass stays as small as its own items need
 }
 
 int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t n, double R, int maxn, int maxm,
@@ -1831,7 +1725,6 @@ int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t 
     base.B = seq_view(B);
     base.R = R; base.maxn = maxn; base.maxm = maxm;
     base.ops = d_ops; base.ops_off = d_ops_off;
-    base.c31 = 0x80000000u; base.c2 = 2u;
     return run_classes(ctx, plans, 0, base, [&](int key, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
         void *args[] = {(void *)&p, (void *)&d_out};
         PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(key, 0), dim3(g.blocks), dim3(g.wpb * 32), args, g.smem_bytes, st));

@@ -97,7 +97,7 @@ struct pb_locate_job {
     std::vector<int64_t> ops_off;
     int64_t extent = 0;
     DevBuf d_recs, d_ops, d_stats, d_votes, d_best_diag;
-    mutable unsigned long long stats[2] = {0, 0};
+    mutable unsigned long long stats[4] = {0, 0, 0, 0};
 };
 
 extern "C" int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const pb_seqset *reads,
@@ -132,7 +132,7 @@ extern "C" int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *r
     const int64_t nkept = (int64_t)kept.size();
     job->nkept = nkept;
     TRYJ(job->d_recs.alloc_zero(ctx, (size_t)std::max<int64_t>(nkept, 1) * sizeof(pb_locate_rec)));
-    TRYJ(job->d_stats.alloc_zero(ctx, 16));
+    TRYJ(job->d_stats.alloc_zero(ctx, 32));
     if (nkept == 0) { *out = job; return PB_OK; }
 
     DevBuf d_kept, d_survive, d_rej, d_ops_off;
@@ -198,7 +198,9 @@ extern "C" int pb_locate_job_stats(const pb_locate_job *job, int64_t *out)
     out[0] = job->ncand;
     out[1] = (int64_t)job->stats[1];
     out[2] = (int64_t)job->stats[0];
-    out[3] = 0;
+    out[3] = (int64_t)job->stats[2];
+    out[4] = (int64_t)job->stats[3];
+    out[5] = out[6] = out[7] = 0;
     return PB_OK;
 }
 
@@ -226,7 +228,7 @@ extern "C" int pb_locate_fetch(pb_ctx *ctx, const pb_locate_job *job, pb_locate_
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     pb_timer_begin(ctx, PB_T_D2H);
     PB_TRY(pb_d2h(ctx, recs, job->d_recs.p, (size_t)job->nkept * sizeof(pb_locate_rec)));
-    PB_TRY(pb_d2h(ctx, job->stats, job->d_stats.p, 16));
+    PB_TRY(pb_d2h(ctx, job->stats, job->d_stats.p, 32));
     if (ops && job->want_ops && job->extent) PB_TRY(pb_d2h(ctx, ops, job->d_ops.p, (size_t)job->extent));
     pb_timer_end(ctx, PB_T_D2H);
     PB_TRY(pb_sync(ctx));
@@ -332,7 +334,7 @@ extern "C" int pb_overlap_subset(pb_ctx *ctx, const pb_index *ix, const pb_seqse
     if (r == PB_OK) r = d_kept.alloc(ctx, (size_t)n * 4);
     if (r == PB_OK) r = pb_h2d(ctx, d_kept.p, kept.data(), (size_t)n * 4);
     if (r == PB_OK) r = d_recs.alloc_zero(ctx, (size_t)n * sizeof(pb_overlap_rec));
-    if (r == PB_OK) r = d_stats.alloc_zero(ctx, 16);
+    if (r == PB_OK) r = d_stats.alloc_zero(ctx, 32);
     if (r == PB_OK && prm->want_ops) {
         for (int64_t k = 0; k < n && r == PB_OK; ++k) {
             if (ops_off[k] < 0) r = pb_fail(ctx, PB_ERR_ARG, "negative ops offset");

@@ -28,13 +28,15 @@ def main():
     ctx = Context(0)
     rs = ctx.seqset_one(ref)
     ix = ctx.index(rs, MASK)
+    s = ctx.seqset(txt, offs, lens)
     for it in range(steps):
         t0 = time.time()
-        recs = ctx.locate(ix, txt, offs, lens, R=R)
-        t = ctx.timings()
+        job = ctx.locate_run(ix, s, R=R)
+        recs = job.fetch()
+        t, st = ctx.timings(), job.stats()
+        job.free()
         print(f"step {it}: {len(recs)} reads, {int(recs['found'].sum())} located, {int(recs['cells'].sum())} ref-equivalent cells, "
-              f"{time.time() - t0:.3f}s wall, align {t['align']:.2f} ms, launches so far {ctx.launches}")
-    s = ctx.seqset(txt, offs, lens)
+              f"{time.time() - t0:.3f}s wall, align {t['align']:.2f} ms, launches so far {ctx.launches}, K3 stats {st}")
     print("seed bulk:", s.seeds_device(MASK))
     ctx.close()
 
