@@ -93,6 +93,18 @@ def make_workload(nreads: int, rank: int):
     return ref, txt, offs, lens
 
 
+def source_sha() -> str:
+    """digest of the kernel sources: ties a committed ncu capture to the code it was taken with"""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "pacbioassembly_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, f), "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -269,14 +281,48 @@ def main():
         phase_s["n"] += 1
         return tot
 
-    def step_e2e():
-        recs = ctx.locate(index, txt_pinned, offs, lens, R=R)
-        state["e2e_timings"] = ctx.timings()
-        return final_reduction(recs)
+    # e2e leg: host text in, records out, through the pipelined entry points (pb_locate_submit / pb_locate_collect): the
+    # host->device copy of step k+1 is queued before step k is collected, so it runs under step k's alignment
+    pipe = {"prev": None, "mode": "text", "tot": None}
+    bin_image = {"buf": None}
 
-    def timed(fn, warmup, steps, collect=None):
+    def submit_e2e():
+        if pipe["mode"] == "bin":
+            return ctx.locate_submit_bin(index, bin_image["buf"], R=R)
+        return ctx.locate_submit(index, txt_pinned, offs, lens, R=R)
+
+    e2e_host = {"submit": 0.0, "collect": 0.0, "reduce": 0.0, "n": 0}
+
+    def step_e2e():
+        t0 = time.perf_counter()
+        cur = submit_e2e()
+        t1 = time.perf_counter()
+        if pipe["prev"] is not None:
+            recs = pipe["prev"].collect(recs=recs_host)
+            t2 = time.perf_counter()
+            state["e2e_timings"] = ctx.timings()
+            pipe["tot"] = final_reduction(recs)
+            e2e_host["collect"] += t2 - t1
+            e2e_host["reduce"] += time.perf_counter() - t2
+        e2e_host["submit"] += t1 - t0
+        e2e_host["n"] += 1
+        pipe["prev"] = cur
+        return pipe["tot"]
+
+    def drain_e2e():
+        if pipe["prev"] is not None:
+            recs = pipe["prev"].collect(recs=recs_host)
+            state["e2e_timings"] = ctx.timings()
+            state["e2e_recs"] = recs.copy()
+            pipe["tot"] = final_reduction(recs)
+            pipe["prev"] = None
+        return pipe["tot"]
+
+    def timed(fn, warmup, steps, collect=None, drain=None):
         for _ in range(warmup):
             fn()
+        if drain is not None:
+            drain()
         for k in phase_s:
             phase_s[k] = 0 if k == "n" else 0.0  # host-phase clocks cover the timed steps only
         barrier()
@@ -287,6 +333,9 @@ def main():
             out = fn()
             if collect is not None:
                 collect()
+        if drain is not None:
+            out = drain()  # the last step in flight is collected inside the timed region
+        reducer.finish()
         e1.record(stream)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
@@ -296,37 +345,72 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    align_ms, dp_cells, stage = [], [], []
+    align_ms, dp_cells, band_cells, alu_instr, redone, stage = [], [], [], [], [], []
 
     def collect():
         align_ms.append(state["timings"]["align"])
         dp_cells.append(state["stats"]["dp_cells"])
+        band_cells.append(state["stats"]["band_cells"])
+        alu_instr.append(state["stats"]["alu_instr"])
+        redone.append(state["stats"]["redone"])
         stage.append(dict(state["timings"]))
 
     ms_dev, tot_dev, launches = timed(step_device, args.warmup, args.steps, collect)
     log(f"[rank {rank}] host wall per timed device-leg step (ms): " + ", ".join(f"{k} {1e3 * v / max(phase_s['n'], 1):.1f}" for k, v in phase_s.items() if k != "n") + "\n")
-    ms_e2e, tot_e2e, _ = timed(step_e2e, max(1, min(args.warmup, 2)), args.steps)
+    state["recs"] = state["recs"].copy()  # the device leg's records (recs_host is reused by the e2e legs)
+    ms_e2e, tot_e2e, _ = timed(step_e2e, max(1, min(args.warmup, 2)), args.steps, drain=drain_e2e)
+    log(f"[rank {rank}] host wall per e2e step (ms): " + ", ".join(f"{k} {1e3 * v / max(e2e_host['n'], 1):.1f}" for k, v in e2e_host.items() if k != "n"))
+    e2e_same = bool((state["e2e_recs"] == state["recs"]).all()) if "e2e_recs" in state else None
+    e2e_stage = state.get("e2e_timings")
+    # the same batch as a .bin image (binary_test.cpp:55-63): a quarter of the bytes to copy
+    ms_bin, bin_same = None, None
+    try:
+        import workload
+        img = workload.pack_bin(txt, offs, lens)
+        bin_image["buf"] = torch.empty(len(img), dtype=torch.uint8, pin_memory=True).numpy()
+        bin_image["buf"][:] = img
+        pipe["mode"] = "bin"
+        ms_bin, tot_bin, _ = timed(step_e2e, 1, args.steps, drain=drain_e2e)
+        bin_same = bool((state["e2e_recs"] == state["recs"]).all())
+    except Exception as e:
+        log(f"[rank {rank}] .bin e2e leg skipped: {e}")
     clocks = sampler.stop()
 
     total_reads = int(tot_dev[3])  # kept reads over all ranks
     value = total_reads / (ms_dev / 1e3)
     e2e_value = int(tot_e2e[3]) / (ms_e2e / 1e3)
 
-    # roofline of the dominant kernel (K3 banded aligner): 2 parent bits written per DP cell
+    # roofline of the dominant kernel (K3 banded aligner): 2 parent bits written per band cell it computes.  Its first pass
+    # computes a certified strip of the reference's band, so two cell counts exist: the strip cells it
+    # really computes (the roofline's algorithmic bytes) and the cells the reference's recurrence would have filled for the
+    # same alignments (the GCUPS the north star asks for: work delivered, in the reference's unit).
     peak, peak_src = peaks()
-    traffic = None
+    traffic, traffic_src = None, None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of one step's K3 launches, from the committed ncu capture
-        with open(os.path.join(ROOT, "profiles", "r01_k3_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_k3_traffic.json")) as f:
             tj = json.load(f)
-        if args.reads == 100_000:
-            traffic = float(tj["dram_bytes_total"])
+        # the capture names the source files it was taken with; a stale one is not quoted
+        if args.reads == int(tj.get("reads", 0)) and tj.get("source_sha") == source_sha():
+            traffic, traffic_src = float(tj["dram_bytes_total"]), "profiles/r02_k3_traffic.json (ncu, same workload and kernel sources, one step)"
+        else:
+            traffic_src = "profiles/r02_k3_traffic.json is from other kernel sources or another workload: not quoted"
     except Exception:
         pass
     k3_ms = float(np.mean(align_ms))
     k3_cells = float(np.mean(dp_cells))
-    alg_bytes = 0.25 * k3_cells
+    k3_band = float(np.mean(band_cells))
+    alg_bytes = 0.25 * k3_band
     achieved = alg_bytes / (k3_ms / 1e3) / 1e9
     gcups = k3_cells / (k3_ms / 1e3) / 1e9
+    # integer pipe: ALU warp instructions of K3's row loops (rows x the per-row count read off each band class's SASS)
+    # against a measured LOP3/SHF peak on the same GPU
+    int_peak = ctx.int_pipe_peak()
+    int_ach = float(np.mean(alu_instr)) / (k3_ms / 1e3)
+    int_pipe = {"achieved_warp_instr_s": int_ach, "peak_warp_instr_s": int_peak, "frac": int_ach / int_peak if int_peak else None,
+                "achieved_ops_s": 32.0 * int_ach, "peak_ops_s": 32.0 * int_peak,
+                "how": "achieved = integer-ALU warp instructions of K3's row loops (12 per band word + 13 per row in the strip pass, "
+                       "19 + 23 in the full-band pass, counted in the SASS) / K3 time; peak = pb_int_pipe_peak, a register-only "
+                       "LOP3/SHF kernel timed on this GPU in this run"}
 
     # K1 bulk seed extraction over every position of the read set: 0.25 B read + 4 B written per position
     rs = ctx.seqset_from_device(d_txt.data_ptr(), d_txt.numel(), offs, lens)
@@ -353,14 +437,15 @@ def main():
 
     cpu = None
     parity = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and not args.no_cpu:  # every N: rank 0 checks a sample of ITS shard against the reference on the host
         nthreads = min(os.cpu_count() or 1, args.cpu_threads)
         sample = args.cpu_sample or 12 * nthreads
         cr = CpuReference(ref)
         rps, crecs, ids, dt = cr.run(txt, offs, lens, sample, nthreads)
         cr.close()
-        cpu = {"value": rps, "unit": UNIT, "cores": nthreads, "kind": cr.kind,
-               "sample": f"{len(ids)} evenly spaced reads of the batch in {dt:.1f}s (seed map prebuilt in {cr.build_s:.1f}s, not timed)"}
+        if world == 1:
+            cpu = {"value": rps, "unit": UNIT, "cores": nthreads, "kind": cr.kind,
+                   "sample": f"{len(ids)} evenly spaced reads of the batch in {dt:.1f}s (seed map prebuilt in {cr.build_s:.1f}s, not timed)"}
         # The same reads through the GPU path must give the same records.  The compiled reference is only a valid
         # witness where its band fits its matrix row (2*max_dst < MAXM = 6000): beyond that its cells alias the next
         # row and its answers depend on what earlier alignments left there (SURVEY Q-D1), so those reads are checked
@@ -382,7 +467,8 @@ def main():
         o.index_free(oix)
         same_port = all((g[n] == precs[n]).all() for n in fields + ["cells"])
         parity = {"reads_checked": int(len(g)), "bit_exact_vs_port": bool(same_port),
-                  "reads_in_reference_domain": int(in_domain.sum()), "bit_exact_vs_reference": same_ref}
+                  "reads_in_reference_domain": int(in_domain.sum()), "bit_exact_vs_reference": same_ref,
+                  "e2e_records_equal_device_leg": e2e_same, "rank": 0, "n_gpus": world}
 
     if rank == 0:
         t = stage[-1]
@@ -396,16 +482,30 @@ def main():
                        "parallelism": f"reads sharded over {world} GPU(s), index replicated"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(len(txt) + offs.nbytes + lens.nbytes),
                     "d2h_bytes_per_step": int(recs_host.nbytes), "ms_per_step": ms_e2e,
-                    "stage_ms": state.get("e2e_timings")},
+                    "how": "pb_locate_submit / pb_locate_collect from pinned host text: step k+1 is submitted before step k is "
+                           "collected, so its host->device copy runs under step k's alignment; every step's records are "
+                           "copied back and reduced inside the timed region",
+                    "stage_ms": e2e_stage,
+                    "bin_input": None if ms_bin is None else {
+                        "value": total_reads / (ms_bin / 1e3), "ms_per_step": ms_bin,
+                        "h2d_bytes_per_step": int(len(bin_image["buf"])), "records_equal_device_leg": bin_same,
+                        "what": "the same batch handed over as a .bin image (binary_test.cpp:55-63) through pb_locate_submit_bin"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "align_locate_kernel<S> (K3 banded bit-parallel DP + traceback)", "bound": "hbm",
+            "roofline": {"kernel": "align_locate_nb_kernel<S> + align_locate_kernel<S> (K3: banded bit-parallel DP + traceback, "
+                                   "certified strip pass then full-band pass for what it could not certify)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": "profiles/r01_k3_traffic.json (ncu, same workload, one step)",
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
-                         "algorithmic": "0.25 B (2 parent bits) per DP cell x cells of the alignments K3 ran",
-                         "kernel_ms": k3_ms, "cells_per_step": k3_cells},
+                         "algorithmic": "0.25 B (2 parent bits) per band cell K3 computes (strip width x rows, summed over the "
+                                        "alignments it ran)",
+                         "kernel_ms": k3_ms, "band_cells_per_step": k3_band, "ref_equiv_cells_per_step": k3_cells,
+                         "ref_equiv_frac": 0.25 * k3_cells / (k3_ms / 1e3) / 1e9 / peak,
+                         "reads_redone_full_band_per_step": float(np.mean(redone))},
             "gcups": gcups,
+            "gcups_note": "reference-equivalent: cells seq_aligner.h:151-190 fills for the alignments K3 ran / K3 time",
+            "gcups_band": k3_band / (k3_ms / 1e3) / 1e9,
+            "int_pipe": int_pipe,
             "seed_extract": {"achieved_gbs": seed_gbs, "frac_of_peak": seed_gbs / peak if seed_gbs else None,
                              "algorithmic": "0.25 B read + 4 B written per position, every position of the read set"},
             "probe_bulk": probe,

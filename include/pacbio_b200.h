@@ -81,6 +81,10 @@ enum {
     PB_T_COUNT
 };
 PB_API int pb_ctx_timings(const pb_ctx *ctx, float *ms /* [PB_T_COUNT] */);
+/* Measured peak of the integer ALU pipe (LOP3 / SHF / IADD3, what the banded aligner issues): a register-only kernel of
+ * independent chains on every SM; *warp_instr_per_s = warp-level instructions retired per second.  The denominator of the
+ * aligner's int-pipe fraction (BASELINE.md section 3 asks for a measured figure, not a datasheet one). */
+PB_API int pb_int_pipe_peak(pb_ctx *ctx, double *warp_instr_per_s);
 
 /* ---- L0: sequence representation (dna_seq.h) -------------------------------------------------- */
 
@@ -167,8 +171,12 @@ typedef struct {
 /* n independent align(seg_a, seg_b) calls with ratio R and template limits (maxn, maxm).
  * Sequences are given as accessor views like pb_seqset_from_text.  ops (may be NULL) receives the forward-ordered
  * edit operations of pair i at ops[ops_off[i] ..), nedit[i] bytes (PB_MATCH/INSERT/DELETE); the caller sizes each
- * slot with at least a_len+b_len+1 bytes.  edit.val (seq_aligner.h:42) is seg_b's element under each MATCH/INSERT and is
- * filled in by the C++ wrapper from the caller's own text. */
+ * slot with at least a_len+b_len+1 bytes.  The transcripts come back in ONE copy: every byte of ops between the lowest
+ * ops_off[i] and the end of the highest slot is overwritten -- nedit bytes of operations per successful pair, zeros
+ * everywhere else (failed pairs, slack behind a transcript, gaps between slots); keep nothing of your own in that range.
+ * The same holds for the ops arguments of pb_locate_batch / pb_locate_fetch / pb_overlap_batch / pb_overlap_subset.
+ * edit.val (seq_aligner.h:42) is seg_b's element under each MATCH/INSERT and is filled in by the C++ wrapper from the
+ * caller's own text. */
 PB_API int pb_align_batch(pb_ctx *ctx, const char *a_text, const int64_t *a_off, const int32_t *a_len, const int32_t *a_stride,
                    const char *b_text, const int64_t *b_off, const int32_t *b_len, const int32_t *b_stride, int64_t n,
                    double R, int maxn, int maxm, pb_align_out *out, uint8_t *ops, const int64_t *ops_off);
@@ -222,7 +230,8 @@ PB_API int64_t pb_locate_job_ncand(const pb_locate_job *job); /* seed hits (cand
 /* after pb_locate_fetch: out[0] = candidates gathered (K2), out[1] = alignments the banded aligner (K3) ran,
  * out[2] = reference cell count of those alignments (what seq_aligner.h:151-190 would have filled for them), out[3] = band
  * cells K3 actually computed (its first pass runs a certified strip of the band), out[4] = reads the strip
- * could not certify and the full-band pass ran again, out[5..7] = 0 */
+ * could not certify and the full-band pass ran again, out[5] = integer-ALU warp instructions of K3's row loops (rows x the
+ * per-row count read off the SASS of each band class), out[6..7] = 0 */
 PB_API int pb_locate_job_stats(const pb_locate_job *job, int64_t *out /* [8] */);
 /* Diagonal-bin tally of each kept read's seed hits (K2): votes[k] = hits whose diagonal pos - j falls in the fullest
  * 256-base bin, best_diag[k] = that bin's first diagonal.  A diagnostic of how concentrated the hits are; candidates are
@@ -230,6 +239,27 @@ PB_API int pb_locate_job_stats(const pb_locate_job *job, int64_t *out /* [8] */)
 PB_API int pb_locate_job_votes(pb_ctx *ctx, const pb_locate_job *job, int32_t *votes, int32_t *best_diag);
 PB_API int pb_locate_job_ops_layout(const pb_locate_job *job, int64_t *ops_off /* [nkept] or NULL */, int64_t *extent);
 PB_API int pb_locate_fetch(pb_ctx *ctx, const pb_locate_job *job, pb_locate_rec *recs, uint8_t *ops);
+
+/* Pipelined locate: what a caller streaming batches through locator.cpp:70-92 uses so that the host->device copy of batch
+ * k+1 runs under the alignment of batch k.  pb_locate_submit starts the copy of the batch's text (pinned host memory makes
+ * it asynchronous) on the context's copy stream, queues the whole step behind the step submitted before it and returns
+ * once its kernels are queued; pb_locate_collect waits for that step only, copies its records (and, with want_ops, the
+ * byte range [0, extent) of its transcripts, layout as pb_locate_run with ops_off == NULL) to the host and frees the step.
+ * Steps complete in submission order; submit k+1 before collecting k.  pb_locate_submit_bin takes the batch as a .bin image
+ * (binary_test.cpp:55-63: u32 length + ceil(len/4) packed bytes per record, 4x fewer bytes to copy) and keeps records with
+ * min_excl < len < max_excl like spaced_seed.cpp:336 -- pass prm->minlen - 1 and INT32_MAX for locator.cpp's rule. */
+typedef struct pb_locate_step pb_locate_step;
+PB_API int pb_locate_submit(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const char *reads,
+                            const int64_t *off, const int32_t *len, int64_t nreads, const pb_locate_params *prm,
+                            pb_locate_step **step);
+PB_API int pb_locate_submit_bin(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const uint8_t *bin,
+                                size_t nbytes, int min_excl, int max_excl, const pb_locate_params *prm, pb_locate_step **step);
+PB_API int64_t pb_locate_step_nkept(const pb_locate_step *step);
+PB_API int64_t pb_locate_step_ops_extent(const pb_locate_step *step);
+/* out[8] as pb_locate_job_stats; timings[PB_T_COUNT] (may be NULL) = this step's stage times as pb_ctx_timings */
+PB_API int pb_locate_collect(pb_ctx *ctx, pb_locate_step *step, pb_locate_rec *recs, int64_t *nkept, uint8_t *ops,
+                             int64_t *stats /* [8] or NULL */);
+PB_API void pb_locate_step_free(pb_locate_step *step); /* only for a step that will not be collected */
 PB_API void pb_locate_job_free(pb_locate_job *job);
 
 /* ---- assembler-side probe / verify (spaced_seed.cpp:261-299, 424-436; ref_seq.h:259-266) -------------------- */

@@ -70,6 +70,7 @@ def lib() -> C.CDLL:
         "pb_ctx_launch_count": (i64, [vp]),
         "pb_ctx_set_scratch_limit": (C.c_int, [vp, sz]),
         "pb_ctx_timings": (C.c_int, [vp, vp]),
+        "pb_int_pipe_peak": (C.c_int, [vp, P(C.c_double)]),
         "pb_encode_batch": (C.c_int, [vp, vp, sz, vp, i64, vp]),
         "pb_decode_batch": (C.c_int, [vp, vp, i64, vp]),
         "pb_text2bin": (C.c_int, [vp, vp, sz, vp, sz, P(sz)]),
@@ -105,6 +106,12 @@ def lib() -> C.CDLL:
         "pb_locate_job_votes": (C.c_int, [vp, vp, vp, vp]),
         "pb_locate_fetch": (C.c_int, [vp, vp, vp, vp]),
         "pb_locate_job_free": (None, [vp]),
+        "pb_locate_submit": (C.c_int, [vp, vp, vp, i64, vp, vp, vp, i64, P(LocateParams), P(vp)]),
+        "pb_locate_submit_bin": (C.c_int, [vp, vp, vp, i64, vp, sz, C.c_int, C.c_int, P(LocateParams), P(vp)]),
+        "pb_locate_step_nkept": (i64, [vp]),
+        "pb_locate_step_ops_extent": (i64, [vp]),
+        "pb_locate_collect": (C.c_int, [vp, vp, vp, P(i64), vp, vp]),
+        "pb_locate_step_free": (None, [vp]),
         "pb_overlap_default_params": (None, [P(OverlapParams)]),
         "pb_overlap_batch": (C.c_int, [vp, vp, vp, i64, vp, P(OverlapParams), vp, vp, vp]),
         "pb_overlap_subset": (C.c_int, [vp, vp, vp, i64, vp, vp, i64, P(OverlapParams), vp, vp, vp]),
@@ -204,6 +211,12 @@ class Context:
 
     def set_scratch_limit(self, nbytes: int):
         self.check(self._L.pb_ctx_set_scratch_limit(self.h, nbytes))
+
+    def int_pipe_peak(self) -> float:
+        """measured peak of the integer ALU pipe, warp instructions per second (pb_int_pipe_peak)"""
+        v = C.c_double(0.0)
+        self.check(self._L.pb_int_pipe_peak(self.h, C.byref(v)))
+        return float(v.value)
 
     def timings(self) -> dict:
         ms = (C.c_float * len(T_NAMES))()
@@ -355,6 +368,26 @@ class Context:
         if want_ops:
             return recs, [ops[ops_off[k]: ops_off[k] + int(recs["nedit"][k])] for k in range(nk)]
         return recs
+
+    def locate_submit(self, index: "Index", reads_text, offs, lens, **params) -> "LocateStep":
+        """Pipelined locate (pb_locate_submit): queue one batch of host text; collect() it after submitting the next one."""
+        prm = default_locate_params(**params)
+        t = _u8(reads_text)
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        h = C.c_void_p()
+        self.check(self._L.pb_locate_submit(self.h, index.h, index.ref.h, index.seq, _ptr(t), _ptr(offs), _ptr(lens), len(lens),
+                                            C.byref(prm), C.byref(h)))
+        return LocateStep(self, h, keep=(t, offs, lens))
+
+    def locate_submit_bin(self, index: "Index", image, **params) -> "LocateStep":
+        """Pipelined locate of a batch given as a .bin image (binary_test.cpp:55-63); records of len >= minlen are kept."""
+        prm = default_locate_params(**params)
+        b = _u8(image)
+        h = C.c_void_p()
+        self.check(self._L.pb_locate_submit_bin(self.h, index.h, index.ref.h, index.seq, _ptr(b), b.size, prm.minlen - 1,
+                                                2 ** 31 - 1, C.byref(prm), C.byref(h)))
+        return LocateStep(self, h, keep=(b,))
 
     def overlap(self, index: "Index", reads: "SeqSet", want_ops: bool = False, ref: "SeqSet | None" = None, ids=None, **params):
         """spaced_seed.cpp:424-436 / try_align: head and tail trials of every read against a REFSEQ-policy index.
@@ -597,6 +630,42 @@ class Index:
         return self.find_batch([key])[0]
 
 
+class LocateStep:
+    """One batch in flight through pb_locate_submit; collect() waits for it, returns its records and frees it."""
+
+    def __init__(self, ctx: Context, h, keep=()):
+        self.ctx, self.h, self._keep = ctx, h, keep  # the host buffers must outlive the asynchronous copy
+        self.stats = None
+
+    @property
+    def nkept(self) -> int:
+        return int(self.ctx._L.pb_locate_step_nkept(self.h))
+
+    def collect(self, recs: np.ndarray | None = None) -> np.ndarray:
+        nk = self.nkept
+        if recs is None:
+            recs = np.zeros(nk, dtype=LOCATE_DTYPE)
+        out = np.zeros(8, dtype=np.int64)
+        got = C.c_int64(0)
+        h, self.h = self.h, None
+        self.ctx.check(self.ctx._L.pb_locate_collect(self.ctx.h, h, _ptr(recs), C.byref(got), None, _ptr(out)))
+        self.stats = {"ncand": int(out[0]), "dp_alignments": int(out[1]), "dp_cells": int(out[2]), "band_cells": int(out[3]),
+                      "redone": int(out[4]), "alu_instr": int(out[5])}
+        self._keep = ()
+        return recs[: got.value]
+
+    def free(self):
+        if self.h and self.ctx.h:
+            self.ctx._L.pb_locate_step_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class LocateJob:
     def __init__(self, ctx: Context, h):
         self.ctx, self.h = ctx, h
@@ -626,7 +695,7 @@ class LocateJob:
         out = np.zeros(8, dtype=np.int64)
         self.ctx.check(self.ctx._L.pb_locate_job_stats(self.h, _ptr(out)))
         return {"ncand": int(out[0]), "dp_alignments": int(out[1]), "dp_cells": int(out[2]), "band_cells": int(out[3]),
-                "redone": int(out[4])}
+                "redone": int(out[4]), "alu_instr": int(out[5])}
 
     def votes(self):
         """(votes, best_diag) per kept read: the diagonal-bin tally of its seed hits (diagnostic only)"""

@@ -965,6 +965,8 @@ align_locate_kernel(const __grid_constant__ AlignLaunch p, const __grid_constant
                 if (lane == 0 && p.stats) {
                     atomicAdd(p.stats, (unsigned long long)res.cells); atomicAdd(p.stats + 1, 1ull);
                     atomicAdd(p.stats + 2, (unsigned long long)res.cells);
+                    // integer-ALU warp instructions of the row loop: 19 per band word + 23 per row (SASS of align_locate_kernel<S>)
+                    atomicAdd(p.stats + 4, (unsigned long long)(res.fail_row ? res.fail_row : res.len_a) * (19ull * S + 23ull));
                 }
                 done = f + 1;
                 mask &= mask - 1;
@@ -1027,7 +1029,7 @@ align_locate_nb_kernel(const __grid_constant__ AlignLaunch p, const __grid_const
         const int T = PAIRS ? lv.d_item_ref[k] : 0;
         const int64_t ref_base = PAIRS ? p.B.base[T] : lv.ref_base;
         const int ref_len = PAIRS ? p.B.len[T] : lv.ref_len;
-        long long cells = 0, k3_cells = 0, band_cells = 0;
+        long long cells = 0, k3_cells = 0, band_cells = 0, alu_rows = 0;
         int ncand = 0, nrun = 0, redo = 0;
         bool found = false;
         AlnRes res;
@@ -1050,6 +1052,7 @@ align_locate_nb_kernel(const __grid_constant__ AlignLaunch p, const __grid_const
                              ref_len, pos, false, cv);
                 align_one_nb<S>(*cv.a, cv.a_bit, cv.a_len, *cv.b, cv.b_bit, cv.b_len, p.R, p.maxn, p.maxm, p.g256, planes, p.PW, par,
                                 p.par_words, opsrev, p.ops ? p.ops + p.ops_off[k] : nullptr, raw, p.RW, bar, phase, res, redo, band_cells);
+                alu_rows += res.fail_row ? res.fail_row : (redo ? 0 : res.len_a);
                 if (redo) break;
                 cells += res.cells; k3_cells += res.cells; ++nrun;
                 done = f + 1;
@@ -1066,6 +1069,7 @@ align_locate_nb_kernel(const __grid_constant__ AlignLaunch p, const __grid_const
         if (lane == 0) {
             if (p.stats) { // what the strip computed counts even when the item has to be redone
                 atomicAdd(p.stats + 2, (unsigned long long)band_cells);
+                atomicAdd(p.stats + 4, (unsigned long long)alu_rows * (12ull * S + 13ull)); // SASS of align_locate_nb_kernel<S>: 12 per word + 13 per row
                 if (redo) atomicAdd(p.stats + 3, 1ull);
                 else { atomicAdd(p.stats, (unsigned long long)k3_cells); atomicAdd(p.stats + 1, (unsigned long long)nrun); }
             }

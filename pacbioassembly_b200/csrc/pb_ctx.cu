@@ -29,6 +29,8 @@ int pb_fail(pb_ctx *ctx, int code, const char *fmt, ...)
 
 extern "C" int pb_abi_version(void) { return PB_ABI_VERSION; }
 
+extern "C" void pb_ctx_destroy(pb_ctx *ctx);
+
 extern "C" int pb_device_count(void)
 {
     int n = 0;
@@ -39,13 +41,18 @@ extern "C" int pb_device_count(void)
     return n;
 }
 
+// Everything the context sets up is its own: a private memory pool for its stream-ordered buffers (bounded release threshold),
+// its own streams and events.  It changes NO process- or device-wide state unless asked to through the environment:
+//   PB_L2_FETCH=<32|64|128>   cudaLimitMaxL2FetchGranularity (device-wide; the traceback's scattered 16-byte reads like 32)
+//   PB_POOL_KEEP_MB=<n>       bytes the private pool keeps across synchronisations (default 16384 MB; what is freed beyond
+//                             that goes back to the driver, so other allocators in the process are not starved)
+// The aligner runs one kernel per band class on its own stream (up to 14); with the default of 8 hardware queues the rest
+// share queues.  Applications that want all of them concurrent set CUDA_DEVICE_MAX_CONNECTIONS=32 before CUDA is
+// initialised (bench.py and the host drivers do); the library does not touch the environment.
 extern "C" int pb_ctx_create(int device, pb_ctx **out)
 {
     if (!out) return pb_fail(nullptr, PB_ERR_ARG, "pb_ctx_create: out is NULL");
     *out = nullptr;
-    // The aligner runs one kernel per band class on its own stream (up to 14); the default of 8 hardware queues would
-    // serialise the rest.  Only effective if CUDA has not been initialised in this process yet (bench.py sets it too).
-    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = pb_device_count();
     if (n <= 0)
         return pb_fail(nullptr, PB_ERR_NO_DEVICE,
@@ -53,31 +60,48 @@ extern "C" int pb_ctx_create(int device, pb_ctx **out)
     if (device < 0 || device >= n) return pb_fail(nullptr, PB_ERR_ARG, "device %d out of range [0,%d)", device, n);
     pb_ctx *ctx = new pb_ctx();
     ctx->device = device;
-    PB_CUDA(nullptr, cudaSetDevice(device));
+    // every failure below releases what was created so far
+#define CREATE_CUDA(call)                                                                                           \
+    do {                                                                                                            \
+        cudaError_t _e = (call);                                                                                    \
+        if (_e != cudaSuccess) {                                                                                    \
+            pb_ctx_destroy(ctx);                                                                                    \
+            return pb_fail(nullptr, _e == cudaErrorMemoryAllocation ? PB_ERR_NOMEM : PB_ERR_CUDA, "%s failed: %s", #call, \
+                           cudaGetErrorString(_e));                                                                 \
+        }                                                                                                           \
+    } while (0)
+    CREATE_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
-    PB_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) {
-        delete ctx;
+        pb_ctx_destroy(ctx);
         return pb_fail(nullptr, PB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
                        prop.major, prop.minor);
     }
     ctx->sm_count = prop.multiProcessorCount;
-    // The traceback reads 8-byte parent pairs scattered over rows: keep DRAM->L2 fills at sector size (a hint)
-    {
-        const char *g = getenv("PB_L2_FETCH");
-        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g ? (size_t)atoi(g) : 32);
+    if (const char *g = getenv("PB_L2_FETCH")) { // opt-in: a device-wide limit
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
         cudaGetLastError();
     }
-    PB_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2 * PB_T_COUNT; ++i) PB_CUDA(nullptr, cudaEventCreate(&ctx->ev[i]));
-    // keep freed blocks in the pool: per-step allocations become pointer bumps
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2 * PB_T_COUNT; ++i) CREATE_CUDA(cudaEventCreate(&ctx->ev[i]));
+    {
+        // private pool: per-step allocations become pointer bumps without touching the device's default pool
+        cudaMemPoolProps pp;
+        memset(&pp, 0, sizeof pp);
+        pp.allocType = cudaMemAllocationTypePinned;
+        pp.handleTypes = cudaMemHandleTypeNone;
+        pp.location.type = cudaMemLocationTypeDevice;
+        pp.location.id = device;
+        CREATE_CUDA(cudaMemPoolCreate(&ctx->pool, &pp));
+        const char *k = getenv("PB_POOL_KEEP_MB");
+        uint64_t thr = (uint64_t)(k ? atoll(k) : 16384) << 20;
+        CREATE_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr));
     }
     ctx->h_pin_bytes = 1 << 20;
-    PB_CUDA(nullptr, cudaMallocHost(&ctx->h_pin, ctx->h_pin_bytes));
+    CREATE_CUDA(cudaMallocHost(&ctx->h_pin, ctx->h_pin_bytes));
+#undef CREATE_CUDA
     *out = ctx;
     return PB_OK;
 }
@@ -86,7 +110,8 @@ extern "C" void pb_ctx_destroy(pb_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (int i = 0; i < 2 * PB_T_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -94,7 +119,14 @@ extern "C" void pb_ctx_destroy(pb_ctx *ctx)
     for (auto ev : ctx->aux_events) cudaEventDestroy(ev);
     if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
     if (ctx->scratch) cudaFree(ctx->scratch);
-    cudaStreamDestroy(ctx->stream);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+        if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+    cudaGetLastError();
     delete ctx;
 }
 
@@ -120,11 +152,16 @@ void pb_timer_reset(pb_ctx *ctx)
 {
     for (int i = 0; i < PB_T_COUNT; ++i) { ctx->times[i] = 0.f; ctx->timed[i] = false; }
 }
-void pb_timer_begin(pb_ctx *ctx, int which) { cudaEventRecord(ctx->ev[2 * which], ctx->stream); }
+void pb_timer_begin(pb_ctx *ctx, int which)
+{
+    cudaEventRecord(ctx->ev[2 * which], ctx->stream);
+    if (ctx->step_ev) cudaEventRecord(ctx->step_ev[2 * which], ctx->stream);
+}
 void pb_timer_end(pb_ctx *ctx, int which)
 {
     cudaEventRecord(ctx->ev[2 * which + 1], ctx->stream);
     ctx->timed[which] = true;
+    if (ctx->step_ev) { cudaEventRecord(ctx->step_ev[2 * which + 1], ctx->stream); ctx->step_timed[which] = true; }
 }
 void pb_timer_collect(pb_ctx *ctx)
 {
@@ -141,7 +178,7 @@ int DevBuf::alloc(pb_ctx *c, size_t n)
     release();
     ctx = c;
     if (n == 0) n = 16;
-    cudaError_t e = cudaMallocAsync(&p, n, c->stream);
+    cudaError_t e = cudaMallocFromPoolAsync(&p, n, c->pool, c->stream);
     if (e != cudaSuccess) {
         p = nullptr;
         cudaGetLastError();
@@ -182,5 +219,58 @@ int pb_d2h(pb_ctx *ctx, void *dst, const void *src, size_t bytes)
 int pb_sync(pb_ctx *ctx)
 {
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// integer-pipe peak: the measured denominator of the aligner's int-pipe fraction
+// ---------------------------------------------------------------------------------------------
+
+// Eight independent register chains per thread, each iteration two LOP3 and one funnel shift per chain: the aligner's
+// row-loop instruction mix, with no memory traffic and enough independent work to keep the pipe full.
+__global__ void __launch_bounds__(256) int_pipe_kernel(uint32_t *out, int iters, uint32_t seed)
+{
+    uint32_t a[8], b[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] = seed * (threadIdx.x + 1) + k; b[k] = seed ^ (blockIdx.x * 977 + k * 31); }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a[k] = (a[k] & b[k]) ^ b[(k + 1) & 7];          // LOP3
+            b[k] = __funnelshift_l(b[k], a[k], 1);           // SHF
+            a[k] = (a[k] | b[(k + 3) & 7]) ^ ~b[(k + 5) & 7]; // LOP3 (a plain add could be issued as IMAD on the FMA pipe)
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r ^= a[k] ^ b[k];
+    if (r == 0x12345u) out[0] = r; // keeps the chains alive
+}
+
+extern "C" int pb_int_pipe_peak(pb_ctx *ctx, double *warp_instr_per_s)
+{
+    if (!ctx || !warp_instr_per_s) return pb_fail(ctx, PB_ERR_ARG, "pb_int_pipe_peak: bad argument");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf d;
+    PB_TRY(d.alloc_zero(ctx, 64));
+    const int iters = 4096, blocks = ctx->sm_count * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    PB_CUDA(ctx, cudaEventCreate(&e0));
+    PB_CUDA(ctx, cudaEventCreate(&e1));
+    float best = 0.f;
+    for (int rep = 0; rep < 4; ++rep) { // first launch warms up; keep the fastest
+        cudaEventRecord(e0, ctx->stream);
+        int_pipe_kernel<<<blocks, threads, 0, ctx->stream>>>(d.as<uint32_t>(), iters, 0x9e3779b9u + rep);
+        cudaEventRecord(e1, ctx->stream);
+        ctx->launches++;
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && (best == 0.f || ms < best)) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double instr = (double)blocks * (threads / 32) * (double)iters * 24.0; // 8 chains x 3 instructions, per warp
+    *warp_instr_per_s = instr / (best * 1e-3);
     return PB_OK;
 }

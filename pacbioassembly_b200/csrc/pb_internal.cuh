@@ -18,9 +18,20 @@
 struct pb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // host<->device copies of the pipelined entry points (pb_locate_submit / _collect)
+    cudaMemPool_t pool = nullptr;       // private pool behind DevBuf (bounded release threshold)
+    // two grow-only device staging buffers for the batches of pb_locate_submit (the copy of batch k+1 lands in one while
+    // batch k is still being ingested from the other); stage_ev[i] = the last ingest that read buffer i has finished
+    void *stage[2] = {nullptr, nullptr};
+    size_t stage_bytes[2] = {0, 0};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    int stage_next = 0;
     cudaEvent_t ev[2 * PB_T_COUNT] = {};
     float times[PB_T_COUNT] = {};
     bool timed[PB_T_COUNT] = {};
+    // pipelined steps (pb_locate_submit) keep their own stage events: while one is being queued the stage timers record here too
+    cudaEvent_t *step_ev = nullptr;
+    bool *step_timed = nullptr;
     int64_t launches = 0;
     size_t scratch_limit = 0;
     int sm_count = 148;

@@ -52,7 +52,7 @@ extern "C" int pb_align_batch(pb_ctx *ctx, const char *a_text, const int64_t *a_
             if (ops_off[i] < 0) { r = pb_fail(ctx, PB_ERR_ARG, "negative ops offset"); break; }
             extent = std::max<int64_t>(extent, ops_off[i] + a_len[i] + b_len[i] + 1);
         }
-        if (r == PB_OK) r = d_ops.alloc(ctx, (size_t)extent + 16);
+        if (r == PB_OK) r = d_ops.alloc_zero(ctx, (size_t)extent + 16);
         if (r == PB_OK) r = d_ops_off.alloc(ctx, (size_t)n * 8);
         if (r == PB_OK) r = pb_h2d(ctx, d_ops_off.p, ops_off, (size_t)n * 8);
     }
@@ -97,7 +97,7 @@ struct pb_locate_job {
     std::vector<int64_t> ops_off;
     int64_t extent = 0;
     DevBuf d_recs, d_ops, d_stats, d_votes, d_best_diag;
-    mutable unsigned long long stats[4] = {0, 0, 0, 0};
+    mutable unsigned long long stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 extern "C" int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const pb_seqset *reads,
@@ -132,7 +132,7 @@ extern "C" int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *r
     const int64_t nkept = (int64_t)kept.size();
     job->nkept = nkept;
     TRYJ(job->d_recs.alloc_zero(ctx, (size_t)std::max<int64_t>(nkept, 1) * sizeof(pb_locate_rec)));
-    TRYJ(job->d_stats.alloc_zero(ctx, 32));
+    TRYJ(job->d_stats.alloc_zero(ctx, 64));
     if (nkept == 0) { *out = job; return PB_OK; }
 
     DevBuf d_kept, d_survive, d_rej, d_ops_off;
@@ -153,7 +153,7 @@ extern "C" int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *r
             }
         }
         job->extent = ext;
-        TRYJ(job->d_ops.alloc(ctx, (size_t)ext + 16));
+        TRYJ(job->d_ops.alloc_zero(ctx, (size_t)ext + 16));
         TRYJ(d_ops_off.alloc(ctx, (size_t)nkept * 8));
         TRYJ(pb_h2d(ctx, d_ops_off.p, job->ops_off.data(), (size_t)nkept * 8));
     }
@@ -200,7 +200,8 @@ extern "C" int pb_locate_job_stats(const pb_locate_job *job, int64_t *out)
     out[2] = (int64_t)job->stats[0];
     out[3] = (int64_t)job->stats[2];
     out[4] = (int64_t)job->stats[3];
-    out[5] = out[6] = out[7] = 0;
+    out[5] = (int64_t)job->stats[4];
+    out[6] = out[7] = 0;
     return PB_OK;
 }
 
@@ -228,7 +229,7 @@ extern "C" int pb_locate_fetch(pb_ctx *ctx, const pb_locate_job *job, pb_locate_
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     pb_timer_begin(ctx, PB_T_D2H);
     PB_TRY(pb_d2h(ctx, recs, job->d_recs.p, (size_t)job->nkept * sizeof(pb_locate_rec)));
-    PB_TRY(pb_d2h(ctx, job->stats, job->d_stats.p, 32));
+    PB_TRY(pb_d2h(ctx, job->stats, job->d_stats.p, 64));
     if (ops && job->want_ops && job->extent) PB_TRY(pb_d2h(ctx, ops, job->d_ops.p, (size_t)job->extent));
     pb_timer_end(ctx, PB_T_D2H);
     PB_TRY(pb_sync(ctx));
@@ -268,6 +269,166 @@ extern "C" int pb_locate_batch(pb_ctx *ctx, const pb_index *ix, const pb_seqset 
     pb_timer_collect(ctx);
     pb_locate_job_free(job);
     pb_seqset_free(rs);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pipelined locate: the copy of batch k+1 runs under the alignment of batch k
+// ---------------------------------------------------------------------------------------------
+
+struct pb_locate_step {
+    pb_ctx *ctx = nullptr;
+    pb_seqset *reads = nullptr;
+    pb_locate_job *job = nullptr;
+    cudaEvent_t done = nullptr;
+    cudaEvent_t ev[2 * PB_T_COUNT] = {};
+    bool timed[PB_T_COUNT] = {};
+};
+
+extern "C" void pb_locate_step_free(pb_locate_step *st)
+{
+    if (!st) return;
+    cudaSetDevice(st->ctx->device);
+    if (st->job) pb_locate_job_free(st->job);
+    if (st->reads) pb_seqset_free(st->reads);
+    if (st->done) cudaEventDestroy(st->done);
+    for (auto e : st->ev)
+        if (e) cudaEventDestroy(e);
+    delete st;
+}
+
+// h_src: the batch as the host holds it (text blob or .bin image); off/len: where each sequence starts in it
+static int submit_common(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const void *h_src, size_t nbytes,
+                         const int64_t *off, const int32_t *len, int64_t n, int src_mode, const pb_locate_params *prm,
+                         pb_locate_step **out)
+{
+    *out = nullptr;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    pb_locate_step *st = new pb_locate_step();
+    st->ctx = ctx;
+    int r = PB_OK;
+    void *d_src = nullptr;
+    auto cu = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && r == PB_OK)
+            r = pb_fail(ctx, e == cudaErrorMemoryAllocation ? PB_ERR_NOMEM : PB_ERR_CUDA, "pb_locate_submit: %s: %s", what, cudaGetErrorString(e));
+    };
+    cu(cudaEventCreateWithFlags(&st->done, cudaEventDisableTiming), "event");
+    for (int i = 0; i < 2 * PB_T_COUNT && r == PB_OK; ++i) cu(cudaEventCreate(&st->ev[i]), "event");
+    // the batch lands in one of the context's two staging buffers (no allocation on the pipelined path)
+    const int slot = ctx->stage_next;
+    ctx->stage_next ^= 1;
+    if (r == PB_OK && !ctx->stage_ev[slot]) cu(cudaEventCreateWithFlags(&ctx->stage_ev[slot], cudaEventDisableTiming), "event");
+    if (r == PB_OK && ctx->stage_bytes[slot] < nbytes + 16) {
+        if (ctx->stage[slot]) {
+            cu(cudaEventSynchronize(ctx->stage_ev[slot]), "wait for the staging buffer");
+            cudaFree(ctx->stage[slot]);
+            ctx->stage[slot] = nullptr;
+            ctx->stage_bytes[slot] = 0;
+        }
+        const size_t want = nbytes + nbytes / 16 + 4096;
+        cu(cudaMalloc(&ctx->stage[slot], want), "device staging buffer for the batch");
+        if (r == PB_OK) ctx->stage_bytes[slot] = want;
+    } else if (r == PB_OK && ctx->stage[slot]) {
+        cu(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_ev[slot], 0), "wait"); // its previous batch has been ingested
+    }
+    d_src = ctx->stage[slot];
+    if (r == PB_OK) {
+        cu(cudaEventRecord(st->ev[2 * PB_T_H2D], ctx->copy_stream), "record");
+        cu(cudaMemcpyAsync(d_src, h_src, nbytes, cudaMemcpyHostToDevice, ctx->copy_stream), "host->device copy");
+        cu(cudaEventRecord(st->ev[2 * PB_T_H2D + 1], ctx->copy_stream), "record");
+        st->timed[PB_T_H2D] = true;
+        cu(cudaStreamWaitEvent(ctx->stream, st->ev[2 * PB_T_H2D + 1], 0), "wait");
+    }
+    if (r == PB_OK) {
+        ctx->step_ev = st->ev;
+        ctx->step_timed = st->timed;
+        pb_timer_begin(ctx, PB_T_TOTAL);
+        r = pb_seqset_build(ctx, d_src, off, len, nullptr, n, src_mode, &st->reads);
+        cu(cudaEventRecord(ctx->stage_ev[slot], ctx->stream), "record"); // ingest has read the staging buffer by then
+        if (r == PB_OK) r = pb_locate_run(ctx, ix, ref, ref_seq, st->reads, prm, nullptr, &st->job);
+        pb_timer_end(ctx, PB_T_TOTAL);
+        ctx->step_ev = nullptr;
+        ctx->step_timed = nullptr;
+        st->timed[PB_T_H2D] = true; // the copy-stream pair recorded above (pb_seqset_build does not touch it)
+    }
+    if (r == PB_OK) cu(cudaEventRecord(st->done, ctx->stream), "record");
+    if (r != PB_OK) { pb_locate_step_free(st); return r; }
+    *out = st;
+    return PB_OK;
+}
+
+extern "C" int pb_locate_submit(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const char *reads_text,
+                                const int64_t *off, const int32_t *len, int64_t nreads, const pb_locate_params *prm,
+                                pb_locate_step **step)
+{
+    if (!ctx || !ix || !ref || !prm || !step || nreads < 0 || (nreads && (!reads_text || !off || !len)))
+        return pb_fail(ctx, PB_ERR_ARG, "pb_locate_submit: bad argument");
+    int64_t lo = INT64_MAX, hi = 0;
+    for (int64_t i = 0; i < nreads; ++i) {
+        if (len[i] <= 0) continue;
+        if (off[i] < 0) return pb_fail(ctx, PB_ERR_ARG, "negative text offset");
+        lo = std::min(lo, off[i]);
+        hi = std::max(hi, off[i] + len[i]);
+    }
+    if (lo > hi) lo = hi = 0;
+    std::vector<int64_t> rel(off, off + nreads);
+    for (auto &x : rel) x -= lo;
+    return submit_common(ctx, ix, ref, ref_seq, reads_text + lo, (size_t)(hi - lo), rel.data(), len, nreads, PB_SRC_TEXT, prm, step);
+}
+
+extern "C" int pb_locate_submit_bin(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const uint8_t *bin,
+                                    size_t nbytes, int min_excl, int max_excl, const pb_locate_params *prm, pb_locate_step **step)
+{
+    if (!ctx || !ix || !ref || !prm || !step || (!bin && nbytes)) return pb_fail(ctx, PB_ERR_ARG, "pb_locate_submit_bin: bad argument");
+    // record walk, spaced_seed.cpp:330-342: u32 length, ceil(len/4) body bytes, records back to back
+    std::vector<int64_t> off;
+    std::vector<int32_t> len;
+    size_t p = 0;
+    while (p + 4 <= nbytes) {
+        uint32_t l;
+        memcpy(&l, bin + p, 4);
+        const size_t body = ((size_t)l + 3) / 4;
+        if (p + 4 + body > nbytes) return pb_fail(ctx, PB_ERR_ARG, "truncated .bin record at byte %zu", p);
+        if ((int64_t)l > min_excl && (int64_t)l < max_excl) {
+            off.push_back((int64_t)p + 4);
+            len.push_back((int32_t)l);
+        }
+        p += 4 + body;
+    }
+    return submit_common(ctx, ix, ref, ref_seq, bin, nbytes, off.data(), len.data(), (int64_t)off.size(), PB_SRC_PACKED, prm, step);
+}
+
+extern "C" int64_t pb_locate_step_nkept(const pb_locate_step *st) { return st && st->job ? st->job->nkept : 0; }
+extern "C" int64_t pb_locate_step_ops_extent(const pb_locate_step *st) { return st && st->job ? st->job->extent : 0; }
+
+extern "C" int pb_locate_collect(pb_ctx *ctx, pb_locate_step *st, pb_locate_rec *recs, int64_t *nkept, uint8_t *ops, int64_t *stats)
+{
+    if (!ctx || !st || !st->job || (st->job->nkept && !recs)) return pb_fail(ctx, PB_ERR_ARG, "pb_locate_collect: bad argument");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    pb_locate_job *job = st->job;
+    int r = PB_OK;
+    auto cu = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && r == PB_OK) r = pb_fail(ctx, PB_ERR_CUDA, "pb_locate_collect: %s: %s", what, cudaGetErrorString(e));
+    };
+    cu(cudaStreamWaitEvent(ctx->copy_stream, st->done, 0), "wait");
+    cu(cudaEventRecord(st->ev[2 * PB_T_D2H], ctx->copy_stream), "record");
+    if (job->nkept) cu(cudaMemcpyAsync(recs, job->d_recs.p, (size_t)job->nkept * sizeof(pb_locate_rec), cudaMemcpyDeviceToHost, ctx->copy_stream), "records");
+    cu(cudaMemcpyAsync(job->stats, job->d_stats.p, 64, cudaMemcpyDeviceToHost, ctx->copy_stream), "stats");
+    if (ops && job->want_ops && job->extent) cu(cudaMemcpyAsync(ops, job->d_ops.p, (size_t)job->extent, cudaMemcpyDeviceToHost, ctx->copy_stream), "transcripts");
+    cu(cudaEventRecord(st->ev[2 * PB_T_D2H + 1], ctx->copy_stream), "record");
+    cu(cudaStreamSynchronize(ctx->copy_stream), "synchronize");
+    if (r == PB_OK) {
+        st->timed[PB_T_D2H] = true;
+        if (nkept) *nkept = job->nkept;
+        if (stats) pb_locate_job_stats(job, stats);
+        for (int i = 0; i < PB_T_COUNT; ++i) { // this step's stage times become the context's current timings
+            float ms = 0.f;
+            ctx->times[i] = 0.f;
+            if (st->timed[i] && cudaEventElapsedTime(&ms, st->ev[2 * i], st->ev[2 * i + 1]) == cudaSuccess) ctx->times[i] = ms;
+            else cudaGetLastError();
+        }
+    }
+    pb_locate_step_free(st);
     return r;
 }
 
@@ -334,13 +495,13 @@ extern "C" int pb_overlap_subset(pb_ctx *ctx, const pb_index *ix, const pb_seqse
     if (r == PB_OK) r = d_kept.alloc(ctx, (size_t)n * 4);
     if (r == PB_OK) r = pb_h2d(ctx, d_kept.p, kept.data(), (size_t)n * 4);
     if (r == PB_OK) r = d_recs.alloc_zero(ctx, (size_t)n * sizeof(pb_overlap_rec));
-    if (r == PB_OK) r = d_stats.alloc_zero(ctx, 32);
+    if (r == PB_OK) r = d_stats.alloc_zero(ctx, 64);
     if (r == PB_OK && prm->want_ops) {
         for (int64_t k = 0; k < n && r == PB_OK; ++k) {
             if (ops_off[k] < 0) r = pb_fail(ctx, PB_ERR_ARG, "negative ops offset");
             extent = std::max<int64_t>(extent, ops_off[k] + 3 * (int64_t)kept_lens[k] + 2 * prm->maxm + 16);
         }
-        if (r == PB_OK) r = d_ops.alloc(ctx, (size_t)extent + 16);
+        if (r == PB_OK) r = d_ops.alloc_zero(ctx, (size_t)extent + 16);
         if (r == PB_OK) r = d_ops_off.alloc(ctx, (size_t)n * 8);
         if (r == PB_OK) r = pb_h2d(ctx, d_ops_off.p, ops_off, (size_t)n * 8);
     }

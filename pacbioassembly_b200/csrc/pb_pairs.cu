@@ -405,7 +405,7 @@ extern "C" int pb_overlap_all_run(pb_ctx *ctx, const pb_index *ix, const pb_seqs
                 STEP(pb_sync(ctx));
                 std::vector<uint8_t> irr((size_t)nlive, 0);
                 STEP(job->d_recs.alloc_zero(ctx, (size_t)nlive * sizeof(pb_pair_rec)));
-                STEP(d_stats.alloc_zero(ctx, 32));
+                STEP(d_stats.alloc_zero(ctx, 64));
                 lv.d_kept = d_lq.as<int32_t>();
                 lv.d_item_ref = d_lref.as<int32_t>();
                 lv.d_item_beg = d_lbeg.as<int64_t>();

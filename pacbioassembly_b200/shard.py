@@ -104,56 +104,88 @@ def gather_pair_records(recs: np.ndarray, device: torch.device | str = "cpu", ds
 
 
 class FinalReduction:
-    """The path's one exchange, with its buffers allocated once: all-reduce of the four counters and a gather of every
-    rank's 56-byte records on rank 0 (fixed-size slots of `cap` records; the kept count travels in the counters' gather).
-    Works over NCCL (device="cuda") or gloo (device="cpu")."""
+    """The path's one exchange, with its buffers allocated once: an all-reduce of the four counters -- the only part a step
+    waits for -- and a gather of every rank's 56-byte records on rank 0 (fixed-size slots of `cap` records behind an 8-byte
+    count), which runs on a side stream under the NEXT step's kernels: `wait()` (called by the next `__call__`, by `records()`
+    and by `finish()`) is where it is joined.  Works over NCCL (device="cuda") or gloo (device="cpu")."""
 
     def __init__(self, cap: int, device="cpu", dst: int = 0):
         self.cap, self.device, self.dst = int(cap), device, dst
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         nbytes = self.cap * LOCATE_DTYPE.itemsize + 8  # 8-byte header: number of valid records
-        cuda = str(device).startswith("cuda")
-        self.h_send = torch.empty(nbytes, dtype=torch.uint8, pin_memory=cuda)
+        self.cuda = str(device).startswith("cuda")
+        self.h_send = torch.empty(nbytes, dtype=torch.uint8, pin_memory=self.cuda)
         self.d_send = torch.empty(nbytes, dtype=torch.uint8, device=device)
         self.counters = torch.zeros(4, dtype=torch.int64, device=device)
-        self.h_counters = torch.zeros(4, dtype=torch.int64, pin_memory=cuda)
+        self.h_counters = torch.zeros(4, dtype=torch.int64, pin_memory=self.cuda)
+        self.side = torch.cuda.Stream() if self.cuda else None
+        self.pending = None  # (work handle or None, event or None) of the gather in flight
+        self.local = None
         if self.rank == dst and self.world > 1:
             self.d_recv = [torch.empty(nbytes, dtype=torch.uint8, device=device) for _ in range(self.world)]
-            self.h_recv = torch.empty(self.world * nbytes, dtype=torch.uint8, pin_memory=cuda)
+            self.h_recv = torch.empty(self.world * nbytes, dtype=torch.uint8, pin_memory=self.cuda)
         else:
             self.d_recv = None
 
+    def wait(self):
+        """join the record gather started by the last call (a no-op when none is in flight)"""
+        if self.pending is None:
+            return
+        work, ev = self.pending
+        self.pending = None
+        if ev is not None:
+            ev.synchronize()
+        elif work is not None:
+            work.wait()
+            if self.rank == self.dst:
+                nbytes = self.d_send.numel()
+                for r in range(self.world):
+                    self.h_recv[r * nbytes: (r + 1) * nbytes].copy_(self.d_recv[r])
+
+    finish = wait
+
     def __call__(self, recs: np.ndarray, want_records: bool = True):
         """returns (summed counters as numpy int64[4], concatenated records on dst or None)"""
+        self.wait()  # the send buffer is reused
         self.h_counters.numpy()[:] = counters_of(recs)
-        self.counters.copy_(self.h_counters, non_blocking=True)
         if self.world == 1:
-            if str(self.device).startswith("cuda"):
-                torch.cuda.current_stream().synchronize()
+            self.local = recs
             return self.h_counters.numpy().copy(), (recs if want_records else None)
-        dist.all_reduce(self.counters)
         n = len(recs)
         assert n <= self.cap
         hs = self.h_send.numpy()
         hs[:8].view(np.int64)[0] = n
         hs[8: 8 + n * LOCATE_DTYPE.itemsize] = recs.view(np.uint8).reshape(-1)
-        self.d_send.copy_(self.h_send, non_blocking=True)
-        dist.gather(self.d_send, self.d_recv, dst=self.dst)
+        # the step's result: four counters, all-reduced
+        self.counters.copy_(self.h_counters, non_blocking=True)
+        dist.all_reduce(self.counters)
         tot = self.counters.cpu().numpy()
-        if self.rank != self.dst:
-            return tot, None
-        nbytes = self.d_send.numel()
-        for r in range(self.world):
-            self.h_recv[r * nbytes: (r + 1) * nbytes].copy_(self.d_recv[r], non_blocking=True)
-        if str(self.device).startswith("cuda"):
-            torch.cuda.current_stream().synchronize()
-        if not want_records:
+        # the records follow on a side stream; nothing below blocks the host
+        if self.cuda:
+            with torch.cuda.stream(self.side):
+                self.d_send.copy_(self.h_send, non_blocking=True)
+                work = dist.gather(self.d_send, self.d_recv, dst=self.dst, async_op=True)
+                work.wait()  # orders the side stream behind the collective, does not block the host
+                if self.rank == self.dst:
+                    nbytes = self.d_send.numel()
+                    for r in range(self.world):
+                        self.h_recv[r * nbytes: (r + 1) * nbytes].copy_(self.d_recv[r], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.side)
+            self.pending = (work, ev)
+        else:
+            self.d_send.copy_(self.h_send)
+            self.pending = (dist.gather(self.d_send, self.d_recv, dst=self.dst, async_op=True), None)
+        if not want_records or self.rank != self.dst:
             return tot, None
         return tot, self.records()
 
     def records(self) -> np.ndarray:
         """dst only, after a call: every rank's records as one array, nseq renumbered into the global kept order"""
+        self.wait()
+        if self.world == 1:
+            return self.local.copy()
         nbytes = self.d_send.numel()
         hr = self.h_recv.numpy()
         parts, base = [], 0

@@ -469,6 +469,92 @@ def test_locate_properties_at_scale(ctx):
     assert (r0["pos"] == s0).all()
 
 
+def test_locate_config1_full(ctx, oracle):
+    """BASELINE config 1 at its stated size: 1 Mbp reference (seed 1), 2 000 reads of 500-3000 bases at 5 % error, every
+    mask of seeds.txt, locator semantics at R = 0.15 and R = 0.3 (locator.cpp:51-54, 62-66, 70-92) -- all against the oracle"""
+    ref = workload.reference(1, 1_000_000)
+    rng = np.random.default_rng(11)
+    lens = rng.integers(500, 3001, size=2000).astype(np.int32)
+    txt, offs, lens, _ = workload.reads(8, ref, lens, 0.025, 0.015, 0.01)
+    nthreads = min(os.cpu_count() or 1, 32)
+    for mask in MASKS:
+        for R in (0.15, 0.3):
+            recs = locate_vs_oracle(ctx, oracle, ref, txt, offs, lens, mask, R, nthreads=nthreads)
+            assert recs["found"].sum() > 1500, (hex(mask), R)
+
+
+def test_locate_strip_redo_paths(ctx, oracle):
+    """K3's first pass runs a certified strip of the band and hands what it cannot certify to the full band.  Reads built to
+    land on both sides of the certificate: a block deletion / insertion late in the read drives the final cost towards R*len and
+    the path far off the diagonal; plus reads at the contig's end (goal on the last column)."""
+    ref = workload.reference(2, 300_000)
+    rng = np.random.default_rng(5)
+    L = 4000
+    lens = np.full(120, L, dtype=np.int32)
+    base, offs, lens, starts = workload.reads(21, ref, lens, 0.01, 0.01, 0.01)
+    parts = []
+    for k in range(len(lens)):
+        r = base[offs[k]: offs[k] + lens[k]]
+        frac = 0.10 + 0.0025 * k  # block size as a share of the read: 10 % .. 40 %
+        blk = int(frac * L)
+        at = int(0.93 * L) - blk // 2
+        if k % 2 == 0:  # deletion from the read: the path jumps right of the diagonal
+            r = np.concatenate([r[:at], r[at + blk:]])
+        else:           # insertion of random bases into the read: the path jumps left
+            r = np.concatenate([r[:at], np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=blk)], r[at:]])
+        parts.append(r)
+    # reads reaching past the contig's end
+    tail = ref[-3000:]
+    parts += [tail[:2500].copy(), tail[200:].copy(), np.concatenate([tail[500:], np.frombuffer(b"ACGT" * 100, np.uint8)])]
+    lens2 = np.array([len(x) for x in parts], dtype=np.int32)
+    offs2 = np.zeros(len(parts), dtype=np.int64)
+    np.cumsum(lens2[:-1], out=offs2[1:])
+    txt2 = np.concatenate(parts)
+    recs = locate_vs_oracle(ctx, oracle, ref, txt2, offs2, lens2, MASKS[0], 0.3)
+    assert recs["found"].sum() > 20
+    rs = ctx.seqset_one(ref)
+    ix = ctx.index(rs, MASKS[0])
+    s = ctx.seqset(txt2, offs2, lens2)
+    job = ctx.locate_run(ix, s, R=0.3)
+    r2 = job.fetch()
+    st = job.stats()
+    for n in recs.dtype.names:
+        assert (r2[n] == recs[n]).all()
+    if os.environ.get("PB_NARROW", "1") != "0":
+        assert st["redone"] > 0 and st["band_cells"] > 0  # both passes ran
+    job.free(); s.free()
+
+
+def test_locate_pipelined_submit_collect(ctx, oracle):
+    """pb_locate_submit / pb_locate_collect (two batches in flight, host text and .bin image) return what pb_locate_batch does"""
+    ref = workload.reference(2, 400_000)
+    rs = ctx.seqset_one(ref)
+    ix = ctx.index(rs, MASKS[0])
+    batches = []
+    for b in range(3):
+        lens = workload.read_lengths(40 + b, 80 + 16 * b, mean=2500.0, sigma_log=0.5, lo=300, hi=8000)
+        batches.append(workload.reads(50 + b, ref, lens))
+    want = [ctx.locate(ix, t, o, l, R=0.3) for t, o, l, _ in batches]
+    steps, got = [], []
+    for b, (t, o, l, _) in enumerate(batches):  # submit k+1 before collecting k
+        if b % 2 == 0:
+            steps.append(ctx.locate_submit(ix, t, o, l, R=0.3))
+        else:
+            steps.append(ctx.locate_submit_bin(ix, workload.pack_bin(t, o, l), R=0.3))
+        if b > 0:
+            got.append(steps[b - 1].collect())
+    got.append(steps[-1].collect())
+    for w, g, st in zip(want, got, steps):
+        assert len(w) == len(g) > 0
+        for n in w.dtype.names:
+            assert (w[n] == g[n]).all(), n
+        assert st.stats["dp_alignments"] > 0
+    # an empty batch and a step that is dropped without being collected
+    assert len(ctx.locate_submit(ix, np.zeros(0, np.uint8), [], [], R=0.3).collect()) == 0
+    ctx.locate_submit(ix, *batches[0][:3], R=0.3).free()
+    assert (ctx.locate(ix, *batches[0][:3], R=0.3)["pos"] == want[0]["pos"]).all()
+
+
 # ---------------------------------------------------------------------------------------------
 # assembler-side trial loop (spaced_seed.cpp:424-436, try_align :261-299)
 # ---------------------------------------------------------------------------------------------

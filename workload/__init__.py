@@ -31,6 +31,8 @@ def _L():
         _lib.pbs_read_lengths.argtypes = [C.c_uint64, C.c_int64, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p]
         _lib.pbs_reads.argtypes = [C.c_uint64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        _lib.pbs_pack_bin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        _lib.pbs_pack_bin.restype = C.c_int64
         _lib.pbs_sweep_pair.argtypes = [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int,
                                         C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
     return _lib
@@ -67,6 +69,19 @@ def reads(seed: int, ref: np.ndarray, lens: np.ndarray, p_ins: float = 0.09, p_d
     _L().pbs_reads(seed, ref.ctypes.data, len(ref), n, lens.ctypes.data, offs.ctypes.data,
                    p_ins, p_del, p_sub, nthreads, out.ctypes.data, starts.ctypes.data)
     return out, offs, lens, starts
+
+
+def pack_bin(text: np.ndarray, offs: np.ndarray, lens: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+    """The batch as a .bin image (binary_test.cpp:55-63): u32 length + ceil(len/4) packed bytes per read."""
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    offs = np.ascontiguousarray(offs, dtype=np.int64)
+    lens = np.ascontiguousarray(lens, dtype=np.int32)
+    n = _L().pbs_pack_bin(text.ctypes.data, offs.ctypes.data, lens.ctypes.data, len(lens), None)
+    if out is None:
+        out = np.empty(n, dtype=np.uint8)
+    assert out.size >= n
+    _L().pbs_pack_bin(text.ctypes.data, offs.ctypes.data, lens.ctypes.data, len(lens), out.ctypes.data)
+    return out[:n]
 
 
 def sweep_pair(seed: int, idx: int, alen: int, band: int, tail: int = 600, nedits: int | None = None):

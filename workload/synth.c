@@ -155,3 +155,33 @@ void pbs_sweep_pair(uint64_t seed, int64_t idx, int alen, int blen, double R, in
     }
     *alen_out = n;
 }
+
+/* A read batch as the .bin image the assembler reads (binary_test.cpp:55-63: per record a native u32 length, then
+ * ceil(len/4) bytes of 4 bases each, first base in bits 7:6, A=0 C=1 G=2 other=3; records back to back).  Returns the
+ * image size; out == NULL only sizes it.  Bench / test INPUT tooling: the product's own packer is pb_text2bin. */
+int64_t pbs_pack_bin(const char *text, const int64_t *offs, const int32_t *lens, int64_t n, uint8_t *out)
+{
+    int64_t p = 0;
+    for (int64_t r = 0; r < n; ++r) {
+        const int32_t l = lens[r];
+        const int64_t body = ((int64_t)l + 3) / 4;
+        if (out) {
+            uint32_t l32 = (uint32_t)l;
+            memcpy(out + p, &l32, 4);
+            const char *t = text + offs[r];
+            uint8_t *o = out + p + 4;
+            for (int64_t b = 0; b < body; ++b) {
+                uint8_t v = 0;
+                for (int k = 0; k < 4; ++k) {
+                    const int64_t i = 4 * b + k;
+                    int c = 0;
+                    if (i < l) { const char ch = t[i]; c = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3; }
+                    v = (uint8_t)((v << 2) | c);
+                }
+                o[b] = v;
+            }
+        }
+        p += 4 + body;
+    }
+    return p;
+}
