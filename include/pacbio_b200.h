@@ -181,6 +181,18 @@ PB_API int pb_align_batch(pb_ctx *ctx, const char *a_text, const int64_t *a_off,
                    const char *b_text, const int64_t *b_off, const int32_t *b_len, const int32_t *b_stride, int64_t n,
                    double R, int maxn, int maxm, pb_align_out *out, uint8_t *ops, const int64_t *ops_off);
 
+/* EXTENSION -- quality-weighted scoring (BASELINE config 3).  The reference has no quality-aware DP: its scoring hooks are
+ * hard-wired to unit costs (seq_aligner.h:136-137) and quality.cpp only prints the mean ASCII code of a line.  This entry
+ * point is seq_aligner::align with those two hooks replaced by per-element table lookups and everything else kept (band,
+ * tie-breaking, early failure, goal cell, coverage test, traceback):
+ *     match(a_i, b_j) = (a_i != b_j) ? a_w[i] : 0      DELETE (a_i skipped) costs a_w[i]      INSERT (b_j skipped) costs b_w[j]
+ * a_w / b_w: one weight (1..4) per byte of a_text / b_text, same offsets.  Forward views only.  The early-failure line is
+ * cost(i,i) > i*R*fail_scale (1 = the reference's).  With all weights 1 and fail_scale 1 the results are pb_align_batch's. */
+PB_API int pb_align_weighted_batch(pb_ctx *ctx, const char *a_text, const uint8_t *a_w, const int64_t *a_off, const int32_t *a_len,
+                                   const char *b_text, const uint8_t *b_w, const int64_t *b_off, const int32_t *b_len, int64_t n,
+                                   double R, double fail_scale, int maxn, int maxm, pb_align_out *out, uint8_t *ops,
+                                   const int64_t *ops_off);
+
 /* ---- the locate loop (locator.cpp:70-92) ----------------------------------------------------- */
 
 typedef struct {

@@ -228,10 +228,29 @@ static int dp_ws_reserve(dp_ws *ws, size_t cells)
 
 static void dp_ws_free(dp_ws *ws) { free(ws->cost); free(ws->par); ws->cost = NULL; ws->par = NULL; ws->cap = 0; }
 
+/* wa / wb == NULL: the reference's unit costs (seq_aligner.h:136-137).  Otherwise the labelled EXTENSION of BASELINE config 3
+ * ("quality-weighted scoring"): the same recurrence with the two scoring hooks replaced by per-element table lookups --
+ * match(a_i, b_j) = (a_i != b_j) ? wa[i] : 0, indel = wa[i] for a DELETE (a_i skipped), wb[j] for an INSERT (b_j skipped) --
+ * and the early-failure line scaled by fail_scale (1 = the reference's cost(i,i) > i*R).  The reference pins no result for it. */
+static int align_ws_w(dp_ws *ws, const char *a, int a_len, int a_stride,
+                      const char *b, int b_len, int b_stride,
+                      const uint8_t *wa, const uint8_t *wb, double fail_scale,
+                      double R, int maxn, int maxm,
+                      pbo_align_out *out, uint8_t *ops, char *vals, size_t cap);
+
 static int align_ws(dp_ws *ws, const char *a, int a_len, int a_stride,
                     const char *b, int b_len, int b_stride,
                     double R, int maxn, int maxm,
                     pbo_align_out *out, uint8_t *ops, char *vals, size_t cap)
+{
+    return align_ws_w(ws, a, a_len, a_stride, b, b_len, b_stride, NULL, NULL, 1.0, R, maxn, maxm, out, ops, vals, cap);
+}
+
+static int align_ws_w(dp_ws *ws, const char *a, int a_len, int a_stride,
+                      const char *b, int b_len, int b_stride,
+                      const uint8_t *wa, const uint8_t *wb, double fail_scale,
+                      double R, int maxn, int maxm,
+                      pbo_align_out *out, uint8_t *ops, char *vals, size_t cap)
 {
     int len_a, len_b, max_dst;
     memset(out, 0, sizeof *out);
@@ -256,28 +275,29 @@ static int align_ws(dp_ws *ws, const char *a, int a_len, int a_stride,
     uint8_t *P = ws->par;
 #define IDX(i, j) ((size_t)(i) * W + (size_t)((j) - (i) + max_dst))
     /* init_cell, seq_aligner.h:139-150 */
-    for (int i = 1; i <= max_dst && i <= len_a; ++i) { C[IDX(i, 0)] = i; P[IDX(i, 0)] = PBO_DELETE; }
-    for (int j = 1; j <= max_dst; ++j) { C[IDX(0, j)] = j; P[IDX(0, j)] = PBO_INSERT; }
     C[IDX(0, 0)] = 0; P[IDX(0, 0)] = 0;
+    for (int i = 1; i <= max_dst && i <= len_a; ++i) { C[IDX(i, 0)] = C[IDX(i - 1, 0)] + (wa ? wa[i - 1] : 1); P[IDX(i, 0)] = PBO_DELETE; }
+    for (int j = 1; j <= max_dst; ++j) { C[IDX(0, j)] = C[IDX(0, j - 1)] + (wb && j <= b_len ? wb[j - 1] : 1); P[IDX(0, j)] = PBO_INSERT; }
 
     /* search, seq_aligner.h:151-190 */
     int64_t cells = 0;
     for (int i = 1; i <= len_a; ++i) {
         char c = a[(ptrdiff_t)(i - 1) * a_stride];
+        const int w_i = wa ? wa[i - 1] : 1; /* weight of a_i: what a mismatch at it or its deletion costs */
         int beg = i - max_dst > 1 ? i - max_dst : 1;
         int end = i + max_dst < len_b ? i + max_dst : len_b;
         for (int j = beg; j <= end; ++j) {
             char d = b[(ptrdiff_t)(j - 1) * b_stride];
-            int t, cost = C[IDX(i - 1, j - 1)] + (c != d);
+            int t, cost = C[IDX(i - 1, j - 1)] + (c != d ? w_i : 0);
             int src = PBO_MATCH;
-            if (i - j < max_dst && (t = C[IDX(i, j - 1)] + 1) < cost) { cost = t; src = PBO_INSERT; }
-            if (j - i < max_dst && (t = C[IDX(i - 1, j)] + 1) < cost) { cost = t; src = PBO_DELETE; }
+            if (i - j < max_dst && (t = C[IDX(i, j - 1)] + (wb ? wb[j - 1] : 1)) < cost) { cost = t; src = PBO_INSERT; }
+            if (j - i < max_dst && (t = C[IDX(i - 1, j)] + w_i) < cost) { cost = t; src = PBO_DELETE; }
             C[IDX(i, j)] = cost;
             P[IDX(i, j)] = (uint8_t)src;
         }
         if (end >= beg) cells += end - beg + 1;
         /* early failure :185 ; cell (i,i) unwritten for i>len_b reads 0 (fresh, Q-D2) */
-        if (i > 10 && i <= len_b && (double)C[IDX(i, i)] > i * R) {
+        if (i > 10 && i <= len_b && (double)C[IDX(i, i)] > i * R * fail_scale) {
             out->fail_row = i;
             out->cells = cells;
             return -1;
@@ -344,6 +364,15 @@ int pbo_align(const char *a, int a_len, int a_stride,
 {
     dp_ws ws = {0, 0, 0};
     int r = align_ws(&ws, a, a_len, a_stride, b, b_len, b_stride, R, maxn, maxm, out, ops, vals, cap);
+    dp_ws_free(&ws);
+    return r;
+}
+
+int pbo_align_weighted(const char *a, int a_len, const uint8_t *wa, const char *b, int b_len, const uint8_t *wb,
+                       double R, double fail_scale, int maxn, int maxm, pbo_align_out *out, uint8_t *ops, size_t cap)
+{
+    dp_ws ws = {0, 0, 0};
+    int r = align_ws_w(&ws, a, a_len, 1, b, b_len, 1, wa, wb, fail_scale, R, maxn, maxm, out, ops, NULL, cap);
     dp_ws_free(&ws);
     return r;
 }

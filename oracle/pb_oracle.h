@@ -97,6 +97,15 @@ int pbo_align(const char *a, int a_len, int a_stride,
               double R, int maxn, int maxm,
               pbo_align_out *out, uint8_t *ops, char *vals, size_t cap);
 
+/* EXTENSION (BASELINE config 3, "quality-weighted scoring"; no counterpart in the reference, whose scoring hooks
+ * seq_aligner.h:136-137 are hard-wired to unit costs and whose quality.cpp is a stand-alone mean-of-ASCII tool): the same
+ * banded recurrence, tie-breaking, goal cell and traceback with the two hooks replaced by per-element table lookups --
+ * match(a_i, b_j) = (a_i != b_j) ? wa[i] : 0; indel = wa[i] when a_i is skipped (DELETE), wb[j] when b_j is skipped
+ * (INSERT) -- weights in 1..4, forward views, and the early-failure line cost(i,i) > i*R*fail_scale.  With all weights 1
+ * and fail_scale 1 it is pbo_align (tests/test_oracle.py checks that), which is what pins it. */
+int pbo_align_weighted(const char *a, int a_len, const uint8_t *wa, const char *b, int b_len, const uint8_t *wb,
+                       double R, double fail_scale, int maxn, int maxm, pbo_align_out *out, uint8_t *ops, size_t cap);
+
 /* ---- locate loop (locator.cpp:70-92) -------------------------------------- */
 
 typedef struct {

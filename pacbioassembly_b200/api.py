@@ -96,6 +96,8 @@ def lib() -> C.CDLL:
         "pb_index_mask": (u32, [vp]),
         "pb_index_find_batch": (C.c_int, [vp, vp, vp, i64, vp, vp, vp, i64]),
         "pb_align_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, C.c_double, C.c_int, C.c_int, vp, vp, vp]),
+        "pb_align_weighted_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, C.c_double, C.c_double, C.c_int, C.c_int,
+                                              vp, vp, vp]),
         "pb_locate_default_params": (None, [P(LocateParams)]),
         "pb_locate_batch": (C.c_int, [vp, vp, vp, i64, vp, vp, vp, i64, P(LocateParams), vp, P(i64), vp, vp]),
         "pb_locate_run": (C.c_int, [vp, vp, vp, i64, vp, P(LocateParams), vp, P(vp)]),
@@ -319,6 +321,32 @@ class Context:
             ops = np.zeros(int(slots.sum()) + 16, dtype=np.uint8)
         self.check(self._L.pb_align_batch(self.h, _ptr(at), _ptr(a_off), _ptr(a_len), _ptr(ast), _ptr(bt), _ptr(b_off),
                                           _ptr(b_len), _ptr(bst), n, R, maxn, maxm, _ptr(out), _ptr(ops), _ptr(ops_off)))
+        if want_ops:
+            return out, [ops[ops_off[i]: ops_off[i] + max(int(out["nedit"][i]), 0)] if out["ret"][i] >= 0 else None
+                         for i in range(n)]
+        return out, None
+
+    def align_weighted_batch(self, a_text, a_w, a_off, a_len, b_text, b_w, b_off, b_len, R: float = 0.3,
+                             fail_scale: float = 1.0, maxn: int = 26000, maxm: int = 6000, want_ops: bool = True):
+        """The quality-weighted EXTENSION (pb_align_weighted_batch): per-element weights 1..4 for a and b, forward views."""
+        at, bt, aw, bw = _u8(a_text), _u8(b_text), _u8(a_w), _u8(b_w)
+        assert len(aw) >= len(at) and len(bw) >= len(bt)
+        a_off = np.ascontiguousarray(a_off, dtype=np.int64)
+        b_off = np.ascontiguousarray(b_off, dtype=np.int64)
+        a_len = np.ascontiguousarray(a_len, dtype=np.int32)
+        b_len = np.ascontiguousarray(b_len, dtype=np.int32)
+        n = len(a_len)
+        out = np.zeros(n, dtype=ALIGN_DTYPE)
+        ops = ops_off = None
+        if want_ops:
+            slots = (a_len.astype(np.int64) + b_len + 1 + 15) & ~15
+            ops_off = np.zeros(n, dtype=np.int64)
+            if n:
+                np.cumsum(slots[:-1], out=ops_off[1:])
+            ops = np.zeros(int(slots.sum()) + 16, dtype=np.uint8)
+        self.check(self._L.pb_align_weighted_batch(self.h, _ptr(at), _ptr(aw), _ptr(a_off), _ptr(a_len), _ptr(bt), _ptr(bw),
+                                                   _ptr(b_off), _ptr(b_len), n, R, fail_scale, maxn, maxm, _ptr(out), _ptr(ops),
+                                                   _ptr(ops_off)))
         if want_ops:
             return out, [ops[ops_off[i]: ops_off[i] + max(int(out["nedit"][i]), 0)] if out["ret"][i] >= 0 else None
                          for i in range(n)]

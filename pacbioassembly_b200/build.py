@@ -16,7 +16,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(HERE, "libpacbio_b200.so")
-SOURCES = ["pb_ctx.cu", "pb_seq.cu", "pb_seed.cu", "pb_align.cu", "pb_locate.cu", "pb_pairs.cu", "pb_cons.cu"]
+SOURCES = ["pb_ctx.cu", "pb_seq.cu", "pb_seed.cu", "pb_align.cu", "pb_alignw.cu", "pb_locate.cu", "pb_pairs.cu", "pb_cons.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 

@@ -81,6 +81,9 @@ class Oracle:
         L.pbo_align.restype = C.c_int
         L.pbo_align.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                 C.POINTER(AlignOut), C.c_void_p, C.c_void_p, C.c_size_t]
+        L.pbo_align_weighted.restype = C.c_int
+        L.pbo_align_weighted.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double,
+                                         C.c_double, C.c_int, C.c_int, C.POINTER(AlignOut), C.c_void_p, C.c_size_t]
         L.pbo_locate.restype = C.c_int64
         L.pbo_locate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                  C.c_uint32, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
@@ -232,6 +235,24 @@ class Oracle:
         if want_ops and out.ret >= 0:
             d["ops"] = ops[: out.nedit].copy()
             d["vals"] = vals[: out.nedit].copy()
+        return d
+
+    def align_weighted(self, a: bytes, wa, b: bytes, wb, R: float = 0.3, fail_scale: float = 1.0, maxn: int = 26000,
+                       maxm: int = 6000):
+        """the quality-weighted EXTENSION (pb_oracle.h): forward views, weights 1..4 per element of a and of b"""
+        abuf = np.frombuffer(a, dtype=np.uint8) if len(a) else np.zeros(1, np.uint8)
+        bbuf = np.frombuffer(b, dtype=np.uint8) if len(b) else np.zeros(1, np.uint8)
+        wa = np.ascontiguousarray(wa, dtype=np.uint8) if len(a) else np.ones(1, np.uint8)
+        wb = np.ascontiguousarray(wb, dtype=np.uint8) if len(b) else np.ones(1, np.uint8)
+        assert len(wa) >= len(a) and len(wb) >= len(b)
+        out = AlignOut()
+        cap = len(a) + len(b) + 8
+        ops = np.zeros(cap, dtype=np.uint8)
+        self.lib.pbo_align_weighted(abuf.ctypes.data, len(a), wa.ctypes.data, bbuf.ctypes.data, len(b), wb.ctypes.data, R,
+                                    fail_scale, maxn, maxm, C.byref(out), ops.ctypes.data, cap)
+        d = out.as_dict()
+        if out.ret >= 0:
+            d["ops"] = ops[: out.nedit].copy()
         return d
 
     def locate(self, ix, ref: np.ndarray, reads: np.ndarray, offs: np.ndarray, lens: np.ndarray, mask: int,

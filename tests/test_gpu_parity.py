@@ -628,6 +628,65 @@ def test_align_narrow_bands_packed(ctx, oracle):
         assert run_batch_vs_oracle(ctx, oracle, [x[0] for x in P], [x[1] for x in P], Rr) == 24
 
 
+def test_config3_sweep_every_point(ctx, oracle):
+    """BASELINE config 3, unit costs: every (length, band) point of the sweep, 32 pairs each, against the oracle with
+    transcripts; every pair of the generator aligns (band == max_dst, edits spaced under the early-failure line)"""
+    for alen in (1000, 2000, 5000, 10000, 19999):
+        for band in (32, 64, 128, 256, 512):
+            P = [workload.sweep_pair(1000 * band + alen, k, alen, band) for k in range(32)]
+            assert run_batch_vs_oracle(ctx, oracle, [x[0] for x in P], [x[1] for x in P], P[0][2]) == 32, (alen, band)
+
+
+def run_weighted_vs_oracle(ctx, oracle, A, WA, B, WB, R, fail_scale, maxn=26000, maxm=6000):
+    a_blob, b_blob = b"".join(A), b"".join(B)
+    wa_blob, wb_blob = np.concatenate(WA), np.concatenate(WB)
+    a_len, b_len = [len(x) for x in A], [len(x) for x in B]
+    a_off, b_off = np.cumsum([0] + a_len[:-1]), np.cumsum([0] + b_len[:-1])
+    recs, ops = ctx.align_weighted_batch(a_blob, wa_blob, a_off, a_len, b_blob, wb_blob, b_off, b_len, R, fail_scale, maxn, maxm)
+    nsucc = 0
+    for i, (a, b) in enumerate(zip(A, B)):
+        w = oracle.align_weighted(a, WA[i], b, WB[i], R, fail_scale, maxn, maxm)
+        for k in ("ret", "len_a", "len_b", "max_dst", "matlen_a", "matlen_b", "cost", "diag_cost", "nedit", "fail_row", "cells"):
+            assert int(recs[k][i]) == w[k], (i, k, int(recs[k][i]), w[k], len(a), len(b))
+        if w["ret"] >= 0:
+            assert (ops[i] == w["ops"]).all(), i
+            nsucc += 1
+    return nsucc, recs, ops
+
+
+def test_align_quality_weighted(ctx, oracle):
+    """the quality-weighted extension (config 3): per-element weights 1..4 through the two scoring hooks, against the
+    extended oracle; with all weights 1 it must reproduce the unit-cost aligner (pb_align_batch) bit for bit"""
+    rng = np.random.default_rng(77)
+    A, B = make_pairs(rng, 160, 700, rates=(0.0, 0.02, 0.08, 0.15))
+    A, B = [a for a, b in zip(A, B) if len(a) and len(b)], [b for a, b in zip(A, B) if len(a) and len(b)]
+    ones_a, ones_b = [np.ones(len(a), np.uint8) for a in A], [np.ones(len(b), np.uint8) for b in B]
+    n1, r1, o1 = run_weighted_vs_oracle(ctx, oracle, A, ones_a, B, ones_b, 0.3, 1.0)
+    assert n1 > 40
+    a_len, b_len = [len(x) for x in A], [len(x) for x in B]
+    ru, ou = ctx.align_batch(b"".join(A), np.cumsum([0] + a_len[:-1]), a_len, b"".join(B), np.cumsum([0] + b_len[:-1]), b_len, 0.3)
+    for k in ru.dtype.names:
+        assert (ru[k] == r1[k]).all(), k
+    for x, y in zip(ou, o1):
+        assert (x is None and y is None) or (x == y).all()
+    WA = [rng.integers(1, 5, size=len(a)).astype(np.uint8) for a in A]
+    WB = [rng.integers(1, 5, size=len(b)).astype(np.uint8) for b in B]
+    for R, fs in ((0.3, 1.0), (0.3, 4.0), (0.1, 2.5), (0.45, 4.0)):
+        n, _, _ = run_weighted_vs_oracle(ctx, oracle, A, WA, B, WB, R, fs)
+        assert n >= 10, (R, fs, n)
+    # multi-word bands and the sweep generator's pairs
+    A, B = make_pairs(rng, 24, 5000, rates=(0.02, 0.1))
+    WA = [rng.integers(1, 5, size=len(a)).astype(np.uint8) for a in A]
+    WB = [rng.integers(1, 5, size=len(b)).astype(np.uint8) for b in B]
+    assert run_weighted_vs_oracle(ctx, oracle, A, WA, B, WB, 0.3, 4.0)[0] > 5
+    for alen, band in ((1000, 32), (5000, 128), (19999, 512)):
+        P = [workload.sweep_pair(1000 * band + alen, k, alen, band) for k in range(8)]
+        A, B = [x[0] for x in P], [x[1] for x in P]
+        WA = [rng.integers(1, 5, size=len(a)).astype(np.uint8) for a in A]
+        WB = [rng.integers(1, 5, size=len(b)).astype(np.uint8) for b in B]
+        assert run_weighted_vs_oracle(ctx, oracle, A, WA, B, WB, P[0][2], 4.0)[0] == 8
+
+
 # ---------------------------------------------------------------------------------------------
 # all-vs-all overlap detection (BASELINE config 5; SURVEY §8 f2): pb_index_build_set + pb_overlap_all_run
 # ---------------------------------------------------------------------------------------------

@@ -418,3 +418,44 @@ def test_golden_assemble(oracle, golden):
         cons, fr, recs = oracle.assemble(ref0, image, g["masks"], weight=g["weight"], quirk=True)
         assert [hashlib.sha1(c).hexdigest() for c in cons] == g["consensus_sha1"] and [len(c) for c in cons] == g["consensus_len"]
         assert fr.tolist() == g["found_round"]
+
+
+def test_weighted_extension_is_pinned_by_unit_weights(oracle):
+    """pbo_align_weighted (the quality-weighted EXTENSION of config 3) with all weights 1 and fail_scale 1 is pbo_align --
+    the function pinned against the compiled reference -- field for field and transcript for transcript; and a weighted
+    cost is what its own transcript adds up to"""
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    nal = 0
+    for case in range(120):
+        n = int(rng.integers(12, 500))
+        a = acgt[rng.integers(0, 4, size=n)]
+        keep = rng.random(n) > 0.05
+        b = a[keep].copy()
+        sub = rng.random(len(b)) < 0.05
+        b[sub] = acgt[rng.integers(0, 4, size=int(sub.sum()))]
+        b = np.concatenate([b, acgt[rng.integers(0, 4, size=int(rng.integers(0, 200)))]])
+        if case % 3 == 0:
+            a, b = b, a
+        a, b = a.tobytes(), b.tobytes()
+        R = float(rng.choice([0.1, 0.3, 0.45]))
+        u = oracle.align(a, b, R)
+        w = oracle.align_weighted(a, np.ones(len(a), np.uint8), b, np.ones(len(b), np.uint8), R, 1.0)
+        for k in ("ret", "len_a", "len_b", "max_dst", "matlen_a", "matlen_b", "cost", "diag_cost", "nedit", "fail_row", "cells"):
+            assert u[k] == w[k], (case, k)
+        if u["ret"] >= 0:
+            assert (u["ops"] == w["ops"]).all()
+            nal += 1
+        wa, wb = rng.integers(1, 5, size=len(a)).astype(np.uint8), rng.integers(1, 5, size=len(b)).astype(np.uint8)
+        q = oracle.align_weighted(a, wa, b, wb, R, 4.0)
+        if q["ret"] >= 0:
+            i = j = cost = 0
+            for op in q["ops"].tolist():
+                if op == 1:
+                    cost += int(wa[i]) if a[i] != b[j] else 0; i += 1; j += 1
+                elif op == 2:
+                    cost += int(wb[j]); j += 1
+                else:
+                    cost += int(wa[i]); i += 1
+            assert (i, j, cost) == (q["matlen_a"], q["matlen_b"], q["cost"])
+    assert nal > 30

@@ -4,8 +4,10 @@
 early-failure line cost(i,i) <= i*R is respected (otherwise the pair aborts after ~11 rows and "GCUPS" means nothing),
 R = (band - 0.5) / len so that max_dst == band.
 
-    python tools/dp_sweep.py [npairs] [--check N]     -> JSON lines + a summary table; --check compares N pairs per
-                                                          point with the CPU oracle (bit-exact, transcripts included)
+    python tools/dp_sweep.py [npairs] [--check N] [--weighted]
+        -> JSON lines + a summary table; --check compares N pairs per point with the CPU oracle (bit-exact, transcripts
+           included); --weighted runs the quality-weighted EXTENSION (pb_align_weighted_batch: per-base weights 1..4 from the
+           PRNG, early-failure line scaled by the largest weight) against the extended oracle instead
 """
 import json
 import os
@@ -25,6 +27,8 @@ from pacbioassembly_b200 import Context  # noqa: E402
 def main():
     npairs = int(sys.argv[1]) if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else 4096
     ncheck = int(sys.argv[sys.argv.index("--check") + 1]) if "--check" in sys.argv else 0
+    weighted = "--weighted" in sys.argv
+    rng = np.random.default_rng(2024)
     ctx = Context(0)
     oracle = None
     if ncheck:
@@ -46,8 +50,15 @@ def main():
             a_off = np.zeros(npairs, dtype=np.int64); np.cumsum(a_len[:-1], out=a_off[1:])
             b_off = np.zeros(npairs, dtype=np.int64); np.cumsum(b_len[:-1], out=b_off[1:])
             best = None
+            if weighted:
+                wa = rng.integers(1, 5, size=len(a_blob)).astype(np.uint8)
+                wb = rng.integers(1, 5, size=len(b_blob)).astype(np.uint8)
             for rep in range(3):
-                recs, ops = ctx.align_batch(a_blob, a_off, a_len, b_blob, b_off, b_len, R, 26000, 6000, want_ops=(rep == 0))
+                if weighted:
+                    recs, ops = ctx.align_weighted_batch(a_blob, wa, a_off, a_len, b_blob, wb, b_off, b_len, R, 4.0, 26000, 6000,
+                                                         want_ops=(rep == 0))
+                else:
+                    recs, ops = ctx.align_batch(a_blob, a_off, a_len, b_blob, b_off, b_len, R, 26000, 6000, want_ops=(rep == 0))
                 t = ctx.timings()
                 if rep == 0:
                     keep_ops = ops
@@ -55,9 +66,13 @@ def main():
             cells = int(recs["cells"].sum())
             ok = int((recs["ret"] >= 0).sum())
             assert (recs["max_dst"] == band).all(), (alen, band, recs["max_dst"][:4])
+            assert ok == npairs, (alen, band, ok)  # every pair of the generator aligns: the GCUPS include the traceback
             checked = 0
             for k in range(min(ncheck, npairs)):
-                w = oracle.align(A[k], B[k], R)
+                if weighted:
+                    w = oracle.align_weighted(A[k], wa[a_off[k]: a_off[k] + a_len[k]], B[k], wb[b_off[k]: b_off[k] + b_len[k]], R, 4.0)
+                else:
+                    w = oracle.align(A[k], B[k], R)
                 for f in ("ret", "matlen_a", "matlen_b", "cost", "diag_cost", "nedit", "fail_row", "cells"):
                     assert int(recs[f][k]) == w[f], (alen, band, k, f)
                 if w["ret"] >= 0:
@@ -68,7 +83,8 @@ def main():
                    "checked_vs_oracle": checked, "gen_s": round(time.time() - t0, 2)}
             rows.append(row)
             print(json.dumps(row), flush=True)
-    print("\nlen \\ band " + "".join(f"{b:>9d}" for b in (32, 64, 128, 256, 512)) + "    (GCUPS, K3 kernel time, unit costs)")
+    print("\nlen \\ band " + "".join(f"{b:>9d}" for b in (32, 64, 128, 256, 512)) + "    (GCUPS, K3 kernel time, "
+          + ("quality-weighted extension" if weighted else "unit costs") + ")")
     for alen in (1000, 2000, 5000, 10000, 19999):
         print(f"{alen:>10d} " + "".join(f"{r['gcups']:9.0f}" for r in rows if r["len"] == alen))
     ctx.close()

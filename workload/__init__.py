@@ -84,8 +84,13 @@ def pack_bin(text: np.ndarray, offs: np.ndarray, lens: np.ndarray, out: np.ndarr
     return out[:n]
 
 
-def sweep_pair(seed: int, idx: int, alen: int, band: int, tail: int = 600, nedits: int | None = None):
-    """One DP-sweep pair (config 3): returns (a bytes, b bytes, R) with max_dst == band for len(a)."""
+def sweep_pair(seed: int, idx: int, alen: int, band: int, tail: int | None = None, nedits: int | None = None):
+    """One DP-sweep pair (config 3): returns (a bytes, b bytes, R) with max_dst == band for len(a).
+    tail = bases of b beyond a's length; the default band // 2 keeps the pair inside align's coverage test
+    matlen_b >= len_b * (1 - R) (seq_aligner.h:114) at every point of the sweep -- with a long tail len_b = len_a + band and
+    narrow bands on long reads (e.g. 5 kbp at band 32) can never pass it."""
+    if tail is None:
+        tail = band // 2
     blen = alen + tail
     a = np.empty(alen + 8, dtype=np.uint8)
     b = np.empty(blen, dtype=np.uint8)
