@@ -256,8 +256,8 @@ def main():
         """the path's only collective: hit/score counters all-reduced, records gathered on rank 0"""
         # records land in rank 0's pinned buffer; stitching them into one numpy array (FinalReduction.records()) is
         # output formatting, not part of the step
-        tot, _ = reducer(recs, want_records=False)
-        return tot
+        reducer(recs, want_records=False, sync=False)  # queued on a side stream; joined by the next call / reducer.finish()
+        return None
 
 
     phase_s = {"seqset": 0.0, "locate_run": 0.0, "fetch": 0.0, "reduction": 0.0, "n": 0}
@@ -334,8 +334,8 @@ def main():
             if collect is not None:
                 collect()
         if drain is not None:
-            out = drain()  # the last step in flight is collected inside the timed region
-        reducer.finish()
+            drain()  # the last step in flight is collected inside the timed region
+        out = reducer.finish()  # the last exchange is joined inside the timed region; the summed counters are the step's result
         e1.record(stream)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")

@@ -104,10 +104,12 @@ def gather_pair_records(recs: np.ndarray, device: torch.device | str = "cpu", ds
 
 
 class FinalReduction:
-    """The path's one exchange, with its buffers allocated once: an all-reduce of the four counters -- the only part a step
-    waits for -- and a gather of every rank's 56-byte records on rank 0 (fixed-size slots of `cap` records behind an 8-byte
-    count), which runs on a side stream under the NEXT step's kernels: `wait()` (called by the next `__call__`, by `records()`
-    and by `finish()`) is where it is joined.  Works over NCCL (device="cuda") or gloo (device="cpu")."""
+    """The path's one exchange, with its buffers allocated once: an all-reduce of the four counters and a gather of every
+    rank's 56-byte records on rank 0 (fixed-size slots of `cap` records behind an 8-byte count).  Both are queued on a side
+    stream and nothing blocks the host: a step's exchange runs under the NEXT step's kernels (a collective's kernel needs a
+    free SM slot, which the aligner's persistent kernels only give up when their band class drains -- waiting for it on the
+    host would stall the pipeline for most of a step).  `wait()` joins the exchange in flight; the next `__call__`, `totals()`,
+    `records()` and `finish()` call it.  sync=True is the blocking form.  NCCL (device="cuda") or gloo (device="cpu")."""
 
     def __init__(self, cap: int, device="cpu", dst: int = 0):
         self.cap, self.device, self.dst = int(cap), device, dst
@@ -119,8 +121,9 @@ class FinalReduction:
         self.d_send = torch.empty(nbytes, dtype=torch.uint8, device=device)
         self.counters = torch.zeros(4, dtype=torch.int64, device=device)
         self.h_counters = torch.zeros(4, dtype=torch.int64, pin_memory=self.cuda)
+        self.h_totals = torch.zeros(4, dtype=torch.int64, pin_memory=self.cuda)
         self.side = torch.cuda.Stream() if self.cuda else None
-        self.pending = None  # (work handle or None, event or None) of the gather in flight
+        self.pending = None  # (work handles, event or None) of the exchange in flight
         self.local = None
         if self.rank == dst and self.world > 1:
             self.d_recv = [torch.empty(nbytes, dtype=torch.uint8, device=device) for _ in range(self.world)]
@@ -129,54 +132,69 @@ class FinalReduction:
             self.d_recv = None
 
     def wait(self):
-        """join the record gather started by the last call (a no-op when none is in flight)"""
+        """join the exchange started by the last call (a no-op when none is in flight)"""
         if self.pending is None:
             return
-        work, ev = self.pending
+        works, ev = self.pending
         self.pending = None
         if ev is not None:
             ev.synchronize()
-        elif work is not None:
-            work.wait()
-            if self.rank == self.dst:
-                nbytes = self.d_send.numel()
-                for r in range(self.world):
-                    self.h_recv[r * nbytes: (r + 1) * nbytes].copy_(self.d_recv[r])
+            return
+        for w in works:
+            w.wait()
+        self.h_totals.copy_(self.counters)
+        if self.rank == self.dst:
+            nbytes = self.d_send.numel()
+            for r in range(self.world):
+                self.h_recv[r * nbytes: (r + 1) * nbytes].copy_(self.d_recv[r])
 
-    finish = wait
+    def finish(self):
+        self.wait()
+        return self.totals()
 
-    def __call__(self, recs: np.ndarray, want_records: bool = True):
-        """returns (summed counters as numpy int64[4], concatenated records on dst or None)"""
-        self.wait()  # the send buffer is reused
+    def totals(self) -> np.ndarray:
+        """counters of the last call summed over the ranks: [mapped reads, sum of costs, reference-equivalent cells, kept reads]"""
+        self.wait()
+        return self.h_totals.numpy().copy()
+
+    def __call__(self, recs: np.ndarray, want_records: bool = True, sync: bool = True):
+        """sync: returns (summed counters as numpy int64[4], concatenated records on dst or None); else (None, None) at once"""
+        self.wait()  # the send buffers are reused
         self.h_counters.numpy()[:] = counters_of(recs)
         if self.world == 1:
             self.local = recs
-            return self.h_counters.numpy().copy(), (recs if want_records else None)
+            self.h_totals.numpy()[:] = self.h_counters.numpy()
+            return self.h_totals.numpy().copy(), (recs if want_records else None)
         n = len(recs)
         assert n <= self.cap
         hs = self.h_send.numpy()
         hs[:8].view(np.int64)[0] = n
         hs[8: 8 + n * LOCATE_DTYPE.itemsize] = recs.view(np.uint8).reshape(-1)
-        # the step's result: four counters, all-reduced
-        self.counters.copy_(self.h_counters, non_blocking=True)
-        dist.all_reduce(self.counters)
-        tot = self.counters.cpu().numpy()
-        # the records follow on a side stream; nothing below blocks the host
         if self.cuda:
             with torch.cuda.stream(self.side):
+                self.counters.copy_(self.h_counters, non_blocking=True)
+                w1 = dist.all_reduce(self.counters, async_op=True)
+                w1.wait()  # orders the side stream behind the collective, does not block the host
+                self.h_totals.copy_(self.counters, non_blocking=True)
                 self.d_send.copy_(self.h_send, non_blocking=True)
-                work = dist.gather(self.d_send, self.d_recv, dst=self.dst, async_op=True)
-                work.wait()  # orders the side stream behind the collective, does not block the host
+                w2 = dist.gather(self.d_send, self.d_recv, dst=self.dst, async_op=True)
+                w2.wait()
                 if self.rank == self.dst:
                     nbytes = self.d_send.numel()
                     for r in range(self.world):
                         self.h_recv[r * nbytes: (r + 1) * nbytes].copy_(self.d_recv[r], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self.side)
-            self.pending = (work, ev)
+            self.pending = ((w1, w2), ev)
         else:
+            self.counters.copy_(self.h_counters)
             self.d_send.copy_(self.h_send)
-            self.pending = (dist.gather(self.d_send, self.d_recv, dst=self.dst, async_op=True), None)
+            w1 = dist.all_reduce(self.counters, async_op=True)
+            w2 = dist.gather(self.d_send, self.d_recv, dst=self.dst, async_op=True)
+            self.pending = ((w1, w2), None)
+        if not sync:
+            return None, None
+        tot = self.totals()
         if not want_records or self.rank != self.dst:
             return tot, None
         return tot, self.records()
