@@ -245,12 +245,11 @@ def main():
     log(f"[rank {rank}] index: {index.nentries} entries, {index.nkeys} keys in {time.time() - t0:.2f}s {index_ms}")
 
     kept = int((lens >= 500).sum())
-    recs_host = torch.empty(kept * LOCATE_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True).numpy().view(LOCATE_DTYPE)
-
     state = {}
     from pacbioassembly_b200 import shard
 
     reducer = shard.FinalReduction(nreads, device="cuda")
+    recs_host = reducer.send_view(kept)  # pinned; the records are fetched straight into the exchange's send buffer
 
     def final_reduction(recs):
         """the path's only collective: hit/score counters all-reduced, records gathered on rank 0"""
@@ -268,6 +267,7 @@ def main():
         t1 = time.perf_counter()
         job = ctx.locate_run(index, s, R=R)
         t2 = time.perf_counter()
+        reducer.wait()  # the previous step's exchange has long finished: its send buffer is this step's record buffer
         recs = job.fetch(recs=recs_host)
         t3 = time.perf_counter()
         t = ctx.timings()
@@ -298,6 +298,7 @@ def main():
         cur = submit_e2e()
         t1 = time.perf_counter()
         if pipe["prev"] is not None:
+            reducer.wait()
             recs = pipe["prev"].collect(recs=recs_host)
             t2 = time.perf_counter()
             state["e2e_timings"] = ctx.timings()
@@ -311,6 +312,7 @@ def main():
 
     def drain_e2e():
         if pipe["prev"] is not None:
+            reducer.wait()
             recs = pipe["prev"].collect(recs=recs_host)
             state["e2e_timings"] = ctx.timings()
             state["e2e_recs"] = recs.copy()

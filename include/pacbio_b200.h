@@ -142,6 +142,11 @@ PB_API int pb_probe_bulk_device(pb_ctx *ctx, const pb_index *ix, const pb_seqset
 
 /* key = encode(ref+i) & mask; if (key) map[key].push_back(i)   (locator.cpp:62-66 / ref_seq.h:291-311) */
 PB_API int pb_index_build(pb_ctx *ctx, const pb_seqset *ref, int64_t seq, uint32_t mask, int policy, pb_index **out);
+/* The seed map filled the way the reference's drivers fill it, one seedmap[key].push_back(pos) at a time (locator.cpp:65,
+ * ref_seq.h:299,307; common.h:54): n (key, position) pairs in insertion order.  pb_index_find_batch returns each key's
+ * positions in that order.  Zero keys are skipped (the drivers never insert one, locator.cpp:64).  Such an index answers
+ * lookups; the batched locate / overlap pipelines want one built by pb_index_build over a resident sequence. */
+PB_API int pb_index_build_pairs(pb_ctx *ctx, const uint32_t *keys, const int32_t *pos, int64_t n, pb_index **out);
 PB_API void pb_index_free(pb_index *ix);
 PB_API int64_t pb_index_nkeys(const pb_index *ix);    /* hash_table::size() */
 PB_API int64_t pb_index_nentries(const pb_index *ix); /* positions stored; get_seedmap's return value is nhead+ntail, see pb_index_nscanned */

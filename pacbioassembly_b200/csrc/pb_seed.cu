@@ -261,7 +261,11 @@ static BucketFn make_bucket_fn(uint32_t mask)
 
 struct EntryMap { // scan order e -> reference position (ref_seq.h:291-311 for REFSEQ; identity for LOCATOR)
     int64_t nhead, len;
-    __host__ __device__ int64_t pos(int64_t e) const { return e < nhead ? e : len - 16 - (e - nhead); }
+    // explicit (key, position) pairs in insertion order (pb_index_build_pairs: the map filled through hash_table::operator[])
+    const uint32_t *xkeys = nullptr;
+    const int32_t *xpos = nullptr;
+    __host__ __device__ int64_t pos(int64_t e) const { return xpos ? (int64_t)xpos[e] : (e < nhead ? e : len - 16 - (e - nhead)); }
+    __device__ uint32_t key(const uint32_t *__restrict__ keys_all, int64_t e) const { return xkeys ? xkeys[e] : keys_all[pos(e)]; }
 };
 
 __global__ void index_count_kernel(const uint32_t *__restrict__ keys_all, EntryMap em, int64_t nscan, BucketFn fn,
@@ -269,7 +273,7 @@ __global__ void index_count_kernel(const uint32_t *__restrict__ keys_all, EntryM
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nscan) return;
-    const uint32_t key = keys_all[em.pos(e)];
+    const uint32_t key = em.key(keys_all, e);
     if (key) atomicAdd(&count[bucket_of(fn, key)], 1u);
 }
 
@@ -278,7 +282,7 @@ __global__ void index_scatter_kernel(const uint32_t *__restrict__ keys_all, Entr
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nscan) return;
-    const uint32_t key = keys_all[em.pos(e)];
+    const uint32_t key = em.key(keys_all, e);
     if (!key) return;
     const uint32_t slot = atomicAdd(&cursor[bucket_of(fn, key)], 1u);
     ent[slot] = (int32_t)e;
@@ -384,9 +388,9 @@ __global__ void index_finalize_kernel(const uint32_t *__restrict__ keys_all, Ent
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nentries) return;
-    const int64_t p = em.pos(ent[i]);
-    ent[i] = (int32_t)p;
-    if (ekey) ekey[i] = keys_all[p];
+    const int64_t e = ent[i];
+    if (ekey) ekey[i] = em.key(keys_all, e);
+    ent[i] = (int32_t)em.pos(e);
 }
 
 __global__ void index_pack_kernel(const uint32_t *__restrict__ start, int64_t nbuckets, int shift, uint32_t esc, uint32_t *__restrict__ pk)
@@ -417,17 +421,25 @@ __global__ void index_nkeys_kernel(const uint32_t *__restrict__ start, int64_t n
 }
 
 // seq >= 0: one sequence under `policy`; seq < 0: every sequence of the set (get_seedmap's head pass per sequence)
-static int index_build_impl(pb_ctx *ctx, const pb_seqset *ref, int64_t seq, uint32_t mask, int policy, pb_index **out)
+// ref == NULL: explicit pairs (d_xkeys / d_xpos, npairs of them, insertion order)
+static int index_build_impl(pb_ctx *ctx, const pb_seqset *ref, int64_t seq, uint32_t mask, int policy, pb_index **out,
+                            const uint32_t *d_xkeys = nullptr, const int32_t *d_xpos = nullptr, int64_t npairs = 0)
 {
     *out = nullptr;
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     pb_timer_reset(ctx);
-    const bool whole_set = seq < 0;
-    const int64_t len = whole_set ? ref->base[ref->n] : ref->len[seq];
+    const bool pairs = ref == nullptr;
+    const bool whole_set = !pairs && seq < 0;
+    const int64_t len = pairs ? npairs : (whole_set ? ref->base[ref->n] : ref->len[seq]);
     EntryMap em;
     em.len = len;
     int64_t nscan;
-    if (whole_set) {
+    if (pairs) {
+        em.nhead = len;
+        em.xkeys = d_xkeys;
+        em.xpos = d_xpos;
+        nscan = len;
+    } else if (whole_set) {
         em.nhead = len; // entries are line positions already
         nscan = len;
     } else if (policy == PB_POLICY_LOCATOR) {
@@ -443,7 +455,7 @@ static int index_build_impl(pb_ctx *ctx, const pb_seqset *ref, int64_t seq, uint
     ix->ctx = ctx;
     ix->mask = mask;
     ix->policy = policy;
-    ix->ref_len = whole_set ? -1 : len;
+    ix->ref_len = (whole_set || pairs) ? -1 : len;
     ix->whole_set = whole_set;
     ix->nscanned = nscan;
     ix->fn = make_bucket_fn(mask);
@@ -452,15 +464,17 @@ static int index_build_impl(pb_ctx *ctx, const pb_seqset *ref, int64_t seq, uint
     int r;
 #define TRYI(x) do { r = (x); if (r != PB_OK) { delete ix; return r; } } while (0)
     DevBuf d_keys, d_count, d_cursor, tmp, d_big, d_nbig, d_nkeys;
-    TRYI(d_keys.alloc(ctx, (size_t)std::max<int64_t>(len, 1) * 4 + 64));
-    pb_timer_begin(ctx, PB_T_SEED);
-    TRYI(pb_seed_bulk_device(ctx, ref, whole_set ? 0 : ref->base[seq], len, mask, d_keys.as<uint32_t>()));
-    pb_timer_end(ctx, PB_T_SEED);
+    if (!pairs) {
+        TRYI(d_keys.alloc(ctx, (size_t)std::max<int64_t>(len, 1) * 4 + 64));
+        pb_timer_begin(ctx, PB_T_SEED);
+        TRYI(pb_seed_bulk_device(ctx, ref, whole_set ? 0 : ref->base[seq], len, mask, d_keys.as<uint32_t>()));
+        pb_timer_end(ctx, PB_T_SEED);
+    }
     pb_timer_begin(ctx, PB_T_INDEX);
     TRYI(d_count.alloc_zero(ctx, (size_t)(nb + 1) * 4));
     TRYI(ix->d_start.alloc(ctx, (size_t)(nb + 2) * 4));
     const unsigned gscan = (unsigned)std::max<int64_t>(1, (nscan + 255) / 256);
-    const unsigned gset = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ref->n, (int64_t)ctx->sm_count * 8));
+    const unsigned gset = (unsigned)std::max<int64_t>(1, std::min<int64_t>(pairs ? 1 : ref->n, (int64_t)ctx->sm_count * 8));
     if (whole_set) {
         int64_t ns = 0;
         for (int64_t i = 0; i < ref->n; ++i) ns += std::max(0, ref->len[i] - 16);
@@ -550,6 +564,23 @@ extern "C" int pb_index_build(pb_ctx *ctx, const pb_seqset *ref, int64_t seq, ui
     if (!ctx || !ref || !out || seq < 0 || seq >= ref->n) return pb_fail(ctx, PB_ERR_ARG, "pb_index_build: bad argument");
     if (policy != PB_POLICY_LOCATOR && policy != PB_POLICY_REFSEQ) return pb_fail(ctx, PB_ERR_ARG, "unknown index policy %d", policy);
     return index_build_impl(ctx, ref, seq, mask, policy, out);
+}
+
+// The seed map as the reference's drivers fill it (locator.cpp:65, ref_seq.h:299,307): seedmap[key].push_back(pos), one pair
+// at a time.  hash_table::operator[] collects the pairs and hands them over here in insertion order; per key the positions
+// come back in that order.  Keys are looked up exactly (hashed buckets + stored key).  A zero key is not stored (the
+// reference never inserts one, locator.cpp:64 -- the host class keeps such an entry itself).
+extern "C" int pb_index_build_pairs(pb_ctx *ctx, const uint32_t *keys, const int32_t *pos, int64_t n, pb_index **out)
+{
+    if (!ctx || !out || n < 0 || (n && (!keys || !pos))) return pb_fail(ctx, PB_ERR_ARG, "pb_index_build_pairs: bad argument");
+    if (n > (int64_t)INT32_MAX) return pb_fail(ctx, PB_ERR_DOMAIN, "too many pairs for one index");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf d_k, d_p;
+    PB_TRY(d_k.alloc(ctx, (size_t)std::max<int64_t>(n, 1) * 4));
+    PB_TRY(d_p.alloc(ctx, (size_t)std::max<int64_t>(n, 1) * 4));
+    PB_TRY(pb_h2d(ctx, d_k.p, keys, (size_t)n * 4));
+    PB_TRY(pb_h2d(ctx, d_p.p, pos, (size_t)n * 4));
+    return index_build_impl(ctx, nullptr, 0, 0xFFFFFFFFu, PB_POLICY_LOCATOR, out, d_k.as<uint32_t>(), d_p.as<int32_t>(), n);
 }
 
 extern "C" int pb_index_build_set(pb_ctx *ctx, const pb_seqset *set, uint32_t mask, pb_index **out)

@@ -16,7 +16,9 @@
 #define MAX_READ_LEN 20000 // common.h:33
 #define MAX_DIFF_LEN 6000  // common.h:35
 #define MAXR 0.3           // common.h:37
-#define OVERLAP_MIN 64     // common.h:39
+#ifndef OVERLAP_MIN
+#define OVERLAP_MIN 64 // common.h:39 (overridable: the reference's test/ref_test.cpp aligns ~45-base strings and predates this value)
+#endif
 
 typedef unsigned t_seed;      // common.h:44
 typedef unsigned char t_bseq; // common.h:49

@@ -69,6 +69,7 @@ inline int RUN_ALL_TESTS()
         delete t;
         ++ran;
         std::printf("[%s] %s\n", ::testing::Registry::failures() == before ? "  OK  " : "FAILED", it.name.c_str());
+        std::fflush(stdout); // a later test may assert() its way out of the process
     }
     std::printf("%d tests, %d failures\n", ran, ::testing::Registry::failures());
     return ::testing::Registry::failures() ? 1 : 0;

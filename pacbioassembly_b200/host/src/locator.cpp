@@ -18,6 +18,7 @@
 
 int main(int argc, char *argv[])
 {
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); // one hardware queue per band-class stream of the aligner (this process is ours)
     if (argc <= 2) {
         fprintf(stderr, "usage: locator contig_file seed [ratio] < seq_file\n");
         return EXIT_FAILURE;
@@ -31,6 +32,9 @@ int main(int argc, char *argv[])
         for (; c != EOF && c != ' ' && c != '\n' && c != '\t' && c != '\r'; c = fgetc(fp)) contig.push_back((char)c);
         fclose(fp);
     }
+    // locator.cpp:56-60, "convert N to A": the loop never advances its pointer, so what it does is turn contig[0] into 'A' when
+    // it is 'N' -- before the seed map is built and before any alignment reads the contig.  Mirrored, not fixed.
+    if (!contig.empty() && contig[0] == 'N') contig[0] = 'A';
     const unsigned mask = pb_parse_pattern(argv[2]); // locator.cpp:51-54
     pb_locate_params prm;
     pb_locate_default_params(&prm);

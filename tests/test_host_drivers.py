@@ -54,6 +54,53 @@ def test_reference_aligner_test_unmodified(tmp_path, golden):
     assert "5 tests, 0 failures" in out  # forward, backward, overlay, remove, sample
 
 
+def test_reference_ref_test_unmodified():
+    """the reference's test/ref_test.cpp against host/include/ref_seq.h + seed_index.h.  As shipped it passes 4 of its 12 tests
+    with the reference's own headers too: the others align 43..52-base strings, which ref_seq::try_align turns away
+    (matlen_a < OVERLAP_MIN = 64, ref_seq.h:265 / common.h:39), and back_insert then trips get_accessor's own
+    assert(contained(pos)) (ref_seq.h:283).  Same outcome here; with OVERLAP_MIN lowered all twelve pass, which drives
+    try_align -> elect -> append / prepend -> evolve through the class interface on the GPU."""
+    r = run("ref_ref_test")
+    out = r.stdout.decode()
+    ok = {ln.split("] ")[1] for ln in out.splitlines() if ln.startswith("[  OK  ]")}
+    failed = {ln.split("] ")[1] for ln in out.splitlines() if ln.startswith("[FAILED]")}
+    assert ok == {"base_vote.basic", "vote_box.basic", "ref_test.basic", "ref_test.grow"}, out + r.stderr.decode()
+    assert {"ref_test.change", "ref_test.remove", "ref_test.insert", "ref_test.insert2"} <= failed and r.returncode != 0
+    r = run("ref_ref_test_ovl8")
+    out = r.stdout.decode()
+    assert r.returncode == 0 and "12 tests, 0 failures" in out, out + r.stderr.decode()
+
+
+def test_reference_locator_unmodified(tmp_path, oracle):
+    """the reference's src/locator.cpp itself -- seedmap[key].push_back(i) loop, seedmap.find, one align() per candidate --
+    compiled against host/include and run on the GPU: TSV identical to the oracle's; the contig starts with 'N', which the
+    driver's "convert N to A" loop turns into 'A' (locator.cpp:57-60 touches contig[0] only)"""
+    ref = workload.reference(71, 60_000)
+    ref[0] = ord("N")
+    lens = workload.read_lengths(72, 40, mean=1200.0, sigma_log=0.4, lo=400, hi=3000)
+    txt, offs, lens, _ = workload.reads(73, ref, lens, 0.02, 0.01, 0.01)
+    txt = txt.copy()
+    txt[offs[0]: offs[0] + 700] = ref[0:700]   # two reads from the contig's very start: their seeds / alignments see contig[0]
+    txt[offs[0]] = ord("A")
+    txt[offs[1]: offs[1] + 600] = ref[0:600]
+    contig = tmp_path / "contig.txt"
+    contig.write_bytes(ref.tobytes() + b"\n")
+    reads_in = b"\n".join(txt[offs[k]: offs[k] + lens[k]].tobytes() for k in range(len(lens))) + b"\n"
+    pattern = "111**111*11*1111"
+    mask = oracle.parse_pattern(pattern.encode())
+    seen = ref.copy()
+    seen[0] = ord("A")  # what the driver maps against
+    ix = oracle.index_build(seen, mask, 0)
+    want = oracle.locate(ix, seen, txt, offs, lens, mask, R=0.15, nthreads=4)
+    oracle.index_free(ix)
+    lines = ["%d\t%d\t%d\t%d\t%d" % (w["nseq"], w["pos"], w["cost"], w["seg_len"], w["diag_cost"]) for w in want if w["found"]]
+    assert len(lines) > 15 and any(w["found"] and w["pos"] == 0 for w in want)
+    for exe in ("ref_locator", "locator"):
+        r = run(exe, stdin=reads_in, args=[str(contig), pattern])
+        assert r.returncode == 0, r.stderr.decode()
+        assert r.stdout.decode().splitlines() == lines, exe
+
+
 def test_locator_cli_matches_oracle(tmp_path, oracle):
     """locator contig_file pattern [R] < reads  ->  TSV identical to the reference driver's (locator.cpp:84-86)"""
     ref = workload.reference(61, 150_000)
