@@ -555,6 +555,29 @@ def test_locate_pipelined_submit_collect(ctx, oracle):
     assert (ctx.locate(ix, *batches[0][:3], R=0.3)["pos"] == want[0]["pos"]).all()
 
 
+def test_locate_config4_reference_size(ctx, oracle):
+    """BASELINE config 4 at its reference size, fewer reads: 64 Mbp reference (seed 4), weight-11 mask (~15 random candidates
+    per probe, hundreds of failing alignments per read before the true locus), CLR reads (seed 5), R = 0.3 -- index and
+    every record field incl. candidate and cell counts against the oracle"""
+    ref = workload.reference(4, 64_000_000)
+    lens = workload.read_lengths(5, 320, mean=5000.0, sigma_log=0.5, lo=500, hi=19999)
+    txt, offs, lens, starts = workload.reads(5, ref, lens)
+    mask = MASKS[2]
+    rs = ctx.seqset_one(ref)
+    ix = ctx.index(rs, mask)
+    oix = oracle.index_build(ref, mask, 0)
+    assert oracle.index_stats(oix) == (ix.nkeys, ix.nentries)
+    recs = ctx.locate(ix, txt, offs, lens, R=0.3)
+    want = oracle.locate(oix, ref, txt, offs, lens, mask, R=0.3, nthreads=min(os.cpu_count() or 1, 32))
+    oracle.index_free(oix)
+    for n in ("found", "j", "pos", "cost", "seg_len", "diag_cost", "matlen_a", "matlen_b", "nedit", "ncand", "cells"):
+        assert (recs[n] == want[n]).all(), n
+    f = recs["found"] == 1
+    assert f.sum() > 150 and want["ncand"].mean() > 100
+    assert (np.abs(recs["pos"][f].astype(np.int64) - recs["j"][f] - starts[f]) < 0.35 * lens[f]).mean() > 0.99
+    ix.free(); rs.free()
+
+
 # ---------------------------------------------------------------------------------------------
 # assembler-side trial loop (spaced_seed.cpp:424-436, try_align :261-299)
 # ---------------------------------------------------------------------------------------------
@@ -752,6 +775,41 @@ def test_allpairs_clr_reads(ctx, oracle):
     o = cpu_libs.oracle()
     image2 = b"".join(o.text2bin(t) for t in texts2)
     assert check_allpairs(ctx, oracle, texts2, image2, MASKS[1]) > 5
+
+
+def test_allpairs_config5_set_size(ctx, oracle):
+    """BASELINE config 5 at its set size: 50 000 CLR reads of a 4.6 Mbp genome (~54x), whole-set index, all-vs-all over a
+    slice of the query reads; sampled target reads are recomputed by the oracle the reference's way (one seed map and one
+    trial loop over the queries per target, spaced_seed.cpp:424-436) and every pair's fields must agree"""
+    nreads, nq = 50_000, 4000
+    g = workload.reference(2, 4_600_000)
+    lens = workload.read_lengths(3, nreads, mean=5000.0, sigma_log=0.5, lo=520, hi=19999)
+    txt, offs, lens, starts = workload.reads(3, g, lens)
+    mask = MASKS[0]
+    rs = ctx.seqset(txt, offs, lens)
+    ix = ctx.index_set(rs, mask)
+    recs, stats = ctx.overlap_all(ix, 0, nq, found_only=True, R=0.3)
+    assert stats["pairs_found"] == len(recs) > 10_000
+    image = b"".join(oracle.text2bin(txt[offs[k]: offs[k] + lens[k]].tobytes()) for k in range(nq))
+    by_target = {}
+    for r in recs:
+        by_target.setdefault(int(r["ref_id"]), {})[int(r["read_id"])] = r
+    targets = [t for t in sorted(by_target, key=lambda t: -len(by_target[t]))[:2]] + [17, 25_000, 49_999]
+    checked = 0
+    for t in targets:
+        tt = txt[offs[t]: offs[t] + lens[t]]
+        oix = oracle.index_build(tt, mask, policy=1)
+        want = oracle.overlap(oix, tt, image, mask, R=0.3, quirk=False, nthreads=min(os.cpu_count() or 1, 32))
+        oracle.index_free(oix)
+        wf = {int(q): want[q] for q in np.nonzero(want["found"] == 1)[0] if q != t}
+        got = by_target.get(t, {})
+        assert sorted(got) == sorted(wf), (t, sorted(set(got) ^ set(wf))[:10])
+        for q, w in wf.items():
+            for f in ("j", "ref_pos", "cost", "read_pos", "dir", "matlen_a", "matlen_b", "nedit", "ncand", "cells"):
+                assert int(got[q][f]) == int(w[f]), (t, q, f, int(got[q][f]), int(w[f]))
+        checked += len(wf)
+    assert checked > 20
+    ix.free(); rs.free()
 
 
 def test_allpairs_errors(ctx):
