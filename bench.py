@@ -360,7 +360,7 @@ def main():
     ms_dev, tot_dev, launches = timed(step_device, args.warmup, args.steps, collect)
     log(f"[rank {rank}] host wall per timed device-leg step (ms): " + ", ".join(f"{k} {1e3 * v / max(phase_s['n'], 1):.1f}" for k, v in phase_s.items() if k != "n") + "\n")
     state["recs"] = state["recs"].copy()  # the device leg's records (recs_host is reused by the e2e legs)
-    ms_e2e, tot_e2e, _ = timed(step_e2e, max(1, min(args.warmup, 2)), args.steps, drain=drain_e2e)
+    ms_e2e, tot_e2e, _ = timed(step_e2e, max(3, args.warmup), args.steps, drain=drain_e2e)
     log(f"[rank {rank}] host wall per e2e step (ms): " + ", ".join(f"{k} {1e3 * v / max(e2e_host['n'], 1):.1f}" for k, v in e2e_host.items() if k != "n"))
     e2e_same = bool((state["e2e_recs"] == state["recs"]).all()) if "e2e_recs" in state else None
     e2e_stage = state.get("e2e_timings")
@@ -372,7 +372,7 @@ def main():
         bin_image["buf"] = torch.empty(len(img), dtype=torch.uint8, pin_memory=True).numpy()
         bin_image["buf"][:] = img
         pipe["mode"] = "bin"
-        ms_bin, tot_bin, _ = timed(step_e2e, 1, args.steps, drain=drain_e2e)
+        ms_bin, tot_bin, _ = timed(step_e2e, 2, args.steps, drain=drain_e2e)
         bin_same = bool((state["e2e_recs"] == state["recs"]).all())
     except Exception as e:
         log(f"[rank {rank}] .bin e2e leg skipped: {e}")

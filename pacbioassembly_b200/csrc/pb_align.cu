@@ -1320,7 +1320,17 @@ static inline bool key_narrow(int key) { return key >= 3000; }
 
 // The strip class of an item whose widest band is D: the smallest S whose strip reaches the wanted goal-side width on the side(s)
 // the item's candidates can have their goal on; -1: run the full band only (tiny bands, or no gain).
+static int narrow_class_for_band_uncached(int D, int g256, bool both_sides);
 static int narrow_class_for_band(int D, int g256, bool both_sides)
+{ // called once per read and step: memoised per band half-width (g256 is fixed for the life of the process)
+    static thread_local std::vector<int> memo[2];
+    std::vector<int> &m = memo[both_sides ? 1 : 0];
+    if (D < 0 || D > (1 << 16)) return narrow_class_for_band_uncached(D, g256, both_sides);
+    if ((size_t)D >= m.size()) m.resize((size_t)D + 1024, INT_MIN);
+    if (m[D] == INT_MIN) m[D] = narrow_class_for_band_uncached(D, g256, both_sides);
+    return m[D];
+}
+static int narrow_class_for_band_uncached(int D, int g256, bool both_sides)
 {
     const int full = class_for_band_plain(D);
     for (int S : kNarrowClasses) {
@@ -1442,9 +1452,28 @@ static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, int locate, si
     g->slot_words = g->par_words + ops_bytes / 4;
     const void *fn = kernel_ptr(key, locate);
     if (g->smem_bytes > 200 * 1024) return pb_fail(ctx, PB_ERR_DOMAIN, "sequence of %d rows needs %zu bytes of shared memory per CTA", cp.max_rows, g->smem_bytes);
-    PB_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes));
     int occ = 0;
-    PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, g->wpb * 32, g->smem_bytes));
+    { // the attribute and the occupancy query cost ~20 us each and are asked for every class of every step: remembered per
+      // (kernel, warps per CTA, shared memory); the attribute only ever needs raising
+        struct Key {
+            const void *fn; int dev, wpb; size_t smem;
+            bool operator<(const Key &o) const
+            { return fn != o.fn ? fn < o.fn : (dev != o.dev ? dev < o.dev : (wpb != o.wpb ? wpb < o.wpb : smem < o.smem)); }
+        };
+        static thread_local std::map<Key, int> occ_memo;
+        static thread_local std::map<std::pair<const void *, int>, size_t> smem_set;
+        const Key key = {fn, ctx->device, g->wpb, g->smem_bytes};
+        auto it = occ_memo.find(key);
+        if (it == occ_memo.end()) {
+            size_t &have = smem_set[std::make_pair(fn, ctx->device)];
+            if (g->smem_bytes > have) {
+                PB_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes));
+                have = g->smem_bytes;
+            }
+            PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, g->wpb * 32, g->smem_bytes));
+            occ_memo[key] = occ;
+        } else occ = it->second;
+    }
     if (occ < 1) occ = 1;
     int64_t blocks = (int64_t)occ * ctx->sm_count;
     const int64_t per_cta = (int64_t)g->wpb * g->groups; // alignments in flight per CTA
@@ -1614,13 +1643,27 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, int locate,
     return PB_OK;
 }
 
-int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_t nkept,
-                    const std::vector<int32_t> &kept_lens, const std::vector<uint8_t> &kept_irr, double R, int maxn, int maxm,
-                    const uint8_t *d_survive, const int32_t *d_rej_cells, pb_locate_rec *d_recs, uint8_t *d_ops,
-                    const int64_t *d_ops_off, unsigned long long *d_stats)
+// The host-side plan of a locate step: which band class every item runs in, in both passes.  It depends on the read lengths
+// only, so the pipelined entry points build it (pb_align_locate_prepare) before they wait for the previous step's kernels, and
+// the planning -- ~2 ms for 100 k reads -- no longer sits between the prefix filter and the aligner with the GPU idle.
+struct LocatePlan {
+    std::vector<int32_t> lens;
+    double R = 0;
+    int maxn = 0, maxm = 0, mode = 0;
+    bool any_irr = false;
+    std::map<int, ClassPlan> plans, narrow_plans;
+    int64_t n_narrow = 0;
+    int g256 = 205;
+};
+
+static int build_locate_plan(pb_ctx *ctx, const std::vector<int32_t> &kept_lens, const std::vector<uint8_t> *kept_irr, double R,
+                             int maxn, int maxm, int mode, LocatePlan *lp)
 {
-    if (nkept == 0) return PB_OK;
-    std::map<int, ClassPlan> plans;
+    const int64_t nkept = (int64_t)kept_lens.size();
+    lp->lens = kept_lens;
+    lp->R = R; lp->maxn = maxn; lp->maxm = maxm; lp->mode = mode;
+    lp->any_irr = false;
+    lp->plans.clear(); lp->narrow_plans.clear(); lp->n_narrow = 0;
     // longest first, ties in input order: a counting sort (all-vs-all batches hold millions of items)
     std::vector<int32_t> order((size_t)nkept);
     {
@@ -1637,34 +1680,84 @@ int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_
     // second pass is planned for the items that are its own plus a small allowance.  PB_NARROW=0 runs the full band only.
     static const bool narrow_on = !(getenv("PB_NARROW") && atoi(getenv("PB_NARROW")) == 0);
     static const int g256 = getenv("PB_NARROW_G") ? std::max(128, std::min(256, (int)(atof(getenv("PB_NARROW_G")) * 256.0))) : 205;
-    std::map<int, ClassPlan> narrow_plans;
-    const bool both_sides = lv.mode != PB_MODE_LOCATE;
-    int64_t n_narrow = 0;
+    lp->g256 = g256;
+    const bool both_sides = mode != PB_MODE_LOCATE;
+    // the class of an item is a function of its length (and of the rare non-ACGT flag): looked up once per distinct length
+    struct PerLen { int cls = INT_MIN, ncls = -1, D = 0, rows = 0; double w_full = 0, w_narrow = 0; };
+    std::vector<PerLen> by_len[2];
     for (int32_t k : order) {
         const int L = kept_lens[k];
-        // widest band / longest seg_a any candidate of this read can reach the DP with: len_a <= L, and the domain
-        // check (seq_aligner.h:104) turns away len_a >= maxn or max_dst >= maxm before any row is computed
-        const int D = std::min(1 + (int)(L * R), maxm - 1);
-        const int cls = class_for_band(std::max(D, 1), kept_irr[k] != 0); // reads (or a contig) with non-ACGT bytes: byte-exact variant
-        if (cls < 0) return pb_fail(ctx, PB_ERR_DOMAIN, "band half-width %d exceeds PB_MAX_BAND", D);
-        // rows = len_a: the read itself (locator), or the reference view cut to len_b + max_dst (overlap, seq_aligner.h:100)
-        const int rows = std::min(lv.mode == PB_MODE_LOCATE ? L : L + D, std::max(maxn - 1, 1));
-        const int ncls = (narrow_on && !kept_irr[k]) ? narrow_class_for_band(D, g256, both_sides) : -1;
-        ClassPlan &cp = plans[cls];
+        const int irr = kept_irr && (*kept_irr)[k] ? 1 : 0;
+        lp->any_irr = lp->any_irr || irr;
+        std::vector<PerLen> &tab = by_len[irr];
+        if ((size_t)L >= tab.size()) tab.resize((size_t)L + 1);
+        PerLen &pl = tab[L];
+        if (pl.cls == INT_MIN) {
+            // widest band / longest seg_a any candidate of this read can reach the DP with: len_a <= L, and the domain
+            // check (seq_aligner.h:104) turns away len_a >= maxn or max_dst >= maxm before any row is computed
+            pl.D = std::min(1 + (int)(L * R), maxm - 1);
+            pl.cls = class_for_band(std::max(pl.D, 1), irr != 0); // non-ACGT bytes in the read (or the contig): byte-exact variant
+            if (pl.cls < 0) return pb_fail(ctx, PB_ERR_DOMAIN, "band half-width %d exceeds PB_MAX_BAND", pl.D);
+            // rows = len_a: the read itself (locator), or the reference view cut to len_b + max_dst (overlap, seq_aligner.h:100)
+            pl.rows = std::min(mode == PB_MODE_LOCATE ? L : L + pl.D, std::max(maxn - 1, 1));
+            pl.ncls = (narrow_on && !irr) ? narrow_class_for_band(pl.D, g256, both_sides) : -1;
+            // ~instructions: rows x (per-word + per-row cost); an item of the first pass comes back only when it could not be certified
+            pl.w_full = (double)L * (30.0 * key_S(pl.cls) + 60.0) * (pl.ncls < 0 ? 1.0 : 0.02);
+            pl.w_narrow = pl.ncls < 0 ? 0.0 : (double)L * (16.0 * key_S(pl.ncls) + 40.0);
+        }
+        ClassPlan &cp = lp->plans[pl.cls];
         cp.items.push_back(k);
-        cp.max_rows = std::max(cp.max_rows, rows);
-        cp.max_D = std::max(cp.max_D, D);
-        // ~instructions: rows x (per-word + per-row cost); an item of the first pass comes back only when it could not be certified
-        cp.work += (double)L * (30.0 * key_S(cls) + 60.0) * (ncls < 0 ? 1.0 : 0.02);
-        if (ncls >= 0) {
-            ClassPlan &np = narrow_plans[ncls];
+        cp.max_rows = std::max(cp.max_rows, pl.rows);
+        cp.max_D = std::max(cp.max_D, pl.D);
+        cp.work += pl.w_full;
+        if (pl.ncls >= 0) {
+            ClassPlan &np = lp->narrow_plans[pl.ncls];
             np.items.push_back(k);
-            np.max_rows = std::max(np.max_rows, rows);
-            np.max_D = std::max(np.max_D, D);
-            np.work += (double)L * (16.0 * key_S(ncls) + 40.0);
-            ++n_narrow;
+            np.max_rows = std::max(np.max_rows, pl.rows);
+            np.max_D = std::max(np.max_D, pl.D);
+            np.work += pl.w_narrow;
+            ++lp->n_narrow;
         }
     }
+    return PB_OK;
+}
+
+void pb_locate_plan_free(LocatePlan *lp) { delete lp; }
+
+// Pipelined callers: plan the step from the kept reads' lengths before anything of it is queued (no non-ACGT reads assumed;
+// a batch that turns out to hold some is planned again when it arrives).
+int pb_align_locate_prepare(pb_ctx *ctx, const std::vector<int32_t> &kept_lens, double R, int maxn, int maxm, int mode)
+{
+    LocatePlan *lp = new LocatePlan();
+    int r = build_locate_plan(ctx, kept_lens, nullptr, R, maxn, maxm, mode, lp);
+    if (r != PB_OK) { delete lp; return r; }
+    if (ctx->planned) delete ctx->planned;
+    ctx->planned = lp;
+    return PB_OK;
+}
+
+int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_t nkept,
+                    const std::vector<int32_t> &kept_lens, const std::vector<uint8_t> &kept_irr, double R, int maxn, int maxm,
+                    const uint8_t *d_survive, const int32_t *d_rej_cells, pb_locate_rec *d_recs, uint8_t *d_ops,
+                    const int64_t *d_ops_off, unsigned long long *d_stats)
+{
+    if (nkept == 0) return PB_OK;
+    LocatePlan local, *lp = nullptr;
+    if (ctx->planned) { // a plan made ahead of time: valid if it was made for exactly these items
+        LocatePlan *pp = ctx->planned;
+        bool irr = false;
+        for (uint8_t f : kept_irr) irr = irr || f;
+        if (!irr && pp->R == R && pp->maxn == maxn && pp->maxm == maxm && pp->mode == lv.mode && pp->lens.size() == kept_lens.size() &&
+            memcmp(pp->lens.data(), kept_lens.data(), kept_lens.size() * sizeof(int32_t)) == 0)
+            lp = pp;
+    }
+    if (!lp) {
+        PB_TRY(build_locate_plan(ctx, kept_lens, &kept_irr, R, maxn, maxm, lv.mode, &local));
+        lp = &local;
+    }
+    std::map<int, ClassPlan> &plans = lp->plans, &narrow_plans = lp->narrow_plans;
+    const int64_t n_narrow = lp->n_narrow;
+    const int g256 = lp->g256;
     AlignLaunch base;
     memset(&base, 0, sizeof base);
     {

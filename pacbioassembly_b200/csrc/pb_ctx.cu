@@ -126,6 +126,7 @@ extern "C" void pb_ctx_destroy(pb_ctx *ctx)
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+    if (ctx->planned) pb_locate_plan_free(ctx->planned);
     cudaGetLastError();
     delete ctx;
 }

@@ -15,8 +15,12 @@
 // context
 // ---------------------------------------------------------------------------------------------
 
+struct LocatePlan; // pb_align.cu: the host-side plan of a locate step (band class of every item)
+void pb_locate_plan_free(LocatePlan *lp);
+
 struct pb_ctx {
     int device = 0;
+    LocatePlan *planned = nullptr; // made ahead of the step by the pipelined entry points (pb_align_locate_prepare)
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr; // host<->device copies of the pipelined entry points (pb_locate_submit / _collect)
     cudaMemPool_t pool = nullptr;       // private pool behind DevBuf (bounded release threshold)
@@ -231,6 +235,7 @@ int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_
                     const uint8_t *d_survive,
                     const int32_t *d_rej_cells, pb_locate_rec *d_recs, uint8_t *d_ops, const int64_t *d_ops_off,
                     unsigned long long *d_stats);
+int pb_align_locate_prepare(pb_ctx *ctx, const std::vector<int32_t> &kept_lens, double R, int maxn, int maxm, int mode);
 int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t n, double R, int maxn, int maxm,
                    pb_align_out *d_out, uint8_t *d_ops, const int64_t *d_ops_off);
 

@@ -1,8 +1,26 @@
 // pb_locate.cu -- the locate loop (locator.cpp:70-92) and the batched align entry point, as pipelines over
 // K1 (seeds) -> K2 (probe/gather) -> K3a (prefix filter) -> K3 (banded aligner, first success in list order).
 #include <algorithm>
+#include <chrono>
 
 #include "pb_internal.cuh"
+
+// PB_HOST_TRACE=1: host wall time of the phases of pb_locate_run on stderr (where the GPU waits for the host)
+struct HostTrace {
+    bool on = getenv("PB_HOST_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    std::string line;
+    void mark(const char *what)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        char buf[64];
+        snprintf(buf, sizeof buf, " %s %.2f", what, std::chrono::duration<double, std::milli>(now - t).count());
+        line += buf;
+        t = now;
+    }
+    ~HostTrace() { if (on) fprintf(stderr, "[pb_host_trace] pb_locate_run (ms):%s\n", line.c_str()); }
+};
 
 extern "C" void pb_locate_default_params(pb_locate_params *p)
 {
@@ -114,6 +132,7 @@ extern "C" int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *r
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     PB_TRY(check_tables(ctx, reads, "read"));
 
+    HostTrace ht;
     pb_locate_job *job = new pb_locate_job();
     job->ctx = ctx;
     job->want_ops = prm->want_ops;
@@ -157,9 +176,11 @@ extern "C" int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *r
         TRYJ(d_ops_off.alloc(ctx, (size_t)nkept * 8));
         TRYJ(pb_h2d(ctx, d_ops_off.p, job->ops_off.data(), (size_t)nkept * 8));
     }
+    ht.mark("kept");
     ProbeOut po;
     TRYJ(pb_locate_seed_probe(ctx, ix, reads, d_kept.as<int32_t>(), nkept, prm->ntrial, &po));
     job->ncand = po.ncand;
+    ht.mark("seed+probe(sync)");
     TRYJ(job->d_votes.alloc(ctx, (size_t)nkept * 4));
     TRYJ(job->d_best_diag.alloc(ctx, (size_t)nkept * 4));
     TRYJ(pb_vote(ctx, &po, nkept, prm->ntrial, job->d_votes.as<int32_t>(), job->d_best_diag.as<int32_t>()));
@@ -179,11 +200,13 @@ extern "C" int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *r
     pb_timer_begin(ctx, PB_T_PREFILTER);
     TRYJ(pb_prefilter(ctx, ss, lv, po.ncand, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(), d_rej.as<int32_t>()));
     pb_timer_end(ctx, PB_T_PREFILTER);
+    ht.mark("vote+prefilter");
     pb_timer_begin(ctx, PB_T_ALIGN);
     TRYJ(pb_align_locate(ctx, ss, lv, nkept, kept_lens, kept_irr, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(),
                          d_rej.as<int32_t>(), job->d_recs.as<pb_locate_rec>(), prm->want_ops ? job->d_ops.as<uint8_t>() : nullptr,
                          prm->want_ops ? d_ops_off.as<int64_t>() : nullptr, job->d_stats.as<unsigned long long>()));
     pb_timer_end(ctx, PB_T_ALIGN);
+    ht.mark("align(plan+launch)");
 #undef TRYJ
     *out = job;
     return PB_OK;
@@ -314,6 +337,12 @@ static int submit_common(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, 
     };
     cu(cudaEventCreateWithFlags(&st->done, cudaEventDisableTiming), "event");
     for (int i = 0; i < 2 * PB_T_COUNT && r == PB_OK; ++i) cu(cudaEventCreate(&st->ev[i]), "event");
+    if (r == PB_OK) { // plan the aligner's band classes now, while the previous step still runs (they depend on the lengths only)
+        std::vector<int32_t> kept_lens;
+        for (int64_t i = 0; i < n; ++i)
+            if (len[i] >= prm->minlen) kept_lens.push_back(len[i]);
+        if (!kept_lens.empty()) r = pb_align_locate_prepare(ctx, kept_lens, prm->R, prm->maxn, prm->maxm, PB_MODE_LOCATE);
+    }
     // the batch lands in one of the context's two staging buffers (no allocation on the pipelined path)
     const int slot = ctx->stage_next;
     ctx->stage_next ^= 1;

@@ -665,7 +665,9 @@ __global__ void probe_gather_tail_kernel(IndexView iv, const uint32_t *__restric
 // from HBM, then two dependent random reads of the bucket table, with nothing else in flight.  Here a thread loads four
 // consecutive keys as one uint4 and issues the eight bucket-header loads back to back before it uses any of them, so four times
 // as many random reads are in flight per resident thread; counts leave as one uint4 store.
-template <int V> // V uint4 groups (4*V queries) per thread
+// CS: keys and counts are streams that pass through once -- loaded / stored evict-first (ld.global.cs / st.global.cs) so that
+// they do not push the bucket table, which every probe hits at random, out of L2
+template <int V, bool CS> // V uint4 groups (4*V queries) per thread
 __global__ void __launch_bounds__(256)
 probe_count4_kernel(IndexView iv, const uint4 *__restrict__ keys4, int64_t nq4, uint4 *__restrict__ cnt4)
 {
@@ -674,7 +676,7 @@ probe_count4_kernel(IndexView iv, const uint4 *__restrict__ keys4, int64_t nq4, 
     uint32_t k[4 * V], s[4 * V], e[4 * V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        const uint4 x = keys4[min(g0 + v, nq4 - 1)];
+        const uint4 x = CS ? __ldcs(keys4 + min(g0 + v, nq4 - 1)) : keys4[min(g0 + v, nq4 - 1)];
         k[4 * v] = x.x; k[4 * v + 1] = x.y; k[4 * v + 2] = x.z; k[4 * v + 3] = x.w;
     }
     if (iv.pk) { // one random read per query: start and (capped) count in one word
@@ -705,10 +707,11 @@ probe_count4_kernel(IndexView iv, const uint4 *__restrict__ keys4, int64_t nq4, 
         c.y = k[4 * v + 1] ? e[4 * v + 1] : 0u;
         c.z = k[4 * v + 2] ? e[4 * v + 2] : 0u;
         c.w = k[4 * v + 3] ? e[4 * v + 3] : 0u;
-        cnt4[g0 + v] = c;
+        if (CS) __stcs(cnt4 + g0 + v, c); else cnt4[g0 + v] = c;
     }
 }
 
+template <bool CS> // CS: offsets, keys and the candidate arrays are streams (evict-first), see probe_count4_kernel
 __global__ void __launch_bounds__(256)
 probe_gather4_kernel(IndexView iv, const uint4 *__restrict__ keys4, int64_t nq4, const int64_t *__restrict__ qoff,
                      int32_t *__restrict__ cand_pos, int32_t *__restrict__ cand_q)
@@ -718,9 +721,9 @@ probe_gather4_kernel(IndexView iv, const uint4 *__restrict__ keys4, int64_t nq4,
     const int64_t q = q4 * 4;
     int64_t o[5];
 #pragma unroll
-    for (int t = 0; t < 5; ++t) o[t] = qoff[q + t];
+    for (int t = 0; t < 5; ++t) o[t] = CS ? __ldcs(qoff + q + t) : qoff[q + t];
     if (o[4] == o[0]) return; // none of the four has a candidate
-    const uint4 k4 = keys4[q4];
+    const uint4 k4 = CS ? __ldcs(keys4 + q4) : keys4[q4];
     const uint32_t k[4] = {k4.x, k4.y, k4.z, k4.w};
     uint32_t s[4];
 #pragma unroll
@@ -733,8 +736,8 @@ probe_gather4_kernel(IndexView iv, const uint4 *__restrict__ keys4, int64_t nq4,
     for (int t = 0; t < 4; ++t) {
         const int64_t n = o[t + 1] - o[t];
         if (n <= 0) continue;
-        cand_pos[o[t]] = first[t];
-        cand_q[o[t]] = (int32_t)(q + t);
+        if (CS) { __stcs(cand_pos + o[t], first[t]); __stcs(cand_q + o[t], (int32_t)(q + t)); }
+        else { cand_pos[o[t]] = first[t]; cand_q[o[t]] = (int32_t)(q + t); }
         for (int64_t i = 1; i < n; ++i) {
             cand_pos[o[t] + i] = __ldg(iv.pos + s[t] + i);
             cand_q[o[t] + i] = (int32_t)(q + t);
@@ -869,13 +872,17 @@ static int launch_probe_count(pb_ctx *ctx, const IndexView &iv, const uint32_t *
         const int64_t nq4 = nq / 4;
         const char *pv = getenv("PB_PROBE_V");
         const int V = pv ? atoi(pv) : 2;
+        const bool cs = !(getenv("PB_PROBE_CS") && atoi(getenv("PB_PROBE_CS")) == 0);
+        const uint4 *k4 = reinterpret_cast<const uint4 *>(d_keys);
+        uint4 *c4 = reinterpret_cast<uint4 *>(d_cnt);
         if (V >= 2) {
-            const int64_t nthr = (nq4 + 1) / 2;
-            probe_count4_kernel<2><<<(unsigned)((nthr + 255) / 256), 256, 0, ctx->stream>>>(iv, reinterpret_cast<const uint4 *>(d_keys), nq4,
-                                                                                        reinterpret_cast<uint4 *>(d_cnt));
+            const unsigned g = (unsigned)(((nq4 + 1) / 2 + 255) / 256);
+            if (cs) probe_count4_kernel<2, true><<<g, 256, 0, ctx->stream>>>(iv, k4, nq4, c4);
+            else probe_count4_kernel<2, false><<<g, 256, 0, ctx->stream>>>(iv, k4, nq4, c4);
         } else {
-            probe_count4_kernel<1><<<(unsigned)((nq4 + 255) / 256), 256, 0, ctx->stream>>>(iv, reinterpret_cast<const uint4 *>(d_keys), nq4,
-                                                                                       reinterpret_cast<uint4 *>(d_cnt));
+            const unsigned g = (unsigned)((nq4 + 255) / 256);
+            if (cs) probe_count4_kernel<1, true><<<g, 256, 0, ctx->stream>>>(iv, k4, nq4, c4);
+            else probe_count4_kernel<1, false><<<g, 256, 0, ctx->stream>>>(iv, k4, nq4, c4);
         }
         PB_LAUNCH_CHECK(ctx);
         done = nq4 * 4;
@@ -893,8 +900,10 @@ static int launch_probe_gather(pb_ctx *ctx, const IndexView &iv, const uint32_t 
     int64_t done = 0;
     if (!iv.key && nq >= 4 && ((uintptr_t)d_keys & 15) == 0 && !getenv("PB_PROBE1")) {
         const int64_t nq4 = nq / 4;
-        probe_gather4_kernel<<<(unsigned)((nq4 + 255) / 256), 256, 0, ctx->stream>>>(iv, reinterpret_cast<const uint4 *>(d_keys), nq4, d_qoff,
-                                                                                  d_cand_pos, d_cand_q);
+        const bool cs = !(getenv("PB_PROBE_CS") && atoi(getenv("PB_PROBE_CS")) == 0);
+        const unsigned g = (unsigned)((nq4 + 255) / 256);
+        if (cs) probe_gather4_kernel<true><<<g, 256, 0, ctx->stream>>>(iv, reinterpret_cast<const uint4 *>(d_keys), nq4, d_qoff, d_cand_pos, d_cand_q);
+        else probe_gather4_kernel<false><<<g, 256, 0, ctx->stream>>>(iv, reinterpret_cast<const uint4 *>(d_keys), nq4, d_qoff, d_cand_pos, d_cand_q);
         PB_LAUNCH_CHECK(ctx);
         done = nq4 * 4;
     }
@@ -987,6 +996,21 @@ extern "C" int pb_probe_bulk_device(pb_ctx *ctx, const pb_index *ix, const pb_se
     cudaEvent_t ev[6];
     for (auto &e : ev) PB_CUDA(ctx, cudaEventCreate(&e));
     IndexView iv = view_of(ix);
+    // PB_PROBE_L2PERSIST=1 (opt-in: the set-aside is a device-wide limit): pin the packed bucket table in L2 for the bulk passes
+    const bool persist = getenv("PB_PROBE_L2PERSIST") && atoi(getenv("PB_PROBE_L2PERSIST")) && iv.pk;
+    if (persist) {
+        const size_t bytes = (size_t)ix->nbuckets * 4;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes + (bytes >> 3));
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof av);
+        av.accessPolicyWindow.base_ptr = (void *)iv.pk;
+        av.accessPolicyWindow.num_bytes = bytes;
+        av.accessPolicyWindow.hitRatio = 1.0f;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+    }
     cudaEventRecord(ev[0], ctx->stream);
     PB_TRY(pb_seed_bulk_device(ctx, s, 0, nq, ix->mask, d_keys.as<uint32_t>()));
     cudaEventRecord(ev[1], ctx->stream);
@@ -1003,6 +1027,14 @@ extern "C" int pb_probe_bulk_device(pb_ctx *ctx, const pb_index *ix, const pb_se
     PB_TRY(launch_probe_gather(ctx, iv, d_keys.as<uint32_t>(), nq, d_qoff.as<int64_t>(), d_pos.as<int32_t>(), d_q.as<int32_t>()));
     cudaEventRecord(ev[5], ctx->stream);
     PB_TRY(pb_sync(ctx));
+    if (persist) {
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof av);
+        cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+        cudaGetLastError();
+    }
     float a = 0, b = 0, c = 0;
     cudaEventElapsedTime(&a, ev[0], ev[1]);
     cudaEventElapsedTime(&b, ev[2], ev[3]);
