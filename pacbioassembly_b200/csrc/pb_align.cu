@@ -21,6 +21,24 @@
 #include "pb_internal.cuh"
 
 #define FULL 0xffffffffu
+// -DPB_BOUNDS_CHECK (tools/ab_build.sh bounds -DPB_BOUNDS_CHECK): every parent-plane address the aligners store to or prefetch
+// from is checked against its warp's scratch slot, every ring slot against the ring; a violation prints and traps.  The pool's
+// compute-sanitizer is closed, so this build is the memory-safety check (tests/test_gpu_parity.py::test_traceback_prefetch_stress
+// run with PB_LIB=build/exp/libpb_bounds.so; profiles/r02_bounds_check.log).
+#ifdef PB_BOUNDS_CHECK
+#define PB_CHECK_RANGE(what, p, bytes, lo, hi)                                                                                 \
+    do {                                                                                                                     \
+        const char *_p = reinterpret_cast<const char *>(p);                                                                  \
+        if (_p < reinterpret_cast<const char *>(lo) || _p + (bytes) > reinterpret_cast<const char *>(hi) ||                   \
+            (reinterpret_cast<uintptr_t>(_p) & ((bytes) - 1))) {                                                             \
+            printf("PB_BOUNDS_CHECK %s: %p + %d outside [%p, %p) or misaligned (block %d thread %d)\n", what, (const void *)_p,  \
+                   (int)(bytes), (const void *)(lo), (const void *)(hi), (int)blockIdx.x, (int)threadIdx.x);                  \
+            __trap();                                                                                                        \
+        }                                                                                                                    \
+    } while (0)
+#else
+#define PB_CHECK_RANGE(what, p, bytes, lo, hi) ((void)0)
+#endif
 #define PB_STAGE_WORDS 128 // staging buffer per plane (words): 4 kbp of seg_b per TMA chunk
 #ifndef PB_TB_WINDOWS
 // traceback: 32-row parent windows in flight per warp (the one being walked + prefetched ones).  The backward walk is 19 % of K3
@@ -487,11 +505,14 @@ __device__ __forceinline__ void finish_alignment(int len_a, int len_b, int D, in
             uint32_t *dst = ring + slot * 256 + 4 * lane;
             // rows above the matrix get plain zero stores, not zero-fill copies: a copy whose source is ignored may still be
             // handed a meaningless address by the assembler, and the hardware faults on it
+            PB_CHECK_RANGE("ring slot", dst, 16, ring, ring + PB_TB_RING * 256);
+            if (q0) PB_CHECK_RANGE("traceback prefetch", q0, pn == 2 ? 16 : 8, gbase, opsrev);
             if (!q0) *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);
             else if (pn == 2) cp_async16(dst, q0, 16);
             else cp_async8(dst, q0, 8);
             if (sn) {
                 const uint2 *q1 = par_addr(row, sb);
+                if (q1) PB_CHECK_RANGE("traceback prefetch (2nd unit)", q1, sn == 2 ? 16 : 8, gbase, opsrev);
                 if (!q1) *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(0u, 0u, 0u, 0u);
                 else if (sn == 2) cp_async16(dst + 128, q1, 16);
                 else cp_async8(dst + 128, q1, 8);
@@ -782,6 +803,8 @@ __device__ __forceinline__ void align_one(const SeqView &A, int64_t a_bit, int a
         const uint32_t *plq = planes + q + lane * S + (PAD ? lane + q / S : 0);
         const int thrs = S - q % S;
         uint32_t *prow = par + (size_t)(i0 - 1) * rstride + lane_off;
+        PB_CHECK_RANGE("parent rows of a block", par + (size_t)(i0 - 1) * rstride, 16, par, opsrev);
+        PB_CHECK_RANGE("parent rows of a block (end)", par + (size_t)(i0 - 1 + tmax) * rstride - 4, 4, par, opsrev);
         uint32_t hist = 0u;
         for (int t = 0; t < tmax; ++t) {
             int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
@@ -1782,7 +1805,8 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, int locate,
         if (ctx->scratch) cudaFree(ctx->scratch);
         ctx->scratch = nullptr;
         ctx->scratch_bytes = 0;
-        const size_t want = need + need / 8 + 256;
+        // some headroom for the next batch, but never past the budget the plan was cut to
+        const size_t want = std::min(need + need / 8, std::max(budget, need)) + 256;
         cudaError_t e = cudaMalloc(&ctx->scratch, want);
         if (e != cudaSuccess) {
             cudaGetLastError();

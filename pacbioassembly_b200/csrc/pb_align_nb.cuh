@@ -220,6 +220,8 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
         const int my_off = (int)(((awh >> lane) & 1u) * 2u + ((awl >> lane) & 1u)) * PW;
         const uint32_t *plq = planes + q + lane * S;
         uint32_t *prow = par + (size_t)(i0 - 1) * rstride + lane_off;
+        PB_CHECK_RANGE("parent rows of a block", par + (size_t)(i0 - 1) * rstride, 16, par, par + par_words);
+        PB_CHECK_RANGE("parent rows of a block (end)", par + (size_t)(i0 - 1 + min(32, rows_max - i0 + 1)) * rstride - 4, 4, par, par + par_words);
         const int tfast = max(0, min(32, nfast - i0 + 1)); // rows of this block with an early-failure test
         const int tall = min(32, rows_max - i0 + 1);
         if (tfast > 0) {
@@ -354,6 +356,9 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
         lane_units(i0w, kd, pb, pn, sb, sn);
         const int row = i0w - lane;
         uint32_t *dst = ring + slot * 256 + 4 * lane;
+        PB_CHECK_RANGE("ring slot", dst, 16, ring, ring + PB_TB_RING * 256);
+        if (pn) PB_CHECK_RANGE("traceback prefetch", par_addr(row, pb), pn == 2 ? 16 : 8, par, par + par_words);
+        if (sn) PB_CHECK_RANGE("traceback prefetch (2nd unit)", par_addr(row, sb), sn == 2 ? 16 : 8, par, par + par_words);
         // rows above the matrix / bits outside the frame: plain zero stores, never zero-fill copies (see pb_align.cu)
         if (!pn) *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);
         else if (pn == 2) cp_async16(dst, par_addr(row, pb), 16);

@@ -61,7 +61,12 @@ extern "C" int pb_align_batch(pb_ctx *ctx, const char *a_text, const int64_t *a_
     pb_seqset *A = nullptr, *B = nullptr;
     int r = pb_seqset_from_text(ctx, a_text, a_off, a_len, a_stride, n, &A);
     if (r == PB_OK) r = pb_seqset_from_text(ctx, b_text, b_off, b_len, b_stride, n, &B);
-    if (r == PB_OK) r = check_tables(ctx, A, "seg_a of pair");
+    // seg_a sequences with more than four distinct bytes outside {A,C,G,T} do not fit the byte-exact bit-parallel variant (one
+    // extra Eq plane per such value): those pairs are redone below by the wavefront aligner, which compares raw bytes
+    std::vector<int64_t> wide;
+    if (r == PB_OK)
+        for (int64_t i = 0; i < n; ++i)
+            if (A->tab_count[i] == 255) wide.push_back(i);
     DevBuf d_out, d_ops, d_ops_off;
     int64_t extent = 0;
     if (r == PB_OK) r = d_out.alloc_zero(ctx, (size_t)n * sizeof(pb_align_out));
@@ -101,6 +106,35 @@ extern "C" int pb_align_batch(pb_ctx *ctx, const char *a_text, const int64_t *a_
     pb_timer_collect(ctx);
     if (A) pb_seqset_free(A);
     if (B) pb_seqset_free(B);
+    if (r == PB_OK && !wide.empty()) { // unit weights: seq_aligner::align itself, any alphabet (pb_alignw.cu); views made forward here
+        std::vector<char> ta, tb;
+        std::vector<int64_t> oa, ob, oo;
+        std::vector<int32_t> la, lb;
+        for (int64_t i : wide) {
+            oa.push_back((int64_t)ta.size()); ob.push_back((int64_t)tb.size());
+            la.push_back(a_len[i]); lb.push_back(b_len[i]);
+            const int64_t sa = a_stride ? a_stride[i] : 1, sb = b_stride ? b_stride[i] : 1;
+            for (int32_t q = 0; q < a_len[i]; ++q) ta.push_back(a_text[a_off[i] + q * sa]);
+            for (int32_t q = 0; q < b_len[i]; ++q) tb.push_back(b_text[b_off[i] + q * sb]);
+            oo.push_back(oo.empty() ? 0 : oo.back() + la[la.size() - 2] + lb[lb.size() - 2] + 1);
+        }
+        std::vector<uint8_t> wops(ops ? (size_t)(oo.back() + la.back() + lb.back() + 16) : 0);
+        std::vector<uint8_t> wa(ta.size() + 1, 1), wb(tb.size() + 1, 1);
+        std::vector<pb_align_out> wo(wide.size());
+        float keep_times[PB_T_COUNT];
+        memcpy(keep_times, ctx->times, sizeof keep_times);
+        r = pb_align_weighted_batch(ctx, ta.data(), wa.data(), oa.data(), la.data(), tb.data(), wb.data(), ob.data(), lb.data(),
+                                    (int64_t)wide.size(), R, 1.0, maxn, maxm, wo.data(), ops ? wops.data() : nullptr,
+                                    ops ? oo.data() : nullptr);
+        for (int q = 0; q < PB_T_COUNT; ++q) ctx->times[q] += keep_times[q];
+        for (size_t q = 0; r == PB_OK && q < wide.size(); ++q) {
+            out[wide[q]] = wo[q];
+            if (ops) { // the pair's own slot only: the neighbours' transcripts stay
+                memset(ops + ops_off[wide[q]], 0, (size_t)a_len[wide[q]] + b_len[wide[q]] + 1);
+                if (wo[q].ret >= 0) memcpy(ops + ops_off[wide[q]], wops.data() + oo[q], (size_t)wo[q].nedit);
+            }
+        }
+    }
     return r;
 }
 

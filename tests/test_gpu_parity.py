@@ -310,9 +310,25 @@ def test_align_non_acgt_bytes(ctx, oracle):
     a = bytearray(g[:6000]); a[1000:1010] = b"N" * 10; a[3000] = ord("n")
     b = bytearray(g[:8000]); b[1003:1007] = b"NNNN"; b[5000:5003] = b"nnn"
     assert run_batch_vs_oracle(ctx, oracle, [bytes(a), bytes(b[:5000])], [bytes(b), bytes(a)], 0.3) >= 1
-    # more than four distinct unusual byte values in seg_a: refused loudly
+    # more than four distinct unusual byte values in seg_a: outside the bit-parallel byte-exact variant (four extra Eq planes);
+    # pb_align_batch hands such pairs to the wavefront aligner, which compares raw bytes -- forward and backward views, mixed
+    # with ordinary pairs in one batch, transcripts of the neighbours untouched
+    wide_a = [b"ACGTNXYZWACGT" * 9, bytes(A2[3]), b"acgtnACGTNRYKMSW" * 20 + b"ACGT" * 30, bytes(A2[5])]
+    wide_b = [b"ACGTACGTACGTA" * 9 + b"GG", bytes(B2[3]), b"acgtnACGTNRYKMSW" * 20 + b"ACGT" * 40, bytes(B2[5])]
+    assert run_batch_vs_oracle(ctx, oracle, wide_a, wide_b, 0.3) >= 2
+    assert run_batch_vs_oracle(ctx, oracle, wide_a, wide_b, 0.45, fwd=False) >= 2
+    # the read-set pipelines keep the four-value limit and say so on every entry point
+    g = workload.reference(92, 30000)
+    weird = bytearray(g[1000:1700].tobytes()); weird[100:105] = b"NXYZW"
+    rs = ctx.seqset_one(g)
+    ix = ctx.index(rs, MASKS[0])
     with pytest.raises(PbError):
-        ctx.align(b"ACGTNXYZWACGT" * 5, b"ACGTACGTACGT" * 5)
+        ctx.locate(ix, np.frombuffer(bytes(weird), np.uint8), [0], [len(weird)], R=0.3)
+    with pytest.raises(PbError):
+        ctx.locate_submit(ix, np.frombuffer(bytes(weird), np.uint8), [0], [len(weird)], R=0.3)
+    ix2 = ctx.index(rs, MASKS[0], policy=1)
+    with pytest.raises(PbError):
+        ctx.overlap(ix2, ctx.seqset(np.frombuffer(bytes(weird), np.uint8), [0], [len(weird)]), R=0.3)
 
 
 def test_align_domain_limits(ctx, oracle):
@@ -523,6 +539,30 @@ def test_locate_strip_redo_paths(ctx, oracle):
     if os.environ.get("PB_NARROW", "1") != "0":
         assert st["redone"] > 0 and st["band_cells"] > 0  # both passes ran
     job.free(); s.free()
+
+
+def test_traceback_prefetch_stress(ctx, oracle):
+    """The traceback's asynchronous window ring (cp.async into shared memory) once faulted on zero-fill copies with a dummy
+    source -- only where prefetched windows reach above row 1, i.e. on SHORT alignments.  Short and long
+    alignments, every band class, both aligner passes, 40 repetitions: no CUDA error and the same records every time."""
+    ref = workload.reference(2, 200_000)
+    lens = np.concatenate([np.full(96, 500), np.full(64, 523), np.arange(500, 2500, 25), np.array([4000, 7000, 12000, 19000])]).astype(np.int32)
+    txt, offs, lens, _ = workload.reads(77, ref, lens, 0.04, 0.02, 0.02)
+    rs = ctx.seqset_one(ref)
+    ix = ctx.index(rs, MASKS[0])
+    first = locate_vs_oracle(ctx, oracle, ref, txt, offs, lens, MASKS[0], 0.3)
+    for rep in range(40):
+        recs, ops = ctx.locate(ix, txt, offs, lens, want_ops=True, R=0.3)
+        for n in first.dtype.names:
+            assert (recs[n] == first[n]).all(), (rep, n)
+    from allpairs_util import allpairs_workload
+    texts, image = allpairs_workload(305, 7000, 44)
+    reads = ctx.seqset_from_bin(image)
+    aix = ctx.index_set(reads, MASKS[0])
+    r0, s0 = ctx.overlap_all(aix, found_only=False, R=0.3)
+    for rep in range(40):
+        r1, s1 = ctx.overlap_all(aix, found_only=False, R=0.3)
+        assert s1 == s0 and all((r1[n] == r0[n]).all() for n in r0.dtype.names), rep
 
 
 def test_locate_pipelined_submit_collect(ctx, oracle):
