@@ -919,6 +919,7 @@ struct AlignLaunch {
     uint8_t *redo;             // two-pass locate: per item, 1 = the full-band kernel must (still) run it.  The first pass (strip)
                                // clears or keeps it; the second pass skips items whose flag is 0.  NULL: single pass
     int g256;                  // first pass: goal-side width of the strip in 1/256 of max_dst (see nb_target)
+    int s256;                  // first pass: goal-side width of the STORED strip in 1/256 of max_dst (see align_one_nb)
 };
 
 // resident CTAs per SM the register allocation is held to (more warps hide the shuffle / ballot latencies of a row)
@@ -1073,7 +1074,7 @@ align_locate_nb_kernel(const __grid_constant__ AlignLaunch p, const __grid_const
                 CandView cv;
                 derive_views(*reinterpret_cast<const PairViews *>(&p.A), lv, PAIRS ? q : q - k * lv.ntrial, r, rlen, rbase, ref_base,
                              ref_len, pos, false, cv);
-                align_one_nb<S>(*cv.a, cv.a_bit, cv.a_len, *cv.b, cv.b_bit, cv.b_len, p.R, p.maxn, p.maxm, p.g256, planes, p.PW, par,
+                align_one_nb<S>(*cv.a, cv.a_bit, cv.a_len, *cv.b, cv.b_bit, cv.b_len, p.R, p.maxn, p.maxm, p.g256, p.s256, planes, p.PW, par,
                                 p.par_words, opsrev, p.ops ? p.ops + p.ops_off[k] : nullptr, raw, p.RW, bar, phase, res, redo, band_cells);
                 alu_rows += res.fail_row ? res.fail_row : (redo ? 0 : res.len_a);
                 if (redo) break;
@@ -1902,7 +1903,7 @@ struct LocatePlan {
     bool any_irr = false;
     std::map<int, ClassPlan> plans, narrow_plans;
     int64_t n_narrow = 0;
-    int g256 = 205;
+    int g256 = 192;
 };
 
 static int build_locate_plan(pb_ctx *ctx, const std::vector<int32_t> &kept_lens, const std::vector<uint8_t> *kept_irr, double R,
@@ -1928,7 +1929,10 @@ static int build_locate_plan(pb_ctx *ctx, const std::vector<int32_t> &kept_lens,
     // take (byte-exact variant, tiny bands) plus those it flagged -- the kernel skips every item whose redo flag is clear, so the
     // second pass is planned for the items that are its own plus a small allowance.  PB_NARROW=0 runs the full band only.
     static const bool narrow_on = !(getenv("PB_NARROW") && atoi(getenv("PB_NARROW")) == 0);
-    static const int g256 = getenv("PB_NARROW_G") ? std::max(128, std::min(256, (int)(atof(getenv("PB_NARROW_G")) * 256.0))) : 205;
+    // goal-side width of the strip as a share of max_dst: what a certified alignment may cost.  A/B on config 2 (CLR reads, cost
+    // 0.15-0.22 of the length at R = 0.3): 0.80 -> 57.9 ms of K3 and 8 reads redone, 0.75 -> 57.0 / 10, 0.70 -> 55.5 / 136,
+    // 0.65 -> 6063 redone.  Whatever the value, results are exact: the certificate decides, the full band redoes the rest.
+    static const int g256 = getenv("PB_NARROW_G") ? std::max(128, std::min(256, (int)(atof(getenv("PB_NARROW_G")) * 256.0))) : 192;
     lp->g256 = g256;
     const bool both_sides = mode != PB_MODE_LOCATE;
     // the class of an item is a function of its length (and of the rare non-ACGT flag): looked up once per distinct length
@@ -2017,6 +2021,10 @@ int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_
     base.ops = d_ops; base.ops_off = d_ops_off;
     base.stats = d_stats;
     base.g256 = g256;
+    // goal-side width of the stored strip: the path may climb to (cost + goal offset) / 2.  CLR reads at R = 0.3 end on the
+    // diagonal with cost <= 0.74 max_dst: 0.45 covers them; what it does not cover is redone (PB_NARROW_S=1 stores the whole strip)
+    static const int s256 = getenv("PB_NARROW_S") ? std::max(64, std::min(256, (int)(atof(getenv("PB_NARROW_S")) * 256.0))) : 115;
+    base.s256 = s256;
     const int kmode = lv.d_item_ref ? 2 : 1;
     auto launch = [&](int key, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
         void *args[] = {(void *)&p, (void *)&lv, (void *)&d_survive, (void *)&d_rej_cells, (void *)&d_recs};

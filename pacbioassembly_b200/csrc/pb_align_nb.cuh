@@ -16,8 +16,13 @@
 // blocks the state moves down one whole word and the word entering on the right starts at h = +1.  Wl is a multiple of
 // 32*S, so the main diagonal sits in slot 0 of one lane and row t's diagonal bit is bit t.  The frame stays strictly
 // inside the reference's band (Wl + 32 <= D, NB - Wl <= D): none of the reference's edge rules is ever in play.
-// Per band word and row: 8 LOP3 + 2 SHF + 2 IADD3 (was 11 + 6 + 2), and the strip is ~1.3 D wide instead of 2 D.
+// Per band word and row: 8 LOP3 + 2 SHF + 2 IADD3 (was 11 + 6 + 2), and the strip is ~1.25 D wide instead of 2 D; parents
+// are written for ~0.85 D of it (the stored strip, see align_one_nb).
 #pragma once
+
+#ifndef PB_NB_RING
+#define PB_NB_RING 3 // traceback windows in flight in the strip pass (A/B on config 2: 3 -> 57.0 ms, 4 -> 57.9, 6 -> 61.0 of K3)
+#endif
 
 // The strip for band half-width D in band class S.  goal_left: the goal is searched on the last column (len_a > len_b).
 // target: wanted width of the goal side.  0: no certified strip in this class; 1: valid, goal side limited by the class
@@ -58,7 +63,8 @@ __host__ __device__ inline int nb_target(int D, int g256) { return (int)(((long 
 // aligned with the frame); prow: this lane's unit column of the row's parent block.  Returns the D0 word of slot 0.
 template <int S>
 __device__ __forceinline__ uint32_t row_step_nb(uint32_t (&Hp)[S], uint32_t (&Hn)[S], uint32_t (&Vp)[S], uint32_t (&Vn)[S],
-                                                const uint32_t *__restrict__ pl, int lane, bool lane0, uint32_t *__restrict__ prow, int tail_off)
+                                                const uint32_t *__restrict__ pl, int lane, bool lane0, uint32_t *__restrict__ prow, int tail_off,
+                                                bool st_on, int NL)
 {
     uint32_t Eq[S], x[S], sum[S];
 #pragma unroll
@@ -99,13 +105,14 @@ __device__ __forceinline__ uint32_t row_step_nb(uint32_t (&Hp)[S], uint32_t (&Hn
         const uint32_t Xh = Eq[s] | Hn[s];
         Hp[s] = vns | ~(Xh | vps);
         Hn[s] = vps & Xh;
-        // parents as 16-byte units {M[2p], I[2p], M[2p+1], I[2p+1]} at unit p*32 + lane; an odd S ends in 8-byte pairs at tail_off
+        // parents as 16-byte units {M[2p], I[2p], M[2p+1], I[2p+1]} at unit p*NL + (lane - first stored lane); an odd S ends in
+        // 8-byte pairs at tail_off.  Only the NL lanes of the stored strip write (rows are compact: no holes in a line).
         if ((s & 1) == 0 && s + 1 < S) {
             heldM = Mw[s]; heldI = Hp[s];
         } else if (s & 1) {
-            reinterpret_cast<uint4 *>(prow)[(s >> 1) * 32] = make_uint4(heldM, heldI, Mw[s], Hp[s]);
+            if (st_on) reinterpret_cast<uint4 *>(prow)[(s >> 1) * NL] = make_uint4(heldM, heldI, Mw[s], Hp[s]);
         } else {
-            *reinterpret_cast<uint2 *>(prow + tail_off) = make_uint2(Mw[s], Hp[s]);
+            if (st_on) *reinterpret_cast<uint2 *>(prow + tail_off) = make_uint2(Mw[s], Hp[s]);
         }
     }
     return d0w;
@@ -114,7 +121,7 @@ __device__ __forceinline__ uint32_t row_step_nb(uint32_t (&Hp)[S], uint32_t (&Hn
 // seq_aligner::align over the strip.  res.redo = 1: nothing certified, the full-band kernel must run this candidate.
 template <int S>
 __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, int a_len, const SeqView &B, int64_t b_bit, int b_len,
-                                             double R, int maxn, int maxm, int g256, uint32_t *__restrict__ planes, int PW,
+                                             double R, int maxn, int maxm, int g256, int s256, uint32_t *__restrict__ planes, int PW,
                                              uint32_t *__restrict__ par, size_t par_words, uint8_t *__restrict__ opsrev,
                                              uint8_t *__restrict__ ops_out, uint32_t *__restrict__ raw, int RW, uint64_t *bar,
                                              uint32_t &phase, AlnRes &res, int &redo, long long &band_cells)
@@ -134,7 +141,20 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
     if (!nb_policy(D, S, goal_left ? 1 : 0, nb_target(D, g256), &Wl, &NBw, &Wgoal)) { redo = 1; return; }
     // rows: past len_b + Wl the last column has left the frame (its cells cost more than Wl >= any certified minimum)
     const int rows_max = goal_left ? min(len_a, len_b + Wl) : len_a;
-    const size_t rstride = (size_t)2 * T; // words per parent row
+    // The STORED strip is narrower still.  A path of cost m ending at offset o_g stays within [-(m - o_g)/2, (m + o_g)/2], so
+    // parents are needed for offsets [-Wgoal/2, +Sg] only (mirrored when the goal is on the last column): the non-goal side is
+    // safe for every certified cost (m <= Wgoal), the goal side Sg = s256/256 of max_dst is checked against (m + o_g)/2 once
+    // the goal is known.  Parents go out for the lanes that own those frame bits, rows compacted to them.
+    const int Sh = (Wgoal + 1) / 2, Sg = max(Sh, (int)(((long long)D * s256) >> 8) + 1);
+    const int lo_off = goal_left ? Sg : Sh, hi_off = goal_left ? Sh : Sg;
+    int L_lo = max(0, Wl - lo_off) / T, L_hi = min(31, min((Wl + hi_off + 31) / T, (32 * NBw - 1) / T));
+    if (((L_hi - L_lo + 1) & 1) && (S & 1)) { // rows of 16-byte units: an odd S needs an even lane count to stay 16-byte aligned
+        if (L_hi < 31) ++L_hi; else --L_lo;
+    }
+    const int NL = L_hi - L_lo + 1;
+    const int lo_eff = Wl - L_lo * T, hi_eff = (L_hi + 1) * T - 1 - Wl - 31; // offsets stored in EVERY row of a block
+    const bool st_on = lane >= L_lo && lane <= L_hi;
+    const size_t rstride = (size_t)2 * S * NL; // words per parent row
     if ((size_t)rows_max * rstride > par_words) { redo = 1; return; } // the slot was sized for the item's own length
 
     // ---- Eq planes of seg_b in shared memory: plane c, bit t <-> (b[t - Wl] == c), zero outside [0,len_b)
@@ -198,7 +218,7 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
 #pragma unroll
     for (int s = 0; s < S; ++s) { Hn[s] = lane < Ld ? 0xffffffffu : 0u; Hp[s] = ~Hn[s]; }
     const int wt = NBw - 1, Lt = wt / S, st = wt - Lt * S; // the frame's last valid word: it starts every block at h = +1
-    const int lane_off = 4 * lane, tail_off = (S / 2) * 32 * 4 - 2 * lane;
+    const int lane_off = 4 * (lane - L_lo), tail_off = (S / 2) * NL * 4 - 2 * (lane - L_lo);
 
     int cii = 0;
     int colc = 0, colbest = 0, col_i = 0;
@@ -228,7 +248,7 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
             uint32_t hist = 0u, tb = 1u;
             for (int t = 0; t < tfast; ++t) {
                 const int off = __shfl_sync(FULL, my_off, t);
-                const uint32_t d0w = row_step_nb<S>(Hp, Hn, Vp, Vn, plq + off, lane, lane0, prow, tail_off);
+                const uint32_t d0w = row_step_nb<S>(Hp, Hn, Vp, Vn, plq + off, lane, lane0, prow, tail_off, st_on, NL);
                 hist |= d0w & tb; // row t's diagonal D0 bit is bit t of slot 0 in the diagonal's owner lane
                 tb <<= 1;
                 prow += rstride;
@@ -245,7 +265,7 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
             for (int t = tfast; t < tall; ++t) {
                 const int i = i0 + t;
                 const int off = __shfl_sync(FULL, my_off, t);
-                row_step_nb<S>(Hp, Hn, Vp, Vn, plq + off, lane, lane0, prow, tail_off);
+                row_step_nb<S>(Hp, Hn, Vp, Vn, plq + off, lane, lane0, prow, tail_off, st_on, NL);
                 prow += rstride;
                 const int c = len_b - i + Wl + t, wk = c >> 5, Lk = wk / S, sk = wk - Lk * S;
                 uint32_t vpw = 0u, vnw = 0u;
@@ -319,44 +339,49 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
         cost = best; matlen_b = bestj;
     }
     if (cost > Wgoal) { redo = 1; return; } // not certified: the full band decides
+    {
+        const int og = matlen_b - matlen_a; // the goal's offset; the path stays within [-(m - og)/2, (m + og)/2]
+        if ((cost - og) / 2 > lo_eff || (cost + og) / 2 > hi_eff) { redo = 1; return; } // it may leave the stored strip
+    }
     res.matlen_a = matlen_a; res.matlen_b = matlen_b; res.cost = cost;
     res.diag_cost = (a_len <= len_a && a_len <= len_b) ? cii : 0; // locator.cpp:86 (Q-L2)
     if ((double)matlen_b < len_b * (1 - R)) return; // seq_aligner.h:114
 
     // ---- find_path, seq_aligner.h:214-233.  Cell (i,j) sits at frame bit c = j - i + Wl + ((i-1)&31) of row i.  Lane r of a
     // window holds row i0w - r: the unit under the bit its row would have if the path kept its diagonal, plus the neighbouring
-    // unit when that bit is within 8 of the unit's edge.  Windows are prefetched PB_TB_RING deep into shared memory (cp.async.cg).
+    // unit when that bit is within 8 of the unit's edge.  Windows are prefetched PB_NB_RING deep into shared memory (cp.async.cg).
     __syncwarp();
     uint32_t *ring = planes + 2 * T;
-    int *meta = reinterpret_cast<int *>(ring + PB_TB_RING * 256);
+    int *meta = reinterpret_cast<int *>(ring + PB_NB_RING * 256);
     auto unit_of = [&](int w, int &b, int &n) {
         const int s = w % S;
         if (s < (S & ~1)) { b = w - (s & 1); n = 2; } else { b = w; n = 1; }
     };
-    auto par_addr = [&](int row, int w) -> const uint2 * {
-        const int L = w / S, s = w - L * S;
+    auto par_addr = [&](int row, int w) -> const uint2 * { // w inside the stored lanes (lane_units sees to that)
+        const int L = w / S, s = w - L * S, Ls = L - L_lo;
         const uint32_t *rb = par + (size_t)(row - 1) * rstride;
-        if (s < (S & ~1)) return reinterpret_cast<const uint2 *>(rb + ((s >> 1) * 32 + L) * 4 + (s & 1) * 2);
-        return reinterpret_cast<const uint2 *>(rb + (S / 2) * 32 * 4 + L * 2);
+        if (s < (S & ~1)) return reinterpret_cast<const uint2 *>(rb + ((s >> 1) * NL + Ls) * 4 + (s & 1) * 2);
+        return reinterpret_cast<const uint2 *>(rb + (S / 2) * NL * 4 + Ls * 2);
     };
+    const int w_lo = L_lo * S, w_hi = (L_hi + 1) * S - 1; // band words whose parents exist
     // this lane's units for a window whose first row is i0w, predicted diagonal kd = j - i + Wl
     auto lane_units = [&](int i0w, int kd, int &pb, int &pn, int &sb, int &sn) {
         const int row = i0w - lane;
         pb = pn = sb = sn = 0;
         if (row < 1) return;
         const int c = kd + ((row - 1) & 31);
-        if (c < 0 || c >= 32 * NBw) return;
+        if (c < 32 * w_lo || c >= 32 * (w_hi + 1)) return;
         unit_of(c >> 5, pb, pn);
         const int pos = c - 32 * pb;
-        if (pos < 8 && pb > 0) unit_of(pb - 1, sb, sn);
-        else if (pos >= 32 * pn - 8 && pb + pn < NBw) unit_of(pb + pn, sb, sn);
+        if (pos < 8 && pb > w_lo) unit_of(pb - 1, sb, sn);
+        else if (pos >= 32 * pn - 8 && pb + pn <= w_hi) unit_of(pb + pn, sb, sn);
     };
     auto fetch = [&](int slot, int i0w, int kd) {
         int pb, pn, sb, sn;
         lane_units(i0w, kd, pb, pn, sb, sn);
         const int row = i0w - lane;
         uint32_t *dst = ring + slot * 256 + 4 * lane;
-        PB_CHECK_RANGE("ring slot", dst, 16, ring, ring + PB_TB_RING * 256);
+        PB_CHECK_RANGE("ring slot", dst, 16, ring, ring + PB_NB_RING * 256);
         if (pn) PB_CHECK_RANGE("traceback prefetch", par_addr(row, pb), pn == 2 ? 16 : 8, par, par + par_words);
         if (sn) PB_CHECK_RANGE("traceback prefetch (2nd unit)", par_addr(row, sb), sn == 2 ? 16 : 8, par, par + par_words);
         // rows above the matrix / bits outside the frame: plain zero stores, never zero-fill copies (see pb_align.cu)
@@ -387,7 +412,7 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
                 need = !((unsigned)(w - b0) < (unsigned)n0 || (unsigned)(w - b1) < (unsigned)n1);
             }
             if (need) {
-                const int nslot = cur_slot + 1 == PB_TB_RING ? 0 : cur_slot + 1;
+                const int nslot = cur_slot + 1 == PB_NB_RING ? 0 : cur_slot + 1;
                 bool usual = have && i <= wend;
                 if (usual) {
                     const int *m = meta + 2 * nslot;
@@ -396,28 +421,28 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
                     if (usual) { // does the prefetched window hold the current cell (its lane 0)?
                         const int kd = m[1], c = kd + ((i - 1) & 31), w = (k + ((i - 1) & 31)) >> 5;
                         pb = pn = sb = sn = 0;
-                        if (c >= 0 && c < 32 * NBw) {
+                        if (c >= 32 * w_lo && c < 32 * (w_hi + 1)) {
                             unit_of(c >> 5, pb, pn);
                             const int pos = c - 32 * pb;
-                            if (pos < 8 && pb > 0) unit_of(pb - 1, sb, sn);
-                            else if (pos >= 32 * pn - 8 && pb + pn < NBw) unit_of(pb + pn, sb, sn);
+                            if (pos < 8 && pb > w_lo) unit_of(pb - 1, sb, sn);
+                            else if (pos >= 32 * pn - 8 && pb + pn <= w_hi) unit_of(pb + pn, sb, sn);
                         }
                         usual = (unsigned)(w - pb) < (unsigned)pn || (unsigned)(w - sb) < (unsigned)sn;
                     }
                 }
                 __syncwarp();
-                if (usual) { // refill the slot just walked with the window PB_TB_RING-1 ahead, on the current diagonal
-                    fetch(cur_slot, i - 32 * (PB_TB_RING - 1), k);
+                if (usual) { // refill the slot just walked with the window PB_NB_RING-1 ahead, on the current diagonal
+                    fetch(cur_slot, i - 32 * (PB_NB_RING - 1), k);
                     cur_slot = nslot;
                 } else { // cold start, or the path left the predicted units
                     cp_async_wait<0>();
                     __syncwarp();
 #pragma unroll
-                    for (int t = 0; t < PB_TB_RING; ++t) fetch(t, i - 32 * t, k);
+                    for (int t = 0; t < PB_NB_RING; ++t) fetch(t, i - 32 * t, k);
                     cur_slot = 0;
                     cold = true;
                 }
-                cp_async_wait<PB_TB_RING - 1>();
+                cp_async_wait<PB_NB_RING - 1>();
                 __syncwarp();
                 cur_i0 = meta[2 * cur_slot];
                 lane_units(cur_i0, meta[2 * cur_slot + 1], cb0, cn0, cb1, cn1);

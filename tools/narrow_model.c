@@ -20,6 +20,8 @@
  *       goal-row cell that beats it has cost <= m and offset o' <= m, so its paths stay within [-m/2, +m]: exact if
  *       m <= Wr (m/2 <= D/2 <= Wl holds already).  Cells right of the strip cost more than Wr >= m.  Mirrored when
  *       the goal is on the last column (len_a > len_b): m <= Wl.
+ *   (5) parents are only STORED where the path can be: a path of cost m ending at offset og never leaves
+ *       [-(m - og)/2, (m + og)/2] (the walk below asserts it); the kernel checks those two numbers against the lanes it wrote.
  *   Not certified -> REDO with the full band.
  *
  * Block-stationary frame: for the 32 rows i0..i0+31 of a block the strip is held in COLUMN coordinates -- frame bit c
@@ -190,6 +192,8 @@ int model_align(const char *a, int a_len, const char *b, int b_len, double R, in
     out->diag_cost = (a_len <= len_a && a_len <= len_b) ? cii : 0;
     if ((double)matlen_b < len_b * (1 - R)) { free(plane); free(par); return -1; }
     int n = 0, i = matlen_a, j = matlen_b;
+    /* the kernel stores parents only where a path of this cost and goal offset can be: [-(m - og)/2, (m + og)/2] */
+    const int og = matlen_b - matlen_a, o_lo = -((cost - og) / 2), o_hi = (cost + og) / 2;
     uint8_t *rev = (uint8_t *)malloc((size_t)len_a + len_b + 8);
     char *rv = (char *)malloc((size_t)len_a + len_b + 8);
     while (i || j) {
@@ -199,6 +203,7 @@ int model_align(const char *a, int a_len, const char *b, int b_len, double R, in
         else {
             const int c = j - i + Wl + ((i - 1) & 31);
             if (c < 0 || c >= 32 * NBw) { fprintf(stderr, "certified path left the frame\n"); abort(); }
+            if (j - i < o_lo || j - i > o_hi) { fprintf(stderr, "path offset %d outside [%d, %d] (cost %d, goal offset %d)\n", j - i, o_lo, o_hi, cost, og); abort(); }
             const uint32_t *prow = par + (size_t)i * 2 * T;
             if ((prow[c >> 5] >> (c & 31)) & 1) op = PBO_MATCH;
             else if ((prow[T + (c >> 5)] >> (c & 31)) & 1) op = PBO_INSERT;
