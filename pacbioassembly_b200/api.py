@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
         "pb_seed_extract_all_device": (C.c_int, [vp, vp, u32, P(i64), P(C.c_float)]),
         "pb_probe_bulk_device": (C.c_int, [vp, vp, vp, P(i64), P(i64), P(C.c_float), P(C.c_float), P(C.c_float)]),
         "pb_index_build": (C.c_int, [vp, vp, i64, u32, C.c_int, P(vp)]),
+        "pb_index_build_pairs": (C.c_int, [vp, vp, vp, i64, P(vp)]),
         "pb_index_free": (None, [vp]),
         "pb_index_nkeys": (i64, [vp]),
         "pb_index_nentries": (i64, [vp]),
@@ -298,6 +299,16 @@ class Context:
         h = C.c_void_p()
         self.check(self._L.pb_index_build(self.h, ref.h, seq, mask, policy, C.byref(h)))
         return Index(self, h, ref, seq)
+
+    def index_from_pairs(self, keys, pos) -> "Index":
+        """the seed map as seedmap[key].push_back(pos) fills it (locator.cpp:65): explicit (key, position) pairs in
+        insertion order; serves find() only (what hash_table::operator[] hands over)"""
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        pos = np.ascontiguousarray(pos, dtype=np.int32)
+        assert len(keys) == len(pos)
+        h = C.c_void_p()
+        self.check(self._L.pb_index_build_pairs(self.h, _ptr(keys), _ptr(pos), len(keys), C.byref(h)))
+        return Index(self, h, None, 0)
 
     # ---- aligner -------------------------------------------------------------------------------
     def align_batch(self, a_text, a_off, a_len, b_text, b_off, b_len, R: float = 0.3, maxn: int = 26000, maxm: int = 6000,

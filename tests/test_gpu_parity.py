@@ -146,6 +146,24 @@ def test_index_ref_test_basic(ctx):
     assert lists[-1] == []
 
 
+def test_index_from_pairs_keeps_insertion_order(ctx):
+    """pb_index_build_pairs: seedmap[key].push_back(pos) in insertion order (locator.cpp:62-66), duplicates kept."""
+    rng = np.random.default_rng(77)
+    keys = rng.integers(1, 5000, 60000).astype(np.uint32) * np.uint32(0x9E3779B1)
+    keys[1000:1400] = keys[0]  # one long list
+    pos = rng.integers(0, 1 << 30, len(keys)).astype(np.int32)
+    ix = ctx.index_from_pairs(keys, pos)
+    want: dict[int, list[int]] = {}
+    for k, p in zip(keys.tolist(), pos.tolist()):
+        want.setdefault(k, []).append(p)
+    assert ix.nkeys == len(want) and ix.nentries == len(keys)
+    probe = list(want)[:700] + [int(keys[0]), 12345]
+    got = ix.find_batch(probe)
+    for k, lst in zip(probe, got):
+        assert lst == want.get(k, []), hex(k)
+    ix.free()
+
+
 def test_index_vs_oracle_large(ctx, oracle):
     g = workload.reference(41, 300000)
     g[5000:5600] = ord("T")  # a repeat: one bucket far above the small-bucket sort threshold
