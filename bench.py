@@ -428,9 +428,14 @@ def main():
         q, cnd = pbk["queries"], pbk["candidates"]
         count_gbs = 12.0 * q / (pbk["count_ms"] / 1e3) / 1e9
         gather_gbs = (12.0 * q + 12.0 * cnd) / (pbk["gather_ms"] / 1e3) / 1e9
+        rg = ctx.random_gather_peak(64 << 20)  # pure random 4-byte reads of a 64 MB table: the request-rate ceiling
         probe = {"queries": q, "candidates": cnd, "count_ms": pbk["count_ms"], "gather_ms": pbk["gather_ms"],
                  "count_gbs": count_gbs, "gather_gbs": gather_gbs, "count_frac_of_peak": count_gbs / peak,
                  "gather_frac_of_peak": gather_gbs / peak,
+                 "random_gather_peak_reads_s": rg, "count_probes_s": q / (pbk["count_ms"] / 1e3),
+                 "count_frac_of_random_gather_peak": q / (pbk["count_ms"] / 1e3) / rg,
+                 "bound": "the SMs' random-request rate (one divergent 32-byte sector per probe), measured by "
+                          "pb_random_gather_peak: independent random reads of a 64 MB table with no other traffic",
                  "algorithmic": "count: 4 B key + 8 B bucket header per query; gather: the same + 4 B per position read + "
                                 "8 B per candidate written; random 8-byte reads of a 64 MB bucket table (L2-resident)"}
     except Exception as e:  # the bulk leg needs ~10 GB of scratch; never let it take the headline down

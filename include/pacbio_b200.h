@@ -85,6 +85,10 @@ PB_API int pb_ctx_timings(const pb_ctx *ctx, float *ms /* [PB_T_COUNT] */);
  * independent chains on every SM; *warp_instr_per_s = warp-level instructions retired per second.  The denominator of the
  * aligner's int-pipe fraction (BASELINE.md section 3 asks for a measured figure, not a datasheet one). */
 PB_API int pb_int_pipe_peak(pb_ctx *ctx, double *warp_instr_per_s);
+/* Measured peak of independent random 4-byte reads of a table of `table_bytes` (0: 64 MB, the bucket table of a weight-12
+ * mask; rounded down to a power of two): no key stream, no result stream, eight reads in flight per thread.  The ceiling the
+ * bulk seed probe (one random bucket read per query, locator.cpp:75-79) is measured against, next to the HBM peak. */
+PB_API int pb_random_gather_peak(pb_ctx *ctx, size_t table_bytes, double *reads_per_s);
 
 /* ---- L0: sequence representation (dna_seq.h) -------------------------------------------------- */
 

@@ -71,6 +71,7 @@ def lib() -> C.CDLL:
         "pb_ctx_set_scratch_limit": (C.c_int, [vp, sz]),
         "pb_ctx_timings": (C.c_int, [vp, vp]),
         "pb_int_pipe_peak": (C.c_int, [vp, P(C.c_double)]),
+        "pb_random_gather_peak": (C.c_int, [vp, sz, P(C.c_double)]),
         "pb_encode_batch": (C.c_int, [vp, vp, sz, vp, i64, vp]),
         "pb_decode_batch": (C.c_int, [vp, vp, i64, vp]),
         "pb_text2bin": (C.c_int, [vp, vp, sz, vp, sz, P(sz)]),
@@ -219,6 +220,12 @@ class Context:
         """measured peak of the integer ALU pipe, warp instructions per second (pb_int_pipe_peak)"""
         v = C.c_double(0.0)
         self.check(self._L.pb_int_pipe_peak(self.h, C.byref(v)))
+        return float(v.value)
+
+    def random_gather_peak(self, table_bytes: int = 0) -> float:
+        """measured peak of independent random 4-byte reads of a table (default 64 MB), reads per second"""
+        v = C.c_double(0.0)
+        self.check(self._L.pb_random_gather_peak(self.h, table_bytes, C.byref(v)))
         return float(v.value)
 
     def timings(self) -> dict:

@@ -153,7 +153,11 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
     }
     const int NL = L_hi - L_lo + 1;
     const int lo_eff = Wl - L_lo * T, hi_eff = (L_hi + 1) * T - 1 - Wl - 31; // offsets stored in EVERY row of a block
+#ifdef PB_EXP_NO_ST // timing experiment only: no parent stores (results are wrong)
+    const bool st_on = false;
+#else
     const bool st_on = lane >= L_lo && lane <= L_hi;
+#endif
     const size_t rstride = (size_t)2 * S * NL; // words per parent row
     if ((size_t)rows_max * rstride > par_words) { redo = 1; return; } // the slot was sized for the item's own length
 
@@ -346,6 +350,10 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
     res.matlen_a = matlen_a; res.matlen_b = matlen_b; res.cost = cost;
     res.diag_cost = (a_len <= len_a && a_len <= len_b) ? cii : 0; // locator.cpp:86 (Q-L2)
     if ((double)matlen_b < len_b * (1 - R)) return; // seq_aligner.h:114
+#ifdef PB_EXP_NO_TB // timing experiment only: no traceback (results are wrong)
+    res.ret = matlen_b;
+    return;
+#endif
 
     // ---- find_path, seq_aligner.h:214-233.  Cell (i,j) sits at frame bit c = j - i + Wl + ((i-1)&31) of row i.  Lane r of a
     // window holds row i0w - r: the unit under the bit its row would have if the path kept its diagonal, plus the neighbouring

@@ -1048,6 +1048,61 @@ extern "C" int pb_probe_bulk_device(pb_ctx *ctx, const pb_index *ix, const pb_se
     return PB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// random-gather peak: the measured ceiling of the bulk probe (K2)
+// ---------------------------------------------------------------------------------------------
+// Nothing but independent random 4-byte reads of a table (default: 64 MB, the bucket table of a weight-12 mask), eight in
+// flight per thread, indices from a register LCG: no key stream in, no count stream out, no bucket function.  What this
+// kernel reaches is what the SMs' request path to L2 delivers for one divergent 32-byte sector per read -- the rate the
+// probe passes are measured against.
+__global__ void __launch_bounds__(256) random_gather_kernel(const uint32_t *__restrict__ table, uint32_t idx_mask, int iters, uint32_t *out)
+{
+    uint32_t x = ((uint32_t)blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    uint32_t acc = 0u;
+    for (int it = 0; it < iters; ++it) {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x = x * 1664525u + 1013904223u;
+            v[k] = __ldg(table + ((x >> 4) & idx_mask));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc ^= v[k];
+    }
+    if (acc == 0x9e3779b9u) out[0] = acc; // keeps the loads alive
+}
+
+extern "C" int pb_random_gather_peak(pb_ctx *ctx, size_t table_bytes, double *reads_per_s)
+{
+    if (!ctx || !reads_per_s) return pb_fail(ctx, PB_ERR_ARG, "pb_random_gather_peak: bad argument");
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!table_bytes) table_bytes = (size_t)64 << 20;
+    size_t words = 1024;
+    while (words * 2 * 4 <= table_bytes) words *= 2; // a power of two: the index is a mask
+    DevBuf d_tab, d_out;
+    PB_TRY(d_tab.alloc_zero(ctx, words * 4));
+    PB_TRY(d_out.alloc_zero(ctx, 64));
+    const int iters = 64, threads = 256, use_blocks = 1 << 15; // 2^15 CTAs * 256 threads * 512 reads = 2^32 reads per launch
+    cudaEvent_t e0, e1;
+    PB_CUDA(ctx, cudaEventCreate(&e0));
+    PB_CUDA(ctx, cudaEventCreate(&e1));
+    float best = 0.f;
+    for (int rep = 0; rep < 4; ++rep) { // the first launch warms up (and pulls the table into L2); keep the fastest
+        cudaEventRecord(e0, ctx->stream);
+        random_gather_kernel<<<use_blocks, threads, 0, ctx->stream>>>(d_tab.as<uint32_t>(), (uint32_t)(words - 1), iters, d_out.as<uint32_t>());
+        cudaEventRecord(e1, ctx->stream);
+        ctx->launches++;
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && (best == 0.f || ms < best)) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *reads_per_s = (double)use_blocks * threads * (double)iters * 8.0 / (best * 1e-3);
+    return PB_OK;
+}
+
 __global__ void find_write_kernel(IndexView iv, const uint32_t *__restrict__ keys, int64_t n, const int64_t *__restrict__ pos_off,
                                   int64_t cap_each, int32_t *__restrict__ out)
 {

@@ -28,4 +28,8 @@ q, c = p["queries"], p["candidates"]
 print(f"PB_PROBE_V={os.environ.get('PB_PROBE_V', '-')} PB_PROBE1={os.environ.get('PB_PROBE1', '-')}: {q} queries, {c} candidates; "
       f"count {p['count_ms']:.3f} ms = {12.0 * q / p['count_ms'] / 1e6:.0f} GB/s algorithmic, {q / p['count_ms'] / 1e6:.1f} G queries/s; "
       f"gather {p['gather_ms']:.3f} ms = {(12.0 * q + 12.0 * c) / p['gather_ms'] / 1e6:.0f} GB/s algorithmic; seed {p['seed_ms']:.3f} ms")
+for mb in (2, 16, 64, 256, 1024):
+    r = ctx.random_gather_peak(mb << 20)
+    print(f"random 4-byte reads of a {mb} MB table: {r / 1e9:.1f} G reads/s ({r * 32 / 1e9:.0f} GB/s of sectors); "
+          f"count pass = {q / (p['count_ms'] / 1e3) / r:.2f} of it")
 ctx.close()
