@@ -410,7 +410,7 @@ def main():
     int_ach = float(np.mean(alu_instr)) / (k3_ms / 1e3)
     int_pipe = {"achieved_warp_instr_s": int_ach, "peak_warp_instr_s": int_peak, "frac": int_ach / int_peak if int_peak else None,
                 "achieved_ops_s": 32.0 * int_ach, "peak_ops_s": 32.0 * int_peak,
-                "how": "achieved = integer-ALU warp instructions of K3's row loops (12 per band word + 13 per row in the strip pass, "
+                "how": "achieved = integer-ALU warp instructions of K3's row loops (11 per band word + 14 per row in the strip pass, "
                        "19 + 23 in the full-band pass, counted in the SASS) / K3 time; peak = pb_int_pipe_peak, a register-only "
                        "LOP3/SHF kernel timed on this GPU in this run"}
 

@@ -252,7 +252,8 @@ PB_API int64_t pb_locate_job_ncand(const pb_locate_job *job); /* seed hits (cand
  * out[2] = reference cell count of those alignments (what seq_aligner.h:151-190 would have filled for them), out[3] = band
  * cells K3 actually computed (its first pass runs a certified strip of the band), out[4] = reads the strip
  * could not certify and the full-band pass ran again, out[5] = integer-ALU warp instructions of K3's row loops (rows x the
- * per-row count read off the SASS of each band class), out[6..7] = 0 */
+ * per-row count read off the SASS of each band class), out[6] = traceback rounds of the strip pass (32 parent
+ * tiles recomputed from their checkpoints per round), out[7] = cold starts of its window ring */
 PB_API int pb_locate_job_stats(const pb_locate_job *job, int64_t *out /* [8] */);
 /* Diagonal-bin tally of each kept read's seed hits (K2): votes[k] = hits whose diagonal pos - j falls in the fullest
  * 256-base bin, best_diag[k] = that bin's first diagonal.  A diagnostic of how concentrated the hits are; candidates are

@@ -741,7 +741,7 @@ class LocateJob:
         out = np.zeros(8, dtype=np.int64)
         self.ctx.check(self.ctx._L.pb_locate_job_stats(self.h, _ptr(out)))
         return {"ncand": int(out[0]), "dp_alignments": int(out[1]), "dp_cells": int(out[2]), "band_cells": int(out[3]),
-                "redone": int(out[4]), "alu_instr": int(out[5])}
+                "redone": int(out[4]), "alu_instr": int(out[5]), "tb_rounds": int(out[6]), "tb_cold": int(out[7])}
 
     def votes(self):
         """(votes, best_diag) per kept read: the diagonal-bin tally of its seed hits (diagnostic only)"""

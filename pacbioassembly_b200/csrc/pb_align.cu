@@ -919,7 +919,6 @@ struct AlignLaunch {
     uint8_t *redo;             // two-pass locate: per item, 1 = the full-band kernel must (still) run it.  The first pass (strip)
                                // clears or keeps it; the second pass skips items whose flag is 0.  NULL: single pass
     int g256;                  // first pass: goal-side width of the strip in 1/256 of max_dst (see nb_target)
-    int s256;                  // first pass: goal-side width of the STORED strip in 1/256 of max_dst (see align_one_nb)
 };
 
 // resident CTAs per SM the register allocation is held to (more warps hide the shuffle / ballot latencies of a row)
@@ -1055,6 +1054,7 @@ align_locate_nb_kernel(const __grid_constant__ AlignLaunch p, const __grid_const
         const int ref_len = PAIRS ? p.B.len[T] : lv.ref_len;
         long long cells = 0, k3_cells = 0, band_cells = 0, alu_rows = 0;
         int ncand = 0, nrun = 0, redo = 0;
+        int tbc[2] = {0, 0}; // traceback: rounds recomputed, cold starts of the window ring
         bool found = false;
         AlnRes res;
         int win_j = 0, win_pos = 0, win_rpos = 0, win_dir = 0;
@@ -1074,8 +1074,10 @@ align_locate_nb_kernel(const __grid_constant__ AlignLaunch p, const __grid_const
                 CandView cv;
                 derive_views(*reinterpret_cast<const PairViews *>(&p.A), lv, PAIRS ? q : q - k * lv.ntrial, r, rlen, rbase, ref_base,
                              ref_len, pos, false, cv);
-                align_one_nb<S>(*cv.a, cv.a_bit, cv.a_len, *cv.b, cv.b_bit, cv.b_len, p.R, p.maxn, p.maxm, p.g256, p.s256, planes, p.PW, par,
-                                p.par_words, opsrev, p.ops ? p.ops + p.ops_off[k] : nullptr, raw, p.RW, bar, phase, res, redo, band_cells);
+                align_one_nb<S>(*cv.a, cv.a_bit, cv.a_len, *cv.b, cv.b_bit, cv.b_len, p.R, p.maxn, p.maxm, p.g256, planes, p.PW, par,
+                                p.par_words, opsrev, (int)((p.slot_words - p.par_words) & ~(size_t)31), p.ops ? p.ops + p.ops_off[k] : nullptr, raw, p.RW,
+                                raw + 2 * p.RW, bar, phase, res, redo,
+                                band_cells, tbc);
                 alu_rows += res.fail_row ? res.fail_row : (redo ? 0 : res.len_a);
                 if (redo) break;
                 cells += res.cells; k3_cells += res.cells; ++nrun;
@@ -1093,9 +1095,10 @@ align_locate_nb_kernel(const __grid_constant__ AlignLaunch p, const __grid_const
         if (lane == 0) {
             if (p.stats) { // what the strip computed counts even when the item has to be redone
                 atomicAdd(p.stats + 2, (unsigned long long)band_cells);
-                atomicAdd(p.stats + 4, (unsigned long long)alu_rows * (12ull * S + 13ull)); // SASS of align_locate_nb_kernel<S>: 12 per word + 13 per row
+                atomicAdd(p.stats + 4, (unsigned long long)alu_rows * (11ull * S + 14ull)); // SASS of align_locate_nb_kernel<S>: 11 per word + 14 per row
                 if (redo) atomicAdd(p.stats + 3, 1ull);
                 else { atomicAdd(p.stats, (unsigned long long)k3_cells); atomicAdd(p.stats + 1, (unsigned long long)nrun); }
+                if (tbc[0]) { atomicAdd(p.stats + 5, (unsigned long long)tbc[0]); atomicAdd(p.stats + 6, (unsigned long long)tbc[1]); }
             }
             p.redo[k] = (uint8_t)redo;
             if (!redo) {
@@ -1686,8 +1689,13 @@ static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, int locate, si
         g->PW = (g->PW + 3) & ~3; // 16-byte aligned sub-arrays (TMA destination)
         g->RW = PB_STAGE_WORDS; // TMA staging buffer per raw plane
         g->warp_words = (key_irr(key) ? 8 : 4) * g->PW + (key_irr(key) ? 3 : 2) * g->RW;
-        g->warp_words = std::max(g->warp_words, (2 * T + PB_TB_RING_WORDS + 3) & ~3); // final deltas + the traceback's window ring
-        g->par_words = (size_t)std::max(cp.max_rows, 1) * 2 * T;
+        if (key_narrow(key)) { // the strip pass keeps its planes for the traceback: goal scan / window ring behind them
+            g->warp_words += nb_tb_words(S);
+            g->par_words = nb_tile_words(S) + nb_ck_words(S, std::max(cp.max_rows, 1)); // a round's tiles + one checkpoint per block
+        } else {
+            g->warp_words = std::max(g->warp_words, (2 * T + PB_TB_RING_WORDS + 3) & ~3); // final deltas + the traceback's window ring
+            g->par_words = (size_t)std::max(cp.max_rows, 1) * 2 * T;
+        }
     }
     // fewer warps per CTA when the per-warp planes are large (long sequences): the packed kernels stay under 96 KB so that two
     // CTAs fit an SM, the others under the 200 KB a CTA may ask for
@@ -2021,10 +2029,6 @@ int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_
     base.ops = d_ops; base.ops_off = d_ops_off;
     base.stats = d_stats;
     base.g256 = g256;
-    // goal-side width of the stored strip: the path may climb to (cost + goal offset) / 2.  CLR reads at R = 0.3 end on the
-    // diagonal with cost <= 0.74 max_dst: 0.45 covers them; what it does not cover is redone (PB_NARROW_S=1 stores the whole strip)
-    static const int s256 = getenv("PB_NARROW_S") ? std::max(64, std::min(256, (int)(atof(getenv("PB_NARROW_S")) * 256.0))) : 115;
-    base.s256 = s256;
     const int kmode = lv.d_item_ref ? 2 : 1;
     auto launch = [&](int key, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
         void *args[] = {(void *)&p, (void *)&lv, (void *)&d_survive, (void *)&d_rej_cells, (void *)&d_recs};

@@ -16,13 +16,32 @@
 // blocks the state moves down one whole word and the word entering on the right starts at h = +1.  Wl is a multiple of
 // 32*S, so the main diagonal sits in slot 0 of one lane and row t's diagonal bit is bit t.  The frame stays strictly
 // inside the reference's band (Wl + 32 <= D, NB - Wl <= D): none of the reference's edge rules is ever in play.
-// Per band word and row: 8 LOP3 + 2 SHF + 2 IADD3 (was 11 + 6 + 2), and the strip is ~1.25 D wide instead of 2 D; parents
-// are written for ~0.85 D of it (the stored strip, see align_one_nb).
+// Per band word and row: 7 LOP3 + 2 SHF + 2 IADD3 (the full-band kernel: 11 + 6 + 2), and the strip is ~1.25 D wide instead of 2 D.
+//
+// No parents are stored by the forward pass.  Per 32-row block every lane writes a CHECKPOINT: its horizontal deltas at the top
+// of the block (2 S words) and three 32-bit columns collected over the block's rows -- the vertical delta entering the lane's
+// first word (+ bit, - bit) and the carry entering its multi-word add.  With those ONE THREAD reproduces the lane's
+// 32 rows x S words of parents by itself (no shuffle, no ballot: everything that crossed the lane boundary is in the
+// checkpoint), so the traceback recomputes just the (block, lane) tiles its path runs through: 32 tiles per round, one per
+// thread, written to a small per-warp buffer that stays in L2 and is walked with the window ring.  Against stored parents
+// (64 S words per lane and block) the forward pass writes 2 S + 3 -- DRAM writes drop ~20x, the aligner's scratch from tens of
+// GB to a few -- and the traceback no longer reads scattered 16-byte units out of rows written long ago.  tools/narrow_model.c
+// asserts that every tile a path touches is reproduced bit for bit.
 #pragma once
 
 #ifndef PB_NB_RING
 #define PB_NB_RING 3 // traceback windows in flight in the strip pass (A/B on config 2: 3 -> 57.0 ms, 4 -> 57.9, 6 -> 61.0 of K3)
 #endif
+// per-warp shared memory behind the Eq planes and the staging buffer: the final deltas for the goal scan (2 x 32 S words), later
+// the traceback's window ring (32 lanes x two {MATCH, INSERT} pairs + one info word per window), two meta words per window and
+// the round's lane table
+__host__ __device__ constexpr int nb_tb_words(int S)
+{
+    return ((2 * 32 * S > PB_NB_RING * 160 + 2 * PB_NB_RING + 16 ? 2 * 32 * S : PB_NB_RING * 160 + 2 * PB_NB_RING + 16) + 3) & ~3;
+}
+// scratch words of a warp slot: the tile buffer of a traceback round (32 tiles x 32 rows x S pairs) + one checkpoint per block
+__host__ __device__ constexpr size_t nb_tile_words(int S) { return (size_t)32 * 32 * S * 2; }
+__host__ __device__ constexpr size_t nb_ck_words(int S, int rows) { return (size_t)((rows + 31) >> 5) * (2 * S + 3) * 32; }
 
 // The strip for band half-width D in band class S.  goal_left: the goal is searched on the last column (len_a > len_b).
 // target: wanted width of the goal side.  0: no certified strip in this class; 1: valid, goal side limited by the class
@@ -60,11 +79,13 @@ __host__ __device__ inline int nb_policy(int D, int S, int goal_left, int target
 __host__ __device__ inline int nb_target(int D, int g256) { return (int)(((long long)D * g256) >> 8) + 1; }
 
 // One row of the stationary frame for the S words of this lane.  pl: this lane's first Eq word of the row's plane (word
-// aligned with the frame); prow: this lane's unit column of the row's parent block.  Returns the D0 word of slot 0.
+// aligned with the frame).  vinp / vinn / cina collect what enters the lane in this row (see the checkpoint above): the vertical
+// deltas shift in from the right (row t of an n-row block ends at bit n-1-t), the carry from the left (bit 32-n+t).
+// Returns the D0 word of slot 0.
 template <int S>
 __device__ __forceinline__ uint32_t row_step_nb(uint32_t (&Hp)[S], uint32_t (&Hn)[S], uint32_t (&Vp)[S], uint32_t (&Vn)[S],
-                                                const uint32_t *__restrict__ pl, int lane, bool lane0, uint32_t *__restrict__ prow, int tail_off,
-                                                bool st_on, int NL)
+                                                const uint32_t *__restrict__ pl, int lane, bool lane0, uint32_t &vinp, uint32_t &vinn,
+                                                uint32_t &cina)
 {
     uint32_t Eq[S], x[S], sum[S];
 #pragma unroll
@@ -78,25 +99,25 @@ __device__ __forceinline__ uint32_t row_step_nb(uint32_t (&Hp)[S], uint32_t (&Hn
     for (int s = 1; s < S; ++s) ones &= sum[s];
     const uint32_t G = __ballot_sync(FULL, carry);
     const uint32_t P = __ballot_sync(FULL, ones == 0xffffffffu);
-    const uint32_t cin = ((((G | P) + G) ^ P) >> lane) & 1u; // carry into this lane's block of S words
-    sum[0] = add_cc(sum[0], cin);
+    const uint32_t cw = (((G | P) + G) ^ P) >> lane; // bit 0: the carry into this lane's block of S words
+    cina = __funnelshift_r(cina, cw, 1);
+    sum[0] = add_cc(sum[0], cw & 1u);
 #pragma unroll
     for (int s = 1; s < S; ++s) sum[s] = addc_cc(sum[s], 0u);
 
-    uint32_t Mw[S];
     uint32_t d0w = 0u;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
         const uint32_t Xv = (sum[s] ^ Hp[s]) | Eq[s];
         Vp[s] = Hn[s] | ~(Xv | Hp[s]);
         Vn[s] = Hp[s] & Xv;
-        Mw[s] = Eq[s] | ~(Xv | Hn[s]); // MATCH iff Eq | ~D0
         if (s == 0) d0w = Xv | Hn[s];
     }
     // the vertical deltas of the column left of this lane's block enter at bit 0 of its first word; +1 at the frame's left edge
     uint32_t pprev = __shfl_up_sync(FULL, Vp[S - 1], 1), nprev = __shfl_up_sync(FULL, Vn[S - 1], 1);
     if (lane0) { pprev = 0x80000000u; nprev = 0u; }
-    uint32_t heldM = 0u, heldI = 0u;
+    vinp = __funnelshift_l(pprev, vinp, 1);
+    vinn = __funnelshift_l(nprev, vinn, 1);
 #pragma unroll
     for (int s = 0; s < S; ++s) {
         const uint32_t vps = __funnelshift_l(pprev, Vp[s], 1), vns = __funnelshift_l(nprev, Vn[s], 1);
@@ -105,28 +126,54 @@ __device__ __forceinline__ uint32_t row_step_nb(uint32_t (&Hp)[S], uint32_t (&Hn
         const uint32_t Xh = Eq[s] | Hn[s];
         Hp[s] = vns | ~(Xh | vps);
         Hn[s] = vps & Xh;
-        // parents as 16-byte units {M[2p], I[2p], M[2p+1], I[2p+1]} at unit p*NL + (lane - first stored lane); an odd S ends in
-        // 8-byte pairs at tail_off.  Only the NL lanes of the stored strip write (rows are compact: no holes in a line).
-        if ((s & 1) == 0 && s + 1 < S) {
-            heldM = Mw[s]; heldI = Hp[s];
-        } else if (s & 1) {
-            if (st_on) reinterpret_cast<uint4 *>(prow)[(s >> 1) * NL] = make_uint4(heldM, heldI, Mw[s], Hp[s]);
-        } else {
-            if (st_on) *reinterpret_cast<uint2 *>(prow + tail_off) = make_uint2(Mw[s], Hp[s]);
-        }
     }
     return d0w;
 }
 
+// The same row for ONE lane on its own, from what its checkpoint recorded: cb = the carry entering the lane's add, the top bits
+// of pprev / nprev = the vertical delta entering its first word.  Writes the row's parents, {MATCH word, INSERT word} per band
+// word (MATCH iff Eq | ~D0, INSERT iff the new h = +1), to out[s].
+template <int S>
+__device__ __forceinline__ void row_step_tile(uint32_t (&Hp)[S], uint32_t (&Hn)[S], const uint32_t *__restrict__ pl, uint32_t cb,
+                                              uint32_t pprev, uint32_t nprev, uint2 *__restrict__ out)
+{
+    uint32_t Eq[S], x[S], sum[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) { Eq[s] = pl[s]; x[s] = Eq[s] & Hp[s]; }
+    sum[0] = add_cc(x[0], Hp[0]);
+#pragma unroll
+    for (int s = 1; s < S; ++s) sum[s] = addc_cc(x[s], Hp[s]);
+    sum[0] = add_cc(sum[0], cb);
+#pragma unroll
+    for (int s = 1; s < S; ++s) sum[s] = addc_cc(sum[s], 0u);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const uint32_t Xv = (sum[s] ^ Hp[s]) | Eq[s];
+        const uint32_t vp = Hn[s] | ~(Xv | Hp[s]), vn = Hp[s] & Xv;
+        const uint32_t Mw = Eq[s] | ~(Xv | Hn[s]);
+        const uint32_t vps = __funnelshift_l(pprev, vp, 1), vns = __funnelshift_l(nprev, vn, 1);
+        pprev = vp;
+        nprev = vn;
+        const uint32_t Xh = Eq[s] | Hn[s];
+        Hp[s] = vns | ~(Xh | vps);
+        Hn[s] = vps & Xh;
+        out[s] = make_uint2(Mw, Hp[s]);
+    }
+}
+
 // seq_aligner::align over the strip.  res.redo = 1: nothing certified, the full-band kernel must run this candidate.
+// scr: this warp's scratch slot -- the tile buffer of a traceback round, then the checkpoints; opsrev: ent_cap words for the
+// path's indel entries; tb: nb_tb_words(S) words of
+// shared memory behind the planes and the staging buffer.
 template <int S>
 __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, int a_len, const SeqView &B, int64_t b_bit, int b_len,
-                                             double R, int maxn, int maxm, int g256, int s256, uint32_t *__restrict__ planes, int PW,
-                                             uint32_t *__restrict__ par, size_t par_words, uint8_t *__restrict__ opsrev,
-                                             uint8_t *__restrict__ ops_out, uint32_t *__restrict__ raw, int RW, uint64_t *bar,
-                                             uint32_t &phase, AlnRes &res, int &redo, long long &band_cells)
+                                             double R, int maxn, int maxm, int g256, uint32_t *__restrict__ planes, int PW,
+                                             uint32_t *__restrict__ scr, size_t scr_words, uint8_t *__restrict__ opsrev, int ent_cap,
+                                             uint8_t *__restrict__ ops_out, uint32_t *__restrict__ raw, int RW, uint32_t *__restrict__ tb,
+                                             uint64_t *bar, uint32_t &phase, AlnRes &res, int &redo, long long &band_cells, int (&tbc)[2])
 {
     constexpr int T = 32 * S;
+    constexpr int F = 2 * S + 3; // checkpoint fields per lane and block
     const int lane = threadIdx.x & 31;
     const bool lane0 = lane == 0;
     int len_a, len_b, D;
@@ -141,25 +188,9 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
     if (!nb_policy(D, S, goal_left ? 1 : 0, nb_target(D, g256), &Wl, &NBw, &Wgoal)) { redo = 1; return; }
     // rows: past len_b + Wl the last column has left the frame (its cells cost more than Wl >= any certified minimum)
     const int rows_max = goal_left ? min(len_a, len_b + Wl) : len_a;
-    // The STORED strip is narrower still.  A path of cost m ending at offset o_g stays within [-(m - o_g)/2, (m + o_g)/2], so
-    // parents are needed for offsets [-Wgoal/2, +Sg] only (mirrored when the goal is on the last column): the non-goal side is
-    // safe for every certified cost (m <= Wgoal), the goal side Sg = s256/256 of max_dst is checked against (m + o_g)/2 once
-    // the goal is known.  Parents go out for the lanes that own those frame bits, rows compacted to them.
-    const int Sh = (Wgoal + 1) / 2, Sg = max(Sh, (int)(((long long)D * s256) >> 8) + 1);
-    const int lo_off = goal_left ? Sg : Sh, hi_off = goal_left ? Sh : Sg;
-    int L_lo = max(0, Wl - lo_off) / T, L_hi = min(31, min((Wl + hi_off + 31) / T, (32 * NBw - 1) / T));
-    if (((L_hi - L_lo + 1) & 1) && (S & 1)) { // rows of 16-byte units: an odd S needs an even lane count to stay 16-byte aligned
-        if (L_hi < 31) ++L_hi; else --L_lo;
-    }
-    const int NL = L_hi - L_lo + 1;
-    const int lo_eff = Wl - L_lo * T, hi_eff = (L_hi + 1) * T - 1 - Wl - 31; // offsets stored in EVERY row of a block
-#ifdef PB_EXP_NO_ST // timing experiment only: no parent stores (results are wrong)
-    const bool st_on = false;
-#else
-    const bool st_on = lane >= L_lo && lane <= L_hi;
-#endif
-    const size_t rstride = (size_t)2 * S * NL; // words per parent row
-    if ((size_t)rows_max * rstride > par_words) { redo = 1; return; } // the slot was sized for the item's own length
+    if (nb_tile_words(S) + nb_ck_words(S, rows_max) > scr_words) { redo = 1; return; } // the slot was sized for the item's own length
+    uint32_t *const mb = scr;                    // tile buffer: [row of the block][band word of the lane][tile] {MATCH, INSERT}
+    uint32_t *const ck = scr + nb_tile_words(S); // checkpoints: [block][field][lane]
 
     // ---- Eq planes of seg_b in shared memory: plane c, bit t <-> (b[t - Wl] == c), zero outside [0,len_b)
     const int PWn = min(PW, ((rows_max + 31) >> 5) + T + 1);
@@ -222,7 +253,6 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
 #pragma unroll
     for (int s = 0; s < S; ++s) { Hn[s] = lane < Ld ? 0xffffffffu : 0u; Hp[s] = ~Hn[s]; }
     const int wt = NBw - 1, Lt = wt / S, st = wt - Lt * S; // the frame's last valid word: it starts every block at h = +1
-    const int lane_off = 4 * (lane - L_lo), tail_off = (S / 2) * NL * 4 - 2 * (lane - L_lo);
 
     int cii = 0;
     int colc = 0, colbest = 0, col_i = 0;
@@ -239,23 +269,25 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
             for (int s = 0; s < S; ++s)
                 if (lane == Lt && s == st) { Hp[s] = 0xffffffffu; Hn[s] = 0u; }
         }
+        // checkpoint, part 1: the deltas the block's first row starts from
+        uint32_t *ckb = ck + (size_t)q * (F * 32) + lane;
+        PB_CHECK_RANGE("checkpoint of a block", ckb + (F - 1) * 32, 4, scr, scr + scr_words);
+#pragma unroll
+        for (int s = 0; s < S; ++s) { ckb[s * 32] = Hp[s]; ckb[(S + s) * 32] = Hn[s]; }
+        uint32_t vinp = 0u, vinn = 0u, cina = 0u;
         // this block's 32 elements of seg_a: lane t keeps the plane offset of row t
         const uint32_t awh = load_window(A.hi, A.nwords, a_bit + i0 - 1), awl = load_window(A.lo, A.nwords, a_bit + i0 - 1);
         const int my_off = (int)(((awh >> lane) & 1u) * 2u + ((awl >> lane) & 1u)) * PW;
         const uint32_t *plq = planes + q + lane * S;
-        uint32_t *prow = par + (size_t)(i0 - 1) * rstride + lane_off;
-        PB_CHECK_RANGE("parent rows of a block", par + (size_t)(i0 - 1) * rstride, 16, par, par + par_words);
-        PB_CHECK_RANGE("parent rows of a block (end)", par + (size_t)(i0 - 1 + min(32, rows_max - i0 + 1)) * rstride - 4, 4, par, par + par_words);
         const int tfast = max(0, min(32, nfast - i0 + 1)); // rows of this block with an early-failure test
         const int tall = min(32, rows_max - i0 + 1);
         if (tfast > 0) {
-            uint32_t hist = 0u, tb = 1u;
+            uint32_t hist = 0u, tb1 = 1u;
             for (int t = 0; t < tfast; ++t) {
                 const int off = __shfl_sync(FULL, my_off, t);
-                const uint32_t d0w = row_step_nb<S>(Hp, Hn, Vp, Vn, plq + off, lane, lane0, prow, tail_off, st_on, NL);
-                hist |= d0w & tb; // row t's diagonal D0 bit is bit t of slot 0 in the diagonal's owner lane
-                tb <<= 1;
-                prow += rstride;
+                const uint32_t d0w = row_step_nb<S>(Hp, Hn, Vp, Vn, plq + off, lane, lane0, vinp, vinn, cina);
+                hist |= d0w & tb1; // row t's diagonal D0 bit is bit t of slot 0 in the diagonal's owner lane
+                tb1 <<= 1;
             }
             hist = __shfl_sync(FULL, hist, Ld);
             const int thr = (int)((i0 + lane) * R); // cost > i*R  <=>  cost > floor(i*R)
@@ -269,8 +301,7 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
             for (int t = tfast; t < tall; ++t) {
                 const int i = i0 + t;
                 const int off = __shfl_sync(FULL, my_off, t);
-                row_step_nb<S>(Hp, Hn, Vp, Vn, plq + off, lane, lane0, prow, tail_off, st_on, NL);
-                prow += rstride;
+                row_step_nb<S>(Hp, Hn, Vp, Vn, plq + off, lane, lane0, vinp, vinn, cina);
                 const int c = len_b - i + Wl + t, wk = c >> 5, Lk = wk / S, sk = wk - Lk * S;
                 uint32_t vpw = 0u, vnw = 0u;
 #pragma unroll
@@ -282,6 +313,8 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
                 if (colc < colbest) { colbest = colc; col_i = i; }
             }
         }
+        // checkpoint, part 2: what entered this lane in the block's rows
+        ckb[(2 * S) * 32] = vinp; ckb[(2 * S + 1) * 32] = vinn; ckb[(2 * S + 2) * 32] = cina;
     }
     if (fail_row) { // certain: both sides of the strip are >= D/2 >= floor(i*R)/2
         res.fail_row = fail_row;
@@ -296,8 +329,8 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
     __syncwarp();
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        planes[lane * S + s] = Hp[s];
-        planes[T + lane * S + s] = Hn[s];
+        tb[lane * S + s] = Hp[s];
+        tb[T + lane * S + s] = Hn[s];
     }
     __syncwarp();
     int matlen_a, matlen_b, cost;
@@ -316,7 +349,7 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
             const int lo = max(c_first, 32 * w), hi = min(c_last, 32 * w + 31);
             int tot = 0, lmin = INT_MAX, lpos = 0;
             if (lo <= hi) {
-                const uint32_t hp = planes[w], hn = planes[T + w];
+                const uint32_t hp = tb[w], hn = tb[T + w];
                 for (int c = lo; c <= hi; ++c) {
                     tot += (int)((hp >> (c & 31)) & 1u) - (int)((hn >> (c & 31)) & 1u);
                     if (tot < lmin) { lmin = tot; lpos = c; }
@@ -343,10 +376,6 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
         cost = best; matlen_b = bestj;
     }
     if (cost > Wgoal) { redo = 1; return; } // not certified: the full band decides
-    {
-        const int og = matlen_b - matlen_a; // the goal's offset; the path stays within [-(m - og)/2, (m + og)/2]
-        if ((cost - og) / 2 > lo_eff || (cost + og) / 2 > hi_eff) { redo = 1; return; } // it may leave the stored strip
-    }
     res.matlen_a = matlen_a; res.matlen_b = matlen_b; res.cost = cost;
     res.diag_cost = (a_len <= len_a && a_len <= len_b) ? cii : 0; // locator.cpp:86 (Q-L2)
     if ((double)matlen_b < len_b * (1 - R)) return; // seq_aligner.h:114
@@ -355,154 +384,256 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
     return;
 #endif
 
-    // ---- find_path, seq_aligner.h:214-233.  Cell (i,j) sits at frame bit c = j - i + Wl + ((i-1)&31) of row i.  Lane r of a
-    // window holds row i0w - r: the unit under the bit its row would have if the path kept its diagonal, plus the neighbouring
-    // unit when that bit is within 8 of the unit's edge.  Windows are prefetched PB_NB_RING deep into shared memory (cp.async.cg).
+    // ---- find_path, seq_aligner.h:214-233.  Cell (i,j) sits at frame bit c = j - i + Wl + ((i-1)&31) of row i, band word c >> 5,
+    // lane (c >> 5) / S.  A ROUND recomputes the parents of NBK blocks going up from the current row, NLK adjacent lanes per
+    // block around the path's predicted diagonal (its diagonal now, plus the drift per row seen so far): thread x takes
+    // block r_qh - x / NLK, lane rtab[x / NLK] + x % NLK.  The walk goes through 32-row windows: lane r of a window holds row
+    // i0w - r, the {MATCH, INSERT} pairs of the two band words around the bit its row has on the predicted diagonal (16 bits of
+    // slack on either side); one ballot finds the run of MATCH steps, one shuffle the indel that ends it.  Windows are prefetched
+    // PB_NB_RING deep (cp.async) from the tile buffer.  A cell outside the round (above its blocks, or in a lane it did not
+    // recompute) starts a new round there.  The transcript is written at the end: MATCH everywhere, then the indels, which the
+    // walk recorded as (position, op) entries.
     __syncwarp();
-    uint32_t *ring = planes + 2 * T;
-    int *meta = reinterpret_cast<int *>(ring + PB_NB_RING * 256);
-    auto unit_of = [&](int w, int &b, int &n) {
-        const int s = w % S;
-        if (s < (S & ~1)) { b = w - (s & 1); n = 2; } else { b = w; n = 1; }
+    constexpr int NLK = S == 1 ? 3 : 2, NBK = 32 / NLK; // A/B on config 2 (S >= 2): 2 lanes 47.1 ms, 3 lanes 48.0, 4 lanes 49.9 of K3
+    uint32_t *ring = tb;                                           // PB_NB_RING windows x 32 lanes x {M, I} of two band words
+    int *winfo = reinterpret_cast<int *>(ring + PB_NB_RING * 128); // per window and lane: first of its two words, which of them it has
+    int *meta = winfo + PB_NB_RING * 32;                           // per window: first row, predicted diagonal
+    int *rtab = meta + 2 * PB_NB_RING;                             // per block of the round: first recomputed lane
+    uint2 *const mb2 = reinterpret_cast<uint2 *>(mb);              // tile buffer: [row of the block][tile][band word of the lane]
+    const int L_last = (NBw - 1) / S; // last lane that holds valid frame words
+    int r_qh = 0, r_nb = 0, r_sl = 0; // the current round: top block, blocks; drift of the diagonal in 1/256 bit per row
+    int r_ai = matlen_a, r_ak = matlen_b - matlen_a + Wl; // where the drift is measured from
+    bool r_have_sl = false;
+    auto tile_of = [&](int row, int w) -> int { // the round's tile that holds band word w of `row`; -1: none
+        if (row < 1 || (unsigned)w >= (unsigned)NBw) return -1;
+        const int bi = r_qh - ((row - 1) >> 5);
+        if (bi >= r_nb) return -1;
+        const int dl = w / S - rtab[bi];
+        return (unsigned)dl < (unsigned)NLK ? bi * NLK + dl : -1;
     };
-    auto par_addr = [&](int row, int w) -> const uint2 * { // w inside the stored lanes (lane_units sees to that)
-        const int L = w / S, s = w - L * S, Ls = L - L_lo;
-        const uint32_t *rb = par + (size_t)(row - 1) * rstride;
-        if (s < (S & ~1)) return reinterpret_cast<const uint2 *>(rb + ((s >> 1) * NL + Ls) * 4 + (s & 1) * 2);
-        return reinterpret_cast<const uint2 *>(rb + (S / 2) * NL * 4 + Ls * 2);
+    auto new_round = [&](int i, int k) {
+        ++tbc[0];
+        r_qh = (i - 1) >> 5;
+        r_nb = min(r_qh + 1, NBK);
+        // drift of the path's diagonal per row, from the stretch walked since the round before (not from the goal: the reference's
+        // goal cell lies at j >= len_a, so a read that spans fewer reference bases than its length begins its way back with one
+        // long run of INSERTs that says nothing about the rest)
+        if (r_ai - i >= 96) {
+            const int sl = max(-128, min(128, ((k - r_ak) * 256) / (r_ai - i)));
+            r_sl = r_have_sl ? (r_sl + sl) / 2 : sl;
+            r_have_sl = true;
+            r_ai = i; r_ak = k;
+        } else if (!r_have_sl) { r_ai = i; r_ak = k; } // still inside the run at the goal: anchor where it ends
+        const int bi = lane / NLK, dl = lane - bi * NLK;
+        const bool act = bi < r_nb;
+        const int qq = r_qh - bi;
+        // NLK lanes centred on the frame bit predicted for the middle of the block, rounded to a lane
+        const int cmid = k + ((r_sl * (i - (32 * qq + 16))) >> 8) + 16;
+        const int num = cmid - (NLK - 1) * (T / 2);
+        const int La = max(0, min(num <= 0 ? 0 : num / T, L_last - NLK + 1));
+        if (act && dl == 0) rtab[bi] = La;
+        const int L = La + dl;
+        uint32_t hp[S], hn[S], vp = 0u, vn = 0u, cc = 0u, awh = 0u, awl = 0u;
+        int nr = 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) hp[s] = hn[s] = 0u;
+        if (act) {
+            const uint32_t *ckb = ck + (size_t)qq * (F * 32) + L;
+            PB_CHECK_RANGE("checkpoint read", ckb + (F - 1) * 32, 4, scr, scr + scr_words);
+#pragma unroll
+            for (int s = 0; s < S; ++s) { hp[s] = __ldcg(ckb + s * 32); hn[s] = __ldcg(ckb + (S + s) * 32); }
+            nr = min(32, rows_max - 32 * qq);
+            // row t's entering deltas on top (<< t brings them to bit 31), its carry at bit t
+            vp = __ldcg(ckb + (2 * S) * 32) << (32 - nr);
+            vn = __ldcg(ckb + (2 * S + 1) * 32) << (32 - nr);
+            cc = __ldcg(ckb + (2 * S + 2) * 32) >> (32 - nr);
+            awh = load_window(A.hi, A.nwords, a_bit + 32 * qq);
+            awl = load_window(A.lo, A.nwords, a_bit + 32 * qq);
+        }
+        const uint32_t *plb = planes + qq + L * S;
+        uint2 *out = mb2 + lane * S;
+        for (int t = 0; t < 32; ++t) {
+            if (t < nr) {
+                const uint32_t *pl = plb + (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u)) * PW;
+                PB_CHECK_RANGE("tile store", out + t * 32 * S + S - 1, 8, scr, scr + nb_tile_words(S));
+                row_step_tile<S>(hp, hn, pl, (cc >> t) & 1u, vp << t, vn << t, out + t * 32 * S);
+            }
+        }
+        __syncwarp();
     };
-    const int w_lo = L_lo * S, w_hi = (L_hi + 1) * S - 1; // band words whose parents exist
-    // this lane's units for a window whose first row is i0w, predicted diagonal kd = j - i + Wl
-    auto lane_units = [&](int i0w, int kd, int &pb, int &pn, int &sb, int &sn) {
-        const int row = i0w - lane;
-        pb = pn = sb = sn = 0;
-        if (row < 1) return;
-        const int c = kd + ((row - 1) & 31);
-        if (c < 32 * w_lo || c >= 32 * (w_hi + 1)) return;
-        unit_of(c >> 5, pb, pn);
-        const int pos = c - 32 * pb;
-        if (pos < 8 && pb > w_lo) unit_of(pb - 1, sb, sn);
-        else if (pos >= 32 * pn - 8 && pb + pn <= w_hi) unit_of(pb + pn, sb, sn);
-    };
+    // window `slot`: rows i0w, i0w-1, ..., one per lane, around the predicted diagonal kd = j - i + Wl
     auto fetch = [&](int slot, int i0w, int kd) {
-        int pb, pn, sb, sn;
-        lane_units(i0w, kd, pb, pn, sb, sn);
-        const int row = i0w - lane;
-        uint32_t *dst = ring + slot * 256 + 4 * lane;
-        PB_CHECK_RANGE("ring slot", dst, 16, ring, ring + PB_NB_RING * 256);
-        if (pn) PB_CHECK_RANGE("traceback prefetch", par_addr(row, pb), pn == 2 ? 16 : 8, par, par + par_words);
-        if (sn) PB_CHECK_RANGE("traceback prefetch (2nd unit)", par_addr(row, sb), sn == 2 ? 16 : 8, par, par + par_words);
-        // rows above the matrix / bits outside the frame: plain zero stores, never zero-fill copies (see pb_align.cu)
-        if (!pn) *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);
-        else if (pn == 2) cp_async16(dst, par_addr(row, pb), 16);
-        else cp_async8(dst, par_addr(row, pb), 8);
-        if (sn == 2) cp_async16(dst + 128, par_addr(row, sb), 16);
-        else if (sn == 1) cp_async8(dst + 128, par_addr(row, sb), 8);
+        const int row = i0w - lane, t = (row - 1) & 31;
+        const int w0 = (kd + t - 16) >> 5; // the row's bit on that diagonal lies in word w0 or w0 + 1, >= 16 bits from their ends
+        const int bi = r_qh - ((row - 1) >> 5);
+        const bool rowok = row >= 1 && bi < r_nb;
+        const int La = rowok ? rtab[bi] : 0;
+        // word w0 is slot s0 of lane L0; w0 + 1 the next slot, or slot 0 of the next lane (w0 = -1: lane -1, never in the round)
+        const int L0 = (w0 + S) / S - 1, s0 = w0 - L0 * S;
+        const int L1 = s0 + 1 < S ? L0 : L0 + 1, s1 = s0 + 1 < S ? s0 + 1 : 0;
+        const bool ok0 = rowok && (unsigned)w0 < (unsigned)NBw && (unsigned)(L0 - La) < (unsigned)NLK;
+        const bool ok1 = rowok && (unsigned)(w0 + 1) < (unsigned)NBw && (unsigned)(L1 - La) < (unsigned)NLK;
+        const int tbase = t * 32 + bi * NLK - La; // tile index of lane L in this row: tbase + L
+        uint32_t *dst = ring + slot * 128 + 4 * lane;
+        PB_CHECK_RANGE("ring slot", dst, 16, ring, ring + PB_NB_RING * 128);
+        // rows above the matrix / words outside the round: plain zero stores, never zero-fill copies (see pb_align.cu)
+        if (ok0) {
+            const uint2 *src = mb2 + (tbase + L0) * S + s0;
+            PB_CHECK_RANGE("traceback prefetch", src, 8, scr, scr + nb_tile_words(S));
+            cp_async8(dst, src, 8);
+        } else *reinterpret_cast<uint2 *>(dst) = make_uint2(0u, 0u);
+        if (ok1) {
+            const uint2 *src = mb2 + (tbase + L1) * S + s1;
+            PB_CHECK_RANGE("traceback prefetch (2nd word)", src, 8, scr, scr + nb_tile_words(S));
+            cp_async8(dst + 2, src, 8);
+        } else *reinterpret_cast<uint2 *>(dst + 2) = make_uint2(0u, 0u);
+        winfo[slot * 32 + lane] = ((w0 + 1) << 2) | (ok1 ? 2 : 0) | (ok0 ? 1 : 0);
         if (lane == 0) { meta[2 * slot] = i0w; meta[2 * slot + 1] = kd; }
         cp_async_commit();
     };
-    int n = 0;
+    // What the walk records, per row of seg_a it leaves: how many INSERT steps it took along the row and whether it left it by
+    // DELETE or by MATCH -- 16 bits per row, written 32 rows at a time; the transcript is laid out from that at the end.
+    uint16_t *rowops = reinterpret_cast<uint16_t *>(opsrev);
+    int i = matlen_a, j = matlen_b, nins = 0;
     {
-        int i = matlen_a, j = matlen_b;
-        const int guard = len_a + len_b + 1;
-        int cur_slot = 0, cur_i0 = 0, wend = 0, cb0 = 0, cn0 = 0, cb1 = 0, cn1 = 0, tr = 0;
-        uint4 U0 = make_uint4(0u, 0u, 0u, 0u), U1 = U0;
-        bool have = false, cold = false;
-        while (i > 0 && j > 0 && n < guard) {
+        const int guard = 2 * (len_a + len_b) + 64; // windows: far more than any path needs
+        int cur_slot = 0, cur_i0 = 0, kd = 0, obase = 0, carry = 0, nwin = 0;
+        bool a0 = false, a1 = false;
+        uint32_t avboth = 0u;
+        uint4 U = make_uint4(0u, 0u, 0u, 0u);
+        bool have = false, round_ok = false;
+        while (i > 0 && j > 0) {
             const int k = j - i + Wl;
-            // is the current cell's word among the units lane r0 holds?
-            bool need = !have || i <= wend;
-            if (!need) {
-                const int r0 = cur_i0 - i;
-                const int w = (k + ((i - 1) & 31)) >> 5;
-                const int b0 = __shfl_sync(FULL, cb0, r0), n0 = __shfl_sync(FULL, cn0, r0);
-                const int b1 = __shfl_sync(FULL, cb1, r0), n1 = __shfl_sync(FULL, cn1, r0);
-                need = !((unsigned)(w - b0) < (unsigned)n0 || (unsigned)(w - b1) < (unsigned)n1);
-            }
-            if (need) {
+            bool fresh = false;
+            if (++nwin > guard) { redo = 1; break; }
+            if (have) { // the window is walked: the next one in the ring starts at row i, unless a cold start intervened
                 const int nslot = cur_slot + 1 == PB_NB_RING ? 0 : cur_slot + 1;
-                bool usual = have && i <= wend;
-                if (usual) {
-                    const int *m = meta + 2 * nslot;
-                    int pb, pn, sb, sn;
-                    usual = m[0] == i;
-                    if (usual) { // does the prefetched window hold the current cell (its lane 0)?
-                        const int kd = m[1], c = kd + ((i - 1) & 31), w = (k + ((i - 1) & 31)) >> 5;
-                        pb = pn = sb = sn = 0;
-                        if (c >= 32 * w_lo && c < 32 * (w_hi + 1)) {
-                            unit_of(c >> 5, pb, pn);
-                            const int pos = c - 32 * pb;
-                            if (pos < 8 && pb > w_lo) unit_of(pb - 1, sb, sn);
-                            else if (pos >= 32 * pn - 8 && pb + pn <= w_hi) unit_of(pb + pn, sb, sn);
-                        }
-                        usual = (unsigned)(w - pb) < (unsigned)pn || (unsigned)(w - sb) < (unsigned)sn;
+                if (meta[2 * nslot] == i) {
+                    __syncwarp();
+                    fetch(cur_slot, i - 32 * (PB_NB_RING - 1), k + ((r_sl * 32 * (PB_NB_RING - 1)) >> 8)); // refill the slot just walked
+                    cur_slot = nslot;
+                } else have = false;
+            }
+            if (!have) { // cold start: (re)fill the ring from the current cell on its own diagonal
+                cp_async_wait<0>();
+                __syncwarp();
+                const int w = (k + ((i - 1) & 31)) >> 5;
+                if (!round_ok || tile_of(i, w) < 0) { // the cell is not in the current round: recompute from here
+                    new_round(i, k);
+                    round_ok = true;
+                    if (tile_of(i, w) < 0) { redo = 1; break; } // outside the frame: never for a certified goal
+                }
+#pragma unroll
+                for (int t = 0; t < PB_NB_RING; ++t) fetch(t, i - 32 * t, k + ((r_sl * 32 * t) >> 8));
+                cur_slot = 0;
+                ++tbc[1];
+                fresh = true;
+            }
+            cp_async_wait<PB_NB_RING - 1>();
+            __syncwarp();
+            cur_i0 = meta[2 * cur_slot];
+            kd = meta[2 * cur_slot + 1];
+            {
+                const int v = winfo[cur_slot * 32 + lane];
+                U = *reinterpret_cast<const uint4 *>(ring + cur_slot * 128 + 4 * lane);
+                a0 = (v & 1) != 0; a1 = (v & 2) != 0;
+                // frame bit c of this lane's row sits at bit c - 32 w0 of its two words: obase + dk on diagonal kd + dk, and
+                // obase is in [16, 48), so the diagonals dk in [-16, 16) lie inside the two words
+                obase = kd + ((cur_i0 - lane - 1) & 31) - 32 * ((v >> 2) - 1);
+                avboth = __ballot_sync(FULL, a0 && a1);
+            }
+            // ---- walk the window: r = row index (lane) of the current cell, dk = its diagonal relative to kd
+            int r = cur_i0 - i, dk = k - kd;
+            const int r_in = r, dk_in = dk;
+            int ins = lane == r ? carry : 0; // INSERT steps along this lane's row
+            uint32_t delmask = 0u;           // rows left by DELETE
+            // careful: some row lacks a word, or the window reaches row 0 / column 0 -- availability and the matrix's edges are
+            // then checked at every step; everywhere else the window is walked with two ballots per step and nothing else
+            const bool careful = avboth != FULL || cur_i0 < 32 || cur_i0 - 31 + kd - 16 - Wl < 1;
+            bool done = false;
+            if (!careful) {
+                while (r < 32 && (unsigned)(dk + 16) < 32u) { // until the window is walked or the path leaves the diagonals it was cut for
+                    const int o = obase + dk;
+                    const bool hi = (o & 32) != 0;
+                    const uint32_t Bm = __ballot_sync(FULL, __funnelshift_r(hi ? U.z : U.x, 0u, o) & 1u);
+                    const uint32_t Bi = __ballot_sync(FULL, __funnelshift_r(hi ? U.w : U.y, 0u, o) & 1u);
+                    r += __clz(__brev(~(Bm >> r))); // MATCH steps: the zeros shifted in end the run at the window's end at the latest
+                    if (r >= 32) break;
+                    if ((Bi >> r) & 1u) { // INSERT: one column left along the row
+                        --dk; ++nins;
+                        ins += lane == r;
+                    } else { // DELETE: up, on the next diagonal
+                        ++dk;
+                        delmask |= 1u << r;
+                        ++r;
                     }
                 }
-                __syncwarp();
-                if (usual) { // refill the slot just walked with the window PB_NB_RING-1 ahead, on the current diagonal
-                    fetch(cur_slot, i - 32 * (PB_NB_RING - 1), k);
-                    cur_slot = nslot;
-                } else { // cold start, or the path left the predicted units
-                    cp_async_wait<0>();
-                    __syncwarp();
-#pragma unroll
-                    for (int t = 0; t < PB_NB_RING; ++t) fetch(t, i - 32 * t, k);
-                    cur_slot = 0;
-                    cold = true;
+            } else
+                for (;;) {
+                    if (r >= 32 || (unsigned)(dk + 16) >= 32u) break;
+                    const int ci = cur_i0 - r, cj = ci + kd + dk - Wl;
+                    if (ci <= 0 || cj <= 0) { done = true; break; }
+                    const int lim = min(32 - r, min(ci, cj));
+                    const int o = obase + dk;
+                    const bool hi = (o & 32) != 0, in = hi ? a1 : a0;
+                    const uint32_t Av = __ballot_sync(FULL, in);
+                    if (!((Av >> r) & 1u)) break; // the window does not hold the current cell
+                    const uint32_t Bm = __ballot_sync(FULL, in && (__funnelshift_r(hi ? U.z : U.x, 0u, o) & 1u));
+                    const uint32_t Bi = __ballot_sync(FULL, __funnelshift_r(hi ? U.w : U.y, 0u, o) & 1u);
+                    const int run = min(__clz(__brev(~(Bm >> r))), lim); // MATCH steps
+                    r += run;
+                    if (run == lim) continue; // the window's end, or row 0 / column 0: decided at the top
+                    if (!((Av >> r) & 1u)) break;
+                    if ((Bi >> r) & 1u) {
+                        --dk; ++nins;
+                        ins += lane == r;
+                    } else {
+                        ++dk;
+                        delmask |= 1u << r;
+                        ++r;
+                    }
                 }
-                cp_async_wait<PB_NB_RING - 1>();
-                __syncwarp();
-                cur_i0 = meta[2 * cur_slot];
-                lane_units(cur_i0, meta[2 * cur_slot + 1], cb0, cn0, cb1, cn1);
-                U0 = *reinterpret_cast<const uint4 *>(ring + cur_slot * 256 + 4 * lane);
-                U1 = cn1 ? *reinterpret_cast<const uint4 *>(ring + cur_slot * 256 + 128 + 4 * lane) : make_uint4(0u, 0u, 0u, 0u);
-                tr = (cur_i0 - lane - 1) & 31; // this lane's row position inside its block
-                wend = cur_i0 - 32;
-                have = true;
+            // rows the walk has left: their record; the row it stands on takes its INSERT count into the next window
+            if (lane < r) {
+                PB_CHECK_RANGE("row record", rowops + (cur_i0 - lane), 2, opsrev, opsrev + (size_t)ent_cap * 4);
+                rowops[cur_i0 - lane] = (uint16_t)((ins << 1) | ((delmask >> lane) & 1u));
             }
-            const int r0 = cur_i0 - i;
-            // every lane looks at the bit its own row has on the current diagonal
-            const int c = k + tr, w = c >> 5, kb = c & 31;
-            const int d0 = w - cb0, d1 = w - cb1;
-            const bool prim = (unsigned)d0 < (unsigned)cn0, sec = (unsigned)d1 < (unsigned)cn1;
-            const int d = prim ? d0 : d1;
-            const uint4 u = prim ? U0 : U1;
-            const uint32_t mbit = (prim | sec) ? (((d ? u.z : u.x) >> kb) & 1u) : 0u;
-            const uint32_t ibit = ((d ? u.w : u.y) >> kb) & 1u;
-            const uint32_t Bm = __ballot_sync(FULL, mbit) >> r0;
-            const uint32_t Av = __ballot_sync(FULL, prim | sec) >> r0; // lanes that hold their bit at all
-            int run = (~Bm) ? __ffs(~Bm) - 1 : 32;
-            const int lim = min(32 - r0, min(i, j));
-            const bool stop_known = run < lim && ((Av >> run) & 1u); // the run ends on a cell this window holds
-            run = min(run, lim);
-            if (lane < run) opsrev[n + lane] = (uint8_t)PB_MATCH;
-            n += run; i -= run; j -= run;
-            // a fresh window that does not even hold its own first cell: the path left the frame (never for a certified goal)
-            if (cold && run == 0 && !stop_known) { redo = 1; break; }
-            cold = false;
-            if (stop_known) {
-                const uint32_t hb = __shfl_sync(FULL, ibit, r0 + run);
-                if (lane == 0) opsrev[n] = (uint8_t)(hb ? PB_INSERT : PB_DELETE);
-                ++n;
-                if (hb) --j; else --i;
-            }
+            carry = r < 32 ? __shfl_sync(FULL, ins, r) : 0;
+            if (fresh && !done && r == r_in && dk == dk_in) { redo = 1; break; } // a fresh window holds its own first cell (never reached for a certified goal)
+            i = cur_i0 - r;
+            j = i + kd + dk - Wl;
+            have = r >= 32;
         }
         cp_async_wait<0>();
         __syncwarp();
         if (redo) return;
-        if (n < guard) {
-            if (i == 0 && j > 0) { // init_cell row 0: INSERT all the way
-                for (int t = lane; t < j; t += 32) opsrev[n + t] = (uint8_t)PB_INSERT;
-                n += j;
-            } else if (j == 0 && i > 0) { // init_cell column 0: DELETE all the way
-                for (int t = lane; t < i; t += 32) opsrev[n + t] = (uint8_t)PB_DELETE;
-                n += i;
+    }
+    // i == 0: INSERT all the way along row 0; j == 0: DELETE all the way down column 0 (init_cell)
+    const int i_end = i, tail_cnt = i == 0 ? max(j, 0) : i;
+    const int tail_op = i == 0 ? PB_INSERT : PB_DELETE;
+    const int n = tail_cnt + (matlen_a - i_end) + nins;
+    if (ops_out) { // forward order: the tail, then row by row the step that enters the row and the INSERT steps along it
+        for (int q = lane; q < tail_cnt; q += 32) ops_out[q] = (uint8_t)tail_op;
+        int base = tail_cnt;
+        for (int row0 = i_end + 1; row0 <= matlen_a; row0 += 32) {
+            const int row = row0 + lane;
+            const bool valid = row <= matlen_a;
+            const uint32_t v = valid ? (uint32_t)__ldcg(rowops + row) : 0u;
+            const int cnt = valid ? 1 + (int)(v >> 1) : 0;
+            int pre = cnt; // inclusive scan over lanes
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int u = __shfl_up_sync(FULL, pre, d);
+                if (lane >= d) pre += u;
             }
+            uint8_t *dst = ops_out + base + pre - cnt;
+            if (valid) {
+                dst[0] = (uint8_t)((v & 1u) ? PB_DELETE : PB_MATCH);
+                for (int e = 1; e < cnt; ++e) dst[e] = (uint8_t)PB_INSERT;
+            }
+            base += __shfl_sync(FULL, pre, 31);
         }
     }
-    __syncwarp();
-    if (ops_out)
-        for (int k = lane; k < n; k += 32) ops_out[k] = __ldcg(opsrev + (n - 1 - k));
     res.nedit = n;
     res.ret = matlen_b;
 }

@@ -258,7 +258,8 @@ extern "C" int pb_locate_job_stats(const pb_locate_job *job, int64_t *out)
     out[3] = (int64_t)job->stats[2];
     out[4] = (int64_t)job->stats[3];
     out[5] = (int64_t)job->stats[4];
-    out[6] = out[7] = 0;
+    out[6] = (int64_t)job->stats[5];
+    out[7] = (int64_t)job->stats[6];
     return PB_OK;
 }
 

@@ -24,6 +24,13 @@
  *       [-(m - og)/2, (m + og)/2] (the walk below asserts it); the kernel checks those two numbers against the lanes it wrote.
  *   Not certified -> REDO with the full band.
  *
+ * Parents are not stored at all by the kernel's forward pass.  Per 32-row block and lane (S words of the frame) it keeps a
+ * CHECKPOINT: the lane's horizontal deltas at the top of the block (2 S words) and three 32-bit columns collected over the
+ * block's rows -- the vertical delta entering the lane's first word (+ and - bit) and the carry entering the lane's
+ * multi-word add.  With those a single thread reproduces the lane's 32 rows x S words of parents on its own (no neighbour
+ * lanes needed), and the traceback recomputes just the (block, lane) tiles the path runs through.  The model keeps the
+ * forward pass's parents only to assert that every tile the path touches is reproduced bit for bit.
+ *
  * Block-stationary frame: for the 32 rows i0..i0+31 of a block the strip is held in COLUMN coordinates -- frame bit c
  * is column j = i0 - Wl + c for the whole block -- so nothing slides per row: Eq words are word-aligned plane words,
  * there is no per-row state shift and no moving edge mask.  Between blocks the state moves down by one whole word;
@@ -118,6 +125,10 @@ int model_align(const char *a, int a_len, const char *b, int b_len, double R, in
         if ((t >> 5) < PW) plane[c * PW + (t >> 5)] |= 1u << (t & 31); /* columns no frame ever reaches are not needed */
     }
     uint32_t *par = (uint32_t *)malloc((size_t)(len_a + 1) * 2 * T * 4); /* [row][0=M,1=I][word] */
+    /* checkpoints: [block][lane]: Hp[S], Hn[S] at the top of the block; vin+ / vin- / carry-in columns (bit t = row t) */
+    const int nblk = (len_a + 31) / 32 + 1;
+    uint32_t *ck_h = (uint32_t *)calloc((size_t)nblk * 32 * 2 * S, 4);
+    uint32_t *ck_c = (uint32_t *)calloc((size_t)nblk * 32 * 3, 4);
     uint32_t Hp[512], Hn[512], Vp[512], Vn[512];
     for (int w = 0; w < T; ++w) {
         uint32_t hn = 0;
@@ -134,14 +145,24 @@ int model_align(const char *a, int a_len, const char *b, int b_len, double R, in
             for (int w = 0; w + 1 < T; ++w) { Hp[w] = Hp[w + 1]; Hn[w] = Hn[w + 1]; }
             Hp[NBw - 1] = 0xFFFFFFFFu; Hn[NBw - 1] = 0u;
         }
+        if (t == 0) /* checkpoint: the state the block's first row starts from */
+            for (int L = 0; L < 32; ++L)
+                for (int s2 = 0; s2 < S; ++s2) {
+                    ck_h[((size_t)q * 32 + L) * 2 * S + s2] = Hp[L * S + s2];
+                    ck_h[((size_t)q * 32 + L) * 2 * S + S + s2] = Hn[L * S + s2];
+                }
         int ca = code_of(a[i - 1]);
-        if (ca < 0) { free(plane); free(par); return -2; }
+        if (ca < 0) { free(plane); free(par); free(ck_h); free(ck_c); return -2; }
         const uint32_t *pl = plane + ca * PW + q;
         uint32_t carry = 0, pin = 1u, nin = 0u; /* vin = +1 at the frame's left edge */
         uint32_t *prow = par + (size_t)i * 2 * T;
         uint32_t d0diag = 0;
         for (int w = 0; w < T; ++w) {
             const uint32_t Eq = pl[w];
+            if (w % S == 0) { /* what enters lane w / S in this row */
+                uint32_t *cc = ck_c + ((size_t)q * 32 + w / S) * 3;
+                cc[0] |= pin << t; cc[1] |= nin << t; cc[2] |= carry << t;
+            }
             uint64_t s64 = (uint64_t)(Eq & Hp[w]) + Hp[w] + carry;
             carry = (uint32_t)(s64 >> 32);
             const uint32_t sum = (uint32_t)s64;
@@ -163,7 +184,7 @@ int model_align(const char *a, int a_len, const char *b, int b_len, double R, in
             cii += 1 - (int)d0diag;
             if (i > 10 && (double)cii > i * R) { /* certain: Wl, Wr >= D/2 >= floor(i*R)/2 */
                 out->fail_row = i;
-                free(plane); free(par);
+                free(plane); free(par); free(ck_h); free(ck_c);
                 return -1;
             }
             if (i == len_b) { colc = colbest = cii; col_i = i; }
@@ -187,15 +208,16 @@ int model_align(const char *a, int a_len, const char *b, int b_len, double R, in
             if (c < cost) { cost = c; matlen_b = j; }
         }
     }
-    if (cost > Wgoal) { out->redo = 1; free(plane); free(par); return -1; } /* (4): not certified */
+    if (cost > Wgoal) { out->redo = 1; free(plane); free(par); free(ck_h); free(ck_c); return -1; } /* (4): not certified */
     out->matlen_a = matlen_a; out->matlen_b = matlen_b; out->cost = cost;
     out->diag_cost = (a_len <= len_a && a_len <= len_b) ? cii : 0;
-    if ((double)matlen_b < len_b * (1 - R)) { free(plane); free(par); return -1; }
+    if ((double)matlen_b < len_b * (1 - R)) { free(plane); free(par); free(ck_h); free(ck_c); return -1; }
     int n = 0, i = matlen_a, j = matlen_b;
     /* the kernel stores parents only where a path of this cost and goal offset can be: [-(m - og)/2, (m + og)/2] */
     const int og = matlen_b - matlen_a, o_lo = -((cost - og) / 2), o_hi = (cost + og) / 2;
     uint8_t *rev = (uint8_t *)malloc((size_t)len_a + len_b + 8);
     char *rv = (char *)malloc((size_t)len_a + len_b + 8);
+    int last_q = -1, last_L = -1;
     while (i || j) {
         int op;
         if (i == 0) op = PBO_INSERT;
@@ -205,6 +227,39 @@ int model_align(const char *a, int a_len, const char *b, int b_len, double R, in
             if (c < 0 || c >= 32 * NBw) { fprintf(stderr, "certified path left the frame\n"); abort(); }
             if (j - i < o_lo || j - i > o_hi) { fprintf(stderr, "path offset %d outside [%d, %d] (cost %d, goal offset %d)\n", j - i, o_lo, o_hi, cost, og); abort(); }
             const uint32_t *prow = par + (size_t)i * 2 * T;
+            { /* the (block, lane) tile this cell lies in, recomputed from its checkpoint alone: must equal the forward pass */
+                const int q = (i - 1) >> 5, L = (c >> 5) / S;
+                if (q != last_q || L != last_L) {
+                    last_q = q; last_L = L;
+                    uint32_t hp[16], hn[16];
+                    for (int s2 = 0; s2 < S; ++s2) { hp[s2] = ck_h[((size_t)q * 32 + L) * 2 * S + s2]; hn[s2] = ck_h[((size_t)q * 32 + L) * 2 * S + S + s2]; }
+                    const uint32_t *cc = ck_c + ((size_t)q * 32 + L) * 3;
+                    for (int t2 = 0; t2 < 32 && 32 * q + t2 + 1 <= rows_max; ++t2) {
+                        const int row = 32 * q + t2 + 1;
+                        const uint32_t *pl2 = plane + code_of(a[row - 1]) * PW + q + L * S;
+                        uint32_t cy = (cc[2] >> t2) & 1u, pin2 = (cc[0] >> t2) & 1u, nin2 = (cc[1] >> t2) & 1u;
+                        const uint32_t *want = par + (size_t)row * 2 * T;
+                        for (int s2 = 0; s2 < S; ++s2) {
+                            const uint32_t Eq = pl2[s2];
+                            uint64_t s64 = (uint64_t)(Eq & hp[s2]) + hp[s2] + cy;
+                            cy = (uint32_t)(s64 >> 32);
+                            const uint32_t sum = (uint32_t)s64;
+                            const uint32_t Xv = (sum ^ hp[s2]) | Eq;
+                            const uint32_t vp = hn[s2] | ~(Xv | hp[s2]), vn = hp[s2] & Xv;
+                            const uint32_t Mm = Eq | ~(Xv | hn[s2]);
+                            const uint32_t Xh = Eq | hn[s2];
+                            const uint32_t vps = (vp << 1) | pin2, vns = (vn << 1) | nin2;
+                            pin2 = vp >> 31; nin2 = vn >> 31;
+                            hp[s2] = vns | ~(Xh | vps);
+                            hn[s2] = vps & Xh;
+                            if (Mm != want[L * S + s2] || hp[s2] != want[T + L * S + s2]) {
+                                fprintf(stderr, "tile (block %d, lane %d) row %d word %d: recomputed parents differ\n", q, L, row, s2);
+                                abort();
+                            }
+                        }
+                    }
+                }
+            }
             if ((prow[c >> 5] >> (c & 31)) & 1) op = PBO_MATCH;
             else if ((prow[T + (c >> 5)] >> (c & 31)) & 1) op = PBO_INSERT;
             else op = PBO_DELETE;
@@ -217,7 +272,7 @@ int model_align(const char *a, int a_len, const char *b, int b_len, double R, in
     for (int k = 0; k < n; ++k) { ops[k] = rev[n - 1 - k]; vals[k] = rv[n - 1 - k]; }
     out->nedit = n;
     out->ret = matlen_b;
-    free(rev); free(rv); free(plane); free(par);
+    free(rev); free(rv); free(plane); free(par); free(ck_h); free(ck_c);
     return matlen_b;
 }
 
