@@ -1021,7 +1021,7 @@ align_locate_kernel(const __grid_constant__ AlignLaunch p, const __grid_constant
 // First pass of the two-pass locate (K3n): the same item loop over align_one_nb.  An item whose result is certified gets its
 // record and redo[k] = 0; one with a candidate the strip cannot decide keeps redo[k] = 1 and is run again, from its first
 // candidate, by align_locate_kernel (full band) in the second pass.
-template <int S, bool PAIRS>
+template <int S>
 __global__ void __launch_bounds__(ALIGN_WPB * 32, MinBlocks<S>::v)
 align_locate_nb_kernel(const __grid_constant__ AlignLaunch p, const __grid_constant__ LocateView lv, const uint8_t *__restrict__ survive,
                        const int32_t *__restrict__ rej_cells, pb_locate_rec *__restrict__ recs)
@@ -1047,11 +1047,10 @@ align_locate_nb_kernel(const __grid_constant__ AlignLaunch p, const __grid_const
         const int r = lv.d_kept[k];
         const int rlen = p.A.len[r];
         const int64_t rbase = p.A.base[r];
-        const int64_t c0 = PAIRS ? lv.d_item_beg[k] : lv.d_qoff[(int64_t)k * lv.ntrial];
-        const int64_t c1 = PAIRS ? lv.d_item_end[k] : lv.d_qoff[(int64_t)(k + 1) * lv.ntrial];
-        const int T = PAIRS ? lv.d_item_ref[k] : 0;
-        const int64_t ref_base = PAIRS ? p.B.base[T] : lv.ref_base;
-        const int ref_len = PAIRS ? p.B.len[T] : lv.ref_len;
+        const int64_t c0 = lv.d_qoff[(int64_t)k * lv.ntrial];
+        const int64_t c1 = lv.d_qoff[(int64_t)(k + 1) * lv.ntrial];
+        const int64_t ref_base = lv.ref_base;
+        const int ref_len = lv.ref_len;
         long long cells = 0, k3_cells = 0, band_cells = 0, alu_rows = 0;
         int ncand = 0, nrun = 0, redo = 0;
         int tbc[2] = {0, 0}; // traceback: rounds recomputed, cold starts of the window ring
@@ -1072,7 +1071,7 @@ align_locate_nb_kernel(const __grid_constant__ AlignLaunch p, const __grid_const
                 const int q = lv.d_cand_q[cb + f];
                 const int pos = lv.d_cand_pos[cb + f];
                 CandView cv;
-                derive_views(*reinterpret_cast<const PairViews *>(&p.A), lv, PAIRS ? q : q - k * lv.ntrial, r, rlen, rbase, ref_base,
+                derive_views(*reinterpret_cast<const PairViews *>(&p.A), lv, q - k * lv.ntrial, r, rlen, rbase, ref_base,
                              ref_len, pos, false, cv);
                 align_one_nb<S>(*cv.a, cv.a_bit, cv.a_len, *cv.b, cv.b_bit, cv.b_len, p.R, p.maxn, p.maxm, p.g256, planes, p.PW, par,
                                 p.par_words, opsrev, (int)((p.slot_words - p.par_words) & ~(size_t)31), p.ops ? p.ops + p.ops_off[k] : nullptr, raw, p.RW,
@@ -1103,14 +1102,14 @@ align_locate_nb_kernel(const __grid_constant__ AlignLaunch p, const __grid_const
             p.redo[k] = (uint8_t)redo;
             if (!redo) {
                 pb_locate_rec rec;
-                rec.nseq = PAIRS ? r : k; rec.found = found ? 1 : 0;
+                rec.nseq = k; rec.found = found ? 1 : 0;
                 rec.j = found ? win_j : 0; rec.pos = found ? win_pos : 0;
                 rec.cost = found ? res.cost : 0;
                 rec.seg_len = !found ? 0 : (lv.mode == PB_MODE_LOCATE ? rlen - win_j : win_rpos);
                 rec.diag_cost = !found ? 0 : (lv.mode == PB_MODE_LOCATE ? res.diag_cost : win_dir);
                 rec.matlen_a = found ? res.matlen_a : 0; rec.matlen_b = found ? res.matlen_b : 0;
                 rec.nedit = found ? res.nedit : 0;
-                rec.ncand = ncand; rec._pad = T; rec.cells = cells;
+                rec.ncand = ncand; rec._pad = 0; rec.cells = cells;
                 recs[k] = rec;
             }
         }
@@ -1606,8 +1605,7 @@ template <int S, bool IRR> struct KernelSel {
     static const void *pairs() { return (const void *)align_pairs_kernel<S, IRR>; }
 };
 template <int S> struct NarrowSel {
-    static const void *locate() { return (const void *)align_locate_nb_kernel<S, false>; }
-    static const void *locate_pairs() { return (const void *)align_locate_nb_kernel<S, true>; }
+    static const void *locate() { return (const void *)align_locate_nb_kernel<S>; }
 };
 
 // locate: 0 = pairs of sequences (pb_align_batch), 1 = locate / overlap items, 2 = all-vs-all items
@@ -1623,7 +1621,7 @@ static const void *kernel_ptr(int key, int locate)
     }
     if (key_narrow(key)) {
         switch (key_S(key)) {
-#define CASE(s) case s: return locate == 2 ? NarrowSel<s>::locate_pairs() : NarrowSel<s>::locate();
+#define CASE(s) case s: return NarrowSel<s>::locate();
             CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
         }
@@ -1760,7 +1758,8 @@ static size_t scratch_budget(pb_ctx *ctx)
 }
 
 template <class LaunchFn>
-static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, int locate, AlignLaunch base, LaunchFn &&launch, bool spread = true)
+static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, int locate, AlignLaunch base, LaunchFn &&launch, bool spread = true,
+                       double slots_scale = 1.0)
 {
     if (plans.empty()) return PB_OK;
     const size_t budget = scratch_budget(ctx);
@@ -1779,7 +1778,7 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, int locate,
         double total_work = 0;
         for (auto &kv : plans) total_work += kv.second.work;
         const char *wenv = getenv("PB_WARPS_PER_SM"); // tuning knob: resident aligner warps per SM shared by all classes
-        const double warp_slots = (double)ctx->sm_count * (wenv ? atof(wenv) : 24.0);
+        const double warp_slots = (double)ctx->sm_count * (wenv ? atof(wenv) : 24.0) * slots_scale;
         need = 0;
         for (auto &kv : geoms) {
             const ClassPlan &cp = plans[kv.first];
@@ -1942,6 +1941,10 @@ static int build_locate_plan(pb_ctx *ctx, const std::vector<int32_t> &kept_lens,
     // 0.65 -> 6063 redone.  Whatever the value, results are exact: the certificate decides, the full band redoes the rest.
     static const int g256 = getenv("PB_NARROW_G") ? std::max(128, std::min(256, (int)(atof(getenv("PB_NARROW_G")) * 256.0))) : 192;
     lp->g256 = g256;
+    // The strip pass runs in locate mode only.  In the overlap modes the goal may lie on either side, so the strip needs the goal
+    // width on both (1.5 max_dst + 64 against the band's 2 max_dst + 1: rarely a class lower), three of four candidate alignments
+    // fail within a few blocks and the overlaps that succeed are short: measured on config 5 (all-vs-all, 50 k reads) the two
+    // passes cost 381 ms of K3 where the full band alone takes 268 ms.
     const bool both_sides = mode != PB_MODE_LOCATE;
     // the class of an item is a function of its length (and of the rare non-ACGT flag): looked up once per distinct length
     struct PerLen { int cls = INT_MIN, ncls = -1, D = 0, rows = 0; double w_full = 0, w_narrow = 0; };
@@ -1961,7 +1964,7 @@ static int build_locate_plan(pb_ctx *ctx, const std::vector<int32_t> &kept_lens,
             if (pl.cls < 0) return pb_fail(ctx, PB_ERR_DOMAIN, "band half-width %d exceeds PB_MAX_BAND", pl.D);
             // rows = len_a: the read itself (locator), or the reference view cut to len_b + max_dst (overlap, seq_aligner.h:100)
             pl.rows = std::min(mode == PB_MODE_LOCATE ? L : L + pl.D, std::max(maxn - 1, 1));
-            pl.ncls = (narrow_on && !irr) ? narrow_class_for_band(pl.D, g256, both_sides) : -1;
+            pl.ncls = (narrow_on && !irr && !both_sides) ? narrow_class_for_band(pl.D, g256, false) : -1;
             // ~instructions: rows x (per-word + per-row cost); an item of the first pass comes back only when it could not be certified
             pl.w_full = (double)L * (30.0 * key_S(pl.cls) + 60.0) * (pl.ncls < 0 ? 1.0 : 0.02);
             pl.w_narrow = pl.ncls < 0 ? 0.0 : (double)L * (16.0 * key_S(pl.ncls) + 40.0);
@@ -2044,7 +2047,9 @@ int pb_align_locate(pb_ctx *ctx, const SeqSets &ss, const LocateView &lv, int64_
         base.redo = d_redo.as<uint8_t>();
         PB_TRY(run_classes(ctx, narrow_plans, kmode, base, launch));
     }
-    return run_classes(ctx, plans, kmode, base, launch, n_narrow == 0); // a second pass stays as small as its own items need
+    // a second pass stays as small as its own items need: nearly all of them have been settled by the first, so it gets an eighth
+    // of the resident warps (and of the scratch: its slots hold stored parents, 15x the first pass's)
+    return run_classes(ctx, plans, kmode, base, launch, n_narrow == 0, n_narrow > 0 && (double)n_narrow >= 0.9 * (double)nkept ? 0.125 : 1.0);
 }
 
 int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t n, double R, int maxn, int maxm,

@@ -176,7 +176,7 @@ struct pb_index {
 
 // pb_seq.cu
 int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, const int32_t *h_len,
-                    const int32_t *h_stride, int64_t n, int src_mode, pb_seqset **out);
+                    const int32_t *h_stride, int64_t n, int src_mode, pb_seqset **out, int64_t text_bytes = -1);
 #define PB_SRC_TEXT 0     // bytes of text, element k at toff + k*stride
 #define PB_SRC_PACKED 1   // 4 bases per byte (dna_seq.h:113-127 body), first byte at toff
 #define PB_SRC_REVLINE 2  // another set's packed line, sequence read backwards; toff = its base offset (in bases)

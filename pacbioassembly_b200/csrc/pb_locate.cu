@@ -407,7 +407,7 @@ static int submit_common(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, 
         ctx->step_ev = st->ev;
         ctx->step_timed = st->timed;
         pb_timer_begin(ctx, PB_T_TOTAL);
-        r = pb_seqset_build(ctx, d_src, off, len, nullptr, n, src_mode, &st->reads);
+        r = pb_seqset_build(ctx, d_src, off, len, nullptr, n, src_mode, &st->reads, (int64_t)nbytes);
         cu(cudaEventRecord(ctx->stage_ev[slot], ctx->stream), "record"); // ingest has read the staging buffer by then
         if (r == PB_OK) r = pb_locate_run(ctx, ix, ref, ref_seq, st->reads, prm, nullptr, &st->job);
         pb_timer_end(ctx, PB_T_TOTAL);

@@ -92,6 +92,98 @@ ingest_kernel(IngestSrc src, const int64_t *__restrict__ base, const int32_t *__
     }
 }
 
+// Text input with stride +1 (the read batches of the locate path): 16 bases per thread.  A thread's granule is 16 consecutive
+// bases of the padded line -- sequences start at multiples of 32, so a granule never straddles two of them -- loaded as five
+// aligned 32-bit words of the text and re-aligned with funnel shifts; C2I (dna_seq.h:21: A, C, G -> 0, 1, 2, anything else 3) and
+// the "not one of ACGT" test are done four bytes at a time with SIMD compares; the 2-bit codes are gathered into the plane bits
+// and the packed byte by one multiplication each (the fields of the products do not overlap, so no carries).  A warp covers 512
+// bases per step and INGEST_STEPS steps: one owner search per warp, then every lane walks forward on its own.
+#define INGEST_STEPS 16
+__global__ void __launch_bounds__(256)
+ingest_text_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const int64_t *__restrict__ toff,
+                   const int64_t *__restrict__ base, const int32_t *__restrict__ len, int64_t n, int64_t nwords,
+                   uint32_t *__restrict__ hi, uint32_t *__restrict__ lo, uint32_t *__restrict__ packed, uint32_t *__restrict__ irr,
+                   uint32_t *__restrict__ flags, unsigned long long *__restrict__ nirr)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t g_first = warp * (512 * INGEST_STEPS), g_line = nwords * 32;
+    if (g_first >= g_line || n <= 0) return;
+    // sequence that owns the warp's first base: largest a with base[a] <= g_first
+    int64_t a = 0, b = n;
+    while (b - a > 1) {
+        const int64_t m = (a + b) >> 1;
+        if (__ldg(base + m) <= g_first) a = m; else b = m;
+    }
+    int64_t a_base = __ldg(base + a), a_next = __ldg(base + a + 1), a_len = __ldg(len + a), a_off = __ldg(toff + a);
+    unsigned long long bad = 0ull;
+    for (int step = 0; step < INGEST_STEPS; ++step) {
+        const int64_t g = g_first + 512 * step + 16 * lane; // first base of this lane's granule
+        if (g_first + 512 * step >= g_line) break;
+        while (a + 1 < n && g >= a_next) {
+            ++a;
+            a_base = a_next; a_next = __ldg(base + a + 1);
+            a_len = __ldg(len + a); a_off = __ldg(toff + a);
+        }
+        const int64_t rel = g - a_base;
+        const int nvalid = (int)max((int64_t)0, min((int64_t)16, a_len - rel)); // bases of the granule inside the sequence
+        uint32_t x[4] = {0x54545454u, 0x54545454u, 0x54545454u, 0x54545454u};   // 'T': code 3 and regular, like the padding
+        if (nvalid > 0 && g < g_line) {
+            const int64_t p = a_off + rel;
+            if ((p & ~(int64_t)3) + 20 <= text_bytes) { // five aligned words around [p, p + 16)
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(text + (p & ~(int64_t)3));
+                const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = __ldg(w + 4);
+                const unsigned sh = 8u * (unsigned)(p & 3);
+                x[0] = __funnelshift_r(w0, w1, sh); x[1] = __funnelshift_r(w1, w2, sh);
+                x[2] = __funnelshift_r(w2, w3, sh); x[3] = __funnelshift_r(w3, w4, sh);
+            } else { // the last bytes of the blob: one by one
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t v = 0u;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v |= (uint32_t)(4 * k + q < nvalid ? text[p + 4 * k + q] : (uint8_t)'T') << (8 * q);
+                    x[k] = v;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { // bytes past the sequence's end read 'T'
+                const int vk = nvalid - 4 * k;
+                const uint32_t keep = vk >= 4 ? 0xffffffffu : (vk <= 0 ? 0u : (1u << (8 * vk)) - 1u);
+                x[k] = (x[k] & keep) | (0x54545454u & ~keep);
+            }
+        }
+        uint32_t whi = 0u, wlo = 0u, wirr = 0u, pk = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t mA = __vcmpeq4(x[k], 0x41414141u), mC = __vcmpeq4(x[k], 0x43434343u), mG = __vcmpeq4(x[k], 0x47474747u),
+                           mT = __vcmpeq4(x[k], 0x54545454u);
+            const uint32_t code = 0x03030303u ^ ((mA & 0x03030303u) | (mC & 0x02020202u) | (mG & 0x01010101u)); // one 2-bit code per byte
+            const uint32_t odd = ~(mA | mC | mG | mT) & 0x01010101u;
+            whi |= ((((code >> 1) & 0x01010101u) * 0x01020408u) >> 24) << (4 * k); // byte q -> bit q (product bits 24..27, nothing above)
+            wlo |= (((code & 0x01010101u) * 0x01020408u) >> 24) << (4 * k);
+            wirr |= ((odd * 0x01020408u) >> 24) << (4 * k);
+            pk |= ((code * 0x40100401u) >> 24) << (8 * k); // first base of a byte in bits 7:6; bytes little-endian in the word
+        }
+        const int64_t w = g >> 5;
+        // the two granules of a 32-base word sit in neighbouring lanes: the even lane writes the plane words
+        const uint32_t ohi = __shfl_down_sync(0xffffffffu, whi, 1), olo = __shfl_down_sync(0xffffffffu, wlo, 1),
+                       oirr = __shfl_down_sync(0xffffffffu, wirr, 1);
+        if (g < g_line) {
+            packed[2 * w + (lane & 1)] = pk;
+            if (!(lane & 1)) {
+                hi[w] = whi | (ohi << 16);
+                lo[w] = wlo | (olo << 16);
+                irr[w] = wirr | (oirr << 16);
+            }
+            if (wirr) {
+                bad += (unsigned long long)__popc(wirr);
+                atomicOr(&flags[a], PB_FLAG_IRREGULAR);
+            }
+        }
+    }
+    if (bad) atomicAdd(nirr, bad);
+}
+
 // second pass, only when the set holds bytes outside {A,C,G,T}: list them as (line position, byte)
 __global__ void __launch_bounds__(256)
 collect_exceptions_kernel(IngestSrc src, const int64_t *__restrict__ base, const int32_t *__restrict__ len, int64_t n,
@@ -120,7 +212,7 @@ collect_exceptions_kernel(IngestSrc src, const int64_t *__restrict__ base, const
 }
 
 int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, const int32_t *h_len,
-                    const int32_t *h_stride, int64_t n, int src_mode, pb_seqset **out)
+                    const int32_t *h_stride, int64_t n, int src_mode, pb_seqset **out, int64_t text_bytes)
 {
     pb_seqset *s = new pb_seqset();
     s->ctx = ctx;
@@ -167,11 +259,20 @@ int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, cons
     src.packed = src_mode;
     int64_t blocks = std::min<int64_t>(((nw + INGEST_RUN - 1) / INGEST_RUN + 7) / 8, (int64_t)ctx->sm_count * 16);
     if (blocks < 1) blocks = 1;
+    bool forward = true; // every view reads its text left to right
+    for (int64_t i = 0; h_stride && forward && i < n; ++i) forward = h_stride[i] == 1;
     pb_timer_begin(ctx, PB_T_INGEST);
-    ingest_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(src, s->d_base.as<int64_t>(), s->d_len.as<int32_t>(), n, nw,
-                                                             s->d_hi.as<uint32_t>(), s->d_lo.as<uint32_t>(),
-                                                             s->d_packed.as<uint32_t>(), s->d_irr.as<uint32_t>(),
-                                                             s->d_flags.as<uint32_t>(), d_nirr.as<unsigned long long>());
+    if (src_mode == PB_SRC_TEXT && forward && text_bytes >= 0 && n > 0 && (reinterpret_cast<uintptr_t>(d_text) & 3) == 0) {
+        const int64_t warps = (nw * 32 + 512 * INGEST_STEPS - 1) / (512 * INGEST_STEPS);
+        ingest_text_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, ctx->stream>>>(
+            (const uint8_t *)d_text, text_bytes, d_toff.as<int64_t>(), s->d_base.as<int64_t>(), s->d_len.as<int32_t>(), n, nw,
+            s->d_hi.as<uint32_t>(), s->d_lo.as<uint32_t>(), s->d_packed.as<uint32_t>(), s->d_irr.as<uint32_t>(),
+            s->d_flags.as<uint32_t>(), d_nirr.as<unsigned long long>());
+    } else
+        ingest_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(src, s->d_base.as<int64_t>(), s->d_len.as<int32_t>(), n, nw,
+                                                                 s->d_hi.as<uint32_t>(), s->d_lo.as<uint32_t>(),
+                                                                 s->d_packed.as<uint32_t>(), s->d_irr.as<uint32_t>(),
+                                                                 s->d_flags.as<uint32_t>(), d_nirr.as<unsigned long long>());
     pb_timer_end(ctx, PB_T_INGEST);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
@@ -266,7 +367,7 @@ extern "C" int pb_seqset_from_text(pb_ctx *ctx, const char *text, const int64_t 
     pb_timer_end(ctx, PB_T_H2D);
     std::vector<int64_t> rel(off, off + n);
     for (auto &x : rel) x -= lo;
-    return pb_seqset_build(ctx, d_text.p, rel.data(), len, stride, n, PB_SRC_TEXT, out);
+    return pb_seqset_build(ctx, d_text.p, rel.data(), len, stride, n, PB_SRC_TEXT, out, (hi - lo) + 16);
 }
 
 extern "C" int pb_seqset_from_device_text(pb_ctx *ctx, const void *d_text, size_t text_bytes, const int64_t *off,
@@ -278,7 +379,7 @@ extern "C" int pb_seqset_from_device_text(pb_ctx *ctx, const void *d_text, size_
     int64_t lo, hi;
     if (!text_extent(off, len, stride, n, &lo, &hi)) return pb_fail(ctx, PB_ERR_ARG, "stride must be +1 or -1");
     if (lo < 0 || (size_t)hi > text_bytes) return pb_fail(ctx, PB_ERR_ARG, "views reach outside the device text blob");
-    return pb_seqset_build(ctx, d_text, off, len, stride, n, PB_SRC_TEXT, out);
+    return pb_seqset_build(ctx, d_text, off, len, stride, n, PB_SRC_TEXT, out, (int64_t)text_bytes);
 }
 
 extern "C" int pb_seqset_from_bin(pb_ctx *ctx, const uint8_t *bin, size_t nbytes, int min_excl, int max_excl,

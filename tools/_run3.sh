@@ -1,1 +1,1 @@
-PB_LIB=build/exp/libpb_dbg.so python tools/profile_step.py 3000 1 4200 5000 > gpurun_out/dbg.log 2>&1; grep -a -c "round:" gpurun_out/dbg.log; head -c 1500 gpurun_out/dbg.log; grep -a "round:\|cold exit" gpurun_out/dbg.log | head -90
+PB_HOST_TRACE=1 python tools/pipe_probe.py 100000 5 text 2>&1 | tail -40 | cut -c1-250
