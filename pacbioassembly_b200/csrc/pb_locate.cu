@@ -175,6 +175,7 @@ extern "C" int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *r
     // kept reads: len >= minlen, nseq = rank among kept (locator.cpp:72, SURVEY Q-L1)
     std::vector<int32_t> kept, kept_lens;
     std::vector<uint8_t> kept_irr;
+    kept.reserve((size_t)reads->n); kept_lens.reserve((size_t)reads->n); kept_irr.reserve((size_t)reads->n);
     const bool ref_irr = (ref->flags[ref_seq] & PB_FLAG_IRREGULAR) != 0;
     for (int64_t i = 0; i < reads->n; ++i)
         if (reads->len[i] >= prm->minlen) {

@@ -277,11 +277,14 @@ int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, cons
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { delete s; return pb_fail(ctx, PB_ERR_CUDA, "ingest launch failed: %s", cudaGetErrorString(e)); }
-    s->flags.resize(n);
+    s->flags.assign((size_t)n, 0u);
     unsigned long long nirr = 0;
-    TRYS(pb_d2h(ctx, s->flags.data(), s->d_flags.p, n * sizeof(uint32_t)));
     TRYS(pb_d2h(ctx, &nirr, d_nirr.p, 8));
-    TRYS(pb_sync(ctx)); // d_toff/d_stride are released after the kernel (stream-ordered) but flags are needed now
+    TRYS(pb_sync(ctx)); // d_toff/d_stride are released after the kernel (stream-ordered) but the count is needed now
+    if (nirr > 0) { // the per-sequence flags only say something when a byte outside {A,C,G,T} was seen
+        TRYS(pb_d2h(ctx, s->flags.data(), s->d_flags.p, n * sizeof(uint32_t)));
+        TRYS(pb_sync(ctx));
+    }
     s->tab.assign((size_t)n, 0x41414141u); // unused slots hold 'A': a value the exception list never contains
     s->tab_count.assign((size_t)n, 0);
     if (nirr > 0 && src_mode == PB_SRC_TEXT) {
