@@ -100,14 +100,13 @@ def make_workload(nreads: int, rank: int):
 
 
 def source_sha() -> str:
-    """digest of the kernel sources: ties a committed ncu capture to the code it was taken with"""
+    """digest of the aligner's kernel sources: ties a committed ncu capture of K3 to the code it was taken with"""
     import hashlib
     h = hashlib.sha1()
     d = os.path.join(ROOT, "pacbioassembly_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh")):
-            with open(os.path.join(d, f), "rb") as fh:
-                h.update(fh.read())
+    for f in ("pb_align.cu", "pb_align_nb.cuh", "pb_internal.cuh"):
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(fh.read())
     return h.hexdigest()[:16]
 
 

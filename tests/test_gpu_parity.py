@@ -559,6 +559,32 @@ def test_locate_strip_redo_paths(ctx, oracle):
     job.free(); s.free()
 
 
+def test_locate_traceback_rounds_all_classes(ctx, oracle):
+    """The strip pass stores no parents: its traceback recomputes (block, lane) tiles from checkpoints, 32 per round, around the
+    path's predicted diagonal.  Reads of every strip class (600 .. 19 000 bases), insertion-heavy, deletion-heavy and balanced --
+    the path drifts one way, the other, or wanders -- with transcripts compared op for op against the oracle."""
+    ref = workload.reference(2, 600_000)
+    parts_t, parts_o, parts_l = [], [], []
+    pos = 0
+    for seed, (pi, pd, ps) in enumerate(((0.14, 0.02, 0.01), (0.02, 0.14, 0.01), (0.07, 0.07, 0.02), (0.01, 0.01, 0.01))):
+        lens = np.array([600, 1500, 2500, 2600, 3000, 5200, 5300, 6000, 9000, 12000, 15000, 19000], dtype=np.int32)
+        t, o, l, _ = workload.reads(300 + seed, ref, lens, pi, pd, ps)
+        parts_t.append(t); parts_o.append(o + pos); parts_l.append(l)
+        pos += len(t)
+    txt, offs, lens = np.concatenate(parts_t), np.concatenate(parts_o), np.concatenate(parts_l)
+    recs = locate_vs_oracle(ctx, oracle, ref, txt, offs, lens, MASKS[0], 0.3, nthreads=16)
+    assert recs["found"].sum() >= 24
+    rs = ctx.seqset_one(ref)
+    ix = ctx.index(rs, MASKS[0])
+    s = ctx.seqset(txt, offs, lens)
+    job = ctx.locate_run(ix, s, R=0.3)
+    job.fetch()
+    st = job.stats()
+    if os.environ.get("PB_NARROW", "1") != "0":
+        assert st["tb_rounds"] >= recs["found"].sum() and st["tb_cold"] >= st["tb_rounds"]  # the checkpointed traceback ran
+    job.free(); s.free()
+
+
 def test_traceback_prefetch_stress(ctx, oracle):
     """The traceback's asynchronous window ring (cp.async into shared memory) once faulted on zero-fill copies with a dummy
     source -- only where prefetched windows reach above row 1, i.e. on SHORT alignments.  Short and long

@@ -1,1 +1,1 @@
-PB_HOST_TRACE=1 python tools/pipe_probe.py 100000 5 text 2>&1 | tail -40 | cut -c1-250
+python tools/allpairs_bench.py > gpurun_out/r02m_allpairs_config5_n1.log 2>&1; tail -3 gpurun_out/r02m_allpairs_config5_n1.log | cut -c1-300
