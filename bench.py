@@ -166,7 +166,7 @@ def run_reference(args, rank: int, world: int):
         return
     ref, txt, offs, lens = make_workload(args.reads, 0)
     nthreads = min(os.cpu_count() or 1, args.cpu_threads)
-    sample = args.cpu_sample or 12 * nthreads
+    sample = args.cpu_sample or 48 * nthreads
     times = []
     cpu = CpuReference(ref)
     kind = cpu.kind
@@ -415,7 +415,7 @@ def main():
     int_ach = float(np.mean(alu_instr)) / (k3_ms / 1e3)
     int_pipe = {"achieved_warp_instr_s": int_ach, "peak_warp_instr_s": int_peak, "frac": int_ach / int_peak if int_peak else None,
                 "achieved_ops_s": 32.0 * int_ach, "peak_ops_s": 32.0 * int_peak,
-                "how": "achieved = integer-ALU warp instructions of K3's row loops (11 per band word + 14 per row in the strip pass, "
+                "how": "achieved = integer-ALU warp instructions of K3's row loops (11 per band word + 12 per row in the strip pass, "
                        "19 + 23 in the full-band pass, counted in the SASS) / K3 time; peak = pb_int_pipe_peak, a register-only "
                        "LOP3/SHF kernel timed on this GPU in this run"}
 
@@ -451,7 +451,7 @@ def main():
     parity = None
     if rank == 0 and not args.no_cpu:  # every N: rank 0 checks a sample of ITS shard against the reference on the host
         nthreads = min(os.cpu_count() or 1, args.cpu_threads)
-        sample = args.cpu_sample or 12 * nthreads
+        sample = args.cpu_sample or 48 * nthreads
         cr = CpuReference(ref)
         rps, crecs, ids, dt = cr.run(txt, offs, lens, sample, nthreads)
         cr.close()

@@ -385,7 +385,7 @@ typedef struct {
     const pbo_index *ix;
     const char *ref; size_t ref_len;
     const char *reads; const int64_t *offs; const int32_t *lens;
-    const int64_t *kept; int64_t k0, k1; /* kept-read range of this thread */
+    const int64_t *kept; int64_t *next, nk; /* threads take the next kept read from a shared counter */
     uint32_t mask; double R; int ntrial, maxn, maxm;
     pbo_locate_rec *recs;
     uint8_t *ops_out; const int64_t *ops_off;
@@ -396,7 +396,9 @@ static void *locate_thread(void *arg)
     locate_job *jb = (locate_job *)arg;
     dp_ws ws = {0, 0, 0};
     uint8_t *ops = NULL; size_t ops_cap = 0;
-    for (int64_t k = jb->k0; k < jb->k1; ++k) {
+    for (;;) {
+        const int64_t k = __atomic_fetch_add(jb->next, 1, __ATOMIC_RELAXED);
+        if (k >= jb->nk) break;
         int64_t r = jb->kept[k];
         const char *seq = jb->reads + jb->offs[r];
         int len = jb->lens[r];
@@ -449,12 +451,12 @@ int64_t pbo_locate(const pbo_index *ix, const char *ref, size_t ref_len,
     if ((int64_t)nthreads > nk) nthreads = nk > 0 ? (int)nk : 1;
     locate_job *jobs = (locate_job *)calloc((size_t)nthreads, sizeof *jobs);
     pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof *th);
-    /* interleaved-contiguous split balanced by count (reads are iid in the benchmarks) */
+    int64_t next = 0; /* dynamic schedule: read lengths vary 40-fold, a static split leaves threads idle */
     for (int t = 0; t < nthreads; ++t) {
         locate_job *jb = &jobs[t];
         jb->ix = ix; jb->ref = ref; jb->ref_len = ref_len;
         jb->reads = reads; jb->offs = offs; jb->lens = lens; jb->kept = kept;
-        jb->k0 = nk * t / nthreads; jb->k1 = nk * (t + 1) / nthreads;
+        jb->next = &next; jb->nk = nk;
         jb->mask = mask; jb->R = R; jb->ntrial = ntrial; jb->maxn = maxn; jb->maxm = maxm;
         jb->recs = recs; jb->ops_out = ops_out; jb->ops_off = ops_off;
         if (nthreads == 1) locate_thread(jb);

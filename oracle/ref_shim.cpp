@@ -166,7 +166,7 @@ struct locate_rec { /* mirrors pbo_locate_rec */
 struct locate_job {
     const hash_table *map; char *contig; long contig_len;
     const char *reads; const int64_t *offs; const int32_t *lens; const int64_t *kept;
-    int64_t k0, k1; unsigned mask; double R; int ntrial;
+    int64_t *next, nk; unsigned mask; double R; int ntrial; /* threads take the next kept read from a shared counter */
     locate_rec *recs; uint8_t *ops_out; const int64_t *ops_off;
 };
 
@@ -175,7 +175,9 @@ static void *locate_thread(void *arg)
     locate_job *jb = (locate_job *)arg;
     loc_aligner *al = fresh_aligner<loc_aligner>(jb->R);
     char *sequence = (char *)malloc(40000 + 64);
-    for (int64_t k = jb->k0; k < jb->k1; ++k) {
+    for (;;) {
+        const int64_t k = __atomic_fetch_add(jb->next, 1, __ATOMIC_RELAXED);
+        if (k >= jb->nk) break;
         int64_t r = jb->kept[k];
         int len = jb->lens[r];
         locate_rec *rec = &jb->recs[k];
@@ -252,11 +254,12 @@ int64_t pbref_locator_run(void *h, const char *reads, const int64_t *offs, const
     if ((int64_t)nthreads > nk) nthreads = nk > 0 ? (int)nk : 1;
     locate_job *jobs = (locate_job *)calloc((size_t)nthreads, sizeof *jobs);
     pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof *th);
+    int64_t next = 0; /* dynamic schedule: read lengths vary 40-fold, a static split leaves threads idle */
     for (int t = 0; t < nthreads; ++t) {
         locate_job *jb = &jobs[t];
         jb->map = st->map; jb->contig = st->contig; jb->contig_len = st->len;
         jb->reads = reads; jb->offs = offs; jb->lens = lens; jb->kept = kept;
-        jb->k0 = nk * t / nthreads; jb->k1 = nk * (t + 1) / nthreads;
+        jb->next = &next; jb->nk = nk;
         jb->mask = st->mask; jb->R = R; jb->ntrial = ntrial;
         jb->recs = recs; jb->ops_out = ops_out; jb->ops_off = ops_off;
         if (nthreads == 1) locate_thread(jb);

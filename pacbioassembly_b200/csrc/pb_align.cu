@@ -344,6 +344,14 @@ __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, int 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// a * b + c on the FMA pipe (IMAD) where the integer pipe is the bound
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
 // multi-word add helpers: the carry chain lives in the PTX condition code between consecutive statements
 __device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b)
 {
@@ -1094,7 +1102,7 @@ align_locate_nb_kernel(const __grid_constant__ AlignLaunch p, const __grid_const
         if (lane == 0) {
             if (p.stats) { // what the strip computed counts even when the item has to be redone
                 atomicAdd(p.stats + 2, (unsigned long long)band_cells);
-                atomicAdd(p.stats + 4, (unsigned long long)alu_rows * (11ull * S + 14ull)); // SASS of align_locate_nb_kernel<S>: 11 per word + 14 per row
+                atomicAdd(p.stats + 4, (unsigned long long)alu_rows * (11ull * S + 12ull)); // SASS of align_locate_nb_kernel<S>: 11 per word + 12 per row
                 if (redo) atomicAdd(p.stats + 3, 1ull);
                 else { atomicAdd(p.stats, (unsigned long long)k3_cells); atomicAdd(p.stats + 1, (unsigned long long)nrun); }
                 if (tbc[0]) { atomicAdd(p.stats + 5, (unsigned long long)tbc[0]); atomicAdd(p.stats + 6, (unsigned long long)tbc[1]); }

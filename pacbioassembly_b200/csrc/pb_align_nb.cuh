@@ -29,6 +29,10 @@
 // asserts that every tile a path touches is reproduced bit for bit.
 #pragma once
 
+#ifndef PB_NB_UNROLL
+#define PB_NB_UNROLL 4 // rows of a full block per trip of the row loop (A/B on config 2: 2 -> 45.3 ms of K3, 4 -> 45.0, 8 -> 45.5, 16 -> 50.0, 32 -> 49.0: the instruction cache)
+#endif
+constexpr int NB_UNROLL = PB_NB_UNROLL;
 #ifndef PB_NB_RING
 #define PB_NB_RING 3 // traceback windows in flight in the strip pass (A/B on config 2: 3 -> 57.0 ms, 4 -> 57.9, 6 -> 61.0 of K3)
 #endif
@@ -80,7 +84,7 @@ __host__ __device__ inline int nb_target(int D, int g256) { return (int)(((long 
 
 // One row of the stationary frame for the S words of this lane.  pl: this lane's first Eq word of the row's plane (word
 // aligned with the frame).  vinp / vinn / cina collect what enters the lane in this row (see the checkpoint above): the vertical
-// deltas shift in from the right (row t of an n-row block ends at bit n-1-t), the carry from the left (bit 32-n+t).
+// deltas and the carry shift in from the right (row t of an n-row block ends at bit n-1-t).
 // Returns the D0 word of slot 0.
 template <int S>
 __device__ __forceinline__ uint32_t row_step_nb(uint32_t (&Hp)[S], uint32_t (&Hn)[S], uint32_t (&Vp)[S], uint32_t (&Vn)[S],
@@ -99,9 +103,9 @@ __device__ __forceinline__ uint32_t row_step_nb(uint32_t (&Hp)[S], uint32_t (&Hn
     for (int s = 1; s < S; ++s) ones &= sum[s];
     const uint32_t G = __ballot_sync(FULL, carry);
     const uint32_t P = __ballot_sync(FULL, ones == 0xffffffffu);
-    const uint32_t cw = (((G | P) + G) ^ P) >> lane; // bit 0: the carry into this lane's block of S words
-    cina = __funnelshift_r(cina, cw, 1);
-    sum[0] = add_cc(sum[0], cw & 1u);
+    const uint32_t cin = ((((G | P) + G) ^ P) >> lane) & 1u; // the carry into this lane's block of S words
+    cina = mad_lo(cina, 2u, cin); // an IMAD: the FMA pipe is idle, the integer pipe is the bound
+    sum[0] = add_cc(sum[0], cin);
 #pragma unroll
     for (int s = 1; s < S; ++s) sum[s] = addc_cc(sum[s], 0u);
 
@@ -282,12 +286,22 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
         const int tfast = max(0, min(32, nfast - i0 + 1)); // rows of this block with an early-failure test
         const int tall = min(32, rows_max - i0 + 1);
         if (tfast > 0) {
-            uint32_t hist = 0u, tb1 = 1u;
-            for (int t = 0; t < tfast; ++t) {
-                const int off = __shfl_sync(FULL, my_off, t);
-                const uint32_t d0w = row_step_nb<S>(Hp, Hn, Vp, Vn, plq + off, lane, lane0, vinp, vinn, cina);
-                hist |= d0w & tb1; // row t's diagonal D0 bit is bit t of slot 0 in the diagonal's owner lane
-                tb1 <<= 1;
+            uint32_t hist = 0u;
+            if (tfast == 32) { // a full block: unrolled, the diagonal bit's mask is an immediate
+#pragma unroll NB_UNROLL
+                for (int t = 0; t < 32; ++t) {
+                    const int off = __shfl_sync(FULL, my_off, t);
+                    const uint32_t d0w = row_step_nb<S>(Hp, Hn, Vp, Vn, plq + off, lane, lane0, vinp, vinn, cina);
+                    hist |= d0w & (1u << t); // row t's diagonal D0 bit is bit t of slot 0 in the diagonal's owner lane
+                }
+            } else {
+                uint32_t tb1 = 1u;
+                for (int t = 0; t < tfast; ++t) {
+                    const int off = __shfl_sync(FULL, my_off, t);
+                    const uint32_t d0w = row_step_nb<S>(Hp, Hn, Vp, Vn, plq + off, lane, lane0, vinp, vinn, cina);
+                    hist |= d0w & tb1;
+                    tb1 <<= 1;
+                }
             }
             hist = __shfl_sync(FULL, hist, Ld);
             const int thr = (int)((i0 + lane) * R); // cost > i*R  <=>  cost > floor(i*R)
@@ -446,7 +460,7 @@ __device__ __forceinline__ void align_one_nb(const SeqView &A, int64_t a_bit, in
             // row t's entering deltas on top (<< t brings them to bit 31), its carry at bit t
             vp = __ldcg(ckb + (2 * S) * 32) << (32 - nr);
             vn = __ldcg(ckb + (2 * S + 1) * 32) << (32 - nr);
-            cc = __ldcg(ckb + (2 * S + 2) * 32) >> (32 - nr);
+            cc = __brev(__ldcg(ckb + (2 * S + 2) * 32) << (32 - nr));
             awh = load_window(A.hi, A.nwords, a_bit + 32 * qq);
             awl = load_window(A.lo, A.nwords, a_bit + 32 * qq);
         }
