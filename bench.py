@@ -51,20 +51,49 @@ def log(*a):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe), sampled every 200 ms.  NVML is asked
+    directly from a thread of this process; a looping nvidia-smi (the fallback when NVML cannot be loaded) takes driver locks
+    long enough to stretch one aligner step in ten by ~5 ms."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.stop_flag, self.thread, self.how = index, [], None, False, None, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = (("hw_slowdown", pynvml.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", pynvml.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", pynvml.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", pynvml.nvmlClocksEventReasonSwPowerCap))
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        self.rows.append([str(sm), str(mx), "0"] + ["Active" if mask & bit else "Not Active" for _, bit in names])
+                    except Exception:
+                        pass
+                    time.sleep(0.2)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.how = "nvml"
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            self.how = "nvidia-smi"
         except Exception:
             self.proc = None
 
@@ -73,10 +102,11 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self) -> dict:
+        self.stop_flag = True
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        for r in list(self.rows):
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -86,7 +116,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "how": self.how}
 
 
 def make_workload(nreads: int, rank: int):
@@ -325,6 +355,8 @@ def main():
             pipe["prev"] = None
         return pipe["tot"]
 
+    walls = []  # host wall time of every call inside the last timed region (ms): shows where a region lost time
+
     def timed(fn, warmup, steps, collect=None, drain=None):
         for _ in range(warmup):
             fn()
@@ -336,12 +368,17 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ctx.launches
         e0.record(stream)
+        walls.clear()
+        tw = time.perf_counter()
         for _ in range(steps):
             out = fn()
             if collect is not None:
                 collect()
+            walls.append(round(1e3 * (time.perf_counter() - tw), 2))
+            tw = time.perf_counter()
         if drain is not None:
             drain()  # the last step in flight is collected inside the timed region
+            walls.append(round(1e3 * (time.perf_counter() - tw), 2))
         out = reducer.finish()  # the last exchange is joined inside the timed region; the summed counters are the step's result
         e1.record(stream)
         barrier()
@@ -362,10 +399,41 @@ def main():
         redone.append(state["stats"]["redone"])
         stage.append(dict(state["timings"]))
 
-    ms_dev, tot_dev, launches = timed(step_device, args.warmup, args.steps, collect)
-    log(f"[rank {rank}] host wall per timed device-leg step (ms): " + ", ".join(f"{k} {1e3 * v / max(phase_s['n'], 1):.1f}" for k, v in phase_s.items() if k != "n") + "\n")
-    state["recs"] = state["recs"].copy()  # the device leg's records (recs_host is reused by the e2e legs)
+    # device leg: the same batches with their text resident in HBM, streamed through the pipelined entry points
+    # (pb_locate_submit_device / pb_locate_collect: no copy in, records out); K steps and the drain inside the timed region.
+    # The strictly serial call sequence (seqset -> locate_run -> fetch, the GPU idle while the host plans) is timed beside it.
+    dpipe = {"prev": None, "tot": None}
+
+    def collect_device(step):
+        reducer.wait()
+        recs = step.collect(recs=recs_host)
+        state["stats"], state["timings"], state["recs"] = step.stats, ctx.timings(), recs
+        collect()
+        dpipe["tot"] = final_reduction(recs)
+
+    def step_device_pipe():
+        cur = ctx.locate_submit_device(index, d_txt.data_ptr(), d_txt.numel(), offs, lens, R=R)
+        if dpipe["prev"] is not None:
+            collect_device(dpipe["prev"])
+        dpipe["prev"] = cur
+        return dpipe["tot"]
+
+    def drain_device():
+        if dpipe["prev"] is not None:
+            collect_device(dpipe["prev"])
+            dpipe["prev"] = None
+        return dpipe["tot"]
+
+    ms_dev, tot_dev, launches = timed(step_device_pipe, args.warmup, args.steps, drain=drain_device)
+    dev_walls = list(walls)
+    for lst in (align_ms, dp_cells, band_cells, alu_instr, redone, stage):
+        del lst[:-args.steps]  # the timed steps are the last K collected
+    dev_recs = state["recs"].copy()  # the device leg's records (recs_host is reused by the other legs)
+    ms_serial, _, _ = timed(step_device, 2, args.steps)
+    state["recs"] = dev_recs
+    log(f"[rank {rank}] host wall per serial device-leg step (ms): " + ", ".join(f"{k} {1e3 * v / max(phase_s['n'], 1):.1f}" for k, v in phase_s.items() if k != "n") + "\n")
     ms_e2e, tot_e2e, _ = timed(step_e2e, max(3, args.warmup), args.steps, drain=drain_e2e)
+    e2e_walls = list(walls)
     log(f"[rank {rank}] host wall per e2e step (ms): " + ", ".join(f"{k} {1e3 * v / max(e2e_host['n'], 1):.1f}" for k, v in e2e_host.items() if k != "n"))
     e2e_same = bool((state["e2e_recs"] == state["recs"]).all()) if "e2e_recs" in state else None
     e2e_stage = state.get("e2e_timings")
@@ -498,6 +566,7 @@ def main():
                            "collected, so its host->device copy runs under step k's alignment; every step's records are "
                            "copied back and reduced inside the timed region",
                     "stage_ms": e2e_stage,
+                    "call_wall_ms": e2e_walls,  # host wall of each step's submit+collect (and of the final drain) in the timed region
                     "bin_input": None if ms_bin is None else {
                         "value": total_reads / (ms_bin / 1e3), "ms_per_step": ms_bin,
                         "h2d_bytes_per_step": int(len(bin_image["buf"])), "records_equal_device_leg": bin_same,
@@ -508,6 +577,7 @@ def main():
                                    "certified strip pass then full-band pass for what it could not certify)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel_ms_per_step": [round(float(x), 2) for x in align_ms],
                          "peak_source": peak_src,
                          "algorithmic": "0.25 B (2 parent bits) per band cell K3 computes (strip width x rows, summed over the "
                                         "alignments it ran)",
@@ -522,6 +592,12 @@ def main():
                              "algorithmic": "0.25 B read + 4 B written per position, every position of the read set"},
             "probe_bulk": probe,
             "stage_ms": t,
+            "device_leg": {"how": "text resident in HBM, pb_locate_submit_device / pb_locate_collect: step k+1 is queued before "
+                                  "step k is collected; K steps and the drain inside the timed region, every step's records "
+                                  "copied back and reduced", "call_wall_ms": dev_walls,
+                           "serial": {"ms_per_step": ms_serial, "value": total_reads / (ms_serial / 1e3),
+                                      "how": "pb_seqset_from_device_text -> pb_locate_run -> pb_locate_fetch, one after the "
+                                             "other: the GPU idles while the host plans and reduces"}},
             "mapped_reads": int(tot_dev[0]), "kept_reads": total_reads, "sum_cost": int(tot_dev[1]),
             "ref_equiv_cells": int(tot_dev[2]),
             "cpu_baseline": cpu,

@@ -276,6 +276,11 @@ PB_API int pb_locate_submit(pb_ctx *ctx, const pb_index *ix, const pb_seqset *re
                             pb_locate_step **step);
 PB_API int pb_locate_submit_bin(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const uint8_t *bin,
                                 size_t nbytes, int min_excl, int max_excl, const pb_locate_params *prm, pb_locate_step **step);
+/* the same for a batch whose text is already in device memory (as pb_seqset_from_device_text takes it): no staging copy; the
+ * caller keeps d_text alive until the step has been collected */
+PB_API int pb_locate_submit_device(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const void *d_text,
+                                   size_t text_bytes, const int64_t *off, const int32_t *len, int64_t nreads,
+                                   const pb_locate_params *prm, pb_locate_step **step);
 PB_API int64_t pb_locate_step_nkept(const pb_locate_step *step);
 PB_API int64_t pb_locate_step_ops_extent(const pb_locate_step *step);
 /* out[8] as pb_locate_job_stats; timings[PB_T_COUNT] (may be NULL) = this step's stage times as pb_ctx_timings */

@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
         "pb_locate_job_free": (None, [vp]),
         "pb_locate_submit": (C.c_int, [vp, vp, vp, i64, vp, vp, vp, i64, P(LocateParams), P(vp)]),
         "pb_locate_submit_bin": (C.c_int, [vp, vp, vp, i64, vp, sz, C.c_int, C.c_int, P(LocateParams), P(vp)]),
+        "pb_locate_submit_device": (C.c_int, [vp, vp, vp, i64, vp, sz, vp, vp, i64, P(LocateParams), P(vp)]),
         "pb_locate_step_nkept": (i64, [vp]),
         "pb_locate_step_ops_extent": (i64, [vp]),
         "pb_locate_collect": (C.c_int, [vp, vp, vp, P(i64), vp, vp]),
@@ -426,6 +427,17 @@ class Context:
                                             C.byref(prm), C.byref(h)))
         return LocateStep(self, h, keep=(t, offs, lens))
 
+    def locate_submit_device(self, index: "Index", dptr: int, nbytes: int, offs, lens, **params) -> "LocateStep":
+        """Pipelined locate of a batch whose text already lies in device memory (dptr, e.g. a torch tensor's data_ptr):
+        no staging copy; the caller keeps the buffer alive until the step is collected."""
+        prm = default_locate_params(**params)
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        h = C.c_void_p()
+        self.check(self._L.pb_locate_submit_device(self.h, index.h, index.ref.h, index.seq, C.c_void_p(dptr), nbytes, _ptr(offs),
+                                                   _ptr(lens), len(lens), C.byref(prm), C.byref(h)))
+        return LocateStep(self, h, keep=(offs, lens))
+
     def locate_submit_bin(self, index: "Index", image, **params) -> "LocateStep":
         """Pipelined locate of a batch given as a .bin image (binary_test.cpp:55-63); records of len >= minlen are kept."""
         prm = default_locate_params(**params)
@@ -696,7 +708,7 @@ class LocateStep:
         h, self.h = self.h, None
         self.ctx.check(self.ctx._L.pb_locate_collect(self.ctx.h, h, _ptr(recs), C.byref(got), None, _ptr(out)))
         self.stats = {"ncand": int(out[0]), "dp_alignments": int(out[1]), "dp_cells": int(out[2]), "band_cells": int(out[3]),
-                      "redone": int(out[4]), "alu_instr": int(out[5])}
+                      "redone": int(out[4]), "alu_instr": int(out[5]), "tb_rounds": int(out[6]), "tb_cold": int(out[7])}
         self._keep = ()
         return recs[: got.value]
 

@@ -356,10 +356,11 @@ extern "C" void pb_locate_step_free(pb_locate_step *st)
     delete st;
 }
 
-// h_src: the batch as the host holds it (text blob or .bin image); off/len: where each sequence starts in it
+// h_src: the batch as the host holds it (text blob or .bin image); off/len: where each sequence starts in it.
+// on_device: h_src is device memory the caller keeps alive until the step is collected -- no staging buffer, no copy
 static int submit_common(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const void *h_src, size_t nbytes,
                          const int64_t *off, const int32_t *len, int64_t n, int src_mode, const pb_locate_params *prm,
-                         pb_locate_step **out)
+                         pb_locate_step **out, bool on_device = false)
 {
     *out = nullptr;
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -381,9 +382,11 @@ static int submit_common(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, 
     }
     // the batch lands in one of the context's two staging buffers (no allocation on the pipelined path)
     const int slot = ctx->stage_next;
-    ctx->stage_next ^= 1;
+    if (!on_device) ctx->stage_next ^= 1;
     if (r == PB_OK && !ctx->stage_ev[slot]) cu(cudaEventCreateWithFlags(&ctx->stage_ev[slot], cudaEventDisableTiming), "event");
-    if (r == PB_OK && ctx->stage_bytes[slot] < nbytes + 16) {
+    if (on_device) {
+        d_src = const_cast<void *>(h_src);
+    } else if (r == PB_OK && ctx->stage_bytes[slot] < nbytes + 16) {
         if (ctx->stage[slot]) {
             cu(cudaEventSynchronize(ctx->stage_ev[slot]), "wait for the staging buffer");
             cudaFree(ctx->stage[slot]);
@@ -396,8 +399,8 @@ static int submit_common(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, 
     } else if (r == PB_OK && ctx->stage[slot]) {
         cu(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_ev[slot], 0), "wait"); // its previous batch has been ingested
     }
-    d_src = ctx->stage[slot];
-    if (r == PB_OK) {
+    if (!on_device) d_src = ctx->stage[slot];
+    if (r == PB_OK && !on_device) {
         cu(cudaEventRecord(st->ev[2 * PB_T_H2D], ctx->copy_stream), "record");
         cu(cudaMemcpyAsync(d_src, h_src, nbytes, cudaMemcpyHostToDevice, ctx->copy_stream), "host->device copy");
         cu(cudaEventRecord(st->ev[2 * PB_T_H2D + 1], ctx->copy_stream), "record");
@@ -409,12 +412,12 @@ static int submit_common(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, 
         ctx->step_timed = st->timed;
         pb_timer_begin(ctx, PB_T_TOTAL);
         r = pb_seqset_build(ctx, d_src, off, len, nullptr, n, src_mode, &st->reads, (int64_t)nbytes);
-        cu(cudaEventRecord(ctx->stage_ev[slot], ctx->stream), "record"); // ingest has read the staging buffer by then
+        if (!on_device) cu(cudaEventRecord(ctx->stage_ev[slot], ctx->stream), "record"); // ingest has read the staging buffer by then
         if (r == PB_OK) r = pb_locate_run(ctx, ix, ref, ref_seq, st->reads, prm, nullptr, &st->job);
         pb_timer_end(ctx, PB_T_TOTAL);
         ctx->step_ev = nullptr;
         ctx->step_timed = nullptr;
-        st->timed[PB_T_H2D] = true; // the copy-stream pair recorded above (pb_seqset_build does not touch it)
+        st->timed[PB_T_H2D] = !on_device; // the copy-stream pair recorded above (pb_seqset_build does not touch it)
     }
     if (r == PB_OK) cu(cudaEventRecord(st->done, ctx->stream), "record");
     if (r != PB_OK) { pb_locate_step_free(st); return r; }
@@ -439,6 +442,18 @@ extern "C" int pb_locate_submit(pb_ctx *ctx, const pb_index *ix, const pb_seqset
     std::vector<int64_t> rel(off, off + nreads);
     for (auto &x : rel) x -= lo;
     return submit_common(ctx, ix, ref, ref_seq, reads_text + lo, (size_t)(hi - lo), rel.data(), len, nreads, PB_SRC_TEXT, prm, step);
+}
+
+extern "C" int pb_locate_submit_device(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const void *d_text,
+                                       size_t text_bytes, const int64_t *off, const int32_t *len, int64_t nreads,
+                                       const pb_locate_params *prm, pb_locate_step **step)
+{
+    if (!ctx || !ix || !ref || !prm || !step || nreads < 0 || (nreads && (!d_text || !off || !len)))
+        return pb_fail(ctx, PB_ERR_ARG, "pb_locate_submit_device: bad argument");
+    for (int64_t i = 0; i < nreads; ++i)
+        if (len[i] > 0 && (off[i] < 0 || (size_t)(off[i] + len[i]) > text_bytes))
+            return pb_fail(ctx, PB_ERR_ARG, "views reach outside the device text blob");
+    return submit_common(ctx, ix, ref, ref_seq, d_text, text_bytes, off, len, nreads, PB_SRC_TEXT, prm, step, true);
 }
 
 extern "C" int pb_locate_submit_bin(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, int64_t ref_seq, const uint8_t *bin,
