@@ -256,7 +256,10 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # the exchange's kernels run under the aligner's persistent CTAs of consecutive steps (no idle gap between steps): on a
+        # high-priority stream they take the first SM slots a retiring CTA frees instead of queueing behind the aligner's blocks
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
 
     def barrier():
         if world > 1:

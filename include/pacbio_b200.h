@@ -75,7 +75,9 @@ PB_API int64_t pb_ctx_launch_count(const pb_ctx *ctx);
 /* upper bound on device scratch (bytes) the aligner may claim for parent matrices; 0 = default (50% of free) */
 PB_API int pb_ctx_set_scratch_limit(pb_ctx *ctx, size_t bytes);
 
-/* named device timings (milliseconds, CUDA events on the context stream) of the most recent call */
+/* named device timings (milliseconds, CUDA events on the context's streams) of the most recent call.  For a pipelined step
+ * (pb_locate_submit*) the stages before the aligner run on a second stream under the aligner of the step before, so PB_T_TOTAL
+ * -- first kernel of the step to the end of its aligner -- includes the wait behind that step. */
 enum {
     PB_T_H2D = 0, PB_T_INGEST, PB_T_SEED, PB_T_INDEX, PB_T_PROBE, PB_T_PREFILTER, PB_T_ALIGN, PB_T_D2H, PB_T_TOTAL,
     PB_T_COUNT

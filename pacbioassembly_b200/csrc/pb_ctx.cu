@@ -124,6 +124,8 @@ extern "C" void pb_ctx_destroy(pb_ctx *ctx)
         if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->prep_stream) { cudaStreamSynchronize(ctx->prep_stream); cudaStreamDestroy(ctx->prep_stream); }
+    if (ctx->prep_event) cudaEventDestroy(ctx->prep_event);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->planned) pb_locate_plan_free(ctx->planned);
@@ -214,6 +216,17 @@ int pb_d2h(pb_ctx *ctx, void *dst, const void *src, size_t bytes)
 {
     if (!bytes) return PB_OK;
     PB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return PB_OK;
+}
+
+int pb_join_main(pb_ctx *ctx)
+{
+    if (!ctx->main_pending) return PB_OK;
+    cudaStream_t prep = ctx->stream;
+    ctx->stream = ctx->main_pending;
+    ctx->main_pending = nullptr;
+    PB_CUDA(ctx, cudaEventRecord(ctx->prep_event, prep));
+    PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->prep_event, 0));
     return PB_OK;
 }
 

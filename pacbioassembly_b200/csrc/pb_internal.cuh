@@ -23,6 +23,12 @@ struct pb_ctx {
     LocatePlan *planned = nullptr; // made ahead of the step by the pipelined entry points (pb_align_locate_prepare)
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr; // host<->device copies of the pipelined entry points (pb_locate_submit / _collect)
+    // Pipelined steps run everything BEFORE the aligner (ingest, seeds, probe, gather, prefilter and the host round trips between
+    // them) on a second, high-priority stream, so that it overlaps the aligner kernels of the step before; `stream` points at it
+    // while that part is being queued, main_pending holds the real stream until pb_join_main() switches back
+    cudaStream_t prep_stream = nullptr;
+    cudaEvent_t prep_event = nullptr;
+    cudaStream_t main_pending = nullptr;
     cudaMemPool_t pool = nullptr;       // private pool behind DevBuf (bounded release threshold)
     // two grow-only device staging buffers for the batches of pb_locate_submit (the copy of batch k+1 lands in one while
     // batch k is still being ingested from the other); stage_ev[i] = the last ingest that read buffer i has finished
@@ -100,6 +106,7 @@ struct DevBuf {
 int pb_h2d(pb_ctx *ctx, void *dst, const void *src, size_t bytes);
 int pb_d2h(pb_ctx *ctx, void *dst, const void *src, size_t bytes);
 int pb_sync(pb_ctx *ctx);
+int pb_join_main(pb_ctx *ctx); // back from the prep stream to the context's own: what follows waits for what was queued there
 
 // ---------------------------------------------------------------------------------------------
 // device-resident sequences

@@ -236,6 +236,9 @@ extern "C" int pb_locate_run(pb_ctx *ctx, const pb_index *ix, const pb_seqset *r
     TRYJ(pb_prefilter(ctx, ss, lv, po.ncand, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(), d_rej.as<int32_t>()));
     pb_timer_end(ctx, PB_T_PREFILTER);
     ht.mark("vote+prefilter");
+    // a pipelined step has queued everything so far on the prep stream, under the aligner of the step before: the aligner
+    // itself goes to the context's own stream, behind that one
+    TRYJ(pb_join_main(ctx));
     // PB_T_ALIGN starts inside the aligner, after its host-side planning: the stage is the kernels' time
     TRYJ(pb_align_locate(ctx, ss, lv, nkept, kept_lens, kept_irr, prm->R, prm->maxn, prm->maxm, d_survive.as<uint8_t>(),
                          d_rej.as<int32_t>(), job->d_recs.as<pb_locate_rec>(), prm->want_ops ? job->d_ops.as<uint8_t>() : nullptr,
@@ -380,6 +383,16 @@ static int submit_common(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, 
             if (len[i] >= prm->minlen) kept_lens.push_back(len[i]);
         if (!kept_lens.empty()) r = pb_align_locate_prepare(ctx, kept_lens, prm->R, prm->maxn, prm->maxm, PB_MODE_LOCATE);
     }
+    if (r == PB_OK && !ctx->prep_stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi); // hi = the greatest priority: the prep kernels take the first SM slots that
+        cu(cudaStreamCreateWithPriority(&ctx->prep_stream, cudaStreamNonBlocking, hi), "prep stream"); // the aligner's CTAs give up
+        cu(cudaEventCreateWithFlags(&ctx->prep_event, cudaEventDisableTiming), "event");
+    }
+    if (r == PB_OK) { // from here to the aligner everything is queued on the prep stream (pb_locate_run switches back)
+        ctx->main_pending = ctx->stream;
+        ctx->stream = ctx->prep_stream;
+    }
     // the batch lands in one of the context's two staging buffers (no allocation on the pipelined path)
     const int slot = ctx->stage_next;
     if (!on_device) ctx->stage_next ^= 1;
@@ -414,11 +427,13 @@ static int submit_common(pb_ctx *ctx, const pb_index *ix, const pb_seqset *ref, 
         r = pb_seqset_build(ctx, d_src, off, len, nullptr, n, src_mode, &st->reads, (int64_t)nbytes);
         if (!on_device) cu(cudaEventRecord(ctx->stage_ev[slot], ctx->stream), "record"); // ingest has read the staging buffer by then
         if (r == PB_OK) r = pb_locate_run(ctx, ix, ref, ref_seq, st->reads, prm, nullptr, &st->job);
+        if (pb_join_main(ctx) != PB_OK && r == PB_OK) r = PB_ERR_CUDA; // a step that never reached the aligner (nothing kept, an error)
         pb_timer_end(ctx, PB_T_TOTAL);
         ctx->step_ev = nullptr;
         ctx->step_timed = nullptr;
         st->timed[PB_T_H2D] = !on_device; // the copy-stream pair recorded above (pb_seqset_build does not touch it)
     }
+    if (ctx->main_pending) { ctx->stream = ctx->main_pending; ctx->main_pending = nullptr; } // an error before anything was queued
     if (r == PB_OK) cu(cudaEventRecord(st->done, ctx->stream), "record");
     if (r != PB_OK) { pb_locate_step_free(st); return r; }
     *out = st;

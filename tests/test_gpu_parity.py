@@ -633,6 +633,17 @@ def test_locate_pipelined_submit_collect(ctx, oracle):
         for n in w.dtype.names:
             assert (w[n] == g[n]).all(), n
         assert st.stats["dp_alignments"] > 0
+    # the same batches with their text already in device memory (pb_locate_submit_device), two in flight
+    import torch
+    dev = [torch.from_numpy(np.ascontiguousarray(t)).cuda() for t, _, _, _ in batches]
+    dsteps = [ctx.locate_submit_device(ix, d.data_ptr(), d.numel(), o, l, R=0.3) for d, (_, o, l, _) in zip(dev[:2], batches[:2])]
+    dgot = [dsteps[0].collect()]
+    dsteps.append(ctx.locate_submit_device(ix, dev[2].data_ptr(), dev[2].numel(), batches[2][1], batches[2][2], R=0.3))
+    dgot += [dsteps[1].collect(), dsteps[2].collect()]
+    for w, g in zip(want, dgot):
+        assert len(w) == len(g) and all((w[n] == g[n]).all() for n in w.dtype.names)
+    with pytest.raises(Exception):  # a view past the end of the blob
+        ctx.locate_submit_device(ix, dev[0].data_ptr(), 100, batches[0][1], batches[0][2], R=0.3)
     # an empty batch and a step that is dropped without being collected
     assert len(ctx.locate_submit(ix, np.zeros(0, np.uint8), [], [], R=0.3).collect()) == 0
     ctx.locate_submit(ix, *batches[0][:3], R=0.3).free()
