@@ -19,6 +19,7 @@
 #include <map>
 
 #include "pb_internal.cuh"
+#include "pb_carry_chain.cuh"
 
 #define FULL 0xffffffffu
 // -DPB_BOUNDS_CHECK (tools/ab_build.sh bounds -DPB_BOUNDS_CHECK): every parent-plane address the aligners store to or prefetch
@@ -352,26 +353,7 @@ __device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c)
     return r;
 }
 
-// multi-word add helpers: the carry chain lives in the PTX condition code between consecutive statements
-__device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b)
-{
-    uint32_t r;
-    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-    return r;
-}
-__device__ __forceinline__ uint32_t addc_cc(uint32_t a, uint32_t b)
-{
-    uint32_t r;
-    asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-    return r;
-}
-__device__ __forceinline__ uint32_t addc(uint32_t a, uint32_t b)
-{
-    uint32_t r;
-    asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-    return r;
-}
-
+// multi-word adds: pb_carry_chain.cuh (generated), one asm statement per carry chain
 
 // One band row for the S words of this lane.  pl points at this lane's first Eq word of the row's plane, sh is the
 // row's bit offset inside those words; prow is this lane's pair column (row base + 2*lane) of the row's parent block.  Returns the D0 word of
@@ -401,19 +383,14 @@ __device__ __forceinline__ uint32_t row_step(uint32_t (&Hp)[S], uint32_t (&Hn)[S
         plw = nxt;
         x[s] = Eq[s] & Hp[s];
     }
-    sum[0] = add_cc(x[0], Hp[0]);
-#pragma unroll
-    for (int s = 1; s < S; ++s) sum[s] = addc_cc(x[s], Hp[s]);
-    const uint32_t carry = addc(0u, 0u);
+    const uint32_t carry = CarryChain<S>::add(sum, x, Hp);
     uint32_t ones = sum[0];
 #pragma unroll
     for (int s = 1; s < S; ++s) ones &= sum[s];
     const uint32_t G = __ballot_sync(FULL, carry);
     const uint32_t P = __ballot_sync(FULL, ones == 0xffffffffu);
     const uint32_t cin = ((((G | P) + G) ^ P) >> lane) & 1u; // carry into this lane's block
-    sum[0] = add_cc(sum[0], cin);
-#pragma unroll
-    for (int s = 1; s < S; ++s) sum[s] = addc_cc(sum[s], 0u);
+    CarryChain<S>::inc(sum, cin);
 
     // phase B: vertical deltas, D0, MATCH plane
     uint32_t d0w = 0u;
@@ -1419,9 +1396,7 @@ align_pairs_thread_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *_
                 w0 = w1;
                 x[s] = Eq[s] & Hp[s];
             }
-            sum[0] = add_cc(x[0], Hp[0]);
-#pragma unroll
-            for (int s = 1; s < W; ++s) sum[s] = addc_cc(x[s], Hp[s]);
+            CarryChain<W>::add_nc(sum, x, Hp);
             uint32_t Vp[W], Vn[W], d0w = 0u;
             uint32_t pprev = 0x80000000u, nprev = 0u; // vin = +1 at the band's left edge
 #pragma unroll

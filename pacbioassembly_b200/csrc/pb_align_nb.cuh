@@ -94,10 +94,7 @@ __device__ __forceinline__ uint32_t row_step_nb(uint32_t (&Hp)[S], uint32_t (&Hn
     uint32_t Eq[S], x[S], sum[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) { Eq[s] = pl[s]; x[s] = Eq[s] & Hp[s]; }
-    sum[0] = add_cc(x[0], Hp[0]);
-#pragma unroll
-    for (int s = 1; s < S; ++s) sum[s] = addc_cc(x[s], Hp[s]);
-    const uint32_t carry = addc(0u, 0u);
+    const uint32_t carry = CarryChain<S>::add(sum, x, Hp);
     uint32_t ones = sum[0];
 #pragma unroll
     for (int s = 1; s < S; ++s) ones &= sum[s];
@@ -105,9 +102,7 @@ __device__ __forceinline__ uint32_t row_step_nb(uint32_t (&Hp)[S], uint32_t (&Hn
     const uint32_t P = __ballot_sync(FULL, ones == 0xffffffffu);
     const uint32_t cin = ((((G | P) + G) ^ P) >> lane) & 1u; // the carry into this lane's block of S words
     cina = mad_lo(cina, 2u, cin); // an IMAD: the FMA pipe is idle, the integer pipe is the bound
-    sum[0] = add_cc(sum[0], cin);
-#pragma unroll
-    for (int s = 1; s < S; ++s) sum[s] = addc_cc(sum[s], 0u);
+    CarryChain<S>::inc(sum, cin);
 
     uint32_t d0w = 0u;
 #pragma unroll
@@ -144,12 +139,8 @@ __device__ __forceinline__ void row_step_tile(uint32_t (&Hp)[S], uint32_t (&Hn)[
     uint32_t Eq[S], x[S], sum[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) { Eq[s] = pl[s]; x[s] = Eq[s] & Hp[s]; }
-    sum[0] = add_cc(x[0], Hp[0]);
-#pragma unroll
-    for (int s = 1; s < S; ++s) sum[s] = addc_cc(x[s], Hp[s]);
-    sum[0] = add_cc(sum[0], cb);
-#pragma unroll
-    for (int s = 1; s < S; ++s) sum[s] = addc_cc(sum[s], 0u);
+    CarryChain<S>::add_nc(sum, x, Hp);
+    CarryChain<S>::inc(sum, cb);
 #pragma unroll
     for (int s = 0; s < S; ++s) {
         const uint32_t Xv = (sum[s] ^ Hp[s]) | Eq[s];
