@@ -1311,23 +1311,30 @@ align_pairs_packed_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *_
 // config 3's band 32 / 64 / 128 points) fits the registers of one thread, so the row needs no shuffle, no ballot and no second
 // carry pass: the W-word add is one carry chain inside the thread, the vertical delta entering word s is the top bit of word
 // s-1.  Same arithmetic and the same band-edge rules as align_one (bit 0 = the band's left edge, Eq forced to 0 above bit
-// 2*max_dst); a warp advances 32 alignments in lockstep (rows of finished or failed ones are predicated off), parents go out
-// as [row][word][lane] pairs -- every store instruction writes 256 contiguous bytes.  The Eq words of the 32 rows of a block
-// are built once per block from seg_b's bit planes into the thread's own column of shared memory ([plane][word][thread]: no
-// bank conflicts, no synchronisation); goal cell, coverage test and traceback run per thread at the end.
+// 2*max_dst); a warp advances 32 alignments in lockstep, parents go out as [row][word][lane] pairs -- every store instruction
+// writes 256 contiguous bytes.
+// A batch of a few thousand pairs is a few hundred warps, at most one per scheduler: the time of a point is rows x the latency
+// of ONE row, so the row is written for latency.  Whole 32-row blocks in which nothing special can happen to any alignment of
+// the warp (no last row, no end of seg_b) run an unrolled, branch-free loop -- the Eq fetches, stores and the failure test of
+// neighbouring rows overlap the carry chain; the rows after that take the general loop.  seg_b's Eq words live in the thread's
+// own column of shared memory ([plane][word][thread], constant stride: every offset an immediate); a block needs ONE new plane
+// word (two raw loads, issued a block ahead).  The traceback fetches, for TBR rows at once, the 32 parent bits around the
+// lane's diagonal -- a lane can then take TBR steps whatever they are, with one vote per TBR steps; transcripts are written
+// [step][lane], so the byte stores of a step coalesce.
 // ---------------------------------------------------------------------------------------------
 template <int W>
 __global__ void __launch_bounds__(ALIGN_WPB * 32)
 align_pairs_thread_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *__restrict__ out)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NT = ALIGN_WPB * 32;         // column stride, whatever the CTA's size (smaller CTAs leave columns unused)
     constexpr int PWT = W + 1;                 // plane words a block of 32 rows can touch
     uint32_t *pl = smem + tid;                 // plane c, word s of this thread: pl[(c * PWT + s) * NT]
-    uint32_t *vv = smem + (size_t)4 * PWT * NT + tid; // Vp / Vn (or the final Hp / Hn) of this thread: vv[s * NT], vv[(W + s) * NT]
+    uint32_t *vv = smem + 4 * PWT * NT + tid;  // Vp / Vn (or the final Hp / Hn) of this thread: vv[s * NT], vv[(W + s) * NT]
     const size_t wslot = ((size_t)blockIdx.x * p.wpb + warp) * 32; // this warp's 32 alignment slots are contiguous
     uint32_t *par = p.scratch + wslot * p.slot_words;               // [row][word][lane] {MATCH word, INSERT word}
-    uint8_t *opsrev = reinterpret_cast<uint8_t *>(par + 32 * p.par_words) + (size_t)lane * (p.slot_words - p.par_words) * 4;
+    uint8_t *ops_w = reinterpret_cast<uint8_t *>(par + 32 * p.par_words) + lane; // reversed transcripts, [step][lane]
     const SeqView &A = p.A, &B = p.B;
     for (;;) {
         int idx0 = 0;
@@ -1356,39 +1363,67 @@ align_pairs_thread_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *_
         int matlen_a = 0, matlen_b = 0, cost = 0;
         const int maxrows = __reduce_max_sync(FULL, rows);
         const int min_lb = __reduce_min_sync(FULL, dom ? len_b : INT_MAX);
-        uint32_t awh = 0u, awl = 0u;
-        for (int i = 1; i <= maxrows; ++i) {
-            const int t = (i - 1) & 31;
-            const bool live = i <= rows && !fail_row;
-            if (t == 0 && i <= rows) { // a block of 32 rows: seg_a's bases and the Eq words the block can touch
-                awh = load_window(A.hi, A.nwords, a_bit + i - 1);
-                awl = load_window(A.lo, A.nwords, a_bit + i - 1);
-                const int q = (i - 1) >> 5;
+
+        // seg_b's bit planes, plane word x: bit y <-> b[32x - D + y] = raw line bits from b_bit + 32x - D on, i.e. raw words
+        // wb0 + x and wb0 + x + 1 funnelled by shb.  hiw / low hold the plane words of the current block, rawh / rawl the last
+        // raw words read, nrh / nrl / nawh / nawl what the NEXT block needs (loaded a block ahead).
+        const int64_t wb0 = (b_bit - D) >> 5;
+        const unsigned shb = (unsigned)((b_bit - D) & 31);
+        auto raw_b = [&](const uint32_t *__restrict__ arr, int64_t wi) -> uint32_t { return (dom && wi >= 0 && wi < B.nwords) ? __ldg(arr + wi) : 0u; };
+        uint32_t hiw[PWT], low[PWT], rawh, rawl, nrh, nrl, awh = 0u, awl = 0u, nawh = 0u, nawl = 0u;
+        rawh = raw_b(B.hi, wb0);
+        rawl = raw_b(B.lo, wb0);
 #pragma unroll
-                for (int s = 0; s < PWT; ++s) {
-                    const int bidx0 = 32 * (q + s) - D; // b index of bit 0 of plane word q + s (bit x <-> b[x - D])
-                    uint32_t valid;
-                    if (bidx0 >= len_b || bidx0 + 31 < 0) valid = 0u;
-                    else {
-                        valid = 0xffffffffu;
-                        if (bidx0 < 0) valid &= 0xffffffffu << (-bidx0);
-                        if (bidx0 + 31 >= len_b) valid &= 0xffffffffu >> (bidx0 + 32 - len_b);
-                    }
-                    uint32_t hi = 0u, lo = 0u;
-                    if (valid) { hi = load_window(B.hi, B.nwords, b_bit + bidx0); lo = load_window(B.lo, B.nwords, b_bit + bidx0); }
-                    pl[(0 * PWT + s) * NT] = ~hi & ~lo & valid;
-                    pl[(1 * PWT + s) * NT] = ~hi & lo & valid;
-                    pl[(2 * PWT + s) * NT] = hi & ~lo & valid;
-                    pl[(3 * PWT + s) * NT] = hi & lo & valid;
-                }
+        for (int s = 0; s < PWT; ++s) {
+            const uint32_t h = raw_b(B.hi, wb0 + s + 1), l = raw_b(B.lo, wb0 + s + 1);
+            hiw[s] = __funnelshift_r(rawh, h, shb);
+            low[s] = __funnelshift_r(rawl, l, shb);
+            rawh = h; rawl = l;
+        }
+        nrh = nrl = 0u;
+        if (dom) { nawh = load_window(A.hi, A.nwords, a_bit); nawl = load_window(A.lo, A.nwords, a_bit); }
+        // block q = rows 32q+1 .. 32q+32; called for q = 0, 1, 2, ... in turn
+        auto refill = [&](int q) {
+            if (q > 0) {
+#pragma unroll
+                for (int s = 0; s + 1 < PWT; ++s) { hiw[s] = hiw[s + 1]; low[s] = low[s + 1]; }
+                hiw[PWT - 1] = __funnelshift_r(rawh, nrh, shb);
+                low[PWT - 1] = __funnelshift_r(rawl, nrl, shb);
+                rawh = nrh; rawl = nrl;
             }
-            const int ca = (int)(((awh >> t) & 1u) * 2u + ((awl >> t) & 1u));
-            const uint32_t *pc = pl + (size_t)ca * PWT * NT;
-            // slide the band one bit; the bit entering at the top is the +1 of a pinned edge
+#pragma unroll
+            for (int s = 0; s < PWT; ++s) {
+                const int bidx0 = 32 * (q + s) - D; // b index of bit 0 of plane word q + s
+                uint32_t valid;
+                if (bidx0 >= len_b || bidx0 + 31 < 0) valid = 0u;
+                else {
+                    valid = 0xffffffffu;
+                    if (bidx0 < 0) valid &= 0xffffffffu << (-bidx0);
+                    if (bidx0 + 31 >= len_b) valid &= 0xffffffffu >> (bidx0 + 32 - len_b);
+                }
+                const uint32_t hi = hiw[s], lo = low[s];
+                pl[(0 * PWT + s) * NT] = ~hi & ~lo & valid;
+                pl[(1 * PWT + s) * NT] = ~hi & lo & valid;
+                pl[(2 * PWT + s) * NT] = hi & ~lo & valid;
+                pl[(3 * PWT + s) * NT] = hi & lo & valid;
+            }
+            awh = nawh; awl = nawl;
+            if (32 * (q + 1) < rows) { // the block after this one
+                nrh = raw_b(B.hi, wb0 + q + 1 + PWT);
+                nrl = raw_b(B.lo, wb0 + q + 1 + PWT);
+                nawh = load_window(A.hi, A.nwords, a_bit + 32 * (q + 1));
+                nawl = load_window(A.lo, A.nwords, a_bit + 32 * (q + 1));
+            }
+        };
+        // one row: slides the band, updates Hp / Hn, leaves the vertical deltas in Vp / Vn, stores the parents when st;
+        // returns the D0 word the main diagonal sits in
+        auto row_core = [&](int i, int t, bool st, uint32_t (&Vp)[W], uint32_t (&Vn)[W]) -> uint32_t {
+            const uint32_t ca = ((awh >> t) & 1u) * 2u + ((awl >> t) & 1u);
+            const uint32_t *pc = pl + ca * (PWT * NT);
             uint32_t Eq[W], x[W], sum[W];
             uint32_t w0 = pc[0];
 #pragma unroll
-            for (int s = 0; s < W; ++s) {
+            for (int s = 0; s < W; ++s) { // slide the band one bit; the bit entering at the top is the +1 of a pinned edge
                 Hp[s] = __funnelshift_r(Hp[s], s + 1 < W ? Hp[s + 1] : 1u, 1);
                 Hn[s] = __funnelshift_r(Hn[s], s + 1 < W ? Hn[s + 1] : 0u, 1);
                 const uint32_t w1 = pc[(s + 1) * NT];
@@ -1397,8 +1432,9 @@ align_pairs_thread_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *_
                 x[s] = Eq[s] & Hp[s];
             }
             CarryChain<W>::add_nc(sum, x, Hp);
-            uint32_t Vp[W], Vn[W], d0w = 0u;
+            uint32_t d0w = 0u;
             uint32_t pprev = 0x80000000u, nprev = 0u; // vin = +1 at the band's left edge
+            uint2 *prow = reinterpret_cast<uint2 *>(par + (size_t)(i - 1) * (W * 64)) + lane;
 #pragma unroll
             for (int s = 0; s < W; ++s) {
                 const uint32_t Xv = (sum[s] ^ Hp[s]) | Eq[s];
@@ -1412,8 +1448,36 @@ align_pairs_thread_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *_
                 const uint32_t Xh = Eq[s] | Hn[s];
                 Hp[s] = vns | ~(Xh | vps);
                 Hn[s] = vps & Xh;
-                if (live) reinterpret_cast<uint2 *>(par + ((size_t)(i - 1) * W + s) * 64)[lane] = make_uint2(Mw, Hp[s]);
+                if (st) prow[s * 32] = make_uint2(Mw, Hp[s]);
             }
+            return d0w;
+        };
+
+        // ---- rows 1 .. fast_rows: whole blocks before any alignment's last row or the end of its seg_b
+        int i = 1;
+        {
+            const int lim = dom ? min(rows, len_b) - 1 : INT_MAX;
+            const int fast_rows = max(0, min(__reduce_min_sync(FULL, lim), maxrows)) & ~31;
+            for (; i <= fast_rows; i += 32) {
+                if (!__any_sync(FULL, dom && !fail_row)) break; // every alignment of the warp has failed
+                refill((i - 1) >> 5);
+#pragma unroll 8
+                for (int t = 0; t < 32; ++t) {
+                    uint32_t Vp[W], Vn[W];
+                    const uint32_t d0w = row_core(i + t, t, dom, Vp, Vn); // a failed alignment's parents are never read
+                    cii += 1 - (int)((d0w >> dbit) & 1u);
+                    if (dom && !fail_row && i + t > 10 && (double)cii > (i + t) * p.R) fail_row = i + t; // seq_aligner.h:185
+                }
+            }
+        }
+        // ---- the remaining rows: last rows, rows past seg_b's end, goal cells
+        const bool any_left = __any_sync(FULL, dom && !fail_row);
+        for (; any_left && i <= maxrows; ++i) {
+            const int t = (i - 1) & 31;
+            const bool live = i <= rows && !fail_row;
+            if (t == 0) refill((i - 1) >> 5);
+            uint32_t Vp[W], Vn[W];
+            const uint32_t d0w = row_core(i, t, live, Vp, Vn);
             if (i > min_lb) { // warp-uniform: only rows past some alignment's seg_b pay for this
 #pragma unroll
                 for (int s = 0; s < W; ++s) { vv[s * NT] = Vp[s]; vv[(W + s) * NT] = Vn[s]; }
@@ -1444,11 +1508,11 @@ align_pairs_thread_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *_
                 }
             }
         }
-        // ---- coverage test, find_path (seq_aligner.h:114, 214-233), record.  Every lane walks its own path, but the lanes take
-        // their steps together and REFILL TOGETHER: a window = the {MATCH, INSERT} words of one band word for TB_ROWS consecutive
-        // rows, fetched into the thread's column of shared memory (the Eq planes are dead by now); when any lane has left its
-        // window all lanes fetch a new one where they stand, so the warp waits for memory once per ~TB_ROWS steps and not at
-        // nearly every step (lanes refilling on their own schedules stall each other: measured, 2.3 M refills for 2.6 M steps).
+        // ---- coverage test, find_path (seq_aligner.h:114, 214-233), record.  Every lane walks its own path, the lanes step
+        // together.  A round: every walking lane fetches, for the TBR rows from where it stands, the 32 {MATCH, INSERT} bits
+        // around its diagonal (two adjacent band words funnelled; bits outside the band read 0 and are never reached) into
+        // its column of shared memory (the Eq planes are dead by now), then takes TBR steps -- a step moves at most one row up
+        // and one bit sideways, so the window holds whatever the steps turn out to be.
         pb_align_out o;
         o.ret = -1; o.len_a = len_a; o.len_b = len_b; o.max_dst = D;
         o.matlen_a = o.matlen_b = o.cost = o.diag_cost = o.nedit = 0;
@@ -1460,44 +1524,64 @@ align_pairs_thread_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *_
             o.diag_cost = (a_len <= len_a && a_len <= len_b) ? cii : 0;
             walk = !((double)matlen_b < len_b * (1 - p.R));
         }
+#ifdef PB_EXP_NOTB // timing experiment only (tools/ab_build.sh): the forward pass without the traceback
+        walk = false;
+#endif
         {
-            int i = walk ? matlen_a : 0, j = walk ? matlen_b : 0, n = 0;
+            int ti = walk ? matlen_a : 0, tj = walk ? matlen_b : 0, n = 0;
             const int guard = len_a + len_b + 1;
-            constexpr int TB_ROWS = (4 * PWT + 2 * W) / 2; // uint2 entries that fit the thread's column
-            uint32_t *win = smem + tid;                    // entry u: win[(2u) * NT], win[(2u + 1) * NT]
-            int w_top = 0, w_s = -1;                       // the window holds rows (w_top - TB_ROWS, w_top] of band word w_s
+            constexpr int TBR = (4 * PWT + 2 * W) / 2 < 15 ? (4 * PWT + 2 * W) / 2 : 15; // rows per round: what fits the thread's column
+            uint32_t *win = smem + tid;                                                  // row u of the round: win[(2u) * NT], win[(2u + 1) * NT]
             for (;;) {
-                const bool act = i > 0 && j > 0 && n < guard;
+                const bool act = ti > 0 && tj > 0 && n < guard;
                 if (!__any_sync(FULL, act)) break;
-                const int kk = j - i + D, sw = kk >> 5, bit = kk & 31;
-                const bool need = act && (sw != w_s || i > w_top || i <= w_top - TB_ROWS);
-                if (__any_sync(FULL, need)) {
-                    if (act) {
-                        w_top = i; w_s = sw;
+                const int p0 = tj - ti + D - 16; // band bit of window bit 0
+                const int wlo = p0 >> 5;
+                const unsigned shw = (unsigned)(p0 & 31);
+                { // branch-free: clamped addresses, all loads of the round in flight together, out-of-range words read as 0
+                    const int wl = min(max(wlo, 0), W - 1), wh = min(max(wlo + 1, 0), W - 1);
+                    const uint32_t ml = (wlo >= 0 && wlo < W) ? 0xffffffffu : 0u, mh = (wlo + 1 >= 0 && wlo + 1 < W) ? 0xffffffffu : 0u;
+                    uint2 a0[TBR], a1[TBR];
 #pragma unroll
-                        for (int u = 0; u < TB_ROWS; ++u) {
-                            const int row = i - u;
-                            const uint2 v = row >= 1 ? __ldcg(reinterpret_cast<const uint2 *>(par + ((size_t)(row - 1) * W + sw) * 64) + lane)
-                                                     : make_uint2(0u, 0u);
-                            win[(2 * u) * NT] = v.x; win[(2 * u + 1) * NT] = v.y;
-                        }
+                    for (int u = 0; u < TBR; ++u) {
+                        const uint2 *base = reinterpret_cast<const uint2 *>(par + (size_t)(max(ti - u, 1) - 1) * (W * 64)) + lane;
+                        a0[u] = __ldcg(base + wl * 32);
+                        a1[u] = __ldcg(base + wh * 32);
+                    }
+#pragma unroll
+                    for (int u = 0; u < TBR; ++u) {
+                        const uint32_t rl = ti - u >= 1 ? ml : 0u, rh = ti - u >= 1 ? mh : 0u;
+                        win[(2 * u) * NT] = __funnelshift_r(a0[u].x & rl, a1[u].x & rh, shw);
+                        win[(2 * u + 1) * NT] = __funnelshift_r(a0[u].y & rl, a1[u].y & rh, shw);
                     }
                 }
-                if (act) {
-                    const int u = w_top - i;
-                    if ((win[(2 * u) * NT] >> bit) & 1u) { opsrev[n++] = (uint8_t)PB_MATCH; --i; --j; }
-                    else if ((win[(2 * u + 1) * NT] >> bit) & 1u) { opsrev[n++] = (uint8_t)PB_INSERT; --j; }
-                    else { opsrev[n++] = (uint8_t)PB_DELETE; --i; }
+                const int w_top = ti;
+                int bit = 16;
+#pragma unroll
+                for (int u = 0; u < TBR; ++u) {
+                    const bool ok = ti > 0 && tj > 0 && n < guard;
+                    const int idx = w_top - ti; // 0 .. u
+                    const uint32_t m = win[(2 * idx) * NT], ins = win[(2 * idx + 1) * NT];
+                    const int mb = (int)((m >> bit) & 1u);            // MATCH wins, then INSERT, else DELETE (seq_aligner.h:214-233)
+                    const int ib = (int)((ins >> bit) & 1u) & (mb ^ 1);
+                    const int db = (mb | ib) ^ 1;
+                    if (ok) {
+                        ops_w[(size_t)n * 32] = (uint8_t)(mb ? PB_MATCH : (ib ? PB_INSERT : PB_DELETE));
+                        ti -= mb | db;
+                        tj -= mb | ib;
+                        bit += db - ib;
+                        ++n;
+                    }
                 }
             }
             if (walk) {
                 if (n < guard) {
-                    for (; j > 0 && i == 0; --j) opsrev[n++] = (uint8_t)PB_INSERT; // init_cell row 0
-                    for (; i > 0 && j == 0; --i) opsrev[n++] = (uint8_t)PB_DELETE; // init_cell column 0
+                    for (; tj > 0 && ti == 0; --tj) { ops_w[(size_t)n * 32] = (uint8_t)PB_INSERT; ++n; } // init_cell row 0
+                    for (; ti > 0 && tj == 0; --ti) { ops_w[(size_t)n * 32] = (uint8_t)PB_DELETE; ++n; } // init_cell column 0
                 }
                 if (p.ops) {
                     uint8_t *dst = p.ops + p.ops_off[k];
-                    for (int q = 0; q < n; ++q) dst[q] = opsrev[n - 1 - q];
+                    for (int q = 0; q < n; ++q) dst[q] = ops_w[(size_t)(n - 1 - q) * 32];
                 }
                 o.nedit = n;
                 o.ret = matlen_b;
@@ -1686,7 +1770,7 @@ static int plan_launch(pb_ctx *ctx, int key, const ClassPlan &cp, int locate, si
     // packed kernels, few items: spread them over more, smaller CTAs rather than leave SMs without work.  (Not for the
     // one-alignment-per-warp kernels: measured on config 2, smaller CTAs for the sparse wide-band classes cost 5 %.)
     while ((key_packed(key) || key_thread(key)) && g->wpb > 2 && (int64_t)cp.items.size() < (int64_t)g->wpb * g->groups * ctx->sm_count) g->wpb >>= 1;
-    g->smem_bytes = (size_t)g->wpb * g->warp_words * sizeof(uint32_t);
+    g->smem_bytes = (size_t)(key_thread(key) ? ALIGN_WPB : g->wpb) * g->warp_words * sizeof(uint32_t); // thread kernels: fixed column stride
     g->slot_words = g->par_words + ops_bytes / 4;
     const void *fn = kernel_ptr(key, locate);
     if (g->smem_bytes > 200 * 1024) return pb_fail(ctx, PB_ERR_DOMAIN, "sequence of %d rows needs %zu bytes of shared memory per CTA", cp.max_rows, g->smem_bytes);
