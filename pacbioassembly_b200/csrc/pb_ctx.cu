@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <chrono>
+
 #include "pb_internal.cuh"
 
 static thread_local std::string g_create_error;
@@ -118,6 +120,7 @@ extern "C" void pb_ctx_destroy(pb_ctx *ctx)
     for (auto st : ctx->aux_streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     for (auto ev : ctx->aux_events) cudaEventDestroy(ev);
     if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
+    if (ctx->wait_event) cudaEventDestroy(ctx->wait_event);
     if (ctx->scratch) cudaFree(ctx->scratch);
     for (int i = 0; i < 2; ++i) {
         if (ctx->stage[i]) cudaFree(ctx->stage[i]);
@@ -230,11 +233,27 @@ int pb_join_main(pb_ctx *ctx)
     return PB_OK;
 }
 
-int pb_sync(pb_ctx *ctx)
+int pb_wait_stream(pb_ctx *ctx, cudaStream_t st)
 {
-    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    static const bool spin = getenv("PB_SPIN_WAIT") && atoi(getenv("PB_SPIN_WAIT")) != 0;
+    if (!spin) {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            const cudaError_t q = cudaStreamQuery(st);
+            if (q == cudaSuccess) return PB_OK;
+            if (q != cudaErrorNotReady) PB_CUDA(ctx, q);
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(300)) break;
+        }
+        if (!ctx->wait_event) PB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->wait_event, cudaEventBlockingSync | cudaEventDisableTiming));
+        PB_CUDA(ctx, cudaEventRecord(ctx->wait_event, st));
+        PB_CUDA(ctx, cudaEventSynchronize(ctx->wait_event));
+        return PB_OK;
+    }
+    PB_CUDA(ctx, cudaStreamSynchronize(st));
     return PB_OK;
 }
+
+int pb_sync(pb_ctx *ctx) { return pb_wait_stream(ctx, ctx->stream); }
 
 // ---------------------------------------------------------------------------------------------
 // integer-pipe peak: the measured denominator of the aligner's int-pipe fraction

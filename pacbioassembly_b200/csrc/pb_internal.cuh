@@ -57,6 +57,7 @@ struct pb_ctx {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     size_t scratch_budget_cached = 0;
+    cudaEvent_t wait_event = nullptr; // blocking-sync event behind pb_wait_stream
 };
 
 void pb_set_error(pb_ctx *ctx, const char *fmt, ...);
@@ -106,6 +107,9 @@ struct DevBuf {
 int pb_h2d(pb_ctx *ctx, void *dst, const void *src, size_t bytes);
 int pb_d2h(pb_ctx *ctx, void *dst, const void *src, size_t bytes);
 int pb_sync(pb_ctx *ctx);
+// waits for `st`: polls for a short while (the common short waits cost no wake-up latency), then sleeps on a blocking-sync
+// event instead of spinning -- a 45 ms aligner step no longer burns a host core per process (PB_SPIN_WAIT=1: plain spinning)
+int pb_wait_stream(pb_ctx *ctx, cudaStream_t st);
 int pb_join_main(pb_ctx *ctx); // back from the prep stream to the context's own: what follows waits for what was queued there
 
 // ---------------------------------------------------------------------------------------------

@@ -511,7 +511,7 @@ extern "C" int pb_locate_collect(pb_ctx *ctx, pb_locate_step *st, pb_locate_rec 
     cu(cudaMemcpyAsync(job->stats, job->d_stats.p, 64, cudaMemcpyDeviceToHost, ctx->copy_stream), "stats");
     if (ops && job->want_ops && job->extent) cu(cudaMemcpyAsync(ops, job->d_ops.p, (size_t)job->extent, cudaMemcpyDeviceToHost, ctx->copy_stream), "transcripts");
     cu(cudaEventRecord(st->ev[2 * PB_T_D2H + 1], ctx->copy_stream), "record");
-    cu(cudaStreamSynchronize(ctx->copy_stream), "synchronize");
+    if (r == PB_OK) r = pb_wait_stream(ctx, ctx->copy_stream);
     if (r == PB_OK) {
         st->timed[PB_T_D2H] = true;
         if (nkept) *nkept = job->nkept;
