@@ -746,6 +746,54 @@ def test_align_narrow_bands_packed(ctx, oracle):
         assert run_batch_vs_oracle(ctx, oracle, [x[0] for x in P], [x[1] for x in P], Rr) == 24
 
 
+def test_align_thread_kernel_blocks_and_rounds(ctx, oracle):
+    """one alignment per thread (bands of at most 96 / 160 / 288 bits): whole 32-row blocks take the unrolled loop, the rest the
+    general one, the traceback moves in rounds -- batches built around those seams: every alignment of a warp failing, equal
+    sequences, lengths of 32k-1 / 32k / 32k+1 / 32k+2 rows, fewer than 32 rows, seg_a longer than seg_b by up to the band,
+    seg_b's tail of insertions past the last row, a lone item in a second warp"""
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def rnd(n):
+        return acgt[rng.integers(0, 4, n)].tobytes()
+
+    def mutate(a, rate):
+        out = bytearray()
+        for ch in a:
+            u = rng.random()
+            if u < rate * 0.4:
+                out += bytes([int(acgt[rng.integers(0, 4)]), ch])
+            elif u < rate * 0.7:
+                continue
+            elif u < rate:
+                out.append(int(acgt[rng.integers(0, 4)]))
+            else:
+                out.append(ch)
+        return bytes(out)
+
+    for R, base in ((0.02, 1500), (0.04, 1500), (0.045, 3000)):  # max_dst ~ 30 / 60 / 135: W = 3 / 5 / 9
+        A, B = [], []
+        for k in range(33):  # 33: the second warp holds one item
+            n = base + (-1, 0, 1, 2, 31, 33)[k % 6] - 32 * (k % 5)
+            a = rnd(n)
+            b = mutate(a, 0.01 if k % 4 else 0.0)
+            if k % 7 == 3:
+                b = b + rnd(int(rng.integers(1, int(R * n))))       # insertions after seg_a's end (goal on the last row)
+            if k % 7 == 5:
+                a = a + rnd(int(rng.integers(1, int(R * n))))       # seg_a longer: goal on the last column
+            A.append(a)
+            B.append(b)
+        assert run_batch_vs_oracle(ctx, oracle, A, B, R) >= 20
+        assert run_batch_vs_oracle(ctx, oracle, [rnd(n) for n in range(600, 640)], [rnd(n) for n in range(600, 640)], R) == 0  # all fail early
+        short_a = [rnd(n) for n in range(12, 44)]
+        assert run_batch_vs_oracle(ctx, oracle, short_a, [mutate(a, 0.02) + b"A" for a in short_a], 0.3) > 10  # under one block
+        # the same long pairs as one batch with early failures and short ones mixed in: lanes leave the unrolled loop's
+        # company at different rows
+        mix_a = A[:20] + [rnd(900) for _ in range(6)] + short_a[:6]
+        mix_b = B[:20] + [rnd(900) for _ in range(6)] + [a + b"C" for a in short_a[:6]]
+        assert run_batch_vs_oracle(ctx, oracle, mix_a, mix_b, R) >= 12
+
+
 def test_config3_sweep_every_point(ctx, oracle):
     """BASELINE config 3, unit costs: every (length, band) point of the sweep, 32 pairs each, against the oracle with
     transcripts; every pair of the generator aligns (band == max_dst, edits spaced under the early-failure line)"""
