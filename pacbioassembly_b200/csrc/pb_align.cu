@@ -1881,10 +1881,17 @@ static int run_classes(pb_ctx *ctx, std::map<int, ClassPlan> &plans, int locate,
         ctx->scratch = nullptr;
         ctx->scratch_bytes = 0;
         // some headroom for the next batch, but never past the budget the plan was cut to
-        const size_t want = std::min(need + need / 8, std::max(budget, need)) + 256;
+        size_t want = std::min(need + need / 8, std::max(budget, need)) + 256;
         cudaError_t e = cudaMalloc(&ctx->scratch, want);
+        if (e != cudaSuccess && want > need + 256) { // no room for the headroom: ask for exactly what this plan needs
+            cudaGetLastError();
+            want = need + 256;
+            e = cudaMalloc(&ctx->scratch, want);
+        }
         if (e != cudaSuccess) {
             cudaGetLastError();
+            ctx->scratch = nullptr;
+            ctx->scratch_budget_cached = 0; // free memory has changed since the budget was taken: the next call measures it again
             return pb_fail(ctx, PB_ERR_NOMEM, "aligner scratch of %zu bytes: %s", want, cudaGetErrorString(e));
         }
         ctx->scratch_bytes = want;
