@@ -1124,6 +1124,7 @@ align_pairs_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *__restri
         idx = __shfl_sync(FULL, idx, 0);
         if (idx >= p.nitems) break;
         const int k = p.order[idx];
+        if (p.redo && !p.redo[k]) continue; // certified by the strip pass
         AlnRes res;
         align_one<S, IRR>(p.A, p.A.base[k], p.A.len[k], IRR ? p.A.tab[k] : 0u, p.B, p.B.base[k], p.B.len[k], p.R, p.maxn, p.maxm, planes, p.PW, par, opsrev,
                      p.ops ? p.ops + p.ops_off[k] : nullptr, raw, p.RW, bar, phase, res);
@@ -1134,6 +1135,55 @@ align_pairs_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *__restri
             o.matlen_a = res.matlen_a; o.matlen_b = res.matlen_b; o.cost = res.cost; o.diag_cost = res.diag_cost;
             o.nedit = res.nedit; o.fail_row = res.fail_row; o.cells = res.cells;
             out[k] = o;
+        }
+    }
+}
+
+// First pass of pb_align_batch for the wide bands: the certified strip (align_one_nb) on explicit pairs.  A pair the strip cannot
+// certify keeps redo[k] = 1 and is run by align_pairs_kernel afterwards, which skips the others.
+template <int S>
+__global__ void __launch_bounds__(ALIGN_WPB * 32, MinBlocks<S>::v)
+align_pairs_nb_kernel(const __grid_constant__ AlignLaunch p, pb_align_out *__restrict__ out)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ __align__(8) uint64_t bars[ALIGN_WPB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *planes = smem + (size_t)warp * p.warp_words;
+    uint32_t *raw = planes + (size_t)4 * p.PW;
+    uint64_t *bar = &bars[warp];
+    uint32_t phase = 0u;
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    const size_t slot = (size_t)blockIdx.x * p.wpb + warp;
+    uint32_t *par = p.scratch + slot * p.slot_words;
+    uint8_t *opsrev = reinterpret_cast<uint8_t *>(par + p.par_words);
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(p.queue, 1);
+        idx = __shfl_sync(FULL, idx, 0);
+        if (idx >= p.nitems) break;
+        const int k = p.order[idx];
+        AlnRes res;
+        int redo = 0;
+        long long band_cells = 0;
+        int tbc[2] = {0, 0};
+        align_one_nb<S>(p.A, p.A.base[k], p.A.len[k], p.B, p.B.base[k], p.B.len[k], p.R, p.maxn, p.maxm, p.g256, planes, p.PW, par,
+                        p.par_words, opsrev, (int)((p.slot_words - p.par_words) & ~(size_t)31), p.ops ? p.ops + p.ops_off[k] : nullptr, raw,
+                        p.RW, raw + 2 * p.RW, bar, phase, res, redo, band_cells, tbc);
+        if (lane == 0) {
+            p.redo[k] = (uint8_t)redo;
+            if (p.stats) {
+                atomicAdd(p.stats + 2, (unsigned long long)band_cells);
+                if (redo) atomicAdd(p.stats + 3, 1ull);
+                else { atomicAdd(p.stats, (unsigned long long)res.cells); atomicAdd(p.stats + 1, 1ull); }
+            }
+            if (!redo) {
+                pb_align_out o;
+                o.ret = res.ret; o.len_a = res.len_a; o.len_b = res.len_b; o.max_dst = res.D;
+                o.matlen_a = res.matlen_a; o.matlen_b = res.matlen_b; o.cost = res.cost; o.diag_cost = res.diag_cost;
+                o.nedit = res.nedit; o.fail_row = res.fail_row; o.cells = res.cells;
+                out[k] = o;
+            }
         }
     }
 }
@@ -1673,6 +1723,7 @@ template <int S, bool IRR> struct KernelSel {
 };
 template <int S> struct NarrowSel {
     static const void *locate() { return (const void *)align_locate_nb_kernel<S>; }
+    static const void *pairs() { return (const void *)align_pairs_nb_kernel<S>; }
 };
 
 // locate: 0 = pairs of sequences (pb_align_batch), 1 = locate / overlap items, 2 = all-vs-all items
@@ -1688,7 +1739,7 @@ static const void *kernel_ptr(int key, int locate)
     }
     if (key_narrow(key)) {
         switch (key_S(key)) {
-#define CASE(s) case s: return NarrowSel<s>::locate();
+#define CASE(s) case s: return locate ? NarrowSel<s>::locate() : NarrowSel<s>::pairs();
             CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
         }
@@ -2130,13 +2181,19 @@ int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t 
                    pb_align_out *d_out, uint8_t *d_ops, const int64_t *d_ops_off)
 {
     if (n == 0) { pb_timer_begin(ctx, PB_T_ALIGN); return PB_OK; }
-    std::map<int, ClassPlan> plans;
+    std::map<int, ClassPlan> plans, narrow_plans;
+    int64_t n_narrow = 0;
+    // wide bands (one warp per alignment) go through the certified strip first, as in pb_align_locate: PB_NARROW=0 turns it off
+    static const bool narrow_on = !(getenv("PB_NARROW") && atoi(getenv("PB_NARROW")) == 0);
+    static const int g256 = getenv("PB_NARROW_G") ? std::max(128, std::min(256, (int)(atof(getenv("PB_NARROW_G")) * 256.0))) : 192;
     std::vector<int32_t> order((size_t)n);
     for (int64_t k = 0; k < n; ++k) order[k] = (int32_t)k;
     std::vector<int> la((size_t)n), D((size_t)n);
+    std::vector<uint8_t> goal_left((size_t)n);
     for (int64_t k = 0; k < n; ++k) {
         int lb;
         pb_align_params(A->len[k], B->len[k], R, &la[k], &lb, &D[k]);
+        goal_left[k] = la[k] > lb; // the goal cell is searched on the last column (seq_aligner.h:191-213)
     }
     std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return (int64_t)la[x] * D[x] > (int64_t)la[y] * D[y]; });
     for (int32_t k : order) {
@@ -2150,13 +2207,24 @@ int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t 
             else cls = class_for_band(D[k], irr);
             if (cls < 0) return pb_fail(ctx, PB_ERR_DOMAIN, "band half-width %d exceeds PB_MAX_BAND", D[k]);
         }
+        int ncls = -1;
+        if (!rejected && narrow_on && cls < 1000) ncls = narrow_class_for_band(D[k], g256, goal_left[k] != 0);
         ClassPlan &cp = plans[cls];
         cp.items.push_back(k);
         if (!rejected) {
             cp.max_rows = std::max(cp.max_rows, la[k]);
             cp.max_D = std::max(cp.max_D, D[k]);
             cp.work += key_thread(cls) ? (double)la[k] * (19.0 * key_S(cls) + 20.0) / 32.0
-                       : (key_packed(cls) ? (double)la[k] * 90.0 * key_lanes(cls) / 32.0 : (double)la[k] * (30.0 * key_S(cls) + 60.0));
+                       : (key_packed(cls) ? (double)la[k] * 90.0 * key_lanes(cls) / 32.0
+                                          : (double)la[k] * (30.0 * key_S(cls) + 60.0) * (ncls < 0 ? 1.0 : 0.02));
+        }
+        if (ncls >= 0) { // the full-band class above only sees it again when the strip could not certify it
+            ClassPlan &np = narrow_plans[ncls];
+            np.items.push_back(k);
+            np.max_rows = std::max(np.max_rows, la[k]);
+            np.max_D = std::max(np.max_D, D[k]);
+            np.work += (double)la[k] * (16.0 * key_S(ncls) + 40.0);
+            ++n_narrow;
         }
     }
     pb_timer_begin(ctx, PB_T_ALIGN); // the caller closes the stage; planning above is host time, not kernel time
@@ -2166,10 +2234,19 @@ int pb_align_pairs(pb_ctx *ctx, const pb_seqset *A, const pb_seqset *B, int64_t 
     base.B = seq_view(B);
     base.R = R; base.maxn = maxn; base.maxm = maxm;
     base.ops = d_ops; base.ops_off = d_ops_off;
-    return run_classes(ctx, plans, 0, base, [&](int key, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
+    base.g256 = g256;
+    auto launch = [&](int key, const AlignLaunch &p, const LaunchGeom &g, cudaStream_t st) -> int {
         void *args[] = {(void *)&p, (void *)&d_out};
         PB_CUDA(ctx, cudaLaunchKernel(kernel_ptr(key, 0), dim3(g.blocks), dim3(g.wpb * 32), args, g.smem_bytes, st));
         ctx->launches++;
         return PB_OK;
-    });
+    };
+    DevBuf d_redo;
+    if (n_narrow > 0) {
+        PB_TRY(d_redo.alloc(ctx, (size_t)n + 16));
+        PB_CUDA(ctx, cudaMemsetAsync(d_redo.p, 1, (size_t)n, ctx->stream)); // pairs the first pass never sees stay flagged
+        base.redo = d_redo.as<uint8_t>();
+        PB_TRY(run_classes(ctx, narrow_plans, 0, base, launch));
+    }
+    return run_classes(ctx, plans, 0, base, launch, n_narrow == 0, n_narrow > 0 && (double)n_narrow >= 0.9 * (double)n ? 0.125 : 1.0);
 }
