@@ -5,7 +5,7 @@
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/config4_bench.py ...
 
 Strong scaling: the read count is fixed and rank r maps reads/N of them (its own deterministic shard of the generator:
-seed 5 + 1000 r), in batches of --batch reads; the index is replicated (built on every rank); the only exchange is the final
+seed 5 + 1000 r), in batches of at most --batch reads streamed through the pipelined entry points; the index is replicated (built on every rank); the only exchange is the final
 reduction (one all-reduce of the counters; records stay on their rank here, bench.py shows the gather).  Rank 0 checks an evenly
 spaced sample of its shard bit-exactly against the CPU oracle (incl. candidate and cell counts) and all ranks check that
 located reads sit on their true locus.
@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--sample", type=int, default=48)
     ap.add_argument("--mask", default="fff0ccfc")  # weight 11: ~15 random candidates per probe at 64 Mbp
+    ap.add_argument("--serial", action="store_true", help="blocking pb_locate_batch calls instead of the pipelined entry points")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     mask, R = int(a.mask, 16), 0.3
@@ -63,17 +64,32 @@ def main():
     if rank == 0:
         print(f"index: {ix.nentries} entries, {ix.nkeys} keys, {time.time() - t0:.2f}s wall", flush=True)
 
+    # batches of a rank: at most --batch reads, and at least four per rank so that copies and planning of one batch run under the
+    # alignment of the one before (pb_locate_submit / pb_locate_collect); --serial: one blocking pb_locate_batch per batch
+    bsz = a.batch if a.serial else min(a.batch, max(20_000, (mine + 3) // 4))
+
     def one_pass():
         parts, cand, k3 = [], 0, 0.0
-        for b0 in range(0, mine, a.batch):
-            b1 = min(mine, b0 + a.batch)
+        prev = None
+        for b0 in range(0, mine, bsz):
+            b1 = min(mine, b0 + bsz)
             base = int(offs[b0])
             end = int(offs[b1 - 1] + lens[b1 - 1])
-            recs = ctx.locate(ix, txt[base:end], offs[b0:b1] - base, lens[b0:b1], R=R)  # pb_locate_batch: host text in, records out
-            parts.append(recs)
-            cand += int(recs["ncand"].sum())
+            if a.serial:
+                recs = ctx.locate(ix, txt[base:end], offs[b0:b1] - base, lens[b0:b1], R=R)  # pb_locate_batch: host text in, records out
+                parts.append(recs)
+                k3 += ctx.timings()["align"]
+                continue
+            cur = ctx.locate_submit(ix, txt[base:end], offs[b0:b1] - base, lens[b0:b1], R=R)
+            if prev is not None:
+                parts.append(prev.collect())
+                k3 += ctx.timings()["align"]
+            prev = cur
+        if prev is not None:
+            parts.append(prev.collect())
             k3 += ctx.timings()["align"]
-        return np.concatenate(parts), cand, k3
+        recs = np.concatenate(parts)
+        return recs, int(recs["ncand"].sum()), k3
 
     best = None
     for it in range(a.steps):
@@ -125,7 +141,7 @@ def main():
     if rank == 0:
         dt, tot = best
         line = {"config": f"config4: {a.ref} bp iid reference, {a.reads} CLR reads (mean 5 kbp, ins 9/del 4/sub 2 %) sharded over {world} GPU(s), "
-                          f"mask {a.mask}, R={R}, locator.cpp semantics, host text in / records out (pb_locate_batch)",
+                          f"mask {a.mask}, R={R}, locator.cpp semantics, host text in / records out ({'pb_locate_batch' if a.serial else 'pb_locate_submit / pb_locate_collect, batches of ' + str(bsz)})",
                 "n_gpus": world, "seconds": dt, "reads_per_s": a.reads / dt, "scaling": "strong", "located": tot[0], "reads": tot[3],
                 "reference_align_calls": tot[4], "reference_dp_cells": tot[2], "oracle_checked_reads": checked,
                 "cpu_baseline": cpu if checked else None}
