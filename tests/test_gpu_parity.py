@@ -794,6 +794,52 @@ def test_align_thread_kernel_blocks_and_rounds(ctx, oracle):
         assert run_batch_vs_oracle(ctx, oracle, mix_a, mix_b, R) >= 5
 
 
+def test_align_batch_strip_pass_and_redo(ctx, oracle):
+    """wide bands of pb_align_batch take the certified strip first (align_pairs_nb_kernel) and the full band redoes what it could
+    not certify: pairs whose cost runs from well inside the strip's goal side (0.75 max_dst) to beyond it, goal on the last row and
+    on the last column, failures and rejected pairs mixed in"""
+    rng = np.random.default_rng(401)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def rnd(n):
+        return acgt[rng.integers(0, 4, n)].tobytes()
+
+    def mutate(a, rate):
+        out = bytearray()
+        u = rng.random(len(a))
+        for ch, x in zip(a, u):
+            if x < rate * 0.45:
+                out += bytes([int(acgt[rng.integers(0, 4)]), ch])
+            elif x < rate * 0.75:
+                continue
+            elif x < rate:
+                out.append(int(acgt[rng.integers(0, 4)]))
+            else:
+                out.append(ch)
+        return bytes(out)
+
+    A, B = [], []
+    for k in range(72):
+        n = int(rng.integers(1200, 5200))
+        a = rnd(n)
+        b = mutate(a, (0.05, 0.16, 0.2, 0.23, 0.26, 0.29)[k % 6])
+        if k % 4 == 1:
+            b = b + rnd(int(rng.integers(1, n // 3)))  # goal on the last row, seg_b cut to len_a + max_dst
+        if k % 4 == 2:
+            a = a + rnd(int(rng.integers(1, n // 3)))  # goal on the last column
+        if k % 9 == 8:
+            b = rnd(len(b))                            # fails early
+        A.append(a)
+        B.append(b)
+    recs_ok = run_batch_vs_oracle(ctx, oracle, A, B, 0.3)
+    assert recs_ok >= 30
+    # costs on both sides of the strip's goal width: the redo pass must have had work
+    costs = [oracle.align(a, b, 0.3, True, True, 26000, 6000) for a, b in zip(A, B)]
+    ratio = [w["cost"] / w["max_dst"] for w in costs if w["ret"] >= 0]
+    assert min(ratio) < 0.5 and max(ratio) > 0.8, (min(ratio), max(ratio))
+    assert run_batch_vs_oracle(ctx, oracle, A[:24], B[:24], 0.3, maxn=4000, maxm=1000) >= 5  # some pairs rejected by the domain check
+
+
 def test_config3_sweep_every_point(ctx, oracle):
     """BASELINE config 3, unit costs: every (length, band) point of the sweep, 32 pairs each, against the oracle with
     transcripts; every pair of the generator aligns (band == max_dst, edits spaced under the early-failure line)"""
