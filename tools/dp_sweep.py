@@ -30,6 +30,7 @@ def main():
     weighted = "--weighted" in sys.argv
     rng = np.random.default_rng(2024)
     ctx = Context(0)
+    int_peak = ctx.int_pipe_peak()  # warp instructions per second of a register-only LOP3 / SHF kernel, measured now
     oracle = None
     if ncheck:
         import cpu_libs
@@ -78,7 +79,18 @@ def main():
                 if w["ret"] >= 0:
                     assert (keep_ops[k] == w["ops"]).all()
                 checked += 1
+            # integer-ALU warp instructions of the kernels that ran (counted in their SASS, row loops and -- for the
+            # one-alignment-per-thread kernels -- traceback steps) over K3 time, against the measured peak of the pipe
+            alu = None
+            if not weighted:
+                nw = (2 * band + 1 + 31) // 32
+                if nw <= 9:    # align_pairs_thread_kernel<3|5|9>: 32 alignments per warp; 63 / 90 / 175 per row, 18 per traceback step
+                    per_row = {3: 63, 5: 90, 9: 175}[3 if nw <= 3 else (5 if nw <= 5 else 9)]
+                    alu = ((npairs + 31) // 32) * float(a_len.mean()) * (per_row + 18)
+                else:          # strip pass, one warp per alignment: 11 per band word and lane + 12 per row (band 256 and 512: S = 1)
+                    alu = npairs * float(a_len.mean()) * (11 * 1 + 12)
             row = {"len": alen, "band": band, "pairs": npairs, "aligned": ok, "cells": cells, "k3_ms": best,
+                   "int_pipe_frac": None if alu is None else round(alu / (best / 1e3) / int_peak, 4),
                    "gcups": cells / (best / 1e3) / 1e9, "mean_cost": float(recs["cost"][recs["ret"] >= 0].mean()) if ok else None,
                    "checked_vs_oracle": checked, "gen_s": round(time.time() - t0, 2)}
             rows.append(row)
@@ -87,6 +99,11 @@ def main():
           + ("quality-weighted extension" if weighted else "unit costs") + ")")
     for alen in (1000, 2000, 5000, 10000, 19999):
         print(f"{alen:>10d} " + "".join(f"{r['gcups']:9.0f}" for r in rows if r["len"] == alen))
+    if not weighted:
+        print(f"\nlen \\ band " + "".join(f"{b:>9d}" for b in (32, 64, 128, 256, 512)) + f"    (integer-pipe fraction: ALU warp instructions "
+              f"of the row loops / K3 time / measured peak {int_peak / 1e9:.0f} G warp-instr/s)")
+        for alen in (1000, 2000, 5000, 10000, 19999):
+            print(f"{alen:>10d} " + "".join(f"{r['int_pipe_frac']:9.3f}" for r in rows if r["len"] == alen))
     ctx.close()
 
 
