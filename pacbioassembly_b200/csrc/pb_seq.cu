@@ -5,6 +5,8 @@
 // coalesced 1 B/base reads, ballot-built plane words, shuffle-combined packed words.
 #include <algorithm>
 
+#include <chrono>
+
 #include "pb_internal.cuh"
 
 // C2I, dna_seq.h:21 : A->0 C->1 G->2 anything else->3
@@ -229,6 +231,10 @@ int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, cons
     s->total = ((g + 127) & ~(int64_t)127) + 128;
     const int64_t nw = s->nwords();
     int r;
+    const bool htrace = getenv("PB_HOST_TRACE") != nullptr; // host wall time of this call's phases on stderr
+    auto hnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double ht0 = htrace ? hnow() : 0.0;
+    double ht1 = 0, ht2 = 0, ht3 = 0;
 #define TRYS(x) do { r = (x); if (r != PB_OK) { delete s; return r; } } while (0)
     TRYS(s->d_base.alloc(ctx, (n + 1) * sizeof(int64_t)));
     TRYS(s->d_len.alloc(ctx, (n + 1) * sizeof(int32_t)));
@@ -240,13 +246,17 @@ int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, cons
     DevBuf d_toff, d_stride, d_nirr;
     TRYS(d_nirr.alloc_zero(ctx, 16));
     TRYS(d_toff.alloc(ctx, (n + 1) * sizeof(int64_t)));
+    const double hta = htrace ? hnow() : 0.0;
     TRYS(pb_h2d(ctx, s->d_base.p, s->base.data(), (n + 1) * sizeof(int64_t)));
+    const double htb = htrace ? hnow() : 0.0;
     TRYS(pb_h2d(ctx, s->d_len.p, s->len.data(), n * sizeof(int32_t)));
     TRYS(pb_h2d(ctx, d_toff.p, h_toff, n * sizeof(int64_t)));
+
     if (h_stride) {
         TRYS(d_stride.alloc(ctx, (n + 1) * sizeof(int32_t)));
         TRYS(pb_h2d(ctx, d_stride.p, h_stride, n * sizeof(int32_t)));
     }
+    if (htrace) ht1 = hnow();
     // guard words past the line read as code 3
     cudaMemsetAsync(s->d_hi.as<uint32_t>() + nw, 0xff, 4 * sizeof(uint32_t), ctx->stream);
     cudaMemsetAsync(s->d_lo.as<uint32_t>() + nw, 0xff, 4 * sizeof(uint32_t), ctx->stream);
@@ -279,8 +289,10 @@ int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, cons
     if (e != cudaSuccess) { delete s; return pb_fail(ctx, PB_ERR_CUDA, "ingest launch failed: %s", cudaGetErrorString(e)); }
     s->flags.assign((size_t)n, 0u);
     unsigned long long nirr = 0;
+    if (htrace) ht2 = hnow();
     TRYS(pb_d2h(ctx, &nirr, d_nirr.p, 8));
     TRYS(pb_sync(ctx)); // d_toff/d_stride are released after the kernel (stream-ordered) but the count is needed now
+    if (htrace) ht3 = hnow();
     if (nirr > 0) { // the per-sequence flags only say something when a byte outside {A,C,G,T} was seen
         TRYS(pb_d2h(ctx, s->flags.data(), s->d_flags.p, n * sizeof(uint32_t)));
         TRYS(pb_sync(ctx));
@@ -333,6 +345,9 @@ int pb_seqset_build(pb_ctx *ctx, const void *d_text, const int64_t *h_toff, cons
     TRYS(s->d_tab.alloc(ctx, (size_t)(n + 1) * 4));
     TRYS(pb_h2d(ctx, s->d_tab.p, s->tab.data(), (size_t)n * 4));
     TRYS(pb_sync(ctx));
+    if (htrace)
+        fprintf(stderr, "[pb_host_trace] pb_seqset_build (ms): allocs %.2f first table copy %.2f other table copies %.2f launch %.2f first sync %.2f tables+sync %.2f\n",
+                hta - ht0, htb - hta, ht1 - htb, ht2 - ht1, ht3 - ht2, hnow() - ht3);
 #undef TRYS
     *out = s;
     return PB_OK;
