@@ -3,8 +3,15 @@
 #include <stdlib.h>
 
 #include <chrono>
+#include <algorithm>
+#include <deque>
+#include <map>
+#include <mutex>
+#include <vector>
 
 #include "pb_internal.cuh"
+
+void pb_pin_ring_release(pb_ctx *ctx);
 
 static thread_local std::string g_create_error;
 
@@ -101,7 +108,10 @@ extern "C" int pb_ctx_create(int device, pb_ctx **out)
         uint64_t thr = (uint64_t)(k ? atoll(k) : 16384) << 20;
         CREATE_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr));
     }
-    ctx->h_pin_bytes = 1 << 20;
+    {
+        const char *k = getenv("PB_PIN_RING_MB"); // ring for the staged table copies (pb_h2d): a few steps' worth
+        ctx->h_pin_bytes = (size_t)std::max<long long>(1, k ? atoll(k) : 32) << 20;
+    }
     CREATE_CUDA(cudaMallocHost(&ctx->h_pin, ctx->h_pin_bytes));
 #undef CREATE_CUDA
     *out = ctx;
@@ -116,7 +126,6 @@ extern "C" void pb_ctx_destroy(pb_ctx *ctx)
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (int i = 0; i < 2 * PB_T_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     for (auto st : ctx->aux_streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     for (auto ev : ctx->aux_events) cudaEventDestroy(ev);
     if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
@@ -129,6 +138,8 @@ extern "C" void pb_ctx_destroy(pb_ctx *ctx)
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->prep_stream) { cudaStreamSynchronize(ctx->prep_stream); cudaStreamDestroy(ctx->prep_stream); }
     if (ctx->prep_event) cudaEventDestroy(ctx->prep_event);
+    pb_pin_ring_release(ctx); // every stream that a staged copy was queued on has been synchronised above
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->planned) pb_locate_plan_free(ctx->planned);
@@ -208,10 +219,78 @@ void DevBuf::release()
     bytes = 0;
 }
 
+// Host->device copies of the library's own tables (per-read offsets and lengths, kept ids, the aligner's item order ...) come from
+// pageable memory.  The driver runs such a copy of more than a few tens of KB through a staging path that needs the GPU's
+// attention at default priority: issued while the aligner's persistent kernels hold the SMs, the call does not return until
+// their narrow band classes retire -- measured, ~40 ms into a 45 ms step wherever in pb_locate_submit the first such copy stood
+// (PB_HOST_TRACE), which left the next step's aligner queued only ~3 ms ahead of the moment the GPU needs it.  So those copies
+// are staged here, through a ring in the context's pinned buffer: memcpy into the ring, cudaMemcpyAsync from pinned memory
+// (returns at once, the copy engine does the rest in stream order), one event per chunk; a chunk's space is reused only after
+// its event has completed.  Sources that are pinned already, tiny copies and copies larger than half the ring go straight through.
+namespace {
+struct PinRing {
+    struct Chunk { size_t off, bytes; cudaEvent_t ev; };
+    size_t head = 0;
+    std::deque<Chunk> live;
+    std::vector<cudaEvent_t> spare;
+};
+std::mutex g_ring_mu;
+std::map<pb_ctx *, PinRing> g_rings; // bookkeeping beside the context (its pinned buffer is ctx->h_pin)
+} // namespace
+
+void pb_pin_ring_release(pb_ctx *ctx) // pb_ctx_destroy: the streams are idle by then
+{
+    std::lock_guard<std::mutex> lk(g_ring_mu);
+    auto it = g_rings.find(ctx);
+    if (it == g_rings.end()) return;
+    for (auto &c : it->second.live) cudaEventDestroy(c.ev);
+    for (auto e : it->second.spare) cudaEventDestroy(e);
+    g_rings.erase(it);
+}
+
 int pb_h2d(pb_ctx *ctx, void *dst, const void *src, size_t bytes)
 {
     if (!bytes) return PB_OK;
-    PB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    static const bool staged = !(getenv("PB_H2D_STAGED") && atoi(getenv("PB_H2D_STAGED")) == 0);
+    const size_t ring = ctx->h_pin_bytes;
+    bool stage = staged && ctx->h_pin && bytes >= (size_t)32 * 1024 && bytes <= ring / 2;
+    if (stage) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, src) == cudaSuccess) stage = at.type == cudaMemoryTypeUnregistered;
+        else { cudaGetLastError(); }
+    }
+    if (!stage) {
+        PB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return PB_OK;
+    }
+    PinRing *rg;
+    {
+        std::lock_guard<std::mutex> lk(g_ring_mu);
+        rg = &g_rings[ctx];
+    }
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (rg->head + need > ring) rg->head = 0;
+    const size_t lo = rg->head, hi = rg->head + need;
+    while (!rg->live.empty()) { // chunks leave in the order they were taken: the oldest ones are the ones in the way
+        const PinRing::Chunk &c = rg->live.front();
+        if (c.off + c.bytes <= lo || c.off >= hi) break;
+        PB_CUDA(ctx, cudaEventSynchronize(c.ev));
+        rg->spare.push_back(c.ev);
+        rg->live.pop_front();
+    }
+    cudaEvent_t ev;
+    if (!rg->spare.empty()) { ev = rg->spare.back(); rg->spare.pop_back(); }
+    else PB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    uint8_t *pin = static_cast<uint8_t *>(ctx->h_pin) + lo;
+    memcpy(pin, src, bytes);
+    cudaError_t e = cudaMemcpyAsync(dst, pin, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ev, ctx->stream);
+    if (e != cudaSuccess) {
+        rg->spare.push_back(ev);
+        return pb_fail(ctx, PB_ERR_CUDA, "staged host->device copy of %zu bytes: %s", bytes, cudaGetErrorString(e));
+    }
+    rg->live.push_back({lo, need, ev});
+    rg->head = hi;
     return PB_OK;
 }
 
