@@ -38,7 +38,7 @@ def _stale(target: str, deps: list[str]) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
-    headers = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")]
+    headers = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))]
     headers += [os.path.join(ROOT, "include", "pacbio_b200.h"), __file__]
 
     def compile_one(src: str) -> str:

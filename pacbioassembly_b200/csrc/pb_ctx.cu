@@ -4,12 +4,12 @@
 
 #include <chrono>
 #include <algorithm>
-#include <deque>
 #include <map>
 #include <mutex>
 #include <vector>
 
 #include "pb_internal.cuh"
+#include "pb_pin_ring.h"
 
 void pb_pin_ring_release(pb_ctx *ctx);
 
@@ -229,9 +229,8 @@ void DevBuf::release()
 // its event has completed.  Sources that are pinned already, tiny copies and copies larger than half the ring go straight through.
 namespace {
 struct PinRing {
-    struct Chunk { size_t off, bytes; cudaEvent_t ev; };
-    size_t head = 0;
-    std::deque<Chunk> live;
+    PbRingBook book;                       // pb_pin_ring.h: where a copy goes, which chunks are in its way
+    std::map<uint64_t, cudaEvent_t> event; // chunk id -> the event recorded behind its copy
     std::vector<cudaEvent_t> spare;
 };
 std::mutex g_ring_mu;
@@ -243,7 +242,7 @@ void pb_pin_ring_release(pb_ctx *ctx) // pb_ctx_destroy: the streams are idle by
     std::lock_guard<std::mutex> lk(g_ring_mu);
     auto it = g_rings.find(ctx);
     if (it == g_rings.end()) return;
-    for (auto &c : it->second.live) cudaEventDestroy(c.ev);
+    for (auto &kv : it->second.event) cudaEventDestroy(kv.second);
     for (auto e : it->second.spare) cudaEventDestroy(e);
     g_rings.erase(it);
 }
@@ -268,29 +267,26 @@ int pb_h2d(pb_ctx *ctx, void *dst, const void *src, size_t bytes)
         std::lock_guard<std::mutex> lk(g_ring_mu);
         rg = &g_rings[ctx];
     }
-    const size_t need = (bytes + 255) & ~(size_t)255;
-    if (rg->head + need > ring) rg->head = 0;
-    const size_t lo = rg->head, hi = rg->head + need;
-    while (!rg->live.empty()) { // chunks leave in the order they were taken: the oldest ones are the ones in the way
-        const PinRing::Chunk &c = rg->live.front();
-        if (c.off + c.bytes <= lo || c.off >= hi) break;
-        PB_CUDA(ctx, cudaEventSynchronize(c.ev));
-        rg->spare.push_back(c.ev);
-        rg->live.pop_front();
+    rg->book.ring = ring;
+    uint64_t id = 0;
+    std::vector<PbRingBook::Chunk> retire;
+    const size_t lo = rg->book.place(bytes, &id, &retire);
+    for (auto &c : retire) { // every chunk in the way must have been copied out (normally a lap ago)
+        auto ev = rg->event.find(c.id);
+        if (ev == rg->event.end()) continue;
+        PB_CUDA(ctx, cudaEventSynchronize(ev->second));
+        rg->spare.push_back(ev->second);
+        rg->event.erase(ev);
     }
     cudaEvent_t ev;
     if (!rg->spare.empty()) { ev = rg->spare.back(); rg->spare.pop_back(); }
     else PB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    rg->event[id] = ev; // from here on the chunk is accounted for whatever happens to the copy
     uint8_t *pin = static_cast<uint8_t *>(ctx->h_pin) + lo;
     memcpy(pin, src, bytes);
     cudaError_t e = cudaMemcpyAsync(dst, pin, bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaEventRecord(ev, ctx->stream);
-    if (e != cudaSuccess) {
-        rg->spare.push_back(ev);
-        return pb_fail(ctx, PB_ERR_CUDA, "staged host->device copy of %zu bytes: %s", bytes, cudaGetErrorString(e));
-    }
-    rg->live.push_back({lo, need, ev});
-    rg->head = hi;
+    if (e != cudaSuccess) return pb_fail(ctx, PB_ERR_CUDA, "staged host->device copy of %zu bytes: %s", bytes, cudaGetErrorString(e));
     return PB_OK;
 }
 
